@@ -1,0 +1,272 @@
+"""ctypes binding of the CPU oracle (oracle/libliorf_oracle.so, oracle/_ref/libliorf_ref.so).
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs import this module.  The product package (liorf_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+P4 = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("i", "<f4")])
+PRAW = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("i", "<f4"), ("ring", "<u2"), ("pad", "<u2"), ("time", "<f4")])
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libliorf_oracle.so")
+    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cpp", "liorf_oracle.hpp", "ref_nanoflann.cpp", "Makefile")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
+    if stale:
+        subprocess.run(["make", "-C", HERE, "-s"], check=True)
+    return so
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _as_p4(a):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 4)
+    return a
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_sc_create.restype = C.c_void_p
+        _lib.orc_get_transformation.argtypes = [C.c_float] * 6 + [C.c_void_p]
+    return _lib
+
+
+def ref():
+    """The reference's vendored nanoflann compiled into oracle/_ref (None if it was never built)."""
+    global _ref
+    if _ref is None:
+        build()
+        p = os.path.join(HERE, "_ref", "libliorf_ref.so")
+        if not os.path.exists(p):
+            return None
+        _ref = C.CDLL(p)
+        _ref.ref_ringkey_tree_build_seconds.restype = C.c_double
+    return _ref
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
+def get_transformation(x, y, z, roll, pitch, yaw):
+    t = np.zeros(12, np.float32)
+    lib().orc_get_transformation(x, y, z, roll, pitch, yaw, _fp(t))
+    return t.reshape(3, 4)
+
+
+def transform_cloud(pts, pose6):
+    pts = _as_p4(pts)
+    out = np.empty_like(pts)
+    pose6 = np.ascontiguousarray(pose6, np.float32)
+    lib().orc_transform_cloud(_fp(pts), C.c_int(len(pts)), _fp(pose6), _fp(out))
+    return out
+
+
+def voxel_grid(pts, leaf, want_meta=False):
+    pts = _as_p4(pts)
+    n = len(pts)
+    out = np.empty((max(n, 1), 4), np.float32)
+    mem = np.empty(max(n, 1), np.int32)
+    keys = np.empty(max(n, 1), np.int32)
+    meta = np.zeros(6, np.int32)
+    r = lib().orc_voxel_grid(_fp(pts), C.c_int(n), C.c_float(leaf), _fp(out), _fp(mem), _fp(keys), _fp(meta))
+    if r < 0:
+        res = (pts.copy(), np.arange(n, dtype=np.int32), None)
+    else:
+        res = (out[:r].copy(), mem[:n].copy(), keys[:r].copy())
+    return res + (meta,) if want_meta else res
+
+
+def knn5(map_pts, q):
+    map_pts = _as_p4(map_pts); q = _as_p4(q)
+    idx = np.empty((len(q), 5), np.int32); d2 = np.empty((len(q), 5), np.float32)
+    lib().orc_knn5(_fp(map_pts), C.c_int(len(map_pts)), _fp(q), C.c_int(len(q)), _fp(idx), _fp(d2))
+    return idx, d2
+
+
+def surf_optimization(scan, map_pts, tf6):
+    scan = _as_p4(scan); map_pts = _as_p4(map_pts); tf6 = np.ascontiguousarray(tf6, np.float32)
+    n = len(scan)
+    coeff = np.zeros((n, 4), np.float32); flag = np.zeros(n, np.uint8)
+    idx = np.empty((n, 5), np.int32); d2 = np.empty((n, 5), np.float32); plane = np.zeros((n, 4), np.float32)
+    sel = np.zeros((n, 4), np.float32)
+    lib().orc_surf_optimization(_fp(scan), C.c_int(n), _fp(map_pts), C.c_int(len(map_pts)), _fp(tf6), _fp(coeff), _fp(flag),
+                                _fp(idx), _fp(d2), _fp(plane), _fp(sel))
+    return dict(coeff=coeff, flag=flag, idx=idx, d2=d2, plane=plane, sel=sel)
+
+
+def combine(scan, coeff, flag):
+    scan = _as_p4(scan); coeff = _as_p4(coeff); flag = np.ascontiguousarray(flag, np.uint8)
+    ori = np.empty_like(scan); cs = np.empty_like(coeff)
+    k = lib().orc_combine_optimization_coeffs(_fp(scan), _fp(coeff), _fp(flag), C.c_int(len(scan)), _fp(ori), _fp(cs))
+    return ori[:k].copy(), cs[:k].copy()
+
+
+def lm_optimization(it, ori, coeff, tf6, state37=None):
+    ori = _as_p4(ori); coeff = _as_p4(coeff)
+    tf = np.array(tf6, np.float32).copy()
+    st = np.zeros(37, np.float32) if state37 is None else np.array(state37, np.float32).copy()
+    tr = np.zeros(52, np.float32)
+    c = lib().orc_lm_optimization(C.c_int(it), _fp(ori), _fp(coeff), C.c_int(len(ori)), _fp(tf), _fp(st), _fp(tr))
+    return dict(converged=bool(c), tf=tf, state=st, AtA=tr[:36].reshape(6, 6).copy(), AtB=tr[36:42].copy(), X=tr[42:48].copy(),
+                nsel=int(tr[48]), degenerate=bool(tr[50]), solved=bool(tr[51]))
+
+
+def scan2map(scan, map_pts, tf6, max_iters=30, force_all=False, state37=None, use_ref_kdtree=False):
+    scan = _as_p4(scan); map_pts = _as_p4(map_pts)
+    tf = np.array(tf6, np.float32).copy()
+    st = np.zeros(37, np.float32) if state37 is None else np.array(state37, np.float32).copy()
+    trace = np.zeros((max_iters, 6), np.float32); nsel = np.zeros(max_iters, np.int32)
+    if use_ref_kdtree:
+        tm = np.zeros(4, np.float64)
+        it = ref().ref_scan2map(_fp(scan), C.c_int(len(scan)), _fp(map_pts), C.c_int(len(map_pts)), _fp(tf), C.c_int(max_iters),
+                                C.c_int(int(force_all)), _fp(st), _fp(trace), _fp(nsel), _fp(tm))
+        return dict(iters=it, tf=tf, state=st, trace=trace[:it].copy(), nsel=nsel[:it].copy(), timings=tm)
+    it = lib().orc_scan2map(_fp(scan), C.c_int(len(scan)), _fp(map_pts), C.c_int(len(map_pts)), _fp(tf), C.c_int(max_iters),
+                            C.c_int(int(force_all)), _fp(st), _fp(trace), _fp(nsel))
+    return dict(iters=it, tf=tf, state=st, trace=trace[:it].copy(), nsel=nsel[:it].copy())
+
+
+def project_point_cloud(raw, params, time_scan_cur, imu_time, imu_rot, imu_pointer_cur, deskew_enabled=True):
+    """raw: structured PRAW array; imu_rot: (rows,3) float64; params: dict(lidarMinRange,lidarMaxRange,N_SCAN,downsampleRate,point_filter_num)."""
+    raw = np.ascontiguousarray(raw, dtype=PRAW)
+    n = len(raw)
+    out = np.empty((max(n, 1), 4), np.float32); kept = np.empty(max(n, 1), np.int32)
+    it = np.ascontiguousarray(imu_time, np.float64)
+    rot = np.ascontiguousarray(imu_rot, np.float64)
+    rx, ry, rz = (np.ascontiguousarray(rot[:, k]) for k in range(3))
+    r = lib().orc_project_point_cloud(_fp(raw), C.c_int(n), C.c_float(params["lidarMinRange"]), C.c_float(params["lidarMaxRange"]),
+                                      C.c_int(params["N_SCAN"]), C.c_int(params["downsampleRate"]), C.c_int(params["point_filter_num"]),
+                                      C.c_double(time_scan_cur), _fp(it), _fp(rx), _fp(ry), _fp(rz), C.c_int(imu_pointer_cur),
+                                      C.c_int(int(deskew_enabled)), _fp(out), _fp(kept))
+    return out[:r].copy(), kept[:r].copy()
+
+
+def sc_make(pts):
+    pts = _as_p4(pts)
+    desc = np.zeros(1200, np.float64); rk = np.zeros(20, np.float32); sk = np.zeros(60, np.float64)
+    lib().orc_sc_make(_fp(pts), C.c_int(len(pts)), _fp(desc), _fp(rk), _fp(sk))
+    return desc.reshape(20, 60), rk, sk
+
+
+def sc_keys_from_desc(desc):
+    desc = np.ascontiguousarray(desc, np.float64).reshape(-1)
+    rk = np.zeros(20, np.float32); sk = np.zeros(60, np.float64)
+    lib().orc_sc_keys_from_desc(_fp(desc), _fp(rk), _fp(sk))
+    return rk, sk
+
+
+def sc_distance(sc1, sc2):
+    sc1 = np.ascontiguousarray(sc1, np.float64).reshape(-1); sc2 = np.ascontiguousarray(sc2, np.float64).reshape(-1)
+    d = C.c_double(); s = C.c_int()
+    lib().orc_sc_distance(_fp(sc1), _fp(sc2), C.byref(d), C.byref(s))
+    return d.value, s.value
+
+
+def ringkey_top3(keys, q, use_ref=False):
+    keys = np.ascontiguousarray(keys, np.float32).reshape(-1, 20); q = np.ascontiguousarray(q, np.float32).reshape(-1, 20)
+    idx = np.zeros((len(q), 3), np.int32); d = np.zeros((len(q), 3), np.float32)
+    f = ref().ref_ringkey_knn3 if use_ref else lib().orc_ringkey_top3
+    f(_fp(keys), C.c_int(len(keys)), _fp(q), C.c_int(len(q)), _fp(idx), _fp(d))
+    return idx, d
+
+
+def kdtree_knn5(map_pts, q):
+    map_pts = _as_p4(map_pts); q = _as_p4(q)
+    idx = np.empty((len(q), 5), np.int32); d2 = np.empty((len(q), 5), np.float32)
+    ref().ref_kdtree_knn5(_fp(map_pts), C.c_int(len(map_pts)), _fp(q), C.c_int(len(q)), _fp(idx), _fp(d2))
+    return idx, d2
+
+
+def sc_query_batch(keys, descs, qkeys, qdescs):
+    keys = np.ascontiguousarray(keys, np.float32).reshape(-1, 20); descs = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+    qkeys = np.ascontiguousarray(qkeys, np.float32).reshape(-1, 20); qdescs = np.ascontiguousarray(qdescs, np.float64).reshape(-1, 1200)
+    Q = len(qkeys)
+    loop = np.zeros(Q, np.int32); shift = np.zeros(Q, np.int32); dist = np.zeros(Q, np.float64); cand = np.zeros((Q, 3), np.int32)
+    lib().orc_sc_query_batch(_fp(keys), _fp(descs), C.c_int(len(keys)), _fp(qkeys), _fp(qdescs), C.c_int(Q), _fp(loop), _fp(shift), _fp(dist), _fp(cand))
+    return loop, shift, dist, cand
+
+
+class SCManager:
+    def __init__(self):
+        self.h = C.c_void_p(lib().orc_sc_create())
+
+    def __del__(self):
+        try:
+            lib().orc_sc_destroy(self.h)
+        except Exception:
+            pass
+
+    def make_and_save(self, pts):
+        pts = _as_p4(pts)
+        lib().orc_sc_make_and_save(self.h, _fp(pts), C.c_int(len(pts)))
+
+    def save_descriptor(self, desc):
+        desc = np.ascontiguousarray(desc, np.float64).reshape(-1)
+        lib().orc_sc_save_descriptor(self.h, _fp(desc))
+
+    def size(self):
+        return lib().orc_sc_size(self.h)
+
+    def get(self, i):
+        d = np.zeros(1200, np.float64); k = np.zeros(20, np.float32)
+        lib().orc_sc_get(self.h, C.c_int(i), _fp(d), _fp(k))
+        return d.reshape(20, 60), k
+
+    def detect(self):
+        lid = C.c_int(); yaw = C.c_float(); md = C.c_double(); cand = np.zeros(3, np.int32)
+        lib().orc_sc_detect(self.h, C.byref(lid), C.byref(yaw), C.byref(md), _fp(cand))
+        return lid.value, yaw.value, md.value, cand
+
+
+def cv_qr_solve6(A, b):
+    A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)
+    x = np.zeros(6, np.float32)
+    ok = lib().orc_cv_qr_solve6(_fp(A), _fp(b), _fp(x))
+    return x, bool(ok)
+
+
+def cv_jacobi6(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(36)
+    W = np.zeros(6, np.float32); V = np.zeros(36, np.float32)
+    lib().orc_cv_jacobi6(_fp(A), _fp(W), _fp(V))
+    return W, V.reshape(6, 6)
+
+
+def cv_lu_invert6(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(36)
+    inv = np.zeros(36, np.float32)
+    ok = lib().orc_cv_lu_invert6(_fp(A), _fp(inv))
+    return inv.reshape(6, 6), bool(ok)
+
+
+def cv_gemm6(A, B):
+    A = np.ascontiguousarray(A, np.float32).reshape(36); B = np.ascontiguousarray(B, np.float32).reshape(36)
+    Cc = np.zeros(36, np.float32)
+    lib().orc_cv_gemm6(_fp(A), _fp(B), _fp(Cc))
+    return Cc.reshape(6, 6)
+
+
+def colpiv_qr_solve_5x3(A, b):
+    A = np.ascontiguousarray(A, np.float32).reshape(15); b = np.ascontiguousarray(b, np.float32).reshape(5)
+    x = np.zeros(3, np.float32)
+    lib().orc_colpiv_qr_solve_5x3(_fp(A), _fp(b), _fp(x))
+    return x
