@@ -1,0 +1,153 @@
+/* liorf_b200.h — C ABI of the B200-native scan-to-map hot path of liorf.
+ *
+ * The reference (jimmyshe/liorf) has no plugin / FFI layer: the path sits behind `void()` C++ member functions that
+ * talk through class members.  Each entry point below replaces ONE of those member-function bodies
+ * and makes the implicit member state explicit.  The file:line after "replaces" is the reference interface.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Return value 0 = success, negative = error code
+ * (never throws).  The caller owns host buffers.  The opaque context owns all device memory and ONE CUDA stream;
+ * like the reference's `mtx` (src/mapOptmization.cpp:136,252) a context is not thread-safe.
+ * Pose layout everywhere: float[6] = (roll, pitch, yaw, x, y, z) = transformTobeMapped (src/mapOptmization.cpp:134).
+ * There is NO CPU fallback: every call needs a CUDA device and fails with LIORF_ERR_CUDA otherwise.
+ */
+#ifndef LIORF_B200_H
+#define LIORF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIORF_MAX_ITERS 64
+
+typedef struct liorf_ctx liorf_ctx;
+
+/* pcl::PointXYZI payload (include/utility.h:61); device layout is the same 16 bytes */
+typedef struct { float x, y, z, intensity; } liorf_point;
+/* VelodynePointXYZIRT payload (src/imageProjection.cpp:4-15), 24 bytes */
+typedef struct { float x, y, z, intensity; uint16_t ring; uint16_t _pad; float time; } liorf_point_xyzirt;
+
+/* The ParamServer subset the path reads (include/utility.h:100-105, 227-241) */
+typedef struct {
+    int   N_SCAN;                               /* utility.h:100 */
+    int   downsampleRate;                       /* utility.h:102 */
+    int   point_filter_num;                     /* utility.h:103 */
+    float lidarMinRange, lidarMaxRange;         /* utility.h:104-105 */
+    float mappingSurfLeafSize;                  /* utility.h:227  (downsampleCurrentScan) */
+    float surroundingKeyframeMapLeafSize;       /* utility.h:240-ish (extractCloud VoxelGrid) */
+    float surroundingKeyframeSearchRadius;      /* extractCloud distance gate, src/mapOptmization.cpp:1018 */
+    int   grid_dim_x, grid_dim_y, grid_dim_z;   /* voxel-hash torus (powers of two, cell = 1 m); 0 → 256,256,32 */
+    int   device;                               /* CUDA device ordinal */
+} liorf_params;
+
+/* per-iteration record of scan2MapOptimization (poses AFTER each LMOptimization call) */
+typedef struct {
+    float pose[LIORF_MAX_ITERS][6];
+    int   nsel[LIORF_MAX_ITERS];                /* laserCloudSelNum of the iteration */
+    int   iters;                                /* iterations executed */
+    int   converged;                            /* LMOptimization returned true */
+    int   degenerate;                           /* isDegenerate after the call */
+    int   ran;                                  /* 0 when the guards of :1297/:1300 skipped the solve */
+} liorf_lm_trace;
+
+void liorf_default_params(liorf_params* p);                      /* config/kitti.yaml values */
+int  liorf_create(const liorf_params* p, liorf_ctx** out);
+void liorf_destroy(liorf_ctx* ctx);
+int  liorf_sync(liorf_ctx* ctx);                                 /* cudaStreamSynchronize + sticky device error flags */
+void* liorf_stream(liorf_ctx* ctx);                              /* the context's cudaStream_t (for CUDA-event timing) */
+const char* liorf_version(void);
+
+/* ---- imageProjection ------------------------------------------------------------------------------------------ */
+/* replaces ImageProjection::projectPointCloud() (src/imageProjection.cpp:568) incl. deskewPoint (:536) and
+ * findRotation (:493).  imu_time / imu_rot_{x,y,z} are the tables filled by imuDeskewInfo (:350-409), rows
+ * 0..imu_pointer_cur valid.  deskew_enabled = !(deskewFlag == -1 || !cloudInfo.imuAvailable) (:538).
+ * Result = fullCloud: kept on the device as the context's laserCloudSurfLast and, if out != NULL, copied to
+ * out[0..*n_out) (capacity n).  kept_index (nullable, capacity n) receives the raw index of every kept point. */
+int liorf_project_point_cloud(liorf_ctx* ctx, const liorf_point_xyzirt* pts, int n, double time_scan_cur,
+                              const double* imu_time, const double* imu_rot_x, const double* imu_rot_y, const double* imu_rot_z,
+                              int imu_pointer_cur, int deskew_enabled, liorf_point* out, int* n_out, int* kept_index);
+/* same, raw points already in device memory (bench "inputs resident in HBM"); nothing is copied back */
+int liorf_project_point_cloud_dev(liorf_ctx* ctx, const void* d_pts, int n, double time_scan_cur, const double* imu_time,
+                                  const double* imu_rot_x, const double* imu_rot_y, const double* imu_rot_z, int imu_pointer_cur,
+                                  int deskew_enabled);
+
+/* ---- mapOptimization ------------------------------------------------------------------------------------------ */
+/* sets laserCloudSurfLast from a host cloud (what pcl::fromROSMsg does at src/mapOptmization.cpp:244) */
+int liorf_set_current_scan(liorf_ctx* ctx, const liorf_point* scan, int n);
+int liorf_set_current_scan_dev(liorf_ctx* ctx, const void* d_scan, int n);
+/* replaces mapOptimization::downsampleCurrentScan() (src/mapOptmization.cpp:1061): VoxelGrid(mappingSurfLeafSize) of
+ * laserCloudSurfLast → laserCloudSurfLastDS.  out (nullable, capacity = input size), n_ds (nullable: skip the read-back).
+ * membership (nullable, capacity = input size): output slot of every input point (bit-exact voxel membership). */
+int liorf_downsample_current_scan(liorf_ctx* ctx, liorf_point* out, int* n_ds, int* membership);
+/* generic VoxelGrid on host data (same kernels; used by parity tests and the global-map filters) */
+int liorf_voxel_grid(liorf_ctx* ctx, const liorf_point* in, int n, float leaf, liorf_point* out, int* n_out, int* membership, int* out_keys);
+
+/* stores laserCloudSurfLastDS as surfCloudKeyFrames[id] with its pose / time (saveKeyFramesAndFactor, :1576-1580);
+ * returns the new keyframe id (>= 0) or a negative error */
+int liorf_add_keyframe(liorf_ctx* ctx, const float pose6[6], double time);
+/* same with an explicit host cloud (tests / map loading) */
+int liorf_add_keyframe_cloud(liorf_ctx* ctx, const liorf_point* cloud, int n, const float pose6[6], double time);
+int liorf_update_keyframe_pose(liorf_ctx* ctx, int id, const float pose6[6]);           /* correctPoses, :1611-1642 */
+int liorf_num_keyframes(liorf_ctx* ctx);
+/* replaces extractCloud (src/mapOptmization.cpp:1012-1044) for the keyframe ids chosen by extractNearby (:975-1010):
+ * transform + concatenate in selection order (duplicates allowed, as the reference), VoxelGrid
+ * (surroundingKeyframeMapLeafSize) → laserCloudSurfFromMapDS, then builds the voxel-hash grid that replaces
+ * kdtreeSurfFromMap->setInputCloud (:1302).  m_ds nullable (skip the read-back). */
+int liorf_extract_surrounding_keyframes(liorf_ctx* ctx, const int* keyframe_ids, int n_ids, int* m_ds);
+/* sets laserCloudSurfFromMapDS directly from a host cloud and builds the grid (parity tests / static maps) */
+int liorf_set_local_map(liorf_ctx* ctx, const liorf_point* map_ds, int m);
+int liorf_get_local_map(liorf_ctx* ctx, liorf_point* out, int capacity, int* m_ds);
+int liorf_get_scan_ds(liorf_ctx* ctx, liorf_point* out, int capacity, int* n_ds);
+
+/* replaces mapOptimization::scan2MapOptimization() (src/mapOptmization.cpp:1295) up to, not including, transformUpdate:
+ * ≤ max_iters × {surfOptimization, combineOptimizationCoeffs, LMOptimization} in one persistent kernel.
+ * force_all_iters != 0 disables the convergence break (benchmark).  trace nullable. */
+int liorf_scan2map_optimization(liorf_ctx* ctx, float pose6_inout[6], int max_iters, int force_all_iters, liorf_lm_trace* trace);
+/* asynchronous variant: pose stays on the device (liorf_get_pose reads it); returns right after the launch */
+int liorf_scan2map_optimization_async(liorf_ctx* ctx, const float pose6_in[6] /*nullable: keep device pose*/, int max_iters, int force_all_iters);
+int liorf_get_pose(liorf_ctx* ctx, float pose6[6], liorf_lm_trace* trace /*nullable*/);
+
+/* per-function parity hooks.
+ * surfOptimization (:1074): per point i of laserCloudSurfLastDS: coeff (coeffSelSurfVec), flag (laserCloudOriSurfFlag),
+ * nn_idx[5] = indices into laserCloudSurfFromMapDS by (distance, index) (only meaningful where the 5th distance < 1.0,
+ * else -1 fills), nn_d2[5], plane[4] = (pa,pb,pc,pd), sel = pointSel.  All nullable except coeff/flag. */
+int liorf_surf_optimization(liorf_ctx* ctx, const float pose6[6], liorf_point* coeff, uint8_t* flag, int* nn_idx, float* nn_d2,
+                            float* plane, liorf_point* sel);
+/* combineOptimizationCoeffs (:1145): compacts the result of the last liorf_surf_optimization → laserCloudOri / coeffSel */
+int liorf_combine_optimization_coeffs(liorf_ctx* ctx, liorf_point* ori /*nullable*/, liorf_point* coeff /*nullable*/, int* n_sel);
+/* LMOptimization(iterCount) (:1158) on the compacted arrays; isDegenerate / matP persist in the context.
+ * Returns 1 = converged, 0 = keep optimizing, negative = error. */
+int liorf_lm_optimization(liorf_ctx* ctx, int iter_count, float pose6_inout[6], float AtA[36], float AtB[6], float X[6], int* n_sel);
+int liorf_get_lm_state(liorf_ctx* ctx, int* is_degenerate, float matP[36]);
+int liorf_set_lm_state(liorf_ctx* ctx, int is_degenerate, const float matP[36]);
+
+/* ---- ScanContext ---------------------------------------------------------------------------------------------- */
+/* replaces SCManager::makeAndSaveScancontextAndKeys(scan) (include/Scancontext.h:72).  cloud == NULL → use the
+ * context's laserCloudSurfLast (the full deskewed cloud, as src/mapOptmization.cpp:1587-1595 passes). */
+int liorf_sc_make_and_save(liorf_ctx* ctx, const liorf_point* cloud, int n);
+/* appends ready-made descriptors (20x60 fp64 row-major [ring][sector]); keys are derived on the device (a11/a12) */
+int liorf_sc_add_descriptors(liorf_ctx* ctx, const double* descs, int count);
+int liorf_sc_size(liorf_ctx* ctx);
+int liorf_sc_get(liorf_ctx* ctx, int i, double desc[1200], float ringkey[20], double sectorkey[60]);
+/* replaces SCManager::detectLoopClosureID() (include/Scancontext.h:73) with the reference's semantics incl. the stale
+ * tree (rebuilt every 10th call over keys[0 : n-30]).  cand3 / min_dist nullable diagnostics. */
+int liorf_sc_detect_loop_closure_id(liorf_ctx* ctx, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3);
+/* batched search (BASELINE config 5): Q queries against the context's database rows [0, n_db) which represent GLOBAL
+ * rows [global_offset, global_offset + n_db) of a sharded database (single GPU: offset 0).
+ *   stage 1: local exact top-3 per query → (dist[Q*3], idx[Q*3]) in DEVICE memory (d_* pointers are device pointers)
+ *   merge  : combines n_parts gathered lists [part][Q][3] into the global top-3
+ *   stage 2: distanceBtnScanContext for owned candidates (others left untouched)
+ *   decide : strict-< argmin in kNN order + threshold */
+int liorf_sc_knn_batch_dev(liorf_ctx* ctx, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx);
+int liorf_sc_merge_top3_dev(liorf_ctx* ctx, const void* d_part_dist, const void* d_part_idx, int n_parts, int Q, void* d_dist, void* d_idx);
+int liorf_sc_prepare_queries_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, void* d_qkeys /*Q*20 f32*/, void* d_qsk /*Q*60 f64*/, void* d_qcn /*Q*60 f64*/);
+int liorf_sc_distance_batch_dev(liorf_ctx* ctx, const void* d_qdescs, const void* d_qsk, const void* d_qcn, const void* d_cand_idx, int Q,
+                                int global_offset, void* d_pair_dist /*Q*3 f64*/, void* d_pair_shift /*Q*3 i32*/);
+int liorf_sc_decide_dev(liorf_ctx* ctx, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q,
+                        void* d_loop_id, void* d_shift, void* d_dist);
+/* single-GPU convenience with host buffers: descriptors of the Q queries → loop ids / shifts / distances */
+int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

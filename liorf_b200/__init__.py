@@ -1,0 +1,9 @@
+"""liorf_b200 — B200-native (sm_100a) scan-to-map registration hot path of liorf behind a C ABI.
+
+The package holds only what the path needs: `csrc/` (CUDA kernels + the C ABI, built into `lib/libliorf_b200.so`),
+`host/` (C++ mirror of the reference's member-function interface) and this thin ctypes binding used by the tests
+and the benchmark.  There is no CPU fallback: importing works without a GPU (so the build can be checked), but every
+compute call needs the CUDA library and a device.
+"""
+from ._lib import load_library, library_path, build_library  # noqa: F401
+from .api import Context, Params, LMTrace, P4, PRAW  # noqa: F401

@@ -1,0 +1,272 @@
+"""ctypes mirror of include/liorf_b200.h.  Method names follow the reference's member functions
+(src/mapOptmization.cpp, src/imageProjection.cpp, include/Scancontext.h) so the parity tests read like the
+reference's call sequence."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import load_library
+
+MAX_ITERS = 64
+P4 = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("i", "<f4")])
+PRAW = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("i", "<f4"), ("ring", "<u2"), ("pad", "<u2"), ("time", "<f4")])
+
+
+class Params(C.Structure):
+    _fields_ = [("N_SCAN", C.c_int), ("downsampleRate", C.c_int), ("point_filter_num", C.c_int),
+                ("lidarMinRange", C.c_float), ("lidarMaxRange", C.c_float),
+                ("mappingSurfLeafSize", C.c_float), ("surroundingKeyframeMapLeafSize", C.c_float),
+                ("surroundingKeyframeSearchRadius", C.c_float),
+                ("grid_dim_x", C.c_int), ("grid_dim_y", C.c_int), ("grid_dim_z", C.c_int), ("device", C.c_int)]
+
+    @staticmethod
+    def default(**kw):
+        p = Params()
+        load_library().liorf_default_params(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        return p
+
+
+class LMTrace(C.Structure):
+    _fields_ = [("pose", (C.c_float * 6) * MAX_ITERS), ("nsel", C.c_int * MAX_ITERS), ("iters", C.c_int),
+                ("converged", C.c_int), ("degenerate", C.c_int), ("ran", C.c_int)]
+
+    def poses(self):
+        return np.array([[self.pose[i][k] for k in range(6)] for i in range(self.iters)], np.float32).reshape(-1, 6)
+
+    def nsels(self):
+        return np.array([self.nsel[i] for i in range(self.iters)], np.int32)
+
+
+class LiorfError(RuntimeError):
+    pass
+
+
+def _chk(rc, what):
+    if rc < 0:
+        raise LiorfError(f"{what} failed with code {rc}")
+    return rc
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _p4(a):
+    return np.ascontiguousarray(a, np.float32).reshape(-1, 4)
+
+
+def _pose(p):
+    return np.ascontiguousarray(p, np.float32).reshape(6).copy()
+
+
+class Context:
+    """One liorf_ctx (device memory + one CUDA stream).  Not thread-safe, like the reference's `mtx` discipline."""
+
+    def __init__(self, params=None, **kw):
+        self.lib = load_library()
+        self.params = params if params is not None else Params.default(**kw)
+        self.h = C.c_void_p()
+        _chk(self.lib.liorf_create(C.byref(self.params), C.byref(self.h)), "liorf_create")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.liorf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _chk(self.lib.liorf_sync(self.h), "liorf_sync")
+
+    def stream(self):
+        return self.lib.liorf_stream(self.h)
+
+    # ---- ImageProjection ----
+    def projectPointCloud(self, raw, time_scan_cur, imu_time=None, imu_rot=None, imu_pointer_cur=-1, deskew_enabled=True,
+                          want_output=True, want_kept_index=False):
+        raw = np.ascontiguousarray(raw, dtype=PRAW)
+        n = len(raw)
+        out = np.empty((max(n, 1), 4), np.float32) if want_output else None
+        kept = np.empty(max(n, 1), np.int32) if want_kept_index else None
+        n_out = C.c_int(0)
+        if deskew_enabled:
+            it = np.ascontiguousarray(imu_time, np.float64)
+            rot = np.ascontiguousarray(imu_rot, np.float64)
+            rx, ry, rz = (np.ascontiguousarray(rot[:, k]) for k in range(3))
+        else:
+            it = rx = ry = rz = None
+        _chk(self.lib.liorf_project_point_cloud(self.h, _vp(raw), C.c_int(n), C.c_double(time_scan_cur), _vp(it), _vp(rx), _vp(ry), _vp(rz),
+                                                C.c_int(imu_pointer_cur), C.c_int(int(bool(deskew_enabled))), _vp(out), C.byref(n_out), _vp(kept)),
+             "liorf_project_point_cloud")
+        k = n_out.value
+        res = [out[:k].copy() if want_output else None, k]
+        if want_kept_index:
+            res.append(kept[:k].copy())
+        return tuple(res)
+
+    def projectPointCloudDev(self, d_ptr, n, time_scan_cur, imu_time=None, imu_rot=None, imu_pointer_cur=-1, deskew_enabled=True):
+        if deskew_enabled:
+            it = np.ascontiguousarray(imu_time, np.float64)
+            rot = np.ascontiguousarray(imu_rot, np.float64)
+            rx, ry, rz = (np.ascontiguousarray(rot[:, k]) for k in range(3))
+        else:
+            it = rx = ry = rz = None
+        _chk(self.lib.liorf_project_point_cloud_dev(self.h, C.c_void_p(d_ptr), C.c_int(n), C.c_double(time_scan_cur), _vp(it), _vp(rx), _vp(ry), _vp(rz),
+                                                    C.c_int(imu_pointer_cur), C.c_int(int(bool(deskew_enabled)))), "liorf_project_point_cloud_dev")
+
+    # ---- mapOptimization ----
+    def setCurrentScan(self, scan):
+        scan = _p4(scan)
+        _chk(self.lib.liorf_set_current_scan(self.h, _vp(scan), C.c_int(len(scan))), "liorf_set_current_scan")
+
+    def setCurrentScanDev(self, d_ptr, n):
+        _chk(self.lib.liorf_set_current_scan_dev(self.h, C.c_void_p(d_ptr), C.c_int(n)), "liorf_set_current_scan_dev")
+
+    def downsampleCurrentScan(self, n_in=None, want_output=True, want_membership=False):
+        """VoxelGrid(mappingSurfLeafSize) of the current scan.  n_in = capacity hint for the host output buffers."""
+        if not want_output and not want_membership:
+            _chk(self.lib.liorf_downsample_current_scan(self.h, None, None, None), "liorf_downsample_current_scan")
+            return None
+        cap = max(int(n_in if n_in is not None else 0), 1)
+        out = np.empty((cap, 4), np.float32) if want_output else None
+        mem = np.empty(cap, np.int32) if want_membership else None
+        nds = C.c_int(0)
+        _chk(self.lib.liorf_downsample_current_scan(self.h, _vp(out), C.byref(nds), _vp(mem)), "liorf_downsample_current_scan")
+        res = [out[:nds.value].copy() if want_output else None, nds.value]
+        if want_membership:
+            res.append(mem[:cap].copy())
+        return tuple(res)
+
+    def voxelGrid(self, pts, leaf):
+        pts = _p4(pts)
+        n = len(pts)
+        out = np.empty((max(n, 1), 4), np.float32); mem = np.empty(max(n, 1), np.int32); keys = np.empty(max(n, 1), np.int32)
+        no = C.c_int(0)
+        _chk(self.lib.liorf_voxel_grid(self.h, _vp(pts), C.c_int(n), C.c_float(leaf), _vp(out), C.byref(no), _vp(mem), _vp(keys)), "liorf_voxel_grid")
+        return out[:no.value].copy(), mem[:n].copy(), keys[:no.value].copy()
+
+    def addKeyframe(self, pose6, time=0.0):
+        return _chk(self.lib.liorf_add_keyframe(self.h, _vp(_pose(pose6)), C.c_double(time)), "liorf_add_keyframe")
+
+    def addKeyframeCloud(self, cloud, pose6, time=0.0):
+        cloud = _p4(cloud)
+        return _chk(self.lib.liorf_add_keyframe_cloud(self.h, _vp(cloud), C.c_int(len(cloud)), _vp(_pose(pose6)), C.c_double(time)), "liorf_add_keyframe_cloud")
+
+    def updateKeyframePose(self, kid, pose6):
+        _chk(self.lib.liorf_update_keyframe_pose(self.h, C.c_int(kid), _vp(_pose(pose6))), "liorf_update_keyframe_pose")
+
+    def numKeyframes(self):
+        return self.lib.liorf_num_keyframes(self.h)
+
+    def extractSurroundingKeyFrames(self, ids, want_count=True):
+        ids = np.ascontiguousarray(ids, np.int32)
+        m = C.c_int(0)
+        _chk(self.lib.liorf_extract_surrounding_keyframes(self.h, _vp(ids), C.c_int(len(ids)), C.byref(m) if want_count else None),
+             "liorf_extract_surrounding_keyframes")
+        return m.value if want_count else None
+
+    def setLocalMap(self, map_ds):
+        map_ds = _p4(map_ds)
+        _chk(self.lib.liorf_set_local_map(self.h, _vp(map_ds), C.c_int(len(map_ds))), "liorf_set_local_map")
+
+    def getLocalMap(self):
+        m = C.c_int(0)
+        _chk(self.lib.liorf_get_local_map(self.h, None, C.c_int(0), C.byref(m)), "liorf_get_local_map")
+        out = np.empty((max(m.value, 1), 4), np.float32)
+        _chk(self.lib.liorf_get_local_map(self.h, _vp(out), C.c_int(len(out)), C.byref(m)), "liorf_get_local_map")
+        return out[:m.value].copy()
+
+    def getScanDS(self):
+        n = C.c_int(0)
+        _chk(self.lib.liorf_get_scan_ds(self.h, None, C.c_int(0), C.byref(n)), "liorf_get_scan_ds")
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _chk(self.lib.liorf_get_scan_ds(self.h, _vp(out), C.c_int(len(out)), C.byref(n)), "liorf_get_scan_ds")
+        return out[:n.value].copy()
+
+    def scan2MapOptimization(self, pose6, max_iters=30, force_all_iters=False, want_trace=True):
+        pose = _pose(pose6)
+        tr = LMTrace() if want_trace else None
+        _chk(self.lib.liorf_scan2map_optimization(self.h, _vp(pose), C.c_int(max_iters), C.c_int(int(force_all_iters)),
+                                                  C.byref(tr) if want_trace else None), "liorf_scan2map_optimization")
+        return pose, tr
+
+    def scan2MapOptimizationAsync(self, pose6=None, max_iters=30, force_all_iters=False):
+        pose = _pose(pose6) if pose6 is not None else None
+        _chk(self.lib.liorf_scan2map_optimization_async(self.h, _vp(pose), C.c_int(max_iters), C.c_int(int(force_all_iters))),
+             "liorf_scan2map_optimization_async")
+
+    def getPose(self, want_trace=False):
+        pose = np.zeros(6, np.float32)
+        tr = LMTrace() if want_trace else None
+        _chk(self.lib.liorf_get_pose(self.h, _vp(pose), C.byref(tr) if want_trace else None), "liorf_get_pose")
+        return (pose, tr) if want_trace else pose
+
+    def surfOptimization(self, pose6, n_ds):
+        n = max(int(n_ds), 1)
+        coeff = np.zeros((n, 4), np.float32); flag = np.zeros(n, np.uint8); idx = np.full((n, 5), -1, np.int32)
+        d2 = np.zeros((n, 5), np.float32); plane = np.zeros((n, 4), np.float32); sel = np.zeros((n, 4), np.float32)
+        _chk(self.lib.liorf_surf_optimization(self.h, _vp(_pose(pose6)), _vp(coeff), _vp(flag), _vp(idx), _vp(d2), _vp(plane), _vp(sel)),
+             "liorf_surf_optimization")
+        k = int(n_ds)
+        return dict(coeff=coeff[:k], flag=flag[:k], idx=idx[:k], d2=d2[:k], plane=plane[:k], sel=sel[:k])
+
+    def combineOptimizationCoeffs(self, n_ds):
+        n = max(int(n_ds), 1)
+        ori = np.zeros((n, 4), np.float32); coeff = np.zeros((n, 4), np.float32); ns = C.c_int(0)
+        _chk(self.lib.liorf_combine_optimization_coeffs(self.h, _vp(ori), _vp(coeff), C.byref(ns)), "liorf_combine_optimization_coeffs")
+        return ori[:ns.value].copy(), coeff[:ns.value].copy()
+
+    def LMOptimization(self, iter_count, pose6):
+        pose = _pose(pose6)
+        AtA = np.zeros(36, np.float32); AtB = np.zeros(6, np.float32); X = np.zeros(6, np.float32); ns = C.c_int(0)
+        rc = _chk(self.lib.liorf_lm_optimization(self.h, C.c_int(iter_count), _vp(pose), _vp(AtA), _vp(AtB), _vp(X), C.byref(ns)), "liorf_lm_optimization")
+        return dict(converged=bool(rc), tf=pose, AtA=AtA.reshape(6, 6), AtB=AtB, X=X, nsel=ns.value)
+
+    def getLMState(self):
+        deg = C.c_int(0); P = np.zeros(36, np.float32)
+        _chk(self.lib.liorf_get_lm_state(self.h, C.byref(deg), _vp(P)), "liorf_get_lm_state")
+        return bool(deg.value), P.reshape(6, 6)
+
+    def setLMState(self, deg, matP):
+        P = np.ascontiguousarray(matP, np.float32).reshape(36)
+        _chk(self.lib.liorf_set_lm_state(self.h, C.c_int(int(deg)), _vp(P)), "liorf_set_lm_state")
+
+    # ---- SCManager ----
+    def makeAndSaveScancontextAndKeys(self, cloud=None):
+        if cloud is None:
+            _chk(self.lib.liorf_sc_make_and_save(self.h, None, C.c_int(0)), "liorf_sc_make_and_save")
+        else:
+            cloud = _p4(cloud)
+            _chk(self.lib.liorf_sc_make_and_save(self.h, _vp(cloud), C.c_int(len(cloud))), "liorf_sc_make_and_save")
+
+    def scAddDescriptors(self, descs):
+        descs = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+        _chk(self.lib.liorf_sc_add_descriptors(self.h, _vp(descs), C.c_int(len(descs))), "liorf_sc_add_descriptors")
+
+    def scSize(self):
+        return self.lib.liorf_sc_size(self.h)
+
+    def scGet(self, i):
+        d = np.zeros(1200, np.float64); k = np.zeros(20, np.float32); sk = np.zeros(60, np.float64)
+        _chk(self.lib.liorf_sc_get(self.h, C.c_int(i), _vp(d), _vp(k), _vp(sk)), "liorf_sc_get")
+        return d.reshape(20, 60), k, sk
+
+    def detectLoopClosureID(self):
+        lid = C.c_int(-1); yaw = C.c_float(0); md = C.c_double(0); cand = np.zeros(3, np.int32)
+        _chk(self.lib.liorf_sc_detect_loop_closure_id(self.h, C.byref(lid), C.byref(yaw), C.byref(md), _vp(cand)), "liorf_sc_detect_loop_closure_id")
+        return lid.value, yaw.value, md.value, cand
+
+    def scQueryBatch(self, qdescs):
+        qdescs = np.ascontiguousarray(qdescs, np.float64).reshape(-1, 1200)
+        Q = len(qdescs)
+        loop = np.zeros(Q, np.int32); shift = np.zeros(Q, np.int32); dist = np.zeros(Q, np.float64); cand = np.zeros((Q, 3), np.int32)
+        _chk(self.lib.liorf_sc_query_batch(self.h, _vp(qdescs), C.c_int(Q), _vp(loop), _vp(shift), _vp(dist), _vp(cand)), "liorf_sc_query_batch")
+        return loop, shift, dist, cand

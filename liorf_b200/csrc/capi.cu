@@ -1,0 +1,742 @@
+// capi.cu — context + extern "C" entry points declared in include/liorf_b200.h.
+// One translation unit; every kernel lives in the .cuh files next to this one.  Built with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+#include "../../include/liorf_b200.h"
+#include "common.cuh"
+#include "prims.cuh"
+#include "voxelgrid.cuh"
+#include "localmap.cuh"
+#include "scan2map.cuh"
+#include "deskew.cuh"
+#include "scancontext.cuh"
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+using namespace liorf;
+
+static_assert(sizeof(S2MTrace) == sizeof(liorf_lm_trace), "trace layout mismatch");
+static_assert(sizeof(liorf_point_xyzirt) == sizeof(RawPoint), "raw point layout mismatch");
+static_assert(S2M_MAX_ITERS == LIORF_MAX_ITERS, "iteration cap mismatch");
+
+enum { C_N_SCAN = 0, C_N_DS, C_M_DS, C_NSEL, C_FIRST_KEPT, C_CONV, C_HOOK_NSEL, C_COUNT = 16 };
+
+struct Keyframe { size_t off; int count; float pose[6]; double time; };
+
+struct liorf_ctx {
+    liorf_params P;
+    cudaStream_t stream = nullptr;
+    int num_sms = kNumSMs;
+    // device scalars
+    int* d_counts = nullptr;        // C_COUNT ints
+    int* d_misc = nullptr;          // tickets / counters / error flag (zero-initialised)
+    int* d_err = nullptr;
+    int* h_mail = nullptr;          // pinned mailbox (128 KB: scalars/trace in the lower half, IMU table staging in the upper)
+    // clouds
+    DevBuf<float4> scan, scan_ds, map_raw, map_ds, kf_points;
+    DevBuf<int> membership, out_keys;
+    int n_scan_bound = 0;           // host-known upper bound of laserCloudSurfLast / DS counts
+    int h_n_scan = -1, h_n_ds = -1, h_m_ds = -1;   // host copies (-1 = unknown)
+    int m_bound = 0;
+    VoxelGridWork vg;
+    MapGrid grid;
+    DeskewWork dk;
+    std::vector<Keyframe> kfs;
+    size_t kf_used = 0;
+    DevBuf<KfSel> d_sel;
+    KfSel* h_sel = nullptr; int h_sel_cap = 0;
+    std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
+    // LM
+    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr;
+    int s2m_grid = 0;
+    DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
+    DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
+    float* d_lm_out = nullptr;      // AtA[36] AtB[6] X[6]
+    // ScanContext
+    DevBuf<double> sc_desc, sc_sk, sc_cn; DevBuf<float> sc_keys; int sc_n = 0;
+    unsigned* d_bins = nullptr;
+    int sc_tree_n = 0, sc_counter = 0;
+    DevBuf<float> sc_part_d; DevBuf<int> sc_part_i;
+    DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
+    DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
+};
+
+static void host_get_transformation(float x, float y, float z, float roll, float pitch, float yaw, float* t) {
+    // pcl::getTransformation on the host, exactly where the reference evaluates it (src/mapOptmization.cpp:317)
+    float A = std::cos(yaw), B = std::sin(yaw), C = std::cos(pitch), D = std::sin(pitch);
+    float E = std::cos(roll), F = std::sin(roll), DE = D * E, DF = D * F;
+    t[0] = A * C;  t[1] = A * DF - B * E;  t[2]  = B * F + A * DE;  t[3]  = x;
+    t[4] = B * C;  t[5] = A * E + B * DF;  t[6]  = B * DE - A * F;  t[7]  = y;
+    t[8] = -D;     t[9] = C * F;           t[10] = C * E;           t[11] = z;
+}
+
+static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-side error flag (bounded look-back spins)
+    int e = 0;
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 4000, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    e = c->h_mail[4000];
+    if (e) { fprintf(stderr, "[liorf_b200] device error flag %d (look-back predecessor never arrived)\n", e); return LIORF_ERR_DEVICE_FLAG; }
+    return LIORF_OK;
+}
+
+static int read_counts(liorf_ctx* c) {
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->h_n_scan = c->h_mail[C_N_SCAN]; c->h_n_ds = c->h_mail[C_N_DS]; c->h_m_ds = c->h_mail[C_M_DS];
+    return LIORF_OK;
+}
+
+extern "C" {
+
+const char* liorf_version(void) { return "liorf_b200 0.1 (sm_100a)"; }
+
+void liorf_default_params(liorf_params* p) {      // config/kitti.yaml
+    std::memset(p, 0, sizeof(*p));
+    p->N_SCAN = 64; p->downsampleRate = 2; p->point_filter_num = 5;
+    p->lidarMinRange = 1.0f; p->lidarMaxRange = 1000.0f;
+    p->mappingSurfLeafSize = 0.4f; p->surroundingKeyframeMapLeafSize = 0.5f; p->surroundingKeyframeSearchRadius = 50.0f;
+    p->grid_dim_x = 256; p->grid_dim_y = 256; p->grid_dim_z = 32; p->device = 0;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int liorf_create(const liorf_params* p, liorf_ctx** out) {
+    if (!p || !out) return LIORF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[liorf_b200] no CUDA device: this library has no CPU path\n");
+        return LIORF_ERR_CUDA;
+    }
+    liorf_ctx* c = new (std::nothrow) liorf_ctx();
+    if (!c) return LIORF_ERR_ARG;
+    c->P = *p;
+    if (c->P.grid_dim_x == 0) c->P.grid_dim_x = 256;
+    if (c->P.grid_dim_y == 0) c->P.grid_dim_y = 256;
+    if (c->P.grid_dim_z == 0) c->P.grid_dim_z = 32;
+    if (!is_pow2(c->P.grid_dim_x) || !is_pow2(c->P.grid_dim_y) || !is_pow2(c->P.grid_dim_z) || c->P.grid_dim_x < 4) { delete c; return LIORF_ERR_ARG; }
+    if (c->P.downsampleRate < 1 || c->P.point_filter_num < 1) { delete c; return LIORF_ERR_ARG; }
+    c->grid.dims = GridDims{c->P.grid_dim_x, c->P.grid_dim_y, c->P.grid_dim_z};
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, c->P.device));
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c->d_counts, C_COUNT * sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_counts, 0, C_COUNT * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_misc, 64 * sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_misc, 0, 64 * sizeof(int)));
+    c->d_err = c->d_misc + 0;
+    c->vg.mm_counter = c->d_misc + 1;
+    c->vg.sort.ticket = c->d_misc + 2; c->vg.sort.err_flag = c->d_err;
+    c->vg.scan.ticket = c->d_misc + 3; c->vg.scan.err_flag = c->d_err;
+    c->grid.scan.ticket = c->d_misc + 4; c->grid.scan.err_flag = c->d_err;
+    c->dk.scan.ticket = c->d_misc + 5; c->dk.scan.err_flag = c->d_err;
+    c->combine_scan.ticket = c->d_misc + 6; c->combine_scan.err_flag = c->d_err;
+    int* lm_counter = c->d_misc + 7; (void)lm_counter;
+    CUDA_TRY(cudaMalloc(&c->vg.meta, sizeof(VoxMeta)));
+    CUDA_TRY(cudaMalloc(&c->dk.start_inv, 12 * sizeof(float)));
+    c->dk.first_kept = c->d_counts + C_FIRST_KEPT;
+    CUDA_TRY(cudaHostAlloc(&c->h_mail, 131072, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc(&c->d_tf6, 6 * sizeof(float)));
+    CUDA_TRY(cudaMemset(c->d_tf6, 0, 6 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->d_lm, sizeof(LMDeviceState)));
+    CUDA_TRY(cudaMemset(c->d_lm, 0, sizeof(LMDeviceState)));
+    CUDA_TRY(cudaMalloc(&c->d_trace, sizeof(S2MTrace)));
+    CUDA_TRY(cudaMemset(c->d_trace, 0, sizeof(S2MTrace)));
+    CUDA_TRY(cudaMalloc(&c->d_lm_out, 48 * sizeof(float)));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan2map_persistent, S2M_BLOCK, 0));
+    if (occ < 1) { fprintf(stderr, "[liorf_b200] persistent kernel does not fit\n"); return LIORF_ERR_CUDA; }
+    if (occ > 4) occ = 4;
+    c->s2m_grid = c->num_sms * occ;
+    CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->s2m_grid * NPROD * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->d_bins, SC_DESC * sizeof(unsigned)));
+    {   // arm the ScanContext bins with the NO_POINT code
+        std::vector<unsigned> init(SC_DESC);
+        float f = -1000.f; unsigned u; std::memcpy(&u, &f, 4); u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        for (auto& v : init) v = u;
+        CUDA_TRY(cudaMemcpy(c->d_bins, init.data(), SC_DESC * sizeof(unsigned), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return LIORF_OK;
+}
+
+void liorf_destroy(liorf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->P.device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf<float4>* f4[] = {&c->scan, &c->scan_ds, &c->map_raw, &c->map_ds, &c->kf_points, &c->h_coeff, &c->h_sel_pts, &c->h_ori_c, &c->h_coeff_c, &c->grid.sorted};
+    for (auto b : f4) b->release();
+    c->membership.release(); c->out_keys.release(); c->h_flag.release(); c->h_idx.release(); c->h_d2.release(); c->h_plane.release();
+    c->lm_partial.release(); c->d_sel.release();
+    c->vg.partial.release(); c->vg.keys.release(); c->vg.seg_start.release();
+    c->vg.sort.keys_alt.release(); c->vg.sort.vals_a.release(); c->vg.sort.vals_b.release(); c->vg.sort.hist.release(); c->vg.sort.status.release();
+    c->vg.scan.status.release(); c->grid.scan.status.release(); c->dk.scan.status.release(); c->combine_scan.status.release();
+    c->grid.counts.release(); c->grid.cell_start.release();
+    c->dk.raw.release(); c->dk.imu.release();
+    c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); c->sc_part_d.release(); c->sc_part_i.release();
+    c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
+    c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
+    cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
+    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins);
+    if (c->h_sel) cudaFreeHost(c->h_sel);
+    cudaFreeHost(c->h_mail);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int liorf_sync(liorf_ctx* c) { if (!c) return LIORF_ERR_ARG; CUDA_TRY(cudaSetDevice(c->P.device)); return check_err(c); }
+void* liorf_stream(liorf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ imageProjection
+static int project_common(liorf_ctx* c, const RawPoint* d_raw, int n, double t0, const double* imu_time, const double* rx, const double* ry,
+                          const double* rz, int imu_ptr, int deskew_enabled, int* d_kept_index) {
+    int rc;
+    if ((rc = c->scan.reserve(n > 0 ? n : 1))) return rc;
+    c->n_scan_bound = n; c->h_n_scan = -1; c->h_n_ds = -1;
+    if (n <= 0) { CUDA_TRY(cudaMemsetAsync(c->d_counts + C_N_SCAN, 0, sizeof(int), c->stream)); c->h_n_scan = 0; return LIORF_OK; }
+    ImuTable T{nullptr, nullptr, nullptr, nullptr, 0};
+    if (deskew_enabled) {
+        if (imu_ptr < 0 || !imu_time || !rx || !ry || !rz) return LIORF_ERR_ARG;
+        const int rows = imu_ptr + 1;
+        if ((rc = c->dk.imu.reserve((size_t)4 * rows))) return rc;
+        if ((size_t)4 * rows * sizeof(double) > 65536) return LIORF_ERR_ARG;        // queueLength = 2000 rows (src/imageProjection.cpp:62) = 64000 B
+        double* stage = reinterpret_cast<double*>(c->h_mail + 16384);             // pinned staging (upper half of the mailbox)
+        CUDA_TRY(cudaStreamSynchronize(c->stream));                                // staging reuse
+        std::memcpy(stage, imu_time, rows * sizeof(double)); std::memcpy(stage + rows, rx, rows * sizeof(double));
+        std::memcpy(stage + 2 * rows, ry, rows * sizeof(double)); std::memcpy(stage + 3 * rows, rz, rows * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(c->dk.imu.p, stage, (size_t)4 * rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        T = ImuTable{c->dk.imu.p, c->dk.imu.p + rows, c->dk.imu.p + 2 * rows, c->dk.imu.p + 3 * rows, imu_ptr};
+    }
+    DeskewParams DP{c->P.lidarMinRange, c->P.lidarMaxRange, c->P.N_SCAN, c->P.downsampleRate, c->P.point_filter_num};
+    k_first_kept<<<1, 1024, 0, c->stream>>>(d_raw, n, DP, t0, T, deskew_enabled, c->dk.start_inv, c->dk.first_kept);
+    rc = launch_scan(Count::of_host(n), DeskewLoad{d_raw, DP}, DeskewStore{d_raw, t0, T, deskew_enabled, c->dk.start_inv, c->scan.p, d_kept_index},
+                     c->dk.scan, (unsigned*)(c->d_counts + C_N_SCAN), c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+
+int liorf_project_point_cloud(liorf_ctx* c, const liorf_point_xyzirt* pts, int n, double t0, const double* imu_time, const double* rx,
+                              const double* ry, const double* rz, int imu_ptr, int deskew_enabled, liorf_point* out, int* n_out, int* kept_index) {
+    if (!c || n < 0 || (n > 0 && !pts)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if ((rc = c->dk.raw.reserve(n > 0 ? n : 1))) return rc;
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(c->dk.raw.p, pts, (size_t)n * sizeof(RawPoint), cudaMemcpyHostToDevice, c->stream));
+    int* d_ki = nullptr;
+    if (kept_index) { if ((rc = c->membership.reserve(n > 0 ? n : 1))) return rc; d_ki = c->membership.p; }
+    if ((rc = project_common(c, c->dk.raw.p, n, t0, imu_time, rx, ry, rz, imu_ptr, deskew_enabled, d_ki))) return rc;
+    if ((rc = read_counts(c))) return rc;
+    if (n_out) *n_out = c->h_n_scan;
+    if (out && c->h_n_scan > 0) CUDA_TRY(cudaMemcpyAsync(out, c->scan.p, (size_t)c->h_n_scan * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (kept_index && c->h_n_scan > 0) CUDA_TRY(cudaMemcpyAsync(kept_index, d_ki, (size_t)c->h_n_scan * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return check_err(c);
+}
+
+int liorf_project_point_cloud_dev(liorf_ctx* c, const void* d_pts, int n, double t0, const double* imu_time, const double* rx, const double* ry,
+                                  const double* rz, int imu_ptr, int deskew_enabled) {
+    if (!c || n < 0 || (n > 0 && !d_pts)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    return project_common(c, (const RawPoint*)d_pts, n, t0, imu_time, rx, ry, rz, imu_ptr, deskew_enabled, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ mapOptimization
+static int set_scan_common(liorf_ctx* c, const void* src, int n, cudaMemcpyKind kind) {
+    int rc;
+    if ((rc = c->scan.reserve(n > 0 ? n : 1))) return rc;
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(c->scan.p, src, (size_t)n * sizeof(float4), kind, c->stream));
+    c->h_mail[100] = n;
+    // count goes through a kernel-visible device int
+    CUDA_TRY(cudaMemcpyAsync(c->d_counts + C_N_SCAN, &c->h_mail[100], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->n_scan_bound = n; c->h_n_scan = n; c->h_n_ds = -1;
+    return LIORF_OK;
+}
+int liorf_set_current_scan(liorf_ctx* c, const liorf_point* scan, int n) {
+    if (!c || n < 0 || (n > 0 && !scan)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    return set_scan_common(c, scan, n, cudaMemcpyHostToDevice);
+}
+int liorf_set_current_scan_dev(liorf_ctx* c, const void* d_scan, int n) {
+    if (!c || n < 0 || (n > 0 && !d_scan)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    return set_scan_common(c, d_scan, n, cudaMemcpyDeviceToDevice);
+}
+
+static int downsample_async(liorf_ctx* c, int* d_membership) {
+    int rc;
+    const int nb = c->n_scan_bound;
+    if ((rc = c->scan_ds.reserve(nb > 0 ? nb : 1))) return rc;
+    c->h_n_ds = -1;
+    Count cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, nb);
+    return voxel_grid_device(c->scan.p, cnt, c->P.mappingSurfLeafSize, c->scan_ds.p, c->d_counts + C_N_DS, d_membership, nullptr, c->vg, c->stream);
+}
+
+int liorf_downsample_current_scan(liorf_ctx* c, liorf_point* out, int* n_ds, int* membership) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    int* d_mem = nullptr;
+    if (membership) { if ((rc = c->membership.reserve(c->n_scan_bound > 0 ? c->n_scan_bound : 1))) return rc; d_mem = c->membership.p; }
+    if ((rc = downsample_async(c, d_mem))) return rc;
+    if (!out && !n_ds && !membership) return LIORF_OK;           // stay asynchronous
+    if ((rc = read_counts(c))) return rc;
+    if (n_ds) *n_ds = c->h_n_ds;
+    if (out && c->h_n_ds > 0) CUDA_TRY(cudaMemcpyAsync(out, c->scan_ds.p, (size_t)c->h_n_ds * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (membership && c->h_n_scan > 0) CUDA_TRY(cudaMemcpyAsync(membership, d_mem, (size_t)c->h_n_scan * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return check_err(c);
+}
+
+int liorf_voxel_grid(liorf_ctx* c, const liorf_point* in, int n, float leaf, liorf_point* out, int* n_out, int* membership, int* out_keys) {
+    if (!c || n < 0 || (n > 0 && !in) || !n_out) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    const int cap = n > 0 ? n : 1;
+    if ((rc = c->map_raw.reserve(cap))) return rc;       // scratch in / out (does not disturb the scan or the map)
+    DevBuf<float4> tmp_out; if ((rc = tmp_out.reserve(cap))) return rc;
+    if ((rc = c->membership.reserve(cap))) return rc;
+    if ((rc = c->out_keys.reserve(cap))) return rc;
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(c->map_raw.p, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    rc = voxel_grid_device(c->map_raw.p, Count::of_host(n), leaf, tmp_out.p, c->d_counts + C_NSEL, c->membership.p, c->out_keys.p, c->vg, c->stream);
+    if (rc) { tmp_out.release(); return rc; }
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 200, c->d_counts + C_NSEL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int no = c->h_mail[200]; *n_out = no;
+    if (out && no > 0) CUDA_TRY(cudaMemcpyAsync(out, tmp_out.p, (size_t)no * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (membership && n > 0) CUDA_TRY(cudaMemcpyAsync(membership, c->membership.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (out_keys && no > 0) CUDA_TRY(cudaMemcpyAsync(out_keys, c->out_keys.p, (size_t)no * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    rc = check_err(c);
+    tmp_out.release();
+    c->map_valid = false;                                 // map_raw scratch was reused
+    return rc;
+}
+
+static int append_keyframe(liorf_ctx* c, const float4* d_src, const float4* h_src, int n, const float pose6[6], double time) {
+    int rc;
+    if ((rc = c->kf_points.reserve(c->kf_used + (size_t)(n > 0 ? n : 1), c->stream, true))) return rc;
+    if (n > 0) {
+        if (d_src) CUDA_TRY(cudaMemcpyAsync(c->kf_points.p + c->kf_used, d_src, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        else CUDA_TRY(cudaMemcpyAsync(c->kf_points.p + c->kf_used, h_src, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    }
+    Keyframe k; k.off = c->kf_used; k.count = n; std::memcpy(k.pose, pose6, sizeof(k.pose)); k.time = time;
+    c->kfs.push_back(k); c->kf_used += (size_t)n;
+    ++c->pose_version;
+    return (int)c->kfs.size() - 1;
+}
+int liorf_add_keyframe(liorf_ctx* c, const float pose6[6], double time) {
+    if (!c || !pose6) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if (c->h_n_ds < 0 && (rc = read_counts(c))) return rc;
+    return append_keyframe(c, c->scan_ds.p, nullptr, c->h_n_ds, pose6, time);
+}
+int liorf_add_keyframe_cloud(liorf_ctx* c, const liorf_point* cloud, int n, const float pose6[6], double time) {
+    if (!c || !pose6 || n < 0 || (n > 0 && !cloud)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int id = append_keyframe(c, nullptr, (const float4*)cloud, n, pose6, time);
+    if (id >= 0) CUDA_TRY(cudaStreamSynchronize(c->stream));      // host buffer may be reused by the caller
+    return id;
+}
+int liorf_update_keyframe_pose(liorf_ctx* c, int id, const float pose6[6]) {
+    if (!c || id < 0 || id >= (int)c->kfs.size() || !pose6) return LIORF_ERR_ARG;
+    std::memcpy(c->kfs[id].pose, pose6, 6 * sizeof(float)); ++c->pose_version;
+    return LIORF_OK;
+}
+int liorf_num_keyframes(liorf_ctx* c) { return c ? (int)c->kfs.size() : LIORF_ERR_ARG; }
+
+int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids, int* m_ds) {
+    if (!c || n_ids < 0 || (n_ids > 0 && !ids)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (c->kfs.empty()) return LIORF_ERR_STATE;                  // extractSurroundingKeyFrames returns early (:1048)
+    int rc;
+    const Keyframe& last = c->kfs.back();
+    std::vector<int> sel; sel.reserve(n_ids);
+    for (int i = 0; i < n_ids; ++i) {
+        int id = ids[i];
+        if (id < 0 || id >= (int)c->kfs.size()) return LIORF_ERR_ARG;
+        const Keyframe& k = c->kfs[id];
+        float dx = k.pose[3] - last.pose[3], dy = k.pose[4] - last.pose[4], dz = k.pose[5] - last.pose[5];
+        float dist = std::sqrt(dx * dx + dy * dy + dz * dz);       // common_lib::pointDistance(p1,p2), lib/common_lib.cpp:33-37
+        if (dist > c->P.surroundingKeyframeSearchRadius) continue; // :1018
+        sel.push_back(id);
+    }
+    // the map is a pure function of (selection, poses): identical request ⇒ keep the resident map and grid
+    if (c->map_valid && sel == c->last_sel && c->last_sel_version == c->pose_version) {
+        if (m_ds) { if (c->h_m_ds < 0 && (rc = read_counts(c))) return rc; *m_ds = c->h_m_ds; }
+        return LIORF_OK;
+    }
+    const int ns = (int)sel.size();
+    if (ns > c->h_sel_cap) {
+        if (c->h_sel) cudaFreeHost(c->h_sel);
+        c->h_sel_cap = ns + 64;
+        CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
+    }
+    if ((rc = c->d_sel.reserve(ns > 0 ? ns : 1))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                  // h_sel staging reuse
+    long long total = 0;
+    for (int i = 0; i < ns; ++i) {
+        const Keyframe& k = c->kfs[sel[i]];
+        KfSel& s = c->h_sel[i];
+        s.src_off = (int)k.off; s.count = k.count; s.dst_off = (int)total; s.pad = 0;
+        host_get_transformation(k.pose[3], k.pose[4], k.pose[5], k.pose[0], k.pose[1], k.pose[2], s.t);
+        total += k.count;
+    }
+    if (total > 0x7fffffffLL) return LIORF_ERR_ARG;
+    const int tot = (int)total;
+    if ((rc = c->map_raw.reserve(tot > 0 ? tot : 1))) return rc;
+    if ((rc = c->map_ds.reserve(tot > 0 ? tot : 1))) return rc;
+    if (ns > 0) CUDA_TRY(cudaMemcpyAsync(c->d_sel.p, c->h_sel, (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, c->stream));
+    if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
+    if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_counts + C_M_DS, nullptr,
+                                nullptr, c->vg, c->stream))) return rc;
+    c->m_bound = tot; c->h_m_ds = -1;
+    if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_counts + C_M_DS, tot), c->grid, c->stream))) return rc;
+    c->last_sel = sel; c->last_sel_version = c->pose_version; c->map_valid = true;
+    if (m_ds) { if ((rc = read_counts(c))) return rc; *m_ds = c->h_m_ds; return check_err(c); }
+    return LIORF_OK;
+}
+
+int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
+    if (!c || m < 0 || (m > 0 && !map_ds)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if ((rc = c->map_ds.reserve(m > 0 ? m : 1))) return rc;
+    if (m > 0) CUDA_TRY(cudaMemcpyAsync(c->map_ds.p, map_ds, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    c->h_mail[101] = m;
+    CUDA_TRY(cudaMemcpyAsync(c->d_counts + C_M_DS, &c->h_mail[101], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->m_bound = m; c->h_m_ds = m; c->map_valid = false;
+    if ((rc = build_map_grid(c->map_ds.p, Count::of_host(m), c->grid, c->stream))) return rc;
+    return check_err(c);
+}
+int liorf_get_local_map(liorf_ctx* c, liorf_point* out, int capacity, int* m_ds) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc; if ((rc = read_counts(c))) return rc;
+    if (m_ds) *m_ds = c->h_m_ds;
+    if (out) { if (capacity < c->h_m_ds) return LIORF_ERR_ARG; if (c->h_m_ds > 0) CUDA_TRY(cudaMemcpy(out, c->map_ds.p, (size_t)c->h_m_ds * sizeof(float4), cudaMemcpyDeviceToHost)); }
+    return LIORF_OK;
+}
+int liorf_get_scan_ds(liorf_ctx* c, liorf_point* out, int capacity, int* n_ds) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc; if ((rc = read_counts(c))) return rc;
+    if (n_ds) *n_ds = c->h_n_ds;
+    if (out) { if (capacity < c->h_n_ds) return LIORF_ERR_ARG; if (c->h_n_ds > 0) CUDA_TRY(cudaMemcpy(out, c->scan_ds.p, (size_t)c->h_n_ds * sizeof(float4), cudaMemcpyDeviceToHost)); }
+    return LIORF_OK;
+}
+
+static Count scan_ds_count(liorf_ctx* c) { return c->h_n_ds >= 0 ? Count::of_host(c->h_n_ds) : Count::of_dev(c->d_counts + C_N_DS, c->n_scan_bound); }
+static Count map_count(liorf_ctx* c) { return c->h_m_ds >= 0 ? Count::of_host(c->h_m_ds) : Count::of_dev(c->d_counts + C_M_DS, c->m_bound); }
+
+static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
+    if (max_iters < 0) return LIORF_ERR_ARG;
+    if (max_iters > S2M_MAX_ITERS) max_iters = S2M_MAX_ITERS;
+    if (!c->grid.cell_start.p || !c->grid.sorted.p) {            // cloudKeyPoses3D empty → return (:1297)
+        CUDA_TRY(cudaMemsetAsync(c->d_trace, 0, sizeof(S2MTrace), c->stream));
+        return LIORF_OK;
+    }
+    S2MArgs a;
+    a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
+    a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
+    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all;
+    void* args[] = {&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2M_BLOCK), args, 0, c->stream));
+    return LIORF_OK;
+}
+
+int liorf_scan2map_optimization_async(liorf_ctx* c, const float pose6_in[6], int max_iters, int force_all) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (pose6_in) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        std::memcpy(c->h_mail + 300, pose6_in, 6 * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(c->d_tf6, c->h_mail + 300, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    return launch_s2m(c, max_iters, force_all);
+}
+int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
+    if (!c || !pose6) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 320, c->d_tf6, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (trace) CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024, c->d_trace, sizeof(S2MTrace), cudaMemcpyDeviceToHost, c->stream));
+    int rc = check_err(c); if (rc) return rc;
+    std::memcpy(pose6, c->h_mail + 320, 6 * sizeof(float));
+    if (trace) std::memcpy(trace, c->h_mail + 1024, sizeof(S2MTrace));
+    return LIORF_OK;
+}
+int liorf_scan2map_optimization(liorf_ctx* c, float pose6[6], int max_iters, int force_all, liorf_lm_trace* trace) {
+    if (!c || !pose6) return LIORF_ERR_ARG;
+    int rc = liorf_scan2map_optimization_async(c, pose6, max_iters, force_all);
+    if (rc) return rc;
+    return liorf_get_pose(c, pose6, trace);
+}
+
+int liorf_surf_optimization(liorf_ctx* c, const float pose6[6], liorf_point* coeff, uint8_t* flag, int* nn_idx, float* nn_d2, float* plane,
+                            liorf_point* sel) {
+    if (!c || !pose6 || !coeff || !flag) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if (!c->grid.cell_start.p) return LIORF_ERR_STATE;
+    if (c->h_n_ds < 0 && (rc = read_counts(c))) return rc;
+    const int n = c->h_n_ds, cap = n > 0 ? n : 1;
+    if ((rc = c->h_coeff.reserve(cap)) || (rc = c->h_flag.reserve(cap)) || (rc = c->h_idx.reserve((size_t)5 * cap)) || (rc = c->h_d2.reserve((size_t)5 * cap)) ||
+        (rc = c->h_plane.reserve((size_t)4 * cap)) || (rc = c->h_sel_pts.reserve(cap))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::memcpy(c->h_mail + 300, pose6, 6 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(c->d_tf6, c->h_mail + 300, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->hook_n = n;
+    if (n > 0) {
+        k_surf_optimization<<<(n + S2M_QPB - 1) / S2M_QPB, S2M_BLOCK, 0, c->stream>>>(c->scan_ds.p, Count::of_host(n), c->d_tf6, c->grid.cell_start.p,
+            c->grid.sorted.p, c->grid.dims, map_count(c), c->h_coeff.p, c->h_flag.p, c->h_idx.p, c->h_d2.p, c->h_plane.p, c->h_sel_pts.p);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(coeff, c->h_coeff.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(flag, c->h_flag.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        if (nn_idx) CUDA_TRY(cudaMemcpyAsync(nn_idx, c->h_idx.p, (size_t)5 * n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (nn_d2) CUDA_TRY(cudaMemcpyAsync(nn_d2, c->h_d2.p, (size_t)5 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (plane) CUDA_TRY(cudaMemcpyAsync(plane, c->h_plane.p, (size_t)4 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (sel) CUDA_TRY(cudaMemcpyAsync(sel, c->h_sel_pts.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    }
+    return check_err(c);
+}
+
+int liorf_combine_optimization_coeffs(liorf_ctx* c, liorf_point* ori, liorf_point* coeff, int* n_sel) {
+    if (!c || !n_sel) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc; const int n = c->hook_n, cap = n > 0 ? n : 1;
+    if ((rc = c->h_ori_c.reserve(cap)) || (rc = c->h_coeff_c.reserve(cap))) return rc;
+    if ((rc = launch_scan(Count::of_host(n), FlagLoad{c->h_flag.p}, CombineStore{c->scan_ds.p, c->h_coeff.p, c->h_ori_c.p, c->h_coeff_c.p}, c->combine_scan,
+                          (unsigned*)(c->d_counts + C_HOOK_NSEL), c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 400, c->d_counts + C_HOOK_NSEL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int ns = c->h_mail[400]; *n_sel = ns;
+    if (ori && ns > 0) CUDA_TRY(cudaMemcpyAsync(ori, c->h_ori_c.p, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (coeff && ns > 0) CUDA_TRY(cudaMemcpyAsync(coeff, c->h_coeff_c.p, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    return check_err(c);
+}
+
+int liorf_lm_optimization(liorf_ctx* c, int iter, float pose6[6], float AtA[36], float AtB[6], float X[6], int* n_sel) {
+    if (!c || !pose6) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc; const int nb = c->hook_n > 0 ? c->hook_n : 1;
+    int blocks = (nb + 255) / 256; if (blocks > 2 * c->num_sms) blocks = 2 * c->num_sms;
+    if ((rc = c->lm_partial.reserve((size_t)blocks * NPROD))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::memcpy(c->h_mail + 300, pose6, 6 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(c->d_tf6, c->h_mail + 300, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    k_lm_hook<<<blocks, 256, 0, c->stream>>>(iter, c->h_ori_c.p, c->h_coeff_c.p, (const unsigned*)(c->d_counts + C_HOOK_NSEL), c->d_tf6, c->d_lm,
+                                             c->lm_partial.p, c->d_misc + 7, c->d_lm_out, c->d_lm_out + 36, c->d_lm_out + 42, c->d_counts + C_NSEL,
+                                             c->d_counts + C_CONV);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 320, c->d_tf6, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 500, c->d_lm_out, 48 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 600, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = check_err(c))) return rc;
+    std::memcpy(pose6, c->h_mail + 320, 6 * sizeof(float));
+    const float* o = reinterpret_cast<const float*>(c->h_mail + 500);
+    if (AtA) std::memcpy(AtA, o, 36 * sizeof(float));
+    if (AtB) std::memcpy(AtB, o + 36, 6 * sizeof(float));
+    if (X) std::memcpy(X, o + 42, 6 * sizeof(float));
+    if (n_sel) *n_sel = c->h_mail[600 + C_NSEL];
+    return c->h_mail[600 + C_CONV] ? 1 : 0;
+}
+int liorf_get_lm_state(liorf_ctx* c, int* deg, float matP[36]) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    LMDeviceState s; CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(&s, c->d_lm, sizeof(s), cudaMemcpyDeviceToHost));
+    if (deg) *deg = s.isDegenerate; if (matP) std::memcpy(matP, s.matP, sizeof(s.matP));
+    return LIORF_OK;
+}
+int liorf_set_lm_state(liorf_ctx* c, int deg, const float matP[36]) {
+    if (!c || !matP) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    LMDeviceState s; s.isDegenerate = deg; std::memcpy(s.matP, matP, sizeof(s.matP));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(c->d_lm, &s, sizeof(s), cudaMemcpyHostToDevice));
+    return LIORF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ScanContext
+static int sc_reserve(liorf_ctx* c, int n) {
+    int rc;
+    if ((rc = c->sc_desc.reserve((size_t)n * SC_DESC, c->stream, true)) || (rc = c->sc_sk.reserve((size_t)n * SC_SECTOR, c->stream, true)) ||
+        (rc = c->sc_cn.reserve((size_t)n * SC_SECTOR, c->stream, true)) || (rc = c->sc_keys.reserve((size_t)n * SC_RING, c->stream, true))) return rc;
+    return LIORF_OK;
+}
+
+int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    const float4* d_pts; Count cnt = Count::of_host(0);
+    if (cloud) {
+        if (n < 0) return LIORF_ERR_ARG;
+        if ((rc = c->map_raw.reserve(n > 0 ? n : 1))) return rc;
+        c->map_valid = false;
+        if (n > 0) CUDA_TRY(cudaMemcpyAsync(c->map_raw.p, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        d_pts = c->map_raw.p; cnt = Count::of_host(n);
+    } else {
+        d_pts = c->scan.p; cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, c->n_scan_bound);
+    }
+    if ((rc = sc_reserve(c, c->sc_n + 1))) return rc;
+    if (cnt.bound > 0) {
+        int blocks = (cnt.bound + 256 * 8 - 1) / (256 * 8); if (blocks > c->num_sms) blocks = c->num_sms;
+        k_sc_bins<<<blocks, 256, 0, c->stream>>>(d_pts, cnt, c->d_bins);
+    }
+    const size_t e = (size_t)c->sc_n;
+    k_sc_finalize<<<1, 64, 0, c->stream>>>(c->d_bins, nullptr, c->sc_desc.p + e * SC_DESC, c->sc_keys.p + e * SC_RING, c->sc_sk.p + e * SC_SECTOR,
+                                           c->sc_cn.p + e * SC_SECTOR);
+    CUDA_TRY(cudaGetLastError());
+    ++c->sc_n;
+    if (cloud) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LIORF_OK;
+}
+
+int liorf_sc_add_descriptors(liorf_ctx* c, const double* descs, int count) {
+    if (!c || count < 0 || (count > 0 && !descs)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if (count == 0) return LIORF_OK;
+    if ((rc = sc_reserve(c, c->sc_n + count))) return rc;
+    const size_t e = (size_t)c->sc_n;
+    CUDA_TRY(cudaMemcpyAsync(c->sc_desc.p + e * SC_DESC, descs, (size_t)count * SC_DESC * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_sc_keys_batch<<<count, 64, 0, c->stream>>>(c->sc_desc.p + e * SC_DESC, count, c->sc_keys.p + e * SC_RING, c->sc_sk.p + e * SC_SECTOR,
+                                                 c->sc_cn.p + e * SC_SECTOR);
+    CUDA_TRY(cudaGetLastError());
+    c->sc_n += count;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LIORF_OK;
+}
+int liorf_sc_size(liorf_ctx* c) { return c ? c->sc_n : LIORF_ERR_ARG; }
+int liorf_sc_get(liorf_ctx* c, int i, double desc[1200], float ringkey[20], double sectorkey[60]) {
+    if (!c || i < 0 || i >= c->sc_n) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (desc) CUDA_TRY(cudaMemcpy(desc, c->sc_desc.p + (size_t)i * SC_DESC, SC_DESC * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ringkey) CUDA_TRY(cudaMemcpy(ringkey, c->sc_keys.p + (size_t)i * SC_RING, SC_RING * sizeof(float), cudaMemcpyDeviceToHost));
+    if (sectorkey) CUDA_TRY(cudaMemcpy(sectorkey, c->sc_sk.p + (size_t)i * SC_SECTOR, SC_SECTOR * sizeof(double), cudaMemcpyDeviceToHost));
+    return LIORF_OK;
+}
+
+// local exact top-3 of Q queries over keys[0:n_keys) → d_dist/d_idx [Q][3]; unfilled slots: dist +inf, idx INT_MAX
+static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
+    int rc;
+    if (Q <= 0) return LIORF_OK;
+    const int bx = (Q + SCK_BLOCK - 1) / SCK_BLOCK;
+    int max_chunks = (n_keys + SCK_TILE - 1) / SCK_TILE; if (max_chunks < 1) max_chunks = 1;
+    int chunks = (4 * c->num_sms + bx - 1) / bx; if (chunks > max_chunks) chunks = max_chunks; if (chunks < 1) chunks = 1;
+    int kpc = (n_keys + chunks - 1) / chunks; kpc = ((kpc + SCK_TILE - 1) / SCK_TILE) * SCK_TILE; if (kpc < SCK_TILE) kpc = SCK_TILE;
+    chunks = (n_keys + kpc - 1) / kpc; if (chunks < 1) chunks = 1;
+    if ((rc = c->sc_part_d.reserve((size_t)chunks * Q * 3)) || (rc = c->sc_part_i.reserve((size_t)chunks * Q * 3))) return rc;
+    k_sc_knn_tile<<<dim3(bx, chunks), SCK_BLOCK, 0, c->stream>>>(d_keys, n_keys, global_offset, d_qkeys, Q, kpc, c->sc_part_d.p, c->sc_part_i.p);
+    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sc_part_d.p, c->sc_part_i.p, chunks, Q, d_dist, d_idx);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+
+int liorf_sc_knn_batch_dev(liorf_ctx* c, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx) {
+    if (!c || Q < 0 || !d_qkeys || !d_dist || !d_idx) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    return sc_knn(c, c->sc_keys.p, c->sc_n, (const float*)d_qkeys, Q, global_offset, (float*)d_dist, (int*)d_idx);
+}
+int liorf_sc_merge_top3_dev(liorf_ctx* c, const void* d_part_dist, const void* d_part_idx, int n_parts, int Q, void* d_dist, void* d_idx) {
+    if (!c || Q < 0 || n_parts < 1) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>((const float*)d_part_dist, (const int*)d_part_idx, n_parts, Q, (float*)d_dist, (int*)d_idx);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+int liorf_sc_prepare_queries_dev(liorf_ctx* c, const void* d_qdescs, int Q, void* d_qkeys, void* d_qsk, void* d_qcn) {
+    if (!c || Q < 0 || !d_qdescs || !d_qsk || !d_qcn) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    k_sc_keys_batch<<<Q, 64, 0, c->stream>>>((const double*)d_qdescs, Q, (float*)d_qkeys, (double*)d_qsk, (double*)d_qcn);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+int liorf_sc_distance_batch_dev(liorf_ctx* c, const void* d_qdescs, const void* d_qsk, const void* d_qcn, const void* d_cand_idx, int Q, int global_offset,
+                                void* d_pair_dist, void* d_pair_shift) {
+    if (!c || Q < 0) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    const int pairs = Q * SC_NUM_CAND;
+    k_sc_distance<<<(pairs + SCD_WARPS - 1) / SCD_WARPS, SCD_WARPS * 32, 0, c->stream>>>((const double*)d_qdescs, (const double*)d_qsk, (const double*)d_qcn,
+        (const int*)d_cand_idx, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n, (double*)d_pair_dist, (int*)d_pair_shift);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q, void* d_loop_id, void* d_shift,
+                        void* d_dist) {
+    if (!c || Q < 0) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    k_sc_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>((const double*)d_pair_dist, (const int*)d_pair_shift, (const int*)d_cand_idx, Q, (int*)d_loop_id,
+                                                         (int*)d_shift, (double*)d_dist);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+
+static int sc_reserve_query(liorf_ctx* c, int Q) {
+    int rc;
+    if ((rc = c->sc_q_d.reserve((size_t)3 * Q)) || (rc = c->sc_q_i.reserve((size_t)3 * Q)) || (rc = c->sc_pair_d.reserve((size_t)3 * Q)) ||
+        (rc = c->sc_pair_s.reserve((size_t)3 * Q)) || (rc = c->sc_res_i.reserve((size_t)2 * Q)) || (rc = c->sc_res_d.reserve(Q))) return rc;
+    return LIORF_OK;
+}
+
+int liorf_sc_query_batch(liorf_ctx* c, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3) {
+    if (!c || Q < 0 || (Q > 0 && (!qdescs || !loop_id || !shift || !dist))) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    if (c->sc_n < 1) return LIORF_ERR_STATE;
+    int rc;
+    if ((rc = c->sc_qdesc.reserve((size_t)Q * SC_DESC)) || (rc = c->sc_qsk.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qcn.reserve((size_t)Q * SC_SECTOR)) ||
+        (rc = c->sc_qkeys.reserve((size_t)Q * SC_RING)) || (rc = sc_reserve_query(c, Q))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->sc_qdesc.p, qdescs, (size_t)Q * SC_DESC * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = liorf_sc_prepare_queries_dev(c, c->sc_qdesc.p, Q, c->sc_qkeys.p, c->sc_qsk.p, c->sc_qcn.p))) return rc;
+    if ((rc = sc_knn(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, 0, c->sc_q_d.p, c->sc_q_i.p))) return rc;
+    if ((rc = liorf_sc_distance_batch_dev(c, c->sc_qdesc.p, c->sc_qsk.p, c->sc_qcn.p, c->sc_q_i.p, Q, 0, c->sc_pair_d.p, c->sc_pair_s.p))) return rc;
+    if ((rc = liorf_sc_decide_dev(c, c->sc_pair_d.p, c->sc_pair_s.p, c->sc_q_i.p, Q, c->sc_res_i.p, c->sc_res_i.p + Q, c->sc_res_d.p))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(loop_id, c->sc_res_i.p, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(shift, c->sc_res_i.p + Q, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist, c->sc_res_d.p, (size_t)Q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (cand3) CUDA_TRY(cudaMemcpyAsync(cand3, c->sc_q_i.p, (size_t)3 * Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return check_err(c);
+}
+
+int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3) {
+    if (!c || !loop_id || !yaw_diff_rad) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    *loop_id = -1; *yaw_diff_rad = 0.f;
+    if (c->sc_n < SC_EXCLUDE_RECENT + 1) return LIORF_OK;                       // :263-267
+    if (c->sc_counter % SC_TREE_PERIOD == 0) c->sc_tree_n = c->sc_n - SC_EXCLUDE_RECENT;   // :270-281 (tree snapshot = keys[0 : n-30])
+    c->sc_counter = c->sc_counter + 1;
+    int rc;
+    if ((rc = sc_reserve_query(c, 1))) return rc;
+    const size_t qe = (size_t)c->sc_n - 1;                                       // query = last entry (:257-258)
+    if ((rc = sc_knn(c, c->sc_keys.p, c->sc_tree_n, c->sc_keys.p + qe * SC_RING, 1, 0, c->sc_q_d.p, c->sc_q_i.p))) return rc;
+    // result slots are zero-initialised in the reference (:289-290): an unfilled slot means candidate 0
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 700, c->sc_q_i.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int cand[3]; for (int j = 0; j < 3; ++j) { cand[j] = c->h_mail[700 + j]; if (cand[j] == 0x7fffffff) cand[j] = 0; c->h_mail[704 + j] = cand[j]; }
+    CUDA_TRY(cudaMemcpyAsync(c->sc_q_i.p, c->h_mail + 704, 3 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_sc_distance<<<1, SCD_WARPS * 32, 0, c->stream>>>(c->sc_desc.p + qe * SC_DESC, c->sc_sk.p + qe * SC_SECTOR, c->sc_cn.p + qe * SC_SECTOR, c->sc_q_i.p, 3, 3,
+                                                       c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, 0, c->sc_n, c->sc_pair_d.p, c->sc_pair_s.p);
+    k_sc_decide<<<1, 128, 0, c->stream>>>(c->sc_pair_d.p, c->sc_pair_s.p, c->sc_q_i.p, 1, c->sc_res_i.p, c->sc_res_i.p + 1, c->sc_res_d.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 710, c->sc_res_i.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 720, c->sc_res_d.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = check_err(c))) return rc;
+    *loop_id = c->h_mail[710];
+    const int nn_align = c->h_mail[711];
+    double md; std::memcpy(&md, c->h_mail + 720, sizeof(double));
+    if (min_dist) *min_dist = md;
+    if (cand3) { cand3[0] = cand[0]; cand3[1] = cand[1]; cand3[2] = cand[2]; }
+    *yaw_diff_rad = (float)((float)(nn_align * (360.0 / 60.0)) * M_PI / 180.0);   // deg2rad(float) (:17-20, :339)
+    return LIORF_OK;
+}
+
+}  // extern "C"
