@@ -113,8 +113,9 @@ def test_surf_optimization_plane_and_coeff(ctx, oracle, kitti_case):
     tf = kitti_case["init"]
     g = ctx.surfOptimization(tf, len(ds))
     o = oracle.surf_optimization(ds, o_map, tf)
-    same_nn = np.all(g["idx"] == o["idx"], axis=1) & (o["d2"][:, 4] < 1.0)
-    assert same_nn.mean() > 0.95
+    valid = o["d2"][:, 4] < 1.0
+    same_nn = np.all(g["idx"] == o["idx"], axis=1) & valid
+    assert same_nn.sum() > 0.99 * valid.sum()                    # pointSel differs by ulps (device vs host trig): rare near-tie flips
     # same neighbours ⇒ same 5x3 QR arithmetic ⇒ planes bit-exact
     assert np.array_equal(g["plane"][same_nn], o["plane"][same_nn])
     agree = g["flag"][same_nn] == o["flag"][same_nn]
