@@ -1,0 +1,581 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the liorf scan-to-map hot path on B200.
+
+Workload (BASELINE.json configs[1], `kitti05_seq`): a synthetic 64-beam (HDL-64 shaped, ~119k returns/scan) driving
+sequence; one STEP = one LiDAR frame through the whole path
+    projectPointCloud (deskew) → downsampleCurrentScan → extractSurroundingKeyFrames (extractNearby selection +
+    extractCloud + voxel-hash grid) → scan2MapOptimization (≤30 LM iterations, early exit as the reference) →
+    saveFrame gate → keyframe store + ScanContext make, detectLoopClosureID every 10th frame.
+`value`  : ms/frame with the raw scans already resident in HBM, timed with CUDA events on the library's stream.
+`e2e`    : the same metric through the C ABI with HOST (pinned) raw scans: H2D of every scan and D2H of the pose inside
+           the timed region.
+Extra keys: `single_frame` (config 1: downsample + grid + 30 forced LM iterations against the local map — the "<1 ms"
+target), `knn_queries_per_s`, `sc` (config 5: ScanContext queries/s over a K-entry database sharded over the ranks,
+NCCL all-gather of the top-3 candidates), `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`.
+
+`--impl reference` times the CPU path (oracle restatement + the reference's vendored nanoflann from oracle/_ref) on
+the same frames, bounded sample, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T0 = 1000.0
+DT = 0.1
+KITTI = dict(lidarMinRange=1.0, lidarMaxRange=1000.0, N_SCAN=64, downsampleRate=2, point_filter_num=5)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# small SE(3) helpers (float64, host): initial guesses stand in for the IMU-preintegration output
+# ----------------------------------------------------------------------------------------------------------------
+def pose_to_T(p):
+    r, pi_, y = p[0], p[1], p[2]
+    A, B, C, D, E, F = np.cos(y), np.sin(y), np.cos(pi_), np.sin(pi_), np.cos(r), np.sin(r)
+    T = np.eye(4)
+    T[:3, :3] = [[A * C, A * D * F - B * E, B * F + A * D * E], [B * C, A * E + B * D * F, B * D * E - A * F], [-D, C * F, C * E]]
+    T[:3, 3] = p[3:6]
+    return T
+
+
+def T_to_pose(T):
+    return np.array([np.arctan2(T[2, 1], T[2, 2]), np.arcsin(-T[2, 0]), np.arctan2(T[1, 0], T[0, 0]), T[0, 3], T[1, 3], T[2, 3]])
+
+
+class Sequence:
+    """Seeded synthetic drive: poses, per-frame gyro tables and raw scans (generated lazily, cached)."""
+
+    def __init__(self, n_frames, rank=0, filters=KITTI):
+        from tools import synth
+        self.synth = synth
+        self.n = n_frames
+        self.filters = filters
+        self.poses = synth.street_trajectory(n_frames + 1, start=(0.0, 160.0 * rank), seed=synth.SEED0 + 1 + rank)
+        self.rank = rank
+        self.raw = {}
+        self.imu = {}
+        rng = np.random.default_rng(synth.SEED0 + 77 + rank)
+        self.guess_noise = np.concatenate([rng.normal(scale=np.deg2rad(0.1), size=(n_frames, 3)), rng.normal(scale=0.02, size=(n_frames, 3))], axis=1)
+
+    def frame(self, i):
+        if i not in self.raw:
+            p = self.poses[i]
+            omega = (self.poses[i + 1][:3] - p[:3]) / DT
+            raw = self.synth.scan(self.synth.HDL64, p, omega=omega, vel=(0, 0, 0), seed=self.synth.SEED0 + 1000 * self.rank + i)
+            t0 = T0 + DT * i
+            it, rot, ptr = self.synth.imu_table(t0, t0 + float(raw["time"][-1]), omega, rate_hz=100.0, gyro_noise=1.56e-3, seed=i)
+            self.raw[i] = raw
+            self.imu[i] = (t0, it, rot, ptr)
+        return self.raw[i], self.imu[i]
+
+    def initial_guess(self, i, prev_est):
+        """previous optimised pose ∘ true increment, perturbed by N(0, 0.1 deg / 2 cm)."""
+        if i == 0 or prev_est is None:
+            return self.poses[0].astype(np.float32)
+        inc = np.linalg.inv(pose_to_T(self.poses[i - 1])) @ pose_to_T(self.poses[i])
+        g = T_to_pose(pose_to_T(np.asarray(prev_est, np.float64)) @ inc) + self.guess_noise[i]
+        return g.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# one frame through the GPU library (the call sequence of cloudHandler + laserCloudInfoHandler)
+# ----------------------------------------------------------------------------------------------------------------
+class GpuPipeline:
+    def __init__(self, seq, device):
+        import liorf_b200
+        self.ctx = liorf_b200.Context(device=device, **{k: seq.filters[k] for k in ("N_SCAN", "downsampleRate", "point_filter_num", "lidarMinRange", "lidarMaxRange")})
+        self.seq = seq
+        self.prev = None
+        self.stats = dict(frames=0, iters=0, knn_queries=0, alg_bytes_s2m=0, keyframes=0, n_ds=0, m_ds=0, loops=0)
+        self.dev_raw = {}
+        self.pin_raw = {}
+
+    def stage(self, frames):
+        """raw scans → HBM (device arm) and pinned host memory (e2e arm), outside any timed region."""
+        import torch
+        for i in frames:
+            raw, _ = self.seq.frame(i)
+            if i not in self.dev_raw:
+                t = torch.from_numpy(raw.view(np.uint8).reshape(-1).copy())
+                self.pin_raw[i] = t.pin_memory()
+                self.dev_raw[i] = self.pin_raw[i].to(f"cuda:{self.ctx.params.device}")
+        torch.cuda.synchronize()
+
+    def step(self, i, mode):
+        ctx, seq = self.ctx, self.seq
+        raw, (t0, it, rot, ptr) = seq.frame(i)
+        if mode == "dev":
+            ctx.projectPointCloudDev(self.dev_raw[i].data_ptr(), len(raw), t0, it, rot, ptr, True)
+        else:                                                    # e2e: HOST buffer through the reference-facing call
+            pin = self.pin_raw[i].numpy().view(raw.dtype)
+            ctx.projectPointCloud(pin, t0, it, rot, ptr, True, want_output=False)
+        ctx.downsampleCurrentScan(want_output=False)
+        guess = seq.initial_guess(i, self.prev)
+        if ctx.numKeyframes() > 0:
+            ids = ctx.extractNearby(t0, 2.0)
+            ctx.extractSurroundingKeyFrames(ids, want_count=False)
+        ctx.scan2MapOptimizationAsync(guess, 30, False)
+        pose = ctx.getPose()                                      # D2H of the step's result (pose + counts)
+        c = ctx.lastCounts()
+        st = self.stats
+        st["frames"] += 1; st["iters"] += c["iters"]; st["knn_queries"] += c["iters"] * max(c["n_ds"], 0)
+        st["alg_bytes_s2m"] += 96 * c["iters"] * max(c["n_ds"], 0); st["n_ds"] += max(c["n_ds"], 0); st["m_ds"] += max(c["m_ds"], 0)
+        if ctx.saveFrame(pose, 1.0, 0.2):
+            ctx.addKeyframe(pose, t0)
+            ctx.makeAndSaveScancontextAndKeys()
+            st["keyframes"] += 1
+        if i % 10 == 9:
+            st["loops"] += ctx.detectLoopClosureID()[0] >= 0
+        self.prev = pose
+        return pose
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the CPU path (oracle + the reference's nanoflann) on the same frames — cpu_baseline and --impl reference
+# ----------------------------------------------------------------------------------------------------------------
+class CpuPipeline:
+    def __init__(self, seq):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        self.o = pyoracle
+        self.seq = seq
+        self.kf_clouds, self.kf_poses, self.kf_times = [], [], []
+        self.prev = None
+        self.state = np.zeros(37, np.float32)
+        self.sc = pyoracle.SCManager()
+        self.use_ref = pyoracle.ref() is not None
+        self.split = dict(deskew=0.0, downsample=0.0, map_build=0.0, scan2map=0.0, sc=0.0)
+
+    def seed_keyframes(self, clouds, poses, times):
+        self.kf_clouds, self.kf_poses, self.kf_times = list(clouds), [np.asarray(p, np.float32) for p in poses], list(times)
+
+    def extract_nearby(self, t_cur, radius=50.0, density=2.0):
+        P = np.array(self.kf_poses, np.float32)[:, 3:6]
+        d = ((P[-1] - P) ** 2).astype(np.float32).sum(1)
+        near = np.lexsort((np.arange(len(P)), d))
+        near = near[d[near] < radius * radius]
+        ids = []
+        if len(near):
+            pts = np.concatenate([P[near], np.zeros((len(near), 1), np.float32)], 1)
+            cent, _, _ = self.o.voxel_grid(pts, density)
+            for c in cent:
+                ids.append(int(np.argmin(((c[:3] - P) ** 2).sum(1))))
+        for i in range(len(P) - 1, -1, -1):
+            if t_cur - self.kf_times[i] < 10.0:
+                ids.append(i)
+            else:
+                break
+        last = P[-1]
+        return [i for i in ids if np.sqrt(((P[i] - last) ** 2).sum()) <= radius]
+
+    def step(self, i):
+        o, seq = self.o, self.seq
+        raw, (t0, it, rot, ptr) = seq.frame(i)
+        a = time.perf_counter()
+        cloud, _ = o.project_point_cloud(raw, seq.filters, t0, it, rot, ptr, True)
+        b = time.perf_counter()
+        ds, _, _ = o.voxel_grid(cloud, 0.4)
+        c = time.perf_counter()
+        guess = seq.initial_guess(i, self.prev)
+        pose = guess.copy()
+        d = c
+        if self.kf_clouds:
+            ids = self.extract_nearby(t0)
+            mraw = np.concatenate([o.transform_cloud(self.kf_clouds[k], self.kf_poses[k]) for k in ids], 0)
+            mds, _, _ = o.voxel_grid(mraw, 0.5)
+            d = time.perf_counter()
+            r = o.scan2map(ds, mds, guess, 30, False, self.state, use_ref_kdtree=self.use_ref)
+            pose, self.state = r["tf"], r["state"]
+        e = time.perf_counter()
+        last = self.kf_poses[-1] if self.kf_poses else None
+        make = last is None
+        if last is not None:
+            Tb = np.linalg.inv(pose_to_T(last.astype(np.float64))) @ pose_to_T(pose.astype(np.float64))
+            pb = T_to_pose(Tb)
+            make = not (abs(pb[0]) < 0.2 and abs(pb[1]) < 0.2 and abs(pb[2]) < 0.2 and np.linalg.norm(pb[3:]) < 1.0)
+        if make:
+            self.kf_clouds.append(ds); self.kf_poses.append(pose.copy()); self.kf_times.append(t0)
+            self.sc.make_and_save(cloud)
+        if i % 10 == 9:
+            self.sc.detect()
+        f = time.perf_counter()
+        s = self.split
+        s["deskew"] += b - a; s["downsample"] += c - b; s["map_build"] += d - c; s["scan2map"] += e - d; s["sc"] += f - e
+        self.prev = pose
+        return pose
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), "fallback"
+
+
+def dist_env():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), ws
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def bench_sc(ctx_device, rank, world, K, Q, reps, dist):
+    """config 5: K-entry database sharded by contiguous ranges over the ranks; Q replicated queries per step."""
+    import torch
+    import liorf_b200
+    from tools import synth
+    kloc = K // world
+    off = rank * kloc
+    ctx = liorf_b200.Context(device=ctx_device)
+    CH = 10000
+    for s in range(0, kloc, CH):
+        ctx.scAddDescriptors(synth.sc_descriptors(min(CH, kloc - s), first=off + s))
+    # queries come from a small replicated sample of the global database (identical on every rank)
+    sample = synth.sc_descriptors(min(K, 2000), first=0)
+    qd, src, shift = synth.sc_queries(sample, Q)
+    dev = torch.device(f"cuda:{ctx_device}")
+    import ctypes as C
+    lib = ctx.lib
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    with torch.cuda.stream(ext):
+        d_q = torch.from_numpy(qd).to(dev)
+        qkeys = torch.empty((Q, 20), dtype=torch.float32, device=dev); qsk = torch.empty((Q, 60), dtype=torch.float64, device=dev); qcn = torch.empty_like(qsk)
+        ld = torch.empty((Q, 3), dtype=torch.float32, device=dev); li = torch.empty((Q, 3), dtype=torch.int32, device=dev)
+        gd = torch.empty((world, Q, 3), dtype=torch.float32, device=dev); gi = torch.empty((world, Q, 3), dtype=torch.int32, device=dev)
+        md = torch.empty_like(ld); mi = torch.empty_like(li)
+        pd = torch.empty((Q, 3), dtype=torch.float64, device=dev); ps = torch.empty((Q, 3), dtype=torch.int32, device=dev)
+        gpd = torch.empty((world, Q, 3), dtype=torch.float64, device=dev); gps = torch.empty((world, Q, 3), dtype=torch.int32, device=dev)
+        loop = torch.empty(Q, dtype=torch.int32, device=dev); sh = torch.empty(Q, dtype=torch.int32, device=dev); dd = torch.empty(Q, dtype=torch.float64, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+
+    def one():
+        with torch.cuda.stream(ext):
+            lib.liorf_sc_prepare_queries_dev(ctx.h, vp(d_q), Q, vp(qkeys), vp(qsk), vp(qcn))
+            lib.liorf_sc_knn_batch_dev(ctx.h, vp(qkeys), Q, off, vp(ld), vp(li))
+            if world > 1:
+                dist.all_gather_into_tensor(gd, ld); dist.all_gather_into_tensor(gi, li)
+                lib.liorf_sc_merge_top3_dev(ctx.h, vp(gd), vp(gi), world, Q, vp(md), vp(mi))
+                cand = mi
+            else:
+                cand = li
+            pd.fill_(float("inf")); ps.zero_()
+            lib.liorf_sc_distance_batch_dev(ctx.h, vp(d_q), vp(qsk), vp(qcn), vp(cand), Q, off, vp(pd), vp(ps))
+            if world > 1:                                           # owner-computes: every pair is finite on exactly one rank
+                dist.all_gather_into_tensor(gpd, pd); dist.all_gather_into_tensor(gps, ps)
+                best = gpd.argmin(dim=0, keepdim=True)
+                pd2 = gpd.gather(0, best)[0]; ps2 = gps.gather(0, best)[0]
+            else:
+                pd2, ps2 = pd, ps
+            lib.liorf_sc_decide_dev(ctx.h, vp(pd2.contiguous()), vp(ps2.contiguous()), vp(cand), Q, vp(loop), vp(sh), vp(dd))
+    for _ in range(3):
+        one()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(reps):
+        one()
+    with torch.cuda.stream(ext):
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    found = int(((loop.cpu().numpy() == src) & (src >= 0)).sum()) if K <= 2000 * world or True else 0
+    res = dict(K=K, Q=Q, shards=world, ms_per_batch=ms / reps, queries_per_s=Q * reps / (ms * 1e-3),
+               planted_loops_found=int(((loop.cpu().numpy() == src) & (src >= 0)).sum()), planted=int((src >= 0).sum()))
+    ctx.close()
+    return res, (qd, sample)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=150)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preroll", type=int, default=100, help="untimed frames that build the ~50-keyframe local map first")
+    ap.add_argument("--sc-k", type=int, default=100000)
+    ap.add_argument("--sc-q", type=int, default=4096)
+    ap.add_argument("--no-sc", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=12, help="bounded CPU-baseline sample (frames)")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return run_reference(args, W, K)
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    P = args.preroll
+    n_frames = P + W + K
+    seq = Sequence(n_frames, rank)
+    for i in range(n_frames):                                   # synthesise everything up front (not timed)
+        seq.frame(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    results = {}
+    sampler = ClockSampler(local_rank)
+    for mode in ("e2e", "dev"):
+        pipe = GpuPipeline(seq, local_rank)
+        pipe.stage(range(n_frames))
+        for i in range(P):
+            pipe.step(i, "dev")
+        for i in range(P, P + W):
+            pipe.step(i, mode)
+        pipe.stats = {k: 0 for k in pipe.stats}
+        pipe.ctx.enableTiming(True)
+        launches0 = pipe.ctx.launchCount()
+        ext = torch.cuda.ExternalStream(pipe.ctx.stream(), device=dev)
+        barrier()
+        if mode == "dev":
+            sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        with torch.cuda.stream(ext):
+            e0.record()
+        for i in range(P + W, P + W + K):
+            pipe.step(i, mode)
+        with torch.cuda.stream(ext):
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = e0.elapsed_time(e1)
+        if mode == "dev":
+            clocks = sampler.stop()
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        results[mode] = dict(ms=ms, wall_ms=wall * 1e3, stats=dict(pipe.stats), timing=pipe.ctx.getTiming(), launches=pipe.ctx.launchCount() - launches0,
+                             h2d=int(np.mean([seq.raw[i].nbytes for i in range(P + W, P + W + K)])) + 4 * 8 * 16 + 24)
+        if mode == "dev":
+            keep = pipe
+        else:
+            pipe.ctx.close()
+
+    # ---- config 1: single-frame solve (downsample + grid build + 30 forced LM iterations) on the resident map ----
+    pipe = keep
+    ctx = pipe.ctx
+    i_last = P + W + K - 1
+    raw, (t0, it, rot, ptr) = seq.frame(i_last)
+    xyz = np.stack([raw["x"], raw["y"], raw["z"], raw["i"]], 1).astype(np.float32)      # filters off: all ~119k returns (BASELINE wording)
+    ids = ctx.extractNearby(t0, 2.0)
+    guess = (pipe.prev + np.array([np.deg2rad(0.5), np.deg2rad(0.3), np.deg2rad(1.5), 0.35, 0.1, 0.02], np.float32)).astype(np.float32)
+    d_xyz = torch.from_numpy(xyz).to(dev)
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    single = []
+    ctx.enableTiming(True)
+    kf0_pose = ctx.getKeyframe(0)[1]
+    for rep in range(3 + 10):
+        ctx.updateKeyframePose(0, kf0_pose)                       # invalidates the map cache → the map + grid are rebuilt every repetition
+        ctx.setCurrentScanDev(d_xyz.data_ptr(), len(xyz))
+        with torch.cuda.stream(ext):
+            flush.zero_()                                         # L2 flush between timed iterations (256 MB > 126 MB L2)
+        ctx.sync()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True); c = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            a.record()
+        ctx.extractSurroundingKeyFrames(ids, want_count=False)
+        with torch.cuda.stream(ext):
+            b.record()
+        ctx.downsampleCurrentScan(want_output=False)
+        ctx.scan2MapOptimizationAsync(guess, 30, True)
+        with torch.cuda.stream(ext):
+            c.record()
+        pose = ctx.getPose()
+        if rep >= 3:
+            single.append((a.elapsed_time(b), b.elapsed_time(c)))
+    cnt = ctx.lastCounts()
+    single = np.array(single)
+    tsec = ctx.getTiming()
+    s2m_ms = tsec["scan2map"][0] / max(tsec["scan2map"][1], 1)
+    single_frame = dict(workload="kitti64_single: %d-pt scan, N_ds=%d, M=%d (%d keyframe clouds), 30 forced LM iterations" % (len(xyz), cnt["n_ds"], cnt["m_ds"], len(ids)),
+                        solve_ms=float(np.median(single[:, 1])), solve_ms_p95=float(np.percentile(single[:, 1], 95)),
+                        map_build_ms=float(np.median(single[:, 0])), solver_kernel_ms=s2m_ms,
+                        knn_queries_per_s=30 * cnt["n_ds"] / (s2m_ms * 1e-3), target_ms=1.0)
+
+    # ---- roofline of the dominant kernel of the sequence step ----
+    peaks, peak_src = load_peaks()
+    dv = results["dev"]
+    tm = dv["timing"]
+    dom = max(("scan2map", "map_build", "downsample", "deskew", "grid_build"), key=lambda k: tm[k][0])
+    st = dv["stats"]
+    alg = dict(scan2map=st["alg_bytes_s2m"],
+               map_build=0, downsample=0, deskew=0, grid_build=0)
+    n_raw = float(np.mean([len(seq.raw[i]) for i in range(P + W, P + W + K)]))
+    alg["deskew"] = (24 * n_raw + 16 * n_raw / 10) * tm["deskew"][1]
+    alg["downsample"] = (16 * n_raw / 10 + 16 * st["n_ds"] / max(st["frames"], 1)) * tm["downsample"][1]
+    alg["map_build"] = (32 * 0 + 16 * st["m_ds"] / max(st["frames"], 1)) * tm["map_build"][1]       # + 16*M_raw in (added below when known)
+    achieved = alg[dom] / (tm[dom][0] * 1e-3) / 1e9 if tm[dom][0] > 0 else 0.0
+    roofline = dict(kernel=dom, bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None,
+                    peak_source=peak_src, share_of_step={k: tm[k][0] / dv["ms"] for k in tm}, avg_launch_ms=tm[dom][0] / max(tm[dom][1], 1))
+
+    # ---- ScanContext search (config 5) ----
+    sc = None
+    if not args.no_sc:
+        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 5, dist)
+
+    # ---- CPU baseline (rank 0, N=1 only): the same frames on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_frames > 0:
+        cpu = run_cpu_sample(seq, keep, P, W, args.cpu_frames)
+        if sc is not None:
+            import pyoracle as o
+            nq = 32
+            kk = min(args.sc_k, 20000)
+            from tools import synth
+            db = synth.sc_descriptors(kk, first=0)
+            keys = np.stack([o.sc_keys_from_desc(d)[0] for d in db])
+            qk = np.stack([o.sc_keys_from_desc(d)[0] for d in qd[:nq]])
+            t = time.perf_counter(); o.sc_query_batch(keys, db, qk, qd[:nq]); dt = time.perf_counter() - t
+            cpu["sc_queries_per_s"] = nq / dt * (kk / args.sc_k)      # brute-force cost scales linearly in K
+            cpu["sc_sample"] = f"{nq} queries x {kk}-entry database, scaled to K={args.sc_k}"
+    keep.ctx.close()
+
+    if rank == 0:
+        tot_frames = K * world
+        line = dict(metric="scan2map_ms_per_frame_64beam", value=dv["ms"] / tot_frames, unit="ms/frame", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=dv["ms"] / K, higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="kitti05_seq: synthetic 64-beam drive, %d-frame window after a %d-frame pre-roll, ~%d returns/scan, yaml filters (downsampleRate 2, point_filter_num 5), leaf 0.4/0.5, early-exit LM; one independent sequence per GPU"
+                                % (K, P, int(n_raw)), l2="inputs streamed: every frame reads a fresh 2.9 MB scan; per-frame working set is not reused across frames",
+                                avg_n_ds=st["n_ds"] / max(st["frames"], 1), avg_m_ds=st["m_ds"] / max(st["frames"], 1), avg_lm_iters=st["iters"] / max(st["frames"], 1),
+                                keyframes_added=st["keyframes"]),
+                    wall_ms_per_step=dv["wall_ms"] / K,
+                    e2e=dict(value=results["e2e"]["ms"] / tot_frames, unit="ms/frame", h2d_bytes_per_step=results["e2e"]["h2d"], d2h_bytes_per_step=24 + 64 + 16,
+                             wall_ms_per_step=results["e2e"]["wall_ms"] / K),
+                    gpu_launches=dv["launches"], knn_queries_per_s=st["knn_queries"] / (tm["scan2map"][0] * 1e-3) if tm["scan2map"][0] > 0 else None,
+                    single_frame=single_frame, sc=sc, roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+                    kernel_ms_per_frame={k: tm[k][0] / K for k in tm})
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cpu_sample(seq, gpu_pipe, P, W, n_frames):
+    """CPU path on frames [P+W, P+W+n) starting from the keyframe state the GPU run had at frame P+W (same inputs)."""
+    import pyoracle as o
+    cpu = CpuPipeline(seq)
+    # rebuild the state as of frame P+W by replaying the GPU context's keyframes that existed then
+    ctx = gpu_pipe.ctx
+    clouds, poses, times = [], [], []
+    t_cut = T0 + DT * (P + W)
+    for k in range(ctx.numKeyframes()):
+        cl, ps, tt = ctx.getKeyframe(k)
+        if tt < t_cut - 1e-9:
+            clouds.append(cl); poses.append(ps); times.append(tt)
+    cpu.seed_keyframes(clouds, poses, times)
+    for cl in clouds[-40:]:
+        cpu.sc.save_descriptor(np.zeros(1200))
+    cpu.prev = poses[-1] if poses else None
+    cpu.step(P + W)                                              # warm-up frame
+    cpu.split = {k: 0.0 for k in cpu.split}
+    t = time.perf_counter()
+    for i in range(P + W + 1, P + W + 1 + n_frames):
+        cpu.step(i)
+    dt = time.perf_counter() - t
+    return dict(value=dt / n_frames * 1e3, unit="ms/frame", cores=o.num_threads(), kind="port",
+                sample=f"{n_frames} consecutive frames of the same sequence from the same keyframe state; oracle restatement, kd-tree = the reference's vendored nanoflann"
+                       + ("" if cpu.use_ref else " (oracle/_ref missing: brute-force kNN)"),
+                split_ms_per_frame={k: v / n_frames * 1e3 for k, v in cpu.split.items()})
+
+
+def run_reference(args, W, K):
+    """--impl reference: the CPU implementation of the path on the host cores, same metric/config, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as o
+    P = min(args.preroll, 60)
+    steps = min(K, 20)
+    seq = Sequence(P + W + steps, 0)
+    cpu = CpuPipeline(seq)
+    for i in range(P + W):
+        cpu.step(i)
+    cpu.split = {k: 0.0 for k in cpu.split}
+    t = time.perf_counter()
+    for i in range(P + W, P + W + steps):
+        cpu.step(i)
+    dt = time.perf_counter() - t
+    v = dt / steps * 1e3
+    line = dict(impl="reference", metric="scan2map_ms_per_frame_64beam", value=v, unit="ms/frame", n_gpus=args.gpus, steps=steps, warmup=W, ms_per_step=v,
+                higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="kitti05_seq: synthetic 64-beam drive, CPU path (oracle restatement + the reference's vendored nanoflann kd-tree), "
+                                     "%d timed frames after a %d-frame pre-roll" % (steps, P + W)),
+                cpu_baseline=dict(value=v, unit="ms/frame", cores=o.num_threads(), kind="port",
+                                  sample=f"{steps} consecutive frames", split_ms_per_frame={k: x / steps * 1e3 for k, x in cpu.split.items()}),
+                e2e=dict(value=v, unit="ms/frame", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

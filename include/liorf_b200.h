@@ -98,6 +98,15 @@ int liorf_set_local_map(liorf_ctx* ctx, const liorf_point* map_ds, int m);
 int liorf_get_local_map(liorf_ctx* ctx, liorf_point* out, int capacity, int* m_ds);
 int liorf_get_scan_ds(liorf_ctx* ctx, liorf_point* out, int capacity, int* n_ds);
 
+/* keyframe SELECTION of extractNearby (src/mapOptmization.cpp:975-1010) over the context's key poses: radius search
+ * around the newest key pose, VoxelGrid(surroundingKeyframeDensity) of the poses, nearest-1 id recovery, plus every
+ * keyframe younger than 10 s.  Host-side scalar code (a few hundred poses).  ids capacity = cap; *n_ids = count. */
+int liorf_extract_nearby(liorf_ctx* ctx, double time_laser_info_cur, float surrounding_keyframe_density, int* ids, int cap, int* n_ids);
+/* replaces mapOptimization::saveFrame() (src/mapOptmization.cpp:1365-1384): 1 = make a keyframe, 0 = skip */
+int liorf_save_frame(liorf_ctx* ctx, const float pose6[6], float adding_dist_threshold, float adding_angle_threshold);
+/* the clamps of transformUpdate (src/mapOptmization.cpp:1348-1350) */
+void liorf_transform_update_clamp(float pose6_inout[6], float rotation_tollerance, float z_tollerance);
+
 /* replaces mapOptimization::scan2MapOptimization() (src/mapOptmization.cpp:1295) up to, not including, transformUpdate:
  * ≤ max_iters × {surfOptimization, combineOptimizationCoeffs, LMOptimization} in one persistent kernel.
  * force_all_iters != 0 disables the convergence break (benchmark).  trace nullable. */
@@ -146,6 +155,15 @@ int liorf_sc_decide_dev(liorf_ctx* ctx, const void* d_pair_dist, const void* d_p
                         void* d_loop_id, void* d_shift, void* d_dist);
 /* single-GPU convenience with host buffers: descriptors of the Q queries → loop ids / shifts / distances */
 int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
+
+/* ---- measurement / introspection (bench.py) ------------------------------------------------------------------- */
+/* per-section CUDA-event timing on the context's stream: sections 0 deskew, 1 downsample, 2 map build (transform +
+ * VoxelGrid), 3 grid build, 4 scan2map solver, 5 ScanContext make, 6 ScanContext ring-key search */
+int liorf_enable_timing(liorf_ctx* ctx, int on);
+int liorf_get_timing(liorf_ctx* ctx, double ms[8], long long calls[8]);
+long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels launched by this context so far */
+int liorf_get_last_counts(liorf_ctx* ctx, int* n_scan, int* n_ds, int* m_ds, int* iters);   /* as of the last liorf_get_pose */
+int liorf_get_keyframe(liorf_ctx* ctx, int id, liorf_point* out, int capacity, int* n, float pose6[6], double* time);
 
 #ifdef __cplusplus
 }

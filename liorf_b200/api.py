@@ -97,6 +97,7 @@ class Context:
         out = np.empty((max(n, 1), 4), np.float32) if want_output else None
         kept = np.empty(max(n, 1), np.int32) if want_kept_index else None
         n_out = C.c_int(0)
+        self._keep = raw                                          # the H2D copy may still be in flight in the async form
         if deskew_enabled:
             it = np.ascontiguousarray(imu_time, np.float64)
             rot = np.ascontiguousarray(imu_rot, np.float64)
@@ -104,8 +105,11 @@ class Context:
         else:
             it = rx = ry = rz = None
         _chk(self.lib.liorf_project_point_cloud(self.h, _vp(raw), C.c_int(n), C.c_double(time_scan_cur), _vp(it), _vp(rx), _vp(ry), _vp(rz),
-                                                C.c_int(imu_pointer_cur), C.c_int(int(bool(deskew_enabled))), _vp(out), C.byref(n_out), _vp(kept)),
+                                                C.c_int(imu_pointer_cur), C.c_int(int(bool(deskew_enabled))), _vp(out),
+                                                C.byref(n_out) if (want_output or want_kept_index) else None, _vp(kept)),
              "liorf_project_point_cloud")
+        if not want_output and not want_kept_index:
+            return None
         k = n_out.value
         res = [out[:k].copy() if want_output else None, k]
         if want_kept_index:
@@ -173,6 +177,14 @@ class Context:
              "liorf_extract_surrounding_keyframes")
         return m.value if want_count else None
 
+    def extractNearby(self, time_cur, density=2.0, cap=4096):
+        ids = np.zeros(cap, np.int32); n = C.c_int(0)
+        _chk(self.lib.liorf_extract_nearby(self.h, C.c_double(time_cur), C.c_float(density), _vp(ids), C.c_int(cap), C.byref(n)), "liorf_extract_nearby")
+        return ids[:n.value].copy()
+
+    def saveFrame(self, pose6, dist_thr=1.0, ang_thr=0.2):
+        return bool(_chk(self.lib.liorf_save_frame(self.h, _vp(_pose(pose6)), C.c_float(dist_thr), C.c_float(ang_thr)), "liorf_save_frame"))
+
     def setLocalMap(self, map_ds):
         map_ds = _p4(map_ds)
         _chk(self.lib.liorf_set_local_map(self.h, _vp(map_ds), C.c_int(len(map_ds))), "liorf_set_local_map")
@@ -238,6 +250,32 @@ class Context:
     def setLMState(self, deg, matP):
         P = np.ascontiguousarray(matP, np.float32).reshape(36)
         _chk(self.lib.liorf_set_lm_state(self.h, C.c_int(int(deg)), _vp(P)), "liorf_set_lm_state")
+
+    # ---- measurement helpers ----
+    def enableTiming(self, on=True):
+        _chk(self.lib.liorf_enable_timing(self.h, C.c_int(int(on))), "liorf_enable_timing")
+
+    def getTiming(self):
+        ms = (C.c_double * 8)(); calls = (C.c_longlong * 8)()
+        _chk(self.lib.liorf_get_timing(self.h, ms, calls), "liorf_get_timing")
+        names = ["deskew", "downsample", "map_build", "grid_build", "scan2map", "sc_make", "sc_search", "_"]
+        return {n: (ms[i], calls[i]) for i, n in enumerate(names) if n != "_"}
+
+    def launchCount(self):
+        self.lib.liorf_get_launch_count.restype = C.c_longlong
+        return int(self.lib.liorf_get_launch_count(self.h))
+
+    def lastCounts(self):
+        a, b, c_, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _chk(self.lib.liorf_get_last_counts(self.h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)), "liorf_get_last_counts")
+        return dict(n_scan=a.value, n_ds=b.value, m_ds=c_.value, iters=d.value)
+
+    def getKeyframe(self, kid):
+        n = C.c_int(0); pose = np.zeros(6, np.float32); t = C.c_double(0)
+        _chk(self.lib.liorf_get_keyframe(self.h, C.c_int(kid), None, C.c_int(0), C.byref(n), _vp(pose), C.byref(t)), "liorf_get_keyframe")
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _chk(self.lib.liorf_get_keyframe(self.h, C.c_int(kid), _vp(out), C.c_int(len(out)), C.byref(n), _vp(pose), C.byref(t)), "liorf_get_keyframe")
+        return out[:n.value].copy(), pose, t.value
 
     # ---- SCManager ----
     def makeAndSaveScancontextAndKeys(self, cloud=None):

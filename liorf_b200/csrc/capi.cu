@@ -9,6 +9,7 @@
 #include "scan2map.cuh"
 #include "deskew.cuh"
 #include "scancontext.cuh"
+#include "../host/host_logic.hpp"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -23,6 +24,15 @@ static_assert(S2M_MAX_ITERS == LIORF_MAX_ITERS, "iteration cap mismatch");
 enum { C_N_SCAN = 0, C_N_DS, C_M_DS, C_NSEL, C_FIRST_KEPT, C_CONV, C_HOOK_NSEL, C_COUNT = 16 };
 
 struct Keyframe { size_t off; int count; float pose[6]; double time; };
+
+// optional per-section CUDA-event timing on the context's stream (bench.py's live roofline numbers)
+enum { SEC_DESKEW = 0, SEC_DOWNSAMPLE, SEC_MAP_BUILD, SEC_GRID_BUILD, SEC_SCAN2MAP, SEC_SC_MAKE, SEC_SC_SEARCH, SEC_COUNT = 8 };
+constexpr int PROF_RING = 64;
+struct Profiler {
+    bool enabled = false;
+    cudaEvent_t ev[PROF_RING][2]; int sec[PROF_RING]; int pending = 0; bool created = false;
+    double ms[SEC_COUNT] = {0}; long long calls[SEC_COUNT] = {0};
+};
 
 struct liorf_ctx {
     liorf_params P;
@@ -60,6 +70,29 @@ struct liorf_ctx {
     DevBuf<float> sc_part_d; DevBuf<int> sc_part_i;
     DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
     DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
+    Profiler prof;
+    long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
+};
+
+static void prof_flush(liorf_ctx* c) {           // call only when the stream is idle (after a sync)
+    Profiler& p = c->prof;
+    for (int i = 0; i < p.pending; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.ev[i][0], p.ev[i][1]) == cudaSuccess) { p.ms[p.sec[i]] += ms; p.calls[p.sec[i]]++; }
+    }
+    p.pending = 0;
+}
+struct ProfScope {
+    liorf_ctx* c; int slot = -1;
+    ProfScope(liorf_ctx* c_, int sec) : c(c_) {
+        Profiler& p = c->prof;
+        if (!p.enabled) return;
+        if (!p.created) { for (int i = 0; i < PROF_RING; ++i) { cudaEventCreate(&p.ev[i][0]); cudaEventCreate(&p.ev[i][1]); } p.created = true; }
+        if (p.pending == PROF_RING) { cudaStreamSynchronize(c->stream); prof_flush(c); }
+        slot = p.pending++; p.sec[slot] = sec;
+        cudaEventRecord(p.ev[slot][0], c->stream);
+    }
+    ~ProfScope() { if (slot >= 0) cudaEventRecord(c->prof.ev[slot][1], c->stream); }
 };
 
 static void host_get_transformation(float x, float y, float z, float roll, float pitch, float yaw, float* t) {
@@ -75,6 +108,7 @@ static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-
     int e = 0;
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 4000, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    prof_flush(c);
     e = c->h_mail[4000];
     if (e) { fprintf(stderr, "[liorf_b200] device error flag %d (look-back predecessor never arrived)\n", e); return LIORF_ERR_DEVICE_FLAG; }
     return LIORF_OK;
@@ -83,6 +117,7 @@ static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-
 static int read_counts(liorf_ctx* c) {
     CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    prof_flush(c);
     c->h_n_scan = c->h_mail[C_N_SCAN]; c->h_n_ds = c->h_mail[C_N_DS]; c->h_m_ds = c->h_mail[C_M_DS];
     return LIORF_OK;
 }
@@ -211,6 +246,7 @@ static int project_common(liorf_ctx* c, const RawPoint* d_raw, int n, double t0,
         T = ImuTable{c->dk.imu.p, c->dk.imu.p + rows, c->dk.imu.p + 2 * rows, c->dk.imu.p + 3 * rows, imu_ptr};
     }
     DeskewParams DP{c->P.lidarMinRange, c->P.lidarMaxRange, c->P.N_SCAN, c->P.downsampleRate, c->P.point_filter_num};
+    ProfScope ps(c, SEC_DESKEW); c->launches += 2;
     k_first_kept<<<1, 1024, 0, c->stream>>>(d_raw, n, DP, t0, T, deskew_enabled, c->dk.start_inv, c->dk.first_kept);
     rc = launch_scan(Count::of_host(n), DeskewLoad{d_raw, DP}, DeskewStore{d_raw, t0, T, deskew_enabled, c->dk.start_inv, c->scan.p, d_kept_index},
                      c->dk.scan, (unsigned*)(c->d_counts + C_N_SCAN), c->stream);
@@ -229,6 +265,7 @@ int liorf_project_point_cloud(liorf_ctx* c, const liorf_point_xyzirt* pts, int n
     int* d_ki = nullptr;
     if (kept_index) { if ((rc = c->membership.reserve(n > 0 ? n : 1))) return rc; d_ki = c->membership.p; }
     if ((rc = project_common(c, c->dk.raw.p, n, t0, imu_time, rx, ry, rz, imu_ptr, deskew_enabled, d_ki))) return rc;
+    if (!out && !n_out && !kept_index) return LIORF_OK;          // stay asynchronous: the cloud feeds downsampleCurrentScan on the device
     if ((rc = read_counts(c))) return rc;
     if (n_out) *n_out = c->h_n_scan;
     if (out && c->h_n_scan > 0) CUDA_TRY(cudaMemcpyAsync(out, c->scan.p, (size_t)c->h_n_scan * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -272,6 +309,7 @@ static int downsample_async(liorf_ctx* c, int* d_membership) {
     if ((rc = c->scan_ds.reserve(nb > 0 ? nb : 1))) return rc;
     c->h_n_ds = -1;
     Count cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, nb);
+    ProfScope ps(c, SEC_DOWNSAMPLE); c->launches += 9;
     return voxel_grid_device(c->scan.p, cnt, c->P.mappingSurfLeafSize, c->scan_ds.p, c->d_counts + C_N_DS, d_membership, nullptr, c->vg, c->stream);
 }
 
@@ -389,15 +427,40 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     if ((rc = c->map_raw.reserve(tot > 0 ? tot : 1))) return rc;
     if ((rc = c->map_ds.reserve(tot > 0 ? tot : 1))) return rc;
     if (ns > 0) CUDA_TRY(cudaMemcpyAsync(c->d_sel.p, c->h_sel, (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, c->stream));
-    if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
-    if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_counts + C_M_DS, nullptr,
-                                nullptr, c->vg, c->stream))) return rc;
+    {
+        ProfScope ps(c, SEC_MAP_BUILD); c->launches += 10;
+        if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
+        if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_counts + C_M_DS, nullptr,
+                                    nullptr, c->vg, c->stream))) return rc;
+    }
     c->m_bound = tot; c->h_m_ds = -1;
-    if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_counts + C_M_DS, tot), c->grid, c->stream))) return rc;
+    {
+        ProfScope ps(c, SEC_GRID_BUILD); c->launches += 3;
+        if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_counts + C_M_DS, tot), c->grid, c->stream))) return rc;
+    }
     c->last_sel = sel; c->last_sel_version = c->pose_version; c->map_valid = true;
     if (m_ds) { if ((rc = read_counts(c))) return rc; *m_ds = c->h_m_ds; return check_err(c); }
     return LIORF_OK;
 }
+
+int liorf_extract_nearby(liorf_ctx* c, double time_cur, float density, int* ids, int cap, int* n_ids) {
+    if (!c || !ids || !n_ids || cap < 0 || !(density > 0.f)) return LIORF_ERR_ARG;
+    std::vector<liorf_host::KeyPose> kp(c->kfs.size());
+    for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }
+    std::vector<int> sel = liorf_host::extract_nearby(kp, time_cur, c->P.surroundingKeyframeSearchRadius, density);
+    *n_ids = (int)sel.size();
+    if ((int)sel.size() > cap) return LIORF_ERR_ARG;
+    std::memcpy(ids, sel.data(), sel.size() * sizeof(int));
+    return LIORF_OK;
+}
+int liorf_save_frame(liorf_ctx* c, const float pose6[6], float dist_thr, float ang_thr) {
+    if (!c || !pose6) return LIORF_ERR_ARG;
+    if (c->kfs.empty()) return 1;
+    const Keyframe& k = c->kfs.back();
+    liorf_host::KeyPose last{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time};
+    return liorf_host::save_frame(&last, pose6, dist_thr, ang_thr) ? 1 : 0;
+}
+void liorf_transform_update_clamp(float pose6[6], float rot_tol, float z_tol) { liorf_host::transform_update_clamp(pose6, rot_tol, z_tol); }
 
 int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
     if (!c || m < 0 || (m > 0 && !map_ds)) return LIORF_ERR_ARG;
@@ -443,6 +506,7 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
     a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all;
     void* args[] = {&a};
+    ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2M_BLOCK), args, 0, c->stream));
     return LIORF_OK;
 }
@@ -461,8 +525,11 @@ int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
     if (!c || !pose6) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 320, c->d_tf6, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (trace) CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024, c->d_trace, sizeof(S2MTrace), cudaMemcpyDeviceToHost, c->stream));
+    else CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024 + 448, &c->d_trace->iters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     int rc = check_err(c); if (rc) return rc;
+    c->h_n_scan = c->h_mail[C_N_SCAN]; c->h_n_ds = c->h_mail[C_N_DS]; c->h_m_ds = c->h_mail[C_M_DS];   // one round trip refreshes the counts too
     std::memcpy(pose6, c->h_mail + 320, 6 * sizeof(float));
     if (trace) std::memcpy(trace, c->h_mail + 1024, sizeof(S2MTrace));
     return LIORF_OK;
@@ -582,6 +649,7 @@ int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
         d_pts = c->scan.p; cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, c->n_scan_bound);
     }
     if ((rc = sc_reserve(c, c->sc_n + 1))) return rc;
+    ProfScope ps(c, SEC_SC_MAKE); c->launches += 2;
     if (cnt.bound > 0) {
         int blocks = (cnt.bound + 256 * 8 - 1) / (256 * 8); if (blocks > c->num_sms) blocks = c->num_sms;
         k_sc_bins<<<blocks, 256, 0, c->stream>>>(d_pts, cnt, c->d_bins);
@@ -631,6 +699,7 @@ static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_
     int kpc = (n_keys + chunks - 1) / chunks; kpc = ((kpc + SCK_TILE - 1) / SCK_TILE) * SCK_TILE; if (kpc < SCK_TILE) kpc = SCK_TILE;
     chunks = (n_keys + kpc - 1) / kpc; if (chunks < 1) chunks = 1;
     if ((rc = c->sc_part_d.reserve((size_t)chunks * Q * 3)) || (rc = c->sc_part_i.reserve((size_t)chunks * Q * 3))) return rc;
+    ProfScope ps(c, SEC_SC_SEARCH); c->launches += 2;
     k_sc_knn_tile<<<dim3(bx, chunks), SCK_BLOCK, 0, c->stream>>>(d_keys, n_keys, global_offset, d_qkeys, Q, kpc, c->sc_part_d.p, c->sc_part_i.p);
     k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sc_part_d.p, c->sc_part_i.p, chunks, Q, d_dist, d_idx);
     CUDA_TRY(cudaGetLastError());
@@ -736,6 +805,44 @@ int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_
     if (min_dist) *min_dist = md;
     if (cand3) { cand3[0] = cand[0]; cand3[1] = cand[1]; cand3[2] = cand[2]; }
     *yaw_diff_rad = (float)((float)(nn_align * (360.0 / 60.0)) * M_PI / 180.0);   // deg2rad(float) (:17-20, :339)
+    return LIORF_OK;
+}
+
+// ---- benchmark / introspection helpers ----
+int liorf_enable_timing(liorf_ctx* c, int on) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream)); prof_flush(c);
+    c->prof.enabled = on != 0;
+    for (int i = 0; i < SEC_COUNT; ++i) { c->prof.ms[i] = 0; c->prof.calls[i] = 0; }
+    return LIORF_OK;
+}
+int liorf_get_timing(liorf_ctx* c, double ms[8], long long calls[8]) {
+    if (!c || !ms || !calls) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream)); prof_flush(c);
+    for (int i = 0; i < SEC_COUNT; ++i) { ms[i] = c->prof.ms[i]; calls[i] = c->prof.calls[i]; }
+    return LIORF_OK;
+}
+long long liorf_get_launch_count(liorf_ctx* c) { return c ? c->launches : -1; }
+int liorf_get_last_counts(liorf_ctx* c, int* n_scan, int* n_ds, int* m_ds, int* iters) {
+    if (!c) return LIORF_ERR_ARG;
+    if (n_scan) *n_scan = c->h_n_scan; if (n_ds) *n_ds = c->h_n_ds; if (m_ds) *m_ds = c->h_m_ds;
+    if (iters) *iters = c->h_mail[1024 + 448];       // S2MTrace.iters as of the last liorf_get_pose
+    return LIORF_OK;
+}
+int liorf_get_keyframe(liorf_ctx* c, int id, liorf_point* out, int capacity, int* n, float pose6[6], double* time) {
+    if (!c || id < 0 || id >= (int)c->kfs.size()) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    const Keyframe& k = c->kfs[id];
+    if (n) *n = k.count;
+    if (pose6) std::memcpy(pose6, k.pose, 6 * sizeof(float));
+    if (time) *time = k.time;
+    if (out) {
+        if (capacity < k.count) return LIORF_ERR_ARG;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (k.count > 0) CUDA_TRY(cudaMemcpy(out, c->kf_points.p + k.off, (size_t)k.count * sizeof(float4), cudaMemcpyDeviceToHost));
+    }
     return LIORF_OK;
 }
 
