@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+ORACLE_DIR = os.path.join(ROOT, "oracle")     # imported ONLY by the cpu_baseline leg and --impl reference (never by the GPU arm)
 
 T0 = 1000.0
 DT = 0.1
@@ -524,6 +525,8 @@ def main():
 
 def run_cpu_sample(seq, gpu_pipe, P, W, n_frames):
     """CPU path on frames [P+W, P+W+n) starting from the keyframe state the GPU run had at frame P+W (same inputs)."""
+    if ORACLE_DIR not in sys.path:
+        sys.path.insert(0, ORACLE_DIR)
     import pyoracle as o
     cpu = CpuPipeline(seq)
     # rebuild the state as of frame P+W by replaying the GPU context's keyframes that existed then

@@ -58,7 +58,8 @@ struct liorf_ctx {
     KfSel* h_sel = nullptr; int h_sel_cap = 0;
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
-    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr;
+    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr;
+    DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0;
     int s2m_grid = 0;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
@@ -181,11 +182,12 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaMemset(c->d_trace, 0, sizeof(S2MTrace)));
     CUDA_TRY(cudaMalloc(&c->d_lm_out, 48 * sizeof(float)));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan2map_persistent, S2M_BLOCK, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan2map_persistent, S2MP_BLOCK, 0));
     if (occ < 1) { fprintf(stderr, "[liorf_b200] persistent kernel does not fit\n"); return LIORF_ERR_CUDA; }
-    if (occ > 4) occ = 4;
-    c->s2m_grid = c->num_sms * occ;
+    c->s2m_grid = c->num_sms;                                   // one persistent CTA per SM
     CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->s2m_grid * NPROD * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->d_result, 2 * sizeof(S2MResult)));
+    CUDA_TRY(cudaMemset(c->d_result, 0, 2 * sizeof(S2MResult)));
     CUDA_TRY(cudaMalloc(&c->d_bins, SC_DESC * sizeof(unsigned)));
     {   // arm the ScanContext bins with the NO_POINT code
         std::vector<unsigned> init(SC_DESC);
@@ -215,7 +217,8 @@ void liorf_destroy(liorf_ctx* c) {
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
     cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
-    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins);
+    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
+    if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->h_sel) cudaFreeHost(c->h_sel);
     cudaFreeHost(c->h_mail);
     cudaStreamDestroy(c->stream);
@@ -501,13 +504,19 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
         CUDA_TRY(cudaMemsetAsync(c->d_trace, 0, sizeof(S2MTrace), c->stream));
         return LIORF_OK;
     }
+    int rc;
+    const size_t qb = (size_t)(c->n_scan_bound > 0 ? c->n_scan_bound : 1);
+    if ((rc = c->qcache.reserve(qb)) || (rc = c->cand.reserve(qb * CAND_CAP))) return rc;
     S2MArgs a;
+    a.qcache = c->qcache.p; a.cand = c->cand.p; a.result = c->d_result;
+    a.arrive = reinterpret_cast<unsigned*>(c->d_misc + 8); a.flag = reinterpret_cast<unsigned*>(c->d_misc + 9); a.err_flag = c->d_err;
+    a.epoch_base = (++c->s2m_launch_seq) * 64u;
     a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
-    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all;
+    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.dbg = c->d_dbg;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2M_BLOCK), args, 0, c->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2MP_BLOCK), args, 0, c->stream));
     return LIORF_OK;
 }
 
@@ -825,6 +834,16 @@ int liorf_get_timing(liorf_ctx* c, double ms[8], long long calls[8]) {
     return LIORF_OK;
 }
 long long liorf_get_launch_count(liorf_ctx* c) { return c ? c->launches : -1; }
+// debug: phase clocks of the persistent solver (CTA 0): out[iter*8 + {0 start,1 loop done,2 block reduced,3 grid synced,4 summed,5 solved}]
+int liorf_debug_s2m_clocks(liorf_ctx* c, int enable, long long* out /*64*8 or null*/) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (enable && !c->d_dbg) { CUDA_TRY(cudaMalloc(&c->d_dbg, S2M_MAX_ITERS * 8 * sizeof(long long))); CUDA_TRY(cudaMemset(c->d_dbg, 0, S2M_MAX_ITERS * 8 * sizeof(long long))); }
+    if (out && c->d_dbg) CUDA_TRY(cudaMemcpy(out, c->d_dbg, S2M_MAX_ITERS * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (!enable && c->d_dbg) { cudaFree(c->d_dbg); c->d_dbg = nullptr; }
+    return LIORF_OK;
+}
 int liorf_get_last_counts(liorf_ctx* c, int* n_scan, int* n_ds, int* m_ds, int* iters) {
     if (!c) return LIORF_ERR_ARG;
     if (n_scan) *n_scan = c->h_n_scan; if (n_ds) *n_ds = c->h_n_ds; if (m_ds) *m_ds = c->h_m_ds;

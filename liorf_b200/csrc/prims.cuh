@@ -34,23 +34,77 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Serial look-back for one chain (status index = tile * stride + lane_of_chain). Returns exclusive prefix.
+// Look-back for one chain (status index = tile * stride + chain), walked by ONE thread in batches of LB_BATCH
+// predecessors whose loads are issued together (one L2 round trip per batch instead of per predecessor).
+// Returns the exclusive prefix.
+constexpr int LB_BATCH = 8;
 __device__ __forceinline__ unsigned lookback_chain(unsigned long long* status, int tile, int stride, int chain, unsigned agg,
                                                    unsigned epoch, int* err_flag) {
     st_status(status + (size_t)tile * stride + chain, pack_status(epoch, tile == 0 ? 2u : 1u, agg));
     if (tile == 0) return 0u;
-    unsigned excl = 0;
-    for (int t = tile - 1; t >= 0; --t) {
-        unsigned long long w; unsigned spins = 0;
-        while (true) {
-            w = ld_status(status + (size_t)t * stride + chain);
-            if ((unsigned)(w >> 34) == (epoch & 0x3fffffffu) && ((w >> 32) & 3u) != 0u) break;
-            if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); return excl; }
+    const unsigned ep = epoch & 0x3fffffffu;
+    unsigned excl = 0; unsigned spins = 0;
+    int t = tile - 1;
+    bool done = false;
+    while (!done && t >= 0) {
+        unsigned long long w[LB_BATCH];
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; ++j) w[j] = (t - j >= 0) ? ld_status(status + (size_t)(t - j) * stride + chain) : pack_status(epoch, 2u, 0u);
+        int used = 0;
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; ++j) {
+            if (done || used != j) continue;                      // stop at the first not-yet-published predecessor
+            const unsigned flag = ((unsigned)(w[j] >> 34) == ep) ? (unsigned)((w[j] >> 32) & 3u) : 0u;
+            if (flag == 0u) continue;
+            excl += (unsigned)w[j]; ++used;
+            if (flag == 2u) done = true;
         }
-        excl += (unsigned)w;
-        if (((w >> 32) & 3u) == 2u) break;
+        t -= used;
+        if (used == 0 && ++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); return excl; }
     }
     st_status(status + (size_t)tile * stride + chain, pack_status(epoch, 2u, excl + agg));
+    return excl;
+}
+
+// Warp-cooperative look-back for a single chain (stride 1): 32 lanes x 4 predecessors per step.
+__device__ __forceinline__ unsigned lookback_warp(unsigned long long* status, int tile, unsigned agg, unsigned epoch, int* err_flag) {
+    const int l = threadIdx.x & 31;
+    if (l == 0) st_status(status + tile, pack_status(epoch, tile == 0 ? 2u : 1u, agg));
+    if (tile == 0) return 0u;
+    const unsigned ep = epoch & 0x3fffffffu;
+    unsigned excl = 0; unsigned spins = 0;
+    int t = tile - 1;                       // nearest predecessor not yet consumed
+    while (t >= 0) {
+        // lane l looks at predecessors t - (4 l + j); nearer ones have smaller offsets
+        unsigned val[4]; unsigned flag[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int tt = t - (4 * l + j);
+            unsigned long long w = tt >= 0 ? ld_status(status + tt) : pack_status(epoch, 2u, 0u);
+            flag[j] = ((unsigned)(w >> 34) == ep) ? (unsigned)((w >> 32) & 3u) : 0u;
+            val[j] = (unsigned)w;
+        }
+        // per lane: number of leading valid entries, whether a PREFIX ends the run, and the partial sum up to there
+        unsigned cnt = 0, sum = 0; bool pre = false, open = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (open) { if (flag[j] == 0u) open = false; else { sum += val[j]; ++cnt; if (flag[j] == 2u) { pre = true; open = false; } } }
+        const unsigned full = __ballot_sync(FULL, cnt == 4u && !pre);        // lanes whose 4 entries are all aggregates
+        const int first_stop = __ffs(~full) - 1;                             // first lane that is not "4 plain aggregates" (32 if none)
+        const int fs = first_stop < 0 ? 32 : first_stop;
+        unsigned contrib = (l < fs) ? sum : (l == fs ? sum : 0u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(FULL, contrib, o);
+        const unsigned stop_cnt = __shfl_sync(FULL, cnt, fs < 32 ? fs : 0);
+        const bool stop_pre = __shfl_sync(FULL, pre ? 1 : 0, fs < 32 ? fs : 0) != 0;
+        excl += contrib;
+        if (fs < 32) {
+            if (stop_pre) { t = -1; break; }
+            const int consumed = 4 * fs + (int)stop_cnt;
+            t -= consumed;
+            if (consumed == 0 && ++spins > SPIN_LIMIT) { if (l == 0) atomicExch(err_flag, 1); return excl; }
+        } else t -= 128;
+    }
+    if (l == 0) st_status(status + tile, pack_status(epoch, 2u, excl + agg));
     return excl;
 }
 
@@ -127,7 +181,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_lookback(Count cnt, LoadOp 
     for (int j = 0; j < SCAN_IPT; ++j) { int i = base + j; v[j] = i < n ? load(i) : 0u; sum += v[j]; }
     unsigned total;
     unsigned off = block_excl_scan<SCAN_BLOCK>(sum, s_warp, total);
-    if (threadIdx.x == 0) s_prefix = lookback_chain(status, tile, 1, 0, total, epoch, err_flag);
+    if (threadIdx.x < 32) { unsigned pf = lookback_warp(status, tile, total, epoch, err_flag); if (threadIdx.x == 0) s_prefix = pf; }
     __syncthreads();
     unsigned run = s_prefix + off;
 #pragma unroll

@@ -17,7 +17,7 @@ namespace liorf {
 namespace cg = cooperative_groups;
 
 constexpr int LIORF_G = 8;                 // lanes per query
-constexpr int S2M_BLOCK = 256;
+constexpr int S2M_BLOCK = 256;             // per-function hook kernels
 constexpr int S2M_QPB = S2M_BLOCK / LIORF_G;
 constexpr int S2M_MAX_ITERS = 64;
 constexpr int NPROD = 28;                  // 21 upper-triangular AtA + 6 AtB + 1 count
@@ -63,6 +63,9 @@ __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ gmap, 
 
 // Exact 5 nearest map points with squared distance < 1.0, ordered by (distance, original index).  All lanes of the
 // group return identical lists.  Slots beyond the number found hold d = +inf, oi = INT_MAX, pos = -1.
+// Latency structure: the 18 cell-range bounds of the 9 x-runs are fetched together (one L2 round trip), then the
+// concatenated candidate list is walked KNN_U candidates per lane per step with the loads issued before any compare.
+constexpr int KNN_U = 4;
 __device__ __forceinline__ void knn5_group(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap,
                                            GridDims g, Top5& res) {
     const int gl = threadIdx.x & (LIORF_G - 1);
@@ -70,14 +73,42 @@ __device__ __forceinline__ void knn5_group(const float4 q, const unsigned* __res
     const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
     const int x0 = (cx - 1) & (g.DX - 1), x1 = cx & (g.DX - 1), x2 = (cx + 1) & (g.DX - 1);
     const bool contiguous = (x0 + 2 == x2);
+    if (contiguous) {
+        unsigned bs[9], P[10];
+        P[0] = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
+            bs[r] = __ldg(cell_start + row + x0);
+            P[r + 1] = __ldg(cell_start + row + x2 + 1);          // end of the run, turned into a prefix below
+        }
+#pragma unroll
+        for (int r = 0; r < 9; ++r) P[r + 1] = P[r] + (P[r + 1] - bs[r]);
+        const unsigned T = P[9];
+        for (unsigned f0 = gl; f0 < T; f0 += LIORF_G * KNN_U) {
+            float4 p[KNN_U]; unsigned pos[KNN_U];
+#pragma unroll
+            for (int u = 0; u < KNN_U; ++u) {
+                const unsigned f = f0 + LIORF_G * u;
+                unsigned base = bs[0], pb = 0;
+#pragma unroll
+                for (int rr = 1; rr < 9; ++rr) if (f >= P[rr]) { base = bs[rr]; pb = P[rr]; }
+                pos[u] = base + (f - pb);
+                p[u] = f < T ? __ldg(gmap + pos[u]) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < KNN_U; ++u) {
+                float dx = q.x - p[u].x, dy = q.y - p[u].y, dz = q.z - p[u].z;
+                float d = dx * dx; d += dy * dy; d += dz * dz;      // FLANN L2_Simple op order, no FMA
+                if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), (int)pos[u]);
+            }
+        }
+    } else {                                                        // x-run wraps around the torus: three separate cells per row
 #pragma unroll 1
-    for (int r = 0; r < 9; ++r) {
-        const int dz = r / 3 - 1, dy = r % 3 - 1;
-        const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
-        if (contiguous) {
-            unsigned b = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x2 + 1);
-            knn_scan_range(gmap, b, e, gl, q, mine);
-        } else {
+        for (int r = 0; r < 9; ++r) {
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
             knn_scan_range(gmap, __ldg(cell_start + row + x0), __ldg(cell_start + row + x0 + 1), gl, q, mine);
             knn_scan_range(gmap, __ldg(cell_start + row + x1), __ldg(cell_start + row + x1 + 1), gl, q, mine);
             knn_scan_range(gmap, __ldg(cell_start + row + x2), __ldg(cell_start + row + x2 + 1), gl, q, mine);
@@ -152,39 +183,104 @@ __device__ __forceinline__ void lm_row_dev(const LMTrig& g, const float4 p, cons
 __host__ __device__ constexpr int prod_i(int p) { return p < 6 ? 0 : p < 11 ? 1 : p < 15 ? 2 : p < 18 ? 3 : p < 20 ? 4 : p < 21 ? 5 : p < 27 ? p - 21 : 7; }
 __host__ __device__ constexpr int prod_j(int p) { return p < 6 ? p : p < 11 ? p - 5 : p < 15 ? p - 9 : p < 18 ? p - 12 : p < 20 ? p - 14 : p < 21 ? 5 : p < 27 ? 6 : 7; }
 
-// Solve step shared by the hook kernel and the persistent kernel; executed by ONE thread.
-// sums: 28 fp64 totals.  Updates tf (6), state; returns converged.  X_out/AtA_out/AtB_out optional.
-__device__ __noinline__ bool lm_solve_dev(int iter, const double* sums, float* tf, LMDeviceState* st, float* scratchA /*36*/, float* scratchV /*36*/,
-                                          float* AtA_out, float* AtB_out, float* X_out, int* nsel_out) {
+// iteration-0 only (:1242-1264): cv::eigen → zero the eigenvector rows of eigenvalues < 100 → matP = V^-1 * V2
+__device__ __noinline__ void lm_degeneracy_dev(const float* AtA, LMDeviceState* st, float* scratchA /*36*/, float* scratchV /*36*/) {
+    float W[6], V2[36], Vinv[36];
+    for (int i = 0; i < 36; ++i) scratchA[i] = AtA[i];
+    jacobi6(scratchA, W, scratchV);
+    for (int i = 0; i < 36; ++i) V2[i] = scratchV[i];
+    int deg = 0;
+    for (int i = 5; i >= 0; --i) {
+        if (W[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; deg = 1; }
+        else break;
+    }
+    for (int i = 0; i < 36; ++i) scratchA[i] = scratchV[i];
+    lu_invert6(scratchA, Vinv);
+    gemm6(Vinv, V2, st->matP);
+    st->isDegenerate = deg;
+}
+
+// Certificate of non-degeneracy: true ⇒ every eigenvalue of the symmetric fp32 matrix AtA exceeds mu, proven by an fp64
+// LDL^T factorisation of (AtA - mu I) with strictly positive pivots.  mu = 100 (the reference's eigen threshold, :1252)
+// plus a margin that dominates the fp32 Jacobi solver's eigenvalue error (<= ~n eps ||A||), so cv::eigen would also
+// report all eigenvalues >= 100 and isDegenerate = false.  When the certificate fails the full Jacobi path runs.
+__device__ __forceinline__ bool certify_non_degenerate(const float* AtA) {
+    double trace = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) trace += (double)AtA[i * 7];
+    const double mu = 100.0 + 2e-5 * trace;
+    double L[6][6], D[6];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = (double)AtA[j * 7] - mu;
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+        D[j] = d;
+        if (!(d > 1e-9 * trace)) ok = false;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = (double)AtA[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = v / d;
+        }
+    }
+    return ok;
+}
+
+// Solve step shared by the hook kernel and the persistent kernel; executed by ONE thread, everything in registers
+// except the iteration-0 eigen step.  sums: 28 fp64 totals.  Updates tf (6), state; returns converged.
+// FAST_DEGENERACY: use the certificate above to skip cv::eigen when the system is provably well conditioned
+// (matP is then set to the identity; it is only ever read when isDegenerate is true).
+template <bool FAST_DEGENERACY>
+__device__ __forceinline__ bool lm_solve_dev(int iter, const double* sums, float* tf, LMDeviceState* st, float* scratchA /*36*/, float* scratchV /*36*/,
+                                             float* AtA_out, float* AtB_out, float* X_out, int* nsel_out) {
     float AtA[36], AtB[6], X[6];
-    int p = 0;
-    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { float v = (float)sums[p++]; AtA[i * 6 + j] = v; AtA[j * 6 + i] = v; }
+#pragma unroll
+    for (int p = 0; p < 21; ++p) { const float v = (float)sums[p]; AtA[prod_i(p) * 6 + prod_j(p)] = v; AtA[prod_j(p) * 6 + prod_i(p)] = v; }
+#pragma unroll
     for (int i = 0; i < 6; ++i) AtB[i] = (float)sums[21 + i];
     const int nsel = (int)(sums[27] + 0.5);
     if (nsel_out) *nsel_out = nsel;
-    if (AtA_out) for (int i = 0; i < 36; ++i) AtA_out[i] = AtA[i];
-    if (AtB_out) for (int i = 0; i < 6; ++i) AtB_out[i] = AtB[i];
-    if (X_out) for (int i = 0; i < 6; ++i) X_out[i] = 0.f;
+    if (AtA_out) {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) AtA_out[i] = AtA[i];
+    }
+    if (AtB_out) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) AtB_out[i] = AtB[i];
+    }
+    if (X_out) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) X_out[i] = 0.f;
+    }
     if (nsel < 50) return false;                                                    // :1178
     qr_solve6(AtA, AtB, X);                                                         // :1240
     if (iter == 0) {                                                                // :1242-1264
-        float W[6], V2[36], Vinv[36];
-        for (int i = 0; i < 36; ++i) scratchA[i] = AtA[i];
-        jacobi6(scratchA, W, scratchV);
-        for (int i = 0; i < 36; ++i) V2[i] = scratchV[i];
-        int deg = 0;
-        for (int i = 5; i >= 0; --i) {
-            if (W[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; deg = 1; }
-            else break;
+        if (FAST_DEGENERACY && certify_non_degenerate(AtA)) {
+            st->isDegenerate = 0;
+#pragma unroll
+            for (int i = 0; i < 36; ++i) st->matP[i] = (i % 7 == 0) ? 1.f : 0.f;
+        } else {
+            float tmpA[36];
+#pragma unroll
+            for (int i = 0; i < 36; ++i) tmpA[i] = AtA[i];
+            lm_degeneracy_dev(tmpA, st, scratchA, scratchV);
         }
-        for (int i = 0; i < 36; ++i) scratchA[i] = scratchV[i];
-        lu_invert6(scratchA, Vinv);
-        gemm6(Vinv, V2, st->matP);
-        st->isDegenerate = deg;
     }
-    if (st->isDegenerate) { float X2[6]; for (int i = 0; i < 6; ++i) X2[i] = X[i]; gemv6(st->matP, X2, X); }   // :1266-1271
+    if (st->isDegenerate) {                                                         // :1266-1271
+        float X2[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) X2[i] = X[i];
+        gemv6(st->matP, X2, X);
+    }
+#pragma unroll
     for (int i = 0; i < 6; ++i) tf[i] += X[i];                                      // :1273-1278
-    if (X_out) for (int i = 0; i < 6; ++i) X_out[i] = X[i];
+    if (X_out) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) X_out[i] = X[i];
+    }
     const float r2d = 57.29578f;
     double a0 = (double)(X[0] * r2d), a1 = (double)(X[1] * r2d), a2 = (double)(X[2] * r2d);
     double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
@@ -269,14 +365,44 @@ __global__ void __launch_bounds__(256) k_lm_hook(int iter, const float4* __restr
     __syncthreads();
     if (threadIdx.x == 0) {
         *counter = 0;
-        bool c = lm_solve_dev(iter, s_sum, tf6, st, s_A, s_V, AtA_out, AtB_out, X_out, nsel_out);
+        bool c = lm_solve_dev<false>(iter, s_sum, tf6, st, s_A, s_V, AtA_out, AtB_out, X_out, nsel_out);
         *conv_out = c ? 1 : 0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// scan2MapOptimization: one persistent cooperative kernel runs the whole ≤30-iteration loop.
+// scan2MapOptimization: ONE persistent kernel (cooperative launch = co-residency guarantee, one CTA per SM) runs the
+// whole ≤30-iteration loop with no host round trips.
+//
+// Per iteration and query (PG = 4 lanes per query):
+//   pointSel = T * pointOri
+//   candidates: iteration-0 style FULL search walks the 27 cells and, on the way, stores every map point within
+//               (1 + m) of the query position q0 (m = S2M_MARGIN) as the query's cached candidate list.
+//               While |pointSel - q0| <= m - eps, every point that can be within 1 m of pointSel is in that list
+//               (triangle inequality), so later iterations scan ONLY the ~15-point list — same exact 5-NN, same order.
+//   plane     : depends only on the ordered neighbour ids → cached with them; the 5x3 QR is redone only when they change.
+//   products  : the 28 normal-equation products are split over the PG lanes, accumulated in fp64.
+// Per iteration and CTA: fixed-tree block reduction → partial[cta][28] → arrive on a counter.  The LAST CTA to arrive
+// sums the partials in CTA order (deterministic whoever is last), solves the 6x6 system, publishes (pose, converged)
+// and releases an epoch flag the other CTAs spin on (bounded).  This replaces grid.sync + 148 redundant sums/solves.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int PG = 4;                       // lanes per query in the persistent solver
+constexpr int S2MP_BLOCK = 512;             // one CTA per SM: 148 x 128 queries = 18.9k queries per round
+constexpr int S2MP_QPB = S2MP_BLOCK / PG;
+constexpr int S2MP_WARPS = S2MP_BLOCK / 32;
+constexpr int CAND_CAP = 64;                // cached candidates per query (float4 each); overflow → always full search
+constexpr float S2M_MARGIN = 0.15f;
+constexpr int PPL = NPROD / PG;             // products per lane (28 / 4 = 7)
+
+struct QueryCache {                         // 64 B per query
+    float qx, qy, qz; int cnt;              // cached query position q0 and candidate count (-1: none, -2: overflow)
+    int nn[5]; int plane_ok;                // ordered neighbour ids of the cached plane (-1: none), planeValid
+    float pa, pb, pc, pd; int pad0, pad1;
+};
+static_assert(sizeof(QueryCache) == 64, "QueryCache must be 64 bytes");
+
+struct alignas(16) S2MResult { float tf[6]; int conv; int nsel; };
+
 struct S2MArgs {
     const float4* scan; Count n_scan;
     const unsigned* cell_start; const float4* gmap; GridDims g; Count m_map;
@@ -285,105 +411,359 @@ struct S2MArgs {
     double* partial;                 // [2][gridDim.x][NPROD]
     S2MTrace* trace;
     int max_iters; int force_all;
+    long long* dbg;                  // optional [S2M_MAX_ITERS][8] clock64 phase stamps of CTA 0 (nullptr = off)
+    QueryCache* qcache;              // [n_scan bound]
+    float4* cand;                    // [n_scan bound][CAND_CAP]
+    S2MResult* result;               // [2]
+    unsigned* arrive;                // arrival counter (zero between iterations)
+    unsigned* flag;                  // epoch flag
+    unsigned epoch_base;             // launch-unique: flag value for iteration k is epoch_base + k + 1
+    int* err_flag;
 };
 
-__global__ void __launch_bounds__(S2M_BLOCK) k_scan2map_persistent(S2MArgs a) {
-    cg::grid_group grid = cg::this_grid();
+template <int G>
+__device__ __forceinline__ void top5_merge(Top5& mine, Top5& res) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        float md = mine.d[0]; int mi = mine.oi[0], mp = mine.pos[0];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(FULL, md, o); int oi = __shfl_xor_sync(FULL, mi, o); int op = __shfl_xor_sync(FULL, mp, o);
+            if (less_di(od, oi, md, mi)) { md = od; mi = oi; mp = op; }
+        }
+        if (mine.d[0] == md && mine.oi[0] == mi) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mine.d[j] = mine.d[j + 1]; mine.oi[j] = mine.oi[j + 1]; mine.pos[j] = mine.pos[j + 1]; }
+            mine.d[4] = INFINITY; mine.oi[4] = 0x7fffffff; mine.pos[4] = -1;
+        }
+        res.d[r] = md; res.oi[r] = mi; res.pos[r] = mp;
+    }
+}
+
+// FULL search over the 27 cells with PG lanes; also builds the cached candidate list around q (= new q0).
+// Returns the number of cached candidates (or -2 on overflow).  `pos` of the results = index into gmap.
+__device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap,
+                                                   GridDims g, float4* __restrict__ clist, Top5& mine) {
+    const int gl = threadIdx.x & (PG - 1);
+    const unsigned gmask = ((1u << PG) - 1u) << (lane_id() & ~(PG - 1));
+    const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
+    const int x0 = (cx - 1) & (g.DX - 1), x1 = cx & (g.DX - 1), x2 = (cx + 1) & (g.DX - 1);
+    const bool contiguous = (x0 + 2 == x2);
+    const float r2c = (1.0f + S2M_MARGIN) * (1.0f + S2M_MARGIN);
+    int ncache = 0;                              // group-uniform running count of cached candidates
+    unsigned bs[9], P[10];
+    if (contiguous) {
+        P[0] = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
+            bs[r] = __ldg(cell_start + row + x0);
+            P[r + 1] = __ldg(cell_start + row + x2 + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < 9; ++r) P[r + 1] = P[r] + (P[r + 1] - bs[r]);
+    } else {                                     // wrapped x-run: 27 single-cell ranges, walked through the same flattened loop
+        P[0] = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) { bs[r] = 0; P[r + 1] = 0; }
+    }
+    if (contiguous) {
+        const unsigned T = P[9];
+        for (unsigned f0 = gl; f0 < T + (PG - 1) - ((T + PG - 1) % PG); f0 += PG * KNN_U) {    // group-uniform trip count
+            float4 p[KNN_U]; unsigned pos[KNN_U];
+#pragma unroll
+            for (int u = 0; u < KNN_U; ++u) {
+                const unsigned f = f0 + PG * u;
+                unsigned base = bs[0], pb = 0;
+#pragma unroll
+                for (int rr = 1; rr < 9; ++rr) if (f >= P[rr]) { base = bs[rr]; pb = P[rr]; }
+                pos[u] = base + (f - pb);
+                p[u] = f < T ? __ldg(gmap + pos[u]) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < KNN_U; ++u) {
+                float dx = q.x - p[u].x, dy = q.y - p[u].y, dz = q.z - p[u].z;
+                float d = dx * dx; d += dy * dy; d += dz * dz;      // FLANN L2_Simple op order, no FMA
+                const bool keep = d < r2c;
+                const unsigned km = __ballot_sync(gmask, keep);          // only this query's lanes vote (other groups may be elsewhere)
+                const int slot = ncache + __popc(km & ((1u << lane_id()) - 1u));
+                if (keep && slot < CAND_CAP) __stcg(clist + slot, p[u]);
+                if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), (int)pos[u]);
+                ncache += __popc(km);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int c27 = 0; c27 < 27; ++c27) {
+            const int r = c27 / 3, xi = c27 % 3;
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
+            const int xc = xi == 0 ? x0 : (xi == 1 ? x1 : x2);
+            const unsigned b = __ldg(cell_start + row + xc), e = __ldg(cell_start + row + xc + 1);
+            const unsigned Tn = e - b;
+            for (unsigned f0 = gl; f0 < Tn + (PG - 1) - ((Tn + PG - 1) % PG); f0 += PG) {
+                const bool in = f0 < Tn;
+                float4 pt = in ? __ldg(gmap + b + f0) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+                float dx = q.x - pt.x, dy2 = q.y - pt.y, dz2 = q.z - pt.z;
+                float d = dx * dx; d += dy2 * dy2; d += dz2 * dz2;
+                const bool keep = d < r2c;
+                const unsigned km = __ballot_sync(gmask, keep);
+                const int slot = ncache + __popc(km & ((1u << lane_id()) - 1u));
+                if (keep && slot < CAND_CAP) __stcg(clist + slot, pt);
+                if (d < 1.0f) top5_insert(mine, d, __float_as_int(pt.w), (int)(b + f0));
+                ncache += __popc(km);
+            }
+        }
+    }
+    return ncache <= CAND_CAP ? ncache : -2;
+}
+
+__global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a) {
     __shared__ float s_tf[6];
-    __shared__ float s_t[12];
-    __shared__ LMTrig s_trig;
-    __shared__ float s_rows[S2M_QPB][8];
-    __shared__ double s_red[S2M_BLOCK / 32][LIORF_G][4];
+    __shared__ float s_sc[6];                              // cos/sin of yaw, pitch, roll for this iteration
+    __shared__ float s_rows[S2MP_QPB][8];
+    __shared__ double s_red[S2MP_WARPS][NPROD];
     __shared__ double s_sum[NPROD];
     __shared__ float s_A[36], s_V[36];
     __shared__ LMDeviceState s_st;
-    __shared__ int s_conv;
+    __shared__ int s_conv, s_last;
 
     const int n = a.n_scan.get();
     const int m = a.m_map.get();
-    const int gl = threadIdx.x & (LIORF_G - 1);
-    const int qslot = threadIdx.x / LIORF_G;
-    int pi[4], pj[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) { const int p = gl + LIORF_G * t; pi[t] = prod_i(p < NPROD ? p : NPROD - 1); pj[t] = prod_j(p < NPROD ? p : NPROD - 1); }
+    const int gl = threadIdx.x & (PG - 1);
+    const int qslot = threadIdx.x / PG;
     if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
-    if (threadIdx.x == 0) s_st = *a.st;
     __syncthreads();
     // guards of scan2MapOptimization (:1297-1300): a map must exist (and hold >= 5 points for the 5-NN), n > 30
     const bool run = (m >= 5) && (n > 30);
     int iters_done = 0, converged = 0;
     if (run) {
+        // product indices owned by this lane: p in [PPL*gl, PPL*gl + PPL)
+        int pij[PPL];
+#pragma unroll
+        for (int t = 0; t < PPL; ++t) { const int p = gl * PPL + t; pij[t] = prod_i(p) | (prod_j(p) << 4); }
+        // iteration 0 never trusts the per-query caches (they belong to an earlier launch / another map)
         for (int iter = 0; iter < a.max_iters; ++iter) {
-            if (threadIdx.x == 0) {
-                get_transformation_dev(s_tf[3], s_tf[4], s_tf[5], s_tf[0], s_tf[1], s_tf[2], s_t);
-                s_trig = lm_trig(s_tf);
-            }
+            const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && iter < S2M_MAX_ITERS;
+            if (dbg) a.dbg[iter * 8 + 0] = clock64();
+            // six fp64-rounded trig values in parallel: (cos, sin) of yaw = tf[2], pitch = tf[1], roll = tf[0]
+            if (threadIdx.x < 6) { const float ang = s_tf[2 - (threadIdx.x >> 1)]; s_sc[threadIdx.x] = (threadIdx.x & 1) ? sin_f(ang) : cos_f(ang); }
             __syncthreads();
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int q0 = blockIdx.x * S2M_QPB; q0 < n; q0 += gridDim.x * S2M_QPB) {
-                const int q = q0 + qslot;
+            float s_t[12]; LMTrig s_trig;
+            {   // pcl::getTransformation from the shared trig values (same arithmetic as get_transformation_dev)
+                const float A = s_sc[0], B = s_sc[1], Cc = s_sc[2], D = s_sc[3], E = s_sc[4], F = s_sc[5], DE = D * E, DF = D * F;
+                s_t[0] = A * Cc; s_t[1] = A * DF - B * E; s_t[2] = B * F + A * DE; s_t[3] = s_tf[3];
+                s_t[4] = B * Cc; s_t[5] = A * E + B * DF; s_t[6] = B * DE - A * F; s_t[7] = s_tf[4];
+                s_t[8] = -D;     s_t[9] = Cc * F;         s_t[10] = Cc * E;        s_t[11] = s_tf[5];
+                s_trig.srx = B; s_trig.crx = A; s_trig.sry = D; s_trig.cry = Cc; s_trig.srz = F; s_trig.crz = E;   // :1170-1175
+            }
+            double acc[PPL];
+#pragma unroll
+            for (int t = 0; t < PPL; ++t) acc[t] = 0.0;
+            // query q is served by CTA (q mod gridDim) so that dense and sparse regions of the scan spread over all SMs
+            for (int j0 = 0; j0 * (int)gridDim.x < n; j0 += S2MP_QPB) {
+                const int q = (j0 + qslot) * (int)gridDim.x + (int)blockIdx.x;
                 const bool active = q < n;
+                const int qq = active ? q : 0;
+                QueryCache* qc = a.qcache + qq;
+                float4* clist = a.cand + (size_t)qq * CAND_CAP;
+                // every independent load of the cached path is issued up front (one L2 round trip): the point, the cache
+                // header (written by this same group earlier in this launch), the cached plane and the first candidates
                 float4 ori = active ? __ldg(a.scan + q) : make_float4(0, 0, 0, 0);
+                const float4 h0 = __ldcg(reinterpret_cast<const float4*>(qc));
+                const float4 h1 = __ldcg(reinterpret_cast<const float4*>(qc) + 1);              // nn[0..3]
+                const float4 h2 = __ldcg(reinterpret_cast<const float4*>(qc) + 2);              // nn[4], plane_ok, pa, pb
+                const float4 h3 = __ldcg(reinterpret_cast<const float4*>(qc) + 3);              // pc, pd
+                float4 pre[KNN_U];
+#pragma unroll
+                for (int u = 0; u < KNN_U; ++u) pre[u] = __ldcg(clist + gl + PG * u);           // speculative: slots exist even if unused
                 float4 sel = apply_affine_dev(s_t, ori);
-                Top5 nn; knn5_group(sel, a.cell_start, a.gmap, a.g, nn);
-                float4 coeff;
-                bool f = surf_point_dev(ori, sel, a.gmap, nn, coeff, nullptr) && active;
+                const int cnt = __float_as_int(h0.w);
+                float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
+                float moved = mx * mx; moved += my * my; moved += mz * mz;
+                const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
+                const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim;
+                Top5 mine; top5_init(mine);
+                int list_cnt;                                       // >= 0: results index the candidate list; -2: they index gmap... see below
+                if (use_cache) {
+                    for (int f0 = gl; f0 < cnt; f0 += PG * KNN_U) {
+                        float4 p[KNN_U];
+#pragma unroll
+                        for (int u = 0; u < KNN_U; ++u) {
+                            const int f = f0 + PG * u;
+                            p[u] = f0 == gl ? pre[u] : (f < cnt ? __ldcg(clist + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f));
+                            if (f >= cnt) p[u] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < KNN_U; ++u) {
+                            float dx = sel.x - p[u].x, dy = sel.y - p[u].y, dz = sel.z - p[u].z;
+                            float d = dx * dx; d += dy * dy; d += dz * dz;
+                            if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), f0 + PG * u);
+                        }
+                    }
+                    list_cnt = cnt;
+                } else if (active) {
+                    list_cnt = knn5_full_and_cache(sel, a.cell_start, a.gmap, a.g, clist, mine);
+                    if (gl == 0) { float4 h = make_float4(sel.x, sel.y, sel.z, __int_as_float(list_cnt)); __stcg(reinterpret_cast<float4*>(qc), h); }
+                } else list_cnt = -1;
+                Top5 nn; top5_merge<PG>(mine, nn);
+                // ---- plane: reuse when the ordered neighbour ids are unchanged ----
+                const bool have5 = active && nn.pos[4] != -1 && (double)nn.d[4] < 1.0;          // :1097
+                bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (have5) {
+                    const bool same = iter > 0 && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
+                                      __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
+                    float pa, pb, pc, pd; bool planeValid;
+                    if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
+                    else {
+                        float A[5][3];
+#pragma unroll
+                        const float4* nsrc = use_cache ? clist : a.gmap;      // results index the candidate list in cached mode, gmap otherwise
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) { float4 mpt = __ldcg(nsrc + nn.pos[j]); A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z; }
+                        float x[3];
+                        colpiv_qr_solve_5x3(A, x);                                               // :1104
+                        pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
+                        float ps = sqrtf(pa * pa + pb * pb + pc * pc);                           // :1111
+                        pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+                        planeValid = true;
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)                                              // :1115-1122
+                            if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
+                        if (gl == 0) {
+                            __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3])));
+                            __stcg(reinterpret_cast<float4*>(qc) + 2, make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb));
+                            __stcg(reinterpret_cast<float4*>(qc) + 3, make_float4(pc, pd, 0.f, 0.f));
+                        }
+                    }
+                    if (planeValid) {
+                        float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;                   // :1125
+                        float rr = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z));
+                        float sw = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)rr);         // :1127-1128
+                        coeff = make_float4(sw * pa, sw * pb, sw * pc, sw * pd2);                // :1130-1133
+                        f = (double)sw > 0.1;                                                    // :1135
+                    }
+                } else if (iter == 0 && active && gl == 0) {
+                    __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)));   // no cached plane
+                }
                 float v[8];
                 lm_row_dev(s_trig, ori, coeff, v); v[7] = 1.f;
                 __syncwarp();
-                if (gl < 8) s_rows[qslot][gl] = f ? (gl == 0 ? v[0] : gl == 1 ? v[1] : gl == 2 ? v[2] : gl == 3 ? v[3] : gl == 4 ? v[4] : gl == 5 ? v[5] : gl == 6 ? v[6] : v[7]) : 0.f;
+                {   // lanes 0..3 of the group publish two row entries each (zero row when the point is not selected)
+                    const float e0 = gl == 0 ? v[0] : gl == 1 ? v[1] : gl == 2 ? v[2] : v[3];
+                    const float e1 = gl == 0 ? v[4] : gl == 1 ? v[5] : gl == 2 ? v[6] : v[7];
+                    s_rows[qslot][gl] = f ? e0 : 0.f; s_rows[qslot][4 + gl] = f ? e1 : 0.f;
+                }
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int p = gl + LIORF_G * t;
-                    if (p < NPROD) acc[t] += (double)s_rows[qslot][pi[t]] * (double)s_rows[qslot][pj[t]];
-                }
+                for (int t = 0; t < PPL; ++t) acc[t] += (double)s_rows[qslot][pij[t] & 15] * (double)s_rows[qslot][pij[t] >> 4];
             }
-            // block reduction: lanes with equal gl across the 4 groups of a warp, then across warps
+            if (dbg) a.dbg[iter * 8 + 1] = clock64();
+            // block reduction (fixed tree): equal-gl lanes of the 8 groups of a warp, then across warps by warp 0
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < PPL; ++t) {
+                acc[t] += __shfl_xor_sync(FULL, acc[t], 4);
                 acc[t] += __shfl_xor_sync(FULL, acc[t], 8);
                 acc[t] += __shfl_xor_sync(FULL, acc[t], 16);
             }
-            if (lane_id() < LIORF_G) {
+            if (lane_id() < PG) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) s_red[warp_id()][gl][t] = acc[t];
+                for (int t = 0; t < PPL; ++t) s_red[warp_id()][gl * PPL + t] = acc[t];
             }
             __syncthreads();
             double* part = a.partial + (size_t)(iter & 1) * gridDim.x * NPROD;
             if (threadIdx.x < NPROD) {
-                const int p = threadIdx.x, pg = p % LIORF_G, pt = p / LIORF_G;
-                double s = 0;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-                for (int w = 0; w < S2M_BLOCK / 32; ++w) s += s_red[w][pg][pt];
-                part[(size_t)blockIdx.x * NPROD + p] = s;
-            }
-            grid.sync();
-            if (threadIdx.x < NPROD) {
-                const double* vp = part;
-                double s = 0;
-                for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(vp + (size_t)b * NPROD + threadIdx.x);
-                s_sum[threadIdx.x] = s;
+                for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
+                __stcg(part + (size_t)blockIdx.x * NPROD + threadIdx.x, (s0 + s1) + (s2 + s3));
+                __threadfence();
             }
             __syncthreads();
+            if (dbg) a.dbg[iter * 8 + 2] = clock64();
+            const unsigned epoch = a.epoch_base + (unsigned)iter + 1u;
             if (threadIdx.x == 0) {
-                int nsel;
-                bool c = lm_solve_dev(iter, s_sum, s_tf, &s_st, s_A, s_V, nullptr, nullptr, nullptr, &nsel);
-                s_conv = c ? 1 : 0;
-                if (blockIdx.x == 0 && a.trace && iter < S2M_MAX_ITERS) {
-                    for (int k = 0; k < 6; ++k) a.trace->pose[iter][k] = s_tf[k];
-                    a.trace->nsel[iter] = nsel;
-                }
+                const unsigned t = atomicAdd(a.arrive, 1u);
+                s_last = (t == gridDim.x - 1) ? 1 : 0;
             }
             __syncthreads();
+            S2MResult* res = a.result + (iter & 1);
+            if (s_last) {
+                if (dbg) a.dbg[iter * 8 + 3] = clock64();
+                const long long lc0 = clock64();
+                __threadfence();
+                {   // partial sums in CTA order: warp w takes CTAs w, w + W, ...; lane = component; then warps in order
+                    const int w = warp_id(), l = lane_id();
+                    double s0 = 0;
+                    if (l < NPROD) {
+                        double vv[10];
+#pragma unroll
+                        for (int k2 = 0; k2 < 10; ++k2) { const int b = w + k2 * S2MP_WARPS; vv[k2] = b < (int)gridDim.x ? __ldcg(part + (size_t)b * NPROD + l) : 0.0; }
+#pragma unroll
+                        for (int k2 = 0; k2 < 10; ++k2) s0 += vv[k2];
+                        for (int b = w + 10 * S2MP_WARPS; b < (int)gridDim.x; b += S2MP_WARPS) s0 += __ldcg(part + (size_t)b * NPROD + l);
+                        s_red[w][l] = s0;
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x < NPROD) {
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                    for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
+                    s_sum[threadIdx.x] = (s0 + s1) + (s2 + s3);
+                }
+                if (threadIdx.x >= 64 && threadIdx.x < 64 + 37)      // persistent LM state (written by whichever CTA solved iteration 0)
+                    reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
+                __syncthreads();
+                if (dbg) a.dbg[iter * 8 + 4] = clock64();
+                const long long lc1 = clock64();
+                if (threadIdx.x == 0) {
+                    int nsel;
+                    float tfn[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) tfn[k] = s_tf[k];
+                    bool c = lm_solve_dev<true>(iter, s_sum, tfn, &s_st, s_A, s_V, nullptr, nullptr, nullptr, &nsel);
+                    if (iter == 0) *a.st = s_st;
+                    {   // result = 2 x 16-byte stores
+                        float4* r4 = reinterpret_cast<float4*>(res);
+                        __stcg(r4, make_float4(tfn[0], tfn[1], tfn[2], tfn[3]));
+                        __stcg(r4 + 1, make_float4(tfn[4], tfn[5], __int_as_float(c ? 1 : 0), __int_as_float(nsel)));
+                    }
+                    *a.arrive = 0u;                                  // nobody arrives again before the flag is released
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flag), "r"(epoch) : "memory");
+                    // off the critical path: the other CTAs are already running the next iteration
+                    if (a.dbg && iter < S2M_MAX_ITERS) { a.dbg[iter * 8 + 6] = lc1 - lc0; a.dbg[iter * 8 + 7] = clock64() - lc1; }
+                    if (a.trace && iter < S2M_MAX_ITERS) {
+                        for (int k = 0; k < 6; ++k) a.trace->pose[iter][k] = tfn[k];
+                        a.trace->nsel[iter] = nsel;
+                        a.trace->degenerate = s_st.isDegenerate;
+                    }
+                }
+            } else {
+                if (dbg) a.dbg[iter * 8 + 3] = clock64();
+                if (threadIdx.x == 0) {
+                    unsigned v, spins = 0;
+                    while (true) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag) : "memory");
+                        if (v == epoch) break;
+                        if (++spins > (1u << 26)) { atomicExch(a.err_flag, 2); break; }
+                    }
+                }
+                if (dbg) a.dbg[iter * 8 + 4] = clock64();
+            }
+            __syncthreads();
+            if (threadIdx.x < 6) s_tf[threadIdx.x] = __ldcg(&res->tf[threadIdx.x]);
+            if (threadIdx.x == 32) s_conv = __ldcg(&res->conv);
+            __syncthreads();
+            if (dbg) a.dbg[iter * 8 + 5] = clock64();
             iters_done = iter + 1;
             if (s_conv) { converged = 1; if (!a.force_all) break; }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int k = 0; k < 6; ++k) a.tf6[k] = s_tf[k];
-        *a.st = s_st;
-        if (a.trace) { a.trace->iters = iters_done; a.trace->converged = converged; a.trace->degenerate = s_st.isDegenerate; a.trace->ran = run ? 1 : 0; }
+        if (a.trace) { a.trace->iters = iters_done; a.trace->converged = converged; a.trace->ran = run ? 1 : 0; if (!run) a.trace->degenerate = __ldcg(&a.st->isDegenerate); }
     }
 }
 
