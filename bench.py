@@ -93,6 +93,7 @@ class GpuPipeline:
     def __init__(self, seq, device):
         import liorf_b200
         self.ctx = liorf_b200.Context(device=device, **{k: seq.filters[k] for k in ("N_SCAN", "downsampleRate", "point_filter_num", "lidarMinRange", "lidarMaxRange")})
+        self.ctx.reserve(131072, 4 << 20, 16 << 20, 4096)         # 180 GB of HBM: size once, never allocate inside a frame
         self.seq = seq
         self.prev = None
         self.stats = dict(frames=0, iters=0, knn_queries=0, alg_bytes_s2m=0, keyframes=0, n_ds=0, m_ds=0, loops=0)

@@ -52,6 +52,8 @@ typedef struct {
 void liorf_default_params(liorf_params* p);                      /* config/kitti.yaml values */
 int  liorf_create(const liorf_params* p, liorf_ctx** out);
 void liorf_destroy(liorf_ctx* ctx);
+/* pre-size all device work buffers (no allocation, hence no device-wide sync, inside later calls) */
+int  liorf_reserve(liorf_ctx* ctx, int n_scan_max, int m_raw_max, int n_keyframe_points_max, int sc_entries_max);
 int  liorf_sync(liorf_ctx* ctx);                                 /* cudaStreamSynchronize + sticky device error flags */
 void* liorf_stream(liorf_ctx* ctx);                              /* the context's cudaStream_t (for CUDA-event timing) */
 const char* liorf_version(void);

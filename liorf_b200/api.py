@@ -83,6 +83,9 @@ class Context:
         except Exception:
             pass
 
+    def reserve(self, n_scan_max, m_raw_max, n_keyframe_points_max=0, sc_entries_max=0):
+        _chk(self.lib.liorf_reserve(self.h, C.c_int(n_scan_max), C.c_int(m_raw_max), C.c_int(n_keyframe_points_max), C.c_int(sc_entries_max)), "liorf_reserve")
+
     def sync(self):
         _chk(self.lib.liorf_sync(self.h), "liorf_sync")
 

@@ -123,6 +123,14 @@ static int read_counts(liorf_ctx* c) {
     return LIORF_OK;
 }
 
+static int sc_reserve(liorf_ctx* c, int n) {
+    int rc;
+    if ((rc = c->sc_desc.reserve((size_t)n * SC_DESC, c->stream, true)) || (rc = c->sc_sk.reserve((size_t)n * SC_SECTOR, c->stream, true)) ||
+        (rc = c->sc_cn.reserve((size_t)n * SC_SECTOR, c->stream, true)) || (rc = c->sc_keys.reserve((size_t)n * SC_RING, c->stream, true))) return rc;
+    return LIORF_OK;
+}
+
+
 extern "C" {
 
 const char* liorf_version(void) { return "liorf_b200 0.1 (sm_100a)"; }
@@ -232,8 +240,11 @@ void* liorf_stream(liorf_ctx* c) { return c ? (void*)c->stream : nullptr; }
 static int project_common(liorf_ctx* c, const RawPoint* d_raw, int n, double t0, const double* imu_time, const double* rx, const double* ry,
                           const double* rz, int imu_ptr, int deskew_enabled, int* d_kept_index) {
     int rc;
-    if ((rc = c->scan.reserve(n > 0 ? n : 1))) return rc;
-    c->n_scan_bound = n; c->h_n_scan = -1; c->h_n_ds = -1;
+    // `i % point_filter_num == 0` is necessary for a point to survive (:591) ⇒ a host-side bound on the kept count
+    const int kept_bound = n > 0 ? (n + c->P.point_filter_num - 1) / c->P.point_filter_num : 0;
+    if ((rc = c->scan.reserve(kept_bound > 0 ? kept_bound : 1))) return rc;
+    if ((rc = c->dk.kept.reserve(kept_bound > 0 ? kept_bound : 1))) return rc;
+    c->n_scan_bound = kept_bound; c->h_n_scan = -1; c->h_n_ds = -1;
     if (n <= 0) { CUDA_TRY(cudaMemsetAsync(c->d_counts + C_N_SCAN, 0, sizeof(int), c->stream)); c->h_n_scan = 0; return LIORF_OK; }
     ImuTable T{nullptr, nullptr, nullptr, nullptr, 0};
     if (deskew_enabled) {
@@ -249,11 +260,12 @@ static int project_common(liorf_ctx* c, const RawPoint* d_raw, int n, double t0,
         T = ImuTable{c->dk.imu.p, c->dk.imu.p + rows, c->dk.imu.p + 2 * rows, c->dk.imu.p + 3 * rows, imu_ptr};
     }
     DeskewParams DP{c->P.lidarMinRange, c->P.lidarMaxRange, c->P.N_SCAN, c->P.downsampleRate, c->P.point_filter_num};
-    ProfScope ps(c, SEC_DESKEW); c->launches += 2;
+    ProfScope ps(c, SEC_DESKEW); c->launches += 3;
     k_first_kept<<<1, 1024, 0, c->stream>>>(d_raw, n, DP, t0, T, deskew_enabled, c->dk.start_inv, c->dk.first_kept);
-    rc = launch_scan(Count::of_host(n), DeskewLoad{d_raw, DP}, DeskewStore{d_raw, t0, T, deskew_enabled, c->dk.start_inv, c->scan.p, d_kept_index},
-                     c->dk.scan, (unsigned*)(c->d_counts + C_N_SCAN), c->stream);
+    int* kept = d_kept_index ? d_kept_index : c->dk.kept.p;
+    rc = launch_scan(Count::of_host(n), DeskewLoad{d_raw, DP}, DeskewStore{kept}, c->dk.scan, (unsigned*)(c->d_counts + C_N_SCAN), c->stream);
     if (rc) return rc;
+    k_deskew_points<<<(kept_bound + 127) / 128, 128, 0, c->stream>>>(d_raw, kept, c->d_counts + C_N_SCAN, t0, T, deskew_enabled, c->dk.start_inv, c->scan.p);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
 }
@@ -636,13 +648,6 @@ int liorf_set_lm_state(liorf_ctx* c, int deg, const float matP[36]) {
 }
 
 // ------------------------------------------------------------------------------------------------ ScanContext
-static int sc_reserve(liorf_ctx* c, int n) {
-    int rc;
-    if ((rc = c->sc_desc.reserve((size_t)n * SC_DESC, c->stream, true)) || (rc = c->sc_sk.reserve((size_t)n * SC_SECTOR, c->stream, true)) ||
-        (rc = c->sc_cn.reserve((size_t)n * SC_SECTOR, c->stream, true)) || (rc = c->sc_keys.reserve((size_t)n * SC_RING, c->stream, true))) return rc;
-    return LIORF_OK;
-}
-
 int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
@@ -814,6 +819,34 @@ int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_
     if (min_dist) *min_dist = md;
     if (cand3) { cand3[0] = cand[0]; cand3[1] = cand[1]; cand3[2] = cand[2]; }
     *yaw_diff_rad = (float)((float)(nn_align * (360.0 / 60.0)) * M_PI / 180.0);   // deg2rad(float) (:17-20, :339)
+    return LIORF_OK;
+}
+
+// Pre-sizes every work buffer so that no call allocates afterwards (allocation = cudaMalloc/cudaFree = device sync).
+int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_points_max, int sc_entries_max) {
+    if (!c || n_scan_max < 0 || m_raw_max < 0) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int rc;
+    const size_t n = (size_t)(n_scan_max > 0 ? n_scan_max : 1), m = (size_t)(m_raw_max > 0 ? m_raw_max : 1), big = n > m ? n : m;
+    if ((rc = c->scan.reserve(n)) || (rc = c->scan_ds.reserve(n)) || (rc = c->dk.raw.reserve(n)) || (rc = c->dk.kept.reserve(n)) ||
+        (rc = c->membership.reserve(big)) || (rc = c->out_keys.reserve(big)) ||
+        (rc = c->map_raw.reserve(m)) || (rc = c->map_ds.reserve(m)) || (rc = c->grid.sorted.reserve(m)) ||
+        (rc = c->vg.keys.reserve(big)) || (rc = c->vg.seg_start.reserve(big + 1)) || (rc = c->vg.partial.reserve((size_t)kNumSMs * 6)) ||
+        (rc = c->vg.sort.keys_alt.reserve(big)) || (rc = c->vg.sort.vals_a.reserve(big)) || (rc = c->vg.sort.vals_b.reserve(big)) ||
+        (rc = c->vg.sort.hist.reserve(4 * RADIX)) ||
+        (rc = reserve_zeroed(c->vg.sort.status, ((big + SORT_TILE - 1) / SORT_TILE) * RADIX, c->stream)) ||
+        (rc = reserve_zeroed(c->vg.scan.status, (big + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
+        (rc = reserve_zeroed(c->dk.scan.status, (n + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
+        (rc = c->qcache.reserve(n)) || (rc = c->cand.reserve(n * CAND_CAP)) || (rc = c->d_sel.reserve(4096))) return rc;
+    if (n_keyframe_points_max > 0 && (rc = c->kf_points.reserve((size_t)n_keyframe_points_max, c->stream, true))) return rc;
+    if (sc_entries_max > 0 && (rc = sc_reserve(c, sc_entries_max))) return rc;
+    if (c->h_sel_cap < 4096) {
+        if (c->h_sel) cudaFreeHost(c->h_sel);
+        c->h_sel_cap = 4096;
+        CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return LIORF_OK;
 }
 

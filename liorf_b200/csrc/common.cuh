@@ -36,7 +36,7 @@ struct DevBuf {
     int reserve(size_t n, cudaStream_t s = nullptr, bool keep = false) {
         if (n <= cap) return LIORF_OK;
         size_t ncap = cap ? cap : 1024;
-        while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+        while (ncap < n) ncap = 2 * ncap + 1024;          // doubling: growth (a cudaMalloc + cudaFree sync) must stay rare
         T* np_ = nullptr;
         CUDA_TRY(cudaMalloc(&np_, ncap * sizeof(T)));
         if (keep && p && cap) CUDA_TRY(cudaMemcpyAsync(np_, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));

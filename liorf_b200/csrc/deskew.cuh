@@ -110,29 +110,36 @@ struct DeskewLoad {
     const RawPoint* raw; DeskewParams P;
     __device__ __forceinline__ unsigned operator()(int i) const { RawPoint r = load_raw(raw, i); return keep_point(r, i, P) ? 1u : 0u; }
 };
-struct DeskewStore {
-    const RawPoint* raw; double timeScanCur; ImuTable T; int deskew_enabled; const float* start_inv; float4* out; int* kept_index;
-    __device__ __forceinline__ void operator()(int i, unsigned v, unsigned excl) const {
-        if (!v) return;
-        RawPoint r = load_raw(raw, i);
-        float4 p = make_float4(r.x, r.y, r.z, r.intensity);
-        if (deskew_enabled) {                                                          // deskewPoint :536-566
-            float rx, ry, rz; find_rotation_dev(timeScanCur + (double)r.time, T, rx, ry, rz);
-            float tf[12]; get_transformation_dev(0.f, 0.f, 0.f, rx, ry, rz, tf);
-            float si[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) si[k] = __ldg(start_inv + k);
-            float bt[12]; affine_mul_dev(si, tf, bt);
-            p = apply_affine_dev(bt, p);
-        }
-        out[excl] = p;
-        if (kept_index) kept_index[excl] = i;
-    }
+struct DeskewStore {                          // compaction only: the ordered list of kept raw indices
+    int* kept_index;
+    __device__ __forceinline__ void operator()(int i, unsigned v, unsigned excl) const { if (v) kept_index[excl] = i; }
 };
+
+// one thread per KEPT point: deskewPoint (:536-566) and the ordered store
+__global__ void __launch_bounds__(128) k_deskew_points(const RawPoint* __restrict__ raw, const int* __restrict__ kept_index, const int* __restrict__ n_kept,
+                                                      double timeScanCur, ImuTable T, int deskew_enabled, const float* __restrict__ start_inv,
+                                                      float4* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *n_kept) return;
+    const int i = kept_index[k];
+    RawPoint r = load_raw(raw, i);
+    float4 p = make_float4(r.x, r.y, r.z, r.intensity);
+    if (deskew_enabled) {
+        float rx, ry, rz; find_rotation_dev(timeScanCur + (double)r.time, T, rx, ry, rz);
+        float tf[12]; get_transformation_dev(0.f, 0.f, 0.f, rx, ry, rz, tf);
+        float si[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) si[q] = __ldg(start_inv + q);
+        float bt[12]; affine_mul_dev(si, tf, bt);
+        p = apply_affine_dev(bt, p);
+    }
+    out[k] = p;
+}
 
 struct DeskewWork {
     DevBuf<RawPoint> raw;           // staging for host input
     DevBuf<double> imu;             // 4 x rows (time, rx, ry, rz)
+    DevBuf<int> kept;               // ordered raw indices of the kept points
     float* start_inv = nullptr;     // 12 floats (device)
     int* first_kept = nullptr;
     ScanWork scan;

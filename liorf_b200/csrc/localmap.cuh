@@ -61,7 +61,7 @@ inline int build_map_grid(const float4* map, Count cnt, MapGrid& G, cudaStream_t
     if ((rc = G.sorted.reserve(cnt.bound > 0 ? cnt.bound : 1))) return rc;
     if (!G.counts_clean) { CUDA_TRY(cudaMemsetAsync(G.counts.p, 0, (size_t)nc * sizeof(unsigned), s)); G.counts_clean = true; }
     if (cnt.bound > 0) k_grid_count<<<(cnt.bound + 255) / 256, 256, 0, s>>>(map, cnt, G.dims, G.counts.p);
-    if ((rc = launch_scan(Count::of_host(nc), GridScanLoad{G.counts.p}, GridScanStore{G.cell_start.p, nc}, G.scan, nullptr, s))) return rc;
+    if ((rc = launch_scan<512, 16>(Count::of_host(nc), GridScanLoad{G.counts.p}, GridScanStore{G.cell_start.p, nc}, G.scan, nullptr, s))) return rc;
     if (cnt.bound > 0) k_grid_scatter<<<(cnt.bound + 255) / 256, 256, 0, s>>>(map, cnt, G.dims, G.counts.p, G.cell_start.p, G.sorted.p);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;

@@ -159,9 +159,10 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* smem_w
 
 // Generic single-pass exclusive scan. LoadOp(i) -> unsigned value of element i; StoreOp(i, value, exclusive_prefix).
 // total_out (optional) receives the grand total.
-template <class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_lookback(Count cnt, LoadOp load, StoreOp store, int* ticket, unsigned long long* status,
-                                                             unsigned epoch, int* err_flag, unsigned* total_out) {
+template <int BLOCK, int IPT, class LoadOp, class StoreOp>
+__global__ void __launch_bounds__(BLOCK) k_scan_lookback(Count cnt, LoadOp load, StoreOp store, int* ticket, unsigned long long* status,
+                                                        unsigned epoch, int* err_flag, unsigned* total_out) {
+    constexpr int SCAN_BLOCK = BLOCK, SCAN_IPT = IPT, SCAN_TILE = BLOCK * IPT;
     __shared__ int s_tile;
     __shared__ unsigned s_warp[SCAN_BLOCK / 32 + 1];
     __shared__ unsigned s_prefix;
@@ -189,13 +190,14 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_lookback(Count cnt, LoadOp 
     if (total_out && tile == ntiles - 1 && threadIdx.x == SCAN_BLOCK - 1) *total_out = run;
 }
 
-template <class LoadOp, class StoreOp>
+template <int BLOCK = SCAN_BLOCK, int IPT = SCAN_IPT, class LoadOp, class StoreOp>
 inline int launch_scan(Count n, LoadOp load, StoreOp store, ScanWork& w, unsigned* total_out, cudaStream_t s) {
     if (n.bound <= 0) { if (total_out) CUDA_TRY(cudaMemsetAsync(total_out, 0, sizeof(unsigned), s)); return LIORF_OK; }
-    int ntiles = (n.bound + SCAN_TILE - 1) / SCAN_TILE;
+    constexpr int TILE = BLOCK * IPT;
+    int ntiles = (n.bound + TILE - 1) / TILE;
     int rc = reserve_zeroed(w.status, ntiles, s); if (rc) return rc;
     ++w.epoch;
-    k_scan_lookback<<<ntiles, SCAN_BLOCK, 0, s>>>(n, load, store, w.ticket, w.status.p, w.epoch, w.err_flag, total_out);
+    k_scan_lookback<BLOCK, IPT><<<ntiles, BLOCK, 0, s>>>(n, load, store, w.ticket, w.status.p, w.epoch, w.err_flag, total_out);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
 }

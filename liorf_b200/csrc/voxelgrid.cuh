@@ -61,11 +61,19 @@ __global__ void __launch_bounds__(VG_MM_BLOCK) k_vg_minmax(const float4* __restr
         s_last = (t == (int)gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        *counter = 0;
+    if (!s_last) return;
+    if (threadIdx.x < 32) {                      // last block: warp 0 folds the per-block partials (min/max are order independent)
         __threadfence();
-        const volatile float* vp = partial;
-        for (int b = 0; b < (int)gridDim.x; ++b) for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], vp[b * 6 + a]); mx[a] = fmaxf(mx[a], vp[b * 6 + 3 + a]); }
+        for (int a = 0; a < 3; ++a) { mn[a] = INFINITY; mx[a] = -INFINITY; }
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32)
+            for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], __ldcg(partial + b * 6 + a)); mx[a] = fmaxf(mx[a], __ldcg(partial + b * 6 + 3 + a)); }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o)); mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o)); }
+    }
+    if (threadIdx.x == 0) {
+        *counter = 0;
         VoxMeta m;
         m.n = n;
         m.inv = 1.0f / leaf;
@@ -119,9 +127,19 @@ __global__ void __launch_bounds__(128) k_vg_centroid(const float4* __restrict__ 
     if (s >= nseg) return;
     unsigned b = seg_start[s], e = seg_start[s + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    for (unsigned k = b; k < e; ++k) {
+    unsigned k = b;
+    for (; k + 4 <= e; k += 4) {                  // gathers issued four at a time; the adds stay in ascending input index
+        unsigned i0 = sorted_idx[k], i1 = sorted_idx[k + 1], i2 = sorted_idx[k + 2], i3 = sorted_idx[k + 3];
+        float4 p0 = __ldg(pts + i0), p1 = __ldg(pts + i1), p2 = __ldg(pts + i2), p3 = __ldg(pts + i3);
+        sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+        sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+        sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+        sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+        if (membership) { membership[i0] = s; membership[i1] = s; membership[i2] = s; membership[i3] = s; }
+    }
+    for (; k < e; ++k) {
         unsigned idx = sorted_idx[k];
-        float4 p = pts[idx];
+        float4 p = __ldg(pts + idx);
         sx += p.x; sy += p.y; sz += p.z; si += p.w;
         if (membership) membership[idx] = s;
     }
@@ -136,7 +154,7 @@ inline int voxel_grid_device(const float4* in, Count cnt, float leaf, float4* ou
     const int nb = cnt.bound;
     if (nb <= 0) { CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(int), s)); return LIORF_OK; }
     int rc;
-    int mmb = (nb + VG_MM_BLOCK * 8 - 1) / (VG_MM_BLOCK * 8); if (mmb > 2 * kNumSMs) mmb = 2 * kNumSMs;
+    int mmb = (nb + VG_MM_BLOCK * 8 - 1) / (VG_MM_BLOCK * 8); if (mmb > kNumSMs) mmb = kNumSMs;
     if ((rc = w.partial.reserve((size_t)mmb * 6))) return rc;
     if ((rc = w.keys.reserve(nb))) return rc;
     if ((rc = w.seg_start.reserve((size_t)nb + 1))) return rc;
