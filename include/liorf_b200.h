@@ -108,6 +108,10 @@ int liorf_extract_nearby(liorf_ctx* ctx, double time_laser_info_cur, float surro
 int liorf_save_frame(liorf_ctx* ctx, const float pose6[6], float adding_dist_threshold, float adding_angle_threshold);
 /* the clamps of transformUpdate (src/mapOptmization.cpp:1348-1350) */
 void liorf_transform_update_clamp(float pose6_inout[6], float rotation_tollerance, float z_tollerance);
+/* context-free forms (host only, usable without a GPU): poses6 = n x (roll,pitch,yaw,x,y,z), times = n stamps */
+int liorf_host_extract_nearby(const float* poses6, const double* times, int n, double time_laser_info_cur, float search_radius,
+                              float keyframe_density, int* ids, int cap, int* n_ids);
+int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose6[6], float adding_dist_threshold, float adding_angle_threshold);
 
 /* replaces mapOptimization::scan2MapOptimization() (src/mapOptmization.cpp:1295) up to, not including, transformUpdate:
  * ≤ max_iters × {surfOptimization, combineOptimizationCoeffs, LMOptimization} in one persistent kernel.

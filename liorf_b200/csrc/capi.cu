@@ -476,6 +476,23 @@ int liorf_save_frame(liorf_ctx* c, const float pose6[6], float dist_thr, float a
     return liorf_host::save_frame(&last, pose6, dist_thr, ang_thr) ? 1 : 0;
 }
 void liorf_transform_update_clamp(float pose6[6], float rot_tol, float z_tol) { liorf_host::transform_update_clamp(pose6, rot_tol, z_tol); }
+// context-free forms of the same host logic (poses: n x 6 floats (roll,pitch,yaw,x,y,z), times: n doubles)
+int liorf_host_extract_nearby(const float* poses6, const double* times, int n, double time_cur, float radius, float density, int* ids, int cap, int* n_ids) {
+    if (n < 0 || !n_ids || (n > 0 && (!poses6 || !times)) || !(density > 0.f)) return LIORF_ERR_ARG;
+    std::vector<liorf_host::KeyPose> kp(n);
+    for (int i = 0; i < n; ++i) kp[i] = liorf_host::KeyPose{poses6[6 * i], poses6[6 * i + 1], poses6[6 * i + 2], poses6[6 * i + 3], poses6[6 * i + 4], poses6[6 * i + 5], times[i]};
+    std::vector<int> sel = liorf_host::extract_nearby(kp, time_cur, radius, density);
+    *n_ids = (int)sel.size();
+    if ((int)sel.size() > cap || !ids) return LIORF_ERR_ARG;
+    std::memcpy(ids, sel.data(), sel.size() * sizeof(int));
+    return LIORF_OK;
+}
+int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose6[6], float dist_thr, float ang_thr) {
+    if (!pose6) return LIORF_ERR_ARG;
+    if (!last_pose6) return 1;
+    liorf_host::KeyPose last{last_pose6[0], last_pose6[1], last_pose6[2], last_pose6[3], last_pose6[4], last_pose6[5], 0.0};
+    return liorf_host::save_frame(&last, pose6, dist_thr, ang_thr) ? 1 : 0;
+}
 
 int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
     if (!c || m < 0 || (m > 0 && !map_ds)) return LIORF_ERR_ARG;
