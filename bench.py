@@ -217,46 +217,54 @@ class CpuPipeline:
 
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle reasons sampled DURING the timed region by an in-process NVML thread (every ~2 ms: the timed
+    region of the default run is only ~50-100 ms, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.idx = gpu_index
-        self.p = None
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = False
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[gpu_index]) if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        if self.nv is None:
+            return
+        import threading
+        self._stop = False
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.p is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None, reasons=sorted(reasons), samples=len(sm))
+        if self.nv is None or self._thr is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable"], samples=0)
+        self._stop = True
+        self._thr.join(timeout=2)
+        sm = self.samples
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(sm))
 
 
 def load_peaks():
@@ -276,73 +284,55 @@ def dist_env():
 
 # ----------------------------------------------------------------------------------------------------------------
 def bench_sc(ctx_device, rank, world, K, Q, reps, dist):
-    """config 5: K-entry database sharded by contiguous ranges over the ranks; Q replicated queries per step."""
+    """config 5: K-entry database sharded by contiguous ranges over the ranks; Q replicated queries per step.
+    Orchestration = liorf_b200/sc_sharded.py (two tiny all_gathers per batch when world > 1)."""
     import torch
     import liorf_b200
+    from liorf_b200.sc_sharded import GpuOps, ShardedScanContextSearch
     from tools import synth
     kloc = K // world
     off = rank * kloc
     ctx = liorf_b200.Context(device=ctx_device)
+    ctx.reserve(1024, 1024, 0, kloc)
     CH = 10000
     for s in range(0, kloc, CH):
         ctx.scAddDescriptors(synth.sc_descriptors(min(CH, kloc - s), first=off + s))
-    # queries come from a small replicated sample of the global database (identical on every rank)
+    # queries: column-shifted noisy copies of entries of the first 2000 global rows (+ fresh ones); identical on every rank
     sample = synth.sc_descriptors(min(K, 2000), first=0)
     qd, src, shift = synth.sc_queries(sample, Q)
-    dev = torch.device(f"cuda:{ctx_device}")
-    import ctypes as C
-    lib = ctx.lib
-    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
-    with torch.cuda.stream(ext):
-        d_q = torch.from_numpy(qd).to(dev)
-        qkeys = torch.empty((Q, 20), dtype=torch.float32, device=dev); qsk = torch.empty((Q, 60), dtype=torch.float64, device=dev); qcn = torch.empty_like(qsk)
-        ld = torch.empty((Q, 3), dtype=torch.float32, device=dev); li = torch.empty((Q, 3), dtype=torch.int32, device=dev)
-        gd = torch.empty((world, Q, 3), dtype=torch.float32, device=dev); gi = torch.empty((world, Q, 3), dtype=torch.int32, device=dev)
-        md = torch.empty_like(ld); mi = torch.empty_like(li)
-        pd = torch.empty((Q, 3), dtype=torch.float64, device=dev); ps = torch.empty((Q, 3), dtype=torch.int32, device=dev)
-        gpd = torch.empty((world, Q, 3), dtype=torch.float64, device=dev); gps = torch.empty((world, Q, 3), dtype=torch.int32, device=dev)
-        loop = torch.empty(Q, dtype=torch.int32, device=dev); sh = torch.empty(Q, dtype=torch.int32, device=dev); dd = torch.empty(Q, dtype=torch.float64, device=dev)
-    vp = lambda t: C.c_void_p(t.data_ptr())
+    ops = GpuOps(ctx, off, torch)
+    search = ShardedScanContextSearch(ops, rank, world, dist)
+    dev = ops.dev
 
     def one():
-        with torch.cuda.stream(ext):
-            lib.liorf_sc_prepare_queries_dev(ctx.h, vp(d_q), Q, vp(qkeys), vp(qsk), vp(qcn))
-            lib.liorf_sc_knn_batch_dev(ctx.h, vp(qkeys), Q, off, vp(ld), vp(li))
-            if world > 1:
-                dist.all_gather_into_tensor(gd, ld); dist.all_gather_into_tensor(gi, li)
-                lib.liorf_sc_merge_top3_dev(ctx.h, vp(gd), vp(gi), world, Q, vp(md), vp(mi))
-                cand = mi
-            else:
-                cand = li
-            pd.fill_(float("inf")); ps.zero_()
-            lib.liorf_sc_distance_batch_dev(ctx.h, vp(d_q), vp(qsk), vp(qcn), vp(cand), Q, off, vp(pd), vp(ps))
-            if world > 1:                                           # owner-computes: every pair is finite on exactly one rank
-                dist.all_gather_into_tensor(gpd, pd); dist.all_gather_into_tensor(gps, ps)
-                best = gpd.argmin(dim=0, keepdim=True)
-                pd2 = gpd.gather(0, best)[0]; ps2 = gps.gather(0, best)[0]
-            else:
-                pd2, ps2 = pd, ps
-            lib.liorf_sc_decide_dev(ctx.h, vp(pd2.contiguous()), vp(ps2.contiguous()), vp(cand), Q, vp(loop), vp(sh), vp(dd))
+        with torch.cuda.stream(ops.stream):
+            q = ops.prepare_dev(d_q)
+            return search.query(q)
+    with torch.cuda.stream(ops.stream):
+        d_q = torch.from_numpy(qd).to(dev)
     for _ in range(3):
-        one()
+        loop, sh, dd, cand = one()
     ctx.sync()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ext):
+    with torch.cuda.stream(ops.stream):
         e0.record()
     for _ in range(reps):
-        one()
-    with torch.cuda.stream(ext):
+        loop, sh, dd, cand = one()
+    with torch.cuda.stream(ops.stream):
         e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    found = int(((loop.cpu().numpy() == src) & (src >= 0)).sum()) if K <= 2000 * world or True else 0
+    tm = ctx.getTiming() if False else None
+    lp = loop.cpu().numpy(); shn = sh.cpu().numpy()
+    ok = (lp == src) & (src >= 0)
     res = dict(K=K, Q=Q, shards=world, ms_per_batch=ms / reps, queries_per_s=Q * reps / (ms * 1e-3),
-               planted_loops_found=int(((loop.cpu().numpy() == src) & (src >= 0)).sum()), planted=int((src >= 0).sum()))
+               planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((shn[ok] == shift[ok]).sum()),
+               flops_ringkey=60.0 * Q * kloc, tflops_ringkey_fp32=None)
     ctx.close()
     return res, (qd, sample)
 
@@ -478,7 +468,14 @@ def main():
     alg["downsample"] = (16 * n_raw / 10 + 16 * st["n_ds"] / max(st["frames"], 1)) * tm["downsample"][1]
     alg["map_build"] = (32 * 0 + 16 * st["m_ds"] / max(st["frames"], 1)) * tm["map_build"][1]       # + 16*M_raw in (added below when known)
     achieved = alg[dom] / (tm[dom][0] * 1e-3) / 1e9 if tm[dom][0] > 0 else 0.0
-    roofline = dict(kernel=dom, bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None,
+    traffic = None
+    try:                                                        # dram bytes per launch from the committed `ncu --set full` capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = dict(kernel=dom, bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=traffic,
+                    algorithmic_bytes_per_launch=alg[dom] / max(tm[dom][1], 1),
                     peak_source=peak_src, share_of_step={k: tm[k][0] / dv["ms"] for k in tm}, avg_launch_ms=tm[dom][0] / max(tm[dom][1], 1))
 
     # ---- ScanContext search (config 5) ----

@@ -71,6 +71,12 @@ class GpuOps:
         t = self.torch
         with t.cuda.stream(self.stream):
             d_q = t.from_numpy(np.ascontiguousarray(qdesc_host, np.float64).reshape(-1, 1200)).to(self.dev)
+        return self.prepare_dev(d_q)
+
+    def prepare_dev(self, d_q):
+        """ring keys (a11), sector keys and column norms of query descriptors already on the device."""
+        t = self.torch
+        with t.cuda.stream(self.stream):
             Q = d_q.shape[0]
             keys = t.empty((Q, 20), dtype=t.float32, device=self.dev)
             sk = t.empty((Q, 60), dtype=t.float64, device=self.dev); cn = t.empty_like(sk)
