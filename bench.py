@@ -65,6 +65,7 @@ class Sequence:
         self.imu = {}
         rng = np.random.default_rng(synth.SEED0 + 77 + rank)
         self.guess_noise = np.concatenate([rng.normal(scale=np.deg2rad(0.1), size=(n_frames, 3)), rng.normal(scale=0.02, size=(n_frames, 3))], axis=1)
+        self.inc = [np.eye(4)] + [np.linalg.inv(pose_to_T(self.poses[i - 1])) @ pose_to_T(self.poses[i]) for i in range(1, n_frames)]
 
     def frame(self, i):
         if i not in self.raw:
@@ -75,14 +76,15 @@ class Sequence:
             it, rot, ptr = self.synth.imu_table(t0, t0 + float(raw["time"][-1]), omega, rate_hz=100.0, gyro_noise=1.56e-3, seed=i)
             self.raw[i] = raw
             self.imu[i] = (t0, it, rot, ptr)
+            self.imu_cols = getattr(self, "imu_cols", {})
+            self.imu_cols[i] = tuple(np.ascontiguousarray(rot[:, k]) for k in range(3))
         return self.raw[i], self.imu[i]
 
     def initial_guess(self, i, prev_est):
         """previous optimised pose ∘ true increment, perturbed by N(0, 0.1 deg / 2 cm)."""
         if i == 0 or prev_est is None:
             return self.poses[0].astype(np.float32)
-        inc = np.linalg.inv(pose_to_T(self.poses[i - 1])) @ pose_to_T(self.poses[i])
-        g = T_to_pose(pose_to_T(np.asarray(prev_est, np.float64)) @ inc) + self.guess_noise[i]
+        g = T_to_pose(pose_to_T(np.asarray(prev_est, np.float64)) @ self.inc[i]) + self.guess_noise[i]
         return g.astype(np.float32)
 
 
@@ -112,30 +114,20 @@ class GpuPipeline:
         torch.cuda.synchronize()
 
     def step(self, i, mode):
+        """one frame = ONE call into the library (liorf_process_frame: the merged cloudHandler + laserCloudInfoHandler)."""
         ctx, seq = self.ctx, self.seq
         raw, (t0, it, rot, ptr) = seq.frame(i)
-        if mode == "dev":
-            ctx.projectPointCloudDev(self.dev_raw[i].data_ptr(), len(raw), t0, it, rot, ptr, True)
-        else:                                                    # e2e: HOST buffer through the reference-facing call
-            pin = self.pin_raw[i].numpy().view(raw.dtype)
-            ctx.projectPointCloud(pin, t0, it, rot, ptr, True, want_output=False)
-        ctx.downsampleCurrentScan(want_output=False)
         guess = seq.initial_guess(i, self.prev)
-        if ctx.numKeyframes() > 0:
-            ids = ctx.extractNearby(t0, 2.0)
-            ctx.extractSurroundingKeyFrames(ids, want_count=False)
-        ctx.scan2MapOptimizationAsync(guess, 30, False)
-        pose = ctx.getPose()                                      # D2H of the step's result (pose + counts)
-        c = ctx.lastCounts()
+        if mode == "dev":
+            fo = ctx.processFrame(self.dev_raw[i].data_ptr(), len(raw), True, t0, it, seq.imu_cols[i], ptr, True, guess, loop_every=10, frame_index=i)
+        else:                                                    # e2e: HOST (pinned) buffer, H2D inside the call
+            fo = ctx.processFrame(self.pin_raw[i].data_ptr(), len(raw), False, t0, it, seq.imu_cols[i], ptr, True, guess, loop_every=10, frame_index=i)
+        pose = np.array(fo.pose[:], np.float32)
         st = self.stats
-        st["frames"] += 1; st["iters"] += c["iters"]; st["knn_queries"] += c["iters"] * max(c["n_ds"], 0)
-        st["alg_bytes_s2m"] += 96 * c["iters"] * max(c["n_ds"], 0); st["n_ds"] += max(c["n_ds"], 0); st["m_ds"] += max(c["m_ds"], 0)
-        if ctx.saveFrame(pose, 1.0, 0.2):
-            ctx.addKeyframe(pose, t0)
-            ctx.makeAndSaveScancontextAndKeys()
-            st["keyframes"] += 1
-        if i % 10 == 9:
-            st["loops"] += ctx.detectLoopClosureID()[0] >= 0
+        st["frames"] += 1; st["iters"] += fo.iters; st["knn_queries"] += fo.iters * max(fo.n_ds, 0)
+        st["alg_bytes_s2m"] += 96 * fo.iters * max(fo.n_ds, 0); st["n_ds"] += max(fo.n_ds, 0); st["m_ds"] += max(fo.m_ds, 0)
+        st["keyframes"] += fo.is_keyframe
+        st["loops"] += int(fo.loop_checked and fo.loop_id >= 0)
         self.prev = pose
         return pose
 

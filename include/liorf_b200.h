@@ -162,6 +162,30 @@ int liorf_sc_decide_dev(liorf_ctx* ctx, const void* d_pair_dist, const void* d_p
 /* single-GPU convenience with host buffers: descriptors of the Q queries → loop ids / shifts / distances */
 int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
 
+/* ---- one LiDAR frame through the whole path ------------------------------------------------------------------- */
+/* The call sequence of ImageProjection::cloudHandler (src/imageProjection.cpp:191-204) followed by
+ * mapOptimization::laserCloudInfoHandler (src/mapOptmization.cpp:236-275) for a merged node: projectPointCloud →
+ * extractSurroundingKeyFrames → downsampleCurrentScan → scan2MapOptimization → transformUpdate clamps → saveFrame →
+ * keyframe store + makeAndSaveScancontextAndKeys, and detectLoopClosureID every `loop_every`-th frame (0 = never).
+ * One host↔device round trip per frame (the pose).  pts_on_device != 0 → `pts` is a device pointer. */
+typedef struct {
+    const void* pts; int n; int pts_on_device;
+    double time_scan_cur;
+    const double *imu_time, *imu_rot_x, *imu_rot_y, *imu_rot_z; int imu_pointer_cur; int deskew_enabled;
+    float initial_guess[6];                     /* transformTobeMapped after updateInitialGuess (:899-958) */
+    float surrounding_keyframe_density;         /* utility.h:139 */
+    float adding_dist_threshold, adding_angle_threshold;   /* utility.h:137-138 */
+    float rotation_tollerance, z_tollerance;    /* utility.h:129-130 */
+    int max_iters; int loop_every; int frame_index;
+} liorf_frame_in;
+typedef struct {
+    float pose[6];
+    int is_keyframe, keyframe_id;
+    int n_kept, n_ds, m_ds, iters, converged, degenerate, ran;
+    int loop_checked, loop_id; float loop_yaw;
+} liorf_frame_out;
+int liorf_process_frame(liorf_ctx* ctx, const liorf_frame_in* in, liorf_frame_out* out);
+
 /* ---- measurement / introspection (bench.py) ------------------------------------------------------------------- */
 /* per-section CUDA-event timing on the context's stream: sections 0 deskew, 1 downsample, 2 map build (transform +
  * VoxelGrid), 3 grid build, 4 scan2map solver, 5 ScanContext make, 6 ScanContext ring-key search */

@@ -41,6 +41,20 @@ class LMTrace(C.Structure):
         return np.array([self.nsel[i] for i in range(self.iters)], np.int32)
 
 
+class FrameIn(C.Structure):
+    _fields_ = [("pts", C.c_void_p), ("n", C.c_int), ("pts_on_device", C.c_int), ("time_scan_cur", C.c_double),
+                ("imu_time", C.c_void_p), ("imu_rot_x", C.c_void_p), ("imu_rot_y", C.c_void_p), ("imu_rot_z", C.c_void_p),
+                ("imu_pointer_cur", C.c_int), ("deskew_enabled", C.c_int), ("initial_guess", C.c_float * 6),
+                ("surrounding_keyframe_density", C.c_float), ("adding_dist_threshold", C.c_float), ("adding_angle_threshold", C.c_float),
+                ("rotation_tollerance", C.c_float), ("z_tollerance", C.c_float), ("max_iters", C.c_int), ("loop_every", C.c_int), ("frame_index", C.c_int)]
+
+
+class FrameOut(C.Structure):
+    _fields_ = [("pose", C.c_float * 6), ("is_keyframe", C.c_int), ("keyframe_id", C.c_int), ("n_kept", C.c_int), ("n_ds", C.c_int), ("m_ds", C.c_int),
+                ("iters", C.c_int), ("converged", C.c_int), ("degenerate", C.c_int), ("ran", C.c_int), ("loop_checked", C.c_int), ("loop_id", C.c_int),
+                ("loop_yaw", C.c_float)]
+
+
 class LiorfError(RuntimeError):
     pass
 
@@ -253,6 +267,21 @@ class Context:
     def setLMState(self, deg, matP):
         P = np.ascontiguousarray(matP, np.float32).reshape(36)
         _chk(self.lib.liorf_set_lm_state(self.h, C.c_int(int(deg)), _vp(P)), "liorf_set_lm_state")
+
+    def processFrame(self, pts_ptr, n, on_device, time_scan_cur, imu_time, imu_rot_xyz, imu_pointer_cur, deskew_enabled, initial_guess,
+                     density=2.0, dist_thr=1.0, ang_thr=0.2, rot_tol=1000.0, z_tol=1000.0, max_iters=30, loop_every=0, frame_index=0):
+        """one frame through cloudHandler + laserCloudInfoHandler (liorf_process_frame).  imu_rot_xyz: three contiguous float64 arrays."""
+        fi = FrameIn()
+        fi.pts = pts_ptr; fi.n = n; fi.pts_on_device = int(on_device); fi.time_scan_cur = time_scan_cur
+        fi.imu_time = imu_time.ctypes.data; fi.imu_rot_x = imu_rot_xyz[0].ctypes.data; fi.imu_rot_y = imu_rot_xyz[1].ctypes.data; fi.imu_rot_z = imu_rot_xyz[2].ctypes.data
+        fi.imu_pointer_cur = imu_pointer_cur; fi.deskew_enabled = int(deskew_enabled)
+        for k in range(6):
+            fi.initial_guess[k] = float(initial_guess[k])
+        fi.surrounding_keyframe_density = density; fi.adding_dist_threshold = dist_thr; fi.adding_angle_threshold = ang_thr
+        fi.rotation_tollerance = rot_tol; fi.z_tollerance = z_tol; fi.max_iters = max_iters; fi.loop_every = loop_every; fi.frame_index = frame_index
+        fo = FrameOut()
+        _chk(self.lib.liorf_process_frame(self.h, C.byref(fi), C.byref(fo)), "liorf_process_frame")
+        return fo
 
     # ---- measurement helpers ----
     def enableTiming(self, on=True):

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <chrono>
+#include <cstdlib>
 
 using namespace liorf;
 
@@ -49,13 +51,17 @@ struct liorf_ctx {
     int n_scan_bound = 0;           // host-known upper bound of laserCloudSurfLast / DS counts
     int h_n_scan = -1, h_n_ds = -1, h_m_ds = -1;   // host copies (-1 = unknown)
     int m_bound = 0;
-    VoxelGridWork vg;
+    VoxelGridWork vg;               // scan-side VoxelGrid work area (main stream)
+    VoxelGridWork vg_map;           // map-side work area: the local-map chain runs concurrently on stream_map
+    cudaStream_t stream_map = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_map = nullptr; bool map_pending = false;
     MapGrid grid;
     DeskewWork dk;
     std::vector<Keyframe> kfs;
     size_t kf_used = 0;
     DevBuf<KfSel> d_sel;
-    KfSel* h_sel = nullptr; int h_sel_cap = 0;
+    KfSel* h_sel = nullptr; int h_sel_cap = 0;       // two halves, alternated per call (see stage_slot)
+    cudaEvent_t stage_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int stage_turn[2] = {0, 0};   // [0] = selection table, [1] = IMU table
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr;
@@ -72,6 +78,8 @@ struct liorf_ctx {
     DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
     DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
     Profiler prof;
+    double host_us[6] = {0, 0, 0, 0, 0, 0}; long long host_frames = 0; bool host_timing = false;   // LIORF_HOST_TIMING=1
+    cudaEvent_t tl_ev[8] = {nullptr}; double tl_ms[8] = {0}; // debug GPU timeline stamps of process_frame
     long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
 };
 
@@ -84,17 +92,21 @@ static void prof_flush(liorf_ctx* c) {           // call only when the stream is
     p.pending = 0;
 }
 struct ProfScope {
-    liorf_ctx* c; int slot = -1;
-    ProfScope(liorf_ctx* c_, int sec) : c(c_) {
+    liorf_ctx* c; int slot = -1; cudaStream_t st;
+    ProfScope(liorf_ctx* c_, int sec, cudaStream_t st_ = nullptr) : c(c_), st(st_ ? st_ : c_->stream) {
         Profiler& p = c->prof;
         if (!p.enabled) return;
         if (!p.created) { for (int i = 0; i < PROF_RING; ++i) { cudaEventCreate(&p.ev[i][0]); cudaEventCreate(&p.ev[i][1]); } p.created = true; }
-        if (p.pending == PROF_RING) { cudaStreamSynchronize(c->stream); prof_flush(c); }
+        if (p.pending == PROF_RING) { cudaStreamSynchronize(c->stream); if (c->stream_map) cudaStreamSynchronize(c->stream_map); prof_flush(c); }
         slot = p.pending++; p.sec[slot] = sec;
-        cudaEventRecord(p.ev[slot][0], c->stream);
+        cudaEventRecord(p.ev[slot][0], st);
     }
-    ~ProfScope() { if (slot >= 0) cudaEventRecord(c->prof.ev[slot][1], c->stream); }
+    ~ProfScope() { if (slot >= 0) cudaEventRecord(c->prof.ev[slot][1], st); }
 };
+
+struct Pose6 { float v[6]; };
+__global__ void k_set_tf6(float* tf6, Pose6 p) { if (threadIdx.x < 6) tf6[threadIdx.x] = p.v[threadIdx.x]; }
+static int upload_pose(liorf_ctx* c, const float* pose6);
 
 static void host_get_transformation(float x, float y, float z, float roll, float pitch, float yaw, float* t) {
     // pcl::getTransformation on the host, exactly where the reference evaluates it (src/mapOptmization.cpp:317)
@@ -105,8 +117,30 @@ static void host_get_transformation(float x, float y, float z, float roll, float
     t[8] = -D;     t[9] = C * F;           t[10] = C * E;           t[11] = z;
 }
 
+// Pinned staging areas are split in two halves used alternately; an event per half tells when its last H2D copy has been
+// consumed, so re-use never needs a stream synchronise (the event is normally long complete).
+static int stage_slot(liorf_ctx* c, int which) {
+    const int turn = c->stage_turn[which] ^= 1;
+    if (!c->stage_ev[which][turn]) { if (cudaEventCreateWithFlags(&c->stage_ev[which][turn], cudaEventDisableTiming) != cudaSuccess) return -1; }
+    else if (cudaEventSynchronize(c->stage_ev[which][turn]) != cudaSuccess) return -1;
+    return turn;
+}
+// The local-map chain (extractCloud + VoxelGrid + grid build) runs on stream_map, concurrently with deskew + downsample on
+// the main stream.  Every main-stream consumer of the map (solver, hooks, read-backs) joins first.
+static int join_map(liorf_ctx* c) {
+    if (c->map_pending) { CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_map, 0)); c->map_pending = false; }
+    return LIORF_OK;
+}
+static int upload_pose(liorf_ctx* c, const float* pose6) {          // by kernel argument: no pinned staging, no sync
+    Pose6 p; std::memcpy(p.v, pose6, sizeof(p.v));
+    k_set_tf6<<<1, 32, 0, c->stream>>>(c->d_tf6, p);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+
 static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-side error flag (bounded look-back spins)
     int e = 0;
+    { int rcj = join_map(c); if (rcj) return rcj; }
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 4000, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     prof_flush(c);
@@ -116,6 +150,7 @@ static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-
 }
 
 static int read_counts(liorf_ctx* c) {
+    { int rcj = join_map(c); if (rcj) return rcj; }
     CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     prof_flush(c);
@@ -156,6 +191,7 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     liorf_ctx* c = new (std::nothrow) liorf_ctx();
     if (!c) return LIORF_ERR_ARG;
     c->P = *p;
+    c->host_timing = std::getenv("LIORF_HOST_TIMING") != nullptr;
     if (c->P.grid_dim_x == 0) c->P.grid_dim_x = 256;
     if (c->P.grid_dim_y == 0) c->P.grid_dim_y = 256;
     if (c->P.grid_dim_z == 0) c->P.grid_dim_z = 32;
@@ -179,9 +215,16 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     c->combine_scan.ticket = c->d_misc + 6; c->combine_scan.err_flag = c->d_err;
     int* lm_counter = c->d_misc + 7; (void)lm_counter;
     CUDA_TRY(cudaMalloc(&c->vg.meta, sizeof(VoxMeta)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_map, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_map, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&c->vg_map.meta, sizeof(VoxMeta)));
+    c->vg_map.mm_counter = c->d_misc + 10;
+    c->vg_map.sort.ticket = c->d_misc + 11; c->vg_map.sort.err_flag = c->d_err;
+    c->vg_map.scan.ticket = c->d_misc + 12; c->vg_map.scan.err_flag = c->d_err;
     CUDA_TRY(cudaMalloc(&c->dk.start_inv, 12 * sizeof(float)));
     c->dk.first_kept = c->d_counts + C_FIRST_KEPT;
-    CUDA_TRY(cudaHostAlloc(&c->h_mail, 131072, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&c->h_mail, 65536 + 2 * 65536, cudaHostAllocDefault));
     CUDA_TRY(cudaMalloc(&c->d_tf6, 6 * sizeof(float)));
     CUDA_TRY(cudaMemset(c->d_tf6, 0, 6 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->d_lm, sizeof(LMDeviceState)));
@@ -210,12 +253,24 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
 
 void liorf_destroy(liorf_ctx* c) {
     if (!c) return;
+    if (c->host_timing && c->host_frames > 0) {
+        const char* nm[6] = {"enqueue deskew", "select+enqueue map", "enqueue downsample", "enqueue solver", "wait pose (sync)", "keyframe+sc+loop"};
+        fprintf(stderr, "[liorf_b200] host timeline per frame over %lld frames:", c->host_frames);
+        for (int k = 0; k < 6; ++k) fprintf(stderr, "  %s %.1f us;", nm[k], c->host_us[k] / c->host_frames);
+        fprintf(stderr, "\n[liorf_b200] GPU timeline (us after frame start): deskew done %.1f; map+grid done %.1f; downsample done %.1f; joined %.1f; solver done %.1f\n",
+                1e3 * c->tl_ms[1] / c->host_frames, 1e3 * c->tl_ms[2] / c->host_frames, 1e3 * c->tl_ms[3] / c->host_frames, 1e3 * c->tl_ms[4] / c->host_frames,
+                1e3 * c->tl_ms[5] / c->host_frames);
+    }
     cudaSetDevice(c->P.device);
     cudaStreamSynchronize(c->stream);
     DevBuf<float4>* f4[] = {&c->scan, &c->scan_ds, &c->map_raw, &c->map_ds, &c->kf_points, &c->h_coeff, &c->h_sel_pts, &c->h_ori_c, &c->h_coeff_c, &c->grid.sorted};
     for (auto b : f4) b->release();
     c->membership.release(); c->out_keys.release(); c->h_flag.release(); c->h_idx.release(); c->h_d2.release(); c->h_plane.release();
     c->lm_partial.release(); c->d_sel.release();
+    cudaStreamSynchronize(c->stream_map);
+    for (VoxelGridWork* w : {&c->vg_map}) { w->partial.release(); w->keys.release(); w->seg_start.release(); w->sort.keys_alt.release(); w->sort.vals_a.release();
+        w->sort.vals_b.release(); w->sort.hist.release(); w->sort.status.release(); w->scan.status.release(); cudaFree(w->meta); }
+    cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_map); cudaStreamDestroy(c->stream_map);
     c->vg.partial.release(); c->vg.keys.release(); c->vg.seg_start.release();
     c->vg.sort.keys_alt.release(); c->vg.sort.vals_a.release(); c->vg.sort.vals_b.release(); c->vg.sort.hist.release(); c->vg.sort.status.release();
     c->vg.scan.status.release(); c->grid.scan.status.release(); c->dk.scan.status.release(); c->combine_scan.status.release();
@@ -228,6 +283,7 @@ void liorf_destroy(liorf_ctx* c) {
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->h_sel) cudaFreeHost(c->h_sel);
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (c->stage_ev[a][b]) cudaEventDestroy(c->stage_ev[a][b]);
     cudaFreeHost(c->h_mail);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -252,11 +308,12 @@ static int project_common(liorf_ctx* c, const RawPoint* d_raw, int n, double t0,
         const int rows = imu_ptr + 1;
         if ((rc = c->dk.imu.reserve((size_t)4 * rows))) return rc;
         if ((size_t)4 * rows * sizeof(double) > 65536) return LIORF_ERR_ARG;        // queueLength = 2000 rows (src/imageProjection.cpp:62) = 64000 B
-        double* stage = reinterpret_cast<double*>(c->h_mail + 16384);             // pinned staging (upper half of the mailbox)
-        CUDA_TRY(cudaStreamSynchronize(c->stream));                                // staging reuse
+        const int slot = stage_slot(c, 1); if (slot < 0) return LIORF_ERR_CUDA;
+        double* stage = reinterpret_cast<double*>(c->h_mail + 16384 + slot * 16384);   // pinned staging (two 64 KB halves above the mailbox)
         std::memcpy(stage, imu_time, rows * sizeof(double)); std::memcpy(stage + rows, rx, rows * sizeof(double));
         std::memcpy(stage + 2 * rows, ry, rows * sizeof(double)); std::memcpy(stage + 3 * rows, rz, rows * sizeof(double));
         CUDA_TRY(cudaMemcpyAsync(c->dk.imu.p, stage, (size_t)4 * rows * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaEventRecord(c->stage_ev[1][slot], c->stream));
         T = ImuTable{c->dk.imu.p, c->dk.imu.p + rows, c->dk.imu.p + 2 * rows, c->dk.imu.p + 3 * rows, imu_ptr};
     }
     DeskewParams DP{c->P.lidarMinRange, c->P.lidarMaxRange, c->P.N_SCAN, c->P.downsampleRate, c->P.point_filter_num};
@@ -347,6 +404,7 @@ int liorf_voxel_grid(liorf_ctx* c, const liorf_point* in, int n, float leaf, lio
     if (!c || n < 0 || (n > 0 && !in) || !n_out) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
+    if ((rc = join_map(c))) return rc;
     const int cap = n > 0 ? n : 1;
     if ((rc = c->map_raw.reserve(cap))) return rc;       // scratch in / out (does not disturb the scan or the map)
     DevBuf<float4> tmp_out; if ((rc = tmp_out.reserve(cap))) return rc;
@@ -423,16 +481,18 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     }
     const int ns = (int)sel.size();
     if (ns > c->h_sel_cap) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
         if (c->h_sel) cudaFreeHost(c->h_sel);
-        c->h_sel_cap = ns + 64;
-        CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
+        c->h_sel_cap = 2 * ns + 64;
+        CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)2 * c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
     }
     if ((rc = c->d_sel.reserve(ns > 0 ? ns : 1))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));                  // h_sel staging reuse
+    const int slot = stage_slot(c, 0); if (slot < 0) return LIORF_ERR_CUDA;
+    KfSel* hsel = c->h_sel + (size_t)slot * c->h_sel_cap;
     long long total = 0;
     for (int i = 0; i < ns; ++i) {
         const Keyframe& k = c->kfs[sel[i]];
-        KfSel& s = c->h_sel[i];
+        KfSel& s = hsel[i];
         s.src_off = (int)k.off; s.count = k.count; s.dst_off = (int)total; s.pad = 0;
         host_get_transformation(k.pose[3], k.pose[4], k.pose[5], k.pose[0], k.pose[1], k.pose[2], s.t);
         total += k.count;
@@ -441,18 +501,26 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     const int tot = (int)total;
     if ((rc = c->map_raw.reserve(tot > 0 ? tot : 1))) return rc;
     if ((rc = c->map_ds.reserve(tot > 0 ? tot : 1))) return rc;
-    if (ns > 0) CUDA_TRY(cudaMemcpyAsync(c->d_sel.p, c->h_sel, (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, c->stream));
+    // fork: everything enqueued so far on the main stream (keyframe copies, the previous solve that still reads the old map)
+    // happens-before the map chain
+    cudaStream_t ms = c->stream_map;
+    CUDA_TRY(cudaEventRecord(c->ev_main, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ms, c->ev_main, 0));
+    if (ns > 0) CUDA_TRY(cudaMemcpyAsync(c->d_sel.p, hsel, (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, ms));
+    CUDA_TRY(cudaEventRecord(c->stage_ev[0][slot], ms));
     {
-        ProfScope ps(c, SEC_MAP_BUILD); c->launches += 10;
-        if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
+        ProfScope ps(c, SEC_MAP_BUILD, ms); c->launches += 10;
+        if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
         if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_counts + C_M_DS, nullptr,
-                                    nullptr, c->vg, c->stream))) return rc;
+                                    nullptr, c->vg_map, ms))) return rc;
     }
     c->m_bound = tot; c->h_m_ds = -1;
     {
-        ProfScope ps(c, SEC_GRID_BUILD); c->launches += 3;
-        if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_counts + C_M_DS, tot), c->grid, c->stream))) return rc;
+        ProfScope ps(c, SEC_GRID_BUILD, ms); c->launches += 3;
+        if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_counts + C_M_DS, tot), c->grid, ms))) return rc;
     }
+    CUDA_TRY(cudaEventRecord(c->ev_map, ms));
+    c->map_pending = true;
     c->last_sel = sel; c->last_sel_version = c->pose_version; c->map_valid = true;
     if (m_ds) { if ((rc = read_counts(c))) return rc; *m_ds = c->h_m_ds; return check_err(c); }
     return LIORF_OK;
@@ -498,6 +566,7 @@ int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
     if (!c || m < 0 || (m > 0 && !map_ds)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
+    if ((rc = join_map(c))) return rc;
     if ((rc = c->map_ds.reserve(m > 0 ? m : 1))) return rc;
     if (m > 0) CUDA_TRY(cudaMemcpyAsync(c->map_ds.p, map_ds, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     c->h_mail[101] = m;
@@ -536,6 +605,7 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     int rc;
     const size_t qb = (size_t)(c->n_scan_bound > 0 ? c->n_scan_bound : 1);
     if ((rc = c->qcache.reserve(qb)) || (rc = c->cand.reserve(qb * CAND_CAP))) return rc;
+    if ((rc = join_map(c))) return rc;
     S2MArgs a;
     a.qcache = c->qcache.p; a.cand = c->cand.p; a.result = c->d_result;
     a.arrive = reinterpret_cast<unsigned*>(c->d_misc + 8); a.flag = reinterpret_cast<unsigned*>(c->d_misc + 9); a.err_flag = c->d_err;
@@ -552,16 +622,13 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
 int liorf_scan2map_optimization_async(liorf_ctx* c, const float pose6_in[6], int max_iters, int force_all) {
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
-    if (pose6_in) {
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        std::memcpy(c->h_mail + 300, pose6_in, 6 * sizeof(float));
-        CUDA_TRY(cudaMemcpyAsync(c->d_tf6, c->h_mail + 300, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    }
+    if (pose6_in) { int rc = upload_pose(c, pose6_in); if (rc) return rc; }
     return launch_s2m(c, max_iters, force_all);
 }
 int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
     if (!c || !pose6) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
+    { int rcj = join_map(c); if (rcj) return rcj; }
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 320, c->d_tf6, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (trace) CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024, c->d_trace, sizeof(S2MTrace), cudaMemcpyDeviceToHost, c->stream));
@@ -585,13 +652,12 @@ int liorf_surf_optimization(liorf_ctx* c, const float pose6[6], liorf_point* coe
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
     if (!c->grid.cell_start.p) return LIORF_ERR_STATE;
+    if ((rc = join_map(c))) return rc;
     if (c->h_n_ds < 0 && (rc = read_counts(c))) return rc;
     const int n = c->h_n_ds, cap = n > 0 ? n : 1;
     if ((rc = c->h_coeff.reserve(cap)) || (rc = c->h_flag.reserve(cap)) || (rc = c->h_idx.reserve((size_t)5 * cap)) || (rc = c->h_d2.reserve((size_t)5 * cap)) ||
         (rc = c->h_plane.reserve((size_t)4 * cap)) || (rc = c->h_sel_pts.reserve(cap))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::memcpy(c->h_mail + 300, pose6, 6 * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(c->d_tf6, c->h_mail + 300, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_pose(c, pose6))) return rc;
     c->hook_n = n;
     if (n > 0) {
         k_surf_optimization<<<(n + S2M_QPB - 1) / S2M_QPB, S2M_BLOCK, 0, c->stream>>>(c->scan_ds.p, Count::of_host(n), c->d_tf6, c->grid.cell_start.p,
@@ -628,9 +694,7 @@ int liorf_lm_optimization(liorf_ctx* c, int iter, float pose6[6], float AtA[36],
     int rc; const int nb = c->hook_n > 0 ? c->hook_n : 1;
     int blocks = (nb + 255) / 256; if (blocks > 2 * c->num_sms) blocks = 2 * c->num_sms;
     if ((rc = c->lm_partial.reserve((size_t)blocks * NPROD))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::memcpy(c->h_mail + 300, pose6, 6 * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(c->d_tf6, c->h_mail + 300, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_pose(c, pose6))) return rc;
     k_lm_hook<<<blocks, 256, 0, c->stream>>>(iter, c->h_ori_c.p, c->h_coeff_c.p, (const unsigned*)(c->d_counts + C_HOOK_NSEL), c->d_tf6, c->d_lm,
                                              c->lm_partial.p, c->d_misc + 7, c->d_lm_out, c->d_lm_out + 36, c->d_lm_out + 42, c->d_counts + C_NSEL,
                                              c->d_counts + C_CONV);
@@ -672,6 +736,7 @@ int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
     const float4* d_pts; Count cnt = Count::of_host(0);
     if (cloud) {
         if (n < 0) return LIORF_ERR_ARG;
+        if ((rc = join_map(c))) return rc;
         if ((rc = c->map_raw.reserve(n > 0 ? n : 1))) return rc;
         c->map_valid = false;
         if (n > 0) CUDA_TRY(cudaMemcpyAsync(c->map_raw.p, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -839,6 +904,62 @@ int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_
     return LIORF_OK;
 }
 
+int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out* out) {
+    if (!c || !in || !out || in->n < 0) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    std::memset(out, 0, sizeof(*out)); out->keyframe_id = -1; out->loop_id = -1;
+    using clk = std::chrono::steady_clock;
+    auto T0 = clk::now();
+    auto stamp = [&](int k, cudaStream_t st) { if (c->host_timing) { if (!c->tl_ev[k]) cudaEventCreate(&c->tl_ev[k]); cudaEventRecord(c->tl_ev[k], st); } };
+    stamp(0, c->stream);
+    auto lap = [&](int k) { if (c->host_timing) { auto t = clk::now(); c->host_us[k] += std::chrono::duration<double, std::micro>(t - T0).count(); T0 = t; } };
+    // cloudHandler: projectPointCloud (the deskewed cloud stays on the device)
+    if (in->pts_on_device) rc = liorf_project_point_cloud_dev(c, in->pts, in->n, in->time_scan_cur, in->imu_time, in->imu_rot_x, in->imu_rot_y, in->imu_rot_z,
+                                                              in->imu_pointer_cur, in->deskew_enabled);
+    else rc = liorf_project_point_cloud(c, (const liorf_point_xyzirt*)in->pts, in->n, in->time_scan_cur, in->imu_time, in->imu_rot_x, in->imu_rot_y, in->imu_rot_z,
+                                        in->imu_pointer_cur, in->deskew_enabled, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    stamp(1, c->stream);
+    lap(0);
+    // laserCloudInfoHandler: extractSurroundingKeyFrames, downsampleCurrentScan, scan2MapOptimization
+    if (!c->kfs.empty()) {
+        std::vector<liorf_host::KeyPose> kp(c->kfs.size());
+        for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }
+        std::vector<int> sel = liorf_host::extract_nearby(kp, in->time_scan_cur, c->P.surroundingKeyframeSearchRadius, in->surrounding_keyframe_density);
+        if ((rc = liorf_extract_surrounding_keyframes(c, sel.data(), (int)sel.size(), nullptr))) return rc;
+    }
+    stamp(2, c->stream_map);
+    lap(1);
+    if ((rc = liorf_downsample_current_scan(c, nullptr, nullptr, nullptr))) return rc;
+    stamp(3, c->stream);
+    lap(2);
+    if ((rc = join_map(c))) return rc;
+    stamp(4, c->stream);
+    if ((rc = liorf_scan2map_optimization_async(c, in->initial_guess, in->max_iters > 0 ? in->max_iters : 30, 0))) return rc;
+    stamp(5, c->stream);
+    lap(3);
+    if ((rc = liorf_get_pose(c, out->pose, nullptr))) return rc;                  // the frame's single round trip
+    lap(4);
+    if (c->host_timing) for (int k = 1; k <= 5; ++k) { float ms = 0; if (c->tl_ev[k] && cudaEventElapsedTime(&ms, c->tl_ev[0], c->tl_ev[k]) == cudaSuccess) c->tl_ms[k] += ms; }
+    out->n_kept = c->h_n_scan; out->n_ds = c->h_n_ds; out->m_ds = c->h_m_ds;
+    out->iters = c->h_mail[1024 + 448]; out->converged = c->h_mail[1024 + 449]; out->degenerate = c->h_mail[1024 + 450]; out->ran = c->h_mail[1024 + 451];
+    if (out->ran) liorf_host::transform_update_clamp(out->pose, in->rotation_tollerance, in->z_tollerance);
+    // saveKeyFramesAndFactor (the parts on the path): saveFrame gate, keyframe cloud, ScanContext descriptor
+    if (liorf_save_frame(c, out->pose, in->adding_dist_threshold, in->adding_angle_threshold) == 1) {
+        int id = liorf_add_keyframe(c, out->pose, in->time_scan_cur);
+        if (id < 0) return id;
+        out->is_keyframe = 1; out->keyframe_id = id;
+        if ((rc = liorf_sc_make_and_save(c, nullptr, 0))) return rc;
+    }
+    if (in->loop_every > 0 && in->frame_index % in->loop_every == in->loop_every - 1) {
+        out->loop_checked = 1;
+        if ((rc = liorf_sc_detect_loop_closure_id(c, &out->loop_id, &out->loop_yaw, nullptr, nullptr))) return rc;
+    }
+    lap(5); ++c->host_frames;
+    return LIORF_OK;
+}
+
 // Pre-sizes every work buffer so that no call allocates afterwards (allocation = cudaMalloc/cudaFree = device sync).
 int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_points_max, int sc_entries_max) {
     if (!c || n_scan_max < 0 || m_raw_max < 0) return LIORF_ERR_ARG;
@@ -855,13 +976,18 @@ int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_po
         (rc = reserve_zeroed(c->vg.sort.status, ((big + SORT_TILE - 1) / SORT_TILE) * RADIX, c->stream)) ||
         (rc = reserve_zeroed(c->vg.scan.status, (big + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
         (rc = reserve_zeroed(c->dk.scan.status, (n + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
-        (rc = c->qcache.reserve(n)) || (rc = c->cand.reserve(n * CAND_CAP)) || (rc = c->d_sel.reserve(4096))) return rc;
+        (rc = c->qcache.reserve(n)) || (rc = c->cand.reserve(n * CAND_CAP)) || (rc = c->d_sel.reserve(4096)) ||
+        (rc = c->vg_map.keys.reserve(m)) || (rc = c->vg_map.seg_start.reserve(m + 1)) || (rc = c->vg_map.partial.reserve((size_t)kNumSMs * 6)) ||
+        (rc = c->vg_map.sort.keys_alt.reserve(m)) || (rc = c->vg_map.sort.vals_a.reserve(m)) || (rc = c->vg_map.sort.vals_b.reserve(m)) ||
+        (rc = c->vg_map.sort.hist.reserve(4 * RADIX)) ||
+        (rc = reserve_zeroed(c->vg_map.sort.status, ((m + SORT_TILE - 1) / SORT_TILE) * RADIX, c->stream)) ||
+        (rc = reserve_zeroed(c->vg_map.scan.status, (m + SCAN_TILE - 1) / SCAN_TILE, c->stream))) return rc;
     if (n_keyframe_points_max > 0 && (rc = c->kf_points.reserve((size_t)n_keyframe_points_max, c->stream, true))) return rc;
     if (sc_entries_max > 0 && (rc = sc_reserve(c, sc_entries_max))) return rc;
     if (c->h_sel_cap < 4096) {
         if (c->h_sel) cudaFreeHost(c->h_sel);
         c->h_sel_cap = 4096;
-        CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)2 * c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return LIORF_OK;

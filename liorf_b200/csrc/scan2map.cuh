@@ -678,13 +678,15 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
 #pragma unroll
                 for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
                 __stcg(part + (size_t)blockIdx.x * NPROD + threadIdx.x, (s0 + s1) + (s2 + s3));
-                __threadfence();
             }
             __syncthreads();
             if (dbg) a.dbg[iter * 8 + 2] = clock64();
             const unsigned epoch = a.epoch_base + (unsigned)iter + 1u;
             if (threadIdx.x == 0) {
-                const unsigned t = atomicAdd(a.arrive, 1u);
+                // release: the CTA's partial (ordered before by the barrier) becomes visible with the arrival;
+                // acquire: the last arriver sees every other CTA's partial
+                unsigned t;
+                asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(t) : "l"(a.arrive), "r"(1u) : "memory");
                 s_last = (t == gridDim.x - 1) ? 1 : 0;
             }
             __syncthreads();
@@ -692,7 +694,8 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
             if (s_last) {
                 if (dbg) a.dbg[iter * 8 + 3] = clock64();
                 const long long lc0 = clock64();
-                __threadfence();
+                if (threadIdx.x >= 64 && threadIdx.x < 64 + 37)      // persistent LM state (written by whichever CTA solved iteration 0)
+                    reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
                 {   // partial sums in CTA order: warp w takes CTAs w, w + W, ...; lane = component; then warps in order
                     const int w = warp_id(), l = lane_id();
                     double s0 = 0;
@@ -713,8 +716,6 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                     for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
                     s_sum[threadIdx.x] = (s0 + s1) + (s2 + s3);
                 }
-                if (threadIdx.x >= 64 && threadIdx.x < 64 + 37)      // persistent LM state (written by whichever CTA solved iteration 0)
-                    reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
                 __syncthreads();
                 if (dbg) a.dbg[iter * 8 + 4] = clock64();
                 const long long lc1 = clock64();
