@@ -186,8 +186,10 @@ class CpuPipeline:
             mraw = np.concatenate([o.transform_cloud(self.kf_clouds[k], self.kf_poses[k]) for k in ids], 0)
             mds, _, _ = o.voxel_grid(mraw, 0.5)
             d = time.perf_counter()
+            self.last = dict(ds=ds, mds=mds, guess=guess.copy(), state=self.state.copy(), ids=list(ids))
             r = o.scan2map(ds, mds, guess, 30, False, self.state, use_ref_kdtree=self.use_ref)
             pose, self.state = r["tf"], r["state"]
+            self.last["iters"] = r["iters"]
         e = time.perf_counter()
         last = self.kf_poses[-1] if self.kf_poses else None
         make = last is None

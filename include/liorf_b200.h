@@ -159,6 +159,16 @@ int liorf_sc_distance_batch_dev(liorf_ctx* ctx, const void* d_qdescs, const void
                                 int global_offset, void* d_pair_dist /*Q*3 f64*/, void* d_pair_shift /*Q*3 i32*/);
 int liorf_sc_decide_dev(liorf_ctx* ctx, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q,
                         void* d_loop_id, void* d_shift, void* d_dist);
+/* Ring-key search implementation used by liorf_sc_knn_batch_dev / liorf_sc_query_batch:
+ *   0 auto (tensor cores for batches of >= 64 queries against >= 4096 keys), 1 CUDA-core brute force,
+ *   2 tcgen05 coarse filter + exact re-rank (csrc/sc_tensor.cuh).  All three return the same exact top-3
+ *   (nanoflann arithmetic, include/nanoflann.hpp:383-408, ties by (dist, idx)). */
+int liorf_sc_set_search_path(liorf_ctx* ctx, int mode);
+/* last tensor-core search: candidates the coarse filter passed to the exact re-rank (summed over the queries) and the
+ * number of queries whose candidate list overflowed (answered by the brute-force kernel instead) */
+int liorf_sc_tensor_stats(liorf_ctx* ctx, long long* n_candidates, int* n_overflow);
+/* test hook: raw tensor-core distances of Q host ring keys against the database, out[q * ld + k] */
+int liorf_sc_tensor_dump(liorf_ctx* ctx, const float* qkeys, int Q, float* out, long long out_capacity, int* ld, float center[20]);
 /* single-GPU convenience with host buffers: descriptors of the Q queries → loop ids / shifts / distances */
 int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
 

@@ -334,6 +334,25 @@ class Context:
         _chk(self.lib.liorf_sc_detect_loop_closure_id(self.h, C.byref(lid), C.byref(yaw), C.byref(md), _vp(cand)), "liorf_sc_detect_loop_closure_id")
         return lid.value, yaw.value, md.value, cand
 
+    def scSetSearchPath(self, mode):
+        """ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tcgen05 coarse filter + exact re-rank"""
+        _chk(self.lib.liorf_sc_set_search_path(self.h, C.c_int(int(mode))), "liorf_sc_set_search_path")
+
+    def scTensorStats(self):
+        n = C.c_longlong(0); o = C.c_int(0)
+        _chk(self.lib.liorf_sc_tensor_stats(self.h, C.byref(n), C.byref(o)), "liorf_sc_tensor_stats")
+        return dict(candidates=n.value, overflow=o.value)
+
+    def scTensorDump(self, qkeys):
+        """test hook: raw tensor-core distances d~[Q, K] of host ring keys against the database, and the image centre"""
+        qkeys = np.ascontiguousarray(qkeys, np.float32).reshape(-1, 20)
+        Q, K = len(qkeys), self.scSize()
+        ldmax = (K + 127) // 128 * 128
+        out = np.empty((Q, ldmax), np.float32); ld = C.c_int(0); center = np.zeros(20, np.float32)
+        _chk(self.lib.liorf_sc_tensor_dump(self.h, _vp(qkeys), C.c_int(Q), _vp(out), C.c_longlong(out.size), C.byref(ld), _vp(center)), "liorf_sc_tensor_dump")
+        assert ld.value == ldmax
+        return out[:, :K], center
+
     def scQueryBatch(self, qdescs):
         qdescs = np.ascontiguousarray(qdescs, np.float64).reshape(-1, 1200)
         Q = len(qdescs)

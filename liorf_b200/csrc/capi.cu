@@ -9,6 +9,7 @@
 #include "scan2map.cuh"
 #include "deskew.cuh"
 #include "scancontext.cuh"
+#include "sc_tensor.cuh"
 #include "../host/host_logic.hpp"
 #include <vector>
 #include <cstring>
@@ -77,6 +78,12 @@ struct liorf_ctx {
     DevBuf<float> sc_part_d; DevBuf<int> sc_part_i;
     DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
     DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
+    // tensor-core ring-key search (sc_tensor.cuh): operand images + work buffers
+    DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_part, sct_thr, sct_qnorm; DevBuf<int> sct_cand, sct_cnt, sct_over;
+    float* sct_center = nullptr; unsigned* sct_nmax = nullptr; int* sct_over_cnt = nullptr;
+    int sct_img_n = -1;              // number of database keys the B image was built from (-1: none)
+    int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
+    bool sct_attr_set = false; int sct_last_Q = 0;
     Profiler prof;
     double host_us[6] = {0, 0, 0, 0, 0, 0}; long long host_frames = 0; bool host_timing = false;   // LIORF_HOST_TIMING=1
     cudaEvent_t tl_ev[8] = {nullptr}; double tl_ms[8] = {0}; // debug GPU timeline stamps of process_frame
@@ -279,6 +286,8 @@ void liorf_destroy(liorf_ctx* c) {
     c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); c->sc_part_d.release(); c->sc_part_i.release();
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
+    c->sct_bimg.release(); c->sct_aimg.release(); c->sct_part.release(); c->sct_thr.release(); c->sct_qnorm.release(); c->sct_cand.release(); c->sct_cnt.release();
+    c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
@@ -786,7 +795,7 @@ int liorf_sc_get(liorf_ctx* c, int i, double desc[1200], float ringkey[20], doub
 }
 
 // local exact top-3 of Q queries over keys[0:n_keys) → d_dist/d_idx [Q][3]; unfilled slots: dist +inf, idx INT_MAX
-static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
+static int sc_knn_brute(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
     int rc;
     if (Q <= 0) return LIORF_OK;
     const int bx = (Q + SCK_BLOCK - 1) / SCK_BLOCK;
@@ -800,6 +809,73 @@ static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_
     k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sc_part_d.p, c->sc_part_i.p, chunks, Q, d_dist, d_idx);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
+}
+
+// tensor-core path (sc_tensor.cuh): operand images → pass A (thresholds) → pass B (candidates) → exact re-rank.
+// The B image of the database is rebuilt only when the database grew since it was made.
+static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, SctArgs& a, int& grid) {
+    int rc;
+    const int nkt = (n_keys + SCT_KT - 1) / SCT_KT, n_sqt = (Q + SCT_QT - 1) / SCT_QT;
+    if (!c->sct_center) {
+        CUDA_TRY(cudaMalloc(&c->sct_center, SC_RING * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&c->sct_nmax, sizeof(unsigned)));
+        CUDA_TRY(cudaMalloc(&c->sct_over_cnt, sizeof(int)));
+    }
+    if (!c->sct_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
+        c->sct_attr_set = true;
+    }
+    if (c->sct_img_n != n_keys) {
+        if ((rc = c->sct_bimg.reserve((size_t)nkt * SCT_TILE_BYTES))) return rc;
+        k_sct_center<<<1, 1024, 0, c->stream>>>(c->sc_keys.p, n_keys, c->sct_center);
+        CUDA_TRY(cudaMemsetAsync(c->sct_nmax, 0, sizeof(unsigned), c->stream));
+        k_sct_image<true><<<(nkt * SCT_KT + 127) / 128, 128, 0, c->stream>>>(c->sc_keys.p, n_keys, nkt * SCT_KT, c->sct_center, c->sct_bimg.p, nullptr, c->sct_nmax);
+        CUDA_TRY(cudaGetLastError());
+        c->sct_img_n = n_keys; c->launches += 2;
+    }
+    const long long total = (long long)n_sqt * nkt;
+    grid = (int)(total < c->num_sms ? total : c->num_sms);
+    const long long spc_min = total / grid;
+    const int maxseg = (int)((nkt + spc_min - 1) / spc_min) + 1;
+    const size_t rows = (size_t)n_sqt * SCT_QT;
+    if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_thr.reserve(rows)) ||
+        (rc = c->sct_part.reserve(rows * maxseg * 3)) || (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q)) ||
+        (rc = c->sct_over.reserve(Q))) return rc;
+    k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, c->sct_center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
+    a.a_img = c->sct_aimg.p; a.b_img = c->sct_bimg.p; a.Q = Q; a.n_keys = n_keys; a.nkt = nkt; a.n_sqt = n_sqt;
+    a.part = c->sct_part.p; a.maxseg = maxseg; a.thr = c->sct_thr.p; a.cand = c->sct_cand.p; a.cand_cnt = c->sct_cnt.p; a.dump = nullptr; a.err_flag = c->d_err;
+    c->launches += 1;
+    return LIORF_OK;
+}
+
+static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
+    int rc, grid;
+    SctArgs a;
+    ProfScope ps(c, SEC_SC_SEARCH);
+    if ((rc = sct_prepare(c, n_keys, d_qkeys, Q, a, grid))) return rc;
+    const size_t rows = (size_t)a.n_sqt * SCT_QT;
+    CUDA_TRY(cudaMemsetAsync(c->sct_part.p, 0x7f, rows * a.maxseg * 3 * sizeof(float), c->stream));     // 0x7f7f7f7f = 3.39e38: "no value"
+    CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
+    k_sc_tensor<0><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
+    k_sct_threshold<<<(int)((rows + 255) / 256), 256, 0, c->stream>>>(c->sct_part.p, a.maxseg, (int)rows, c->sct_qnorm.p, Q, c->sct_nmax, c->sct_thr.p, c->sct_cnt.p);
+    k_sc_tensor<1><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
+    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p, c->sct_over_cnt);
+    k_sc_knn_overflow<<<64, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, global_offset, d_qkeys, c->sct_over.p, c->sct_over_cnt, d_dist, d_idx);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 5; c->sct_last_Q = Q;
+    return LIORF_OK;
+}
+
+static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
+    if (Q <= 0) return LIORF_OK;
+    // the tensor-core filter pays off for query batches against a sizeable database; the live detectLoopClosureID
+    // (one query) stays on the exact CUDA-core kernel
+    const bool can_tensor = d_keys == c->sc_keys.p && n_keys >= 1;
+    const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && n_keys >= 4096);
+    if (can_tensor && want_tensor) return sc_knn_tensor(c, n_keys, d_qkeys, Q, global_offset, d_dist, d_idx);
+    return sc_knn_brute(c, d_keys, n_keys, d_qkeys, Q, global_offset, d_dist, d_idx);
 }
 
 int liorf_sc_knn_batch_dev(liorf_ctx* c, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx) {
@@ -843,6 +919,52 @@ int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pai
                                                          (int*)d_shift, (double*)d_dist);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
+}
+
+/* selects the ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank */
+int liorf_sc_set_search_path(liorf_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return LIORF_ERR_ARG;
+    c->sc_path = mode;
+    return LIORF_OK;
+}
+/* statistics of the last tensor-core search: candidates emitted by the coarse filter (sum over queries), queries that
+ * overflowed their list and were answered by the brute-force kernel */
+int liorf_sc_tensor_stats(liorf_ctx* c, long long* n_candidates, int* n_overflow) {
+    if (!c || !n_candidates || !n_overflow) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    *n_candidates = 0; *n_overflow = 0;
+    const int Q = c->sct_last_Q;
+    if (Q <= 0 || !c->sct_cnt.p) return LIORF_OK;
+    std::vector<int> cnt(Q);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(cnt.data(), c->sct_cnt.p, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(n_overflow, c->sct_over_cnt, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int v : cnt) *n_candidates += v;
+    return LIORF_OK;
+}
+/* test hook: the raw tensor-core distances d~ of Q host queries (ring keys) against the whole database,
+ * out[(q) * ld + k] with ld = ceil(n_db / 128) * 128 (returned), center[20] = the database mean the images use */
+int liorf_sc_tensor_dump(liorf_ctx* c, const float* qkeys, int Q, float* out, long long out_capacity, int* ld, float center[20]) {
+    if (!c || !qkeys || Q <= 0 || !out || !ld) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (c->sc_n < 1) return LIORF_ERR_STATE;
+    int rc, grid;
+    if ((rc = c->sc_qkeys.reserve((size_t)Q * SC_RING))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->sc_qkeys.p, qkeys, (size_t)Q * SC_RING * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    SctArgs a;
+    if ((rc = sct_prepare(c, c->sc_n, c->sc_qkeys.p, Q, a, grid))) return rc;
+    const size_t rows = (size_t)a.n_sqt * SCT_QT, cols = (size_t)a.nkt * SCT_KT;
+    *ld = (int)cols;
+    if ((long long)((size_t)Q * cols) > out_capacity) return LIORF_ERR_ARG;
+    DevBuf<float> dump; if ((rc = dump.reserve(rows * cols))) return rc;
+    a.dump = dump.p;
+    k_sc_tensor<2><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dump.p, (size_t)Q * cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (center) CUDA_TRY(cudaMemcpyAsync(center, c->sct_center, SC_RING * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    rc = check_err(c);
+    dump.release();
+    return rc;
 }
 
 static int sc_reserve_query(liorf_ctx* c, int Q) {

@@ -1,0 +1,452 @@
+// sc_tensor.cuh — ScanContext ring-key search (detectLoopClosureID stage 1, include/Scancontext.cpp:289-295) as a dense
+// contraction on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA bulk copies).
+//
+// The reference asks a kd-tree for the exact 3 nearest 20-D fp32 ring keys (nanoflann, include/nanoflann.hpp:383-408).
+// A GEMM cannot reproduce nanoflann's fp32 operation order, so the tensor cores are used as a PROVABLY COMPLETE coarse
+// filter and the survivors are re-ranked with the exact arithmetic:
+//
+//   d~(q,k) = |x|^2 + |y|^2 - 2 x.y ,  x = q - c, y = k - c (c = database mean: shrinks the norms, hence the error)
+//   every fp32 value is split in two bf16 terms (hi + lo); the three significant cross terms, the two norms (split
+//   likewise) and the constant 1s are laid along ONE contraction axis of length 64:
+//       A row (query):  [ xh(20) | xh(20) | xl(20) | nxh nxl 1 1 ]
+//       B row (key)  :  [-2yh(20)|-2yl(20)|-2yh(20)| 1 1 nyh nyl ]
+//   so one 128x128x64 bf16 MMA chain with fp32 accumulation in TMEM yields d~ directly.
+//   |d~ - d| <= eps(q,k) = 2^-13 (|x|^2 + |y|^2)   (split truncation 3*2^-18, norm split 2^-17, accumulation budget
+//   2^-14; tests/test_gpu_sc_tensor.py measures the real error over millions of pairs and asserts a 4x margin).
+//
+//   pass A : per query, the 3rd smallest d~ over all keys                      -> t3(q)
+//   pass B : emit every key with d~ <= t3(q) + 2 eps_max(q)                    -> candidate list (<= SCT_CAP per query)
+//   re-rank: exact nanoflann-order distances of the candidates, top-3 by (dist, idx)
+//   Completeness: the exact 3rd-best distance d3 <= t3 + eps (the 3 keys behind t3 have exact distance <= t3 + eps),
+//   and a key of the exact top-3 has d~ <= d + eps <= d3 + eps <= t3 + 2 eps  =>  it is emitted.  A query whose list
+//   overflows is answered by the exact brute-force kernel instead (k_sc_knn_overflow) — never a wrong answer.
+//
+// Kernel shape (k_sc_tensor): persistent, one CTA per SM, 192 threads:
+//   warp 0   TMA producer: 16 KB operand images with cp.async.bulk + mbarrier complete_tx (6-stage B ring, 2 A buffers)
+//   warp 1   one lane issues tcgen05.mma (M=128,N=128,K=16 x4 k-steps x2 query sub-tiles per step), tcgen05.commit
+//   warps 2-5  epilogue: tcgen05.ld 32x32b.x32 from TMEM, 3-input min tree per 32 columns, rare slow path
+//   TMEM: 2 accumulator stages x (2 sub-tiles x 128 columns) = 512 columns.
+// The work list is the linearised (256-query tile, 128-key tile) grid cut into gridDim equal runs; a CTA keeps the two
+// query images resident and streams key images, so each key image is read from L2 once per 256 queries.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "scancontext.cuh"
+
+namespace liorf {
+
+constexpr int SCT_SUB = 128;                       // MMA M (queries per sub-tile) and N (keys per step)
+constexpr int SCT_QT = 2 * SCT_SUB;                // queries per CTA segment
+constexpr int SCT_KT = 128;                        // keys per step
+constexpr int SCT_KDIM = 64;                       // contraction length
+constexpr int SCT_TILE_BYTES = SCT_SUB * SCT_KDIM * 2;     // 16 KB operand image (128 rows x 64 bf16)
+constexpr int SCT_STAGES = 6;
+constexpr int SCT_CAP = 64;                        // candidates kept per query
+constexpr int SCT_THREADS = 192;
+constexpr float SCT_EPS_REL = 1.0f / 8192.0f;      // eps(q,k) = 2^-13 (|x|^2 + |y|^2)
+constexpr uint32_t SCT_LBO = 2048, SCT_SBO = 128;  // no-swizzle K-major image: 8x8 core matrices of 128 B; K-adjacent cores 2 KB apart
+constexpr int SCT_SMEM = 1024 + 4 * SCT_TILE_BYTES + SCT_STAGES * SCT_TILE_BYTES + 256;
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand images
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned short bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+__device__ __forceinline__ float bf16_val(unsigned short b) { return __uint_as_float((unsigned)b << 16); }
+
+__global__ void __launch_bounds__(1024) k_sct_center(const float* __restrict__ keys, int n, float* __restrict__ center) {
+    __shared__ double s_part[32][SC_RING];
+    double acc[SC_RING];
+#pragma unroll
+    for (int d = 0; d < SC_RING; ++d) acc[d] = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const float4* p = reinterpret_cast<const float4*>(keys + (size_t)SC_RING * r);
+#pragma unroll
+        for (int g = 0; g < 5; ++g) { float4 v = __ldg(p + g); acc[4 * g] += v.x; acc[4 * g + 1] += v.y; acc[4 * g + 2] += v.z; acc[4 * g + 3] += v.w; }
+    }
+#pragma unroll
+    for (int d = 0; d < SC_RING; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(FULL, acc[d], o);
+    }
+    if (lane_id() == 0) for (int d = 0; d < SC_RING; ++d) s_part[warp_id()][d] = acc[d];
+    __syncthreads();
+    if (threadIdx.x < SC_RING) {
+        double s = 0; for (int w = 0; w < (int)(blockDim.x / 32); ++w) s += s_part[w][threadIdx.x];
+        center[threadIdx.x] = n > 0 ? (float)(s / n) : 0.f;
+    }
+}
+
+// one thread per image row.  IS_KEY: B image (rows = keys, padded to a multiple of 128 with never-selected rows);
+// otherwise A image (rows = queries, padded to a multiple of 256 with zero rows).
+template <bool IS_KEY>
+__global__ void __launch_bounds__(128) k_sct_image(const float* __restrict__ vecs, int n, int n_pad, const float* __restrict__ center,
+                                                  uint8_t* __restrict__ img, float* __restrict__ norm_out, unsigned* __restrict__ nmax_bits) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    unsigned short v[SCT_KDIM];
+#pragma unroll
+    for (int k = 0; k < SCT_KDIM; ++k) v[k] = 0;
+    const unsigned short ONE = 0x3f80;
+    if (r < n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int d = 0; d < SC_RING; ++d) {
+            const float x = __ldg(vecs + (size_t)SC_RING * r + d) - __ldg(center + d);
+            acc += (double)x * (double)x;
+            const unsigned short h = bf16_bits(x);
+            const unsigned short l = bf16_bits(x - bf16_val(h));
+            if (IS_KEY) {
+                const unsigned short h2 = bf16_bits(-2.f * bf16_val(h)), l2 = bf16_bits(-2.f * bf16_val(l));
+                v[d] = h2; v[20 + d] = l2; v[40 + d] = h2;
+            } else { v[d] = h; v[20 + d] = h; v[40 + d] = l; }
+        }
+        const float nrm = (float)acc;
+        const unsigned short nh = bf16_bits(nrm), nl = bf16_bits(nrm - bf16_val(nh));
+        if (IS_KEY) { v[60] = ONE; v[61] = ONE; v[62] = nh; v[63] = nl; }
+        else { v[60] = nh; v[61] = nl; v[62] = ONE; v[63] = ONE; }
+        if (norm_out) norm_out[r] = nrm;
+        if (nmax_bits) atomicMax(nmax_bits, __float_as_uint(nrm));
+    } else if (IS_KEY) v[62] = bf16_bits(1e30f);
+    uint8_t* base = img + (size_t)(r / SCT_SUB) * SCT_TILE_BYTES + ((r % SCT_SUB) / 8) * SCT_SBO + (r % 8) * 16;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+        uint4 w;
+        w.x = v[8 * kc] | ((unsigned)v[8 * kc + 1] << 16); w.y = v[8 * kc + 2] | ((unsigned)v[8 * kc + 3] << 16);
+        w.z = v[8 * kc + 4] | ((unsigned)v[8 * kc + 5] << 16); w.w = v[8 * kc + 6] | ((unsigned)v[8 * kc + 7] << 16);
+        *reinterpret_cast<uint4*>(base + (size_t)kc * SCT_LBO) = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must end the kernel with an error flag, never hang the device
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* s_abort, int* err_flag) {
+    for (uint32_t it = 0; it < (1u << 21); ++it) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((it & 255u) == 255u && *s_abort) return false;
+    }
+    *s_abort = 1; atomicExch(err_flag, 3);
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+                 "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor, no swizzle, K-major: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version 1 [46,48)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(SCT_LBO >> 4) << 16) | ((uint64_t)(SCT_SBO >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t SCT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SCT_KT >> 3) << 17) | ((uint32_t)(SCT_SUB >> 4) << 24);
+
+#define SCT_R32(v) "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), \
+    "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define SCT_RW32(v) "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), \
+    "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), \
+    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+                 "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : SCT_R32(v) : "r"(taddr) : "memory");
+}
+// the registers of an earlier tmem_ld32 become valid here; tying them to the wait keeps every use after it
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : SCT_RW32(v) : : "memory"); }
+
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
+    float m[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) m[i] = min3f(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    m[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float a = min3f(m[0], m[1], m[2]), b = min3f(m[3], m[4], m[5]), c = min3f(m[6], m[7], m[8]), d = fminf(m[9], m[10]);
+    return fminf(min3f(a, b, c), d);
+}
+
+struct SctArgs {
+    const uint8_t* a_img;      // [n_sqt][2][SCT_TILE_BYTES]
+    const uint8_t* b_img;      // [nkt][SCT_TILE_BYTES]
+    int Q, n_keys, nkt, n_sqt;
+    float* part;               // pass A out: [n_sqt][maxseg][SCT_QT][3]   (pre-filled with a huge value)
+    int maxseg;
+    const float* thr;          // pass B in : [n_sqt * SCT_QT]  t3 + 2 eps
+    int* cand; int* cand_cnt;  // pass B out: [Q][SCT_CAP], [Q]
+    float* dump;               // PASS 2 (tests): every d~, [n_sqt * SCT_QT][nkt * SCT_KT]
+    int* err_flag;
+};
+
+__device__ __forceinline__ long long sct_first_step(int cta, long long total, int grid) { return (long long)cta * total / grid; }
+
+// PASS 0: thresholds (3 smallest d~ per query and segment)   PASS 1: candidate emission   PASS 2: dump d~ (tests)
+template <int PASS>
+__global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
+    extern __shared__ uint8_t sct_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)sct_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                            // [2 buffers][2 sub-tiles][16 KB]
+    uint8_t* sB = smem + 4 * SCT_TILE_BYTES;                       // [SCT_STAGES][16 KB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SCT_STAGES * SCT_TILE_BYTES);
+    // barrier indices
+    constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = B_FULL + SCT_STAGES, T_FULL = B_EMPTY + SCT_STAGES, T_EMPTY = T_FULL + 2, NBAR = T_EMPTY + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NBAR);
+    volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int warp = warp_id(), lane = lane_id();
+    const long long total = (long long)a.n_sqt * a.nkt;
+    const long long s_begin = sct_first_step(blockIdx.x, total, gridDim.x), s_end = sct_first_step(blockIdx.x + 1, total, gridDim.x);
+
+    if (threadIdx.x == 0) {
+        *s_abort = 0;
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 1); mbar_init(BAR(A_EMPTY + i), 1); mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
+        for (int i = 0; i < SCT_STAGES; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int seg = 0; uint32_t it = 0;
+            for (long long s = s_begin; s < s_end && !*s_abort; ++s, ++it) {
+                const int sqt = (int)(s / a.nkt), kt = (int)(s % a.nkt);
+                if (s == s_begin || kt == 0) {
+                    const int ab = seg & 1;
+                    if (!mbar_wait(BAR(A_EMPTY + ab), ((seg >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
+                    mbar_expect_tx(BAR(A_FULL + ab), 2 * SCT_TILE_BYTES);
+                    bulk_g2s(smem_u32(sA + (size_t)ab * 2 * SCT_TILE_BYTES), a.a_img + (size_t)sqt * 2 * SCT_TILE_BYTES, 2 * SCT_TILE_BYTES, BAR(A_FULL + ab));
+                    ++seg;
+                }
+                const int st = it % SCT_STAGES;
+                if (!mbar_wait(BAR(B_EMPTY + st), ((it / SCT_STAGES) & 1) ^ 1, s_abort, a.err_flag)) break;
+                mbar_expect_tx(BAR(B_FULL + st), SCT_TILE_BYTES);
+                bulk_g2s(smem_u32(sB + (size_t)st * SCT_TILE_BYTES), a.b_img + (size_t)kt * SCT_TILE_BYTES, SCT_TILE_BYTES, BAR(B_FULL + st));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one lane) =====
+        if (lane == 0) {
+            int seg = -1; uint32_t it = 0;
+            for (long long s = s_begin; s < s_end && !*s_abort; ++s, ++it) {
+                const int kt = (int)(s % a.nkt);
+                if (s == s_begin || kt == 0) {
+                    ++seg;
+                    if (!mbar_wait(BAR(A_FULL + (seg & 1)), (seg >> 1) & 1, s_abort, a.err_flag)) break;
+                }
+                const int ab = seg & 1, st = it % SCT_STAGES, acc = it & 1;
+                if (!mbar_wait(BAR(B_FULL + st), (it / SCT_STAGES) & 1, s_abort, a.err_flag)) break;
+                if (!mbar_wait(BAR(T_EMPTY + acc), ((it >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + (size_t)ab * 2 * SCT_TILE_BYTES), b_addr = smem_u32(sB + (size_t)st * SCT_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < SCT_KDIM / 16; ++ks) {
+                    const uint64_t db = smem_desc(b_addr + ks * 2 * SCT_LBO);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        tc_mma_bf16(tmem_base + acc * 256 + j * SCT_SUB, smem_desc(a_addr + j * SCT_TILE_BYTES + ks * 2 * SCT_LBO), db, SCT_IDESC, ks > 0 ? 1u : 0u);
+                }
+                tc_commit(BAR(B_EMPTY + st));                       // the key image may be overwritten once these MMAs have read it
+                tc_commit(BAR(T_FULL + acc));                       // accumulators ready for the epilogue
+                const bool seg_end = (s + 1 == s_end) || (kt == a.nkt - 1);
+                if (seg_end) tc_commit(BAR(A_EMPTY + ab));
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        const int qd = warp & 3;
+        const int row = 32 * qd + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(32 * qd) << 16);
+        float t1[2], t2[2], t3[2], thr[2];
+        int seg_in_sqt = 0;
+        uint32_t it = 0;
+        for (long long s = s_begin; s < s_end && !*s_abort; ++s, ++it) {
+            const int sqt = (int)(s / a.nkt), kt = (int)(s % a.nkt);
+            if (s == s_begin || kt == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    t1[j] = t2[j] = t3[j] = 3.0e38f;
+                    thr[j] = PASS == 1 ? __ldg(a.thr + (size_t)sqt * SCT_QT + j * SCT_SUB + row) : 3.0e38f;
+                }
+                if (PASS == 0) {
+                    // segment index of this CTA inside the query tile = CTAs between the one holding the tile's first step and this one
+                    const long long first = (long long)sqt * a.nkt;
+                    int c0 = (int)(first * gridDim.x / total);
+                    while (c0 + 1 < (int)gridDim.x && sct_first_step(c0 + 1, total, gridDim.x) <= first) ++c0;
+                    while (c0 > 0 && sct_first_step(c0, total, gridDim.x) > first) --c0;
+                    seg_in_sqt = (int)blockIdx.x - c0;
+                }
+            }
+            const int acc = it & 1;
+            if (!mbar_wait(BAR(T_FULL + acc), (it >> 1) & 1, s_abort, a.err_flag)) break;
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t tcol = t_lane + acc * 256 + j * SCT_SUB;
+                uint32_t va[32], vb[32];
+                __syncwarp();
+                tmem_ld32(tcol, va);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                    __syncwarp();                                   // .sync.aligned instructions: the warp must be converged after a slow path
+                    tmem_wait_ld(cur);
+                    if (c < 3) tmem_ld32(tcol + 32 * (c + 1), nxt);
+                    if (PASS == 2) {
+                        float* o = a.dump + ((size_t)sqt * SCT_QT + j * SCT_SUB + row) * ((size_t)a.nkt * SCT_KT) + (size_t)kt * SCT_KT + 32 * c;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(cur[i]);
+                    } else {
+                        const float m = min32(cur);
+                        if (PASS == 0) {
+                            if (m < t3[j]) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const float d = __uint_as_float(cur[i]);
+                                    if (d < t3[j]) {
+                                        t3[j] = d;
+                                        if (t3[j] < t2[j]) { const float x = t2[j]; t2[j] = t3[j]; t3[j] = x; }
+                                        if (t2[j] < t1[j]) { const float x = t1[j]; t1[j] = t2[j]; t2[j] = x; }
+                                    }
+                                }
+                            }
+                        } else {
+                            if (m <= thr[j]) {
+                                const int q = sqt * SCT_QT + j * SCT_SUB + row;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const float d = __uint_as_float(cur[i]);
+                                    const int kidx = kt * SCT_KT + 32 * c + i;
+                                    if (d <= thr[j] && kidx < a.n_keys && q < a.Q) {
+                                        const int slot = atomicAdd(a.cand_cnt + q, 1);
+                                        if (slot < SCT_CAP) a.cand[(size_t)q * SCT_CAP + slot] = kidx;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+            const bool seg_end = (s + 1 == s_end) || (kt == a.nkt - 1);
+            if (PASS == 0 && seg_end) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float* o = a.part + (((size_t)sqt * a.maxseg + seg_in_sqt) * SCT_QT + j * SCT_SUB + row) * 3;
+                    o[0] = t1[j]; o[1] = t2[j]; o[2] = t3[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// per query: 3rd smallest d~ over the segments of pass A, widened by 2 eps_max(q) = 2^-12 (|x|^2 + max |y|^2)
+__global__ void __launch_bounds__(256) k_sct_threshold(const float* __restrict__ part, int maxseg, int n_rows, const float* __restrict__ qnorm, int Q,
+                                                      const unsigned* __restrict__ nmax_bits, float* __restrict__ thr, int* __restrict__ cand_cnt) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_rows) return;
+    const int sqt = q / SCT_QT, row = q % SCT_QT;
+    float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
+    for (int sg = 0; sg < maxseg; ++sg) {
+        const float* p = part + (((size_t)sqt * maxseg + sg) * SCT_QT + row) * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float d = p[j];
+            if (d < t3) { t3 = d; if (t3 < t2) { float x = t2; t2 = t3; t3 = x; } if (t2 < t1) { float x = t1; t1 = t2; t2 = x; } }
+        }
+    }
+    const float nq = q < Q ? qnorm[q] : 0.f;
+    const float slack = 2.f * SCT_EPS_REL * (nq + __uint_as_float(*nmax_bits));
+    thr[q] = t3 < 1.0e38f ? t3 + slack : 3.0e38f;
+    if (q < Q) cand_cnt[q] = 0;
+}
+
+// exact re-rank: one warp per query; nanoflann's evalMetric op order (ringkey_dist_dev), total order (dist, idx)
+__global__ void __launch_bounds__(256) k_sct_rerank(const float* __restrict__ keys, int idx_offset, const float* __restrict__ qkeys, int Q, const int* __restrict__ cand,
+                                                   const int* __restrict__ cand_cnt, float* __restrict__ out_d, int* __restrict__ out_i, int* __restrict__ over_list,
+                                                   int* __restrict__ over_cnt) {
+    const int q = blockIdx.x * (blockDim.x / 32) + warp_id();
+    if (q >= Q) return;
+    const int l = lane_id();
+    const int n = cand_cnt[q];
+    if (n > SCT_CAP) { if (l == 0) { const int s = atomicAdd(over_cnt, 1); over_list[s] = q; } return; }
+    float aq[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) aq[k] = __ldg(qkeys + 20 * (size_t)q + k);
+    Top3 t; top3_init(t);
+    for (int i = l; i < n; i += 32) {
+        const int kidx = cand[(size_t)q * SCT_CAP + i];
+        const float d = ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)kidx));
+        top3_insert(t, d, idx_offset + kidx);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float md = t.d[0]; int mi = t.i[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(FULL, md, o); const int oi = __shfl_xor_sync(FULL, mi, o);
+            if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+        }
+        if (t.d[0] == md && t.i[0] == mi) { t.d[0] = t.d[1]; t.i[0] = t.i[1]; t.d[1] = t.d[2]; t.i[1] = t.i[2]; t.d[2] = INFINITY; t.i[2] = 0x7fffffff; }
+        if (l == 0) { out_d[3 * (size_t)q + r] = md; out_i[3 * (size_t)q + r] = mi; }
+    }
+}
+
+// queries whose candidate list overflowed: exact brute force, one block per query (grid-stride over the device-side list)
+__global__ void __launch_bounds__(256) k_sc_knn_overflow(const float* __restrict__ keys, int n_keys, int idx_offset, const float* __restrict__ qkeys,
+                                                        const int* __restrict__ over_list, const int* __restrict__ over_cnt, float* __restrict__ out_d, int* __restrict__ out_i) {
+    __shared__ float s_d[256 * 3]; __shared__ int s_i[256 * 3];
+    const int n_over = *over_cnt;
+    for (int o = blockIdx.x; o < n_over; o += gridDim.x) {
+        const int q = over_list[o];
+        float aq[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) aq[k] = __ldg(qkeys + 20 * (size_t)q + k);
+        Top3 t; top3_init(t);
+        for (int k = threadIdx.x; k < n_keys; k += blockDim.x) top3_insert(t, ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)k)), idx_offset + k);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { s_d[3 * threadIdx.x + j] = t.d[j]; s_i[3 * threadIdx.x + j] = t.i[j]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Top3 g; top3_init(g);
+            for (int e = 0; e < 256 * 3; ++e) if (s_i[e] != 0x7fffffff) top3_insert(g, s_d[e], s_i[e]);
+            for (int j = 0; j < 3; ++j) { out_d[3 * (size_t)q + j] = g.d[j]; out_i[3 * (size_t)q + j] = g.i[j]; }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace liorf

@@ -378,8 +378,10 @@ __global__ void __launch_bounds__(256) k_lm_hook(int iter, const float4* __restr
 //   pointSel = T * pointOri
 //   candidates: iteration-0 style FULL search walks the 27 cells and, on the way, stores every map point within
 //               (1 + m) of the query position q0 (m = S2M_MARGIN) as the query's cached candidate list.
-//               While |pointSel - q0| <= m - eps, every point that can be within 1 m of pointSel is in that list
-//               (triangle inequality), so later iterations scan ONLY the ~15-point list — same exact 5-NN, same order.
+//               While |pointSel - q0| <= m - eps AND pointSel stays in q0's grid cell, every point that can be within
+//               1 m of pointSel is in that list (triangle inequality for the radius; same cell so that the unit ball
+//               around pointSel stays inside the 27 cells that were searched), so later iterations scan ONLY the
+//               ~15-point list — same exact 5-NN, same order.
 //   plane     : depends only on the ordered neighbour ids → cached with them; the 5x3 QR is redone only when they change.
 //   products  : the 28 normal-equation products are split over the PG lanes, accumulated in fp64.
 // Per iteration and CTA: fixed-tree block reduction → partial[cta][28] → arrive on a counter.  The LAST CTA to arrive
@@ -583,7 +585,10 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                 float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
                 float moved = mx * mx; moved += my * my; moved += mz * mz;
                 const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
-                const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim;
+                // the list holds the points within 1 + m of q0 THAT LIE IN q0's 27 cells; the unit ball around pointSel stays
+                // inside that block of cells only while pointSel is in q0's own cell
+                const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
+                const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell;
                 Top5 mine; top5_init(mine);
                 int list_cnt;                                       // >= 0: results index the candidate list; -2: they index gmap... see below
                 if (use_cache) {
