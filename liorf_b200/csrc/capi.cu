@@ -831,7 +831,7 @@ static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, Sc
         if ((rc = c->sct_bimg.reserve((size_t)nkt * SCT_TILE_BYTES))) return rc;
         k_sct_center<<<1, 1024, 0, c->stream>>>(c->sc_keys.p, n_keys, c->sct_center);
         CUDA_TRY(cudaMemsetAsync(c->sct_nmax, 0, sizeof(unsigned), c->stream));
-        k_sct_image<true><<<(nkt * SCT_KT + 127) / 128, 128, 0, c->stream>>>(c->sc_keys.p, n_keys, nkt * SCT_KT, c->sct_center, c->sct_bimg.p, nullptr, c->sct_nmax);
+        k_sct_image<true><<<(nkt * SCT_KT + 127) / 128, 128, 0, c->stream>>>(c->sc_keys.p, n_keys, nkt * SCT_KT, nkt, c->sct_center, c->sct_bimg.p, nullptr, c->sct_nmax);
         CUDA_TRY(cudaGetLastError());
         c->sct_img_n = n_keys; c->launches += 2;
     }
@@ -843,7 +843,7 @@ static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, Sc
     if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_thr.reserve(rows)) ||
         (rc = c->sct_part.reserve(rows * maxseg * 3)) || (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q)) ||
         (rc = c->sct_over.reserve(Q))) return rc;
-    k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, c->sct_center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
+    k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, nkt, c->sct_center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
     a.a_img = c->sct_aimg.p; a.b_img = c->sct_bimg.p; a.Q = Q; a.n_keys = n_keys; a.nkt = nkt; a.n_sqt = n_sqt;
     a.part = c->sct_part.p; a.maxseg = maxseg; a.thr = c->sct_thr.p; a.cand = c->sct_cand.p; a.cand_cnt = c->sct_cnt.p; a.dump = nullptr; a.err_flag = c->d_err;
     c->launches += 1;

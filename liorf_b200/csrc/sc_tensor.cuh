@@ -14,10 +14,10 @@
 //   |d~ - d| <= eps(q,k) = 2^-13 (|x|^2 + |y|^2)   (split truncation 3*2^-18, norm split 2^-17, accumulation budget
 //   2^-14; tests/test_gpu_sc_tensor.py measures the real error over millions of pairs and asserts a 4x margin).
 //
-//   pass A : per query, the 3rd smallest d~ over all keys                      -> t3(q)
+//   pass A : per query, an upper bound of the 3rd smallest d~ over all keys      -> t3(q)  (3rd smallest of the per-32-key minima)
 //   pass B : emit every key with d~ <= t3(q) + 2 eps_max(q)                    -> candidate list (<= SCT_CAP per query)
 //   re-rank: exact nanoflann-order distances of the candidates, top-3 by (dist, idx)
-//   Completeness: the exact 3rd-best distance d3 <= t3 + eps (the 3 keys behind t3 have exact distance <= t3 + eps),
+//   Completeness: the exact 3rd-best distance d3 <= t3 + eps (three different keys have d~ <= t3, hence exact distance <= t3 + eps),
 //   and a key of the exact top-3 has d~ <= d + eps <= d3 + eps <= t3 + 2 eps  =>  it is emitted.  A query whose list
 //   overflows is answered by the exact brute-force kernel instead (k_sc_knn_overflow) — never a wrong answer.
 //
@@ -44,7 +44,9 @@ constexpr int SCT_STAGES = 6;
 constexpr int SCT_CAP = 64;                        // candidates kept per query
 constexpr int SCT_THREADS = 192;
 constexpr float SCT_EPS_REL = 1.0f / 8192.0f;      // eps(q,k) = 2^-13 (|x|^2 + |y|^2)
-constexpr uint32_t SCT_LBO = 2048, SCT_SBO = 128;  // no-swizzle K-major image: 8x8 core matrices of 128 B; K-adjacent cores 2 KB apart
+// operand image = the canonical K-major SWIZZLE_128B shared-memory layout (what TMA writes for a 64-element bf16 box):
+// one 128-byte row per query/key, 8-row groups of 1024 B, 16-byte chunk c of row r stored at chunk position c ^ (r % 8)
+constexpr uint32_t SCT_SBO = 1024;
 constexpr int SCT_SMEM = 1024 + 4 * SCT_TILE_BYTES + SCT_STAGES * SCT_TILE_BYTES + 256;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -76,13 +78,16 @@ __global__ void __launch_bounds__(1024) k_sct_center(const float* __restrict__ k
     }
 }
 
-// one thread per image row.  IS_KEY: B image (rows = keys, padded to a multiple of 128 with never-selected rows);
-// otherwise A image (rows = queries, padded to a multiple of 256 with zero rows).
+// one thread per image row.  IS_KEY: B image, rows = keys padded to nkt * 128 with never-selected rows; image position
+// p = tile * 128 + col holds key (col * nkt + tile), so keys adjacent in the database (similar ring keys along a drive)
+// land in different tiles and the per-32-column minima the epilogue tracks stay decorrelated.  Otherwise A image,
+// rows = queries in order, padded to a multiple of 256 with zero rows.
 template <bool IS_KEY>
-__global__ void __launch_bounds__(128) k_sct_image(const float* __restrict__ vecs, int n, int n_pad, const float* __restrict__ center,
+__global__ void __launch_bounds__(128) k_sct_image(const float* __restrict__ vecs, int n, int n_pad, int nkt, const float* __restrict__ center,
                                                   uint8_t* __restrict__ img, float* __restrict__ norm_out, unsigned* __restrict__ nmax_bits) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_pad) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    const int r = IS_KEY ? (p % SCT_SUB) * nkt + p / SCT_SUB : p;
     unsigned short v[SCT_KDIM];
 #pragma unroll
     for (int k = 0; k < SCT_KDIM; ++k) v[k] = 0;
@@ -107,13 +112,14 @@ __global__ void __launch_bounds__(128) k_sct_image(const float* __restrict__ vec
         if (norm_out) norm_out[r] = nrm;
         if (nmax_bits) atomicMax(nmax_bits, __float_as_uint(nrm));
     } else if (IS_KEY) v[62] = bf16_bits(1e30f);
-    uint8_t* base = img + (size_t)(r / SCT_SUB) * SCT_TILE_BYTES + ((r % SCT_SUB) / 8) * SCT_SBO + (r % 8) * 16;
+    const int row = p % SCT_SUB;
+    uint8_t* base = img + (size_t)(p / SCT_SUB) * SCT_TILE_BYTES + (size_t)row * 128;
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) {
         uint4 w;
         w.x = v[8 * kc] | ((unsigned)v[8 * kc + 1] << 16); w.y = v[8 * kc + 2] | ((unsigned)v[8 * kc + 3] << 16);
         w.z = v[8 * kc + 4] | ((unsigned)v[8 * kc + 5] << 16); w.w = v[8 * kc + 6] | ((unsigned)v[8 * kc + 7] << 16);
-        *reinterpret_cast<uint4*>(base + (size_t)kc * SCT_LBO) = w;
+        *reinterpret_cast<uint4*>(base + ((kc ^ (row & 7)) << 4)) = w;
     }
 }
 
@@ -150,9 +156,11 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
                  "r"(idesc), "r"(accumulate) : "memory");
 }
-// shared-memory matrix descriptor, no swizzle, K-major: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version 1 [46,48)
+// shared-memory matrix descriptor, K-major SWIZZLE_128B: start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major: 1),
+// SBO>>4 [32,46) = 1024 B between 8-row groups, version 1 [46,48), layout type 2 [61,64).  A k-step of 16 bf16 advances the
+// start address by 32 B inside the swizzle atom.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(SCT_LBO >> 4) << 16) | ((uint64_t)(SCT_SBO >> 4) << 32) | (1ull << 46);
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(SCT_SBO >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t SCT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SCT_KT >> 3) << 17) | ((uint32_t)(SCT_SUB >> 4) << 24);
@@ -265,10 +273,10 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
                 const uint32_t a_addr = smem_u32(sA + (size_t)ab * 2 * SCT_TILE_BYTES), b_addr = smem_u32(sB + (size_t)st * SCT_TILE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < SCT_KDIM / 16; ++ks) {
-                    const uint64_t db = smem_desc(b_addr + ks * 2 * SCT_LBO);
+                    const uint64_t db = smem_desc(b_addr + ks * 32);
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
-                        tc_mma_bf16(tmem_base + acc * 256 + j * SCT_SUB, smem_desc(a_addr + j * SCT_TILE_BYTES + ks * 2 * SCT_LBO), db, SCT_IDESC, ks > 0 ? 1u : 0u);
+                        tc_mma_bf16(tmem_base + acc * 256 + j * SCT_SUB, smem_desc(a_addr + j * SCT_TILE_BYTES + ks * 32), db, SCT_IDESC, ks > 0 ? 1u : 0u);
                 }
                 tc_commit(BAR(B_EMPTY + st));                       // the key image may be overwritten once these MMAs have read it
                 tc_commit(BAR(T_FULL + acc));                       // accumulators ready for the epilogue
@@ -318,30 +326,24 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
                     tmem_wait_ld(cur);
                     if (c < 3) tmem_ld32(tcol + 32 * (c + 1), nxt);
                     if (PASS == 2) {
-                        float* o = a.dump + ((size_t)sqt * SCT_QT + j * SCT_SUB + row) * ((size_t)a.nkt * SCT_KT) + (size_t)kt * SCT_KT + 32 * c;
+                        float* o = a.dump + ((size_t)sqt * SCT_QT + j * SCT_SUB + row) * ((size_t)a.nkt * SCT_KT);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(cur[i]);
+                        for (int i = 0; i < 32; ++i) o[(size_t)(32 * c + i) * a.nkt + kt] = __uint_as_float(cur[i]);
                     } else {
                         const float m = min32(cur);
                         if (PASS == 0) {
-                            if (m < t3[j]) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const float d = __uint_as_float(cur[i]);
-                                    if (d < t3[j]) {
-                                        t3[j] = d;
-                                        if (t3[j] < t2[j]) { const float x = t2[j]; t2[j] = t3[j]; t3[j] = x; }
-                                        if (t2[j] < t1[j]) { const float x = t1[j]; t1[j] = t2[j]; t2[j] = x; }
-                                    }
-                                }
-                            }
+                            // branch-free top-3 of the per-32-column minima: three minima belong to three different keys, so
+                            // the 3rd smallest of them bounds the 3rd smallest d~ from above — all the filter needs
+                            const float b = fmaxf(m, t1[j]); t1[j] = fminf(m, t1[j]);
+                            const float e = fmaxf(b, t2[j]); t2[j] = fminf(b, t2[j]);
+                            t3[j] = fminf(e, t3[j]);
                         } else {
                             if (m <= thr[j]) {
                                 const int q = sqt * SCT_QT + j * SCT_SUB + row;
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     const float d = __uint_as_float(cur[i]);
-                                    const int kidx = kt * SCT_KT + 32 * c + i;
+                                    const int kidx = (32 * c + i) * a.nkt + kt;       // image position → database key (see k_sct_image)
                                     if (d <= thr[j] && kidx < a.n_keys && q < a.Q) {
                                         const int slot = atomicAdd(a.cand_cnt + q, 1);
                                         if (slot < SCT_CAP) a.cand[(size_t)q * SCT_CAP + slot] = kidx;
