@@ -79,7 +79,7 @@ struct liorf_ctx {
     DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
     DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
     // tensor-core ring-key search (sc_tensor.cuh): operand images + work buffers
-    DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_part, sct_thr, sct_qnorm; DevBuf<int> sct_cand, sct_cnt, sct_over;
+    DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_cmin, sct_qnorm; DevBuf<int> sct_cand, sct_cnt, sct_over;
     float* sct_center = nullptr; unsigned* sct_nmax = nullptr; int* sct_over_cnt = nullptr;
     int sct_img_n = -1;              // number of database keys the B image was built from (-1: none)
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
@@ -286,7 +286,7 @@ void liorf_destroy(liorf_ctx* c) {
     c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); c->sc_part_d.release(); c->sc_part_i.release();
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
-    c->sct_bimg.release(); c->sct_aimg.release(); c->sct_part.release(); c->sct_thr.release(); c->sct_qnorm.release(); c->sct_cand.release(); c->sct_cnt.release();
+    c->sct_bimg.release(); c->sct_aimg.release(); c->sct_cmin.release(); c->sct_qnorm.release(); c->sct_cand.release(); c->sct_cnt.release();
     c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
@@ -822,9 +822,8 @@ static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, Sc
         CUDA_TRY(cudaMalloc(&c->sct_over_cnt, sizeof(int)));
     }
     if (!c->sct_attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
-        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
-        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
         c->sct_attr_set = true;
     }
     if (c->sct_img_n != n_keys) {
@@ -837,15 +836,12 @@ static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, Sc
     }
     const long long total = (long long)n_sqt * nkt;
     grid = (int)(total < c->num_sms ? total : c->num_sms);
-    const long long spc_min = total / grid;
-    const int maxseg = (int)((nkt + spc_min - 1) / spc_min) + 1;
     const size_t rows = (size_t)n_sqt * SCT_QT;
-    if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_thr.reserve(rows)) ||
-        (rc = c->sct_part.reserve(rows * maxseg * 3)) || (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q)) ||
-        (rc = c->sct_over.reserve(Q))) return rc;
+    if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_cmin.reserve(rows * nkt * 4)) ||
+        (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q)) || (rc = c->sct_over.reserve(Q))) return rc;
     k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, nkt, c->sct_center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
     a.a_img = c->sct_aimg.p; a.b_img = c->sct_bimg.p; a.Q = Q; a.n_keys = n_keys; a.nkt = nkt; a.n_sqt = n_sqt;
-    a.part = c->sct_part.p; a.maxseg = maxseg; a.thr = c->sct_thr.p; a.cand = c->sct_cand.p; a.cand_cnt = c->sct_cnt.p; a.dump = nullptr; a.err_flag = c->d_err;
+    a.cmin = c->sct_cmin.p; a.dump = nullptr; a.err_flag = c->d_err;
     c->launches += 1;
     return LIORF_OK;
 }
@@ -855,16 +851,15 @@ static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, 
     SctArgs a;
     ProfScope ps(c, SEC_SC_SEARCH);
     if ((rc = sct_prepare(c, n_keys, d_qkeys, Q, a, grid))) return rc;
-    const size_t rows = (size_t)a.n_sqt * SCT_QT;
-    CUDA_TRY(cudaMemsetAsync(c->sct_part.p, 0x7f, rows * a.maxseg * 3 * sizeof(float), c->stream));     // 0x7f7f7f7f = 3.39e38: "no value"
+    const int rows = a.n_sqt * SCT_QT;
     CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
-    k_sc_tensor<0><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
-    k_sct_threshold<<<(int)((rows + 255) / 256), 256, 0, c->stream>>>(c->sct_part.p, a.maxseg, (int)rows, c->sct_qnorm.p, Q, c->sct_nmax, c->sct_thr.p, c->sct_cnt.p);
-    k_sc_tensor<1><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
-    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p, c->sct_over_cnt);
+    k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
+    k_sct_select<<<rows / 32, 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, a.nkt * 4, rows, c->sct_qnorm.p, Q, c->sct_nmax, c->sct_cand.p, c->sct_cnt.p);
+    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, a.nkt, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p,
+                                                     c->sct_over_cnt);
     k_sc_knn_overflow<<<64, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, global_offset, d_qkeys, c->sct_over.p, c->sct_over_cnt, d_dist, d_idx);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 5; c->sct_last_Q = Q;
+    c->launches += 4; c->sct_last_Q = Q;
     return LIORF_OK;
 }
 
@@ -958,7 +953,7 @@ int liorf_sc_tensor_dump(liorf_ctx* c, const float* qkeys, int Q, float* out, lo
     if ((long long)((size_t)Q * cols) > out_capacity) return LIORF_ERR_ARG;
     DevBuf<float> dump; if ((rc = dump.reserve(rows * cols))) return rc;
     a.dump = dump.p;
-    k_sc_tensor<2><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
+    k_sc_tensor<true><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, dump.p, (size_t)Q * cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (center) CUDA_TRY(cudaMemcpyAsync(center, c->sct_center, SC_RING * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

@@ -14,17 +14,20 @@
 //   |d~ - d| <= eps(q,k) = 2^-13 (|x|^2 + |y|^2)   (split truncation 3*2^-18, norm split 2^-17, accumulation budget
 //   2^-14; tests/test_gpu_sc_tensor.py measures the real error over millions of pairs and asserts a 4x margin).
 //
-//   pass A : per query, an upper bound of the 3rd smallest d~ over all keys      -> t3(q)  (3rd smallest of the per-32-key minima)
-//   pass B : emit every key with d~ <= t3(q) + 2 eps_max(q)                    -> candidate list (<= SCT_CAP per query)
-//   re-rank: exact nanoflann-order distances of the candidates, top-3 by (dist, idx)
-//   Completeness: the exact 3rd-best distance d3 <= t3 + eps (three different keys have d~ <= t3, hence exact distance <= t3 + eps),
-//   and a key of the exact top-3 has d~ <= d + eps <= d3 + eps <= t3 + 2 eps  =>  it is emitted.  A query whose list
-//   overflows is answered by the exact brute-force kernel instead (k_sc_knn_overflow) — never a wrong answer.
+//   k_sc_tensor : the GEMM; its epilogue reduces every 32 consecutive accumulator columns (a "chunk" = 32 keys) to
+//                 their minimum and stores only that: cmin[chunk][query]  (1/32 of the Q x K matrix, L2 resident)
+//   k_sct_select: per query t3 = 3rd smallest chunk minimum (three different chunks hold three different keys, so t3
+//                 bounds the 3rd smallest d~ from above), then every chunk with cmin <= t3 + 2 eps_max(q) is a candidate
+//   k_sct_rerank: exact nanoflann-order distances of the <= 32 keys of each candidate chunk, top-3 by (dist, idx)
+//   Completeness: the exact 3rd-best distance d3 <= t3 + eps (three different keys have d~ <= t3, hence exact distance
+//   <= t3 + eps), and a key of the exact top-3 has d~ <= d + eps <= d3 + eps <= t3 + 2 eps  =>  its chunk is a candidate.
+//   A query with more than SCT_CAP candidate chunks is answered by the exact brute-force kernel instead
+//   (k_sc_knn_overflow) — never a wrong answer.
 //
-// Kernel shape (k_sc_tensor): persistent, one CTA per SM, 192 threads:
-//   warp 0   TMA producer: 16 KB operand images with cp.async.bulk + mbarrier complete_tx (6-stage B ring, 2 A buffers)
-//   warp 1   one lane issues tcgen05.mma (M=128,N=128,K=16 x4 k-steps x2 query sub-tiles per step), tcgen05.commit
-//   warps 2-5  epilogue: tcgen05.ld 32x32b.x32 from TMEM, 3-input min tree per 32 columns, rare slow path
+// Kernel shape (k_sc_tensor): persistent, one CTA per SM, 320 threads:
+//   warp 0     TMA producer: 16 KB operand images with cp.async.bulk + mbarrier complete_tx (6-stage key ring, 2 query buffers)
+//   warp 1     one lane issues tcgen05.mma (M=128,N=128,K=16 x4 k-steps x2 query sub-tiles per step), tcgen05.commit
+//   warps 2-9  epilogue (one 128x128 accumulator each): 4 x tcgen05.ld 32x32b.x32 in flight, min trees, 4 coalesced stores
 //   TMEM: 2 accumulator stages x (2 sub-tiles x 128 columns) = 512 columns.
 // The work list is the linearised (256-query tile, 128-key tile) grid cut into gridDim equal runs; a CTA keeps the two
 // query images resident and streams key images, so each key image is read from L2 once per 256 queries.
@@ -41,8 +44,9 @@ constexpr int SCT_KT = 128;                        // keys per step
 constexpr int SCT_KDIM = 64;                       // contraction length
 constexpr int SCT_TILE_BYTES = SCT_SUB * SCT_KDIM * 2;     // 16 KB operand image (128 rows x 64 bf16)
 constexpr int SCT_STAGES = 6;
-constexpr int SCT_CAP = 64;                        // candidates kept per query
-constexpr int SCT_THREADS = 192;
+constexpr int SCT_CAP = 64;                        // candidate chunks (of 32 keys) kept per query
+constexpr int SCT_CHUNK = 32;                      // accumulator columns reduced to one minimum
+constexpr int SCT_THREADS = 320;                   // producer warp, MMA warp, 8 epilogue warps
 constexpr float SCT_EPS_REL = 1.0f / 8192.0f;      // eps(q,k) = 2^-13 (|x|^2 + |y|^2)
 // operand image = the canonical K-major SWIZZLE_128B shared-memory layout (what TMA writes for a 64-element bf16 box):
 // one 128-byte row per query/key, 8-row groups of 1024 B, 16-byte chunk c of row r stored at chunk position c ^ (r % 8)
@@ -179,39 +183,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // the registers of an earlier tmem_ld32 become valid here; tying them to the wait keeps every use after it
 __device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : SCT_RW32(v) : : "memory"); }
 
-__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t (&c)[32], uint32_t (&d)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : SCT_RW32(a) : : "memory");
+    asm volatile("" : SCT_RW32(b) : : "memory");
+    asm volatile("" : SCT_RW32(c) : : "memory");
+    asm volatile("" : SCT_RW32(d) : : "memory");
+}
+// 2-input minimum tree (FMNMX on the ALU pipe; the 3-input FMNMX3 form issues at a fraction of that rate)
 __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
-    float m[11];
+    float m[16];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) m[i] = min3f(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-    m[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-    const float a = min3f(m[0], m[1], m[2]), b = min3f(m[3], m[4], m[5]), c = min3f(m[6], m[7], m[8]), d = fminf(m[9], m[10]);
-    return fminf(min3f(a, b, c), d);
+    for (int i = 0; i < 16; ++i) m[i] = fminf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; ++i) m[i] = fminf(m[i], m[i + w]);
+    }
+    return m[0];
+}
+__device__ __forceinline__ void top3_min_update(float m, float& t1, float& t2, float& t3) {
+    const float b = fmaxf(m, t1); t1 = fminf(m, t1);
+    const float e = fmaxf(b, t2); t2 = fminf(b, t2);
+    t3 = fminf(e, t3);
 }
 
 struct SctArgs {
     const uint8_t* a_img;      // [n_sqt][2][SCT_TILE_BYTES]
     const uint8_t* b_img;      // [nkt][SCT_TILE_BYTES]
     int Q, n_keys, nkt, n_sqt;
-    float* part;               // pass A out: [n_sqt][maxseg][SCT_QT][3]   (pre-filled with a huge value)
-    int maxseg;
-    const float* thr;          // pass B in : [n_sqt * SCT_QT]  t3 + 2 eps
-    int* cand; int* cand_cnt;  // pass B out: [Q][SCT_CAP], [Q]
-    float* dump;               // PASS 2 (tests): every d~, [n_sqt * SCT_QT][nkt * SCT_KT]
+    float* cmin;               // out: [nkt * 4][n_sqt * SCT_QT]  minimum d~ of each 32-key chunk
+    float* dump;               // DUMP (tests): every d~, [n_sqt * SCT_QT][nkt * SCT_KT] indexed by database key
     int* err_flag;
 };
 
 __device__ __forceinline__ long long sct_first_step(int cta, long long total, int grid) { return (long long)cta * total / grid; }
 
-// PASS 0: thresholds (3 smallest d~ per query and segment)   PASS 1: candidate emission   PASS 2: dump d~ (tests)
-template <int PASS>
+template <bool DUMP>
 __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
     extern __shared__ uint8_t sct_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)sct_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                            // [2 buffers][2 sub-tiles][16 KB]
     uint8_t* sB = smem + 4 * SCT_TILE_BYTES;                       // [SCT_STAGES][16 KB]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SCT_STAGES * SCT_TILE_BYTES);
-    // barrier indices
     constexpr int A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = B_FULL + SCT_STAGES, T_FULL = B_EMPTY + SCT_STAGES, T_EMPTY = T_FULL + 2, NBAR = T_EMPTY + 2;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NBAR);
     volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
@@ -221,10 +234,11 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
     const int warp = warp_id(), lane = lane_id();
     const long long total = (long long)a.n_sqt * a.nkt;
     const long long s_begin = sct_first_step(blockIdx.x, total, gridDim.x), s_end = sct_first_step(blockIdx.x + 1, total, gridDim.x);
+    const int sqt0 = (int)(s_begin / a.nkt), kt0 = (int)(s_begin % a.nkt);          // the only division: the roles step (sqt, kt) incrementally
 
     if (threadIdx.x == 0) {
         *s_abort = 0;
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 1); mbar_init(BAR(A_EMPTY + i), 1); mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 1); mbar_init(BAR(A_EMPTY + i), 1); mbar_init(BAR(T_FULL + i), 1); mbar_init(BAR(T_EMPTY + i), 8); }
         for (int i = 0; i < SCT_STAGES; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -236,14 +250,14 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    const int n_steps = (int)(s_end - s_begin);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int seg = 0; uint32_t it = 0;
-            for (long long s = s_begin; s < s_end && !*s_abort; ++s, ++it) {
-                const int sqt = (int)(s / a.nkt), kt = (int)(s % a.nkt);
-                if (s == s_begin || kt == 0) {
+            int seg = 0, sqt = sqt0, kt = kt0;
+            for (int it = 0; it < n_steps && !*s_abort; ++it) {
+                if (it == 0 || kt == 0) {
                     const int ab = seg & 1;
                     if (!mbar_wait(BAR(A_EMPTY + ab), ((seg >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
                     mbar_expect_tx(BAR(A_FULL + ab), 2 * SCT_TILE_BYTES);
@@ -254,15 +268,15 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
                 if (!mbar_wait(BAR(B_EMPTY + st), ((it / SCT_STAGES) & 1) ^ 1, s_abort, a.err_flag)) break;
                 mbar_expect_tx(BAR(B_FULL + st), SCT_TILE_BYTES);
                 bulk_g2s(smem_u32(sB + (size_t)st * SCT_TILE_BYTES), a.b_img + (size_t)kt * SCT_TILE_BYTES, SCT_TILE_BYTES, BAR(B_FULL + st));
+                if (++kt == a.nkt) { kt = 0; ++sqt; }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one lane) =====
         if (lane == 0) {
-            int seg = -1; uint32_t it = 0;
-            for (long long s = s_begin; s < s_end && !*s_abort; ++s, ++it) {
-                const int kt = (int)(s % a.nkt);
-                if (s == s_begin || kt == 0) {
+            int seg = -1, kt = kt0;
+            for (int it = 0; it < n_steps && !*s_abort; ++it) {
+                if (it == 0 || kt == 0) {
                     ++seg;
                     if (!mbar_wait(BAR(A_FULL + (seg & 1)), (seg >> 1) & 1, s_abort, a.err_flag)) break;
                 }
@@ -280,91 +294,44 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
                 }
                 tc_commit(BAR(B_EMPTY + st));                       // the key image may be overwritten once these MMAs have read it
                 tc_commit(BAR(T_FULL + acc));                       // accumulators ready for the epilogue
-                const bool seg_end = (s + 1 == s_end) || (kt == a.nkt - 1);
+                const bool seg_end = (it + 1 == n_steps) || (kt == a.nkt - 1);
                 if (seg_end) tc_commit(BAR(A_EMPTY + ab));
+                if (++kt == a.nkt) kt = 0;
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
-        const int qd = warp & 3;
+        // ===== epilogue: 8 warps; TMEM lane quadrant = warp % 4, query sub-tile j = (warp - 2) / 4 =====
+        // Two warps share each SM sub-partition, so one warp's TMEM loads overlap the other's min tree.
+        const int qd = warp & 3, j = (warp - 2) >> 2;
         const int row = 32 * qd + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(32 * qd) << 16);
-        float t1[2], t2[2], t3[2], thr[2];
-        int seg_in_sqt = 0;
-        uint32_t it = 0;
-        for (long long s = s_begin; s < s_end && !*s_abort; ++s, ++it) {
-            const int sqt = (int)(s / a.nkt), kt = (int)(s % a.nkt);
-            if (s == s_begin || kt == 0) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    t1[j] = t2[j] = t3[j] = 3.0e38f;
-                    thr[j] = PASS == 1 ? __ldg(a.thr + (size_t)sqt * SCT_QT + j * SCT_SUB + row) : 3.0e38f;
-                }
-                if (PASS == 0) {
-                    // segment index of this CTA inside the query tile = CTAs between the one holding the tile's first step and this one
-                    const long long first = (long long)sqt * a.nkt;
-                    int c0 = (int)(first * gridDim.x / total);
-                    while (c0 + 1 < (int)gridDim.x && sct_first_step(c0 + 1, total, gridDim.x) <= first) ++c0;
-                    while (c0 > 0 && sct_first_step(c0, total, gridDim.x) > first) --c0;
-                    seg_in_sqt = (int)blockIdx.x - c0;
-                }
-            }
+        const uint32_t t_lane = tmem_base + ((uint32_t)(32 * qd) << 16) + j * SCT_SUB;
+        const size_t n_rows = (size_t)a.n_sqt * SCT_QT;
+        int sqt = sqt0, kt = kt0;
+        for (int it = 0; it < n_steps && !*s_abort; ++it) {
+            const int q = sqt * SCT_QT + j * SCT_SUB + row;
             const int acc = it & 1;
             if (!mbar_wait(BAR(T_FULL + acc), (it >> 1) & 1, s_abort, a.err_flag)) break;
             tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t tcol = t_lane + acc * 256 + j * SCT_SUB;
-                uint32_t va[32], vb[32];
-                __syncwarp();
-                tmem_ld32(tcol, va);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
-                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-                    __syncwarp();                                   // .sync.aligned instructions: the warp must be converged after a slow path
-                    tmem_wait_ld(cur);
-                    if (c < 3) tmem_ld32(tcol + 32 * (c + 1), nxt);
-                    if (PASS == 2) {
-                        float* o = a.dump + ((size_t)sqt * SCT_QT + j * SCT_SUB + row) * ((size_t)a.nkt * SCT_KT);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[(size_t)(32 * c + i) * a.nkt + kt] = __uint_as_float(cur[i]);
-                    } else {
-                        const float m = min32(cur);
-                        if (PASS == 0) {
-                            // branch-free top-3 of the per-32-column minima: three minima belong to three different keys, so
-                            // the 3rd smallest of them bounds the 3rd smallest d~ from above — all the filter needs
-                            const float b = fmaxf(m, t1[j]); t1[j] = fminf(m, t1[j]);
-                            const float e = fmaxf(b, t2[j]); t2[j] = fminf(b, t2[j]);
-                            t3[j] = fminf(e, t3[j]);
-                        } else {
-                            if (m <= thr[j]) {
-                                const int q = sqt * SCT_QT + j * SCT_SUB + row;
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const float d = __uint_as_float(cur[i]);
-                                    const int kidx = (32 * c + i) * a.nkt + kt;       // image position → database key (see k_sct_image)
-                                    if (d <= thr[j] && kidx < a.n_keys && q < a.Q) {
-                                        const int slot = atomicAdd(a.cand_cnt + q, 1);
-                                        if (slot < SCT_CAP) a.cand[(size_t)q * SCT_CAP + slot] = kidx;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+            const uint32_t tcol = t_lane + acc * 256;
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            __syncwarp();
+            tmem_ld32(tcol, v0); tmem_ld32(tcol + 32, v1); tmem_ld32(tcol + 64, v2); tmem_ld32(tcol + 96, v3);      // 16 KB per warp in flight
+            tmem_wait_ld4(v0, v1, v2, v3);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
-            const bool seg_end = (s + 1 == s_end) || (kt == a.nkt - 1);
-            if (PASS == 0 && seg_end) {
+            if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));        // the values are in registers: release the accumulator stage early
+            if (DUMP) {
+                float* o = a.dump + (size_t)q * ((size_t)a.nkt * SCT_KT);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float* o = a.part + (((size_t)sqt * a.maxseg + seg_in_sqt) * SCT_QT + j * SCT_SUB + row) * 3;
-                    o[0] = t1[j]; o[1] = t2[j]; o[2] = t3[j];
+                for (int i = 0; i < 32; ++i) {
+                    o[(size_t)i * a.nkt + kt] = __uint_as_float(v0[i]); o[(size_t)(32 + i) * a.nkt + kt] = __uint_as_float(v1[i]);
+                    o[(size_t)(64 + i) * a.nkt + kt] = __uint_as_float(v2[i]); o[(size_t)(96 + i) * a.nkt + kt] = __uint_as_float(v3[i]);
                 }
+            } else {
+                float* o = a.cmin + (size_t)kt * 4 * n_rows + q;   // lanes = consecutive queries: each store is one 128-byte line
+                o[0] = min32(v0); o[n_rows] = min32(v1); o[2 * n_rows] = min32(v2); o[3 * n_rows] = min32(v3);
             }
+            if (++kt == a.nkt) { kt = 0; ++sqt; }
         }
     }
     tc_fence_before();
@@ -375,31 +342,64 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
     }
 }
 
-// per query: 3rd smallest d~ over the segments of pass A, widened by 2 eps_max(q) = 2^-12 (|x|^2 + max |y|^2)
-__global__ void __launch_bounds__(256) k_sct_threshold(const float* __restrict__ part, int maxseg, int n_rows, const float* __restrict__ qnorm, int Q,
-                                                      const unsigned* __restrict__ nmax_bits, float* __restrict__ thr, int* __restrict__ cand_cnt) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_rows) return;
-    const int sqt = q / SCT_QT, row = q % SCT_QT;
+// Candidate selection on the chunk minima.  Block = 32 queries x 32 chunk slices; the block sees ALL chunks of its queries:
+// phase 1 reduces them to t3(q) (3rd smallest chunk minimum), phase 2 re-reads them (L1/L2 hits) and appends every chunk
+// with cmin <= t3 + 2 eps_max(q),  2 eps_max = 2^-12 (|x|^2 + max_k |y|^2), to the query's candidate list.
+constexpr int SCS_SLICES = 32;
+__global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __restrict__ cmin, int n_chunks, int n_rows, const float* __restrict__ qnorm, int Q,
+                                                               const unsigned* __restrict__ nmax_bits, int* __restrict__ cand, int* __restrict__ cand_cnt) {
+    __shared__ float s_t[SCS_SLICES][3][32];
+    __shared__ float s_thr[32];
+    __shared__ int s_cnt[32];
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane;
+    const float* col = cmin + q;
     float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
-    for (int sg = 0; sg < maxseg; ++sg) {
-        const float* p = part + (((size_t)sqt * maxseg + sg) * SCT_QT + row) * 3;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float d = p[j];
-            if (d < t3) { t3 = d; if (t3 < t2) { float x = t2; t2 = t3; t3 = x; } if (t2 < t1) { float x = t1; t1 = t2; t2 = x; } }
-        }
+    int ch = sl;
+    for (; ch + 3 * SCS_SLICES < n_chunks; ch += 4 * SCS_SLICES) {                 // four independent 128-byte rows in flight per warp
+        const float a0 = __ldg(col + (size_t)ch * n_rows), a1 = __ldg(col + (size_t)(ch + SCS_SLICES) * n_rows);
+        const float a2 = __ldg(col + (size_t)(ch + 2 * SCS_SLICES) * n_rows), a3 = __ldg(col + (size_t)(ch + 3 * SCS_SLICES) * n_rows);
+        top3_min_update(a0, t1, t2, t3); top3_min_update(a1, t1, t2, t3); top3_min_update(a2, t1, t2, t3); top3_min_update(a3, t1, t2, t3);
     }
-    const float nq = q < Q ? qnorm[q] : 0.f;
-    const float slack = 2.f * SCT_EPS_REL * (nq + __uint_as_float(*nmax_bits));
-    thr[q] = t3 < 1.0e38f ? t3 + slack : 3.0e38f;
-    if (q < Q) cand_cnt[q] = 0;
+    for (; ch < n_chunks; ch += SCS_SLICES) top3_min_update(__ldg(col + (size_t)ch * n_rows), t1, t2, t3);
+    s_t[sl][0][lane] = t1; s_t[sl][1][lane] = t2; s_t[sl][2][lane] = t3;
+    if (sl == 0) s_cnt[lane] = 0;
+    __syncthreads();
+    if (sl == 0) {
+        t1 = t2 = t3 = 3.0e38f;
+#pragma unroll 4
+        for (int w = 0; w < SCS_SLICES; ++w) { top3_min_update(s_t[w][0][lane], t1, t2, t3); top3_min_update(s_t[w][1][lane], t1, t2, t3); top3_min_update(s_t[w][2][lane], t1, t2, t3); }
+        const float nq = q < Q ? qnorm[q] : 0.f;
+        const float slack = 2.f * SCT_EPS_REL * (nq + __uint_as_float(*nmax_bits));
+        s_thr[lane] = t3 < 1.0e38f ? t3 + slack : 3.0e38f;
+    }
+    __syncthreads();
+    const float thr = s_thr[lane];
+    if (q < Q) {
+        ch = sl;
+        for (; ch + 3 * SCS_SLICES < n_chunks; ch += 4 * SCS_SLICES) {
+            const float a0 = __ldg(col + (size_t)ch * n_rows), a1 = __ldg(col + (size_t)(ch + SCS_SLICES) * n_rows);
+            const float a2 = __ldg(col + (size_t)(ch + 2 * SCS_SLICES) * n_rows), a3 = __ldg(col + (size_t)(ch + 3 * SCS_SLICES) * n_rows);
+            if (fminf(fminf(a0, a1), fminf(a2, a3)) <= thr) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float au = u == 0 ? a0 : u == 1 ? a1 : u == 2 ? a2 : a3;
+                    if (au <= thr) { const int slot = atomicAdd(&s_cnt[lane], 1); if (slot < SCT_CAP) cand[(size_t)q * SCT_CAP + slot] = ch + u * SCS_SLICES; }
+                }
+            }
+        }
+        for (; ch < n_chunks; ch += SCS_SLICES)
+            if (__ldg(col + (size_t)ch * n_rows) <= thr) { const int slot = atomicAdd(&s_cnt[lane], 1); if (slot < SCT_CAP) cand[(size_t)q * SCT_CAP + slot] = ch; }
+    }
+    __syncthreads();
+    if (sl == 0 && q < Q) cand_cnt[q] = s_cnt[lane];
 }
 
-// exact re-rank: one warp per query; nanoflann's evalMetric op order (ringkey_dist_dev), total order (dist, idx)
-__global__ void __launch_bounds__(256) k_sct_rerank(const float* __restrict__ keys, int idx_offset, const float* __restrict__ qkeys, int Q, const int* __restrict__ cand,
-                                                   const int* __restrict__ cand_cnt, float* __restrict__ out_d, int* __restrict__ out_i, int* __restrict__ over_list,
-                                                   int* __restrict__ over_cnt) {
+// exact re-rank: one warp per query, one lane per key of a candidate chunk; nanoflann's evalMetric op order
+// (ringkey_dist_dev), total order (dist, idx).  chunk id = kt * 4 + c holds keys ((32 c + lane) * nkt + kt).
+__global__ void __launch_bounds__(256) k_sct_rerank(const float* __restrict__ keys, int n_keys, int nkt, int idx_offset, const float* __restrict__ qkeys, int Q,
+                                                   const int* __restrict__ cand, const int* __restrict__ cand_cnt, float* __restrict__ out_d, int* __restrict__ out_i,
+                                                   int* __restrict__ over_list, int* __restrict__ over_cnt) {
     const int q = blockIdx.x * (blockDim.x / 32) + warp_id();
     if (q >= Q) return;
     const int l = lane_id();
@@ -409,10 +409,10 @@ __global__ void __launch_bounds__(256) k_sct_rerank(const float* __restrict__ ke
 #pragma unroll
     for (int k = 0; k < 20; ++k) aq[k] = __ldg(qkeys + 20 * (size_t)q + k);
     Top3 t; top3_init(t);
-    for (int i = l; i < n; i += 32) {
-        const int kidx = cand[(size_t)q * SCT_CAP + i];
-        const float d = ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)kidx));
-        top3_insert(t, d, idx_offset + kidx);
+    for (int i = 0; i < n; ++i) {
+        const int ch = cand[(size_t)q * SCT_CAP + i];
+        const int kidx = (SCT_CHUNK * (ch & 3) + l) * nkt + (ch >> 2);
+        if (kidx < n_keys) top3_insert(t, ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)kidx)), idx_offset + kidx);
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {

@@ -69,12 +69,12 @@ def test_tensor_topk_equals_brute_force_and_oracle(oracle, synth, K, Q):
 
 
 def test_tensor_overflow_falls_back_to_exact(oracle, synth):
-    """more than SCT_CAP keys inside the filter band of a query (here: 200 identical keys) → that query is answered by
-    the brute-force kernel; results stay exact."""
+    """more than SCT_CAP candidate chunks inside the filter band of a query (here: 3000 identical keys spread over ~160
+    chunks of 32) → that query is answered by the brute-force kernel; results stay exact."""
     import liorf_b200
     ctx = liorf_b200.Context()
     db = synth.sc_descriptors(5000, seed=41)
-    db[1000:1200] = db[17]
+    db[1000:4000] = db[17]
     q, _, _ = synth.sc_queries(db, 128, seed=42)
     q[5] = db[17]
     ctx.scAddDescriptors(db)
