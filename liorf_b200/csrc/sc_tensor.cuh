@@ -169,6 +169,39 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 // instruction descriptor: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t SCT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SCT_KT >> 3) << 17) | ((uint32_t)(SCT_SUB >> 4) << 24);
 
+// One step's tensor-core work issued by ONE elected lane from warp-uniform operands: 2 query sub-tiles x 4 k-steps of
+// M128 N128 K16, then the commits.  Everything the issue needs is computed by the whole warp in uniform code, so the
+// descriptors stay in uniform registers (a single lane re-deriving them costs ~150 cycles per MMA in register moves and
+// makes the issue loop, not the tensor core, the bottleneck).
+__device__ __forceinline__ void tc_issue_step(uint32_t td, uint64_t da, uint64_t db, uint32_t bar_b_empty, uint32_t bar_t_full, uint32_t bar_a_empty, uint32_t seg_end) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pz, po, pa;\n\t"
+        ".reg .b64 a1, a2, a3, a4, a5, a6, a7, b1, b2, b3;\n\t"
+        ".reg .b32 t1;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pz, 0, 0;\n\t"
+        "setp.eq.b32 po, 0, 0;\n\t"
+        "setp.ne.and.b32 pa, %5, 0, pe;\n\t"
+        "add.u64 a1, %1, 2;\n\t add.u64 a2, %1, 4;\n\t add.u64 a3, %1, 6;\n\t"
+        "add.u64 a4, %1, 1024;\n\t add.u64 a5, %1, 1026;\n\t add.u64 a6, %1, 1028;\n\t add.u64 a7, %1, 1030;\n\t"
+        "add.u64 b1, %2, 2;\n\t add.u64 b2, %2, 4;\n\t add.u64 b3, %2, 6;\n\t"
+        "add.u32 t1, %0, 128;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pz;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [t1], a4, %2, %3, pz;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, po;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [t1], a5, b1, %3, po;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, po;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [t1], a6, b2, %3, po;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, po;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [t1], a7, b3, %3, po;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+        "@pa tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+        "}\n"
+        ::"r"(td), "l"(da), "l"(db), "r"(SCT_IDESC), "r"(bar_b_empty), "r"(seg_end), "r"(bar_t_full), "r"(bar_a_empty) : "memory");
+}
+
 #define SCT_R32(v) "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), \
     "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
     "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
@@ -252,52 +285,48 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
     const uint32_t tmem_base = *s_tmem;
     const int n_steps = (int)(s_end - s_begin);
 
+    // The producer and MMA loops run on ALL lanes of their warp (uniform control flow keeps counters, addresses and
+    // descriptors in uniform registers); only the asynchronous issue itself is done by one elected lane.
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            int seg = 0, sqt = sqt0, kt = kt0;
-            for (int it = 0; it < n_steps && !*s_abort; ++it) {
-                if (it == 0 || kt == 0) {
-                    const int ab = seg & 1;
-                    if (!mbar_wait(BAR(A_EMPTY + ab), ((seg >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
+        int seg = 0, sqt = sqt0, kt = kt0, st = 0; uint32_t ph = 1;                 // ph: parity to wait for on B_EMPTY[st] (first lap passes)
+        for (int it = 0; it < n_steps; ++it) {
+            if (it == 0 || kt == 0) {
+                const int ab = seg & 1;
+                if (!mbar_wait(BAR(A_EMPTY + ab), ((seg >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
+                if (lane == 0) {
                     mbar_expect_tx(BAR(A_FULL + ab), 2 * SCT_TILE_BYTES);
-                    bulk_g2s(smem_u32(sA + (size_t)ab * 2 * SCT_TILE_BYTES), a.a_img + (size_t)sqt * 2 * SCT_TILE_BYTES, 2 * SCT_TILE_BYTES, BAR(A_FULL + ab));
-                    ++seg;
+                    bulk_g2s(smem_u32(sA) + ab * 2 * SCT_TILE_BYTES, a.a_img + (size_t)sqt * 2 * SCT_TILE_BYTES, 2 * SCT_TILE_BYTES, BAR(A_FULL + ab));
                 }
-                const int st = it % SCT_STAGES;
-                if (!mbar_wait(BAR(B_EMPTY + st), ((it / SCT_STAGES) & 1) ^ 1, s_abort, a.err_flag)) break;
-                mbar_expect_tx(BAR(B_FULL + st), SCT_TILE_BYTES);
-                bulk_g2s(smem_u32(sB + (size_t)st * SCT_TILE_BYTES), a.b_img + (size_t)kt * SCT_TILE_BYTES, SCT_TILE_BYTES, BAR(B_FULL + st));
-                if (++kt == a.nkt) { kt = 0; ++sqt; }
+                ++seg;
             }
+            if (!mbar_wait(BAR(B_EMPTY + st), ph, s_abort, a.err_flag)) break;
+            if (lane == 0) {
+                mbar_expect_tx(BAR(B_FULL + st), SCT_TILE_BYTES);
+                bulk_g2s(smem_u32(sB) + st * SCT_TILE_BYTES, a.b_img + (size_t)kt * SCT_TILE_BYTES, SCT_TILE_BYTES, BAR(B_FULL + st));
+            }
+            if (++st == SCT_STAGES) { st = 0; ph ^= 1; }
+            if (++kt == a.nkt) { kt = 0; ++sqt; }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one lane) =====
-        if (lane == 0) {
-            int seg = -1, kt = kt0;
-            for (int it = 0; it < n_steps && !*s_abort; ++it) {
-                if (it == 0 || kt == 0) {
-                    ++seg;
-                    if (!mbar_wait(BAR(A_FULL + (seg & 1)), (seg >> 1) & 1, s_abort, a.err_flag)) break;
-                }
-                const int ab = seg & 1, st = it % SCT_STAGES, acc = it & 1;
-                if (!mbar_wait(BAR(B_FULL + st), (it / SCT_STAGES) & 1, s_abort, a.err_flag)) break;
-                if (!mbar_wait(BAR(T_EMPTY + acc), ((it >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + (size_t)ab * 2 * SCT_TILE_BYTES), b_addr = smem_u32(sB + (size_t)st * SCT_TILE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < SCT_KDIM / 16; ++ks) {
-                    const uint64_t db = smem_desc(b_addr + ks * 32);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        tc_mma_bf16(tmem_base + acc * 256 + j * SCT_SUB, smem_desc(a_addr + j * SCT_TILE_BYTES + ks * 32), db, SCT_IDESC, ks > 0 ? 1u : 0u);
-                }
-                tc_commit(BAR(B_EMPTY + st));                       // the key image may be overwritten once these MMAs have read it
-                tc_commit(BAR(T_FULL + acc));                       // accumulators ready for the epilogue
-                const bool seg_end = (it + 1 == n_steps) || (kt == a.nkt - 1);
-                if (seg_end) tc_commit(BAR(A_EMPTY + ab));
-                if (++kt == a.nkt) kt = 0;
+        // ===== MMA issuer =====
+        int seg = -1, kt = kt0, st = 0; uint32_t ph = 0;                            // ph: parity to wait for on B_FULL[st]
+        const uint64_t da0 = smem_desc(smem_u32(sA)), db0 = smem_desc(smem_u32(sB));   // descriptors advance by (bytes >> 4) in the low word
+        for (int it = 0; it < n_steps; ++it) {
+            if (it == 0 || kt == 0) {
+                ++seg;
+                if (!mbar_wait(BAR(A_FULL + (seg & 1)), (seg >> 1) & 1, s_abort, a.err_flag)) break;
             }
+            const int ab = seg & 1, acc = it & 1;
+            if (!mbar_wait(BAR(B_FULL + st), ph, s_abort, a.err_flag)) break;
+            if (!mbar_wait(BAR(T_EMPTY + acc), ((it >> 1) & 1) ^ 1, s_abort, a.err_flag)) break;
+            tc_fence_after();
+            const bool seg_end = (it + 1 == n_steps) || (kt == a.nkt - 1);
+            tc_issue_step(tmem_base + acc * 256, da0 + (uint64_t)(ab * (2 * SCT_TILE_BYTES >> 4)), db0 + (uint64_t)(st * (SCT_TILE_BYTES >> 4)),
+                          BAR(B_EMPTY + st), BAR(T_FULL + acc), BAR(A_EMPTY + ab), seg_end ? 1u : 0u);
+            __syncwarp();
+            if (++st == SCT_STAGES) { st = 0; ph ^= 1; }
+            if (++kt == a.nkt) kt = 0;
         }
     } else {
         // ===== epilogue: 8 warps; TMEM lane quadrant = warp % 4, query sub-tile j = (warp - 2) / 4 =====
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * qd) << 16) + j * SCT_SUB;
         const size_t n_rows = (size_t)a.n_sqt * SCT_QT;
         int sqt = sqt0, kt = kt0;
-        for (int it = 0; it < n_steps && !*s_abort; ++it) {
+        for (int it = 0; it < n_steps; ++it) {
             const int q = sqt * SCT_QT + j * SCT_SUB + row;
             const int acc = it & 1;
             if (!mbar_wait(BAR(T_FULL + acc), (it >> 1) & 1, s_abort, a.err_flag)) break;

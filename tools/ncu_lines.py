@@ -28,13 +28,16 @@ for ln in dis:
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
 rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
-hi = [i for i, r in enumerate(rows) if len(r) > 3 and r[0] == "Address"][0]
+his = [i for i, r in enumerate(rows) if len(r) > 3 and r[0] == "Address"]
+sec = int(os.environ.get("NCU_SECTION", "0"))            # report with several launches: pick the launch (0-based)
+hi = his[sec]
+rows = rows[:his[sec + 1] - 2] if sec + 1 < len(his) else rows
 hdr = rows[hi]; ci = {h: i for i, h in enumerate(hdr)}
 agg = defaultdict(lambda: [0, 0, defaultdict(int)])
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = 0; toti = 0
 for k, r in enumerate(rows[hi + 1:]):
-    if len(r) < len(hdr):
+    if len(r) < len(hdr) or not r[ci["# Samples"]].isdigit():
         continue
     s = int(r[ci["# Samples"]]); ie = int(r[ci["Instructions Executed"]])
     key = lines[k] if k < len(lines) else ("?", -1)
