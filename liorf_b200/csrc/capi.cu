@@ -79,7 +79,7 @@ struct liorf_ctx {
     DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
     DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
     // tensor-core ring-key search (sc_tensor.cuh): operand images + work buffers
-    DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_cmin, sct_qnorm; DevBuf<int> sct_cand, sct_cnt, sct_over;
+    DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_cmin, sct_cmin32, sct_qnorm, sct_part; DevBuf<int> sct_cand, sct_cnt, sct_over;
     float* sct_center = nullptr; unsigned* sct_nmax = nullptr; int* sct_over_cnt = nullptr;
     int sct_img_n = -1;              // number of database keys the B image was built from (-1: none)
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
@@ -286,7 +286,7 @@ void liorf_destroy(liorf_ctx* c) {
     c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); c->sc_part_d.release(); c->sc_part_i.release();
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
-    c->sct_bimg.release(); c->sct_aimg.release(); c->sct_cmin.release(); c->sct_qnorm.release(); c->sct_cand.release(); c->sct_cnt.release();
+    c->sct_bimg.release(); c->sct_aimg.release(); c->sct_cmin.release(); c->sct_cmin32.release(); c->sct_qnorm.release(); c->sct_part.release(); c->sct_cand.release(); c->sct_cnt.release();
     c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
@@ -837,11 +837,11 @@ static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, Sc
     const long long total = (long long)n_sqt * nkt;
     grid = (int)(total < c->num_sms ? total : c->num_sms);
     const size_t rows = (size_t)n_sqt * SCT_QT;
-    if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_cmin.reserve(rows * nkt * 4)) ||
+    if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_cmin.reserve(rows * nkt)) || (rc = c->sct_cmin32.reserve(rows * nkt * 4)) || (rc = c->sct_part.reserve(rows * SCS_SPLITS * 3)) ||
         (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q)) || (rc = c->sct_over.reserve(Q))) return rc;
     k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, nkt, c->sct_center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
     a.a_img = c->sct_aimg.p; a.b_img = c->sct_bimg.p; a.Q = Q; a.n_keys = n_keys; a.nkt = nkt; a.n_sqt = n_sqt;
-    a.cmin = c->sct_cmin.p; a.dump = nullptr; a.err_flag = c->d_err;
+    a.cmin = c->sct_cmin.p; a.cmin32 = c->sct_cmin32.p; a.dump = nullptr; a.err_flag = c->d_err;
     c->launches += 1;
     return LIORF_OK;
 }
@@ -854,12 +854,15 @@ static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, 
     const int rows = a.n_sqt * SCT_QT;
     CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
     k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
-    k_sct_select<<<rows / 32, 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, a.nkt * 4, rows, c->sct_qnorm.p, Q, c->sct_nmax, c->sct_cand.p, c->sct_cnt.p);
+    CUDA_TRY(cudaMemsetAsync(c->sct_cnt.p, 0, (size_t)Q * sizeof(int), c->stream));
+    k_sct_top3<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, a.nkt, rows, c->sct_part.p);
+    k_sct_select<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, c->sct_cmin32.p, a.nkt, rows, c->sct_part.p, c->sct_qnorm.p, Q, c->sct_nmax,
+                                                                                 c->sct_cand.p, c->sct_cnt.p);
     k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, a.nkt, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p,
                                                      c->sct_over_cnt);
     k_sc_knn_overflow<<<64, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, global_offset, d_qkeys, c->sct_over.p, c->sct_over_cnt, d_dist, d_idx);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 4; c->sct_last_Q = Q;
+    c->launches += 5; c->sct_last_Q = Q;
     return LIORF_OK;
 }
 

@@ -14,10 +14,10 @@
 //   |d~ - d| <= eps(q,k) = 2^-13 (|x|^2 + |y|^2)   (split truncation 3*2^-18, norm split 2^-17, accumulation budget
 //   2^-14; tests/test_gpu_sc_tensor.py measures the real error over millions of pairs and asserts a 4x margin).
 //
-//   k_sc_tensor : the GEMM; its epilogue reduces every 32 consecutive accumulator columns (a "chunk" = 32 keys) to
-//                 their minimum and stores only that: cmin[chunk][query]  (1/32 of the Q x K matrix, L2 resident)
-//   k_sct_select: per query t3 = 3rd smallest chunk minimum (three different chunks hold three different keys, so t3
-//                 bounds the 3rd smallest d~ from above), then every chunk with cmin <= t3 + 2 eps_max(q) is a candidate
+//   k_sc_tensor : the GEMM; its epilogue reduces every 32 consecutive accumulator columns (a "chunk" = 32 keys) to their
+//                 minimum and stores only the minima: per chunk (cmin32) and per 128-key tile (cmin, what the selection streams)
+//   k_sct_top3 / k_sct_select: per query t3 = 3rd smallest chunk minimum (three different chunks hold three different keys,
+//                 so t3 bounds the 3rd smallest d~ from above), then every chunk with cmin32 <= t3 + 2 eps_max(q) is a candidate
 //   k_sct_rerank: exact nanoflann-order distances of the <= 32 keys of each candidate chunk, top-3 by (dist, idx)
 //   Completeness: the exact 3rd-best distance d3 <= t3 + eps (three different keys have d~ <= t3, hence exact distance
 //   <= t3 + eps), and a key of the exact top-3 has d~ <= d + eps <= d3 + eps <= t3 + 2 eps  =>  its chunk is a candidate.
@@ -45,7 +45,7 @@ constexpr int SCT_KDIM = 64;                       // contraction length
 constexpr int SCT_TILE_BYTES = SCT_SUB * SCT_KDIM * 2;     // 16 KB operand image (128 rows x 64 bf16)
 constexpr int SCT_STAGES = 6;
 constexpr int SCT_CAP = 64;                        // candidate chunks (of 32 keys) kept per query
-constexpr int SCT_CHUNK = 32;                      // accumulator columns reduced to one minimum
+constexpr int SCT_CHUNK = 32;                      // accumulator columns (keys) per candidate chunk; 4 chunks per key tile
 constexpr int SCT_THREADS = 320;                   // producer warp, MMA warp, 8 epilogue warps
 constexpr float SCT_EPS_REL = 1.0f / 8192.0f;      // eps(q,k) = 2^-13 (|x|^2 + |y|^2)
 // operand image = the canonical K-major SWIZZLE_128B shared-memory layout (what TMA writes for a 64-element bf16 box):
@@ -244,7 +244,8 @@ struct SctArgs {
     const uint8_t* a_img;      // [n_sqt][2][SCT_TILE_BYTES]
     const uint8_t* b_img;      // [nkt][SCT_TILE_BYTES]
     int Q, n_keys, nkt, n_sqt;
-    float* cmin;               // out: [nkt * 4][n_sqt * SCT_QT]  minimum d~ of each 32-key chunk
+    float* cmin;               // out: [nkt][n_sqt * SCT_QT]      minimum d~ over the 128 keys of each tile (streamed by the selection)
+    float* cmin32;             // out: [nkt * 4][n_sqt * SCT_QT]  minimum d~ of each 32-key chunk (read only for tiles that pass)
     float* dump;               // DUMP (tests): every d~, [n_sqt * SCT_QT][nkt * SCT_KT] indexed by database key
     int* err_flag;
 };
@@ -357,8 +358,10 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
                     o[(size_t)(64 + i) * a.nkt + kt] = __uint_as_float(v2[i]); o[(size_t)(96 + i) * a.nkt + kt] = __uint_as_float(v3[i]);
                 }
             } else {
-                float* o = a.cmin + (size_t)kt * 4 * n_rows + q;   // lanes = consecutive queries: each store is one 128-byte line
-                o[0] = min32(v0); o[n_rows] = min32(v1); o[2 * n_rows] = min32(v2); o[3 * n_rows] = min32(v3);
+                const float m0 = min32(v0), m1 = min32(v1), m2 = min32(v2), m3 = min32(v3);
+                float* o = a.cmin32 + (size_t)kt * 4 * n_rows + q;             // lanes = consecutive queries: every store is one 128-byte line
+                o[0] = m0; o[n_rows] = m1; o[2 * n_rows] = m2; o[3 * n_rows] = m3;
+                a.cmin[(size_t)kt * n_rows + q] = fminf(fminf(m0, m1), fminf(m2, m3));
             }
             if (++kt == a.nkt) { kt = 0; ++sqt; }
         }
@@ -371,57 +374,79 @@ __global__ void __launch_bounds__(SCT_THREADS, 1) k_sc_tensor(SctArgs a) {
     }
 }
 
-// Candidate selection on the chunk minima.  Block = 32 queries x 32 chunk slices; the block sees ALL chunks of its queries:
-// phase 1 reduces them to t3(q) (3rd smallest chunk minimum), phase 2 re-reads them (L1/L2 hits) and appends every chunk
-// with cmin <= t3 + 2 eps_max(q),  2 eps_max = 2^-12 (|x|^2 + max_k |y|^2), to the query's candidate list.
-constexpr int SCS_SLICES = 32;
-__global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __restrict__ cmin, int n_chunks, int n_rows, const float* __restrict__ qnorm, int Q,
-                                                               const unsigned* __restrict__ nmax_bits, int* __restrict__ cand, int* __restrict__ cand_cnt) {
+// Candidate selection on the chunk minima, two small kernels over a (32-query block) x (chunk split) grid so that enough
+// 128-byte rows are in flight to stream the minima from L2:
+//   k_sct_top3  : partial top-3 of the chunk minima per (query, split)                        → part[split][row][3]
+//   k_sct_select: t3(q) = 3rd smallest over the splits (three different chunks hold three different keys, so t3 bounds the
+//                 3rd smallest d~ from above); every chunk of this split with cmin <= t3 + 2 eps_max(q),
+//                 2 eps_max = 2^-12 (|x|^2 + max_k |y|^2), is appended to the query's candidate list.
+constexpr int SCS_SLICES = 8;              // warps per block: each takes every 8th chunk of the block's split
+constexpr int SCS_SPLITS = 8;              // chunk ranges (grid.y)
+__device__ __forceinline__ void scs_range(int n_chunks, int& c0, int& c1) {
+    const int per = (n_chunks + SCS_SPLITS - 1) / SCS_SPLITS;
+    c0 = blockIdx.y * per; c1 = min(n_chunks, c0 + per);
+}
+__global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_top3(const float* __restrict__ cmin, int n_chunks, int n_rows, float* __restrict__ part) {
     __shared__ float s_t[SCS_SLICES][3][32];
-    __shared__ float s_thr[32];
-    __shared__ int s_cnt[32];
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane;
     const float* col = cmin + q;
+    int c0, c1; scs_range(n_chunks, c0, c1);
     float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
-    int ch = sl;
-    for (; ch + 3 * SCS_SLICES < n_chunks; ch += 4 * SCS_SLICES) {                 // four independent 128-byte rows in flight per warp
+    int ch = c0 + sl;
+    for (; ch + 3 * SCS_SLICES < c1; ch += 4 * SCS_SLICES) {                       // four independent 128-byte rows in flight per warp
         const float a0 = __ldg(col + (size_t)ch * n_rows), a1 = __ldg(col + (size_t)(ch + SCS_SLICES) * n_rows);
         const float a2 = __ldg(col + (size_t)(ch + 2 * SCS_SLICES) * n_rows), a3 = __ldg(col + (size_t)(ch + 3 * SCS_SLICES) * n_rows);
         top3_min_update(a0, t1, t2, t3); top3_min_update(a1, t1, t2, t3); top3_min_update(a2, t1, t2, t3); top3_min_update(a3, t1, t2, t3);
     }
-    for (; ch < n_chunks; ch += SCS_SLICES) top3_min_update(__ldg(col + (size_t)ch * n_rows), t1, t2, t3);
+    for (; ch < c1; ch += SCS_SLICES) top3_min_update(__ldg(col + (size_t)ch * n_rows), t1, t2, t3);
     s_t[sl][0][lane] = t1; s_t[sl][1][lane] = t2; s_t[sl][2][lane] = t3;
-    if (sl == 0) s_cnt[lane] = 0;
     __syncthreads();
     if (sl == 0) {
         t1 = t2 = t3 = 3.0e38f;
-#pragma unroll 4
-        for (int w = 0; w < SCS_SLICES; ++w) { top3_min_update(s_t[w][0][lane], t1, t2, t3); top3_min_update(s_t[w][1][lane], t1, t2, t3); top3_min_update(s_t[w][2][lane], t1, t2, t3); }
-        const float nq = q < Q ? qnorm[q] : 0.f;
-        const float slack = 2.f * SCT_EPS_REL * (nq + __uint_as_float(*nmax_bits));
-        s_thr[lane] = t3 < 1.0e38f ? t3 + slack : 3.0e38f;
-    }
-    __syncthreads();
-    const float thr = s_thr[lane];
-    if (q < Q) {
-        ch = sl;
-        for (; ch + 3 * SCS_SLICES < n_chunks; ch += 4 * SCS_SLICES) {
-            const float a0 = __ldg(col + (size_t)ch * n_rows), a1 = __ldg(col + (size_t)(ch + SCS_SLICES) * n_rows);
-            const float a2 = __ldg(col + (size_t)(ch + 2 * SCS_SLICES) * n_rows), a3 = __ldg(col + (size_t)(ch + 3 * SCS_SLICES) * n_rows);
-            if (fminf(fminf(a0, a1), fminf(a2, a3)) <= thr) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float au = u == 0 ? a0 : u == 1 ? a1 : u == 2 ? a2 : a3;
-                    if (au <= thr) { const int slot = atomicAdd(&s_cnt[lane], 1); if (slot < SCT_CAP) cand[(size_t)q * SCT_CAP + slot] = ch + u * SCS_SLICES; }
-                }
+        for (int w = 0; w < SCS_SLICES; ++w) { top3_min_update(s_t[w][0][lane], t1, t2, t3); top3_min_update(s_t[w][1][lane], t1, t2, t3); top3_min_update(s_t[w][2][lane], t1, t2, t3); }
+        float* o = part + ((size_t)blockIdx.y * n_rows + q) * 3;
+        o[0] = t1; o[1] = t2; o[2] = t3;
+    }
+}
+__device__ __forceinline__ void sct_emit_tile(const float* __restrict__ cmin32, int n_rows, int q, int kt, float thr, int* __restrict__ cand, int* __restrict__ cand_cnt) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (__ldg(cmin32 + (size_t)(4 * kt + c) * n_rows + q) <= thr) {
+            const int slot = atomicAdd(cand_cnt + q, 1);
+            if (slot < SCT_CAP) cand[(size_t)q * SCT_CAP + slot] = 4 * kt + c;
+        }
+}
+__global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __restrict__ cmin, const float* __restrict__ cmin32, int n_chunks, int n_rows, const float* __restrict__ part,
+                                                               const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
+                                                               int* __restrict__ cand, int* __restrict__ cand_cnt) {
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane;
+    if (q >= Q) return;
+    float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
+#pragma unroll
+    for (int sp = 0; sp < SCS_SPLITS; ++sp) {
+        const float* p = part + ((size_t)sp * n_rows + q) * 3;
+        top3_min_update(p[0], t1, t2, t3); top3_min_update(p[1], t1, t2, t3); top3_min_update(p[2], t1, t2, t3);
+    }
+    const float thr = t3 < 1.0e38f ? t3 + 2.f * SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits)) : 3.0e38f;
+    const float* col = cmin + q;
+    int c0, c1; scs_range(n_chunks, c0, c1);
+    int ch = c0 + sl;
+    for (; ch + 3 * SCS_SLICES < c1; ch += 4 * SCS_SLICES) {
+        const float a0 = __ldg(col + (size_t)ch * n_rows), a1 = __ldg(col + (size_t)(ch + SCS_SLICES) * n_rows);
+        const float a2 = __ldg(col + (size_t)(ch + 2 * SCS_SLICES) * n_rows), a3 = __ldg(col + (size_t)(ch + 3 * SCS_SLICES) * n_rows);
+        if (fminf(fminf(a0, a1), fminf(a2, a3)) <= thr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float au = u == 0 ? a0 : u == 1 ? a1 : u == 2 ? a2 : a3;
+                if (au <= thr) sct_emit_tile(cmin32, n_rows, q, ch + u * SCS_SLICES, thr, cand, cand_cnt);
             }
         }
-        for (; ch < n_chunks; ch += SCS_SLICES)
-            if (__ldg(col + (size_t)ch * n_rows) <= thr) { const int slot = atomicAdd(&s_cnt[lane], 1); if (slot < SCT_CAP) cand[(size_t)q * SCT_CAP + slot] = ch; }
     }
-    __syncthreads();
-    if (sl == 0 && q < Q) cand_cnt[q] = s_cnt[lane];
+    for (; ch < c1; ch += SCS_SLICES)
+        if (__ldg(col + (size_t)ch * n_rows) <= thr) sct_emit_tile(cmin32, n_rows, q, ch, thr, cand, cand_cnt);
 }
 
 // exact re-rank: one warp per query, one lane per key of a candidate chunk; nanoflann's evalMetric op order
