@@ -283,6 +283,9 @@ class Context:
         _chk(self.lib.liorf_process_frame(self.h, C.byref(fi), C.byref(fo)), "liorf_process_frame")
         return fo
 
+    def forceLargeVoxelGrid(self, on=True):
+        _chk(self.lib.liorf_debug_force_large_voxelgrid(self.h, C.c_int(int(on))), "liorf_debug_force_large_voxelgrid")
+
     # ---- measurement helpers ----
     def enableTiming(self, on=True):
         _chk(self.lib.liorf_enable_timing(self.h, C.c_int(int(on))), "liorf_enable_timing")

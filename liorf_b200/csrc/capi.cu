@@ -208,7 +208,12 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaSetDevice(c->P.device));
     cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, c->P.device));
     c->num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // the main stream carries the latency-critical chain (deskew → downsample → solver); giving it the highest priority lets
+    // its large-footprint CTAs (single-CTA VoxelGrid, one-CTA-per-SM solver) claim SMs from the concurrent local-map chain
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (std::getenv("LIORF_NO_PRIO")) prio_lo = prio_hi = 0;
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     CUDA_TRY(cudaMalloc(&c->d_counts, C_COUNT * sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_counts, 0, C_COUNT * sizeof(int)));
     CUDA_TRY(cudaMalloc(&c->d_misc, 64 * sizeof(int)));
@@ -222,7 +227,7 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     c->combine_scan.ticket = c->d_misc + 6; c->combine_scan.err_flag = c->d_err;
     int* lm_counter = c->d_misc + 7; (void)lm_counter;
     CUDA_TRY(cudaMalloc(&c->vg.meta, sizeof(VoxMeta)));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_map, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_map, cudaStreamNonBlocking, prio_lo));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_map, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->vg_map.meta, sizeof(VoxMeta)));
@@ -919,6 +924,12 @@ int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pai
     return LIORF_OK;
 }
 
+/* tests: 1 = run the multi-kernel (large-cloud) VoxelGrid path on small clouds too; 0 = automatic */
+int liorf_debug_force_large_voxelgrid(liorf_ctx* c, int on) {
+    if (!c) return LIORF_ERR_ARG;
+    c->vg.force_large = c->vg_map.force_large = on != 0;
+    return LIORF_OK;
+}
 /* selects the ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank */
 int liorf_sc_set_search_path(liorf_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return LIORF_ERR_ARG;
@@ -1042,7 +1053,9 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     if (rc) return rc;
     stamp(1, c->stream);
     lap(0);
-    // laserCloudInfoHandler: extractSurroundingKeyFrames, downsampleCurrentScan, scan2MapOptimization
+    // laserCloudInfoHandler: extractSurroundingKeyFrames, downsampleCurrentScan, scan2MapOptimization.  The local-map chain is the
+    // longer of the two independent preparations, so it is enqueued first (on its own stream); the downsample follows on the
+    // main stream while it runs.
     if (!c->kfs.empty()) {
         std::vector<liorf_host::KeyPose> kp(c->kfs.size());
         for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }

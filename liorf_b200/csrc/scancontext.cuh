@@ -167,11 +167,20 @@ __global__ void __launch_bounds__(SCD_WARPS * 32) k_sc_distance(const double* __
     __syncwarp();
     // fastAlignUsingVkey (:93-113): lane ↔ shift, sequential sum over columns; first strict minimum of the norm
     double best = 10000000.0; int best_s = 0x7fffffff;
-    for (int s = l; s < SC_SECTOR; s += 32) {
-        double ss = 0;
-        for (int k = 0; k < SC_SECTOR; ++k) { int k2 = k - s; if (k2 < 0) k2 += SC_SECTOR; double d = s_vk1[w][k] - s_vk2[w][k2]; ss += d * d; }
-        double nrm = sqrt(ss);
-        if (nrm < best) { best = nrm; best_s = s; }             // ascending s within the lane ⇒ first minimum kept
+    {   // shifts l and l + 32 of this lane as two independent sequential sums (same per-shift order, twice the ILP)
+        const int sA = l, sB = l + 32;
+        const bool hasB = sB < SC_SECTOR;
+        double ssA = 0, ssB = 0;
+        for (int k = 0; k < SC_SECTOR; ++k) {
+            int kA = k - sA; if (kA < 0) kA += SC_SECTOR;
+            int kB = k - (hasB ? sB : 0); if (kB < 0) kB += SC_SECTOR;
+            const double v1 = s_vk1[w][k];
+            const double dA = v1 - s_vk2[w][kA], dB = v1 - s_vk2[w][kB];
+            ssA += dA * dA; ssB += dB * dB;
+        }
+        const double nA = sqrt(ssA), nB = sqrt(ssB);
+        if (nA < best) { best = nA; best_s = sA; }              // ascending s within the lane ⇒ first minimum kept
+        if (hasB && nB < best) { best = nB; best_s = sB; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

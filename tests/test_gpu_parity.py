@@ -27,6 +27,21 @@ def test_voxel_grid_random(ctx, oracle, n, leaf, seed):
     assert np.array_equal(out, o_out)            # canonical order ⇒ centroids bit-exact too
 
 
+@pytest.mark.parametrize("n", [1, 2, 767, 768, 769, 3071, 3072, 3073, 20000])
+def test_voxel_grid_small_and_large_paths_agree(ctx, oracle, n):
+    """clouds of <= 3072 points take the single-CTA kernel (radix sort in shared memory), larger ones the multi-kernel
+    radix path; both must give the oracle's result bit for bit, including at the capacity boundary."""
+    rng = np.random.default_rng(n)
+    pts = rng.uniform(-30, 30, size=(n, 4)).astype(np.float32); pts[:, 2] *= 0.05
+    pts[n // 2:] = pts[:n - n // 2] + np.float32(0.01)        # many multi-point voxels
+    o_out, o_mem, o_keys = oracle.voxel_grid(pts, 0.4)
+    for force_large in (False, True):
+        ctx.forceLargeVoxelGrid(force_large)
+        out, mem, keys = ctx.voxelGrid(pts, 0.4)
+        assert np.array_equal(out, o_out) and np.array_equal(mem, o_mem) and np.array_equal(keys, o_keys), (n, force_large)
+    ctx.forceLargeVoxelGrid(False)
+
+
 def test_voxel_grid_empty_and_edges(ctx, oracle):
     out, mem, keys = ctx.voxelGrid(np.zeros((0, 4), np.float32), 0.4)
     assert len(out) == 0
