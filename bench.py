@@ -277,9 +277,10 @@ def dist_env():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def bench_sc(ctx_device, rank, world, K, Q, reps, dist):
+def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     """config 5: K-entry database sharded by contiguous ranges over the ranks; Q replicated queries per step.
-    Orchestration = liorf_b200/sc_sharded.py (two tiny all_gathers per batch when world > 1)."""
+    Orchestration = liorf_b200/sc_sharded.py (two small all_gathers per batch when world > 1).  The ring-key stage runs on
+    the tensor cores (csrc/sc_tensor.cuh); its GEMM kernel is timed live by the library's CUDA events."""
     import torch
     import liorf_b200
     from liorf_b200.sc_sharded import GpuOps, ShardedScanContextSearch
@@ -293,40 +294,57 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist):
         ctx.scAddDescriptors(synth.sc_descriptors(min(CH, kloc - s), first=off + s))
     # queries: column-shifted noisy copies of entries of the first 2000 global rows (+ fresh ones); identical on every rank
     sample = synth.sc_descriptors(min(K, 2000), first=0)
-    qd, src, shift = synth.sc_queries(sample, Q)
     ops = GpuOps(ctx, off, torch)
     search = ShardedScanContextSearch(ops, rank, world, dist)
     dev = ops.dev
 
-    def one():
+    def run(Qn, reps_n):
+        qd, src, shift = synth.sc_queries(sample, Qn)
         with torch.cuda.stream(ops.stream):
-            q = ops.prepare_dev(d_q)
-            return search.query(q)
-    with torch.cuda.stream(ops.stream):
-        d_q = torch.from_numpy(qd).to(dev)
-    for _ in range(3):
-        loop, sh, dd, cand = one()
-    ctx.sync()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ops.stream):
-        e0.record()
-    for _ in range(reps):
-        loop, sh, dd, cand = one()
-    with torch.cuda.stream(ops.stream):
-        e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    tm = ctx.getTiming() if False else None
-    lp = loop.cpu().numpy(); shn = sh.cpu().numpy()
-    ok = (lp == src) & (src >= 0)
-    res = dict(K=K, Q=Q, shards=world, ms_per_batch=ms / reps, queries_per_s=Q * reps / (ms * 1e-3),
-               planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((shn[ok] == shift[ok]).sum()),
-               flops_ringkey=60.0 * Q * kloc, tflops_ringkey_fp32=None)
+            d_q = torch.from_numpy(qd).to(dev)
+
+        def one():
+            with torch.cuda.stream(ops.stream):
+                return search.query(ops.prepare_dev(d_q))
+        for _ in range(3):
+            loop, sh, dd, cand = one()
+        ctx.sync()
+        ctx.enableTiming(True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ops.stream):
+            e0.record()
+        for _ in range(reps_n):
+            loop, sh, dd, cand = one()
+        with torch.cuda.stream(ops.stream):
+            e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        tm = ctx.getTiming(); ctx.enableTiming(False)
+        st = ctx.scTensorStats()
+        lp = loop.cpu().numpy(); shn = sh.cpu().numpy()
+        ok = (lp == src) & (src >= 0)
+        gemm_ms = tm["sc_gemm"][0] / max(tm["sc_gemm"][1], 1)
+        kpad, qpad = (kloc + 127) // 128 * 128, (Qn + 255) // 256 * 256
+        tflops = 2.0 * 64 * kpad * qpad / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        res = dict(K=K, Q=Qn, shards=world, ms_per_batch=ms / reps_n, queries_per_s=Qn * reps_n / (ms * 1e-3),
+                   planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((shn[ok] == shift[ok]).sum()),
+                   ringkey_path="tcgen05 filter + exact re-rank" if tm["sc_gemm"][1] > 0 else "cuda-core brute force",
+                   ringkey_stage_ms=tm["sc_search"][0] / max(tm["sc_search"][1], 1), candidates_per_query=st["candidates"] / max(Qn, 1) * 32,
+                   overflow_queries=st["overflow"],
+                   roofline=dict(kernel="k_sc_tensor", bound="tensor", achieved=tflops, peak=peaks.get("bf16_tflops"), unit="TFLOP/s",
+                                 frac=(tflops / peaks["bf16_tflops"]) if tflops and peaks.get("bf16_tflops") else None, traffic=None,
+                                 avg_launch_ms=gemm_ms,
+                                 note="executed tensor-core flops: 2 x 64 (split-bf16 contraction) x Kpad x Qpad per launch; the distance itself is 3 x 20 flops per pair"))
+        return res, qd
+    res, qd = run(Q, reps)
+    if q_large > Q:
+        res["large_batch"], _ = run(q_large, max(2, reps // 2))
+        res["large_batch"].pop("roofline", None)
     ctx.close()
     return res, (qd, sample)
 
@@ -340,6 +358,7 @@ def main():
     ap.add_argument("--preroll", type=int, default=100, help="untimed frames that build the ~50-keyframe local map first")
     ap.add_argument("--sc-k", type=int, default=100000)
     ap.add_argument("--sc-q", type=int, default=4096)
+    ap.add_argument("--sc-q-large", type=int, default=32768, help="second, larger query batch for the sharded search (0 = skip)")
     ap.add_argument("--no-sc", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=12, help="bounded CPU-baseline sample (frames)")
     args = ap.parse_args()
@@ -475,7 +494,7 @@ def main():
     # ---- ScanContext search (config 5) ----
     sc = None
     if not args.no_sc:
-        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 5, dist)
+        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 10, dist, peaks, q_large=args.sc_q_large)
 
     # ---- CPU baseline (rank 0, N=1 only): the same frames on the host cores ----
     cpu = None

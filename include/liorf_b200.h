@@ -154,6 +154,12 @@ int liorf_sc_detect_loop_closure_id(liorf_ctx* ctx, int* loop_id, float* yaw_dif
  *   decide : strict-< argmin in kNN order + threshold */
 int liorf_sc_knn_batch_dev(liorf_ctx* ctx, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx);
 int liorf_sc_merge_top3_dev(liorf_ctx* ctx, const void* d_part_dist, const void* d_part_idx, int n_parts, int Q, void* d_dist, void* d_idx);
+/* the same merge on ONE all-gathered buffer: packed[part] = { float dist[Q*3]; int idx[Q*3]; } (a rank's stage-1 output
+ * written into one allocation travels in a single collective) */
+int liorf_sc_merge_top3_packed_dev(liorf_ctx* ctx, const void* d_packed, int n_parts, int Q, void* d_dist, void* d_idx);
+/* sharded stage 2 → per pair the entry of the rank that owns the candidate; gathered[part] = { double dist[Q*3];
+ * int shift[Q*3]; } at part * stride_bytes (stride_bytes >= 36 Q, multiple of 8) */
+int liorf_sc_combine_pairs_dev(liorf_ctx* ctx, const void* d_gathered, int n_parts, long long stride_bytes, int Q, void* d_pair_dist, void* d_pair_shift);
 int liorf_sc_prepare_queries_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, void* d_qkeys /*Q*20 f32*/, void* d_qsk /*Q*60 f64*/, void* d_qcn /*Q*60 f64*/);
 int liorf_sc_distance_batch_dev(liorf_ctx* ctx, const void* d_qdescs, const void* d_qsk, const void* d_qcn, const void* d_cand_idx, int Q,
                                 int global_offset, void* d_pair_dist /*Q*3 f64*/, void* d_pair_shift /*Q*3 i32*/);
@@ -198,7 +204,8 @@ int liorf_process_frame(liorf_ctx* ctx, const liorf_frame_in* in, liorf_frame_ou
 
 /* ---- measurement / introspection (bench.py) ------------------------------------------------------------------- */
 /* per-section CUDA-event timing on the context's stream: sections 0 deskew, 1 downsample, 2 map build (transform +
- * VoxelGrid), 3 grid build, 4 scan2map solver, 5 ScanContext make, 6 ScanContext ring-key search */
+ * VoxelGrid), 3 grid build, 4 scan2map solver, 5 ScanContext make, 6 ScanContext ring-key search, 7 the tcgen05 GEMM
+ * kernel inside 6 */
 int liorf_enable_timing(liorf_ctx* ctx, int on);
 int liorf_get_timing(liorf_ctx* ctx, double ms[8], long long calls[8]);
 long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels launched by this context so far */

@@ -293,7 +293,7 @@ class Context:
     def getTiming(self):
         ms = (C.c_double * 8)(); calls = (C.c_longlong * 8)()
         _chk(self.lib.liorf_get_timing(self.h, ms, calls), "liorf_get_timing")
-        names = ["deskew", "downsample", "map_build", "grid_build", "scan2map", "sc_make", "sc_search", "_"]
+        names = ["deskew", "downsample", "map_build", "grid_build", "scan2map", "sc_make", "sc_search", "sc_gemm"]
         return {n: (ms[i], calls[i]) for i, n in enumerate(names) if n != "_"}
 
     def launchCount(self):

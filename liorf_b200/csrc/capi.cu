@@ -29,7 +29,7 @@ enum { C_N_SCAN = 0, C_N_DS, C_M_DS, C_NSEL, C_FIRST_KEPT, C_CONV, C_HOOK_NSEL, 
 struct Keyframe { size_t off; int count; float pose[6]; double time; };
 
 // optional per-section CUDA-event timing on the context's stream (bench.py's live roofline numbers)
-enum { SEC_DESKEW = 0, SEC_DOWNSAMPLE, SEC_MAP_BUILD, SEC_GRID_BUILD, SEC_SCAN2MAP, SEC_SC_MAKE, SEC_SC_SEARCH, SEC_COUNT = 8 };
+enum { SEC_DESKEW = 0, SEC_DOWNSAMPLE, SEC_MAP_BUILD, SEC_GRID_BUILD, SEC_SCAN2MAP, SEC_SC_MAKE, SEC_SC_SEARCH, SEC_SC_GEMM, SEC_COUNT = 8 };
 constexpr int PROF_RING = 64;
 struct Profiler {
     bool enabled = false;
@@ -811,7 +811,7 @@ static int sc_knn_brute(liorf_ctx* c, const float* d_keys, int n_keys, const flo
     if ((rc = c->sc_part_d.reserve((size_t)chunks * Q * 3)) || (rc = c->sc_part_i.reserve((size_t)chunks * Q * 3))) return rc;
     ProfScope ps(c, SEC_SC_SEARCH); c->launches += 2;
     k_sc_knn_tile<<<dim3(bx, chunks), SCK_BLOCK, 0, c->stream>>>(d_keys, n_keys, global_offset, d_qkeys, Q, kpc, c->sc_part_d.p, c->sc_part_i.p);
-    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sc_part_d.p, c->sc_part_i.p, chunks, Q, d_dist, d_idx);
+    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sc_part_d.p, c->sc_part_i.p, chunks, (size_t)Q * 3, Q, d_dist, d_idx);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
 }
@@ -858,7 +858,7 @@ static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, 
     if ((rc = sct_prepare(c, n_keys, d_qkeys, Q, a, grid))) return rc;
     const int rows = a.n_sqt * SCT_QT;
     CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
-    k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
+    { ProfScope pg(c, SEC_SC_GEMM); k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a); }
     CUDA_TRY(cudaMemsetAsync(c->sct_cnt.p, 0, (size_t)Q * sizeof(int), c->stream));
     k_sct_top3<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, a.nkt, rows, c->sct_part.p);
     k_sct_select<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, c->sct_cmin32.p, a.nkt, rows, c->sct_part.p, c->sct_qnorm.p, Q, c->sct_nmax,
@@ -890,7 +890,24 @@ int liorf_sc_merge_top3_dev(liorf_ctx* c, const void* d_part_dist, const void* d
     if (!c || Q < 0 || n_parts < 1) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
-    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>((const float*)d_part_dist, (const int*)d_part_idx, n_parts, Q, (float*)d_dist, (int*)d_idx);
+    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>((const float*)d_part_dist, (const int*)d_part_idx, n_parts, (size_t)Q * 3, Q, (float*)d_dist, (int*)d_idx);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+int liorf_sc_merge_top3_packed_dev(liorf_ctx* c, const void* d_packed, int n_parts, int Q, void* d_dist, void* d_idx) {
+    if (!c || Q < 0 || n_parts < 1 || !d_packed) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    const float* pd = (const float*)d_packed;
+    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(pd, (const int*)(pd + (size_t)Q * 3), n_parts, (size_t)Q * 6, Q, (float*)d_dist, (int*)d_idx);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+int liorf_sc_combine_pairs_dev(liorf_ctx* c, const void* d_gathered, int n_parts, long long stride_bytes, int Q, void* d_pair_dist, void* d_pair_shift) {
+    if (!c || Q < 0 || n_parts < 1 || !d_gathered || stride_bytes < (long long)Q * 36 || (stride_bytes & 7)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    if (Q == 0) return LIORF_OK;
+    k_sc_combine_pairs<<<(3 * Q + 127) / 128, 128, 0, c->stream>>>((const unsigned char*)d_gathered, n_parts, (size_t)stride_bytes, 3 * Q, (double*)d_pair_dist, (int*)d_pair_shift);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
 }

@@ -126,14 +126,15 @@ __global__ void __launch_bounds__(SCK_BLOCK) k_sc_knn_tile(const float* __restri
         for (int j = 0; j < 3; ++j) { part_d[o + j] = t.d[j]; part_i[o + j] = t.i[j]; }
     }
 }
-// merges n_parts partial top-3 lists per query (layout [part][Q][3]) by (dist, idx)
-__global__ void __launch_bounds__(128) k_sc_merge_top3(const float* __restrict__ part_d, const int* __restrict__ part_i, int n_parts, int Q,
+// merges n_parts partial top-3 lists per query by (dist, idx); part p starts at p * part_stride elements ([part][Q][3] when
+// part_stride = 3 Q; the packed all-gather layout [part]{dist[Q][3], idx[Q][3]} uses 6 Q)
+__global__ void __launch_bounds__(128) k_sc_merge_top3(const float* __restrict__ part_d, const int* __restrict__ part_i, int n_parts, size_t part_stride, int Q,
                                                       float* __restrict__ out_d, int* __restrict__ out_i) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     Top3 t; top3_init(t);
     for (int p = 0; p < n_parts; ++p) {
-        const size_t o = ((size_t)p * Q + q) * 3;
+        const size_t o = (size_t)p * part_stride + (size_t)q * 3;
 #pragma unroll
         for (int j = 0; j < 3; ++j) { int i = part_i[o + j]; if (i != 0x7fffffff) top3_insert(t, part_d[o + j], i); }
     }
@@ -229,6 +230,20 @@ __global__ void __launch_bounds__(SCD_WARPS * 32) k_sc_distance(const double* __
         if (dj < mn) { mn = dj; arg = sj; }
     }
     if (l == 0) { out_dist[pair] = mn; out_shift[pair] = arg; }
+}
+
+// sharded stage 2: every (query, candidate) pair was evaluated by exactly one rank (the owner of the candidate), all others
+// left +inf / 0.  gathered[part] = { double dist[3 Q]; int shift[3 Q]; } at part * stride_bytes.  Picks the owner's entry.
+__global__ void __launch_bounds__(128) k_sc_combine_pairs(const unsigned char* __restrict__ gathered, int n_parts, size_t stride_bytes, int n_pairs,
+                                                         double* __restrict__ out_dist, int* __restrict__ out_shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    double d = INFINITY; int sh = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        const double dp = reinterpret_cast<const double*>(gathered + (size_t)p * stride_bytes)[i];
+        if (dp != INFINITY) { d = dp; sh = reinterpret_cast<const int*>(gathered + (size_t)p * stride_bytes + (size_t)n_pairs * 8)[i]; break; }   // NaN != inf: an owner's NaN is kept
+    }
+    out_dist[i] = d; out_shift[i] = sh;
 }
 
 // final decision per query (:302-340): candidates in kNN order, strict <, threshold

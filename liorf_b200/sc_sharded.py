@@ -31,37 +31,77 @@ def merge_top3_numpy(gd, gi):
 class ShardedScanContextSearch:
     def __init__(self, ops, rank, world, dist=None):
         self.ops, self.rank, self.world, self.dist = ops, rank, world, dist
+        self._gbuf = {}
 
     def _all_gather(self, t):
         if self.world == 1:
             return t.unsqueeze(0)
-        out = t.new_empty((self.world * t.shape[0],) + tuple(t.shape[1:]))     # concatenated layout works for NCCL and gloo
+        key = (tuple(t.shape), t.dtype, t.device)
+        out = self._gbuf.get(key)
+        if out is None:
+            out = self._gbuf[key] = t.new_empty((self.world * t.shape[0],) + tuple(t.shape[1:]))     # concatenated layout works for NCCL and gloo
         self.dist.all_gather_into_tensor(out, t.contiguous())
         return out.view((self.world,) + tuple(t.shape))
 
     def query(self, q):
         """q: prepared queries (ops-specific handle).  Returns (loop_id, shift, dist, cand) as tensors of the ops' device."""
+        if self.world > 1 and hasattr(self.ops, "knn_packed"):
+            return self._query_packed(q)
         ld, li = self.ops.knn(q)                                   # 1
         if self.world > 1:
-            gd, gi = self._all_gather(ld), self._all_gather(li)    # 2
+            # 2: ONE collective for (f32 dist, i32 idx): the distance travels as its bit pattern next to the index
+            packed = self._all_gather(self.ops.xp_stack_i32(ld, li))
+            gd, gi = self.ops.xp_unstack_i32(packed)
             cd, ci = self.ops.merge(gd, gi)                        # 3
         else:
             cd, ci = ld, li
         pd, ps = self.ops.distance(q, ci)                          # 4
         if self.world > 1:
-            gpd, gps = self._all_gather(pd), self._all_gather(ps)  # 5
+            # 5: ONE collective for (f64 dist, shift): the shift (0..59) travels as an exact double
+            g = self._all_gather(self.ops.xp_stack_f64(pd, ps))
+            gpd, gps = g[..., 0], g[..., 1]
             best = gpd.argmin(dim=0, keepdim=True)
-            pd, ps = gpd.gather(0, best)[0].contiguous(), gps.gather(0, best)[0].contiguous()
+            pd, ps = gpd.gather(0, best)[0].contiguous(), gps.gather(0, best)[0].to(ps.dtype).contiguous()
         return self.ops.decide(pd, ps, ci) + (ci,)                 # 6
 
+    def _query_packed(self, q):
+        """same protocol with the library writing each phase's output into ONE buffer per collective and doing the merge /
+        owner pick in its own kernels: per batch 7 library calls + 2 all_gathers, no tensor-library ops on the host path."""
+        ops = self.ops
+        buf = ops.knn_packed(q)                                    # 1   {f32 dist[Q][3], i32 idx[Q][3]}
+        cd, ci = ops.merge_packed(self._all_gather(buf), self.world)          # 2, 3
+        pbuf = ops.distance_packed(q, ci)                          # 4   {f64 dist[Q][3], i32 shift[Q][3]}
+        pd, ps = ops.combine_packed(self._all_gather(pbuf), self.world)       # 5
+        return ops.decide(pd, ps, ci) + (ci,)                      # 6
 
-class GpuOps:
+
+class TorchPacking:
+    """(dist, idx) / (dist, shift) packing shared by the GPU ops and the CPU stand-in of the tests (torch tensors)."""
+
+    @staticmethod
+    def xp_stack_i32(d, i):
+        import torch
+        return torch.stack([d.contiguous().view(torch.int32), i], dim=-1).contiguous()
+
+    @staticmethod
+    def xp_unstack_i32(p):
+        import torch
+        return p[..., 0].contiguous().view(torch.float32), p[..., 1].contiguous()
+
+    @staticmethod
+    def xp_stack_f64(d, s):
+        import torch
+        return torch.stack([d, s.to(torch.float64)], dim=-1).contiguous()
+
+
+class GpuOps(TorchPacking):
     """The four local steps on the CUDA library; all tensors live on the context's device and stream."""
 
     def __init__(self, ctx, global_offset, torch):
         self.ctx, self.off, self.torch = ctx, int(global_offset), torch
         self.dev = torch.device(f"cuda:{ctx.params.device}")
         self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.dev)
+        self._bufs = {}
 
     @staticmethod
     def _vp(t):
@@ -73,20 +113,28 @@ class GpuOps:
             d_q = t.from_numpy(np.ascontiguousarray(qdesc_host, np.float64).reshape(-1, 1200)).to(self.dev)
         return self.prepare_dev(d_q)
 
+    def _buf(self, name, shape, dtype):
+        """output tensors are allocated once per (name, shape): a batch is a handful of ~100 us kernels, so allocator calls
+        in the loop would show up in the queries/s."""
+        key = (name, tuple(shape))
+        b = self._bufs.get(key)
+        if b is None:
+            b = self._bufs[key] = self.torch.empty(shape, dtype=dtype, device=self.dev)
+        return b
+
     def prepare_dev(self, d_q):
         """ring keys (a11), sector keys and column norms of query descriptors already on the device."""
         t = self.torch
         with t.cuda.stream(self.stream):
             Q = d_q.shape[0]
-            keys = t.empty((Q, 20), dtype=t.float32, device=self.dev)
-            sk = t.empty((Q, 60), dtype=t.float64, device=self.dev); cn = t.empty_like(sk)
+            keys = self._buf("keys", (Q, 20), t.float32); sk = self._buf("sk", (Q, 60), t.float64); cn = self._buf("cn", (Q, 60), t.float64)
             self.ctx.lib.liorf_sc_prepare_queries_dev(self.ctx.h, self._vp(d_q), Q, self._vp(keys), self._vp(sk), self._vp(cn))
         return dict(desc=d_q, keys=keys, sk=sk, cn=cn, Q=Q)
 
     def knn(self, q):
         t = self.torch
         with t.cuda.stream(self.stream):
-            d = t.empty((q["Q"], 3), dtype=t.float32, device=self.dev); i = t.empty((q["Q"], 3), dtype=t.int32, device=self.dev)
+            d = self._buf("knn_d", (q["Q"], 3), t.float32); i = self._buf("knn_i", (q["Q"], 3), t.int32)
             self.ctx.lib.liorf_sc_knn_batch_dev(self.ctx.h, self._vp(q["keys"]), q["Q"], self.off, self._vp(d), self._vp(i))
         return d, i
 
@@ -94,14 +142,15 @@ class GpuOps:
         t = self.torch
         G, Q, _ = gd.shape
         with t.cuda.stream(self.stream):
-            d = t.empty((Q, 3), dtype=t.float32, device=self.dev); i = t.empty((Q, 3), dtype=t.int32, device=self.dev)
+            d = self._buf("mrg_d", (Q, 3), t.float32); i = self._buf("mrg_i", (Q, 3), t.int32)
             self.ctx.lib.liorf_sc_merge_top3_dev(self.ctx.h, self._vp(gd), self._vp(gi), G, Q, self._vp(d), self._vp(i))
         return d, i
 
     def distance(self, q, cand):
         t = self.torch
         with t.cuda.stream(self.stream):
-            pd = t.full((q["Q"], 3), float("inf"), dtype=t.float64, device=self.dev); ps = t.zeros((q["Q"], 3), dtype=t.int32, device=self.dev)
+            pd = self._buf("pd", (q["Q"], 3), t.float64); ps = self._buf("ps", (q["Q"], 3), t.int32)
+            pd.fill_(float("inf")); ps.zero_()
             self.ctx.lib.liorf_sc_distance_batch_dev(self.ctx.h, self._vp(q["desc"]), self._vp(q["sk"]), self._vp(q["cn"]), self._vp(cand), q["Q"], self.off,
                                                      self._vp(pd), self._vp(ps))
         return pd, ps
@@ -110,6 +159,43 @@ class GpuOps:
         t = self.torch
         Q = pd.shape[0]
         with t.cuda.stream(self.stream):
-            loop = t.empty(Q, dtype=t.int32, device=self.dev); sh = t.empty(Q, dtype=t.int32, device=self.dev); dd = t.empty(Q, dtype=t.float64, device=self.dev)
+            loop = self._buf("loop", (Q,), t.int32); sh = self._buf("sh", (Q,), t.int32); dd = self._buf("dd", (Q,), t.float64)
             self.ctx.lib.liorf_sc_decide_dev(self.ctx.h, self._vp(pd), self._vp(ps), self._vp(cand), Q, self._vp(loop), self._vp(sh), self._vp(dd))
         return loop, sh, dd
+
+    # ---- packed variants: one allocation per collective ----
+    def knn_packed(self, q):
+        t = self.torch
+        Q = q["Q"]
+        with t.cuda.stream(self.stream):
+            buf = self._buf("knn_packed", (6 * Q,), t.int32)
+            self.ctx.lib.liorf_sc_knn_batch_dev(self.ctx.h, self._vp(q["keys"]), Q, self.off, C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr() + 12 * Q))
+        return buf
+
+    def merge_packed(self, g, world):
+        t = self.torch
+        Q = g.shape[-1] // 6
+        with t.cuda.stream(self.stream):
+            d = self._buf("mrg_d", (Q, 3), t.float32); i = self._buf("mrg_i", (Q, 3), t.int32)
+            self.ctx.lib.liorf_sc_merge_top3_packed_dev(self.ctx.h, self._vp(g), world, Q, self._vp(d), self._vp(i))
+        return d, i
+
+    def distance_packed(self, q, cand):
+        t = self.torch
+        Q = q["Q"]
+        with t.cuda.stream(self.stream):
+            buf = self._buf("pair_packed", (9 * Q + (Q & 1),), t.int32)             # 24 Q bytes of f64 + 12 Q bytes of i32, 8-byte multiple
+            pd = buf[:6 * Q].view(t.float64); ps = buf[6 * Q:9 * Q]
+            pd.fill_(float("inf")); ps.zero_()
+            self.ctx.lib.liorf_sc_distance_batch_dev(self.ctx.h, self._vp(q["desc"]), self._vp(q["sk"]), self._vp(q["cn"]), self._vp(cand), Q, self.off,
+                                                     C.c_void_p(pd.data_ptr()), C.c_void_p(ps.data_ptr()))
+        return buf
+
+    def combine_packed(self, g, world):
+        t = self.torch
+        stride = g.shape[-1] * 4
+        Q = (g.shape[-1]) // 9
+        with t.cuda.stream(self.stream):
+            pd = self._buf("cmb_d", (Q, 3), t.float64); ps = self._buf("cmb_s", (Q, 3), t.int32)
+            self.ctx.lib.liorf_sc_combine_pairs_dev(self.ctx.h, self._vp(g), world, C.c_longlong(stride), Q, self._vp(pd), self._vp(ps))
+        return pd, ps

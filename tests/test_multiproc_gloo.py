@@ -13,9 +13,12 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from liorf_b200.sc_sharded import TorchPacking  # noqa: E402
 
 
-class OracleOps:
+class OracleOps(TorchPacking):
     """CPU stand-in for GpuOps (tests only)."""
 
     def __init__(self, o, keys, descs, off):
