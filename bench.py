@@ -170,7 +170,9 @@ class CpuPipeline:
         last = P[-1]
         return [i for i in ids if np.sqrt(((P[i] - last) ** 2).sum()) <= radius]
 
-    def step(self, i):
+    def step(self, i, guess=None, post=None):
+        """guess: initial pose override (tests feed updateInitialGuess' output); post: callable applied to the solved pose
+        (transformUpdate)"""
         o, seq = self.o, self.seq
         raw, (t0, it, rot, ptr) = seq.frame(i)
         a = time.perf_counter()
@@ -178,7 +180,9 @@ class CpuPipeline:
         b = time.perf_counter()
         ds, _, _ = o.voxel_grid(cloud, 0.4)
         c = time.perf_counter()
-        guess = seq.initial_guess(i, self.prev)
+        if guess is None:
+            guess = seq.initial_guess(i, self.prev)
+        guess = np.asarray(guess, np.float32)
         pose = guess.copy()
         d = c
         if self.kf_clouds:
@@ -190,6 +194,8 @@ class CpuPipeline:
             r = o.scan2map(ds, mds, guess, 30, False, self.state, use_ref_kdtree=self.use_ref)
             pose, self.state = r["tf"], r["state"]
             self.last["iters"] = r["iters"]
+            if post is not None and r["iters"] > 0:
+                pose = post(pose)
         e = time.perf_counter()
         last = self.kf_poses[-1] if self.kf_poses else None
         make = last is None

@@ -111,6 +111,21 @@ void liorf_transform_update_clamp(float pose6_inout[6], float rotation_tolleranc
 /* context-free forms (host only, usable without a GPU): poses6 = n x (roll,pitch,yaw,x,y,z), times = n stamps */
 int liorf_host_extract_nearby(const float* poses6, const double* times, int n, double time_laser_info_cur, float search_radius,
                               float keyframe_density, int* ids, int cap, int* n_ids);
+/* mapOptimization::updateInitialGuess (src/mapOptmization.cpp:899-958), host scalar code.  `state` replaces the function's
+ * static locals (zero-initialise it once: identity transforms are filled in on first use).  cloud_info fields as in
+ * msg/cloud_info.msg.  tf = transformTobeMapped (roll, pitch, yaw, x, y, z), updated in place. */
+typedef struct { float lastImuTransformation[12]; float lastImuPreTransformation[12]; int lastImuPreTransAvailable; int initialised; } liorf_guess_state;
+typedef struct {
+    int imuAvailable, odomAvailable;
+    float imuRollInit, imuPitchInit, imuYawInit;
+    float initialGuessX, initialGuessY, initialGuessZ, initialGuessRoll, initialGuessPitch, initialGuessYaw;
+} liorf_cloud_info_guess;
+int liorf_host_update_initial_guess(liorf_guess_state* state, int no_keyframes_yet, const liorf_cloud_info_guess* cloud_info,
+                                    int use_imu_heading_initialization, int imu_type, float transformTobeMapped[6]);
+/* mapOptimization::transformUpdate (:1323-1353) in full: 9-axis roll / pitch slerp towards the IMU attitude (tf::Quaternion
+ * arithmetic in double) when imuAvailable && imuType, then the clamps */
+int liorf_host_transform_update(float transformTobeMapped[6], int imu_available, int imu_type, float imu_roll_init, float imu_pitch_init,
+                                float imu_rpy_weight, float rotation_tollerance, float z_tollerance);
 int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose6[6], float adding_dist_threshold, float adding_angle_threshold);
 
 /* replaces mapOptimization::scan2MapOptimization() (src/mapOptmization.cpp:1295) up to, not including, transformUpdate:
@@ -193,6 +208,9 @@ typedef struct {
     float adding_dist_threshold, adding_angle_threshold;   /* utility.h:137-138 */
     float rotation_tollerance, z_tollerance;    /* utility.h:129-130 */
     int max_iters; int loop_every; int frame_index;
+    /* use_cloud_info != 0: the initial guess is produced by updateInitialGuess (:899-958) from the context's previous pose and
+     * these cloud_info fields (initial_guess[] is ignored), and transformUpdate (:1323-1353) runs in full after the solve */
+    int use_cloud_info; liorf_cloud_info_guess cloud_info; int imu_type; int use_imu_heading_initialization; float imu_rpy_weight;
 } liorf_frame_in;
 typedef struct {
     float pose[6];

@@ -41,12 +41,25 @@ class LMTrace(C.Structure):
         return np.array([self.nsel[i] for i in range(self.iters)], np.int32)
 
 
+class CloudInfoGuess(C.Structure):
+    _fields_ = [("imuAvailable", C.c_int), ("odomAvailable", C.c_int), ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float), ("imuYawInit", C.c_float),
+                ("initialGuessX", C.c_float), ("initialGuessY", C.c_float), ("initialGuessZ", C.c_float), ("initialGuessRoll", C.c_float),
+                ("initialGuessPitch", C.c_float), ("initialGuessYaw", C.c_float)]
+
+
+class GuessState(C.Structure):
+    _fields_ = [("lastImuTransformation", C.c_float * 12), ("lastImuPreTransformation", C.c_float * 12), ("lastImuPreTransAvailable", C.c_int),
+                ("initialised", C.c_int)]
+
+
 class FrameIn(C.Structure):
     _fields_ = [("pts", C.c_void_p), ("n", C.c_int), ("pts_on_device", C.c_int), ("time_scan_cur", C.c_double),
                 ("imu_time", C.c_void_p), ("imu_rot_x", C.c_void_p), ("imu_rot_y", C.c_void_p), ("imu_rot_z", C.c_void_p),
                 ("imu_pointer_cur", C.c_int), ("deskew_enabled", C.c_int), ("initial_guess", C.c_float * 6),
                 ("surrounding_keyframe_density", C.c_float), ("adding_dist_threshold", C.c_float), ("adding_angle_threshold", C.c_float),
-                ("rotation_tollerance", C.c_float), ("z_tollerance", C.c_float), ("max_iters", C.c_int), ("loop_every", C.c_int), ("frame_index", C.c_int)]
+                ("rotation_tollerance", C.c_float), ("z_tollerance", C.c_float), ("max_iters", C.c_int), ("loop_every", C.c_int), ("frame_index", C.c_int),
+                ("use_cloud_info", C.c_int), ("cloud_info", CloudInfoGuess), ("imu_type", C.c_int), ("use_imu_heading_initialization", C.c_int),
+                ("imu_rpy_weight", C.c_float)]
 
 
 class FrameOut(C.Structure):
@@ -269,14 +282,19 @@ class Context:
         _chk(self.lib.liorf_set_lm_state(self.h, C.c_int(int(deg)), _vp(P)), "liorf_set_lm_state")
 
     def processFrame(self, pts_ptr, n, on_device, time_scan_cur, imu_time, imu_rot_xyz, imu_pointer_cur, deskew_enabled, initial_guess,
-                     density=2.0, dist_thr=1.0, ang_thr=0.2, rot_tol=1000.0, z_tol=1000.0, max_iters=30, loop_every=0, frame_index=0):
+                     density=2.0, dist_thr=1.0, ang_thr=0.2, rot_tol=1000.0, z_tol=1000.0, max_iters=30, loop_every=0, frame_index=0,
+                     cloud_info=None, imu_type=0, use_imu_heading=True, imu_rpy_weight=0.01):
         """one frame through cloudHandler + laserCloudInfoHandler (liorf_process_frame).  imu_rot_xyz: three contiguous float64 arrays."""
         fi = FrameIn()
         fi.pts = pts_ptr; fi.n = n; fi.pts_on_device = int(on_device); fi.time_scan_cur = time_scan_cur
         fi.imu_time = imu_time.ctypes.data; fi.imu_rot_x = imu_rot_xyz[0].ctypes.data; fi.imu_rot_y = imu_rot_xyz[1].ctypes.data; fi.imu_rot_z = imu_rot_xyz[2].ctypes.data
         fi.imu_pointer_cur = imu_pointer_cur; fi.deskew_enabled = int(deskew_enabled)
-        for k in range(6):
-            fi.initial_guess[k] = float(initial_guess[k])
+        if cloud_info is not None:                              # initial guess by updateInitialGuess from these cloud_info fields
+            fi.use_cloud_info = 1; fi.cloud_info = cloud_info; fi.imu_type = imu_type; fi.use_imu_heading_initialization = int(use_imu_heading)
+            fi.imu_rpy_weight = imu_rpy_weight
+        else:
+            for k in range(6):
+                fi.initial_guess[k] = float(initial_guess[k])
         fi.surrounding_keyframe_density = density; fi.adding_dist_threshold = dist_thr; fi.adding_angle_threshold = ang_thr
         fi.rotation_tollerance = rot_tol; fi.z_tollerance = z_tol; fi.max_iters = max_iters; fi.loop_every = loop_every; fi.frame_index = frame_index
         fo = FrameOut()

@@ -82,6 +82,7 @@ struct liorf_ctx {
     DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_cmin, sct_cmin32, sct_qnorm, sct_part; DevBuf<int> sct_cand, sct_cnt, sct_over;
     float* sct_center = nullptr; unsigned* sct_nmax = nullptr; int* sct_over_cnt = nullptr;
     int sct_img_n = -1;              // number of database keys the B image was built from (-1: none)
+    liorf_guess_state guess_state = {}; float tf_mapped[6] = {0, 0, 0, 0, 0, 0};   // updateInitialGuess statics + transformTobeMapped
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
     bool sct_attr_set = false; int sct_last_Q = 0;
     Profiler prof;
@@ -567,6 +568,31 @@ int liorf_host_extract_nearby(const float* poses6, const double* times, int n, d
     *n_ids = (int)sel.size();
     if ((int)sel.size() > cap || !ids) return LIORF_ERR_ARG;
     std::memcpy(ids, sel.data(), sel.size() * sizeof(int));
+    return LIORF_OK;
+}
+static void guess_state_init(liorf_guess_state* st) {
+    if (st->initialised) return;
+    const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    std::memcpy(st->lastImuTransformation, I, sizeof(I)); std::memcpy(st->lastImuPreTransformation, I, sizeof(I));
+    st->lastImuPreTransAvailable = 0; st->initialised = 1;
+}
+int liorf_host_update_initial_guess(liorf_guess_state* state, int no_keyframes_yet, const liorf_cloud_info_guess* ci, int use_imu_heading, int imu_type, float tf[6]) {
+    if (!state || !ci || !tf) return LIORF_ERR_ARG;
+    guess_state_init(state);
+    liorf_host::InitialGuessState s;
+    std::memcpy(s.lastImuTransformation, state->lastImuTransformation, 48); std::memcpy(s.lastImuPreTransformation, state->lastImuPreTransformation, 48);
+    s.lastImuPreTransAvailable = state->lastImuPreTransAvailable != 0;
+    liorf_host::CloudInfoGuess g{ci->imuAvailable, ci->odomAvailable, ci->imuRollInit, ci->imuPitchInit, ci->imuYawInit, ci->initialGuessX, ci->initialGuessY,
+                                 ci->initialGuessZ, ci->initialGuessRoll, ci->initialGuessPitch, ci->initialGuessYaw};
+    liorf_host::update_initial_guess(s, no_keyframes_yet != 0, g, use_imu_heading != 0, imu_type, tf);
+    std::memcpy(state->lastImuTransformation, s.lastImuTransformation, 48); std::memcpy(state->lastImuPreTransformation, s.lastImuPreTransformation, 48);
+    state->lastImuPreTransAvailable = s.lastImuPreTransAvailable ? 1 : 0;
+    return LIORF_OK;
+}
+int liorf_host_transform_update(float tf[6], int imu_available, int imu_type, float imu_roll_init, float imu_pitch_init, float imu_rpy_weight, float rot_tol,
+                                float z_tol) {
+    if (!tf) return LIORF_ERR_ARG;
+    liorf_host::transform_update(tf, imu_available != 0, imu_type, imu_roll_init, imu_pitch_init, imu_rpy_weight, rot_tol, z_tol);
     return LIORF_OK;
 }
 int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose6[6], float dist_thr, float ang_thr) {
@@ -1086,7 +1112,12 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     lap(2);
     if ((rc = join_map(c))) return rc;
     stamp(4, c->stream);
-    if ((rc = liorf_scan2map_optimization_async(c, in->initial_guess, in->max_iters > 0 ? in->max_iters : 30, 0))) return rc;
+    float guess[6];
+    if (in->use_cloud_info) {                                                    // updateInitialGuess (:899-958) from the previous pose
+        std::memcpy(guess, c->tf_mapped, sizeof(guess));
+        liorf_host_update_initial_guess(&c->guess_state, c->kfs.empty() ? 1 : 0, &in->cloud_info, in->use_imu_heading_initialization, in->imu_type, guess);
+    } else std::memcpy(guess, in->initial_guess, sizeof(guess));
+    if ((rc = liorf_scan2map_optimization_async(c, guess, in->max_iters > 0 ? in->max_iters : 30, 0))) return rc;
     stamp(5, c->stream);
     lap(3);
     if ((rc = liorf_get_pose(c, out->pose, nullptr))) return rc;                  // the frame's single round trip
@@ -1094,7 +1125,12 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     if (c->host_timing) for (int k = 1; k <= 5; ++k) { float ms = 0; if (c->tl_ev[k] && cudaEventElapsedTime(&ms, c->tl_ev[0], c->tl_ev[k]) == cudaSuccess) c->tl_ms[k] += ms; }
     out->n_kept = c->h_n_scan; out->n_ds = c->h_n_ds; out->m_ds = c->h_m_ds;
     out->iters = c->h_mail[1024 + 448]; out->converged = c->h_mail[1024 + 449]; out->degenerate = c->h_mail[1024 + 450]; out->ran = c->h_mail[1024 + 451];
-    if (out->ran) liorf_host::transform_update_clamp(out->pose, in->rotation_tollerance, in->z_tollerance);
+    if (out->ran) {                                                              // transformUpdate (:1323-1353) only after a solve (:1317)
+        if (in->use_cloud_info) liorf_host::transform_update(out->pose, in->cloud_info.imuAvailable != 0, in->imu_type, in->cloud_info.imuRollInit,
+                                                             in->cloud_info.imuPitchInit, in->imu_rpy_weight, in->rotation_tollerance, in->z_tollerance);
+        else liorf_host::transform_update_clamp(out->pose, in->rotation_tollerance, in->z_tollerance);
+    }
+    std::memcpy(c->tf_mapped, out->pose, sizeof(c->tf_mapped));
     // saveKeyFramesAndFactor (the parts on the path): saveFrame gate, keyframe cloud, ScanContext descriptor
     if (liorf_save_frame(c, out->pose, in->adding_dist_threshold, in->adding_angle_threshold) == 1) {
         int id = liorf_add_keyframe(c, out->pose, in->time_scan_cur);

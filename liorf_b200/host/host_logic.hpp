@@ -3,6 +3,8 @@
 //   extract_nearby            mapOptimization::extractNearby            src/mapOptmization.cpp:975-1010 (keyframe SELECTION only)
 //   save_frame                mapOptimization::saveFrame                src/mapOptmization.cpp:1365-1384
 //   transform_update_clamp    mapOptimization::transformUpdate          src/mapOptmization.cpp:1348-1350 (the clamps)
+//   transform_update          mapOptimization::transformUpdate          src/mapOptmization.cpp:1323-1353 (9-axis roll/pitch slerp + clamps)
+//   update_initial_guess      mapOptimization::updateInitialGuess       src/mapOptmization.cpp:899-958
 // They run on a few hundred key poses per frame; the heavy half of extractSurroundingKeyFrames (extractCloud) is CUDA.
 #pragma once
 #include <algorithm>
@@ -60,6 +62,104 @@ inline void transform_update_clamp(float tf[6], float rotation_tollerance, float
     tf[0] = constraint_transformation(tf[0], rotation_tollerance);
     tf[1] = constraint_transformation(tf[1], rotation_tollerance);
     tf[5] = constraint_transformation(tf[5], z_tollerance);
+}
+
+
+// ---- transformUpdate with the 9-axis IMU fusion (:1323-1353) --------------------------------------------------------
+// tf::Quaternion / tf::Matrix3x3 (tfScalar = double) restated for the two single-axis blends the reference performs.
+struct Quat { double x, y, z, w; };
+inline Quat quat_set_rpy(double roll, double pitch, double yaw) {                 // tf::Quaternion::setRPY
+    const double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+    const double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+    return Quat{sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+}
+inline double quat_dot(const Quat& a, const Quat& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+inline Quat quat_slerp(const Quat& a, const Quat& q, double t) {                  // tf::Quaternion::slerp (shortest path)
+    const double s = std::sqrt(quat_dot(a, a) * quat_dot(q, q));
+    const double dp = quat_dot(a, q);
+    const double theta = (dp < 0 ? std::acos(-dp / s) * 2.0 : std::acos(dp / s) * 2.0) / 2.0;       // angleShortestPath(q) / 2
+    if (theta != 0.0) {
+        const double d = 1.0 / std::sin(theta), s0 = std::sin((1.0 - t) * theta), s1 = std::sin(t * theta);
+        if (dp < 0) return Quat{(a.x * s0 + -q.x * s1) * d, (a.y * s0 + -q.y * s1) * d, (a.z * s0 + -q.z * s1) * d, (a.w * s0 + -q.w * s1) * d};
+        return Quat{(a.x * s0 + q.x * s1) * d, (a.y * s0 + q.y * s1) * d, (a.z * s0 + q.z * s1) * d, (a.w * s0 + q.w * s1) * d};
+    }
+    return a;
+}
+inline void quat_get_rpy(const Quat& q, double& roll, double& pitch, double& yaw) {   // tf::Matrix3x3(q).getRPY → getEulerYPR, solution 1
+    const double d = quat_dot(q, q), s = 2.0 / d;
+    const double xs = q.x * s, ys = q.y * s, zs = q.z * s;
+    const double wx = q.w * xs, wy = q.w * ys, wz = q.w * zs, xx = q.x * xs, xy = q.x * ys, xz = q.x * zs, yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+    const double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+    if (std::fabs(m20) >= 1.0) {                                                 // gimbal lock branch of getEulerYPR
+        yaw = 0.0;
+        const double delta = std::atan2(m21, m22);
+        if (m20 < 0) { pitch = M_PI / 2.0; roll = delta; } else { pitch = -M_PI / 2.0; roll = delta; }
+        return;
+    }
+    pitch = -std::asin(m20);
+    roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+    yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+}
+inline void transform_update(float tf[6], bool imu_available, int imu_type, float imu_roll_init, float imu_pitch_init, float imu_rpy_weight,
+                             float rotation_tollerance, float z_tollerance) {
+    if (imu_available && imu_type) {                                             // :1325
+        if (std::abs(imu_pitch_init) < 1.4) {                                    // :1327 (float abs compared with the double literal)
+            const double w = imu_rpy_weight;
+            double r, p, y;
+            quat_get_rpy(quat_slerp(quat_set_rpy(tf[0], 0, 0), quat_set_rpy(imu_roll_init, 0, 0), w), r, p, y);   // :1335-1338
+            tf[0] = (float)r;
+            quat_get_rpy(quat_slerp(quat_set_rpy(0, tf[1], 0), quat_set_rpy(0, imu_pitch_init, 0), w), r, p, y);  // :1341-1344
+            tf[1] = (float)p;
+        }
+    }
+    transform_update_clamp(tf, rotation_tollerance, z_tollerance);              // :1348-1350
+}
+
+// ---- updateInitialGuess (:899-958) -----------------------------------------------------------------------------------
+// The function-local statics of the reference become an explicit state object.
+struct InitialGuessState {
+    float lastImuTransformation[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    bool lastImuPreTransAvailable = false;
+    float lastImuPreTransformation[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+};
+struct CloudInfoGuess {                      // the cloud_info fields the function reads (msg/cloud_info.msg)
+    int imuAvailable, odomAvailable;
+    float imuRollInit, imuPitchInit, imuYawInit;
+    float initialGuessX, initialGuessY, initialGuessZ, initialGuessRoll, initialGuessPitch, initialGuessYaw;
+};
+inline void update_initial_guess(InitialGuessState& st, bool no_keyframes_yet, const CloudInfoGuess& ci, bool useImuHeadingInitialization, int imuType, float tf[6]) {
+    if (no_keyframes_yet) {                                                      // :906-917
+        tf[0] = ci.imuRollInit; tf[1] = ci.imuPitchInit; tf[2] = ci.imuYawInit;
+        if (!useImuHeadingInitialization) tf[2] = 0;
+        get_transformation(0, 0, 0, ci.imuRollInit, ci.imuPitchInit, ci.imuYawInit, st.lastImuTransformation);
+        return;
+    }
+    if (ci.odomAvailable) {                                                      // :922-943 IMU pre-integration increment
+        float transBack[12];
+        get_transformation(ci.initialGuessX, ci.initialGuessY, ci.initialGuessZ, ci.initialGuessRoll, ci.initialGuessPitch, ci.initialGuessYaw, transBack);
+        if (!st.lastImuPreTransAvailable) {
+            for (int i = 0; i < 12; ++i) st.lastImuPreTransformation[i] = transBack[i];
+            st.lastImuPreTransAvailable = true;                                  // falls through to the IMU-rotation branch (:945)
+        } else {
+            float inv[12], incre[12], tobe[12], fin[12];
+            affine_inverse(st.lastImuPreTransformation, inv); affine_mul(inv, transBack, incre);
+            get_transformation(tf[3], tf[4], tf[5], tf[0], tf[1], tf[2], tobe);
+            affine_mul(tobe, incre, fin);
+            get_translation_and_euler(fin, tf[3], tf[4], tf[5], tf[0], tf[1], tf[2]);
+            for (int i = 0; i < 12; ++i) st.lastImuPreTransformation[i] = transBack[i];
+            get_transformation(0, 0, 0, ci.imuRollInit, ci.imuPitchInit, ci.imuYawInit, st.lastImuTransformation);
+            return;
+        }
+    }
+    if (ci.imuAvailable && imuType) {                                            // :946-957 rotation-only increment
+        float transBack[12], inv[12], incre[12], tobe[12], fin[12];
+        get_transformation(0, 0, 0, ci.imuRollInit, ci.imuPitchInit, ci.imuYawInit, transBack);
+        affine_inverse(st.lastImuTransformation, inv); affine_mul(inv, transBack, incre);
+        get_transformation(tf[3], tf[4], tf[5], tf[0], tf[1], tf[2], tobe);
+        affine_mul(tobe, incre, fin);
+        get_translation_and_euler(fin, tf[3], tf[4], tf[5], tf[0], tf[1], tf[2]);
+        for (int i = 0; i < 12; ++i) st.lastImuTransformation[i] = transBack[i];
+    }
 }
 
 // extractNearby (:975-1010): ids of the keyframes whose clouds extractCloud will fuse, IN ORDER, duplicates included.

@@ -20,6 +20,7 @@ struct ParamServer {                                   // include/utility.h:68-2
     liorf_params p;
     float surroundingkeyframeAddingDistThreshold = 1.0f, surroundingkeyframeAddingAngleThreshold = 0.2f;
     float surroundingKeyframeDensity = 2.0f, z_tollerance = 1000.f, rotation_tollerance = 1000.f;
+    int imuType = 0, useImuHeadingInitialization = 1; float imuRPYWeight = 0.01f;      // utility.h: imuType, useImuHeadingInitialization, imuRPYWeight
     ParamServer() { liorf_default_params(&p); }
 };
 
@@ -84,7 +85,14 @@ public:
         if (!lastTrace.ran) { std::fprintf(stderr, "Not enough features!\n"); return; }   // ROS_WARN at :1319
         transformUpdate();
     }
-    void transformUpdate() { liorf_transform_update_clamp(transformTobeMapped, P.rotation_tollerance, P.z_tollerance); }   // :1348-1350 (6-axis IMU)
+    liorf_cloud_info_guess cloudInfo{};                                          // the cloud_info fields the two scalar steps read
+    void updateInitialGuess() {                                                  // :899-958
+        liorf_host_update_initial_guess(&guessState, liorf_num_keyframes(ctx.get()) <= 0, &cloudInfo, P.useImuHeadingInitialization, P.imuType, transformTobeMapped);
+    }
+    void transformUpdate() {                                                     // :1323-1353
+        liorf_host_transform_update(transformTobeMapped, cloudInfo.imuAvailable, P.imuType, cloudInfo.imuRollInit, cloudInfo.imuPitchInit, P.imuRPYWeight,
+                                    P.rotation_tollerance, P.z_tollerance);
+    }
     bool saveFrame() { return liorf_save_frame(ctx.get(), transformTobeMapped, P.surroundingkeyframeAddingDistThreshold, P.surroundingkeyframeAddingAngleThreshold) == 1; }
     // the part of saveKeyFramesAndFactor that touches the hot path's data (:1576-1595); the factor graph stays outside
     int saveKeyFrame() { int id = liorf_add_keyframe(ctx.get(), transformTobeMapped, timeLaserInfoCur); if (id >= 0) liorf_sc_make_and_save(ctx.get(), nullptr, 0); return id; }
@@ -100,6 +108,7 @@ public:
 private:
     Context& ctx;
     const ParamServer& P;
+    liorf_guess_state guessState{};
 };
 
 class SCManager {

@@ -510,6 +510,92 @@ inline void affine_mul(const float a[12], const float b[12], float o[12]) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// updateInitialGuess (src/mapOptmization.cpp:899-958) and transformUpdate (:1323-1353), scalar host code in the reference.
+// Restated as one object holding what the reference keeps in members / function-local statics.  tf::Quaternion and
+// tf::Matrix3x3 (ROS tf, tfScalar = double; not in this container → parity unpinned) are restated from their published
+// formulas: setRPY, angleShortestPath, slerp, Matrix3x3::setRotation + getEulerYPR.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GuessCloudInfo { int imuAvailable, odomAvailable; float imuRollInit, imuPitchInit, imuYawInit, gx, gy, gz, groll, gpitch, gyaw; };
+struct MapOptScalarState {
+    float transformTobeMapped[6] = {0, 0, 0, 0, 0, 0};
+    float lastImuTransformation[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    float lastImuPreTransformation[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    int lastImuPreTransAvailable = 0;
+
+    void euler_of(const float t[12]) {                                          // pcl::getTranslationAndEulerAngles into transformTobeMapped
+        transformTobeMapped[3] = t[3]; transformTobeMapped[4] = t[7]; transformTobeMapped[5] = t[11];
+        transformTobeMapped[0] = std::atan2(t[9], t[10]); transformTobeMapped[1] = std::asin(-t[8]); transformTobeMapped[2] = std::atan2(t[4], t[0]);
+    }
+    void advance_by(const float last[12], const float now[12]) {                 // transTobe * (last^-1 * now)
+        float li[12], inc[12], tobe[12], fin[12];
+        affine_inverse(last, li); affine_mul(li, now, inc);
+        trans2affine(transformTobeMapped, tobe); affine_mul(tobe, inc, fin);
+        euler_of(fin);
+    }
+    void updateInitialGuess(bool cloudKeyPoses3D_empty, const GuessCloudInfo& ci, bool useImuHeadingInitialization, int imuType) {
+        float imuNow[12]; get_transformation(0, 0, 0, ci.imuRollInit, ci.imuPitchInit, ci.imuYawInit, imuNow);
+        if (cloudKeyPoses3D_empty) {                                             // :906-917
+            transformTobeMapped[0] = ci.imuRollInit; transformTobeMapped[1] = ci.imuPitchInit;
+            transformTobeMapped[2] = useImuHeadingInitialization ? ci.imuYawInit : 0.f;
+            std::memcpy(lastImuTransformation, imuNow, sizeof(imuNow));
+            return;
+        }
+        if (ci.odomAvailable) {                                                  // :922
+            float transBack[12]; get_transformation(ci.gx, ci.gy, ci.gz, ci.groll, ci.gpitch, ci.gyaw, transBack);
+            const bool first = !lastImuPreTransAvailable;
+            if (!first) advance_by(lastImuPreTransformation, transBack);         // :932-936
+            std::memcpy(lastImuPreTransformation, transBack, sizeof(transBack)); lastImuPreTransAvailable = 1;
+            if (!first) { std::memcpy(lastImuTransformation, imuNow, sizeof(imuNow)); return; }   // :940-941
+        }
+        if (ci.imuAvailable && imuType) {                                        // :946-957
+            advance_by(lastImuTransformation, imuNow);
+            std::memcpy(lastImuTransformation, imuNow, sizeof(imuNow));
+        }
+    }
+    // tf pieces
+    struct Q { double x, y, z, w; };
+    static Q setRPY(double roll, double pitch, double yaw) {
+        double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+        double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+        Q q; q.x = sr * cp * cy - cr * sp * sy; q.y = cr * sp * cy + sr * cp * sy; q.z = cr * cp * sy - sr * sp * cy; q.w = cr * cp * cy + sr * sp * sy;
+        return q;
+    }
+    static double dot(const Q& a, const Q& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+    static Q slerp(const Q& a, const Q& b, double t) {
+        double s = std::sqrt(dot(a, a) * dot(b, b)), dab = dot(a, b);
+        double shortest = dab < 0 ? std::acos(-dab / s) * 2.0 : std::acos(dab / s) * 2.0;
+        double theta = shortest / 2.0;
+        if (theta == 0.0) return a;
+        double d = 1.0 / std::sin(theta), s0 = std::sin((1.0 - t) * theta), s1 = std::sin(t * theta);
+        double sg = dab < 0 ? -1.0 : 1.0;
+        Q r; r.x = (a.x * s0 + sg * b.x * s1) * d; r.y = (a.y * s0 + sg * b.y * s1) * d; r.z = (a.z * s0 + sg * b.z * s1) * d; r.w = (a.w * s0 + sg * b.w * s1) * d;
+        return r;
+    }
+    static void getRPY(const Q& q, double& roll, double& pitch, double& yaw) {
+        double s = 2.0 / dot(q, q);
+        double xs = q.x * s, ys = q.y * s, zs = q.z * s, wx = q.w * xs, wy = q.w * ys, wz = q.w * zs;
+        double xx = q.x * xs, xy = q.x * ys, xz = q.x * zs, yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+        double r0x = 1.0 - (yy + zz), r1x = xy + wz, r2x = xz - wy, r2y = yz + wx, r2z = 1.0 - (xx + yy);
+        if (std::fabs(r2x) >= 1) { yaw = 0; roll = std::atan2(r2y, r2z); pitch = r2x < 0 ? M_PI / 2.0 : -M_PI / 2.0; return; }
+        pitch = -std::asin(r2x);
+        double c = std::cos(pitch);
+        roll = std::atan2(r2y / c, r2z / c); yaw = std::atan2(r1x / c, r0x / c);
+    }
+    void transformUpdate(const GuessCloudInfo& ci, int imuType, float imuRPYWeight, float rotation_tollerance, float z_tollerance) {
+        if (ci.imuAvailable && imuType && std::abs(ci.imuPitchInit) < 1.4) {
+            double w = imuRPYWeight, r, p, y;
+            getRPY(slerp(setRPY(transformTobeMapped[0], 0, 0), setRPY(ci.imuRollInit, 0, 0), w), r, p, y); transformTobeMapped[0] = (float)r;
+            getRPY(slerp(setRPY(0, transformTobeMapped[1], 0), setRPY(0, ci.imuPitchInit, 0), w), r, p, y); transformTobeMapped[1] = (float)p;
+        }
+        auto clampf = [](float v, float lim) { return v < -lim ? -lim : (v > lim ? lim : v); };
+        transformTobeMapped[0] = clampf(transformTobeMapped[0], rotation_tollerance);
+        transformTobeMapped[1] = clampf(transformTobeMapped[1], rotation_tollerance);
+        transformTobeMapped[5] = clampf(transformTobeMapped[5], z_tollerance);
+    }
+};
+
 // deskew_enabled == 0 reproduces `deskewFlag == -1 || imuAvailable == false` passthrough (:538).
 inline int project_point_cloud(const PRaw* in, int n, const DeskewParams& P, double timeScanCur, const double* imuTime,
                                const double* rx, const double* ry, const double* rz, int imuPointerCur, int deskew_enabled,

@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE — never linked into the product library.
 #include "liorf_oracle.hpp"
 #include <chrono>
+#include <cstring>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -23,6 +24,22 @@ void orc_set_num_threads(int n) {
 #else
     (void)n;
 #endif
+}
+
+// scalar pre/post steps of laserCloudInfoHandler: state37 = {tf[6], lastImuTransformation[12], lastImuPreTransformation[12], available}
+static void st_load(MapOptScalarState& m, const float* st) { std::memcpy(m.transformTobeMapped, st, 24); std::memcpy(m.lastImuTransformation, st + 6, 48); std::memcpy(m.lastImuPreTransformation, st + 18, 48); m.lastImuPreTransAvailable = (int)st[30]; }
+static void st_store(const MapOptScalarState& m, float* st) { std::memcpy(st, m.transformTobeMapped, 24); std::memcpy(st + 6, m.lastImuTransformation, 48); std::memcpy(st + 18, m.lastImuPreTransformation, 48); st[30] = (float)m.lastImuPreTransAvailable; }
+void orc_update_initial_guess(float* state31, int no_keyframes, const float* ci11 /*imuAvail, odomAvail, imu rpy, guess xyz rpy*/, int useImuHeading, int imuType) {
+    MapOptScalarState m; st_load(m, state31);
+    GuessCloudInfo ci{(int)ci11[0], (int)ci11[1], ci11[2], ci11[3], ci11[4], ci11[5], ci11[6], ci11[7], ci11[8], ci11[9], ci11[10]};
+    m.updateInitialGuess(no_keyframes != 0, ci, useImuHeading != 0, imuType);
+    st_store(m, state31);
+}
+void orc_transform_update(float* tf6, int imuAvailable, int imuType, float imuRoll, float imuPitch, float weight, float rot_tol, float z_tol) {
+    MapOptScalarState m; std::memcpy(m.transformTobeMapped, tf6, 24);
+    GuessCloudInfo ci{imuAvailable, 0, imuRoll, imuPitch, 0, 0, 0, 0, 0, 0, 0};
+    m.transformUpdate(ci, imuType, weight, rot_tol, z_tol);
+    std::memcpy(tf6, m.transformTobeMapped, 24);
 }
 
 void orc_get_transformation(float x, float y, float z, float roll, float pitch, float yaw, float* t12) {

@@ -145,6 +145,21 @@ def scan2map(scan, map_pts, tf6, max_iters=30, force_all=False, state37=None, us
     return dict(iters=it, tf=tf, state=st, trace=trace[:it].copy(), nsel=nsel[:it].copy())
 
 
+def update_initial_guess(state31, no_keyframes, cloud_info11, use_imu_heading=True, imu_type=1):
+    """state31 = tf[6] + lastImuTransformation[12] + lastImuPreTransformation[12] + available; cloud_info11 = (imuAvailable,
+    odomAvailable, imuRollInit, imuPitchInit, imuYawInit, initialGuessX, Y, Z, Roll, Pitch, Yaw).  Returns the new state."""
+    st = np.array(state31, np.float32).copy(); ci = np.ascontiguousarray(cloud_info11, np.float32)
+    lib().orc_update_initial_guess(_fp(st), C.c_int(int(no_keyframes)), _fp(ci), C.c_int(int(use_imu_heading)), C.c_int(int(imu_type)))
+    return st
+
+
+def transform_update(tf6, imu_available, imu_type, imu_roll, imu_pitch, weight, rot_tol, z_tol):
+    tf = np.array(tf6, np.float32).copy()
+    lib().orc_transform_update(_fp(tf), C.c_int(int(imu_available)), C.c_int(int(imu_type)), C.c_float(imu_roll), C.c_float(imu_pitch), C.c_float(weight),
+                               C.c_float(rot_tol), C.c_float(z_tol))
+    return tf
+
+
 def project_point_cloud(raw, params, time_scan_cur, imu_time, imu_rot, imu_pointer_cur, deskew_enabled=True):
     """raw: structured PRAW array; imu_rot: (rows,3) float64; params: dict(lidarMinRange,lidarMaxRange,N_SCAN,downsampleRate,point_filter_num)."""
     raw = np.ascontiguousarray(raw, dtype=PRAW)

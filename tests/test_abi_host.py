@@ -104,3 +104,73 @@ def test_save_frame_gate(lib):
     p = np.array([5.0, -3.0, 0.1, 1, 2, 12.0], np.float32)
     lib.liorf_transform_update_clamp(p.ctypes.data_as(C.c_void_p), C.c_float(1.0), C.c_float(10.0))
     assert list(p) == [1.0, -1.0, np.float32(0.1), 1.0, 2.0, 10.0]
+
+
+# ---------------------------------------------------------------------------------------------- §8f-2 scalar pre / post steps
+def _guess_lib(lib, st, no_kf, ci, tf, heading=True, imu_type=1):
+    from liorf_b200 import CloudInfoGuess
+    c = CloudInfoGuess(int(ci[0]), int(ci[1]), *[float(v) for v in ci[2:]])
+    t = np.array(tf, np.float32)
+    assert lib.liorf_host_update_initial_guess(C.byref(st), int(no_kf), C.byref(c), int(heading), int(imu_type), t.ctypes.data_as(C.c_void_p)) == 0
+    return t
+
+
+def test_update_initial_guess_matches_oracle_sequence(lib):
+    """updateInitialGuess (src/mapOptmization.cpp:899-958) over a synthetic drive: first frame (no keyframes), first frame with
+    odometry (only latches lastImuPreTransformation and falls through to the IMU-rotation branch), then pre-integration
+    increments, with and without odometry / IMU — library host code vs the oracle's separate restatement, float for float."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as o
+    from liorf_b200 import GuessState
+    rng = np.random.default_rng(3)
+    for imu_type, heading in ((1, True), (0, True), (1, False)):
+        st = GuessState(); ost = np.zeros(31, np.float32); ost[6:18] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]; ost[18:30] = ost[6:18]
+        tf = np.zeros(6, np.float32)
+        odo = np.array([0, 0, 0, 0.01, -0.02, 0.3], np.float64)      # x y z roll pitch yaw of the pre-integration odometry
+        for k in range(40):
+            odo += np.array([0.8, 0.05, 0.01, 0.001, -0.002, 0.02]) + rng.normal(scale=1e-3, size=6)
+            imu_rpy = odo[3:] + rng.normal(scale=2e-3, size=3)
+            ci = np.array([k % 7 != 6, k % 5 != 4, *imu_rpy, *odo], np.float32)
+            no_kf = k == 0
+            tf = _guess_lib(lib, st, no_kf, ci, tf, heading, imu_type)
+            ost[:6] = ost[:6] if k else 0
+            ost = o.update_initial_guess(ost, no_kf, ci, heading, imu_type)
+            assert np.array_equal(tf, ost[:6]), (imu_type, heading, k, tf, ost[:6])
+            assert np.array_equal(np.array(st.lastImuTransformation[:], np.float32), ost[6:18])
+            assert np.array_equal(np.array(st.lastImuPreTransformation[:], np.float32), ost[18:30]) and st.lastImuPreTransAvailable == int(ost[30])
+        assert tf[3] > 15.0 and tf[2] > 0.4                      # the chained increments carried the pose along the drive
+
+
+def test_update_initial_guess_increment_is_body_frame(lib):
+    from liorf_b200 import GuessState
+    st = GuessState()
+    tf = _guess_lib(lib, st, True, [1, 1, 0, 0, 0.5, 10, 20, 0, 0, 0, 0.5], np.zeros(6))     # first frame: attitude from the IMU
+    assert np.allclose(tf, [0, 0, 0.5, 0, 0, 0])
+    tf = _guess_lib(lib, st, False, [1, 1, 0, 0, 0.5, 10, 20, 0, 0, 0, 0.5], tf)            # latches the odometry pose, no motion
+    assert np.allclose(tf, [0, 0, 0.5, 0, 0, 0], atol=1e-6)
+    tf[2] = 1.0                                                                              # the optimiser turned the pose to yaw = 1.0
+    c, s = np.cos(0.5), np.sin(0.5)
+    tf = _guess_lib(lib, st, False, [1, 1, 0, 0, 0.5, 10 + c, 20 + s, 0, 0, 0, 0.5], tf)    # odometry: 1 m forward in ITS heading
+    assert np.allclose(tf[3:5], [np.cos(1.0), np.sin(1.0)], atol=1e-5) and abs(tf[2] - 1.0) < 1e-6   # applied in the pose's own frame
+
+
+def test_transform_update_slerp_and_clamps(lib):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as o
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        tf = rng.normal(scale=[0.2, 0.2, 1.0, 30, 30, 3], size=6).astype(np.float32)
+        ir, ip, w = float(rng.normal(scale=0.2)), float(rng.normal(scale=0.2)), float(rng.choice([0.0, 0.01, 0.3, 1.0]))
+        avail, itype = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        g = tf.copy()
+        lib.liorf_host_transform_update(g.ctypes.data_as(C.c_void_p), avail, itype, C.c_float(ir), C.c_float(ip), C.c_float(w), C.c_float(0.3), C.c_float(2.0))
+        r = o.transform_update(tf, avail, itype, ir, ip, w, 0.3, 2.0)
+        assert np.array_equal(g, r)
+        if avail and itype:                                        # single-axis slerp == linear blend of the angle
+            assert abs(g[0] - np.clip((1 - w) * tf[0] + w * np.float32(ir), -0.3, 0.3)) < 2e-6
+            assert abs(g[1] - np.clip((1 - w) * tf[1] + w * np.float32(ip), -0.3, 0.3)) < 2e-6
+        else:
+            assert g[0] == np.clip(tf[0], -0.3, 0.3) and g[1] == np.clip(tf[1], -0.3, 0.3)
+        assert g[5] == np.clip(tf[5], -2.0, 2.0) and np.array_equal(g[2:5], tf[2:5])

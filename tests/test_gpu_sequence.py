@@ -73,3 +73,38 @@ def test_process_frame_equals_stepwise_calls(drive):
         prev_c = pc
         assert a.ctx.numKeyframes() == c.numKeyframes()
     a.ctx.close(); c.close()
+
+
+def test_process_frame_with_cloud_info_guess(drive, oracle):
+    """liorf_process_frame fed like the reference's callback: the initial guess comes from updateInitialGuess
+    (src/mapOptmization.cpp:899-958) applied to the context's previous pose and the cloud_info odometry fields, and the full
+    transformUpdate (:1323-1353, 9-axis roll/pitch blend) follows the solve.  Same steps on the oracle side, frame by frame."""
+    bench, seq = drive
+    from liorf_b200 import CloudInfoGuess
+    gpu = bench.GpuPipeline(seq, 0)
+    gpu.stage(range(N_FRAMES))
+    cpu = bench.CpuPipeline(seq)
+    rng = np.random.default_rng(11)
+    ost = np.zeros(31, np.float32); ost[6:18] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]; ost[18:30] = ost[6:18]
+    for i in range(N_FRAMES):
+        raw, (t0, it, rot, ptr) = seq.frame(i)
+        p = seq.poses[i]                                            # (roll, pitch, yaw, x, y, z): stands in for the IMU pre-integration odometry
+        odo = np.concatenate([p[3:], p[:3]]) + rng.normal(scale=[0.02, 0.02, 0.02, 1e-3, 1e-3, 1e-3])
+        imu_rpy = p[:3] + rng.normal(scale=2e-3, size=3)
+        ci11 = np.array([1, 1, *imu_rpy, *odo], np.float32)
+        ci = CloudInfoGuess(1, 1, *[float(v) for v in ci11[2:]])
+        no_kf = gpu.ctx.numKeyframes() == 0
+        fo = gpu.ctx.processFrame(gpu.pin_raw[i].data_ptr(), len(raw), False, t0, it, seq.imu_cols[i], ptr, True, None, loop_every=10, frame_index=i,
+                                  cloud_info=ci, imu_type=1, use_imu_heading=True, imu_rpy_weight=0.01, rot_tol=1000.0, z_tol=1000.0)
+        ost[:6] = cpu.prev if cpu.prev is not None else 0
+        ost = oracle.update_initial_guess(ost, no_kf, ci11, True, 1)
+        post = lambda pose: oracle.transform_update(pose, 1, 1, float(ci11[2]), float(ci11[3]), 0.01, 1000.0, 1000.0)
+        o_pose = cpu.step(i, guess=ost[:6].copy(), post=post)
+        g_pose = np.array(fo.pose[:], np.float32)
+        assert np.max(np.abs(g_pose[3:] - o_pose[3:])) < 1e-4 and np.max(np.abs(g_pose[:3] - o_pose[:3])) < 1e-5, (i, g_pose, o_pose)
+        assert gpu.ctx.numKeyframes() == len(cpu.kf_clouds)
+        # keep the two pose chains in lock step (differences below the tolerance must not accumulate through the guess)
+        cpu.prev = g_pose.copy()
+        if fo.is_keyframe:
+            cpu.kf_poses[-1] = g_pose.copy()
+    gpu.ctx.close()
