@@ -193,6 +193,25 @@ int liorf_sc_tensor_dump(liorf_ctx* ctx, const float* qkeys, int Q, float* out, 
 /* single-GPU convenience with host buffers: descriptors of the Q queries → loop ids / shifts / distances */
 int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
 
+/* ---- loop-closure registration ------------------------------------------------------------------- */
+/* The ICP of mapOptimization::performSCLoopClosure (src/mapOptmization.cpp:624-730) without the factor graph:
+ * cureKeyframeCloud = loopFindNearKeyframes(loop_key_cur, 0, loop_index), prevKeyframeCloud = loopFindNearKeyframes(loop_key_pre,
+ * history_search_num, loop_index) (:821-844; loop_index = the keyframe whose pose transforms every cloud, the reference passes
+ * base_key = 0; -1 = each cloud by its own pose as performRSLoopClosure does), VoxelGrid(icp_leaf = loopClosureICPSurfLeafSize),
+ * guards (< 300 / < 1000 points → ran = 0), pcl::IterativeClosestPoint with max correspondence distance max_corr_dist
+ * (= 2 historyKeyframeSearchRadius), max_iters (100), transformation / fitness epsilons 1e-6, no RANSAC, then getFitnessScore().
+ * The caller applies `converged && fitness <= historyKeyframeFitnessScore` (:665). */
+typedef struct {
+    int ran, converged, convergence_state /* 1 iterations, 2 transform, 3 abs mse, 4 rel mse, 5 no correspondences */, iterations;
+    int n_source, n_target;
+    float fitness;
+    float transform[16];            /* icp.getFinalTransformation(), row-major 4x4 */
+    float pose6[6];                 /* its (roll, pitch, yaw, x, y, z) by pcl::getTranslationAndEulerAngles (:693) */
+} liorf_icp_result;
+int liorf_loop_closure_icp(liorf_ctx* ctx, int loop_key_cur, int loop_key_pre, int history_search_num, int loop_index, float icp_leaf, float max_corr_dist,
+                           int max_iters, liorf_icp_result* out);
+int liorf_icp_get_clouds(liorf_ctx* ctx, liorf_point* source, int cap_source, liorf_point* target, int cap_target);   /* test hook */
+
 /* ---- one LiDAR frame through the whole path ------------------------------------------------------------------- */
 /* The call sequence of ImageProjection::cloudHandler (src/imageProjection.cpp:191-204) followed by
  * mapOptimization::laserCloudInfoHandler (src/mapOptmization.cpp:236-275) for a merged node: projectPointCloud →

@@ -68,6 +68,11 @@ class FrameOut(C.Structure):
                 ("loop_yaw", C.c_float)]
 
 
+class IcpResult(C.Structure):
+    _fields_ = [("ran", C.c_int), ("converged", C.c_int), ("convergence_state", C.c_int), ("iterations", C.c_int), ("n_source", C.c_int), ("n_target", C.c_int),
+                ("fitness", C.c_float), ("transform", C.c_float * 16), ("pose6", C.c_float * 6)]
+
+
 class LiorfError(RuntimeError):
     pass
 
@@ -354,6 +359,18 @@ class Context:
         lid = C.c_int(-1); yaw = C.c_float(0); md = C.c_double(0); cand = np.zeros(3, np.int32)
         _chk(self.lib.liorf_sc_detect_loop_closure_id(self.h, C.byref(lid), C.byref(yaw), C.byref(md), _vp(cand)), "liorf_sc_detect_loop_closure_id")
         return lid.value, yaw.value, md.value, cand
+
+    def loopClosureICP(self, loop_key_cur, loop_key_pre, history_search_num=25, loop_index=0, icp_leaf=0.5, max_corr_dist=20.0, max_iters=100):
+        """the ICP of performSCLoopClosure (src/mapOptmization.cpp:624-730) between two stored keyframes"""
+        r = IcpResult()
+        _chk(self.lib.liorf_loop_closure_icp(self.h, C.c_int(loop_key_cur), C.c_int(loop_key_pre), C.c_int(history_search_num), C.c_int(loop_index),
+                                             C.c_float(icp_leaf), C.c_float(max_corr_dist), C.c_int(max_iters), C.byref(r)), "liorf_loop_closure_icp")
+        return r
+
+    def icpClouds(self, n_source, n_target):
+        s = np.empty((max(n_source, 1), 4), np.float32); t = np.empty((max(n_target, 1), 4), np.float32)
+        _chk(self.lib.liorf_icp_get_clouds(self.h, _vp(s), C.c_int(n_source), _vp(t), C.c_int(n_target)), "liorf_icp_get_clouds")
+        return s[:n_source].copy(), t[:n_target].copy()
 
     def scSetSearchPath(self, mode):
         """ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tcgen05 coarse filter + exact re-rank"""

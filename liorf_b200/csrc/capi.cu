@@ -10,6 +10,7 @@
 #include "deskew.cuh"
 #include "scancontext.cuh"
 #include "sc_tensor.cuh"
+#include "icp.cuh"
 #include "../host/host_logic.hpp"
 #include <vector>
 #include <cstring>
@@ -82,6 +83,9 @@ struct liorf_ctx {
     DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_cmin, sct_cmin32, sct_qnorm, sct_part; DevBuf<int> sct_cand, sct_cnt, sct_over;
     float* sct_center = nullptr; unsigned* sct_nmax = nullptr; int* sct_over_cnt = nullptr;
     int sct_img_n = -1;              // number of database keys the B image was built from (-1: none)
+    // loop-closure ICP (icp.cuh)
+    DevBuf<float4> icp_raw, icp_src, icp_src0, icp_tgt; MapGrid icp_grid; DevBuf<double> icp_partial; double* icp_out = nullptr; int* icp_counter = nullptr;
+    DevBuf<KfSel> icp_sel; DevBuf<int> icp_nn_idx; DevBuf<float> icp_nn_d2;
     liorf_guess_state guess_state = {}; float tf_mapped[6] = {0, 0, 0, 0, 0, 0};   // updateInitialGuess statics + transformTobeMapped
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
     bool sct_attr_set = false; int sct_last_Q = 0;
@@ -235,6 +239,7 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     c->vg_map.mm_counter = c->d_misc + 10;
     c->vg_map.sort.ticket = c->d_misc + 11; c->vg_map.sort.err_flag = c->d_err;
     c->vg_map.scan.ticket = c->d_misc + 12; c->vg_map.scan.err_flag = c->d_err;
+    c->icp_grid.scan.ticket = c->d_misc + 13; c->icp_grid.scan.err_flag = c->d_err;
     CUDA_TRY(cudaMalloc(&c->dk.start_inv, 12 * sizeof(float)));
     c->dk.first_kept = c->d_counts + C_FIRST_KEPT;
     CUDA_TRY(cudaHostAlloc(&c->h_mail, 65536 + 2 * 65536, cudaHostAllocDefault));
@@ -293,6 +298,9 @@ void liorf_destroy(liorf_ctx* c) {
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
     c->sct_bimg.release(); c->sct_aimg.release(); c->sct_cmin.release(); c->sct_cmin32.release(); c->sct_qnorm.release(); c->sct_part.release(); c->sct_cand.release(); c->sct_cnt.release();
+    c->icp_raw.release(); c->icp_src.release(); c->icp_src0.release(); c->icp_tgt.release(); c->icp_partial.release(); c->icp_sel.release(); c->icp_nn_idx.release();
+    c->icp_nn_d2.release(); c->icp_grid.counts.release(); c->icp_grid.cell_start.release(); c->icp_grid.sorted.release(); c->icp_grid.scan.status.release();
+    if (c->icp_out) cudaFree(c->icp_out);
     c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
@@ -1075,6 +1083,106 @@ int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_
     if (min_dist) *min_dist = md;
     if (cand3) { cand3[0] = cand[0]; cand3[1] = cand[1]; cand3[2] = cand[2]; }
     *yaw_diff_rad = (float)((float)(nn_align * (360.0 / 60.0)) * M_PI / 180.0);   // deg2rad(float) (:17-20, :339)
+    return LIORF_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ loop-closure ICP
+// clouds of loopFindNearKeyframes (:821-844) as performSCLoopClosure calls it (:652-653): every selected keyframe cloud is
+// transformed by the pose of keyframe `loop_index` (the reference passes base_key = 0), concatenated, VoxelGrid(icp leaf).
+static int icp_build_cloud(liorf_ctx* c, int key, int search_num, int loop_index, float leaf, DevBuf<float4>& out, int* n_out) {
+    int rc;
+    std::vector<KfSel> sel; long long total = 0;
+    const int n_kf = (int)c->kfs.size();
+    for (int i = -search_num; i <= search_num; ++i) {
+        const int kn = key + i;
+        if (kn < 0 || kn >= n_kf) continue;
+        const Keyframe& k = c->kfs[kn];
+        const Keyframe& pk = c->kfs[loop_index != -1 ? loop_index : kn];
+        KfSel s; s.src_off = (int)k.off; s.count = k.count; s.dst_off = (int)total; s.pad = 0;
+        host_get_transformation(pk.pose[3], pk.pose[4], pk.pose[5], pk.pose[0], pk.pose[1], pk.pose[2], s.t);
+        total += k.count; sel.push_back(s);
+    }
+    *n_out = 0;
+    if (sel.empty() || total == 0) return LIORF_OK;
+    if (total > 0x7fffffffLL) return LIORF_ERR_ARG;
+    const int tot = (int)total, ns = (int)sel.size();
+    if ((rc = c->icp_sel.reserve(ns)) || (rc = c->icp_raw.reserve(tot)) || (rc = out.reserve(tot))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->icp_sel.p, sel.data(), (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                      // `sel` is pageable host memory going out of scope
+    k_transform_concat<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->kf_points.p, c->icp_sel.p, ns, tot, c->icp_raw.p);
+    if ((rc = voxel_grid_device(c->icp_raw.p, Count::of_host(tot), leaf, out.p, c->d_counts + C_HOOK_NSEL, nullptr, nullptr, c->vg, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_mail + 900, c->d_counts + C_HOOK_NSEL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_out = c->h_mail[900];
+    c->launches += 10;
+    return LIORF_OK;
+}
+
+int liorf_loop_closure_icp(liorf_ctx* c, int loop_key_cur, int loop_key_pre, int history_search_num, int loop_index, float icp_leaf, float max_corr_dist,
+                           int max_iters, liorf_icp_result* out) {
+    if (!c || !out || history_search_num < 0 || max_iters < 1 || !(icp_leaf > 0.f) || !(max_corr_dist > 0.f)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    std::memset(out, 0, sizeof(*out));
+    for (int i = 0; i < 4; ++i) out->transform[5 * i] = 1.f;
+    const int n_kf = (int)c->kfs.size();
+    if (loop_key_cur < 0 || loop_key_cur >= n_kf || loop_key_pre < 0 || loop_key_pre >= n_kf || loop_index < -1 || loop_index >= n_kf) return LIORF_ERR_ARG;
+    int rc;
+    if ((rc = join_map(c))) return rc;
+    int n_src = 0, n_tgt = 0;
+    if ((rc = icp_build_cloud(c, loop_key_cur, 0, loop_index, icp_leaf, c->icp_src0, &n_src))) return rc;                 // cureKeyframeCloud  (:652)
+    if ((rc = icp_build_cloud(c, loop_key_pre, history_search_num, loop_index, icp_leaf, c->icp_tgt, &n_tgt))) return rc;   // prevKeyframeCloud  (:653)
+    out->n_source = n_src; out->n_target = n_tgt;
+    if (n_src < 300 || n_tgt < 1000) return check_err(c);           // :655-656
+    out->ran = 1;
+    if (!c->icp_out) { CUDA_TRY(cudaMalloc(&c->icp_out, ICP_NSUM * sizeof(double))); c->icp_counter = c->d_misc + 14; }
+    int blocks = (n_src + ICP_BLOCK - 1) / ICP_BLOCK; if (blocks > 4 * c->num_sms) blocks = 4 * c->num_sms;
+    if ((rc = c->icp_partial.reserve((size_t)blocks * ICP_NSUM)) || (rc = c->icp_src.reserve(n_src))) return rc;
+    if ((rc = build_map_grid(c->icp_tgt.p, Count::of_host(n_tgt), c->icp_grid, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->icp_src.p, c->icp_src0.p, (size_t)n_src * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    const int r_max = (int)std::ceil(max_corr_dist) + 1;
+    const float max_d2 = max_corr_dist * max_corr_dist;
+    liorf_host::IcpConvergence cc; cc.max_iterations = max_iters;
+    float final_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, inc[16];
+    std::memcpy(inc, final_T, sizeof(inc));
+    bool converged = false;
+    double* h_sums = reinterpret_cast<double*>(c->h_mail + 3000);   // 8-byte aligned slot of the pinned mailbox
+    while (true) {
+        IcpT Ti; std::memcpy(Ti.t, inc, 12 * sizeof(float));
+        k_icp_iteration<<<blocks, ICP_BLOCK, 0, c->stream>>>(c->icp_src.p, n_src, Ti, c->icp_grid.cell_start.p, c->icp_grid.sorted.p, c->icp_grid.dims, r_max, max_d2,
+                                                           c->icp_partial.p, c->icp_counter, c->icp_out, nullptr, nullptr);
+        CUDA_TRY(cudaMemcpyAsync(h_sums, c->icp_out, ICP_NSUM * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        ++c->launches;
+        if (!liorf_host::icp_estimate(h_sums, inc)) { cc.state = liorf_host::IcpConvergence::NO_CORRESPONDENCES; converged = false; break; }
+        liorf_host::mat4_mul(inc, final_T, final_T);               // final_transformation_ = transformation_ * final_transformation_
+        ++out->iterations;
+        if (cc.has_converged(inc, h_sums[16] / h_sums[0])) { converged = true; break; }
+    }
+    out->converged = converged ? 1 : 0; out->convergence_state = (int)cc.state;
+    std::memcpy(out->transform, final_T, sizeof(final_T));
+    // getFitnessScore(): the original source under the final transformation, no range limit
+    {
+        IcpT Tf; std::memcpy(Tf.t, final_T, 12 * sizeof(float));
+        const int rfit = 64;
+        k_icp_fitness<<<blocks, ICP_BLOCK, 0, c->stream>>>(c->icp_src0.p, n_src, Tf, c->icp_grid.cell_start.p, c->icp_grid.sorted.p, c->icp_grid.dims, rfit, c->icp_partial.p,
+                                                         c->icp_counter, c->icp_out);
+        CUDA_TRY(cudaMemcpyAsync(h_sums, c->icp_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        ++c->launches;
+        out->fitness = h_sums[1] > 0 ? (float)(h_sums[0] / h_sums[1]) : 3.4028235e38f;
+    }
+    float t12[12]; for (int r = 0; r < 3; ++r) for (int k = 0; k < 4; ++k) t12[4 * r + k] = final_T[4 * r + k];
+    liorf_host::get_translation_and_euler(t12, out->pose6[3], out->pose6[4], out->pose6[5], out->pose6[0], out->pose6[1], out->pose6[2]);   // :693
+    return check_err(c);
+}
+/* test hook: the two clouds of the last liorf_loop_closure_icp (cureKeyframeCloud / prevKeyframeCloud after the ICP VoxelGrid) */
+int liorf_icp_get_clouds(liorf_ctx* c, liorf_point* source, int cap_source, liorf_point* target, int cap_target) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (source && cap_source > 0) CUDA_TRY(cudaMemcpy(source, c->icp_src0.p, (size_t)cap_source * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (target && cap_target > 0) CUDA_TRY(cudaMemcpy(target, c->icp_tgt.p, (size_t)cap_target * sizeof(float4), cudaMemcpyDeviceToHost));
     return LIORF_OK;
 }
 

@@ -5,6 +5,7 @@
 //   transform_update_clamp    mapOptimization::transformUpdate          src/mapOptmization.cpp:1348-1350 (the clamps)
 //   transform_update          mapOptimization::transformUpdate          src/mapOptmization.cpp:1323-1353 (9-axis roll/pitch slerp + clamps)
 //   update_initial_guess      mapOptimization::updateInitialGuess       src/mapOptmization.cpp:899-958
+//   icp_estimate / IcpConvergence   the scalar half of pcl::IterativeClosestPoint as performSCLoopClosure configures it (:652-674)
 // They run on a few hundred key poses per frame; the heavy half of extractSurroundingKeyFrames (extractCloud) is CUDA.
 #pragma once
 #include <algorithm>
@@ -161,6 +162,94 @@ inline void update_initial_guess(InitialGuessState& st, bool no_keyframes_yet, c
         for (int i = 0; i < 12; ++i) st.lastImuTransformation[i] = transBack[i];
     }
 }
+
+// ---- scalar half of pcl::IterativeClosestPoint (performSCLoopClosure, :652-674) ------------------------------------------
+// TransformationEstimationSVD → Eigen::umeyama without scaling, from the 17 sums the device reduces:
+// s[0] = n, s[1..3] = sum of source points, s[4..6] = sum of their target neighbours, s[7..15] = sum d_r * s_c (row r of the
+// target point, column c of the source point), s[16] = sum of squared distances.  Returns false for fewer than 3 pairs.
+inline void sym3_jacobi(double A[3][3], double V[3][3]) {      // eigen-decomposition of a symmetric 3x3 by cyclic Jacobi rotations
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        const double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            if (A[p][q] == 0.0) continue;
+            const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+            const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+            for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - sn * akq; A[k][q] = sn * akp + c * akq; }
+            for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - sn * aqk; A[q][k] = sn * apk + c * aqk; }
+            for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq; }
+        }
+    }
+}
+inline double det3(const double M[3][3]) {
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+inline bool icp_estimate(const double s[17], float T[16]) {
+    const double n = s[0];
+    if (n < 3.0) return false;                                   // min_number_correspondences_
+    const double ms[3] = {s[1] / n, s[2] / n, s[3] / n}, md[3] = {s[4] / n, s[5] / n, s[6] / n};
+    double S[3][3];                                              // sigma = (1/n) dst_demean * src_demean^T
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[r][c] = s[7 + 3 * r + c] / n - md[r] * ms[c];
+    double A[3][3], V[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = S[0][i] * S[0][j] + S[1][i] * S[1][j] + S[2][i] * S[2][j];   // S^T S
+    sym3_jacobi(A, V);
+    int ord[3] = {0, 1, 2};                                      // singular values descending
+    for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (A[ord[b]][ord[b]] > A[ord[a]][ord[a]]) std::swap(ord[a], ord[b]);
+    double Vs[3][3], U[3][3], sv[3];
+    for (int k = 0; k < 3; ++k) { sv[k] = std::sqrt(std::max(A[ord[k]][ord[k]], 0.0)); for (int i = 0; i < 3; ++i) Vs[i][k] = V[i][ord[k]]; }
+    for (int k = 0; k < 2; ++k) {
+        double u[3] = {0, 0, 0};
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) u[i] += S[i][j] * Vs[j][k];
+        const double nrm = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (!(nrm > 0.0)) return false;                          // rank < 2: no unique rotation
+        for (int i = 0; i < 3; ++i) U[i][k] = u[i] / nrm;
+    }
+    {   // third left vector: S v3 / s3 when well conditioned, else the completion of the frame (any sign: fixed below)
+        double u[3] = {0, 0, 0};
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) u[i] += S[i][j] * Vs[j][2];
+        const double nrm = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (nrm > 1e-9 * sv[0]) { for (int i = 0; i < 3; ++i) U[i][2] = u[i] / nrm; }
+        else { U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1]; U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1]; U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1]; }
+    }
+    const double sgn = det3(U) * det3(Vs) < 0 ? -1.0 : 1.0;     // Eigen::umeyama: S(2) = -1 when det(U) det(V) < 0
+    double R[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i][j] = U[i][0] * Vs[j][0] + U[i][1] * Vs[j][1] + sgn * U[i][2] * Vs[j][2];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T[4 * i + j] = (float)R[i][j];
+        T[4 * i + 3] = (float)(md[i] - (R[i][0] * ms[0] + R[i][1] * ms[1] + R[i][2] * ms[2]));
+    }
+    T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+    return true;
+}
+inline void mat4_mul(const float a[16], const float b[16], float o[16]) {       // Eigen Matrix4f product (float, k ascending)
+    float r[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float v = 0.f; for (int k = 0; k < 4; ++k) v += a[4 * i + k] * b[4 * k + j]; r[4 * i + j] = v; }
+    for (int k = 0; k < 16; ++k) o[k] = r[k];
+}
+// pcl::registration::DefaultConvergenceCriteria as pcl::IterativeClosestPoint::computeTransformation configures it (PCL 1.10):
+// max iterations, translation threshold = transformation_epsilon (on the SQUARED translation), rotation threshold
+// = 1 - transformation_epsilon (on cos of the angle), relative MSE = euclidean_fitness_epsilon, absolute MSE 1e-12,
+// max_iterations_similar_transforms = 0.
+struct IcpConvergence {
+    int max_iterations = 100; double translation_threshold = 1e-6, rotation_threshold = 1.0 - 1e-6, mse_relative = 1e-6, mse_absolute = 1e-12;
+    int iterations = 0; double prev_mse = 1.7976931348623157e308;
+    enum State { NOT_CONVERGED, ITERATIONS, TRANSFORM, ABS_MSE, REL_MSE, NO_CORRESPONDENCES } state = NOT_CONVERGED;
+    bool has_converged(const float T[16], double cur_mse) {
+        state = NOT_CONVERGED;
+        ++iterations;
+        if (iterations >= max_iterations) { state = ITERATIONS; return true; }
+        const double cos_angle = 0.5 * ((double)T[0] + (double)T[5] + (double)T[10] - 1.0);
+        const double tr2 = (double)T[3] * T[3] + (double)T[7] * T[7] + (double)T[11] * T[11];
+        if (cos_angle >= rotation_threshold && tr2 <= translation_threshold) { state = TRANSFORM; return true; }
+        if (std::fabs(cur_mse - prev_mse) < mse_absolute) { state = ABS_MSE; return true; }
+        if (std::fabs(cur_mse - prev_mse) / prev_mse < mse_relative) { state = REL_MSE; return true; }
+        prev_mse = cur_mse;
+        return false;
+    }
+};
 
 // extractNearby (:975-1010): ids of the keyframes whose clouds extractCloud will fuse, IN ORDER, duplicates included.
 inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double time_cur, float radius, float density) {

@@ -21,6 +21,8 @@ struct ParamServer {                                   // include/utility.h:68-2
     float surroundingkeyframeAddingDistThreshold = 1.0f, surroundingkeyframeAddingAngleThreshold = 0.2f;
     float surroundingKeyframeDensity = 2.0f, z_tollerance = 1000.f, rotation_tollerance = 1000.f;
     int imuType = 0, useImuHeadingInitialization = 1; float imuRPYWeight = 0.01f;      // utility.h: imuType, useImuHeadingInitialization, imuRPYWeight
+    float historyKeyframeSearchRadius = 10.0f, historyKeyframeFitnessScore = 0.3f, loopClosureICPSurfLeafSize = 0.5f;   // utility.h:239-248
+    int historyKeyframeSearchNum = 25;
     ParamServer() { liorf_default_params(&p); }
 };
 
@@ -96,6 +98,23 @@ public:
     bool saveFrame() { return liorf_save_frame(ctx.get(), transformTobeMapped, P.surroundingkeyframeAddingDistThreshold, P.surroundingkeyframeAddingAngleThreshold) == 1; }
     // the part of saveKeyFramesAndFactor that touches the hot path's data (:1576-1595); the factor graph stays outside
     int saveKeyFrame() { int id = liorf_add_keyframe(ctx.get(), transformTobeMapped, timeLaserInfoCur); if (id >= 0) liorf_sc_make_and_save(ctx.get(), nullptr, 0); return id; }
+    // performSCLoopClosure (:624-730) up to the point where the reference queues the loop factor: detectLoopClosureID, the two
+    // clouds of loopFindNearKeyframes (base_key = 0), pcl::IterativeClosestPoint, the fitness gate.  True = a factor
+    // (loopKeyCur, loopKeyPre, icp.pose6) would be pushed to loopIndexQueue / loopPoseQueue.
+    bool performSCLoopClosure(int& loopKeyCur, int& loopKeyPre, liorf_icp_result& icp) {
+        const int n = liorf_num_keyframes(ctx.get());
+        if (n <= 0) return false;                                                 // :626
+        float yawDiffRad = 0.f;
+        loopKeyCur = n - 1; loopKeyPre = -1;
+        if (liorf_sc_detect_loop_closure_id(ctx.get(), &loopKeyPre, &yawDiffRad, nullptr, nullptr) != 0 || loopKeyPre == -1) return false;   // :636-641
+        for (const auto& e : loopIndexContainer) if (e.first == loopKeyCur) return false;                                                  // :643-645
+        if (liorf_loop_closure_icp(ctx.get(), loopKeyCur, loopKeyPre, P.historyKeyframeSearchNum, 0, P.loopClosureICPSurfLeafSize,
+                                   P.historyKeyframeSearchRadius * 2, 100, &icp) != 0 || !icp.ran) return false;                            // :652-671
+        if (!icp.converged || icp.fitness > P.historyKeyframeFitnessScore) return false;                                                    // :673
+        loopIndexContainer.emplace_back(loopKeyCur, loopKeyPre);                                                                            // :727
+        return true;
+    }
+    std::vector<std::pair<int, int>> loopIndexContainer;
     // per-function forms used by the parity tests
     void surfOptimization(std::vector<liorf_point>& coeffSelSurfVec, std::vector<uint8_t>& laserCloudOriSurfFlag) {            // :1074
         int n = 0; liorf_get_scan_ds(ctx.get(), nullptr, 0, &n); laserCloudSurfLastDSNum = n;
