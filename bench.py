@@ -157,18 +157,21 @@ class CpuPipeline:
         near = np.lexsort((np.arange(len(P)), d))
         near = near[d[near] < radius * radius]
         ids = []
+        last = P[-1]
+        dist = lambda a, b: np.sqrt(((a - b) ** 2).astype(np.float32).sum(dtype=np.float32))
         if len(near):
             pts = np.concatenate([P[near], np.zeros((len(near), 1), np.float32)], 1)
             cent, _, _ = self.o.voxel_grid(pts, density)
-            for c in cent:
-                ids.append(int(np.argmin(((c[:3] - P) ** 2).sum(1))))
+            for c in cent:                                           # :1018 tests the voxel centroid, the id is its nearest real key pose
+                if not dist(c[:3], last) > radius:
+                    ids.append(int(np.argmin(((c[:3] - P) ** 2).sum(1))))
         for i in range(len(P) - 1, -1, -1):
             if t_cur - self.kf_times[i] < 10.0:
-                ids.append(i)
+                if not dist(P[i], last) > radius:
+                    ids.append(i)
             else:
                 break
-        last = P[-1]
-        return [i for i in ids if np.sqrt(((P[i] - last) ** 2).sum()) <= radius]
+        return ids
 
     def step(self, i, guess=None, post=None):
         """guess: initial pose override (tests feed updateInitialGuess' output); post: callable applied to the solved pose

@@ -102,7 +102,8 @@ int liorf_get_scan_ds(liorf_ctx* ctx, liorf_point* out, int capacity, int* n_ds)
 
 /* keyframe SELECTION of extractNearby (src/mapOptmization.cpp:975-1010) over the context's key poses: radius search
  * around the newest key pose, VoxelGrid(surroundingKeyframeDensity) of the poses, nearest-1 id recovery, plus every
- * keyframe younger than 10 s.  Host-side scalar code (a few hundred poses).  ids capacity = cap; *n_ids = count. */
+ * keyframe younger than 10 s, each passed through extractCloud's distance gate (:1018) on the position the reference tests (the
+ * voxel centroid for the thinned set, the real pose for the tail).  Host-side scalar code.  ids capacity = cap; *n_ids = count. */
 int liorf_extract_nearby(liorf_ctx* ctx, double time_laser_info_cur, float surrounding_keyframe_density, int* ids, int cap, int* n_ids);
 /* replaces mapOptimization::saveFrame() (src/mapOptmization.cpp:1365-1384): 1 = make a keyframe, 0 = skip */
 int liorf_save_frame(liorf_ctx* ctx, const float pose6[6], float adding_dist_threshold, float adding_angle_threshold);
@@ -211,6 +212,14 @@ typedef struct {
 int liorf_loop_closure_icp(liorf_ctx* ctx, int loop_key_cur, int loop_key_pre, int history_search_num, int loop_index, float icp_leaf, float max_corr_dist,
                            int max_iters, liorf_icp_result* out);
 int liorf_icp_get_clouds(liorf_ctx* ctx, liorf_point* source, int cap_source, liorf_point* target, int cap_target);   /* test hook */
+
+/* ---- global map ---------------------------------------------------------------------------------- */
+/* mapOptimization::publishGlobalMap (src/mapOptmization.cpp:453-502): key poses within search_radius
+ * (globalMapVisualizationSearchRadius) of the newest, thinned by a VoxelGrid of pose_density
+ * (globalMapVisualizationPoseDensity), their keyframe clouds transformed by their own poses, concatenated and VoxelGrid(leaf =
+ * globalMapVisualizationLeafSize).  search_radius <= 0 takes every keyframe and leaf <= 0 skips the last filter — the map of
+ * saveMapService (:379-432, req.resolution).  out == NULL / capacity 0 just returns the size in *n_out. */
+int liorf_build_global_map(liorf_ctx* ctx, float search_radius, float pose_density, float leaf, liorf_point* out, int capacity, int* n_out);
 
 /* ---- one LiDAR frame through the whole path ------------------------------------------------------------------- */
 /* The call sequence of ImageProjection::cloudHandler (src/imageProjection.cpp:191-204) followed by

@@ -372,6 +372,16 @@ class Context:
         _chk(self.lib.liorf_icp_get_clouds(self.h, _vp(s), C.c_int(n_source), _vp(t), C.c_int(n_target)), "liorf_icp_get_clouds")
         return s[:n_source].copy(), t[:n_target].copy()
 
+    def buildGlobalMap(self, search_radius=1000.0, pose_density=10.0, leaf=1.0):
+        """publishGlobalMap (src/mapOptmization.cpp:453-502); search_radius <= 0 and leaf <= 0 give saveMapService's map"""
+        n = C.c_int(0)
+        _chk(self.lib.liorf_build_global_map(self.h, C.c_float(search_radius), C.c_float(pose_density), C.c_float(leaf), None, C.c_int(0), C.byref(n)),
+             "liorf_build_global_map")
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _chk(self.lib.liorf_build_global_map(self.h, C.c_float(search_radius), C.c_float(pose_density), C.c_float(leaf), _vp(out), C.c_int(len(out)), C.byref(n)),
+             "liorf_build_global_map")
+        return out[:n.value].copy()
+
     def scSetSearchPath(self, mode):
         """ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tcgen05 coarse filter + exact re-rank"""
         _chk(self.lib.liorf_sc_set_search_path(self.h, C.c_int(int(mode))), "liorf_sc_set_search_path")

@@ -486,16 +486,10 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (c->kfs.empty()) return LIORF_ERR_STATE;                  // extractSurroundingKeyFrames returns early (:1048)
     int rc;
-    const Keyframe& last = c->kfs.back();
-    std::vector<int> sel; sel.reserve(n_ids);
-    for (int i = 0; i < n_ids; ++i) {
-        int id = ids[i];
-        if (id < 0 || id >= (int)c->kfs.size()) return LIORF_ERR_ARG;
-        const Keyframe& k = c->kfs[id];
-        float dx = k.pose[3] - last.pose[3], dy = k.pose[4] - last.pose[4], dz = k.pose[5] - last.pose[5];
-        float dist = std::sqrt(dx * dx + dy * dy + dz * dz);       // common_lib::pointDistance(p1,p2), lib/common_lib.cpp:33-37
-        if (dist > c->P.surroundingKeyframeSearchRadius) continue; // :1018
-        sel.push_back(id);
+    std::vector<int> sel; sel.reserve(n_ids);                    // ids verbatim: the :1018 distance gate lives in liorf_extract_nearby, which knows the
+    for (int i = 0; i < n_ids; ++i) {                            // positions extractCloud tests (voxel centroids for the thinned radius set)
+        if (ids[i] < 0 || ids[i] >= (int)c->kfs.size()) return LIORF_ERR_ARG;
+        sel.push_back(ids[i]);
     }
     // the map is a pure function of (selection, poses): identical request ⇒ keep the resident map and grid
     if (c->map_valid && sel == c->last_sel && c->last_sel_version == c->pose_version) {
@@ -1184,6 +1178,55 @@ int liorf_icp_get_clouds(liorf_ctx* c, liorf_point* source, int cap_source, lior
     if (source && cap_source > 0) CUDA_TRY(cudaMemcpy(source, c->icp_src0.p, (size_t)cap_source * sizeof(float4), cudaMemcpyDeviceToHost));
     if (target && cap_target > 0) CUDA_TRY(cudaMemcpy(target, c->icp_tgt.p, (size_t)cap_target * sizeof(float4), cudaMemcpyDeviceToHost));
     return LIORF_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ global map (§8f-4)
+// publishGlobalMap (:453-502): key poses within search_radius of the newest, thinned to pose_density voxels, nearest-1 id
+// recovery, distance gate, then the selected keyframe clouds transformed by their own poses, concatenated and VoxelGrid(leaf).
+// search_radius <= 0 selects EVERY keyframe (saveMapService, :379-432; leaf <= 0 there means "no down-sampling").
+int liorf_build_global_map(liorf_ctx* c, float search_radius, float pose_density, float leaf, liorf_point* out, int capacity, int* n_out) {
+    if (!c || !n_out || capacity < 0 || (capacity > 0 && !out)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    *n_out = 0;
+    if (c->kfs.empty()) return LIORF_OK;
+    int rc;
+    if ((rc = join_map(c))) return rc;
+    std::vector<int> ids;
+    if (search_radius > 0.f) {
+        if (!(pose_density > 0.f)) return LIORF_ERR_ARG;
+        std::vector<liorf_host::KeyPose> kp(c->kfs.size());
+        for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }
+        ids = liorf_host::extract_nearby(kp, 0.0, search_radius, pose_density, false);
+    } else { ids.resize(c->kfs.size()); for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i; }
+    std::vector<KfSel> sel; long long total = 0;
+    for (int id : ids) {
+        const Keyframe& k = c->kfs[id];
+        KfSel s; s.src_off = (int)k.off; s.count = k.count; s.dst_off = (int)total; s.pad = 0;
+        host_get_transformation(k.pose[3], k.pose[4], k.pose[5], k.pose[0], k.pose[1], k.pose[2], s.t);
+        total += k.count; sel.push_back(s);
+    }
+    if (total == 0) return LIORF_OK;
+    if (total > 0x7fffffffLL) return LIORF_ERR_ARG;
+    const int tot = (int)total, ns = (int)sel.size();
+    if ((rc = c->icp_sel.reserve(ns)) || (rc = c->icp_raw.reserve(tot)) || (rc = c->icp_tgt.reserve(tot))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->icp_sel.p, sel.data(), (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    k_transform_concat<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->kf_points.p, c->icp_sel.p, ns, tot, c->icp_raw.p);
+    const float4* result = c->icp_raw.p; int n = tot;
+    if (leaf > 0.f) {
+        if ((rc = voxel_grid_device(c->icp_raw.p, Count::of_host(tot), leaf, c->icp_tgt.p, c->d_counts + C_HOOK_NSEL, nullptr, nullptr, c->vg, c->stream))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->h_mail + 900, c->d_counts + C_HOOK_NSEL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        n = c->h_mail[900]; result = c->icp_tgt.p;
+    }
+    c->launches += 10;
+    *n_out = n;
+    if (out && n > 0) {
+        if (n > capacity) return LIORF_ERR_ARG;                      // *n_out tells the caller how much room is needed
+        CUDA_TRY(cudaMemcpyAsync(out, result, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    }
+    return check_err(c);
 }
 
 int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out* out) {

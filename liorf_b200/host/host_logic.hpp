@@ -252,7 +252,14 @@ struct IcpConvergence {
 };
 
 // extractNearby (:975-1010): ids of the keyframes whose clouds extractCloud will fuse, IN ORDER, duplicates included.
-inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double time_cur, float radius, float density) {
+// extractCloud's distance gate (:1018) is applied here, on the positions the reference tests: the VOXEL CENTROID for an entry of
+// the thinned radius set (its intensity carries the id of the nearest real key pose, which may itself lie beyond the radius),
+// the real key pose for an entry of the "younger than 10 s" tail.  include_recent = false gives publishGlobalMap's selection
+// (:467-489), which is the same radius / thinning / nearest-1 / gate sequence without the tail.
+inline float point_distance(float ax, float ay, float az, float bx, float by, float bz) {   // common_lib::pointDistance(p1, p2), lib/common_lib.cpp:33-37
+    return std::sqrt((ax - bx) * (ax - bx) + (ay - by) * (ay - by) + (az - bz) * (az - bz));
+}
+inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double time_cur, float radius, float density, bool include_recent = true) {
     std::vector<int> out;
     const int n = (int)kp.size();
     if (n == 0) return out;
@@ -295,13 +302,15 @@ inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double ti
                 float d = ex * ex; d += ey * ey; d += ez * ez;
                 if (d < bd) { bd = d; best = i; }
             }
-            out.push_back(best);
+            if (!(point_distance(cx, cy, cz, back.x, back.y, back.z) > radius)) out.push_back(best);      // :1018 on the centroid
             k = j;
         }
     }
-    for (int i = n - 1; i >= 0; --i) {                                            // :1000-1007
-        if (time_cur - kp[i].time < 10.0) out.push_back(i); else break;
-    }
+    if (include_recent)
+        for (int i = n - 1; i >= 0; --i) {                                        // :1000-1007
+            if (time_cur - kp[i].time < 10.0) { if (!(point_distance(kp[i].x, kp[i].y, kp[i].z, back.x, back.y, back.z) > radius)) out.push_back(i); }   // :1018
+            else break;
+        }
     return out;
 }
 

@@ -103,3 +103,31 @@ def test_degenerate_scene_projector(oracle):
     assert abs(pose[5]) < 0.01 and abs(pose[0]) < 1e-3 and abs(pose[1]) < 1e-3      # observable dof converge; x,y,yaw stay near the guess
     assert abs(pose[3] - 0.2) < 0.05 and abs(pose[4] + 0.1) < 0.05
     c.close()
+
+
+def test_global_map_filters(oracle, synth):
+    """§8f-4: publishGlobalMap (src/mapOptmization.cpp:453-502) and saveMapService's map (:379-432) on the resident keyframes."""
+    import liorf_b200
+    kfs, _, _, _ = _make_case(synth, oracle, synth.HDL64, 14, 0.4, 900)
+    for k, (cl, p) in enumerate(kfs):                                # spread them: 6 m apart so that the pose thinning (10 m) bites
+        p[3] = 6.0 * k
+    c = liorf_b200.Context()
+    for cl, p in kfs:
+        c.addKeyframeCloud(cl, p)
+    # saveMapService: every keyframe, own pose, VoxelGrid(resolution)
+    g = c.buildGlobalMap(search_radius=0.0, pose_density=0.0, leaf=0.8)
+    o_all = np.concatenate([oracle.transform_cloud(cl, p) for cl, p in kfs])
+    assert np.array_equal(g, oracle.voxel_grid(o_all, 0.8)[0])
+    raw = c.buildGlobalMap(search_radius=0.0, pose_density=0.0, leaf=0.0)          # req.resolution == 0: no down-sampling
+    assert np.array_equal(raw, o_all)
+    # publishGlobalMap: radius 40 m around the newest pose, poses thinned to 10 m voxels, nearest-1 id recovery
+    P = np.array([p for _, p in kfs], np.float32)[:, 3:6]
+    d = ((P[-1] - P) ** 2).astype(np.float32).sum(1)
+    near = [i for i in np.lexsort((np.arange(len(P)), d)) if d[i] < 40.0 ** 2]
+    cent, _, _ = oracle.voxel_grid(np.concatenate([P[near], np.zeros((len(near), 1), np.float32)], 1), 10.0)
+    ids = [int(np.argmin(((cc[:3] - P) ** 2).sum(1))) for cc in cent if not np.sqrt(((cc[:3] - P[-1]) ** 2).sum()) > 40.0]
+    assert 2 <= len(ids) < len(near)
+    o_sel = np.concatenate([oracle.transform_cloud(kfs[i][0], kfs[i][1]) for i in ids])
+    g2 = c.buildGlobalMap(search_radius=40.0, pose_density=10.0, leaf=1.0)
+    assert np.array_equal(g2, oracle.voxel_grid(o_sel, 1.0)[0])
+    c.close()
