@@ -358,6 +358,46 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     return res, (qd, sample)
 
 
+def bench_batched(local_rank, rank, n_seq, P, W, K):
+    """SURVEY §8d "batched figure": n_seq INDEPENDENT sequences in flight on one GPU (one context, host thread and pair of CUDA
+    streams each; ctypes releases the GIL inside the library).  One sequence leaves the GPU idle while the host synchronises on
+    the pose and between dependent launches; several fill those gaps.  Wall-clock aggregate, device-resident inputs."""
+    import threading
+    import torch
+    n_frames = P + W + K
+    seqs = [Sequence(n_frames, 100 + 10 * rank + s) for s in range(n_seq)]
+    for q in seqs:
+        for i in range(n_frames):
+            q.frame(i)
+    pipes = [GpuPipeline(q, local_rank) for q in seqs]
+    for p in pipes:
+        p.stage(range(n_frames))
+        for i in range(P + W):
+            p.step(i, "dev")
+    torch.cuda.synchronize()
+    start = threading.Barrier(n_seq + 1)
+    done = [0.0] * n_seq
+
+    def run(k):
+        start.wait()
+        for i in range(P + W, P + W + K):
+            pipes[k].step(i, "dev")
+        pipes[k].ctx.sync()
+        done[k] = time.perf_counter()
+    th = [threading.Thread(target=run, args=(k,)) for k in range(n_seq)]
+    for t in th:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for t in th:
+        t.join()
+    wall = max(done) - t0
+    for p in pipes:
+        p.ctx.close()
+    return dict(sequences_in_flight=n_seq, frames=n_seq * K, ms_per_frame=wall * 1e3 / (n_seq * K), frames_per_s=n_seq * K / wall,
+                timing="host wall clock around all threads (each ends with a stream synchronise)")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -368,6 +408,7 @@ def main():
     ap.add_argument("--sc-k", type=int, default=100000)
     ap.add_argument("--sc-q", type=int, default=4096)
     ap.add_argument("--sc-q-large", type=int, default=32768, help="second, larger query batch for the sharded search (0 = skip)")
+    ap.add_argument("--batched", type=int, default=2, help="independent sequences in flight on one GPU for the batched figure (0 = skip)")
     ap.add_argument("--no-sc", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=12, help="bounded CPU-baseline sample (frames)")
     args = ap.parse_args()
@@ -477,6 +518,11 @@ def main():
                         map_build_ms=float(np.median(single[:, 0])), solver_kernel_ms=s2m_ms,
                         knn_queries_per_s=30 * cnt["n_ds"] / (s2m_ms * 1e-3), target_ms=1.0)
 
+    # ---- batched figure: several independent sequences in flight on this GPU ----
+    batched = None
+    if args.batched > 1:
+        batched = bench_batched(local_rank, rank, args.batched, min(P, 60), W, min(K, 60))
+
     # ---- roofline of the dominant kernel of the sequence step ----
     peaks, peak_src = load_peaks()
     dv = results["dev"]
@@ -534,7 +580,7 @@ def main():
                     e2e=dict(value=results["e2e"]["ms"] / tot_frames, unit="ms/frame", h2d_bytes_per_step=results["e2e"]["h2d"], d2h_bytes_per_step=24 + 64 + 16,
                              wall_ms_per_step=results["e2e"]["wall_ms"] / K),
                     gpu_launches=dv["launches"], knn_queries_per_s=st["knn_queries"] / (tm["scan2map"][0] * 1e-3) if tm["scan2map"][0] > 0 else None,
-                    single_frame=single_frame, sc=sc, roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+                    single_frame=single_frame, batched=batched, sc=sc, roofline=roofline, cpu_baseline=cpu, clocks=clocks,
                     kernel_ms_per_frame={k: tm[k][0] / K for k in tm})
         print(json.dumps(line))
     if world > 1:
@@ -580,6 +626,8 @@ def run_reference(args, W, K):
     P = min(args.preroll, 60)
     steps = min(K, 20)
     seq = Sequence(P + W + steps, 0)
+    for i in range(P + W + steps):                               # synthesise the scans up front: generation is not part of the path
+        seq.frame(i)
     cpu = CpuPipeline(seq)
     for i in range(P + W):
         cpu.step(i)
