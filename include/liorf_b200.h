@@ -257,6 +257,7 @@ int liorf_get_timing(liorf_ctx* ctx, double ms[8], long long calls[8]);
 long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels launched by this context so far */
 int liorf_get_last_counts(liorf_ctx* ctx, int* n_scan, int* n_ds, int* m_ds, int* iters);   /* as of the last liorf_get_pose */
 int liorf_debug_force_large_voxelgrid(liorf_ctx* ctx, int on);   /* tests: multi-kernel VoxelGrid path on small clouds too */
+int liorf_debug_s2m_disable_cache(liorf_ctx* ctx, int on);        /* tests: full 27-cell search + plane refit every iteration */
 int liorf_debug_s2m_clocks(liorf_ctx* ctx, int enable, long long* out /* 64*8, nullable */);   /* solver phase clocks (debug) */
 int liorf_get_keyframe(liorf_ctx* ctx, int id, liorf_point* out, int capacity, int* n, float pose6[6], double* time);
 

@@ -306,6 +306,9 @@ class Context:
         _chk(self.lib.liorf_process_frame(self.h, C.byref(fi), C.byref(fo)), "liorf_process_frame")
         return fo
 
+    def disableSolverCache(self, on=True):
+        _chk(self.lib.liorf_debug_s2m_disable_cache(self.h, C.c_int(int(on))), "liorf_debug_s2m_disable_cache")
+
     def forceLargeVoxelGrid(self, on=True):
         _chk(self.lib.liorf_debug_force_large_voxelgrid(self.h, C.c_int(int(on))), "liorf_debug_force_large_voxelgrid")
 

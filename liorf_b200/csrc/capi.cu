@@ -68,7 +68,7 @@ struct liorf_ctx {
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr;
     DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0;
-    int s2m_grid = 0;
+    int s2m_grid = 0; bool s2m_no_cache = false;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
     float* d_lm_out = nullptr;      // AtA[36] AtB[6] X[6]
@@ -654,7 +654,7 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     a.epoch_base = (++c->s2m_launch_seq) * 64u;
     a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
-    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.dbg = c->d_dbg;
+    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.dbg = c->d_dbg;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2MP_BLOCK), args, 0, c->stream));
@@ -1348,6 +1348,12 @@ int liorf_get_timing(liorf_ctx* c, double ms[8], long long calls[8]) {
 }
 long long liorf_get_launch_count(liorf_ctx* c) { return c ? c->launches : -1; }
 // debug: phase clocks of the persistent solver (CTA 0): out[iter*8 + {0 start,1 loop done,2 block reduced,3 grid synced,4 summed,5 solved}]
+/* tests: 1 = the solver never reuses its per-query candidate lists / plane fits (reference-style full search every iteration) */
+int liorf_debug_s2m_disable_cache(liorf_ctx* c, int on) {
+    if (!c) return LIORF_ERR_ARG;
+    c->s2m_no_cache = on != 0;
+    return LIORF_OK;
+}
 int liorf_debug_s2m_clocks(liorf_ctx* c, int enable, long long* out /*64*8 or null*/) {
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));

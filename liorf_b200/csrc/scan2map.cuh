@@ -413,6 +413,7 @@ struct S2MArgs {
     double* partial;                 // [2][gridDim.x][NPROD]
     S2MTrace* trace;
     int max_iters; int force_all;
+    int no_cache;                    // tests: 1 = never reuse candidate lists / planes (every iteration searches the 27 cells and refits)
     long long* dbg;                  // optional [S2M_MAX_ITERS][8] clock64 phase stamps of CTA 0 (nullptr = off)
     QueryCache* qcache;              // [n_scan bound]
     float4* cand;                    // [n_scan bound][CAND_CAP]
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                 // the list holds the points within 1 + m of q0 THAT LIE IN q0's 27 cells; the unit ball around pointSel stays
                 // inside that block of cells only while pointSel is in q0's own cell
                 const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
-                const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell;
+                const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
                 Top5 mine; top5_init(mine);
                 int list_cnt;                                       // >= 0: results index the candidate list; -2: they index gmap... see below
                 if (use_cache) {
@@ -617,7 +618,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                 const bool have5 = active && nn.pos[4] != -1 && (double)nn.d[4] < 1.0;          // :1097
                 bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (have5) {
-                    const bool same = iter > 0 && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
+                    const bool same = iter > 0 && !a.no_cache && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
                                       __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
                     float pa, pb, pc, pd; bool planeValid;
                     if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }

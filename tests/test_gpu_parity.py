@@ -247,3 +247,33 @@ def test_scan2map_deterministic(ctx, oracle, kitti_case):
     ctx.setLMState(False, np.zeros(36, np.float32))
     b, _ = ctx.scan2MapOptimization(kitti_case["init"], 30, force_all_iters=True)
     assert np.array_equal(a, b)                                   # fixed reduction tree, no float atomics
+
+
+# ---------------------------------------------------------------------------------------------- solver caches are exact
+@pytest.mark.parametrize("seed", range(6))
+def test_solver_caches_do_not_change_results(kitti_case, seed):
+    """property test (no oracle needed): the persistent solver with its candidate-list / plane caches must produce the SAME
+    trace, bit for bit, as with the caches disabled (full 27-cell search and refit every iteration) — for start poses that
+    push the scan across voxel-cell boundaries between iterations (large perturbations, 30 forced iterations)."""
+    import liorf_b200
+    rng = np.random.default_rng(100 + seed)
+    c = liorf_b200.Context()
+    for cl, p in kitti_case["keyframes"]:
+        c.addKeyframeCloud(cl, p)
+    c.extractSurroundingKeyFrames(list(range(len(kitti_case["keyframes"]))))
+    scan = kitti_case["scan"]
+    if seed % 2:                                                   # a small scan as in the sequence workload (many idle query slots)
+        scan = scan[::9]
+    c.setCurrentScan(scan)
+    c.downsampleCurrentScan(want_output=False)
+    init = (kitti_case["truth"] + rng.normal(scale=[0.01, 0.01, 0.03, 0.6, 0.6, 0.1])).astype(np.float32)
+    traces = []
+    for no_cache in (False, True):
+        c.disableSolverCache(no_cache)
+        c.setLMState(0, np.eye(6, dtype=np.float32))
+        pose, tr = c.scan2MapOptimization(init, 30, force_all_iters=True)
+        traces.append((tr.poses().copy(), tr.nsels().copy(), pose.copy()))
+    assert np.array_equal(traces[0][1], traces[1][1]), (traces[0][1], traces[1][1])          # selected-row counts per iteration
+    assert np.array_equal(traces[0][0].view(np.uint32), traces[1][0].view(np.uint32))        # every iteration's pose, bit for bit
+    assert np.array_equal(traces[0][2], traces[1][2])
+    c.close()
