@@ -153,3 +153,37 @@ def test_sharded_packed_protocol_equals_unsharded(oracle, synth):
         assert np.array_equal(dd.cpu().numpy(), r_dist, equal_nan=True)
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("case", ["random_walk", "all_identical", "huge_heights", "two_clusters"])
+def test_tensor_filter_adversarial_databases(oracle, synth, case):
+    """key distributions chosen to stress the filter's completeness argument: a drive-like random walk (neighbouring keys nearly
+    equal → many near-ties), a database of identical keys (every distance ties → overflow → brute-force fallback), heights of
+    ~1000 m (large norms → wide eps band) and two far-apart clusters (the database mean is far from every key).  In every case
+    the tensor path must return the brute-force kernel's ids and distances bit for bit."""
+    import liorf_b200
+    rng = np.random.default_rng(77)
+    K, Q = 7000, 200
+    base = synth.sc_descriptors(K, seed=91)
+    if case == "random_walk":
+        db = np.empty_like(base); cur = base[0].copy()
+        for i in range(K):
+            cur = np.clip(cur + rng.normal(scale=0.02, size=1200) * (cur > 0), 0, 12); db[i] = cur
+        q = db[rng.integers(0, K, Q)] + rng.normal(scale=0.01, size=(Q, 1200)) * (db[0] > 0)
+    elif case == "all_identical":
+        db = np.repeat(base[:1], K, 0); q = np.concatenate([base[:1], base[1:Q]], 0)
+    elif case == "huge_heights":
+        db = base * 90.0; q = db[rng.integers(0, K, Q)] + rng.normal(scale=0.5, size=(Q, 1200))
+    else:
+        db = base.copy(); db[K // 2:] += 500.0; q = np.concatenate([db[:Q // 2] + 0.01, db[K // 2:K // 2 + Q // 2] - 0.01], 0)
+    ctx = liorf_b200.Context()
+    ctx.scAddDescriptors(db)
+    qkeys = _keys(oracle, q)
+    ctx.scSetSearchPath(1); bd, bi = _knn_dev(ctx, qkeys)
+    ctx.scSetSearchPath(2); td, ti = _knn_dev(ctx, qkeys)
+    st = ctx.scTensorStats()
+    print(case, "candidate chunks/query %.1f overflow %d" % (st["candidates"] / Q, st["overflow"]))
+    assert np.array_equal(bi, ti) and np.array_equal(bd.view(np.uint32), td.view(np.uint32))
+    if case == "all_identical":
+        assert st["overflow"] >= 1 and list(ti[0]) == [0, 1, 2]
+    ctx.close()
