@@ -239,6 +239,13 @@ typedef struct {
     /* use_cloud_info != 0: the initial guess is produced by updateInitialGuess (:899-958) from the context's previous pose and
      * these cloud_info fields (initial_guess[] is ignored), and transformUpdate (:1323-1353) runs in full after the solve */
     int use_cloud_info; liorf_cloud_info_guess cloud_info; int imu_type; int use_imu_heading_initialization; float imu_rpy_weight;
+    /* optional look-ahead: the liorf_frame_in of the FOLLOWING frame (NULL = none).  Its cloudHandler part (projectPointCloud) and
+     * downsampleCurrentScan are enqueued on a second stream as soon as this frame's solver has been launched and run while the
+     * solver iterates — the reference runs imageProjection and mapOptimization as two concurrent nodes with a queue in between
+     * (src/imageProjection.cpp:191-204 publishes, src/mapOptmization.cpp:236 consumes).  Only pts / n / pts_on_device / time_scan_cur /
+     * imu_* / deskew_enabled / frame_index of `next` are read; its buffers must stay valid until the call that processes that frame
+     * (same frame_index, pts, n) returns.  Results are bit-identical with and without look-ahead. */
+    const void* next;
 } liorf_frame_in;
 typedef struct {
     float pose[6];
@@ -247,12 +254,17 @@ typedef struct {
     int loop_checked, loop_id; float loop_yaw;
 } liorf_frame_out;
 int liorf_process_frame(liorf_ctx* ctx, const liorf_frame_in* in, liorf_frame_out* out);
+/* ImageProjection::cloudHandler (src/imageProjection.cpp:191-204) for a frame that a later liorf_process_frame call (same
+ * frame_index, pts, n) will consume: asynchronous, second stream, second set of scan buffers.  Primes the pipeline for frame 0;
+ * afterwards liorf_frame_in.next does the same from inside liorf_process_frame. */
+int liorf_cloud_handler_async(liorf_ctx* ctx, const liorf_frame_in* frame);
 
 /* ---- measurement / introspection (bench.py) ------------------------------------------------------------------- */
 /* per-section CUDA-event timing on the context's stream: sections 0 deskew, 1 downsample, 2 map build (transform +
  * VoxelGrid), 3 grid build, 4 scan2map solver, 5 ScanContext make, 6 ScanContext ring-key search, 7 the tcgen05 GEMM
  * kernel inside 6 */
 int liorf_enable_timing(liorf_ctx* ctx, int on);
+int liorf_enable_timing_mask(liorf_ctx* ctx, unsigned mask);         /* only the sections whose bit is set record events */
 int liorf_get_timing(liorf_ctx* ctx, double ms[8], long long calls[8]);
 long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels launched by this context so far */
 int liorf_get_last_counts(liorf_ctx* ctx, int* n_scan, int* n_ds, int* m_ds, int* iters);   /* as of the last liorf_get_pose */

@@ -59,7 +59,7 @@ class FrameIn(C.Structure):
                 ("surrounding_keyframe_density", C.c_float), ("adding_dist_threshold", C.c_float), ("adding_angle_threshold", C.c_float),
                 ("rotation_tollerance", C.c_float), ("z_tollerance", C.c_float), ("max_iters", C.c_int), ("loop_every", C.c_int), ("frame_index", C.c_int),
                 ("use_cloud_info", C.c_int), ("cloud_info", CloudInfoGuess), ("imu_type", C.c_int), ("use_imu_heading_initialization", C.c_int),
-                ("imu_rpy_weight", C.c_float)]
+                ("imu_rpy_weight", C.c_float), ("next", C.c_void_p)]
 
 
 class FrameOut(C.Structure):
@@ -286,25 +286,56 @@ class Context:
         P = np.ascontiguousarray(matP, np.float32).reshape(36)
         _chk(self.lib.liorf_set_lm_state(self.h, C.c_int(int(deg)), _vp(P)), "liorf_set_lm_state")
 
-    def processFrame(self, pts_ptr, n, on_device, time_scan_cur, imu_time, imu_rot_xyz, imu_pointer_cur, deskew_enabled, initial_guess,
-                     density=2.0, dist_thr=1.0, ang_thr=0.2, rot_tol=1000.0, z_tol=1000.0, max_iters=30, loop_every=0, frame_index=0,
-                     cloud_info=None, imu_type=0, use_imu_heading=True, imu_rpy_weight=0.01):
-        """one frame through cloudHandler + laserCloudInfoHandler (liorf_process_frame).  imu_rot_xyz: three contiguous float64 arrays."""
+    @staticmethod
+    def frameIn(pts_ptr, n, on_device, time_scan_cur, imu_time, imu_rot_xyz, imu_pointer_cur, deskew_enabled, initial_guess=None,
+                density=2.0, dist_thr=1.0, ang_thr=0.2, rot_tol=1000.0, z_tol=1000.0, max_iters=30, loop_every=0, frame_index=0,
+                cloud_info=None, imu_type=0, use_imu_heading=True, imu_rpy_weight=0.01):
+        """a liorf_frame_in.  imu_rot_xyz: three contiguous float64 arrays (kept alive by the returned object)."""
         fi = FrameIn()
         fi.pts = pts_ptr; fi.n = n; fi.pts_on_device = int(on_device); fi.time_scan_cur = time_scan_cur
         fi.imu_time = imu_time.ctypes.data; fi.imu_rot_x = imu_rot_xyz[0].ctypes.data; fi.imu_rot_y = imu_rot_xyz[1].ctypes.data; fi.imu_rot_z = imu_rot_xyz[2].ctypes.data
+        fi._keep = (imu_time, imu_rot_xyz)
         fi.imu_pointer_cur = imu_pointer_cur; fi.deskew_enabled = int(deskew_enabled)
         if cloud_info is not None:                              # initial guess by updateInitialGuess from these cloud_info fields
             fi.use_cloud_info = 1; fi.cloud_info = cloud_info; fi.imu_type = imu_type; fi.use_imu_heading_initialization = int(use_imu_heading)
             fi.imu_rpy_weight = imu_rpy_weight
-        else:
+        elif initial_guess is not None:
             for k in range(6):
                 fi.initial_guess[k] = float(initial_guess[k])
         fi.surrounding_keyframe_density = density; fi.adding_dist_threshold = dist_thr; fi.adding_angle_threshold = ang_thr
         fi.rotation_tollerance = rot_tol; fi.z_tollerance = z_tol; fi.max_iters = max_iters; fi.loop_every = loop_every; fi.frame_index = frame_index
+        return fi
+
+    def processFrame(self, pts_ptr, n, on_device, time_scan_cur, imu_time, imu_rot_xyz, imu_pointer_cur, deskew_enabled, initial_guess,
+                     density=2.0, dist_thr=1.0, ang_thr=0.2, rot_tol=1000.0, z_tol=1000.0, max_iters=30, loop_every=0, frame_index=0,
+                     cloud_info=None, imu_type=0, use_imu_heading=True, imu_rpy_weight=0.01, next_frame=None):
+        """one frame through cloudHandler + laserCloudInfoHandler (liorf_process_frame).  imu_rot_xyz: three contiguous float64 arrays.
+        next_frame: a frameIn(...) of the FOLLOWING frame — its deskew + downsample overlap this frame's solve (liorf_frame_in.next)."""
+        fi = self.frameIn(pts_ptr, n, on_device, time_scan_cur, imu_time, imu_rot_xyz, imu_pointer_cur, deskew_enabled, initial_guess, density, dist_thr,
+                          ang_thr, rot_tol, z_tol, max_iters, loop_every, frame_index, cloud_info, imu_type, use_imu_heading, imu_rpy_weight)
+        if next_frame is not None:
+            fi.next = C.addressof(next_frame)
+            self._next_keep = next_frame                        # stays referenced until the call that consumes it
         fo = FrameOut()
         _chk(self.lib.liorf_process_frame(self.h, C.byref(fi), C.byref(fo)), "liorf_process_frame")
         return fo
+
+    def processFrameIn(self, fi, guess=None, next_frame=None, fo=None):
+        """liorf_process_frame on a prepared frameIn(...) (inputs staged ahead of time: nothing is rebuilt per frame)."""
+        if guess is not None:
+            g = fi.initial_guess
+            g[0], g[1], g[2], g[3], g[4], g[5] = guess
+        fi.next = C.addressof(next_frame) if next_frame is not None else None
+        self._next_keep = next_frame
+        if fo is None:
+            fo = FrameOut()
+        _chk(self.lib.liorf_process_frame(self.h, C.byref(fi), C.byref(fo)), "liorf_process_frame")
+        return fo
+
+    def cloudHandlerAsync(self, frame_in):
+        """primes the pipeline: cloudHandler + downsample of a frame a later processFrame call (same frame_index / pts / n) consumes"""
+        self._next_keep = frame_in
+        _chk(self.lib.liorf_cloud_handler_async(self.h, C.byref(frame_in)), "liorf_cloud_handler_async")
 
     def disableSolverCache(self, on=True):
         _chk(self.lib.liorf_debug_s2m_disable_cache(self.h, C.c_int(int(on))), "liorf_debug_s2m_disable_cache")
@@ -313,8 +344,14 @@ class Context:
         _chk(self.lib.liorf_debug_force_large_voxelgrid(self.h, C.c_int(int(on))), "liorf_debug_force_large_voxelgrid")
 
     # ---- measurement helpers ----
-    def enableTiming(self, on=True):
-        _chk(self.lib.liorf_enable_timing(self.h, C.c_int(int(on))), "liorf_enable_timing")
+    def enableTiming(self, on=True, sections=None):
+        """sections: iterable of section names to time (None = all)"""
+        if sections is None:
+            _chk(self.lib.liorf_enable_timing(self.h, C.c_int(int(on))), "liorf_enable_timing")
+        else:
+            names = ["deskew", "downsample", "map_build", "grid_build", "scan2map", "sc_make", "sc_search", "sc_gemm"]
+            mask = sum(1 << names.index(n) for n in sections) if on else 0
+            _chk(self.lib.liorf_enable_timing_mask(self.h, C.c_uint(mask)), "liorf_enable_timing_mask")
 
     def getTiming(self):
         ms = (C.c_double * 8)(); calls = (C.c_longlong * 8)()

@@ -32,8 +32,9 @@ struct Keyframe { size_t off; int count; float pose[6]; double time; };
 // optional per-section CUDA-event timing on the context's stream (bench.py's live roofline numbers)
 enum { SEC_DESKEW = 0, SEC_DOWNSAMPLE, SEC_MAP_BUILD, SEC_GRID_BUILD, SEC_SCAN2MAP, SEC_SC_MAKE, SEC_SC_SEARCH, SEC_SC_GEMM, SEC_COUNT = 8 };
 constexpr int PROF_RING = 64;
+constexpr int S2M_SPARE_SMS = 16;      // SMs the persistent solver leaves to the concurrent front end of the next frame
 struct Profiler {
-    bool enabled = false;
+    bool enabled = false; unsigned mask = 0xffu;        // mask: sections that record events (bit = section id)
     cudaEvent_t ev[PROF_RING][2]; int sec[PROF_RING]; int pending = 0; bool created = false;
     double ms[SEC_COUNT] = {0}; long long calls[SEC_COUNT] = {0};
 };
@@ -43,7 +44,9 @@ struct liorf_ctx {
     cudaStream_t stream = nullptr;
     int num_sms = kNumSMs;
     // device scalars
-    int* d_counts = nullptr;        // C_COUNT ints
+    int* d_counts = nullptr;        // C_COUNT ints of the CURRENT front set (N_SCAN, N_DS, FIRST_KEPT, hook counts)
+    int* d_counts_base = nullptr;   // [front set 0 | shared | front set 1], C_COUNT ints each: either set is contiguous with the shared block
+    int* d_shared = nullptr;        // counts that do not belong to a front set (C_M_DS)
     int* d_misc = nullptr;          // tickets / counters / error flag (zero-initialised)
     int* d_err = nullptr;
     int* h_mail = nullptr;          // pinned mailbox (128 KB: scalars/trace in the lower half, IMU table staging in the upper)
@@ -67,7 +70,7 @@ struct liorf_ctx {
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr;
-    DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0;
+    DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false;
     int s2m_grid = 0; bool s2m_no_cache = false;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
@@ -93,21 +96,53 @@ struct liorf_ctx {
     double host_us[6] = {0, 0, 0, 0, 0, 0}; long long host_frames = 0; bool host_timing = false;   // LIORF_HOST_TIMING=1
     cudaEvent_t tl_ev[8] = {nullptr}; double tl_ms[8] = {0}; // debug GPU timeline stamps of process_frame
     long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
+    // ---- pipelined front end (cloudHandler of frame i+1 overlaps laserCloudInfoHandler of frame i) ----
+    // Everything projectPointCloud + downsampleCurrentScan read or write for ONE frame lives in a "front set"; the context
+    // holds two and swaps them, so the next frame's set is filled on stream_pre while the solver works on the current one.
+    struct FrontSet {
+        DevBuf<float4> scan, scan_ds; DeskewWork dk; VoxelGridWork vg;
+        int* d_counts = nullptr; int n_scan_bound = 0, h_n_scan = -1, h_n_ds = -1;
+    } alt;
+    cudaStream_t stream_pre = nullptr;
+    cudaEvent_t ev_pre_done = nullptr, ev_frame_start = nullptr;
+    bool pre_valid = false, frame_start_recorded = false; int pre_index = 0, pre_n = 0; const void* pre_pts = nullptr;
 };
+
+// swaps the current front set with the alternate one (pointer swaps only)
+static void front_swap(liorf_ctx* c) {
+    std::swap(c->scan, c->alt.scan); std::swap(c->scan_ds, c->alt.scan_ds); std::swap(c->dk, c->alt.dk); std::swap(c->vg, c->alt.vg);
+    std::swap(c->d_counts, c->alt.d_counts); std::swap(c->n_scan_bound, c->alt.n_scan_bound);
+    std::swap(c->h_n_scan, c->alt.h_n_scan); std::swap(c->h_n_ds, c->alt.h_n_ds);
+}
+// D2H of the current set's counts together with the shared block: ONE 2 x C_COUNT copy into h_mail[0 : 2 C_COUNT)
+static cudaError_t mail_counts(liorf_ctx* c) {
+    const int* src = c->d_counts < c->d_shared ? c->d_counts : c->d_shared;
+    return cudaMemcpyAsync(c->h_mail, src, 2 * C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+}
+static void take_counts(liorf_ctx* c) {
+    const int so = c->d_counts < c->d_shared ? 0 : C_COUNT, sh = C_COUNT - so;
+    c->h_n_scan = c->h_mail[so + C_N_SCAN]; c->h_n_ds = c->h_mail[so + C_N_DS]; c->h_m_ds = c->h_mail[sh + C_M_DS];
+}
 
 static void prof_flush(liorf_ctx* c) {           // call only when the stream is idle (after a sync)
     Profiler& p = c->prof;
+    int keep = 0;
     for (int i = 0; i < p.pending; ++i) {
         float ms = 0.f;
+        if (cudaEventQuery(p.ev[i][1]) == cudaErrorNotReady && keep < PROF_RING / 2) {      // still running on another stream (pipelined front end)
+            std::swap(p.ev[i][0], p.ev[keep][0]); std::swap(p.ev[i][1], p.ev[keep][1]); std::swap(p.sec[i], p.sec[keep]); ++keep;
+            continue;
+        }
         if (cudaEventElapsedTime(&ms, p.ev[i][0], p.ev[i][1]) == cudaSuccess) { p.ms[p.sec[i]] += ms; p.calls[p.sec[i]]++; }
     }
-    p.pending = 0;
+    (void)cudaGetLastError();
+    p.pending = keep;
 }
 struct ProfScope {
     liorf_ctx* c; int slot = -1; cudaStream_t st;
     ProfScope(liorf_ctx* c_, int sec, cudaStream_t st_ = nullptr) : c(c_), st(st_ ? st_ : c_->stream) {
         Profiler& p = c->prof;
-        if (!p.enabled) return;
+        if (!p.enabled || !((p.mask >> sec) & 1u)) return;
         if (!p.created) { for (int i = 0; i < PROF_RING; ++i) { cudaEventCreate(&p.ev[i][0]); cudaEventCreate(&p.ev[i][1]); } p.created = true; }
         if (p.pending == PROF_RING) { cudaStreamSynchronize(c->stream); if (c->stream_map) cudaStreamSynchronize(c->stream_map); prof_flush(c); }
         slot = p.pending++; p.sec[slot] = sec;
@@ -163,10 +198,10 @@ static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-
 
 static int read_counts(liorf_ctx* c) {
     { int rcj = join_map(c); if (rcj) return rcj; }
-    CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(mail_counts(c));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     prof_flush(c);
-    c->h_n_scan = c->h_mail[C_N_SCAN]; c->h_n_ds = c->h_mail[C_N_DS]; c->h_m_ds = c->h_mail[C_M_DS];
+    take_counts(c);
     return LIORF_OK;
 }
 
@@ -219,8 +254,9 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     if (std::getenv("LIORF_NO_PRIO")) prio_lo = prio_hi = 0;
     CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
-    CUDA_TRY(cudaMalloc(&c->d_counts, C_COUNT * sizeof(int)));
-    CUDA_TRY(cudaMemset(c->d_counts, 0, C_COUNT * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_counts_base, 3 * C_COUNT * sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_counts_base, 0, 3 * C_COUNT * sizeof(int)));
+    c->d_counts = c->d_counts_base; c->d_shared = c->d_counts_base + C_COUNT; c->alt.d_counts = c->d_counts_base + 2 * C_COUNT;
     CUDA_TRY(cudaMalloc(&c->d_misc, 64 * sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_misc, 0, 64 * sizeof(int)));
     c->d_err = c->d_misc + 0;
@@ -242,6 +278,17 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     c->icp_grid.scan.ticket = c->d_misc + 13; c->icp_grid.scan.err_flag = c->d_err;
     CUDA_TRY(cudaMalloc(&c->dk.start_inv, 12 * sizeof(float)));
     c->dk.first_kept = c->d_counts + C_FIRST_KEPT;
+    // the alternate front set: its own look-back tickets, VoxelGrid meta and deskew scalars
+    c->alt.vg.mm_counter = c->d_misc + 20;
+    c->alt.vg.sort.ticket = c->d_misc + 21; c->alt.vg.sort.err_flag = c->d_err;
+    c->alt.vg.scan.ticket = c->d_misc + 22; c->alt.vg.scan.err_flag = c->d_err;
+    c->alt.dk.scan.ticket = c->d_misc + 23; c->alt.dk.scan.err_flag = c->d_err;
+    CUDA_TRY(cudaMalloc(&c->alt.vg.meta, sizeof(VoxMeta)));
+    CUDA_TRY(cudaMalloc(&c->alt.dk.start_inv, 12 * sizeof(float)));
+    c->alt.dk.first_kept = c->alt.d_counts + C_FIRST_KEPT;
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_pre, cudaStreamNonBlocking, prio_lo));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pre_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_frame_start, cudaEventDisableTiming));
     CUDA_TRY(cudaHostAlloc(&c->h_mail, 65536 + 2 * 65536, cudaHostAllocDefault));
     CUDA_TRY(cudaMalloc(&c->d_tf6, 6 * sizeof(float)));
     CUDA_TRY(cudaMemset(c->d_tf6, 0, 6 * sizeof(float)));
@@ -253,8 +300,19 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan2map_persistent, S2MP_BLOCK, 0));
     if (occ < 1) { fprintf(stderr, "[liorf_b200] persistent kernel does not fit\n"); return LIORF_ERR_CUDA; }
-    c->s2m_grid = c->num_sms;                                   // one persistent CTA per SM
-    CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->s2m_grid * NPROD * sizeof(double)));
+    // One persistent CTA per SM, on all but S2M_SPARE_SMS of them.  The solver's CTA owns its SM outright (512 threads x 128
+    // registers = the whole register file), so the SMs it leaves free are where the NEXT frame's cloudHandler + downsample
+    // (stream_pre) run while it iterates.  The solve is latency-bound (one round of <= 128 queries per CTA up to ~17k points), so
+    // the narrower grid costs nothing at the KITTI sizes; the grid is the same with and without look-ahead, which keeps the
+    // CTA-ordered fp64 partial sums — and therefore the results — bit-identical between the two.
+    {
+        int spare = S2M_SPARE_SMS;
+        if (const char* e = std::getenv("LIORF_SOLVER_SPARE_SMS")) spare = std::atoi(e);
+        if (spare < 0) spare = 0;
+        c->s2m_grid = c->num_sms - spare; if (c->s2m_grid < 1) c->s2m_grid = c->num_sms;
+    }
+    CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->num_sms * NPROD * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->d_mail, sizeof(S2MMail)));
     CUDA_TRY(cudaMalloc(&c->d_result, 2 * sizeof(S2MResult)));
     CUDA_TRY(cudaMemset(c->d_result, 0, 2 * sizeof(S2MResult)));
     CUDA_TRY(cudaMalloc(&c->d_bins, SC_DESC * sizeof(unsigned)));
@@ -281,6 +339,17 @@ void liorf_destroy(liorf_ctx* c) {
     }
     cudaSetDevice(c->P.device);
     cudaStreamSynchronize(c->stream);
+    if (c->stream_pre) cudaStreamSynchronize(c->stream_pre);
+    {   // the alternate front set (the current one is released below)
+        liorf_ctx::FrontSet& a = c->alt;
+        a.scan.release(); a.scan_ds.release(); a.dk.raw.release(); a.dk.imu.release(); a.dk.kept.release(); a.dk.scan.status.release();
+        a.vg.partial.release(); a.vg.keys.release(); a.vg.seg_start.release(); a.vg.sort.keys_alt.release(); a.vg.sort.vals_a.release();
+        a.vg.sort.vals_b.release(); a.vg.sort.hist.release(); a.vg.sort.status.release(); a.vg.scan.status.release();
+        cudaFree(a.vg.meta); cudaFree(a.dk.start_inv);
+    }
+    if (c->stream_pre) cudaStreamDestroy(c->stream_pre);
+    if (c->ev_pre_done) cudaEventDestroy(c->ev_pre_done);
+    if (c->ev_frame_start) cudaEventDestroy(c->ev_frame_start);
     DevBuf<float4>* f4[] = {&c->scan, &c->scan_ds, &c->map_raw, &c->map_ds, &c->kf_points, &c->h_coeff, &c->h_sel_pts, &c->h_ori_c, &c->h_coeff_c, &c->grid.sorted};
     for (auto b : f4) b->release();
     c->membership.release(); c->out_keys.release(); c->h_flag.release(); c->h_idx.release(); c->h_d2.release(); c->h_plane.release();
@@ -293,7 +362,7 @@ void liorf_destroy(liorf_ctx* c) {
     c->vg.sort.keys_alt.release(); c->vg.sort.vals_a.release(); c->vg.sort.vals_b.release(); c->vg.sort.hist.release(); c->vg.sort.status.release();
     c->vg.scan.status.release(); c->grid.scan.status.release(); c->dk.scan.status.release(); c->combine_scan.status.release();
     c->grid.counts.release(); c->grid.cell_start.release();
-    c->dk.raw.release(); c->dk.imu.release();
+    c->dk.raw.release(); c->dk.imu.release(); c->dk.kept.release();
     c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); c->sc_part_d.release(); c->sc_part_i.release();
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
@@ -302,8 +371,8 @@ void liorf_destroy(liorf_ctx* c) {
     c->icp_nn_d2.release(); c->icp_grid.counts.release(); c->icp_grid.cell_start.release(); c->icp_grid.sorted.release(); c->icp_grid.scan.status.release();
     if (c->icp_out) cudaFree(c->icp_out);
     c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
-    cudaFree(c->d_counts); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
-    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); c->qcache.release(); c->cand.release();
+    cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
+    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->h_sel) cudaFreeHost(c->h_sel);
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (c->stage_ev[a][b]) cudaEventDestroy(c->stage_ev[a][b]);
@@ -528,13 +597,13 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     {
         ProfScope ps(c, SEC_MAP_BUILD, ms); c->launches += 10;
         if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
-        if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_counts + C_M_DS, nullptr,
+        if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_shared + C_M_DS, nullptr,
                                     nullptr, c->vg_map, ms))) return rc;
     }
     c->m_bound = tot; c->h_m_ds = -1;
     {
         ProfScope ps(c, SEC_GRID_BUILD, ms); c->launches += 3;
-        if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_counts + C_M_DS, tot), c->grid, ms))) return rc;
+        if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_shared + C_M_DS, tot), c->grid, ms))) return rc;
     }
     CUDA_TRY(cudaEventRecord(c->ev_map, ms));
     c->map_pending = true;
@@ -612,7 +681,7 @@ int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
     if ((rc = c->map_ds.reserve(m > 0 ? m : 1))) return rc;
     if (m > 0) CUDA_TRY(cudaMemcpyAsync(c->map_ds.p, map_ds, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     c->h_mail[101] = m;
-    CUDA_TRY(cudaMemcpyAsync(c->d_counts + C_M_DS, &c->h_mail[101], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_shared + C_M_DS, &c->h_mail[101], sizeof(int), cudaMemcpyHostToDevice, c->stream));
     c->m_bound = m; c->h_m_ds = m; c->map_valid = false;
     if ((rc = build_map_grid(c->map_ds.p, Count::of_host(m), c->grid, c->stream))) return rc;
     return check_err(c);
@@ -635,11 +704,12 @@ int liorf_get_scan_ds(liorf_ctx* c, liorf_point* out, int capacity, int* n_ds) {
 }
 
 static Count scan_ds_count(liorf_ctx* c) { return c->h_n_ds >= 0 ? Count::of_host(c->h_n_ds) : Count::of_dev(c->d_counts + C_N_DS, c->n_scan_bound); }
-static Count map_count(liorf_ctx* c) { return c->h_m_ds >= 0 ? Count::of_host(c->h_m_ds) : Count::of_dev(c->d_counts + C_M_DS, c->m_bound); }
+static Count map_count(liorf_ctx* c) { return c->h_m_ds >= 0 ? Count::of_host(c->h_m_ds) : Count::of_dev(c->d_shared + C_M_DS, c->m_bound); }
 
 static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     if (max_iters < 0) return LIORF_ERR_ARG;
     if (max_iters > S2M_MAX_ITERS) max_iters = S2M_MAX_ITERS;
+    c->mail_fresh = false;
     if (!c->grid.cell_start.p || !c->grid.sorted.p) {            // cloudKeyPoses3D empty → return (:1297)
         CUDA_TRY(cudaMemsetAsync(c->d_trace, 0, sizeof(S2MTrace), c->stream));
         return LIORF_OK;
@@ -655,9 +725,11 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
     a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.dbg = c->d_dbg;
+    a.mail = c->d_mail; a.cnt_n_scan = c->d_counts + C_N_SCAN;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2MP_BLOCK), args, 0, c->stream));
+    c->mail_fresh = true;
     return LIORF_OK;
 }
 
@@ -672,15 +744,36 @@ int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
     CUDA_TRY(cudaSetDevice(c->P.device));
     { int rcj = join_map(c); if (rcj) return rcj; }
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 320, c->d_tf6, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->h_mail, c->d_counts, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(mail_counts(c));
     if (trace) CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024, c->d_trace, sizeof(S2MTrace), cudaMemcpyDeviceToHost, c->stream));
     else CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024 + 448, &c->d_trace->iters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     int rc = check_err(c); if (rc) return rc;
-    c->h_n_scan = c->h_mail[C_N_SCAN]; c->h_n_ds = c->h_mail[C_N_DS]; c->h_m_ds = c->h_mail[C_M_DS];   // one round trip refreshes the counts too
+    take_counts(c);                                              // one round trip refreshes the counts too
     std::memcpy(pose6, c->h_mail + 320, 6 * sizeof(float));
     if (trace) std::memcpy(trace, c->h_mail + 1024, sizeof(S2MTrace));
     return LIORF_OK;
 }
+// liorf_process_frame's round trip: the solver left everything the host needs in ONE 64-byte record (pose, iteration count,
+// flags, the three counts, the sticky device error flag) → one D2H copy instead of four.
+static int get_pose_mail(liorf_ctx* c, float pose6[6], int* iters, int* converged, int* degenerate, int* ran) {
+    if (!c->mail_fresh) {
+        int rc = liorf_get_pose(c, pose6, nullptr); if (rc) return rc;
+        *iters = c->h_mail[1024 + 448]; *converged = c->h_mail[1024 + 449]; *degenerate = c->h_mail[1024 + 450]; *ran = c->h_mail[1024 + 451];
+        return LIORF_OK;
+    }
+    c->mail_fresh = false;
+    S2MMail* hm = reinterpret_cast<S2MMail*>(c->h_mail + 3200);
+    CUDA_TRY(cudaMemcpyAsync(hm, c->d_mail, sizeof(S2MMail), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    prof_flush(c);
+    if (hm->err) { fprintf(stderr, "[liorf_b200] device error flag %d (look-back predecessor never arrived)\n", hm->err); return LIORF_ERR_DEVICE_FLAG; }
+    std::memcpy(pose6, hm->tf, 6 * sizeof(float));
+    *iters = hm->iters; *converged = hm->converged; *degenerate = hm->degenerate; *ran = hm->ran;
+    c->h_n_scan = hm->n_scan; c->h_n_ds = hm->n_ds; c->h_m_ds = hm->m_ds;
+    c->h_mail[1024 + 448] = hm->iters;                           // liorf_get_last_counts reads the iteration count here
+    return LIORF_OK;
+}
+
 int liorf_scan2map_optimization(liorf_ctx* c, float pose6[6], int max_iters, int force_all, liorf_lm_trace* trace) {
     if (!c || !pose6) return LIORF_ERR_ARG;
     int rc = liorf_scan2map_optimization_async(c, pose6, max_iters, force_all);
@@ -1229,6 +1322,37 @@ int liorf_build_global_map(liorf_ctx* c, float search_radius, float pose_density
     return check_err(c);
 }
 
+// cloudHandler + downsampleCurrentScan of a FUTURE frame into the alternate front set, on stream_pre.
+static int front_prefetch(liorf_ctx* c, const liorf_frame_in* nx) {
+    if (!nx || nx->n < 0) return LIORF_ERR_ARG;
+    c->pre_valid = false;
+    front_swap(c);                                   // the enqueue helpers below work on "the current set" and "the context's stream"
+    cudaStream_t main_stream = c->stream; c->stream = c->stream_pre;
+    int rc = LIORF_OK;
+    // the set being overwritten was last read by work enqueued on the main stream before this frame began (keyframe copy, ScanContext)
+    if (c->frame_start_recorded && cudaStreamWaitEvent(c->stream_pre, c->ev_frame_start, 0) != cudaSuccess) rc = LIORF_ERR_CUDA;
+    if (!rc) {
+        if (nx->pts_on_device) rc = liorf_project_point_cloud_dev(c, nx->pts, nx->n, nx->time_scan_cur, nx->imu_time, nx->imu_rot_x, nx->imu_rot_y, nx->imu_rot_z,
+                                                                  nx->imu_pointer_cur, nx->deskew_enabled);
+        else rc = liorf_project_point_cloud(c, (const liorf_point_xyzirt*)nx->pts, nx->n, nx->time_scan_cur, nx->imu_time, nx->imu_rot_x, nx->imu_rot_y,
+                                            nx->imu_rot_z, nx->imu_pointer_cur, nx->deskew_enabled, nullptr, nullptr, nullptr);
+    }
+    if (!rc) rc = downsample_async(c, nullptr);
+    if (!rc && cudaEventRecord(c->ev_pre_done, c->stream_pre) != cudaSuccess) rc = LIORF_ERR_CUDA;
+    c->stream = main_stream;
+    front_swap(c);
+    if (rc) return rc;
+    c->pre_valid = true; c->pre_index = nx->frame_index; c->pre_n = nx->n; c->pre_pts = nx->pts;
+    return LIORF_OK;
+}
+
+int liorf_cloud_handler_async(liorf_ctx* c, const liorf_frame_in* frame) {
+    if (!c || !frame) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaEventRecord(c->ev_frame_start, c->stream)); c->frame_start_recorded = true;
+    return front_prefetch(c, frame);
+}
+
 int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out* out) {
     if (!c || !in || !out || in->n < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
@@ -1239,12 +1363,22 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     auto stamp = [&](int k, cudaStream_t st) { if (c->host_timing) { if (!c->tl_ev[k]) cudaEventCreate(&c->tl_ev[k]); cudaEventRecord(c->tl_ev[k], st); } };
     stamp(0, c->stream);
     auto lap = [&](int k) { if (c->host_timing) { auto t = clk::now(); c->host_us[k] += std::chrono::duration<double, std::micro>(t - T0).count(); T0 = t; } };
-    // cloudHandler: projectPointCloud (the deskewed cloud stays on the device)
-    if (in->pts_on_device) rc = liorf_project_point_cloud_dev(c, in->pts, in->n, in->time_scan_cur, in->imu_time, in->imu_rot_x, in->imu_rot_y, in->imu_rot_z,
-                                                              in->imu_pointer_cur, in->deskew_enabled);
-    else rc = liorf_project_point_cloud(c, (const liorf_point_xyzirt*)in->pts, in->n, in->time_scan_cur, in->imu_time, in->imu_rot_x, in->imu_rot_y, in->imu_rot_z,
-                                        in->imu_pointer_cur, in->deskew_enabled, nullptr, nullptr, nullptr);
-    if (rc) return rc;
+    // everything the earlier frames left on the main stream precedes this point: the front set they lived in may be refilled after it
+    CUDA_TRY(cudaEventRecord(c->ev_frame_start, c->stream)); c->frame_start_recorded = true;
+    // cloudHandler: projectPointCloud (the deskewed cloud stays on the device) — already done on stream_pre when this frame was
+    // announced as the previous call's `next` (or through liorf_cloud_handler_async)
+    const bool prefetched = c->pre_valid && c->pre_index == in->frame_index && c->pre_n == in->n && c->pre_pts == in->pts;
+    c->pre_valid = false;
+    if (prefetched) {
+        front_swap(c);
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_pre_done, 0));
+    } else {
+        if (in->pts_on_device) rc = liorf_project_point_cloud_dev(c, in->pts, in->n, in->time_scan_cur, in->imu_time, in->imu_rot_x, in->imu_rot_y, in->imu_rot_z,
+                                                                  in->imu_pointer_cur, in->deskew_enabled);
+        else rc = liorf_project_point_cloud(c, (const liorf_point_xyzirt*)in->pts, in->n, in->time_scan_cur, in->imu_time, in->imu_rot_x, in->imu_rot_y, in->imu_rot_z,
+                                            in->imu_pointer_cur, in->deskew_enabled, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
     stamp(1, c->stream);
     lap(0);
     // laserCloudInfoHandler: extractSurroundingKeyFrames, downsampleCurrentScan, scan2MapOptimization.  The local-map chain is the
@@ -1258,7 +1392,7 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     }
     stamp(2, c->stream_map);
     lap(1);
-    if ((rc = liorf_downsample_current_scan(c, nullptr, nullptr, nullptr))) return rc;
+    if (!prefetched && (rc = liorf_downsample_current_scan(c, nullptr, nullptr, nullptr))) return rc;
     stamp(3, c->stream);
     lap(2);
     if ((rc = join_map(c))) return rc;
@@ -1270,12 +1404,14 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     } else std::memcpy(guess, in->initial_guess, sizeof(guess));
     if ((rc = liorf_scan2map_optimization_async(c, guess, in->max_iters > 0 ? in->max_iters : 30, 0))) return rc;
     stamp(5, c->stream);
+    // the NEXT frame's cloudHandler + downsample go to stream_pre now, behind this frame's critical chain in host order, and run
+    // on the device while the solver iterates (the reference runs imageProjection and mapOptimization as two concurrent nodes)
+    if (in->next && (rc = front_prefetch(c, (const liorf_frame_in*)in->next))) return rc;
     lap(3);
-    if ((rc = liorf_get_pose(c, out->pose, nullptr))) return rc;                  // the frame's single round trip
+    if ((rc = get_pose_mail(c, out->pose, &out->iters, &out->converged, &out->degenerate, &out->ran))) return rc;   // the frame's single round trip
     lap(4);
     if (c->host_timing) for (int k = 1; k <= 5; ++k) { float ms = 0; if (c->tl_ev[k] && cudaEventElapsedTime(&ms, c->tl_ev[0], c->tl_ev[k]) == cudaSuccess) c->tl_ms[k] += ms; }
     out->n_kept = c->h_n_scan; out->n_ds = c->h_n_ds; out->m_ds = c->h_m_ds;
-    out->iters = c->h_mail[1024 + 448]; out->converged = c->h_mail[1024 + 449]; out->degenerate = c->h_mail[1024 + 450]; out->ran = c->h_mail[1024 + 451];
     if (out->ran) {                                                              // transformUpdate (:1323-1353) only after a solve (:1317)
         if (in->use_cloud_info) liorf_host::transform_update(out->pose, in->cloud_info.imuAvailable != 0, in->imu_type, in->cloud_info.imuRollInit,
                                                              in->cloud_info.imuPitchInit, in->imu_rpy_weight, in->rotation_tollerance, in->z_tollerance);
@@ -1302,17 +1438,24 @@ int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_po
     if (!c || n_scan_max < 0 || m_raw_max < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream_pre)); c->pre_valid = false;
     int rc;
     const size_t n = (size_t)(n_scan_max > 0 ? n_scan_max : 1), m = (size_t)(m_raw_max > 0 ? m_raw_max : 1), big = n > m ? n : m;
-    if ((rc = c->scan.reserve(n)) || (rc = c->scan_ds.reserve(n)) || (rc = c->dk.raw.reserve(n)) || (rc = c->dk.kept.reserve(n)) ||
-        (rc = c->membership.reserve(big)) || (rc = c->out_keys.reserve(big)) ||
+    for (int set = 0; set < 2; ++set) {                           // both front sets (see liorf_ctx::FrontSet)
+        rc = 0;
+        if ((rc = c->scan.reserve(n)) || (rc = c->scan_ds.reserve(n)) || (rc = c->dk.raw.reserve(n)) || (rc = c->dk.kept.reserve(n)) ||
+            (rc = c->vg.keys.reserve(big)) || (rc = c->vg.seg_start.reserve(big + 1)) || (rc = c->vg.partial.reserve((size_t)kNumSMs * 6)) ||
+            (rc = c->vg.sort.keys_alt.reserve(big)) || (rc = c->vg.sort.vals_a.reserve(big)) || (rc = c->vg.sort.vals_b.reserve(big)) ||
+            (rc = c->vg.sort.hist.reserve(4 * RADIX)) ||
+            (rc = reserve_zeroed(c->vg.sort.status, ((big + SORT_TILE - 1) / SORT_TILE) * RADIX, c->stream)) ||
+            (rc = reserve_zeroed(c->vg.scan.status, (big + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
+            (rc = reserve_zeroed(c->dk.scan.status, (n + SCAN_TILE - 1) / SCAN_TILE, c->stream))) { /* fall through to the swap back */ }
+        front_swap(c);
+        if (rc && set == 0) { front_swap(c); return rc; }
+        if (rc) return rc;
+    }
+    if ((rc = c->membership.reserve(big)) || (rc = c->out_keys.reserve(big)) ||
         (rc = c->map_raw.reserve(m)) || (rc = c->map_ds.reserve(m)) || (rc = c->grid.sorted.reserve(m)) ||
-        (rc = c->vg.keys.reserve(big)) || (rc = c->vg.seg_start.reserve(big + 1)) || (rc = c->vg.partial.reserve((size_t)kNumSMs * 6)) ||
-        (rc = c->vg.sort.keys_alt.reserve(big)) || (rc = c->vg.sort.vals_a.reserve(big)) || (rc = c->vg.sort.vals_b.reserve(big)) ||
-        (rc = c->vg.sort.hist.reserve(4 * RADIX)) ||
-        (rc = reserve_zeroed(c->vg.sort.status, ((big + SORT_TILE - 1) / SORT_TILE) * RADIX, c->stream)) ||
-        (rc = reserve_zeroed(c->vg.scan.status, (big + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
-        (rc = reserve_zeroed(c->dk.scan.status, (n + SCAN_TILE - 1) / SCAN_TILE, c->stream)) ||
         (rc = c->qcache.reserve(n)) || (rc = c->cand.reserve(n * CAND_CAP)) || (rc = c->d_sel.reserve(4096)) ||
         (rc = c->vg_map.keys.reserve(m)) || (rc = c->vg_map.seg_start.reserve(m + 1)) || (rc = c->vg_map.partial.reserve((size_t)kNumSMs * 6)) ||
         (rc = c->vg_map.sort.keys_alt.reserve(m)) || (rc = c->vg_map.sort.vals_a.reserve(m)) || (rc = c->vg_map.sort.vals_b.reserve(m)) ||
@@ -1335,9 +1478,16 @@ int liorf_enable_timing(liorf_ctx* c, int on) {
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream)); prof_flush(c);
-    c->prof.enabled = on != 0;
+    c->prof.enabled = on != 0; c->prof.mask = 0xffu;
     for (int i = 0; i < SEC_COUNT; ++i) { c->prof.ms[i] = 0; c->prof.calls[i] = 0; }
     return LIORF_OK;
+}
+/* like liorf_enable_timing(ctx, 1) but only the sections whose bit is set in `mask` record events (two cudaEventRecord calls per
+ * section and frame are host time on the frame's critical path: the headline window times the dominant kernel only) */
+int liorf_enable_timing_mask(liorf_ctx* c, unsigned mask) {
+    int rc = liorf_enable_timing(c, mask != 0);
+    if (!rc) c->prof.mask = mask & 0xffu;
+    return rc;
 }
 int liorf_get_timing(liorf_ctx* c, double ms[8], long long calls[8]) {
     if (!c || !ms || !calls) return LIORF_ERR_ARG;

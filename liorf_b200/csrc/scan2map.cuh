@@ -404,6 +404,8 @@ struct QueryCache {                         // 64 B per query
 static_assert(sizeof(QueryCache) == 64, "QueryCache must be 64 bytes");
 
 struct alignas(16) S2MResult { float tf[6]; int conv; int nsel; };
+struct alignas(16) S2MMail { float tf[6]; int iters, converged, degenerate, ran, n_scan, n_ds, m_ds, err; int pad[2]; };
+static_assert(sizeof(S2MMail) == 64, "S2MMail must be 64 bytes");
 
 struct S2MArgs {
     const float4* scan; Count n_scan;
@@ -422,6 +424,8 @@ struct S2MArgs {
     unsigned* flag;                  // epoch flag
     unsigned epoch_base;             // launch-unique: flag value for iteration k is epoch_base + k + 1
     int* err_flag;
+    S2MMail* mail;                   // optional: everything the host reads after a frame, in ONE 64-byte record (one D2H copy)
+    const int* cnt_n_scan;           // device counts copied into the mail (nullable)
 };
 
 template <int G>
@@ -771,6 +775,13 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int k = 0; k < 6; ++k) a.tf6[k] = s_tf[k];
         if (a.trace) { a.trace->iters = iters_done; a.trace->converged = converged; a.trace->ran = run ? 1 : 0; if (!run) a.trace->degenerate = __ldcg(&a.st->isDegenerate); }
+        if (a.mail) {
+            S2MMail mm;
+            for (int k = 0; k < 6; ++k) mm.tf[k] = s_tf[k];
+            mm.iters = iters_done; mm.converged = converged; mm.degenerate = __ldcg(&a.st->isDegenerate); mm.ran = run ? 1 : 0;
+            mm.n_scan = a.cnt_n_scan ? __ldcg(a.cnt_n_scan) : -1; mm.n_ds = n; mm.m_ds = m; mm.err = __ldcg(a.err_flag); mm.pad[0] = mm.pad[1] = 0;
+            *a.mail = mm;
+        }
     }
 }
 
