@@ -243,7 +243,8 @@ typedef struct {
      * downsampleCurrentScan are enqueued on a second stream as soon as this frame's solver has been launched and run while the
      * solver iterates — the reference runs imageProjection and mapOptimization as two concurrent nodes with a queue in between
      * (src/imageProjection.cpp:191-204 publishes, src/mapOptmization.cpp:236 consumes).  Only pts / n / pts_on_device / time_scan_cur /
-     * imu_* / deskew_enabled / frame_index of `next` are read; its buffers must stay valid until the call that processes that frame
+     * imu_* / deskew_enabled / frame_index / surrounding_keyframe_density of `next` are read (the last two also let a frame that
+     * became a keyframe start the next frame's extractSurroundingKeyFrames before the call returns); its buffers must stay valid until the call that processes that frame
      * (same frame_index, pts, n) returns.  Results are bit-identical with and without look-ahead. */
     const void* next;
 } liorf_frame_in;
@@ -268,9 +269,12 @@ int liorf_enable_timing_mask(liorf_ctx* ctx, unsigned mask);         /* only the
 int liorf_get_timing(liorf_ctx* ctx, double ms[8], long long calls[8]);
 long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels launched by this context so far */
 int liorf_get_last_counts(liorf_ctx* ctx, int* n_scan, int* n_ds, int* m_ds, int* iters);   /* as of the last liorf_get_pose */
+int liorf_debug_qr_solve6(liorf_ctx* ctx, const float* A, const float* b, int n, float* x);   /* tests: the device routine behind cv::solve(DECOMP_QR) 6x6 (src/mapOptmization.cpp:1240) */
 int liorf_debug_force_large_voxelgrid(liorf_ctx* ctx, int on);   /* tests: multi-kernel VoxelGrid path on small clouds too */
+int liorf_debug_s2m_lanes(liorf_ctx* ctx, int lanes);              /* tests: lanes per query in the solver (4 / 8 / 16, 0 = automatic) */
 int liorf_debug_s2m_disable_cache(liorf_ctx* ctx, int on);        /* tests: full 27-cell search + plane refit every iteration */
-int liorf_debug_s2m_clocks(liorf_ctx* ctx, int enable, long long* out /* 64*8, nullable */);   /* solver phase clocks (debug) */
+int liorf_debug_s2m_clocks(liorf_ctx* ctx, int enable, long long* out /* 64*8, nullable */);
+int liorf_debug_s2m_arrivals(liorf_ctx* ctx, int enable, unsigned long long* out /* 64*160, nullable */);   /* %globaltimer stamps (debug) */   /* solver phase clocks (debug) */
 int liorf_get_keyframe(liorf_ctx* ctx, int id, liorf_point* out, int capacity, int* n, float pose6[6], double* time);
 
 #ifdef __cplusplus

@@ -337,6 +337,16 @@ class Context:
         self._next_keep = frame_in
         _chk(self.lib.liorf_cloud_handler_async(self.h, C.byref(frame_in)), "liorf_cloud_handler_async")
 
+    def debugQrSolve6(self, A, b):
+        """cv::solve(DECOMP_QR) on the device for n systems (the routine the solver uses)"""
+        A = np.ascontiguousarray(A, np.float32).reshape(-1, 36); b = np.ascontiguousarray(b, np.float32).reshape(-1, 6)
+        x = np.zeros_like(b)
+        _chk(self.lib.liorf_debug_qr_solve6(self.h, _vp(A), _vp(b), C.c_int(len(A)), _vp(x)), "liorf_debug_qr_solve6")
+        return x
+
+    def solverLanes(self, lanes=0):
+        _chk(self.lib.liorf_debug_s2m_lanes(self.h, C.c_int(int(lanes))), "liorf_debug_s2m_lanes")
+
     def disableSolverCache(self, on=True):
         _chk(self.lib.liorf_debug_s2m_disable_cache(self.h, C.c_int(int(on))), "liorf_debug_s2m_disable_cache")
 

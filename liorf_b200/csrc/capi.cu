@@ -55,6 +55,7 @@ struct liorf_ctx {
     DevBuf<int> membership, out_keys;
     int n_scan_bound = 0;           // host-known upper bound of laserCloudSurfLast / DS counts
     int h_n_scan = -1, h_n_ds = -1, h_m_ds = -1;   // host copies (-1 = unknown)
+    int rep_counts[3] = {-1, -1, -1};              // n_scan, n_ds, m_ds as of the last pose read-back (liorf_get_last_counts)
     int m_bound = 0;
     VoxelGridWork vg;               // scan-side VoxelGrid work area (main stream)
     VoxelGridWork vg_map;           // map-side work area: the local-map chain runs concurrently on stream_map
@@ -69,9 +70,9 @@ struct liorf_ctx {
     cudaEvent_t stage_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int stage_turn[2] = {0, 0};   // [0] = selection table, [1] = IMU table
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
-    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr;
-    DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false;
-    int s2m_grid = 0; bool s2m_no_cache = false;
+    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
+    DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; unsigned* d_s2m_arrive = nullptr;
+    int s2m_grid = 0; bool s2m_no_cache = false; int s2m_force_pg = 0;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
     float* d_lm_out = nullptr;      // AtA[36] AtB[6] X[6]
@@ -309,10 +310,12 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
         int spare = S2M_SPARE_SMS;
         if (const char* e = std::getenv("LIORF_SOLVER_SPARE_SMS")) spare = std::atoi(e);
         if (spare < 0) spare = 0;
-        c->s2m_grid = c->num_sms - spare; if (c->s2m_grid < 1) c->s2m_grid = c->num_sms;
+        c->s2m_grid = c->num_sms - spare; if (c->s2m_grid < 2) c->s2m_grid = c->num_sms;      // >= 2: workers + the reducer CTA
     }
     CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->num_sms * NPROD * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->d_mail, sizeof(S2MMail)));
+    CUDA_TRY(cudaMalloc(&c->d_s2m_arrive, (size_t)c->num_sms * sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(c->d_s2m_arrive, 0, (size_t)c->num_sms * sizeof(unsigned)));
     CUDA_TRY(cudaMalloc(&c->d_result, 2 * sizeof(S2MResult)));
     CUDA_TRY(cudaMemset(c->d_result, 0, 2 * sizeof(S2MResult)));
     CUDA_TRY(cudaMalloc(&c->d_bins, SC_DESC * sizeof(unsigned)));
@@ -372,8 +375,9 @@ void liorf_destroy(liorf_ctx* c) {
     if (c->icp_out) cudaFree(c->icp_out);
     c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
-    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); c->qcache.release(); c->cand.release();
+    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); cudaFree(c->d_s2m_arrive); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
+    if (c->d_dbg_gt) cudaFree(c->d_dbg_gt);
     if (c->h_sel) cudaFreeHost(c->h_sel);
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (c->stage_ev[a][b]) cudaEventDestroy(c->stage_ev[a][b]);
     cudaFreeHost(c->h_mail);
@@ -720,11 +724,11 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     if ((rc = join_map(c))) return rc;
     S2MArgs a;
     a.qcache = c->qcache.p; a.cand = c->cand.p; a.result = c->d_result;
-    a.arrive = reinterpret_cast<unsigned*>(c->d_misc + 8); a.flag = reinterpret_cast<unsigned*>(c->d_misc + 9); a.err_flag = c->d_err;
+    a.arrive = c->d_s2m_arrive; a.flag = reinterpret_cast<unsigned*>(c->d_misc + 9); a.err_flag = c->d_err;
     a.epoch_base = (++c->s2m_launch_seq) * 64u;
     a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
-    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.dbg = c->d_dbg;
+    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.force_pg = c->s2m_force_pg; a.dbg = c->d_dbg; a.dbg_gt = c->d_dbg_gt;
     a.mail = c->d_mail; a.cnt_n_scan = c->d_counts + C_N_SCAN;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
@@ -749,6 +753,7 @@ int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
     else CUDA_TRY(cudaMemcpyAsync(c->h_mail + 1024 + 448, &c->d_trace->iters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     int rc = check_err(c); if (rc) return rc;
     take_counts(c);                                              // one round trip refreshes the counts too
+    c->rep_counts[0] = c->h_n_scan; c->rep_counts[1] = c->h_n_ds; c->rep_counts[2] = c->h_m_ds;
     std::memcpy(pose6, c->h_mail + 320, 6 * sizeof(float));
     if (trace) std::memcpy(trace, c->h_mail + 1024, sizeof(S2MTrace));
     return LIORF_OK;
@@ -770,6 +775,7 @@ static int get_pose_mail(liorf_ctx* c, float pose6[6], int* iters, int* converge
     std::memcpy(pose6, hm->tf, 6 * sizeof(float));
     *iters = hm->iters; *converged = hm->converged; *degenerate = hm->degenerate; *ran = hm->ran;
     c->h_n_scan = hm->n_scan; c->h_n_ds = hm->n_ds; c->h_m_ds = hm->m_ds;
+    c->rep_counts[0] = c->h_n_scan; c->rep_counts[1] = c->h_n_ds; c->rep_counts[2] = c->h_m_ds;
     c->h_mail[1024 + 448] = hm->iters;                           // liorf_get_last_counts reads the iteration count here
     return LIORF_OK;
 }
@@ -1062,6 +1068,22 @@ int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pai
     return LIORF_OK;
 }
 
+/* tests: cv::solve(DECOMP_QR) (hal::QR32f) of n 6x6 systems (A row-major [n][36], b [n][6]) by the device routine of the solver */
+int liorf_debug_qr_solve6(liorf_ctx* c, const float* A, const float* b, int n, float* x) {
+    if (!c || !A || !b || n <= 0 || !x) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    DevBuf<float> d; int rc;
+    if ((rc = d.reserve((size_t)n * (36 + 6 + 6)))) return rc;
+    float* dA = d.p; float* db = dA + (size_t)36 * n; float* dx = db + (size_t)6 * n;
+    CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)36 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(db, b, (size_t)6 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    k_debug_qr6<<<(n + 63) / 64, 64, 0, c->stream>>>(dA, db, n, dx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(x, dx, (size_t)6 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    rc = check_err(c);
+    d.release();
+    return rc;
+}
 /* tests: 1 = run the multi-kernel (large-cloud) VoxelGrid path on small clouds too; 0 = automatic */
 int liorf_debug_force_large_voxelgrid(liorf_ctx* c, int on) {
     if (!c) return LIORF_ERR_ARG;
@@ -1423,6 +1445,16 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
         int id = liorf_add_keyframe(c, out->pose, in->time_scan_cur);
         if (id < 0) return id;
         out->is_keyframe = 1; out->keyframe_id = id;
+        // A new keyframe changes the NEXT frame's local map.  With look-ahead its timestamp is known, so extractSurroundingKeyFrames
+        // for that frame is launched right here (stream_map, behind the keyframe copy only) instead of after the host has returned,
+        // built the next call and come back; the next call's identical request then finds the map resident.
+        if (in->next) {
+            const liorf_frame_in* nx = (const liorf_frame_in*)in->next;
+            std::vector<liorf_host::KeyPose> kp(c->kfs.size());
+            for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }
+            std::vector<int> sel = liorf_host::extract_nearby(kp, nx->time_scan_cur, c->P.surroundingKeyframeSearchRadius, nx->surrounding_keyframe_density);
+            if ((rc = liorf_extract_surrounding_keyframes(c, sel.data(), (int)sel.size(), nullptr))) return rc;
+        }
         if ((rc = liorf_sc_make_and_save(c, nullptr, 0))) return rc;
     }
     if (in->loop_every > 0 && in->frame_index % in->loop_every == in->loop_every - 1) {
@@ -1504,6 +1536,24 @@ int liorf_debug_s2m_disable_cache(liorf_ctx* c, int on) {
     c->s2m_no_cache = on != 0;
     return LIORF_OK;
 }
+/* tests: lanes per query of the persistent solver (4, 8 or 16); 0 = automatic (the widest group that covers the scan in one round) */
+int liorf_debug_s2m_lanes(liorf_ctx* c, int lanes) {
+    if (!c || !(lanes == 0 || lanes == 4 || lanes == 8 || lanes == 16)) return LIORF_ERR_ARG;
+    c->s2m_force_pg = lanes;
+    return LIORF_OK;
+}
+/* debug: %globaltimer stamps of the last solve, out[iter * 160 + k]: k < workers = that worker's arrival, 156 = reducer sums
+ * ready, 157 = reducer published, 158 = worker 0 saw the flag (ns) */
+int liorf_debug_s2m_arrivals(liorf_ctx* c, int enable, unsigned long long* out /* 64*160 or null */) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t bytes = (size_t)S2M_MAX_ITERS * S2M_GT_STRIDE * sizeof(unsigned long long);
+    if (enable && !c->d_dbg_gt) { CUDA_TRY(cudaMalloc(&c->d_dbg_gt, bytes)); CUDA_TRY(cudaMemset(c->d_dbg_gt, 0, bytes)); }
+    if (out && c->d_dbg_gt) CUDA_TRY(cudaMemcpy(out, c->d_dbg_gt, bytes, cudaMemcpyDeviceToHost));
+    if (!enable && c->d_dbg_gt) { cudaFree(c->d_dbg_gt); c->d_dbg_gt = nullptr; }
+    return LIORF_OK;
+}
 int liorf_debug_s2m_clocks(liorf_ctx* c, int enable, long long* out /*64*8 or null*/) {
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
@@ -1515,7 +1565,7 @@ int liorf_debug_s2m_clocks(liorf_ctx* c, int enable, long long* out /*64*8 or nu
 }
 int liorf_get_last_counts(liorf_ctx* c, int* n_scan, int* n_ds, int* m_ds, int* iters) {
     if (!c) return LIORF_ERR_ARG;
-    if (n_scan) *n_scan = c->h_n_scan; if (n_ds) *n_ds = c->h_n_ds; if (m_ds) *m_ds = c->h_m_ds;
+    if (n_scan) *n_scan = c->rep_counts[0]; if (n_ds) *n_ds = c->rep_counts[1]; if (m_ds) *m_ds = c->rep_counts[2];
     if (iters) *iters = c->h_mail[1024 + 448];       // S2MTrace.iters as of the last liorf_get_pose
     return LIORF_OK;
 }

@@ -292,6 +292,15 @@ __device__ __forceinline__ bool lm_solve_dev(int iter, const double* sums, float
 // ---------------------------------------------------------------------------------------------------------------
 // Per-function parity hooks
 // ---------------------------------------------------------------------------------------------------------------
+// test hook: cv::solve(DECOMP_QR) of n 6x6 systems by the device routine the solver uses (one thread each)
+__global__ void __launch_bounds__(64) k_debug_qr6(const float* __restrict__ A, const float* __restrict__ b, int n, float* __restrict__ x) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float xs[6];
+    qr_solve6(A + 36 * s, b + 6 * s, xs);
+    for (int i = 0; i < 6; ++i) x[6 * s + i] = xs[i];
+}
+
 __global__ void __launch_bounds__(S2M_BLOCK) k_surf_optimization(const float4* __restrict__ scan, Count n_scan, const float* __restrict__ tf6,
                                                                 const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap,
                                                                 GridDims g, Count m_map, float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out,
@@ -388,13 +397,13 @@ __global__ void __launch_bounds__(256) k_lm_hook(int iter, const float4* __restr
 // sums the partials in CTA order (deterministic whoever is last), solves the 6x6 system, publishes (pose, converged)
 // and releases an epoch flag the other CTAs spin on (bounded).  This replaces grid.sync + 148 redundant sums/solves.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PG = 4;                       // lanes per query in the persistent solver
-constexpr int S2MP_BLOCK = 512;             // one CTA per SM: 148 x 128 queries = 18.9k queries per round
-constexpr int S2MP_QPB = S2MP_BLOCK / PG;
+constexpr int PG_MIN = 4;                   // FEWEST lanes per query in the persistent solver (large scans); small scans get 8 or 16
+constexpr int S2MP_BLOCK = 512;             // one CTA per SM: grid x 128 queries per round at 4 lanes per query
+constexpr int S2MP_QPB = S2MP_BLOCK / PG_MIN;
 constexpr int S2MP_WARPS = S2MP_BLOCK / 32;
 constexpr int CAND_CAP = 64;                // cached candidates per query (float4 each); overflow → always full search
 constexpr float S2M_MARGIN = 0.15f;
-constexpr int PPL = NPROD / PG;             // products per lane (28 / 4 = 7)
+constexpr int PPL = NPROD / 4;              // products per accumulating lane (lanes 0..3 of a group: 28 / 4 = 7)
 
 struct QueryCache {                         // 64 B per query
     float qx, qy, qz; int cnt;              // cached query position q0 and candidate count (-1: none, -2: overflow)
@@ -407,6 +416,9 @@ struct alignas(16) S2MResult { float tf[6]; int conv; int nsel; };
 struct alignas(16) S2MMail { float tf[6]; int iters, converged, degenerate, ran, n_scan, n_ds, m_ds, err; int pad[2]; };
 static_assert(sizeof(S2MMail) == 64, "S2MMail must be 64 bytes");
 
+constexpr int S2M_MAX_WORKERS = 152;    // >= SMs - 1 (B200: 147)
+constexpr int S2M_GT_STRIDE = 160;      // per iteration: [0..W) worker arrival, [156] reducer sums ready, [157] reducer published, [158] worker 0 saw the flag
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 struct S2MArgs {
     const float4* scan; Count n_scan;
     const unsigned* cell_start; const float4* gmap; GridDims g; Count m_map;
@@ -415,12 +427,14 @@ struct S2MArgs {
     double* partial;                 // [2][gridDim.x][NPROD]
     S2MTrace* trace;
     int max_iters; int force_all;
+    int force_pg;                    // tests: lanes per query (4, 8 or 16); 0 = automatic
     int no_cache;                    // tests: 1 = never reuse candidate lists / planes (every iteration searches the 27 cells and refits)
     long long* dbg;                  // optional [S2M_MAX_ITERS][8] clock64 phase stamps of CTA 0 (nullptr = off)
+    unsigned long long* dbg_gt;      // optional [S2M_MAX_ITERS][S2M_GT_STRIDE] %globaltimer stamps: worker arrivals, flag seen by worker 0, reducer sum-ready / published
     QueryCache* qcache;              // [n_scan bound]
     float4* cand;                    // [n_scan bound][CAND_CAP]
     S2MResult* result;               // [2]
-    unsigned* arrive;                // arrival counter (zero between iterations)
+    unsigned* arrive;                // [gridDim.x] per-worker arrival words (hold the epoch of the iteration whose partial is complete)
     unsigned* flag;                  // epoch flag
     unsigned epoch_base;             // launch-unique: flag value for iteration k is epoch_base + k + 1
     int* err_flag;
@@ -449,6 +463,7 @@ __device__ __forceinline__ void top5_merge(Top5& mine, Top5& res) {
 
 // FULL search over the 27 cells with PG lanes; also builds the cached candidate list around q (= new q0).
 // Returns the number of cached candidates (or -2 on overflow).  `pos` of the results = index into gmap.
+template <int PG>
 __device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap,
                                                    GridDims g, float4* __restrict__ clist, Top5& mine) {
     const int gl = threadIdx.x & (PG - 1);
@@ -526,6 +541,118 @@ __device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigne
     return ncache <= CAND_CAP ? ncache : -2;
 }
 
+// One pass over the scan for one LM iteration with PG lanes per query (4, 8 or 16): surfOptimization for every query and
+// the 28 normal-equation products, accumulated in fp64 by the first four lanes of each group (7 products each).
+// More lanes per query shorten the serial candidate walk of the 27-cell search and put fewer queries in a warp (less
+// divergence between cached / searching / refitting queries); the kernel picks the widest group that still covers the
+// scan in ONE round of the grid.
+template <int PG>
+__device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, const int W, const int iter, const float (&s_t)[12], const LMTrig& s_trig,
+                                               float (*s_rows)[8], const int (&pij)[PPL], double (&acc)[PPL]) {
+    const int gl = threadIdx.x & (PG - 1);
+    const int qslot = threadIdx.x / PG;
+    for (int j0 = 0; j0 * W < n; j0 += (S2MP_BLOCK / PG)) {          // query q is served by worker (q mod W): dense and sparse regions spread over all SMs
+        const int q = (j0 + qslot) * W + (int)blockIdx.x;
+        const bool active = q < n;
+        const int qq = active ? q : 0;
+        QueryCache* qc = a.qcache + qq;
+        float4* clist = a.cand + (size_t)qq * CAND_CAP;
+        // every independent load of the cached path is issued up front (one L2 round trip): the point, the cache
+        // header (written by this same group earlier in this launch), the cached plane and the first candidates
+        float4 ori = active ? __ldg(a.scan + q) : make_float4(0, 0, 0, 0);
+        const float4 h0 = __ldcg(reinterpret_cast<const float4*>(qc));
+        const float4 h1 = __ldcg(reinterpret_cast<const float4*>(qc) + 1);              // nn[0..3]
+        const float4 h2 = __ldcg(reinterpret_cast<const float4*>(qc) + 2);              // nn[4], plane_ok, pa, pb
+        const float4 h3 = __ldcg(reinterpret_cast<const float4*>(qc) + 3);              // pc, pd
+        float4 pre[KNN_U];
+#pragma unroll
+        for (int u = 0; u < KNN_U; ++u) pre[u] = __ldcg(clist + gl + PG * u);           // speculative: slots exist even if unused
+        float4 sel = apply_affine_dev(s_t, ori);
+        const int cnt = __float_as_int(h0.w);
+        float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
+        float moved = mx * mx; moved += my * my; moved += mz * mz;
+        const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
+        // the list holds the points within 1 + m of q0 THAT LIE IN q0's 27 cells; the unit ball around pointSel stays
+        // inside that block of cells only while pointSel is in q0's own cell
+        const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
+        const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
+        Top5 mine; top5_init(mine);
+        int list_cnt;                                       // >= 0: results index the candidate list; -2: they index gmap... see below
+        if (use_cache) {
+            for (int f0 = gl; f0 < cnt; f0 += PG * KNN_U) {
+                float4 p[KNN_U];
+#pragma unroll
+                for (int u = 0; u < KNN_U; ++u) {
+                    const int f = f0 + PG * u;
+                    p[u] = f0 == gl ? pre[u] : (f < cnt ? __ldcg(clist + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f));
+                    if (f >= cnt) p[u] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < KNN_U; ++u) {
+                    float dx = sel.x - p[u].x, dy = sel.y - p[u].y, dz = sel.z - p[u].z;
+                    float d = dx * dx; d += dy * dy; d += dz * dz;
+                    if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), f0 + PG * u);
+                }
+            }
+            list_cnt = cnt;
+        } else if (active) {
+            list_cnt = knn5_full_and_cache<PG>(sel, a.cell_start, a.gmap, a.g, clist, mine);
+            if (gl == 0) { float4 h = make_float4(sel.x, sel.y, sel.z, __int_as_float(list_cnt)); __stcg(reinterpret_cast<float4*>(qc), h); }
+        } else list_cnt = -1;
+        Top5 nn; top5_merge<PG>(mine, nn);
+        // ---- plane: reuse when the ordered neighbour ids are unchanged ----
+        const bool have5 = active && nn.pos[4] != -1 && (double)nn.d[4] < 1.0;          // :1097
+        bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have5) {
+            const bool same = iter > 0 && !a.no_cache && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
+                              __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
+            float pa, pb, pc, pd; bool planeValid;
+            if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
+            else {
+                float A[5][3];
+#pragma unroll
+                const float4* nsrc = use_cache ? clist : a.gmap;      // results index the candidate list in cached mode, gmap otherwise
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { float4 mpt = __ldcg(nsrc + nn.pos[j]); A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z; }
+                float x[3];
+                colpiv_qr_solve_5x3(A, x);                                               // :1104
+                pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
+                float ps = sqrtf(pa * pa + pb * pb + pc * pc);                           // :1111
+                pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+                planeValid = true;
+#pragma unroll
+                for (int j = 0; j < 5; ++j)                                              // :1115-1122
+                    if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
+                if (gl == 0) {
+                    __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3])));
+                    __stcg(reinterpret_cast<float4*>(qc) + 2, make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb));
+                    __stcg(reinterpret_cast<float4*>(qc) + 3, make_float4(pc, pd, 0.f, 0.f));
+                }
+            }
+            if (planeValid) {
+                float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;                   // :1125
+                float rr = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z));
+                float sw = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)rr);         // :1127-1128
+                coeff = make_float4(sw * pa, sw * pb, sw * pc, sw * pd2);                // :1130-1133
+                f = (double)sw > 0.1;                                                    // :1135
+            }
+        } else if (iter == 0 && active && gl == 0) {
+            __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)));   // no cached plane
+        }
+        float v[8];
+        lm_row_dev(s_trig, ori, coeff, v); v[7] = 1.f;
+        __syncwarp();
+        {   // lanes 0..3 of the group publish two row entries each (zero row when the point is not selected)
+            const float e0 = gl == 0 ? v[0] : gl == 1 ? v[1] : gl == 2 ? v[2] : v[3];
+            const float e1 = gl == 0 ? v[4] : gl == 1 ? v[5] : gl == 2 ? v[6] : v[7];
+            if (gl < 4) { s_rows[qslot][gl] = f ? e0 : 0.f; s_rows[qslot][4 + gl] = f ? e1 : 0.f; }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < PPL; ++t) if (gl < 4) acc[t] += (double)s_rows[qslot][pij[t] & 15] * (double)s_rows[qslot][pij[t] >> 4];
+    }
+}
+
 __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a) {
     __shared__ float s_tf[6];
     __shared__ float s_sc[6];                              // cos/sin of yaw, pitch, roll for this iteration
@@ -534,13 +661,24 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     __shared__ double s_sum[NPROD];
     __shared__ float s_A[36], s_V[36];
     __shared__ LMDeviceState s_st;
-    __shared__ int s_conv, s_last;
+    __shared__ int s_conv;
+    __shared__ double s_part[NPROD][S2M_MAX_WORKERS];      // reducer only: the workers' partial sums, component-major
 
+    // Roles: CTAs 0 .. W-1 are WORKERS (queries), the last CTA is the REDUCER: it owns the LM state, sums the workers'
+    // partials in CTA order as they arrive, solves the 6x6 system and publishes (pose, converged).  A fixed reducer keeps the
+    // solve's code and state hot in ONE SM's caches — with "the last CTA to arrive solves" a different SM ran ~60 KB of cold
+    // straight-line code every iteration (measured: 2.4 us warm, 5.6 us cold) — and its sum is done by the time the slowest worker
+    // arrives instead of starting there.
+    const int W = (int)gridDim.x - 1;
+    const bool reducer = (int)blockIdx.x == W;
     const int n = a.n_scan.get();
     const int m = a.m_map.get();
-    const int gl = threadIdx.x & (PG - 1);
-    const int qslot = threadIdx.x / PG;
+    // lanes per query: the widest group that covers the scan in one round of the workers (same choice in every CTA)
+    const int pg = a.force_pg ? a.force_pg : (n <= W * (S2MP_BLOCK / 16) ? 16 : (n <= W * (S2MP_BLOCK / 8) ? 8 : 4));
+    const int gl = threadIdx.x & (pg - 1);              // lane within the query group; lanes 0..3 own 7 products each
     if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
+    if (reducer && threadIdx.x >= 64 && threadIdx.x < 64 + 37)          // persistent LM state (members :139-140)
+        reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
     __syncthreads();
     // guards of scan2MapOptimization (:1297-1300): a map must exist (and hold >= 5 points for the 5-NN), n > 30
     const bool run = (m >= 5) && (n > 30);
@@ -549,201 +687,129 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
         // product indices owned by this lane: p in [PPL*gl, PPL*gl + PPL)
         int pij[PPL];
 #pragma unroll
-        for (int t = 0; t < PPL; ++t) { const int p = gl * PPL + t; pij[t] = prod_i(p) | (prod_j(p) << 4); }
+        for (int t = 0; t < PPL; ++t) { const int p = (gl & 3) * PPL + t; pij[t] = prod_i(p) | (prod_j(p) << 4); }
         // iteration 0 never trusts the per-query caches (they belong to an earlier launch / another map)
         for (int iter = 0; iter < a.max_iters; ++iter) {
-            const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && iter < S2M_MAX_ITERS;
-            if (dbg) a.dbg[iter * 8 + 0] = clock64();
-            // six fp64-rounded trig values in parallel: (cos, sin) of yaw = tf[2], pitch = tf[1], roll = tf[0]
-            if (threadIdx.x < 6) { const float ang = s_tf[2 - (threadIdx.x >> 1)]; s_sc[threadIdx.x] = (threadIdx.x & 1) ? sin_f(ang) : cos_f(ang); }
-            __syncthreads();
-            float s_t[12]; LMTrig s_trig;
-            {   // pcl::getTransformation from the shared trig values (same arithmetic as get_transformation_dev)
-                const float A = s_sc[0], B = s_sc[1], Cc = s_sc[2], D = s_sc[3], E = s_sc[4], F = s_sc[5], DE = D * E, DF = D * F;
-                s_t[0] = A * Cc; s_t[1] = A * DF - B * E; s_t[2] = B * F + A * DE; s_t[3] = s_tf[3];
-                s_t[4] = B * Cc; s_t[5] = A * E + B * DF; s_t[6] = B * DE - A * F; s_t[7] = s_tf[4];
-                s_t[8] = -D;     s_t[9] = Cc * F;         s_t[10] = Cc * E;        s_t[11] = s_tf[5];
-                s_trig.srx = B; s_trig.crx = A; s_trig.sry = D; s_trig.cry = Cc; s_trig.srz = F; s_trig.crz = E;   // :1170-1175
-            }
-            double acc[PPL];
-#pragma unroll
-            for (int t = 0; t < PPL; ++t) acc[t] = 0.0;
-            // query q is served by CTA (q mod gridDim) so that dense and sparse regions of the scan spread over all SMs
-            for (int j0 = 0; j0 * (int)gridDim.x < n; j0 += S2MP_QPB) {
-                const int q = (j0 + qslot) * (int)gridDim.x + (int)blockIdx.x;
-                const bool active = q < n;
-                const int qq = active ? q : 0;
-                QueryCache* qc = a.qcache + qq;
-                float4* clist = a.cand + (size_t)qq * CAND_CAP;
-                // every independent load of the cached path is issued up front (one L2 round trip): the point, the cache
-                // header (written by this same group earlier in this launch), the cached plane and the first candidates
-                float4 ori = active ? __ldg(a.scan + q) : make_float4(0, 0, 0, 0);
-                const float4 h0 = __ldcg(reinterpret_cast<const float4*>(qc));
-                const float4 h1 = __ldcg(reinterpret_cast<const float4*>(qc) + 1);              // nn[0..3]
-                const float4 h2 = __ldcg(reinterpret_cast<const float4*>(qc) + 2);              // nn[4], plane_ok, pa, pb
-                const float4 h3 = __ldcg(reinterpret_cast<const float4*>(qc) + 3);              // pc, pd
-                float4 pre[KNN_U];
-#pragma unroll
-                for (int u = 0; u < KNN_U; ++u) pre[u] = __ldcg(clist + gl + PG * u);           // speculative: slots exist even if unused
-                float4 sel = apply_affine_dev(s_t, ori);
-                const int cnt = __float_as_int(h0.w);
-                float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
-                float moved = mx * mx; moved += my * my; moved += mz * mz;
-                const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
-                // the list holds the points within 1 + m of q0 THAT LIE IN q0's 27 cells; the unit ball around pointSel stays
-                // inside that block of cells only while pointSel is in q0's own cell
-                const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
-                const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
-                Top5 mine; top5_init(mine);
-                int list_cnt;                                       // >= 0: results index the candidate list; -2: they index gmap... see below
-                if (use_cache) {
-                    for (int f0 = gl; f0 < cnt; f0 += PG * KNN_U) {
-                        float4 p[KNN_U];
-#pragma unroll
-                        for (int u = 0; u < KNN_U; ++u) {
-                            const int f = f0 + PG * u;
-                            p[u] = f0 == gl ? pre[u] : (f < cnt ? __ldcg(clist + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f));
-                            if (f >= cnt) p[u] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < KNN_U; ++u) {
-                            float dx = sel.x - p[u].x, dy = sel.y - p[u].y, dz = sel.z - p[u].z;
-                            float d = dx * dx; d += dy * dy; d += dz * dz;
-                            if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), f0 + PG * u);
-                        }
-                    }
-                    list_cnt = cnt;
-                } else if (active) {
-                    list_cnt = knn5_full_and_cache(sel, a.cell_start, a.gmap, a.g, clist, mine);
-                    if (gl == 0) { float4 h = make_float4(sel.x, sel.y, sel.z, __int_as_float(list_cnt)); __stcg(reinterpret_cast<float4*>(qc), h); }
-                } else list_cnt = -1;
-                Top5 nn; top5_merge<PG>(mine, nn);
-                // ---- plane: reuse when the ordered neighbour ids are unchanged ----
-                const bool have5 = active && nn.pos[4] != -1 && (double)nn.d[4] < 1.0;          // :1097
-                bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (have5) {
-                    const bool same = iter > 0 && !a.no_cache && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
-                                      __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
-                    float pa, pb, pc, pd; bool planeValid;
-                    if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
-                    else {
-                        float A[5][3];
-#pragma unroll
-                        const float4* nsrc = use_cache ? clist : a.gmap;      // results index the candidate list in cached mode, gmap otherwise
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) { float4 mpt = __ldcg(nsrc + nn.pos[j]); A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z; }
-                        float x[3];
-                        colpiv_qr_solve_5x3(A, x);                                               // :1104
-                        pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
-                        float ps = sqrtf(pa * pa + pb * pb + pc * pc);                           // :1111
-                        pa /= ps; pb /= ps; pc /= ps; pd /= ps;
-                        planeValid = true;
-#pragma unroll
-                        for (int j = 0; j < 5; ++j)                                              // :1115-1122
-                            if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
-                        if (gl == 0) {
-                            __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3])));
-                            __stcg(reinterpret_cast<float4*>(qc) + 2, make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb));
-                            __stcg(reinterpret_cast<float4*>(qc) + 3, make_float4(pc, pd, 0.f, 0.f));
-                        }
-                    }
-                    if (planeValid) {
-                        float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;                   // :1125
-                        float rr = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z));
-                        float sw = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)rr);         // :1127-1128
-                        coeff = make_float4(sw * pa, sw * pb, sw * pc, sw * pd2);                // :1130-1133
-                        f = (double)sw > 0.1;                                                    // :1135
-                    }
-                } else if (iter == 0 && active && gl == 0) {
-                    __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)));   // no cached plane
-                }
-                float v[8];
-                lm_row_dev(s_trig, ori, coeff, v); v[7] = 1.f;
-                __syncwarp();
-                {   // lanes 0..3 of the group publish two row entries each (zero row when the point is not selected)
-                    const float e0 = gl == 0 ? v[0] : gl == 1 ? v[1] : gl == 2 ? v[2] : v[3];
-                    const float e1 = gl == 0 ? v[4] : gl == 1 ? v[5] : gl == 2 ? v[6] : v[7];
-                    s_rows[qslot][gl] = f ? e0 : 0.f; s_rows[qslot][4 + gl] = f ? e1 : 0.f;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < PPL; ++t) acc[t] += (double)s_rows[qslot][pij[t] & 15] * (double)s_rows[qslot][pij[t] >> 4];
-            }
-            if (dbg) a.dbg[iter * 8 + 1] = clock64();
-            // block reduction (fixed tree): equal-gl lanes of the 8 groups of a warp, then across warps by warp 0
-#pragma unroll
-            for (int t = 0; t < PPL; ++t) {
-                acc[t] += __shfl_xor_sync(FULL, acc[t], 4);
-                acc[t] += __shfl_xor_sync(FULL, acc[t], 8);
-                acc[t] += __shfl_xor_sync(FULL, acc[t], 16);
-            }
-            if (lane_id() < PG) {
-#pragma unroll
-                for (int t = 0; t < PPL; ++t) s_red[warp_id()][gl * PPL + t] = acc[t];
-            }
-            __syncthreads();
-            double* part = a.partial + (size_t)(iter & 1) * gridDim.x * NPROD;
-            if (threadIdx.x < NPROD) {
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-                for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
-                __stcg(part + (size_t)blockIdx.x * NPROD + threadIdx.x, (s0 + s1) + (s2 + s3));
-            }
-            __syncthreads();
-            if (dbg) a.dbg[iter * 8 + 2] = clock64();
             const unsigned epoch = a.epoch_base + (unsigned)iter + 1u;
-            if (threadIdx.x == 0) {
-                // release: the CTA's partial (ordered before by the barrier) becomes visible with the arrival;
-                // acquire: the last arriver sees every other CTA's partial
-                unsigned t;
-                asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(t) : "l"(a.arrive), "r"(1u) : "memory");
-                s_last = (t == gridDim.x - 1) ? 1 : 0;
-            }
-            __syncthreads();
+            double* part = a.partial + (size_t)(iter & 1) * gridDim.x * NPROD;
             S2MResult* res = a.result + (iter & 1);
-            if (s_last) {
-                if (dbg) a.dbg[iter * 8 + 3] = clock64();
-                const long long lc0 = clock64();
-                if (threadIdx.x >= 64 && threadIdx.x < 64 + 37)      // persistent LM state (written by whichever CTA solved iteration 0)
-                    reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
-                {   // partial sums in CTA order: warp w takes CTAs w, w + W, ...; lane = component; then warps in order
-                    const int w = warp_id(), l = lane_id();
-                    double s0 = 0;
-                    if (l < NPROD) {
-                        double vv[10];
+            if (!reducer) {
+                const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && iter < S2M_MAX_ITERS;
+                if (dbg) a.dbg[iter * 8 + 0] = clock64();
+                // six fp64-rounded trig values in parallel: (cos, sin) of yaw = tf[2], pitch = tf[1], roll = tf[0]
+                if (threadIdx.x < 6) { const float ang = s_tf[2 - (threadIdx.x >> 1)]; s_sc[threadIdx.x] = (threadIdx.x & 1) ? sin_f(ang) : cos_f(ang); }
+                __syncthreads();
+                float s_t[12]; LMTrig s_trig;
+                {   // pcl::getTransformation from the shared trig values (same arithmetic as get_transformation_dev)
+                    const float A = s_sc[0], B = s_sc[1], Cc = s_sc[2], D = s_sc[3], E = s_sc[4], F = s_sc[5], DE = D * E, DF = D * F;
+                    s_t[0] = A * Cc; s_t[1] = A * DF - B * E; s_t[2] = B * F + A * DE; s_t[3] = s_tf[3];
+                    s_t[4] = B * Cc; s_t[5] = A * E + B * DF; s_t[6] = B * DE - A * F; s_t[7] = s_tf[4];
+                    s_t[8] = -D;     s_t[9] = Cc * F;         s_t[10] = Cc * E;        s_t[11] = s_tf[5];
+                    s_trig.srx = B; s_trig.crx = A; s_trig.sry = D; s_trig.cry = Cc; s_trig.srz = F; s_trig.crz = E;   // :1170-1175
+                }
+                double acc[PPL];
 #pragma unroll
-                        for (int k2 = 0; k2 < 10; ++k2) { const int b = w + k2 * S2MP_WARPS; vv[k2] = b < (int)gridDim.x ? __ldcg(part + (size_t)b * NPROD + l) : 0.0; }
+                for (int t = 0; t < PPL; ++t) acc[t] = 0.0;
+                if (pg == 16) s2m_query_pass<16>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
+                else if (pg == 8) s2m_query_pass<8>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
+                else s2m_query_pass<4>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
+                if (dbg) a.dbg[iter * 8 + 1] = clock64();
+                // block reduction (fixed tree): lanes 0..3 of the groups of a warp, then across warps
 #pragma unroll
-                        for (int k2 = 0; k2 < 10; ++k2) s0 += vv[k2];
-                        for (int b = w + 10 * S2MP_WARPS; b < (int)gridDim.x; b += S2MP_WARPS) s0 += __ldcg(part + (size_t)b * NPROD + l);
-                        s_red[w][l] = s0;
-                    }
+                for (int t = 0; t < PPL; ++t) {                      // lanes 0..3 of every group hold sums; groups are pg lanes apart
+                    if (pg <= 4) acc[t] += __shfl_xor_sync(FULL, acc[t], 4);
+                    if (pg <= 8) acc[t] += __shfl_xor_sync(FULL, acc[t], 8);
+                    acc[t] += __shfl_xor_sync(FULL, acc[t], 16);
+                }
+                if (lane_id() < 4) {
+#pragma unroll
+                    for (int t = 0; t < PPL; ++t) s_red[warp_id()][gl * PPL + t] = acc[t];
                 }
                 __syncthreads();
                 if (threadIdx.x < NPROD) {
                     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                     for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
-                    s_sum[threadIdx.x] = (s0 + s1) + (s2 + s3);
+                    __stcg(part + (size_t)blockIdx.x * NPROD + threadIdx.x, (s0 + s1) + (s2 + s3));
                 }
                 __syncthreads();
-                if (dbg) a.dbg[iter * 8 + 4] = clock64();
+                if (dbg) a.dbg[iter * 8 + 2] = clock64();
+                if (threadIdx.x == 0) {
+                    // release: this CTA's partial (ordered before by the barrier) becomes visible with its arrival word
+                    if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + blockIdx.x] = gtimer();
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.arrive + blockIdx.x), "r"(epoch) : "memory");
+                    if (dbg) a.dbg[iter * 8 + 3] = clock64();
+                    unsigned v, spins = 0;
+                    while (true) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag) : "memory");
+                        if (v == epoch) break;
+                        if (++spins > (1u << 26)) { atomicExch(a.err_flag, 2); break; }
+                    }
+                    if (dbg) a.dbg[iter * 8 + 4] = clock64();
+                    if (a.dbg_gt && blockIdx.x == 0 && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 158] = gtimer();
+                }
+                __syncthreads();
+                if (threadIdx.x < 6) s_tf[threadIdx.x] = __ldcg(&res->tf[threadIdx.x]);
+                if (threadIdx.x == 32) s_conv = __ldcg(&res->conv);
+                __syncthreads();
+                if (dbg) a.dbg[iter * 8 + 5] = clock64();
+            } else {
+                // ---- reducer: thread t waits for worker t and pulls its 28 partial sums into shared memory (all workers in
+                // parallel: two L2 round trips after the last arrival, not two per worker); the sums are then taken in a FIXED
+                // order (chunk k = workers k, k + 16, ... sequentially; chunks combined by the 4-chain tree below), so the
+                // result does not depend on the arrival order ----
+                for (int b = threadIdx.x; b < W; b += S2MP_BLOCK) {
+                    unsigned v, spins = 0;
+                    while (true) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.arrive + b) : "memory");
+                        if (v == epoch) break;
+                        if (++spins > (1u << 26)) { atomicExch(a.err_flag, 2); break; }
+                    }
+                    const double2* src = reinterpret_cast<const double2*>(part + (size_t)b * NPROD);
+                    double2 vv[NPROD / 2];
+#pragma unroll
+                    for (int k2 = 0; k2 < NPROD / 2; ++k2) vv[k2] = __ldcg(src + k2);
+#pragma unroll
+                    for (int k2 = 0; k2 < NPROD / 2; ++k2) { s_part[2 * k2][b] = vv[k2].x; s_part[2 * k2 + 1][b] = vv[k2].y; }
+                }
+                __syncthreads();
+                if (threadIdx.x < S2MP_WARPS * 32) {
+                    const int k = threadIdx.x >> 5, c = threadIdx.x & 31;        // chunk k, component c
+                    if (c < NPROD) {
+                        double s0 = 0;
+                        for (int b = k; b < W; b += S2MP_WARPS) s0 += s_part[c][b];
+                        s_red[k][c] = s0;
+                    }
+                }
+                __syncthreads();
+                const long long lc0 = clock64();
+                if (threadIdx.x < NPROD) {
+                    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#pragma unroll
+                    for (int ww = 0; ww < S2MP_WARPS; ww += 4) { t0 += s_red[ww][threadIdx.x]; t1 += s_red[ww + 1][threadIdx.x]; t2 += s_red[ww + 2][threadIdx.x]; t3 += s_red[ww + 3][threadIdx.x]; }
+                    s_sum[threadIdx.x] = (t0 + t1) + (t2 + t3);
+                }
+                __syncthreads();
                 const long long lc1 = clock64();
                 if (threadIdx.x == 0) {
+                    if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 156] = gtimer();
                     int nsel;
                     float tfn[6];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) tfn[k] = s_tf[k];
                     bool c = lm_solve_dev<true>(iter, s_sum, tfn, &s_st, s_A, s_V, nullptr, nullptr, nullptr, &nsel);
-                    if (iter == 0) *a.st = s_st;
                     {   // result = 2 x 16-byte stores
                         float4* r4 = reinterpret_cast<float4*>(res);
                         __stcg(r4, make_float4(tfn[0], tfn[1], tfn[2], tfn[3]));
                         __stcg(r4 + 1, make_float4(tfn[4], tfn[5], __int_as_float(c ? 1 : 0), __int_as_float(nsel)));
                     }
-                    *a.arrive = 0u;                                  // nobody arrives again before the flag is released
                     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flag), "r"(epoch) : "memory");
-                    // off the critical path: the other CTAs are already running the next iteration
+                    if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 157] = gtimer();
+                    // off the critical path: the workers are already running the next iteration
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s_tf[k] = tfn[k];
+                    s_conv = c ? 1 : 0;
+                    if (iter == 0) *a.st = s_st;
                     if (a.dbg && iter < S2M_MAX_ITERS) { a.dbg[iter * 8 + 6] = lc1 - lc0; a.dbg[iter * 8 + 7] = clock64() - lc1; }
                     if (a.trace && iter < S2M_MAX_ITERS) {
                         for (int k = 0; k < 6; ++k) a.trace->pose[iter][k] = tfn[k];
@@ -751,34 +817,19 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                         a.trace->degenerate = s_st.isDegenerate;
                     }
                 }
-            } else {
-                if (dbg) a.dbg[iter * 8 + 3] = clock64();
-                if (threadIdx.x == 0) {
-                    unsigned v, spins = 0;
-                    while (true) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag) : "memory");
-                        if (v == epoch) break;
-                        if (++spins > (1u << 26)) { atomicExch(a.err_flag, 2); break; }
-                    }
-                }
-                if (dbg) a.dbg[iter * 8 + 4] = clock64();
+                __syncthreads();
             }
-            __syncthreads();
-            if (threadIdx.x < 6) s_tf[threadIdx.x] = __ldcg(&res->tf[threadIdx.x]);
-            if (threadIdx.x == 32) s_conv = __ldcg(&res->conv);
-            __syncthreads();
-            if (dbg) a.dbg[iter * 8 + 5] = clock64();
             iters_done = iter + 1;
             if (s_conv) { converged = 1; if (!a.force_all) break; }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (reducer && threadIdx.x == 0) {
         for (int k = 0; k < 6; ++k) a.tf6[k] = s_tf[k];
-        if (a.trace) { a.trace->iters = iters_done; a.trace->converged = converged; a.trace->ran = run ? 1 : 0; if (!run) a.trace->degenerate = __ldcg(&a.st->isDegenerate); }
+        if (a.trace) { a.trace->iters = iters_done; a.trace->converged = converged; a.trace->ran = run ? 1 : 0; if (!run) a.trace->degenerate = s_st.isDegenerate; }
         if (a.mail) {
             S2MMail mm;
             for (int k = 0; k < 6; ++k) mm.tf[k] = s_tf[k];
-            mm.iters = iters_done; mm.converged = converged; mm.degenerate = __ldcg(&a.st->isDegenerate); mm.ran = run ? 1 : 0;
+            mm.iters = iters_done; mm.converged = converged; mm.degenerate = s_st.isDegenerate; mm.ran = run ? 1 : 0;
             mm.n_scan = a.cnt_n_scan ? __ldcg(a.cnt_n_scan) : -1; mm.n_ds = n; mm.m_ds = m; mm.err = __ldcg(a.err_flag); mm.pad[0] = mm.pad[1] = 0;
             *a.mail = mm;
         }

@@ -198,6 +198,47 @@ def test_combine_and_lm_optimization(ctx, oracle, kitti_case):
     assert np.allclose(P, o["state"][1:].reshape(6, 6), atol=1e-4)
 
 
+def test_device_qr_solve_matches_opencv_golden(ctx, oracle):
+    """cv::solve(AtA, AtB, X, DECOMP_QR) (src/mapOptmization.cpp:1240): the device routine of the solver against the OpenCV 4.13
+    golden vectors, bit for bit, and against the oracle's restatement on random SPD systems."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_lm6.npz"))
+    n = int(g["n_cases"])
+    A = np.stack([g[f"AtA_{i}"] for i in range(n)]); b = np.stack([g[f"AtB_{i}"].ravel() for i in range(n)])
+    x = ctx.debugQrSolve6(A, b)
+    for i in range(n):
+        if bool(g[f"ok_{i}"]):
+            assert np.array_equal(x[i], g[f"X_{i}"].ravel()), i
+    rng = np.random.default_rng(5)
+    M = rng.normal(size=(256, 6, 6)).astype(np.float32) * rng.uniform(0.1, 300, size=(256, 1, 1)).astype(np.float32)
+    A2 = np.einsum("nij,nkj->nik", M, M).astype(np.float32); b2 = rng.normal(size=(256, 6)).astype(np.float32) * 50
+    x2 = ctx.debugQrSolve6(A2, b2)
+    for i in range(len(A2)):
+        xo, ok = oracle.cv_qr_solve6(A2[i], b2[i])
+        if ok:
+            assert np.array_equal(x2[i], xo), i
+
+
+def test_solver_lane_widths_agree(ctx, oracle, kitti_case):
+    """The persistent solver works with 4, 8 or 16 lanes per query (chosen from the scan size).  The width only changes how the
+    candidate walk is split and the order of the fp64 partial sums: the selected-row counts of all 30 iterations are identical,
+    the poses agree to fp32 rounding with each other and with the oracle within the north-star tolerance."""
+    o_map, ds = _setup_registration(ctx, oracle, kitti_case)
+    tf0 = kitti_case["init"]
+    o = oracle.scan2map(ds, o_map, tf0, 30, force_all=True)
+    runs = {}
+    for lanes in (4, 8, 16):
+        ctx.solverLanes(lanes)
+        pose, tr = ctx.scan2MapOptimization(tf0, 30, force_all_iters=True)
+        runs[lanes] = (tr.poses().copy(), np.array(tr.nsel[:30]))
+        assert tr.iters == 30
+        assert np.max(np.abs(runs[lanes][0][:, 3:] - o["trace"][:, 3:])) < 1e-4 and np.max(np.abs(runs[lanes][0][:, :3] - o["trace"][:, :3])) < 1e-5
+    ctx.solverLanes(0)
+    for lanes in (8, 16):
+        assert np.array_equal(runs[lanes][1], runs[4][1])
+        assert np.max(np.abs(runs[lanes][0] - runs[4][0])) < 2e-6
+
+
 def test_lm_too_few_correspondences(ctx, oracle):
     rng = np.random.default_rng(1)
     mp = rng.uniform(-2, 2, size=(500, 4)).astype(np.float32)
