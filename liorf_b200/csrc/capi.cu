@@ -1,6 +1,7 @@
 // capi.cu — context + extern "C" entry points declared in include/liorf_b200.h.
 // One translation unit; every kernel lives in the .cuh files next to this one.  Built with
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+#include <map>
 #include "../../include/liorf_b200.h"
 #include "common.cuh"
 #include "prims.cuh"
@@ -47,7 +48,8 @@ struct liorf_ctx {
     int* d_counts = nullptr;        // C_COUNT ints of the CURRENT front set (N_SCAN, N_DS, FIRST_KEPT, hook counts)
     int* d_counts_base = nullptr;   // [front set 0 | shared | front set 1], C_COUNT ints each: either set is contiguous with the shared block
     int* d_shared = nullptr;        // counts that do not belong to a front set (C_M_DS)
-    int* d_misc = nullptr;          // tickets / counters / error flag (zero-initialised)
+    int* d_misc = nullptr;          // counters / error flag (zero-initialised)
+    unsigned long long* d_tick = nullptr;   // look-back ticket words (prims.cuh: draw_ticket), one per scan / sort work area
     int* d_err = nullptr;
     int* h_mail = nullptr;          // pinned mailbox (128 KB: scalars/trace in the lower half, IMU table staging in the upper)
     // clouds
@@ -68,6 +70,9 @@ struct liorf_ctx {
     DevBuf<KfSel> d_sel;
     KfSel* h_sel = nullptr; int h_sel_cap = 0;       // two halves, alternated per call (see stage_slot)
     cudaEvent_t stage_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int stage_turn[2] = {0, 0};   // [0] = selection table, [1] = IMU table
+    // the local-map chain as CUDA graphs (one pair per 64k-point size bucket): ~20 stream operations become 2 launches
+    struct MapGraphs { cudaGraphExec_t vg = nullptr, grid = nullptr; const void* sig[20] = {nullptr}; };
+    std::map<int, MapGraphs> map_graphs; bool use_graphs = true;
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
@@ -240,6 +245,7 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     if (!c) return LIORF_ERR_ARG;
     c->P = *p;
     c->host_timing = std::getenv("LIORF_HOST_TIMING") != nullptr;
+    c->use_graphs = std::getenv("LIORF_NO_GRAPH") == nullptr;
     if (c->P.grid_dim_x == 0) c->P.grid_dim_x = 256;
     if (c->P.grid_dim_y == 0) c->P.grid_dim_y = 256;
     if (c->P.grid_dim_z == 0) c->P.grid_dim_z = 32;
@@ -261,12 +267,17 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->d_misc, 64 * sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_misc, 0, 64 * sizeof(int)));
     c->d_err = c->d_misc + 0;
+    {
+        unsigned long long init[16]; for (auto& v : init) v = TICKET_INIT;
+        CUDA_TRY(cudaMalloc(&c->d_tick, sizeof(init)));
+        CUDA_TRY(cudaMemcpy(c->d_tick, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     c->vg.mm_counter = c->d_misc + 1;
-    c->vg.sort.ticket = c->d_misc + 2; c->vg.sort.err_flag = c->d_err;
-    c->vg.scan.ticket = c->d_misc + 3; c->vg.scan.err_flag = c->d_err;
-    c->grid.scan.ticket = c->d_misc + 4; c->grid.scan.err_flag = c->d_err;
-    c->dk.scan.ticket = c->d_misc + 5; c->dk.scan.err_flag = c->d_err;
-    c->combine_scan.ticket = c->d_misc + 6; c->combine_scan.err_flag = c->d_err;
+    c->vg.sort.ticket = c->d_tick + 0; c->vg.sort.err_flag = c->d_err;
+    c->vg.scan.ticket = c->d_tick + 1; c->vg.scan.err_flag = c->d_err;
+    c->grid.scan.ticket = c->d_tick + 2; c->grid.scan.err_flag = c->d_err;
+    c->dk.scan.ticket = c->d_tick + 3; c->dk.scan.err_flag = c->d_err;
+    c->combine_scan.ticket = c->d_tick + 4; c->combine_scan.err_flag = c->d_err;
     int* lm_counter = c->d_misc + 7; (void)lm_counter;
     CUDA_TRY(cudaMalloc(&c->vg.meta, sizeof(VoxMeta)));
     CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_map, cudaStreamNonBlocking, prio_lo));
@@ -274,16 +285,16 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_map, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->vg_map.meta, sizeof(VoxMeta)));
     c->vg_map.mm_counter = c->d_misc + 10;
-    c->vg_map.sort.ticket = c->d_misc + 11; c->vg_map.sort.err_flag = c->d_err;
-    c->vg_map.scan.ticket = c->d_misc + 12; c->vg_map.scan.err_flag = c->d_err;
-    c->icp_grid.scan.ticket = c->d_misc + 13; c->icp_grid.scan.err_flag = c->d_err;
+    c->vg_map.sort.ticket = c->d_tick + 5; c->vg_map.sort.err_flag = c->d_err;
+    c->vg_map.scan.ticket = c->d_tick + 6; c->vg_map.scan.err_flag = c->d_err;
+    c->icp_grid.scan.ticket = c->d_tick + 7; c->icp_grid.scan.err_flag = c->d_err;
     CUDA_TRY(cudaMalloc(&c->dk.start_inv, 12 * sizeof(float)));
     c->dk.first_kept = c->d_counts + C_FIRST_KEPT;
     // the alternate front set: its own look-back tickets, VoxelGrid meta and deskew scalars
     c->alt.vg.mm_counter = c->d_misc + 20;
-    c->alt.vg.sort.ticket = c->d_misc + 21; c->alt.vg.sort.err_flag = c->d_err;
-    c->alt.vg.scan.ticket = c->d_misc + 22; c->alt.vg.scan.err_flag = c->d_err;
-    c->alt.dk.scan.ticket = c->d_misc + 23; c->alt.dk.scan.err_flag = c->d_err;
+    c->alt.vg.sort.ticket = c->d_tick + 8; c->alt.vg.sort.err_flag = c->d_err;
+    c->alt.vg.scan.ticket = c->d_tick + 9; c->alt.vg.scan.err_flag = c->d_err;
+    c->alt.dk.scan.ticket = c->d_tick + 10; c->alt.dk.scan.err_flag = c->d_err;
     CUDA_TRY(cudaMalloc(&c->alt.vg.meta, sizeof(VoxMeta)));
     CUDA_TRY(cudaMalloc(&c->alt.dk.start_inv, 12 * sizeof(float)));
     c->alt.dk.first_kept = c->alt.d_counts + C_FIRST_KEPT;
@@ -360,6 +371,7 @@ void liorf_destroy(liorf_ctx* c) {
     cudaStreamSynchronize(c->stream_map);
     for (VoxelGridWork* w : {&c->vg_map}) { w->partial.release(); w->keys.release(); w->seg_start.release(); w->sort.keys_alt.release(); w->sort.vals_a.release();
         w->sort.vals_b.release(); w->sort.hist.release(); w->sort.status.release(); w->scan.status.release(); cudaFree(w->meta); }
+    for (auto& kv : c->map_graphs) { if (kv.second.vg) cudaGraphExecDestroy(kv.second.vg); if (kv.second.grid) cudaGraphExecDestroy(kv.second.grid); }
     cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_map); cudaStreamDestroy(c->stream_map);
     c->vg.partial.release(); c->vg.keys.release(); c->vg.seg_start.release();
     c->vg.sort.keys_alt.release(); c->vg.sort.vals_a.release(); c->vg.sort.vals_b.release(); c->vg.sort.hist.release(); c->vg.sort.status.release();
@@ -374,7 +386,7 @@ void liorf_destroy(liorf_ctx* c) {
     c->icp_nn_d2.release(); c->icp_grid.counts.release(); c->icp_grid.cell_start.release(); c->icp_grid.sorted.release(); c->icp_grid.scan.status.release();
     if (c->icp_out) cudaFree(c->icp_out);
     c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
-    cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
+    cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); cudaFree(c->d_s2m_arrive); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->d_dbg_gt) cudaFree(c->d_dbg_gt);
@@ -570,45 +582,91 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
         return LIORF_OK;
     }
     const int ns = (int)sel.size();
-    if (ns > c->h_sel_cap) {
+    if (ns + 1 > c->h_sel_cap) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream_map));
         if (c->h_sel) cudaFreeHost(c->h_sel);
         c->h_sel_cap = 2 * ns + 64;
         CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)2 * c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
     }
-    if ((rc = c->d_sel.reserve(ns > 0 ? ns : 1))) return rc;
+    if ((rc = c->d_sel.reserve(ns + 1))) return rc;
     const int slot = stage_slot(c, 0); if (slot < 0) return LIORF_ERR_CUDA;
-    KfSel* hsel = c->h_sel + (size_t)slot * c->h_sel_cap;
+    KfSel* hsel = c->h_sel + (size_t)slot * c->h_sel_cap;      // entry 0 = header {nsel, total}, selections from entry 1
     long long total = 0;
     for (int i = 0; i < ns; ++i) {
         const Keyframe& k = c->kfs[sel[i]];
-        KfSel& s = hsel[i];
+        KfSel& s = hsel[1 + i];
         s.src_off = (int)k.off; s.count = k.count; s.dst_off = (int)total; s.pad = 0;
         host_get_transformation(k.pose[3], k.pose[4], k.pose[5], k.pose[0], k.pose[1], k.pose[2], s.t);
         total += k.count;
     }
     if (total > 0x7fffffffLL) return LIORF_ERR_ARG;
     const int tot = (int)total;
-    if ((rc = c->map_raw.reserve(tot > 0 ? tot : 1))) return rc;
-    if ((rc = c->map_ds.reserve(tot > 0 ? tot : 1))) return rc;
+    std::memset(&hsel[0], 0, sizeof(KfSel)); hsel[0].src_off = ns; hsel[0].count = tot;
+    // graph path: grids are sized from the bucket bound, the exact total is read from the header on the device
+    const bool graphs = c->use_graphs && tot > VGS_CAP;
+    const int bucket = graphs ? (tot + 65535) / 65536 : 0;
+    const int bound = graphs ? bucket * 65536 : tot;
+    if ((rc = c->map_raw.reserve(bound > 0 ? bound : 1))) return rc;
+    if ((rc = c->map_ds.reserve(bound > 0 ? bound : 1))) return rc;
     // fork: everything enqueued so far on the main stream (keyframe copies, the previous solve that still reads the old map)
     // happens-before the map chain
     cudaStream_t ms = c->stream_map;
     CUDA_TRY(cudaEventRecord(c->ev_main, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(ms, c->ev_main, 0));
-    if (ns > 0) CUDA_TRY(cudaMemcpyAsync(c->d_sel.p, hsel, (size_t)ns * sizeof(KfSel), cudaMemcpyHostToDevice, ms));
+    CUDA_TRY(cudaMemcpyAsync(c->d_sel.p, hsel, (size_t)(ns + 1) * sizeof(KfSel), cudaMemcpyHostToDevice, ms));
     CUDA_TRY(cudaEventRecord(c->stage_ev[0][slot], ms));
-    {
-        ProfScope ps(c, SEC_MAP_BUILD, ms); c->launches += 10;
-        if (tot > 0) k_transform_concat<<<(tot + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p, ns, tot, c->map_raw.p);
-        if ((rc = voxel_grid_device(c->map_raw.p, Count::of_host(tot), c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_shared + C_M_DS, nullptr,
-                                    nullptr, c->vg_map, ms))) return rc;
+    const Count cnt_raw = graphs ? Count::of_dev(&c->d_sel.p[0].count, bound) : Count::of_host(tot);
+    auto enqueue_vg = [&]() -> int {
+        if (tot > 0) {
+            if (graphs) k_transform_concat_hdr<<<(bound + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p, c->map_raw.p);
+            else k_transform_concat<<<(tot + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p + 1, ns, tot, c->map_raw.p);
+        }
+        return voxel_grid_device(c->map_raw.p, cnt_raw, c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_shared + C_M_DS, nullptr, nullptr, c->vg_map, ms);
+    };
+    auto enqueue_grid = [&]() -> int { return build_map_grid(c->map_ds.p, Count::of_dev(c->d_shared + C_M_DS, bound), c->grid, ms); };
+    if (!graphs) {
+        { ProfScope ps(c, SEC_MAP_BUILD, ms); c->launches += 10; if ((rc = enqueue_vg())) return rc; }
+        { ProfScope ps(c, SEC_GRID_BUILD, ms); c->launches += 3; if ((rc = enqueue_grid())) return rc; }
+    } else {
+        liorf_ctx::MapGraphs& G = c->map_graphs[bucket];
+        // every buffer the chain touches, sized for the bucket BEFORE capture (no allocation or memset may happen inside it)
+        VoxelGridWork& w = c->vg_map; MapGrid& gr = c->grid;
+        const int nc = grid_cells(gr.dims);
+        int mmb = (bound + VG_MM_BLOCK * 8 - 1) / (VG_MM_BLOCK * 8); if (mmb > kNumSMs) mmb = kNumSMs;
+        if ((rc = w.partial.reserve((size_t)mmb * 6)) || (rc = w.keys.reserve(bound)) || (rc = w.seg_start.reserve((size_t)bound + 1)) ||
+            (rc = w.sort.keys_alt.reserve(bound)) || (rc = w.sort.vals_a.reserve(bound)) || (rc = w.sort.vals_b.reserve(bound)) || (rc = w.sort.hist.reserve(4 * RADIX)) ||
+            (rc = reserve_zeroed(w.sort.status, (size_t)((bound + SORT_TILE - 1) / SORT_TILE) * RADIX, ms)) ||
+            (rc = reserve_zeroed(w.scan.status, (size_t)(bound + SCAN_TILE - 1) / SCAN_TILE, ms)) ||
+            (rc = gr.counts.reserve(nc)) || (rc = gr.cell_start.reserve((size_t)nc + 1)) || (rc = gr.sorted.reserve(bound)) ||
+            (rc = reserve_zeroed(gr.scan.status, (size_t)(nc + 512 * 16 - 1) / (512 * 16), ms))) return rc;
+        if (!gr.counts_clean) { CUDA_TRY(cudaMemsetAsync(gr.counts.p, 0, (size_t)nc * sizeof(unsigned), ms)); gr.counts_clean = true; }
+        const void* sig[20] = {c->kf_points.p, c->d_sel.p, c->map_raw.p, c->map_ds.p, w.partial.p, w.keys.p, w.seg_start.p, w.sort.keys_alt.p, w.sort.vals_a.p,
+                               w.sort.vals_b.p, w.sort.hist.p, w.sort.status.p, w.scan.status.p, gr.counts.p, gr.cell_start.p, gr.sorted.p, gr.scan.status.p,
+                               w.meta, (const void*)(size_t)w.force_large, nullptr};
+        if (G.vg && std::memcmp(sig, G.sig, sizeof(sig)) != 0) { cudaGraphExecDestroy(G.vg); cudaGraphExecDestroy(G.grid); G.vg = G.grid = nullptr; }
+        if (!G.vg) {
+            const bool prof_on = c->prof.enabled; c->prof.enabled = false;          // no timing events inside a capture
+            cudaGraph_t g1 = nullptr, g2 = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(ms, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_vg();
+            cudaError_t e1 = cudaStreamEndCapture(ms, &g1);
+            if (!rc && e1 == cudaSuccess) {
+                CUDA_TRY(cudaStreamBeginCapture(ms, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue_grid();
+                e1 = cudaStreamEndCapture(ms, &g2);
+            }
+            c->prof.enabled = prof_on;
+            if (rc || e1 != cudaSuccess) { if (g1) cudaGraphDestroy(g1); if (g2) cudaGraphDestroy(g2); return rc ? rc : LIORF_ERR_CUDA; }
+            CUDA_TRY(cudaGraphInstantiate(&G.vg, g1, 0));
+            CUDA_TRY(cudaGraphInstantiate(&G.grid, g2, 0));
+            cudaGraphDestroy(g1); cudaGraphDestroy(g2);
+            std::memcpy(G.sig, sig, sizeof(sig));
+        }
+        { ProfScope ps(c, SEC_MAP_BUILD, ms); c->launches += 10; CUDA_TRY(cudaGraphLaunch(G.vg, ms)); }
+        { ProfScope ps(c, SEC_GRID_BUILD, ms); c->launches += 3; CUDA_TRY(cudaGraphLaunch(G.grid, ms)); }
     }
-    c->m_bound = tot; c->h_m_ds = -1;
-    {
-        ProfScope ps(c, SEC_GRID_BUILD, ms); c->launches += 3;
-        if ((rc = build_map_grid(c->map_ds.p, Count::of_dev(c->d_shared + C_M_DS, tot), c->grid, ms))) return rc;
-    }
+    c->m_bound = bound; c->h_m_ds = -1;
     CUDA_TRY(cudaEventRecord(c->ev_map, ms));
     c->map_pending = true;
     c->last_sel = sel; c->last_sel_version = c->pose_version; c->map_valid = true;

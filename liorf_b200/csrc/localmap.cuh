@@ -70,8 +70,8 @@ inline int build_map_grid(const float4* map, Count cnt, MapGrid& G, cudaStream_t
 // ---- extractCloud: transform each selected keyframe by its pose and concatenate in selection order ----
 struct KfSel { int src_off, count, dst_off, pad; float t[12]; };       // 64 B
 
-__global__ void __launch_bounds__(256) k_transform_concat(const float4* __restrict__ kf_points, const KfSel* __restrict__ sel, int nsel,
-                                                          int total, float4* __restrict__ out) {
+__device__ __forceinline__ void transform_concat_body(const float4* __restrict__ kf_points, const KfSel* __restrict__ sel, int nsel,
+                                                      int total, float4* __restrict__ out) {
     __shared__ int s_dst[1024];
     const int ns = nsel < 1024 ? nsel : 1024;
     for (int i = threadIdx.x; i < ns; i += blockDim.x) s_dst[i] = sel[i].dst_off;
@@ -87,6 +87,15 @@ __global__ void __launch_bounds__(256) k_transform_concat(const float4* __restri
     const KfSel& k = sel[lo];
     float4 p = kf_points[k.src_off + (i - k.dst_off)];
     out[i] = apply_affine_dev(k.t, p);
+}
+__global__ void __launch_bounds__(256) k_transform_concat(const float4* __restrict__ kf_points, const KfSel* __restrict__ sel, int nsel,
+                                                          int total, float4* __restrict__ out) {
+    transform_concat_body(kf_points, sel, nsel, total, out);
+}
+// Same, with the selection count and the point total read from a header entry in front of the table (hdr[0].src_off = nsel,
+// hdr[0].count = total, selections from hdr[1]): no per-call kernel argument, so the local-map chain replays from a CUDA graph.
+__global__ void __launch_bounds__(256) k_transform_concat_hdr(const float4* __restrict__ kf_points, const KfSel* __restrict__ hdr, float4* __restrict__ out) {
+    transform_concat_body(kf_points, hdr + 1, hdr[0].src_off, hdr[0].count, out);
 }
 
 }  // namespace liorf

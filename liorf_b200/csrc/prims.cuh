@@ -125,11 +125,22 @@ inline int reserve_zeroed(DevBuf<T>& b, size_t n, cudaStream_t s) {     // growt
     return LIORF_OK;
 }
 
-struct ScanWork {            // per-scan scratch: ticket counter + status array
-    int* ticket = nullptr;                      // zero-initialised once; the last block of a launch resets it
+// Ticket word of a look-back kernel: [63:32] launch epoch | [31:0] next tile ticket.  ONE atomicAdd hands a block its tile and
+// the epoch that tags this launch's status words; the block that draws the last ticket stores (epoch + 1, 0) for the next
+// launch.  Nothing about a launch is a host-side argument any more, so a chain of these kernels can be replayed from a CUDA graph.
+constexpr unsigned long long TICKET_INIT = 1ull << 32;      // epoch 1: zero-filled status arrays (epoch 0) are never valid
+__device__ __forceinline__ int draw_ticket(unsigned long long* ticket, unsigned& epoch) {
+    const unsigned long long old = atomicAdd(ticket, 1ull);
+    const int t = (int)(unsigned)(old & 0xffffffffull);
+    epoch = (unsigned)(old >> 32);
+    if (t == (int)gridDim.x - 1) atomicExch(ticket, (unsigned long long)(epoch + 1u) << 32);   // every ticket of this launch has been handed out
+    return t;
+}
+
+struct ScanWork {            // per-scan scratch: ticket word + status array
+    unsigned long long* ticket = nullptr;       // device, initialised to TICKET_INIT once
     DevBuf<unsigned long long> status;
     int* err_flag = nullptr;
-    unsigned epoch = 0;
 };
 
 __device__ __forceinline__ unsigned warp_incl_scan(unsigned v) {
@@ -160,21 +171,19 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* smem_w
 // Generic single-pass exclusive scan. LoadOp(i) -> unsigned value of element i; StoreOp(i, value, exclusive_prefix).
 // total_out (optional) receives the grand total.
 template <int BLOCK, int IPT, class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(BLOCK) k_scan_lookback(Count cnt, LoadOp load, StoreOp store, int* ticket, unsigned long long* status,
-                                                        unsigned epoch, int* err_flag, unsigned* total_out) {
+__global__ void __launch_bounds__(BLOCK) k_scan_lookback(Count cnt, LoadOp load, StoreOp store, unsigned long long* ticket, unsigned long long* status,
+                                                        int* err_flag, unsigned* total_out) {
     constexpr int SCAN_BLOCK = BLOCK, SCAN_IPT = IPT, SCAN_TILE = BLOCK * IPT;
     __shared__ int s_tile;
     __shared__ unsigned s_warp[SCAN_BLOCK / 32 + 1];
     __shared__ unsigned s_prefix;
+    __shared__ unsigned s_epoch;
     const int n = cnt.get();
     const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if (threadIdx.x == 0) {
-        int t = atomicAdd(ticket, 1);
-        if (t == (int)gridDim.x - 1) *ticket = 0;       // every ticket of this launch has been handed out
-        s_tile = t;
-    }
+    if (threadIdx.x == 0) { unsigned e; s_tile = draw_ticket(ticket, e); s_epoch = e; }
     __syncthreads();
     const int tile = s_tile;
+    const unsigned epoch = s_epoch;
     if (tile >= ntiles) { if (n == 0 && tile == 0 && threadIdx.x == 0 && total_out) *total_out = 0u; return; }
     const int base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
     unsigned v[SCAN_IPT]; unsigned sum = 0;
@@ -196,8 +205,7 @@ inline int launch_scan(Count n, LoadOp load, StoreOp store, ScanWork& w, unsigne
     constexpr int TILE = BLOCK * IPT;
     int ntiles = (n.bound + TILE - 1) / TILE;
     int rc = reserve_zeroed(w.status, ntiles, s); if (rc) return rc;
-    ++w.epoch;
-    k_scan_lookback<BLOCK, IPT><<<ntiles, BLOCK, 0, s>>>(n, load, store, w.ticket, w.status.p, w.epoch, w.err_flag, total_out);
+    k_scan_lookback<BLOCK, IPT><<<ntiles, BLOCK, 0, s>>>(n, load, store, w.ticket, w.status.p, w.err_flag, total_out);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
 }
@@ -223,22 +231,20 @@ __global__ void __launch_bounds__(256) k_radix_hist(const unsigned* __restrict__
 // One stable counting pass on digit `shift`.  vals_in == nullptr means value = element index (first pass).
 __global__ void __launch_bounds__(SORT_BLOCK) k_radix_pass(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
                                                            unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out, Count cnt, int shift,
-                                                           const unsigned* __restrict__ ghist /*256 counts of this digit*/, int* ticket,
-                                                           unsigned long long* status, unsigned epoch, int* err_flag) {
+                                                           const unsigned* __restrict__ ghist /*256 counts of this digit*/, unsigned long long* ticket,
+                                                           unsigned long long* status, int* err_flag) {
     __shared__ int s_tile;
+    __shared__ unsigned s_epoch;
     __shared__ unsigned s_whist[SORT_WARPS][RADIX];   // per-warp digit counts → exclusive warp offsets
     __shared__ unsigned s_base[RADIX];                // global base + tile exclusive prefix per digit
     __shared__ unsigned s_warp[SORT_BLOCK / 32 + 1];
     const int n = cnt.get();
     const int ntiles = (n + SORT_TILE - 1) / SORT_TILE;
-    if (threadIdx.x == 0) {
-        int t = atomicAdd(ticket, 1);
-        if (t == (int)gridDim.x - 1) *ticket = 0;
-        s_tile = t;
-    }
+    if (threadIdx.x == 0) { unsigned e; s_tile = draw_ticket(ticket, e); s_epoch = e; }
     for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_BLOCK) (&s_whist[0][0])[i] = 0;
     __syncthreads();
     const int tile = s_tile;
+    const unsigned epoch = s_epoch;
     if (tile >= ntiles) return;
     const int w = warp_id(), l = lane_id();
     const int wbase = tile * SORT_TILE + w * (32 * SORT_IPT);
@@ -288,9 +294,8 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_radix_pass(const unsigned* __res
 struct SortWork {
     DevBuf<unsigned> keys_alt, vals_a, vals_b, hist;
     DevBuf<unsigned long long> status;
-    int* ticket = nullptr;
+    unsigned long long* ticket = nullptr;       // device, initialised to TICKET_INIT once (see draw_ticket)
     int* err_flag = nullptr;
-    unsigned epoch = 0;
 };
 
 // Sorts keys (in place semantic: result ends in keys / vals_out) stably; values start as iota.
@@ -312,8 +317,7 @@ inline int radix_sort_pairs_iota(unsigned* keys, Count cnt, SortWork& w, unsigne
     unsigned* kin = keys; unsigned* kout = w.keys_alt.p;
     unsigned* vin = nullptr; unsigned* vout = w.vals_a.p;
     for (int p = 0; p < 4; ++p) {
-        ++w.epoch;
-        k_radix_pass<<<ntiles, SORT_BLOCK, 0, s>>>(kin, vin, kout, vout, cnt, 8 * p, w.hist.p + p * RADIX, w.ticket, w.status.p, w.epoch, w.err_flag);
+        k_radix_pass<<<ntiles, SORT_BLOCK, 0, s>>>(kin, vin, kout, vout, cnt, 8 * p, w.hist.p + p * RADIX, w.ticket, w.status.p, w.err_flag);
         unsigned* t = kin; kin = kout; kout = t;
         vin = vout; vout = (vin == w.vals_a.p) ? w.vals_b.p : w.vals_a.p;
     }
