@@ -334,8 +334,13 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     # queries: column-shifted noisy copies of entries of the first 2000 global rows (+ fresh ones); identical on every rank
     sample = synth.sc_descriptors(min(K, 2000), first=0)
     ops = GpuOps(ctx, off, torch)
-    search = ShardedScanContextSearch(ops, rank, world, dist)
+    search = ShardedScanContextSearch(ops, rank, world, dist)      # world == 1: plain local search (no exchange at all)
     dev = ops.dev
+    peer = None
+    if world > 1:                                                  # exchange through NVLink peer windows (csrc/sc_shard.cuh), no NCCL inside a batch
+        from liorf_b200.sc_sharded import PeerShardedSearch
+        peer = PeerShardedSearch(ctx, rank, world, off, max(Q, q_large), torch)
+        peer.connect_processes(dist)
 
     def run(Qn, reps_n):
         qd, src, shift = synth.sc_queries(sample, Qn)
@@ -343,6 +348,8 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
             d_q = torch.from_numpy(qd).to(dev)
 
         def one():
+            if peer is not None:
+                return peer.query(d_q)
             with torch.cuda.stream(ops.stream):
                 return search.query(ops.prepare_dev(d_q))
         for _ in range(3):
@@ -373,6 +380,7 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
         res = dict(K=K, Q=Qn, shards=world, ms_per_batch=ms / reps_n, queries_per_s=Qn * reps_n / (ms * 1e-3),
                    planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((shn[ok] == shift[ok]).sum()),
                    ringkey_path="tcgen05 filter + exact re-rank" if tm["sc_gemm"][1] > 0 else "cuda-core brute force",
+                   exchange=("NVLink peer windows (push + flags from the kernels, 3 phases per batch), no NCCL" if peer is not None else "none (one shard)"),
                    ringkey_stage_ms=tm["sc_search"][0] / max(tm["sc_search"][1], 1), candidates_per_query=st["candidates"] / max(Qn, 1) * 32,
                    overflow_queries=st["overflow"],
                    roofline=dict(kernel="k_sc_tensor", bound="tensor", achieved=tflops, peak=peaks.get("bf16_tflops"), unit="TFLOP/s",

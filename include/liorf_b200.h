@@ -194,6 +194,25 @@ int liorf_sc_tensor_dump(liorf_ctx* ctx, const float* qkeys, int Q, float* out, 
 /* single-GPU convenience with host buffers: descriptors of the Q queries → loop ids / shifts / distances */
 int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
 
+/* ---- database sharded across GPUs, exchanged through NVLink peer memory (BASELINE config 5) -----------------
+ * Rank g holds rows [g K/G, (g+1) K/G) of the SCManager database (polarcontexts_ / polarcontext_invkeys_mat_,
+ * include/Scancontext.h:104-108); queries are replicated.  Each rank owns an exchange window that every peer maps; the
+ * kernels of a batch push their per-query results (candidate-threshold bounds, local top-3, owner-computed
+ * distanceBtnScanContext values) into all windows over NVLink and wait on flags in their own window — no NCCL call and no
+ * host round trip inside a batch (csrc/sc_shard.cuh).  Exactly the global top-3 ring-key candidates are evaluated
+ * (include/Scancontext.cpp:289-317), so loop ids / shifts / distances equal the unsharded search bit for bit.
+ *   liorf_sc_shard_init    : allocate this rank's window for batches of up to q_max queries; returns its cudaIpc handle
+ *                            (64 bytes, for peers in other processes) and / or its device pointer (peers in this process)
+ *   liorf_sc_shard_connect : map the peers' windows (array of `world` handles or pointers, own entry ignored)
+ *   liorf_sc_shard_query_dev: one batch, asynchronous on the context's stream; every rank passes the same queries in the same order;
+ *                            global_offset = index of this rank's first database row */
+int liorf_sc_shard_init(liorf_ctx* ctx, int rank, int world, int q_max, void* ipc_handle_out, void** window_out);
+int liorf_sc_shard_connect(liorf_ctx* ctx, const void* ipc_handles, void* const* window_ptrs);
+int liorf_sc_shard_query_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand);
+/* the same batch enqueued in steps (bit 0: up to the first push, 1: global threshold .. local top-3 push, 2: merge .. distance push, 3: decision) so that
+ * several ranks sharing ONE device (tests) can interleave their steps and never wait on work that has not been enqueued yet */
+int liorf_sc_shard_query_phases_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases);
+
 /* ---- loop-closure registration ------------------------------------------------------------------- */
 /* The ICP of mapOptimization::performSCLoopClosure (src/mapOptmization.cpp:624-730) without the factor graph:
  * cureKeyframeCloud = loopFindNearKeyframes(loop_key_cur, 0, loop_index), prevKeyframeCloud = loopFindNearKeyframes(loop_key_pre,

@@ -2,6 +2,7 @@
 // One translation unit; every kernel lives in the .cuh files next to this one.  Built with
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 #include <map>
+#include <algorithm>
 #include "../../include/liorf_b200.h"
 #include "common.cuh"
 #include "prims.cuh"
@@ -11,6 +12,7 @@
 #include "deskew.cuh"
 #include "scancontext.cuh"
 #include "sc_tensor.cuh"
+#include "sc_shard.cuh"
 #include "icp.cuh"
 #include "../host/host_logic.hpp"
 #include <vector>
@@ -96,6 +98,9 @@ struct liorf_ctx {
     DevBuf<float4> icp_raw, icp_src, icp_src0, icp_tgt; MapGrid icp_grid; DevBuf<double> icp_partial; double* icp_out = nullptr; int* icp_counter = nullptr;
     DevBuf<KfSel> icp_sel; DevBuf<int> icp_nn_idx; DevBuf<float> icp_nn_d2;
     liorf_guess_state guess_state = {}; float tf_mapped[6] = {0, 0, 0, 0, 0, 0};   // updateInitialGuess statics + transformTobeMapped
+    // sharded search over peer windows (sc_shard.cuh)
+    struct ScShard { bool ready = false; ShardWin W; int qmax = 0; size_t win_bytes = 0; unsigned batch = 0; unsigned* d_counter = nullptr; bool ipc_opened[SCSH_MAX] = {false};
+                     DevBuf<float> u3, thr; DevBuf<unsigned> packC, packD; } shard;
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
     bool sct_attr_set = false; int sct_last_Q = 0;
     Profiler prof;
@@ -389,6 +394,13 @@ void liorf_destroy(liorf_ctx* c) {
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); cudaFree(c->d_s2m_arrive); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
+    {   // peer windows
+        liorf_ctx::ScShard& S = c->shard;
+        for (int g = 0; g < SCSH_MAX; ++g) if (S.ipc_opened[g]) cudaIpcCloseMemHandle(S.W.base[g]);
+        if (S.W.base[S.W.rank]) cudaFree(S.W.base[S.W.rank]);
+        if (S.d_counter) cudaFree(S.d_counter);
+        S.u3.release(); S.thr.release(); S.packC.release(); S.packD.release();
+    }
     if (c->d_dbg_gt) cudaFree(c->d_dbg_gt);
     if (c->h_sel) cudaFreeHost(c->h_sel);
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (c->stage_ev[a][b]) cudaEventDestroy(c->stage_ev[a][b]);
@@ -1036,23 +1048,42 @@ static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, Sc
     return LIORF_OK;
 }
 
-static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
+// shard_phase: 0 = unsharded search; sharded search (sc_shard.cuh): 1 = images + GEMM + local bounds + push (phase T),
+// 2 = global threshold + select + exact re-rank
+static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx, int shard_phase = 0) {
     int rc, grid;
     SctArgs a;
     ProfScope ps(c, SEC_SC_SEARCH);
-    if ((rc = sct_prepare(c, n_keys, d_qkeys, Q, a, grid))) return rc;
-    const int rows = a.n_sqt * SCT_QT;
-    CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
-    { ProfScope pg(c, SEC_SC_GEMM); k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a); }
-    CUDA_TRY(cudaMemsetAsync(c->sct_cnt.p, 0, (size_t)Q * sizeof(int), c->stream));
-    k_sct_top3<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, a.nkt, rows, c->sct_part.p);
-    k_sct_select<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, c->sct_cmin32.p, a.nkt, rows, c->sct_part.p, c->sct_qnorm.p, Q, c->sct_nmax,
-                                                                                 c->sct_cand.p, c->sct_cnt.p);
-    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, a.nkt, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p,
+    const int nkt = (n_keys + SCT_KT - 1) / SCT_KT, rows = ((Q + SCT_QT - 1) / SCT_QT) * SCT_QT;
+    liorf_ctx::ScShard& S = c->shard;
+    if (shard_phase != 2) {
+        if ((rc = sct_prepare(c, n_keys, d_qkeys, Q, a, grid))) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
+        { ProfScope pg(c, SEC_SC_GEMM); k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a); }
+        CUDA_TRY(cudaMemsetAsync(c->sct_cnt.p, 0, (size_t)Q * sizeof(int), c->stream));
+        k_sct_top3<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, nkt, rows, c->sct_part.p);
+        c->launches += 3;
+        if (shard_phase == 1) {      // phase T: this rank's inflated top-3 tile minima go to every window
+            if ((rc = S.u3.reserve((size_t)3 * Q)) || (rc = S.thr.reserve(Q))) return rc;
+            k_scsh_u3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sct_part.p, rows, c->sct_qnorm.p, Q, c->sct_nmax, S.u3.p);
+            k_scsh_push<<<std::min(64, (3 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_T, reinterpret_cast<const unsigned*>(S.u3.p), (size_t)3 * Q, S.batch, S.d_counter);
+            CUDA_TRY(cudaGetLastError());
+            c->launches += 2;
+            return LIORF_OK;
+        }
+    }
+    const float* thr_in = nullptr;
+    if (shard_phase == 2) {          // every rank's bounds → the global candidate threshold
+        k_scsh_thr<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.batch, c->sct_qnorm.p, Q, c->sct_nmax, S.thr.p, c->d_err);
+        thr_in = S.thr.p; c->launches += 1;
+    }
+    k_sct_select<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, c->sct_cmin32.p, nkt, rows, c->sct_part.p, c->sct_qnorm.p, Q, c->sct_nmax,
+                                                                                 c->sct_cand.p, c->sct_cnt.p, thr_in);
+    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, nkt, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p,
                                                      c->sct_over_cnt);
     k_sc_knn_overflow<<<64, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, global_offset, d_qkeys, c->sct_over.p, c->sct_over_cnt, d_dist, d_idx);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 5; c->sct_last_Q = Q;
+    c->launches += 3; c->sct_last_Q = Q;
     return LIORF_OK;
 }
 
@@ -1219,6 +1250,100 @@ int liorf_sc_query_batch(liorf_ctx* c, const double* qdescs, int Q, int* loop_id
     CUDA_TRY(cudaMemcpyAsync(dist, c->sc_res_d.p, (size_t)Q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (cand3) CUDA_TRY(cudaMemcpyAsync(cand3, c->sc_q_i.p, (size_t)3 * Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     return check_err(c);
+}
+
+// ---- sharded search over NVLink peer windows (sc_shard.cuh) ----
+static size_t scsh_round(size_t b) { return (b + 255) / 256 * 256; }
+int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, void* ipc_handle_out /*64 B, nullable*/, void** window_out /*nullable*/) {
+    if (!c || world < 1 || world > SCSH_MAX || rank < 0 || rank >= world || q_max < 1) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    liorf_ctx::ScShard& S = c->shard;
+    if (S.ready) return LIORF_ERR_STATE;
+    std::memset(&S.W, 0, sizeof(S.W));
+    S.W.rank = rank; S.W.world = world; S.qmax = q_max;
+    const size_t flags = scsh_round((size_t)world * 4 * sizeof(unsigned));
+    S.W.stride[SCSH_T] = scsh_round((size_t)q_max * 12); S.W.stride[SCSH_C] = scsh_round((size_t)q_max * 24); S.W.stride[SCSH_D] = scsh_round((size_t)q_max * 36);
+    S.W.off[SCSH_T] = flags; S.W.off[SCSH_C] = S.W.off[SCSH_T] + world * S.W.stride[SCSH_T]; S.W.off[SCSH_D] = S.W.off[SCSH_C] + world * S.W.stride[SCSH_C];
+    S.win_bytes = S.W.off[SCSH_D] + world * S.W.stride[SCSH_D];
+    unsigned char* win = nullptr;
+    CUDA_TRY(cudaMalloc(&win, S.win_bytes));
+    CUDA_TRY(cudaMemset(win, 0, S.win_bytes));
+    CUDA_TRY(cudaMalloc(&S.d_counter, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(S.d_counter, 0, sizeof(unsigned)));
+    S.W.base[rank] = win;
+    if (ipc_handle_out) { cudaIpcMemHandle_t h; CUDA_TRY(cudaIpcGetMemHandle(&h, win)); static_assert(sizeof(h) == 64, "ipc handle"); std::memcpy(ipc_handle_out, &h, 64); }
+    if (window_out) *window_out = win;
+    S.batch = 0;
+    return LIORF_OK;
+}
+int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B, nullable*/, void* const* window_ptrs /*world entries, nullable*/) {
+    if (!c || (!ipc_handles && !window_ptrs)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    liorf_ctx::ScShard& S = c->shard;
+    if (!S.W.base[S.W.rank] || S.ready) return LIORF_ERR_STATE;
+    for (int g = 0; g < S.W.world; ++g) {
+        if (g == S.W.rank) continue;
+        if (window_ptrs) S.W.base[g] = (unsigned char*)window_ptrs[g];               // same process: the peer context's pointer is directly usable
+        else {
+            cudaIpcMemHandle_t h; std::memcpy(&h, (const unsigned char*)ipc_handles + (size_t)64 * g, 64);
+            void* p = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            S.W.base[g] = (unsigned char*)p; S.ipc_opened[g] = true;
+        }
+        if (!S.W.base[g]) return LIORF_ERR_ARG;
+    }
+    S.ready = true;
+    return LIORF_OK;
+}
+/* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
+ * with the SAME queries in the same order. */
+int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases) {
+    if (!c || !d_qdescs || Q < 1 || !d_loop_id || !d_shift || !d_dist || !(phases & 15)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    liorf_ctx::ScShard& S = c->shard;
+    if (!S.ready || Q > S.qmax) return LIORF_ERR_STATE;
+    if (c->sc_n < 1) return LIORF_ERR_STATE;
+    int rc;
+    if ((rc = c->sc_qsk.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qcn.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qkeys.reserve((size_t)Q * SC_RING)) ||
+        (rc = sc_reserve_query(c, Q)) || (rc = S.packC.reserve((size_t)6 * Q)) || (rc = S.packD.reserve((size_t)9 * Q + 1))) return rc;
+    const double* qd = (const double*)d_qdescs;
+    float* ld = reinterpret_cast<float*>(S.packC.p); int* li = reinterpret_cast<int*>(S.packC.p) + (size_t)3 * Q;
+    double* pd = reinterpret_cast<double*>(S.packD.p); int* psh = reinterpret_cast<int*>(S.packD.p) + (size_t)6 * Q;
+    int* cand = d_cand ? (int*)d_cand : c->sc_q_i.p;
+    const int pairs = 3 * Q;
+    const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && c->sc_n >= 4096);
+    if (phases & 1) {        // keys, stage-1 filter, push of the threshold bounds (tensor path) or of the exact local top-3 (CUDA-core path)
+        ++S.batch;
+        if ((rc = liorf_sc_prepare_queries_dev(c, qd, Q, c->sc_qkeys.p, c->sc_qsk.p, c->sc_qcn.p))) return rc;
+        if (want_tensor) { if ((rc = sc_knn_tensor(c, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li, 1))) return rc; }
+        else {
+            if ((rc = sc_knn_brute(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li))) return rc;
+            k_scsh_push<<<std::min(64, (6 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_C, S.packC.p, (size_t)6 * Q, S.batch, S.d_counter);
+        }
+    }
+    if (phases & 2) {        // global threshold → select → exact re-rank → push of the exact local top-3
+        if (want_tensor) {
+            if ((rc = sc_knn_tensor(c, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li, 2))) return rc;
+            k_scsh_push<<<std::min(64, (6 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_C, S.packC.p, (size_t)6 * Q, S.batch, S.d_counter);
+        }
+    }
+    if (phases & 4) {        // merge to the global top-3, owner-computes distanceBtnScanContext, push
+        k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.batch, Q, c->sc_q_d.p, cand, c->d_err);
+        k_scsh_fill_pairs<<<(pairs + 255) / 256, 256, 0, c->stream>>>(pd, psh, pairs);
+        k_sc_distance<<<(pairs + SCD_WARPS - 1) / SCD_WARPS, SCD_WARPS * 32, 0, c->stream>>>(qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p,
+                                                                                             c->sc_cn.p, global_offset, c->sc_n, pd, psh);
+        k_scsh_push<<<std::min(64, (9 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_D, S.packD.p, (size_t)9 * Q, S.batch, S.d_counter);
+    }
+    if (phases & 8)          // owner pick + decision
+        k_scsh_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.batch, cand, Q, (int*)d_loop_id, (int*)d_shift, (double*)d_dist, c->d_err);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 7;
+    return LIORF_OK;
+}
+/* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
+ * with the SAME queries in the same order. */
+int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand) {
+    return liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 15);
 }
 
 int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3) {

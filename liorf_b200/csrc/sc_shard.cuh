@@ -1,0 +1,148 @@
+// sc_shard.cuh — ScanContext search over a keyframe database sharded across GPUs, exchanged through NVLink PEER MEMORY.
+// (SURVEY §8e / BASELINE config 5: rows [g K/G, (g+1) K/G) of the database on rank g, queries replicated.)
+//
+// Every rank owns an exchange WINDOW in its HBM that all peers map (cudaIpc across processes, plain pointers inside one).
+// A phase's producer kernel PUSHES its small per-query result into slot [my rank] of every rank's window with ordinary
+// stores over NVLink, fences at system scope and raises flag[my rank][phase] = batch number in every window; the consumer
+// kernel of that phase spins on its OWN window's flags (local L2 reads) before it touches the slots.  No NCCL call, no host
+// round trip, no collective launch: a batch is one stream of kernels per rank, and the transfer of a phase overlaps whatever
+// the peers are still computing.
+//
+//   phase T: the three smallest tile minima of the tensor-core filter per query, each inflated by this rank's error bound, so
+//            that every rank can derive the GLOBAL candidate threshold (a rank that only knew its local third-smallest value
+//            would re-rank ~100 candidates per query whatever the shard size; with the global bound the re-rank work shards too)
+//   phase C: exact local top-3 {f32 dist, i32 global idx} → every rank merges the G lists by (dist, idx): identical global top-3
+//   phase D: distanceBtnScanContext of the candidates THIS rank owns {f64 dist, i32 shift}, +inf elsewhere → owner pick + decision
+// Exactly the global top-3 are evaluated, so results equal the unsharded search bit for bit (tests/test_gpu_sc_shard.py).
+//
+// Reuse without double buffering is safe: a rank enters phase p of batch b+1 only after it has consumed phase D of batch b,
+// which needs every rank's phase-D push, which each rank issues after it has finished reading phases T and C of batch b.
+#pragma once
+#include "sc_tensor.cuh"
+
+namespace liorf {
+
+constexpr int SCSH_MAX = 16;                 // ranks
+enum { SCSH_T = 0, SCSH_C = 1, SCSH_D = 2 };
+
+struct ShardWin {                            // passed by value to the kernels
+    unsigned char* base[SCSH_MAX];           // window of every rank as mapped into THIS process (base[rank] = own)
+    int rank, world;
+    unsigned long long off[3], stride[3];    // byte offset of a phase's region inside a window, byte stride between source slots
+};
+__host__ __device__ __forceinline__ size_t scsh_flag_off(int src, int phase) { return ((size_t)src * 4 + phase) * sizeof(unsigned); }
+
+// consumer side: thread 0 waits until every peer's flag of `phase` has reached `batch` (own window, acquire at system scope)
+__device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, unsigned batch, int* err_flag) {
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < W.world; ++g) {
+            if (g == W.rank) continue;
+            const unsigned* f = reinterpret_cast<const unsigned*>(W.base[W.rank] + scsh_flag_off(g, phase));
+            unsigned v, spins = 0;
+            while (true) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if ((int)(v - batch) >= 0) break;
+                if (++spins > (1u << 22)) { atomicExch(err_flag, 3); break; }      // ~seconds: a peer that never arrives is an error, not a hang
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// producer side: copy `words` 32-bit words from src into slot [my rank] of every window, then (last block) raise the flags
+__global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const unsigned* __restrict__ src, size_t words, unsigned batch, unsigned* counter) {
+    const size_t slot = W.off[phase] + (size_t)W.rank * W.stride[phase];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned v = src[i];
+        for (int g = 0; g < W.world; ++g) reinterpret_cast<unsigned*>(W.base[g] + slot)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) { const unsigned t = atomicAdd(counter, 1u); s_last = (t == gridDim.x - 1); }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *counter = 0u;
+    __threadfence_system();
+    if ((int)threadIdx.x < W.world && (int)threadIdx.x != W.rank) {
+        unsigned* f = reinterpret_cast<unsigned*>(W.base[threadIdx.x] + scsh_flag_off(W.rank, phase));
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(batch) : "memory");
+    }
+}
+
+// phase T producer: merge the per-split partial top-3 tile minima of a query and inflate them by this rank's error bound:
+// u_j = m_j + eps_r(q) is an upper bound of the TRUE distance of a distinct database key
+__global__ void __launch_bounds__(128) k_scsh_u3(const float* __restrict__ part, int n_rows, const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
+                                                float* __restrict__ u3) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
+#pragma unroll
+    for (int sp = 0; sp < SCS_SPLITS; ++sp) {
+        const float* p = part + ((size_t)sp * n_rows + q) * 3;
+        top3_min_update(p[0], t1, t2, t3); top3_min_update(p[1], t1, t2, t3); top3_min_update(p[2], t1, t2, t3);
+    }
+    const float eps = SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits));
+    u3[3 * (size_t)q + 0] = t1 < 1.0e38f ? t1 + eps : 3.0e38f;
+    u3[3 * (size_t)q + 1] = t2 < 1.0e38f ? t2 + eps : 3.0e38f;
+    u3[3 * (size_t)q + 2] = t3 < 1.0e38f ? t3 + eps : 3.0e38f;
+}
+// phase T consumer: U3(q) = third smallest over all ranks' bounds >= the true global third-smallest distance d3; a key of THIS
+// rank in the global top-3 has d~ <= d + eps_r <= d3 + eps_r <= U3 + eps_r =: thr(q)
+__global__ void __launch_bounds__(128) k_scsh_thr(ShardWin W, unsigned batch, const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
+                                                 float* __restrict__ thr, int* err_flag) {
+    scsh_wait(W, SCSH_T, batch, err_flag);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
+    for (int g = 0; g < W.world; ++g) {
+        const float* p = reinterpret_cast<const float*>(W.base[W.rank] + W.off[SCSH_T] + (size_t)g * W.stride[SCSH_T]) + 3 * (size_t)q;
+        top3_min_update(__ldcg(p), t1, t2, t3); top3_min_update(__ldcg(p + 1), t1, t2, t3); top3_min_update(__ldcg(p + 2), t1, t2, t3);
+    }
+    const float eps = SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits));
+    thr[q] = t3 < 1.0e38f ? t3 + eps : 3.0e38f;
+}
+
+// phase C consumer: the G local top-3 lists → global top-3 by (dist, idx)   [same arithmetic as k_sc_merge_top3]
+__global__ void __launch_bounds__(128) k_scsh_merge(ShardWin W, unsigned batch, int Q, float* __restrict__ out_d, int* __restrict__ out_i, int* err_flag) {
+    scsh_wait(W, SCSH_C, batch, err_flag);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    Top3 t; top3_init(t);
+    for (int g = 0; g < W.world; ++g) {
+        const float* pd = reinterpret_cast<const float*>(W.base[W.rank] + W.off[SCSH_C] + (size_t)g * W.stride[SCSH_C]);
+        const int* pi = reinterpret_cast<const int*>(pd + 3 * (size_t)Q);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const int i = __ldcg(pi + 3 * (size_t)q + j); if (i != 0x7fffffff) top3_insert(t, __ldcg(pd + 3 * (size_t)q + j), i); }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { out_d[3 * (size_t)q + j] = t.d[j]; out_i[3 * (size_t)q + j] = t.i[j]; }
+}
+
+__global__ void __launch_bounds__(256) k_scsh_fill_pairs(double* __restrict__ pd, int* __restrict__ ps, int n_pairs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pairs) { pd[i] = INFINITY; ps[i] = 0; }
+}
+
+// phase D consumer: owner pick per (query, candidate) pair, then the decision of detectLoopClosureID (:302-340)
+__global__ void __launch_bounds__(128) k_scsh_decide(ShardWin W, unsigned batch, const int* __restrict__ cand, int Q, int* __restrict__ loop_id, int* __restrict__ shift,
+                                                    double* __restrict__ dist, int* err_flag) {
+    scsh_wait(W, SCSH_D, batch, err_flag);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    double mn = 10000000.0; int al = 0, nn = 0;
+#pragma unroll
+    for (int c = 0; c < SC_NUM_CAND; ++c) {
+        const size_t i = 3 * (size_t)q + c;
+        double d = INFINITY; int sh = 0;
+        for (int g = 0; g < W.world; ++g) {
+            const unsigned char* slot = W.base[W.rank] + W.off[SCSH_D] + (size_t)g * W.stride[SCSH_D];
+            const double dp = __ldcg(reinterpret_cast<const double*>(slot) + i);
+            if (dp != INFINITY) { d = dp; sh = __ldcg(reinterpret_cast<const int*>(slot + (size_t)3 * Q * 8) + i); break; }   // NaN != inf: an owner's NaN is kept
+        }
+        if (d < mn) { mn = d; al = sh; nn = cand[i]; }
+    }
+    loop_id[q] = mn < SC_DIST_THRES ? nn : -1; shift[q] = al; dist[q] = mn;
+}
+
+}  // namespace liorf

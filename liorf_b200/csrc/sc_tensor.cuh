@@ -420,17 +420,21 @@ __device__ __forceinline__ void sct_emit_tile(const float* __restrict__ cmin32, 
 }
 __global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __restrict__ cmin, const float* __restrict__ cmin32, int n_chunks, int n_rows, const float* __restrict__ part,
                                                                const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
-                                                               int* __restrict__ cand, int* __restrict__ cand_cnt) {
+                                                               int* __restrict__ cand, int* __restrict__ cand_cnt, const float* __restrict__ thr_in = nullptr) {
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane;
     if (q >= Q) return;
-    float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
+    float thr;
+    if (thr_in) thr = thr_in[q];                     // sharded search: the threshold derived from every rank's bounds (sc_shard.cuh)
+    else {
+        float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
 #pragma unroll
-    for (int sp = 0; sp < SCS_SPLITS; ++sp) {
-        const float* p = part + ((size_t)sp * n_rows + q) * 3;
-        top3_min_update(p[0], t1, t2, t3); top3_min_update(p[1], t1, t2, t3); top3_min_update(p[2], t1, t2, t3);
+        for (int sp = 0; sp < SCS_SPLITS; ++sp) {
+            const float* p = part + ((size_t)sp * n_rows + q) * 3;
+            top3_min_update(p[0], t1, t2, t3); top3_min_update(p[1], t1, t2, t3); top3_min_update(p[2], t1, t2, t3);
+        }
+        thr = t3 < 1.0e38f ? t3 + 2.f * SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits)) : 3.0e38f;
     }
-    const float thr = t3 < 1.0e38f ? t3 + 2.f * SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits)) : 3.0e38f;
     const float* col = cmin + q;
     int c0, c1; scs_range(n_chunks, c0, c1);
     int ch = c0 + sl;

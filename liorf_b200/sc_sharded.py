@@ -199,3 +199,58 @@ class GpuOps(TorchPacking):
             pd = self._buf("cmb_d", (Q, 3), t.float64); ps = self._buf("cmb_s", (Q, 3), t.int32)
             self.ctx.lib.liorf_sc_combine_pairs_dev(self.ctx.h, self._vp(g), world, C.c_longlong(stride), Q, self._vp(pd), self._vp(ps))
         return pd, ps
+
+
+class PeerShardedSearch:
+    """The same sharded search with the exchange done by the library's own kernels over NVLink PEER MEMORY
+    (csrc/sc_shard.cuh, liorf_sc_shard_*): every rank owns a window that all peers map, producers push and raise flags,
+    consumers spin on their own window.  One library call per batch, no collective launch, no host round trip.
+    torch.distributed is used once, to hand the 64-byte cudaIpc handles around."""
+
+    def __init__(self, ctx, rank, world, global_offset, q_max, torch):
+        self.ctx, self.rank, self.world, self.off, self.q_max, self.torch = ctx, rank, world, int(global_offset), int(q_max), torch
+        self.dev = torch.device(f"cuda:{ctx.params.device}")
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.dev)
+        self.handle = (C.c_ubyte * 64)()
+        self.window = C.c_void_p()
+        rc = ctx.lib.liorf_sc_shard_init(ctx.h, C.c_int(rank), C.c_int(world), C.c_int(self.q_max), self.handle, C.byref(self.window))
+        if rc < 0:
+            raise RuntimeError(f"liorf_sc_shard_init failed with code {rc}")
+        self._out = {}
+
+    def connect_processes(self, dist):
+        """peers live in other processes (one per GPU): exchange the cudaIpc handles, map the windows"""
+        if self.world > 1:
+            hs = [None] * self.world
+            dist.all_gather_object(hs, bytes(self.handle))
+            buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(hs))
+            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, buf, None)
+        else:
+            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, self.handle, None)
+        if rc < 0:
+            raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
+        if self.world > 1:
+            dist.barrier()
+
+    def connect_local(self, searches):
+        """peers are other contexts of THIS process (tests: several shards on one GPU)"""
+        ptrs = (C.c_void_p * self.world)(*[s.window.value for s in searches])
+        rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, None, ptrs)
+        if rc < 0:
+            raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
+
+    def query(self, d_q, phases=15):
+        """d_q: (Q, 1200) float64 query descriptors on this rank's device (the same on every rank).  Asynchronous on the context's
+        stream.  Returns (loop_id, shift, dist, cand) device tensors.  phases: bit mask of the batch's four steps (tests that put
+        several ranks on one device enqueue step by step over the ranks; a real rank passes 15)."""
+        t = self.torch
+        Q = int(d_q.shape[0])
+        o = self._out.get(Q)
+        if o is None:
+            o = self._out[Q] = (t.empty(Q, dtype=t.int32, device=self.dev), t.empty(Q, dtype=t.int32, device=self.dev),
+                                t.empty(Q, dtype=t.float64, device=self.dev), t.empty((Q, 3), dtype=t.int32, device=self.dev))
+        rc = self.ctx.lib.liorf_sc_shard_query_phases_dev(self.ctx.h, C.c_void_p(d_q.data_ptr()), C.c_int(Q), C.c_int(self.off), C.c_void_p(o[0].data_ptr()),
+                                                          C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr()), C.c_void_p(o[3].data_ptr()), C.c_int(phases))
+        if rc < 0:
+            raise RuntimeError(f"liorf_sc_shard_query_dev failed with code {rc}")
+        return o
