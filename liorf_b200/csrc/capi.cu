@@ -13,6 +13,7 @@
 #include "scancontext.cuh"
 #include "sc_tensor.cuh"
 #include "sc_shard.cuh"
+#include "sc_distance.cuh"
 #include "icp.cuh"
 #include "../host/host_logic.hpp"
 #include <vector>
@@ -102,7 +103,7 @@ struct liorf_ctx {
     struct ScShard { bool ready = false; ShardWin W; int qmax = 0; size_t win_bytes = 0; unsigned batch = 0; unsigned* d_counter = nullptr; bool ipc_opened[SCSH_MAX] = {false};
                      DevBuf<float> u3, thr; DevBuf<unsigned> packC, packD; } shard;
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
-    bool sct_attr_set = false; int sct_last_Q = 0;
+    bool sct_attr_set = false; int sct_last_Q = 0; bool scdb_attr_set = false; int scdb_blocks_per_sm = 1;
     Profiler prof;
     double host_us[6] = {0, 0, 0, 0, 0, 0}; long long host_frames = 0; bool host_timing = false;   // LIORF_HOST_TIMING=1
     cudaEvent_t tl_ev[8] = {nullptr}; double tl_ms[8] = {0}; // debug GPU timeline stamps of process_frame
@@ -1097,6 +1098,23 @@ static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_
     return sc_knn_brute(c, d_keys, n_keys, d_qkeys, Q, global_offset, d_dist, d_idx);
 }
 
+// stage 2 for a batch of (query, candidate) pairs: TMA-staged kernel (sc_distance.cuh), persistent warps over the pairs
+static int sc_distance_launch(liorf_ctx* c, const double* qd, const double* qsk, const double* qcn, const int* cand, int pairs, int global_offset, double* pd, int* ps) {
+    if (!c->scdb_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_sc_distance_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SCDB_SMEM));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sc_distance_bulk, SCDB_WARPS * 32, SCDB_SMEM));
+        c->scdb_blocks_per_sm = occ > 0 ? occ : 1; c->scdb_attr_set = true;
+    }
+    int blocks = (pairs + SCDB_WARPS - 1) / SCDB_WARPS;
+    const int cap = c->num_sms * c->scdb_blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    k_sc_distance_bulk<<<blocks, SCDB_WARPS * 32, SCDB_SMEM, c->stream>>>(qd, qsk, qcn, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n,
+                                                                          pd, ps, c->d_err);
+    CUDA_TRY(cudaGetLastError());
+    return LIORF_OK;
+}
+
 int liorf_sc_knn_batch_dev(liorf_ctx* c, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx) {
     if (!c || Q < 0 || !d_qkeys || !d_dist || !d_idx) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
@@ -1141,10 +1159,8 @@ int liorf_sc_distance_batch_dev(liorf_ctx* c, const void* d_qdescs, const void* 
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
     const int pairs = Q * SC_NUM_CAND;
-    k_sc_distance<<<(pairs + SCD_WARPS - 1) / SCD_WARPS, SCD_WARPS * 32, 0, c->stream>>>((const double*)d_qdescs, (const double*)d_qsk, (const double*)d_qcn,
-        (const int*)d_cand_idx, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n, (double*)d_pair_dist, (int*)d_pair_shift);
-    CUDA_TRY(cudaGetLastError());
-    return LIORF_OK;
+    return sc_distance_launch(c, (const double*)d_qdescs, (const double*)d_qsk, (const double*)d_qcn, (const int*)d_cand_idx, pairs, global_offset, (double*)d_pair_dist,
+                              (int*)d_pair_shift);
 }
 int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q, void* d_loop_id, void* d_shift,
                         void* d_dist) {
@@ -1330,8 +1346,7 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     if (phases & 4) {        // merge to the global top-3, owner-computes distanceBtnScanContext, push
         k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.batch, Q, c->sc_q_d.p, cand, c->d_err);
         k_scsh_fill_pairs<<<(pairs + 255) / 256, 256, 0, c->stream>>>(pd, psh, pairs);
-        k_sc_distance<<<(pairs + SCD_WARPS - 1) / SCD_WARPS, SCD_WARPS * 32, 0, c->stream>>>(qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p,
-                                                                                             c->sc_cn.p, global_offset, c->sc_n, pd, psh);
+        if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, pd, psh))) return rc;
         k_scsh_push<<<std::min(64, (9 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_D, S.packD.p, (size_t)9 * Q, S.batch, S.d_counter);
     }
     if (phases & 8)          // owner pick + decision
