@@ -209,7 +209,8 @@ int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_
 int liorf_sc_shard_init(liorf_ctx* ctx, int rank, int world, int q_max, void* ipc_handle_out, void** window_out);
 int liorf_sc_shard_connect(liorf_ctx* ctx, const void* ipc_handles, void* const* window_ptrs);
 int liorf_sc_shard_query_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand);
-/* the same batch enqueued in steps (bit 0: up to the first push, 1: global threshold .. local top-3 push, 2: merge .. distance push, 3: decision) so that
+/* the same batch enqueued in steps (bit 4: ring keys of this rank's query slice + push, then bit 0: all keys .. threshold-bound push, 1: global threshold ..
+ * local top-3 push, 2: merge .. distance push, 3: decision; 31 = everything) so that
  * several ranks sharing ONE device (tests) can interleave their steps and never wait on work that has not been enqueued yet */
 int liorf_sc_shard_query_phases_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases);
 

@@ -781,7 +781,8 @@ int liorf_get_scan_ds(liorf_ctx* c, liorf_point* out, int capacity, int* n_ds) {
 static Count scan_ds_count(liorf_ctx* c) { return c->h_n_ds >= 0 ? Count::of_host(c->h_n_ds) : Count::of_dev(c->d_counts + C_N_DS, c->n_scan_bound); }
 static Count map_count(liorf_ctx* c) { return c->h_m_ds >= 0 ? Count::of_host(c->h_m_ds) : Count::of_dev(c->d_shared + C_M_DS, c->m_bound); }
 
-static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
+// pipelined: the call comes from liorf_process_frame, whose next frame's front end runs beside the solver → leave the spare SMs free
+static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined = false) {
     if (max_iters < 0) return LIORF_ERR_ARG;
     if (max_iters > S2M_MAX_ITERS) max_iters = S2M_MAX_ITERS;
     c->mail_fresh = false;
@@ -803,7 +804,7 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all) {
     a.mail = c->d_mail; a.cnt_n_scan = c->d_counts + C_N_SCAN;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(c->s2m_grid), dim3(S2MP_BLOCK), args, 0, c->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(pipelined ? c->s2m_grid : c->num_sms), dim3(S2MP_BLOCK), args, 0, c->stream));
     c->mail_fresh = true;
     return LIORF_OK;
 }
@@ -1280,7 +1281,8 @@ int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, void* ipc_
     const size_t flags = scsh_round((size_t)world * 4 * sizeof(unsigned));
     S.W.stride[SCSH_T] = scsh_round((size_t)q_max * 12); S.W.stride[SCSH_C] = scsh_round((size_t)q_max * 24); S.W.stride[SCSH_D] = scsh_round((size_t)q_max * 36);
     S.W.off[SCSH_T] = flags; S.W.off[SCSH_C] = S.W.off[SCSH_T] + world * S.W.stride[SCSH_T]; S.W.off[SCSH_D] = S.W.off[SCSH_C] + world * S.W.stride[SCSH_C];
-    S.win_bytes = S.W.off[SCSH_D] + world * S.W.stride[SCSH_D];
+    S.W.off[SCSH_K] = S.W.off[SCSH_D] + world * S.W.stride[SCSH_D]; S.W.stride[SCSH_K] = 0;      // one [q_max][20] f32 array, rank g fills the rows of its query slice
+    S.win_bytes = S.W.off[SCSH_K] + scsh_round((size_t)q_max * SC_RING * sizeof(float));
     unsigned char* win = nullptr;
     CUDA_TRY(cudaMalloc(&win, S.win_bytes));
     CUDA_TRY(cudaMemset(win, 0, S.win_bytes));
@@ -1314,7 +1316,7 @@ int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B,
 /* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
  * with the SAME queries in the same order. */
 int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases) {
-    if (!c || !d_qdescs || Q < 1 || !d_loop_id || !d_shift || !d_dist || !(phases & 15)) return LIORF_ERR_ARG;
+    if (!c || !d_qdescs || Q < 1 || !d_loop_id || !d_shift || !d_dist || !(phases & 31)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
     if (!S.ready || Q > S.qmax) return LIORF_ERR_STATE;
@@ -1328,9 +1330,16 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     int* cand = d_cand ? (int*)d_cand : c->sc_q_i.p;
     const int pairs = 3 * Q;
     const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && c->sc_n >= 4096);
-    if (phases & 1) {        // keys, stage-1 filter, push of the threshold bounds (tensor path) or of the exact local top-3 (CUDA-core path)
-        ++S.batch;
-        if ((rc = liorf_sc_prepare_queries_dev(c, qd, Q, c->sc_qkeys.p, c->sc_qsk.p, c->sc_qcn.p))) return rc;
+    if (phases & 16) {       // phase K: ring keys of this rank's slice of the queries → every window; the sector keys / column norms stage 2 needs
+        ++S.batch;           // are derived inside k_sc_distance_bulk for the pairs a rank owns
+        const int q0 = (int)((long long)Q * S.W.rank / S.W.world), q1 = (int)((long long)Q * (S.W.rank + 1) / S.W.world);
+        if (q1 > q0) k_sc_keys_batch<<<q1 - q0, 64, 0, c->stream>>>(qd + (size_t)q0 * SC_DESC, q1 - q0, c->sc_qkeys.p + (size_t)q0 * SC_RING, nullptr, nullptr);
+        const size_t words = (size_t)(q1 - q0) * SC_RING;
+        k_scsh_push<<<std::max(1, std::min(64, (int)((words + 255) / 256))), 256, 0, c->stream>>>(S.W, SCSH_K, reinterpret_cast<const unsigned*>(c->sc_qkeys.p + (size_t)q0 * SC_RING),
+                                                                                             words, S.batch, S.d_counter, (size_t)q0 * SC_RING * sizeof(float));
+    }
+    if (phases & 1) {        // all ring keys, stage-1 filter, push of the threshold bounds (tensor path) or of the exact local top-3 (CUDA-core path)
+        k_scsh_gather_keys<<<std::min(64, (Q * SC_RING + 255) / 256), 256, 0, c->stream>>>(S.W, S.batch, Q * SC_RING, reinterpret_cast<unsigned*>(c->sc_qkeys.p), c->d_err);
         if (want_tensor) { if ((rc = sc_knn_tensor(c, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li, 1))) return rc; }
         else {
             if ((rc = sc_knn_brute(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li))) return rc;
@@ -1346,6 +1355,7 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     if (phases & 4) {        // merge to the global top-3, owner-computes distanceBtnScanContext, push
         k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.batch, Q, c->sc_q_d.p, cand, c->d_err);
         k_scsh_fill_pairs<<<(pairs + 255) / 256, 256, 0, c->stream>>>(pd, psh, pairs);
+        k_scsh_skcn_owned<<<Q, 64, 0, c->stream>>>(qd, cand, Q, global_offset, c->sc_n, c->sc_qsk.p, c->sc_qcn.p);      // sector keys / column norms of the queries whose candidates this rank owns
         if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, pd, psh))) return rc;
         k_scsh_push<<<std::min(64, (9 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_D, S.packD.p, (size_t)9 * Q, S.batch, S.d_counter);
     }
@@ -1358,7 +1368,7 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
 /* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
  * with the SAME queries in the same order. */
 int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand) {
-    return liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 15);
+    return liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 31);
 }
 
 int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3) {
@@ -1622,7 +1632,7 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
         std::memcpy(guess, c->tf_mapped, sizeof(guess));
         liorf_host_update_initial_guess(&c->guess_state, c->kfs.empty() ? 1 : 0, &in->cloud_info, in->use_imu_heading_initialization, in->imu_type, guess);
     } else std::memcpy(guess, in->initial_guess, sizeof(guess));
-    if ((rc = liorf_scan2map_optimization_async(c, guess, in->max_iters > 0 ? in->max_iters : 30, 0))) return rc;
+    if ((rc = upload_pose(c, guess)) || (rc = launch_s2m(c, in->max_iters > 0 ? in->max_iters : 30, 0, true))) return rc;
     stamp(5, c->stream);
     // the NEXT frame's cloudHandler + downsample go to stream_pre now, behind this frame's critical chain in host order, and run
     // on the device while the solver iterates (the reference runs imageProjection and mapOptimization as two concurrent nodes)

@@ -8,6 +8,7 @@
 // round trip, no collective launch: a batch is one stream of kernels per rank, and the transfer of a phase overlaps whatever
 // the peers are still computing.
 //
+//   phase K: ring keys of this rank's SLICE of the queries (every rank would otherwise read all Q descriptors, 9.6 kB each, to derive them)
 //   phase T: the three smallest tile minima of the tensor-core filter per query, each inflated by this rank's error bound, so
 //            that every rank can derive the GLOBAL candidate threshold (a rank that only knew its local third-smallest value
 //            would re-rank ~100 candidates per query whatever the shard size; with the global bound the re-rank work shards too)
@@ -23,12 +24,12 @@
 namespace liorf {
 
 constexpr int SCSH_MAX = 16;                 // ranks
-enum { SCSH_T = 0, SCSH_C = 1, SCSH_D = 2 };
+enum { SCSH_T = 0, SCSH_C = 1, SCSH_D = 2, SCSH_K = 3 };
 
 struct ShardWin {                            // passed by value to the kernels
     unsigned char* base[SCSH_MAX];           // window of every rank as mapped into THIS process (base[rank] = own)
     int rank, world;
-    unsigned long long off[3], stride[3];    // byte offset of a phase's region inside a window, byte stride between source slots
+    unsigned long long off[4], stride[4];    // byte offset of a phase's region inside a window, byte stride between source slots (phase K: one shared array, stride 0)
 };
 __host__ __device__ __forceinline__ size_t scsh_flag_off(int src, int phase) { return ((size_t)src * 4 + phase) * sizeof(unsigned); }
 
@@ -50,8 +51,9 @@ __device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, unsigned
 }
 
 // producer side: copy `words` 32-bit words from src into slot [my rank] of every window, then (last block) raise the flags
-__global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const unsigned* __restrict__ src, size_t words, unsigned batch, unsigned* counter) {
-    const size_t slot = W.off[phase] + (size_t)W.rank * W.stride[phase];
+__global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const unsigned* __restrict__ src, size_t words, unsigned batch, unsigned* counter,
+                                                  size_t dst_byte_off = 0) {
+    const size_t slot = W.off[phase] + (size_t)W.rank * W.stride[phase] + dst_byte_off;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
         const unsigned v = src[i];
         for (int g = 0; g < W.world; ++g) reinterpret_cast<unsigned*>(W.base[g] + slot)[i] = v;
@@ -68,6 +70,13 @@ __global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const 
         unsigned* f = reinterpret_cast<unsigned*>(W.base[threadIdx.x] + scsh_flag_off(W.rank, phase));
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(batch) : "memory");
     }
+}
+
+// phase K consumer: the ring keys of all queries, derived slice by slice on the ranks, are complete in this window → contiguous copy
+__global__ void __launch_bounds__(256) k_scsh_gather_keys(ShardWin W, unsigned batch, int words, unsigned* __restrict__ dst, int* err_flag) {
+    scsh_wait(W, SCSH_K, batch, err_flag);
+    const unsigned* src = reinterpret_cast<const unsigned*>(W.base[W.rank] + W.off[SCSH_K]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) dst[i] = __ldcg(src + i);
 }
 
 // phase T producer: merge the per-split partial top-3 tile minima of a query and inflate them by this rank's error bound:
@@ -117,6 +126,24 @@ __global__ void __launch_bounds__(128) k_scsh_merge(ShardWin W, unsigned batch, 
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) { out_d[3 * (size_t)q + j] = t.d[j]; out_i[3 * (size_t)q + j] = t.i[j]; }
+}
+
+// sector key and column norms (k_sc_keys_batch arithmetic) of the queries that have at least one candidate in THIS rank's rows: the
+// other queries' descriptors (9.6 kB each) are never read here
+__global__ void __launch_bounds__(64) k_scsh_skcn_owned(const double* __restrict__ desc, const int* __restrict__ cand, int Q, int own_begin, int own_count,
+                                                        double* __restrict__ sectorkey, double* __restrict__ colnorm) {
+    const int e = blockIdx.x; if (e >= Q) return;
+    bool own = false;
+#pragma unroll
+    for (int j = 0; j < SC_NUM_CAND; ++j) { const int c = cand[3 * (size_t)e + j]; own |= (c != 0x7fffffff && c - own_begin >= 0 && c - own_begin < own_count); }
+    if (!own) return;
+    const int t = threadIdx.x;
+    if (t < SC_SECTOR) {
+        double s = 0, q = 0;
+        for (int r = 0; r < SC_RING; ++r) { const double v = desc[(size_t)e * SC_DESC + r * SC_SECTOR + t]; s += v; q += v * v; }
+        sectorkey[(size_t)e * SC_SECTOR + t] = s / SC_RING;
+        colnorm[(size_t)e * SC_SECTOR + t] = sqrt(q);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_scsh_fill_pairs(double* __restrict__ pd, int* __restrict__ ps, int n_pairs) {

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(64) k_sc_keys_batch(const double* __restrict__
     __syncthreads();
     const int t = threadIdx.x;
     if (t < SC_RING && ringkey) { double s = 0; for (int c = 0; c < SC_SECTOR; ++c) s += s_d[t * SC_SECTOR + c]; ringkey[(size_t)e * SC_RING + t] = (float)(s / SC_SECTOR); }
-    if (t < SC_SECTOR) {
+    if (t < SC_SECTOR && sectorkey) {
         double s = 0, q = 0;
         for (int r = 0; r < SC_RING; ++r) { double v = s_d[r * SC_SECTOR + t]; s += v; q += v * v; }
         sectorkey[(size_t)e * SC_SECTOR + t] = s / SC_RING;

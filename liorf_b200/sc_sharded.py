@@ -239,10 +239,10 @@ class PeerShardedSearch:
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
 
-    def query(self, d_q, phases=15):
+    def query(self, d_q, phases=31):
         """d_q: (Q, 1200) float64 query descriptors on this rank's device (the same on every rank).  Asynchronous on the context's
         stream.  Returns (loop_id, shift, dist, cand) device tensors.  phases: bit mask of the batch's four steps (tests that put
-        several ranks on one device enqueue step by step over the ranks; a real rank passes 15)."""
+        several ranks on one device enqueue step by step over the ranks; a real rank passes 31)."""
         t = self.torch
         Q = int(d_q.shape[0])
         o = self._out.get(Q)

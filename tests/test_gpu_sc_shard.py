@@ -38,7 +38,7 @@ def _run(synth, K, Q_list, world, path, bounds=None):
                 dq[g] = torch.from_numpy(qd).to(dev)
         # the ranks share ONE device here: enqueue step by step over the ranks, so that a kernel that waits for a peer's push is
         # never queued in front of the kernel that pushes (separate GPUs run the four steps as one call)
-        for step in (1, 2, 4, 8):
+        for step in (16, 1, 2, 4, 8):
             for g in order:
                 res[g] = S[g].query(dq[g], phases=step)
         for c in ctxs:

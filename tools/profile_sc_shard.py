@@ -34,10 +34,10 @@ def main():
     for s in S:
         with torch.cuda.stream(s.stream):
             dq.append(torch.from_numpy(qd).to(s.dev))
-    names = {1: "keys + images + GEMM + top3 + push T", 2: "threshold + select + re-rank + push C", 4: "merge + distance + push D", 8: "decide"}
+    names = {16: "keys of the own query slice + push K", 1: "gather keys + images + GEMM + top3 + push T", 2: "threshold + select + re-rank + push C", 4: "merge + distance + push D", 8: "decide"}
     for rep in range(3):
         t = {}
-        for step in (1, 2, 4, 8):
+        for step in (16, 1, 2, 4, 8):
             ev = []
             for g, s in enumerate(S):
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -51,7 +51,7 @@ def main():
                 c.sync()
             t[step] = [a.elapsed_time(b) for a, b in ev]
         if rep == 2:
-            for step in (1, 2, 4, 8):
+            for step in (16, 1, 2, 4, 8):
                 print("%-42s %s ms per rank" % (names[step], ["%.3f" % v for v in t[step]]))
             print("sum over steps, rank 0: %.3f ms for %d queries, %d keys per rank" % (sum(t[k][0] for k in t), Q, kloc))
     loop = res[0].cpu().numpy()
