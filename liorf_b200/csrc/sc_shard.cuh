@@ -34,7 +34,8 @@ struct ShardWin {                            // passed by value to the kernels
 __host__ __device__ __forceinline__ size_t scsh_flag_off(int src, int phase) { return ((size_t)src * 4 + phase) * sizeof(unsigned); }
 
 // consumer side: thread 0 waits until every peer's flag of `phase` has reached `batch` (own window, acquire at system scope)
-__device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, unsigned batch, int* err_flag) {
+__device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, const unsigned* batch_p, int* err_flag) {
+    const unsigned batch = *batch_p;
     if (threadIdx.x == 0) {
         for (int g = 0; g < W.world; ++g) {
             if (g == W.rank) continue;
@@ -50,8 +51,12 @@ __device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, unsigned
     __syncthreads();
 }
 
+// the batch number lives in device memory (bumped by the first kernel of a batch) so that a batch is the same kernel sequence with the
+// same arguments every time — it replays from a CUDA graph
+__global__ void k_scsh_next_batch(unsigned* batch) { *batch += 1u; }
+
 // producer side: copy `words` 32-bit words from src into slot [my rank] of every window, then (last block) raise the flags
-__global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const unsigned* __restrict__ src, size_t words, unsigned batch, unsigned* counter,
+__global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const unsigned* __restrict__ src, size_t words, const unsigned* __restrict__ batch_p, unsigned* counter,
                                                   size_t dst_byte_off = 0) {
     const size_t slot = W.off[phase] + (size_t)W.rank * W.stride[phase] + dst_byte_off;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
@@ -68,12 +73,12 @@ __global__ void __launch_bounds__(256) k_scsh_push(ShardWin W, int phase, const 
     __threadfence_system();
     if ((int)threadIdx.x < W.world && (int)threadIdx.x != W.rank) {
         unsigned* f = reinterpret_cast<unsigned*>(W.base[threadIdx.x] + scsh_flag_off(W.rank, phase));
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(batch) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(*batch_p) : "memory");
     }
 }
 
 // phase K consumer: the ring keys of all queries, derived slice by slice on the ranks, are complete in this window → contiguous copy
-__global__ void __launch_bounds__(256) k_scsh_gather_keys(ShardWin W, unsigned batch, int words, unsigned* __restrict__ dst, int* err_flag) {
+__global__ void __launch_bounds__(256) k_scsh_gather_keys(ShardWin W, const unsigned* __restrict__ batch, int words, unsigned* __restrict__ dst, int* err_flag) {
     scsh_wait(W, SCSH_K, batch, err_flag);
     const unsigned* src = reinterpret_cast<const unsigned*>(W.base[W.rank] + W.off[SCSH_K]);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) dst[i] = __ldcg(src + i);
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(128) k_scsh_u3(const float* __restrict__ part,
 }
 // phase T consumer: U3(q) = third smallest over all ranks' bounds >= the true global third-smallest distance d3; a key of THIS
 // rank in the global top-3 has d~ <= d + eps_r <= d3 + eps_r <= U3 + eps_r =: thr(q)
-__global__ void __launch_bounds__(128) k_scsh_thr(ShardWin W, unsigned batch, const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
+__global__ void __launch_bounds__(128) k_scsh_thr(ShardWin W, const unsigned* __restrict__ batch, const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
                                                  float* __restrict__ thr, int* err_flag) {
     scsh_wait(W, SCSH_T, batch, err_flag);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(128) k_scsh_thr(ShardWin W, unsigned batch, co
 }
 
 // phase C consumer: the G local top-3 lists → global top-3 by (dist, idx)   [same arithmetic as k_sc_merge_top3]
-__global__ void __launch_bounds__(128) k_scsh_merge(ShardWin W, unsigned batch, int Q, float* __restrict__ out_d, int* __restrict__ out_i, int* err_flag) {
+__global__ void __launch_bounds__(128) k_scsh_merge(ShardWin W, const unsigned* __restrict__ batch, int Q, float* __restrict__ out_d, int* __restrict__ out_i, int* err_flag) {
     scsh_wait(W, SCSH_C, batch, err_flag);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(256) k_scsh_fill_pairs(double* __restrict__ pd
 }
 
 // phase D consumer: owner pick per (query, candidate) pair, then the decision of detectLoopClosureID (:302-340)
-__global__ void __launch_bounds__(128) k_scsh_decide(ShardWin W, unsigned batch, const int* __restrict__ cand, int Q, int* __restrict__ loop_id, int* __restrict__ shift,
+__global__ void __launch_bounds__(128) k_scsh_decide(ShardWin W, const unsigned* __restrict__ batch, const int* __restrict__ cand, int Q, int* __restrict__ loop_id, int* __restrict__ shift,
                                                     double* __restrict__ dist, int* err_flag) {
     scsh_wait(W, SCSH_D, batch, err_flag);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;

@@ -249,8 +249,12 @@ class PeerShardedSearch:
         if o is None:
             o = self._out[Q] = (t.empty(Q, dtype=t.int32, device=self.dev), t.empty(Q, dtype=t.int32, device=self.dev),
                                 t.empty(Q, dtype=t.float64, device=self.dev), t.empty((Q, 3), dtype=t.int32, device=self.dev))
-        rc = self.ctx.lib.liorf_sc_shard_query_phases_dev(self.ctx.h, C.c_void_p(d_q.data_ptr()), C.c_int(Q), C.c_int(self.off), C.c_void_p(o[0].data_ptr()),
-                                                          C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr()), C.c_void_p(o[3].data_ptr()), C.c_int(phases))
+        args = (self.ctx.h, C.c_void_p(d_q.data_ptr()), C.c_int(Q), C.c_int(self.off), C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()),
+                C.c_void_p(o[2].data_ptr()), C.c_void_p(o[3].data_ptr()))
+        if phases == 31:
+            rc = self.ctx.lib.liorf_sc_shard_query_dev(*args)           # the whole batch (a CUDA graph replay from the third identical request on)
+        else:
+            rc = self.ctx.lib.liorf_sc_shard_query_phases_dev(*args, C.c_int(phases))
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_query_dev failed with code {rc}")
         return o

@@ -88,3 +88,30 @@ def test_global_threshold_shards_the_rerank(synth):
     total = sum(s["candidates"] for s in stats)
     print(f"candidate chunks: unsharded {base}, 4 shards together {total}")
     assert total < 1.6 * base
+
+
+def test_whole_batch_call_replays_from_a_graph(synth):
+    """liorf_sc_shard_query_dev (the one-call batch a real rank issues) on a single rank: the third identical request (same buffers,
+    same size) is captured as a CUDA graph and replayed from then on.  New query CONTENTS in the same buffers must give the new
+    answers — nothing about a batch may be baked into the graph except the kernel sequence."""
+    import torch
+    import liorf_b200
+    from liorf_b200.sc_sharded import PeerShardedSearch
+    K, Q = 9000, 500
+    db = synth.sc_descriptors(K, seed=81)
+    ref = liorf_b200.Context(); ref.scAddDescriptors(db)
+    ctx = liorf_b200.Context(); ctx.scAddDescriptors(db); ctx.scSetSearchPath(2)
+    S = PeerShardedSearch(ctx, 0, 1, 0, Q, torch)
+    S.connect_local([S])
+    d_q = torch.empty((Q, 1200), dtype=torch.float64, device=S.dev)
+    for b in range(6):
+        qd, src, shift = synth.sc_queries(db, Q, seed=90 + b)
+        with torch.cuda.stream(S.stream):
+            d_q.copy_(torch.from_numpy(qd).to(S.dev))
+        loop, sh, dd, cand = S.query(d_q)
+        ctx.sync(); torch.cuda.synchronize()
+        r_loop, r_sh, r_dist, r_cand = ref.scQueryBatch(qd)
+        assert np.array_equal(cand.cpu().numpy(), r_cand), b
+        assert np.array_equal(loop.cpu().numpy(), r_loop) and np.array_equal(sh.cpu().numpy(), r_sh), b
+        assert np.array_equal(np.nan_to_num(dd.cpu().numpy(), nan=-7.0), np.nan_to_num(r_dist, nan=-7.0)), b
+    ctx.close(); ref.close()
