@@ -331,14 +331,17 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     CH = 10000
     for s in range(0, kloc, CH):
         ctx.scAddDescriptors(synth.sc_descriptors(min(CH, kloc - s), first=off + s))
-    # queries: column-shifted noisy copies of entries of the first 2000 global rows (+ fresh ones); identical on every rank
-    sample = synth.sc_descriptors(min(K, 2000), first=0)
+    # queries: column-shifted noisy copies of 2000 database entries spread evenly over ALL rows (+ fresh ones); identical on every rank.
+    # (Sources taken from the first rows only would put every true loop's candidates — and with them most of stage 2 — on rank 0.)
+    n_src = min(K, 2000)
+    src_rows = (np.arange(n_src, dtype=np.int64) * K) // n_src
+    sample = np.concatenate([synth.sc_descriptors(1, first=int(i)) for i in src_rows])
     ops = GpuOps(ctx, off, torch)
     search = ShardedScanContextSearch(ops, rank, world, dist)      # world == 1: plain local search (no exchange at all)
     dev = ops.dev
     # exchange through NVLink peer windows (csrc/sc_shard.cuh), no NCCL inside a batch; one rank = the same code path with nothing to wait for
     from liorf_b200.sc_sharded import PeerShardedSearch
-    peer = PeerShardedSearch(ctx, rank, world, off, max(Q, q_large), torch)
+    peer = PeerShardedSearch(ctx, rank, world, [g * kloc for g in range(world + 1)], max(Q, q_large), torch)
     peer.connect_processes(dist)
 
     def run(Qn, reps_n):
@@ -351,6 +354,7 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
         for _ in range(4):                                         # warm-up (the third identical request captures the batch as a CUDA graph)
             loop, sh, dd, cand = one()
         ctx.sync()
+        peer.wait_stats()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -363,6 +367,7 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
             e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        waits, _ = peer.wait_stats()
         if world > 1:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         # the tcgen05 GEMM's own duration: a few more batches of the same work with the library's CUDA-event sections on (plain launches)
@@ -375,6 +380,7 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
         tm = ctx.getTiming(); ctx.enableTiming(False)
         st = ctx.scTensorStats()
         lp = loop.cpu().numpy(); shn = sh.cpu().numpy()
+        src = np.where(src >= 0, src_rows[np.maximum(src, 0)], -1)      # sample index → global database row
         ok = (lp == src) & (src >= 0)
         gemm_ms = tm["sc_gemm"][0] / max(tm["sc_gemm"][1], 1)
         kpad, qpad = (kloc + 127) // 128 * 128, (Qn + 255) // 256 * 256
@@ -385,6 +391,7 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
                    exchange=("NVLink peer windows (push + system-scope flags from the kernels, 4 phases per batch), no NCCL; batch replayed from a CUDA graph" if world > 1 else "none (one shard)"),
                    ringkey_stage_ms=2 * tm["sc_search"][0] / max(tm["sc_search"][1], 1), candidates_per_query=st["candidates"] / max(Qn, 1) * 32,
                    overflow_queries=st["overflow"],
+                   peer_wait_us_per_batch={k: v / 1e3 / reps_n for k, v in waits.items()},      # rank 0: time its consumer kernels spent waiting for the peers' pushes
                    roofline=dict(kernel="k_sc_tensor", bound="tensor", achieved=tflops, peak=peaks.get("bf16_tflops"), unit="TFLOP/s",
                                  frac=(tflops / peaks["bf16_tflops"]) if tflops and peaks.get("bf16_tflops") else None, traffic=None,
                                  avg_launch_ms=gemm_ms,

@@ -207,7 +207,8 @@ int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_
  *   liorf_sc_shard_query_dev: one batch, asynchronous on the context's stream; every rank passes the same queries in the same order;
  *                            global_offset = index of this rank's first database row */
 int liorf_sc_shard_init(liorf_ctx* ctx, int rank, int world, int q_max, void* ipc_handle_out, void** window_out);
-int liorf_sc_shard_connect(liorf_ctx* ctx, const void* ipc_handles, void* const* window_ptrs);
+int liorf_sc_shard_connect(liorf_ctx* ctx, const void* ipc_handles, void* const* window_ptrs, const int* row_begin /* world + 1: rows [row_begin[g], row_begin[g+1]) on rank g */);
+int liorf_sc_shard_wait_stats(liorf_ctx* ctx, unsigned long long wait_ns[4], unsigned* batches);   /* time spent waiting for peers per phase (T, C, D, K), measurement */
 int liorf_sc_shard_query_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand);
 /* the same batch enqueued in steps (bit 4: ring keys of this rank's query slice + push, then bit 0: all keys .. threshold-bound push, 1: global threshold ..
  * local top-3 push, 2: merge .. distance push, 3: decision; 31 = everything) so that

@@ -102,7 +102,7 @@ struct liorf_ctx {
     // sharded search over peer windows (sc_shard.cuh)
     struct ScShard { bool ready = false; ShardWin W; int qmax = 0; size_t win_bytes = 0; unsigned* d_batch = nullptr; unsigned* d_counter = nullptr;
                      cudaGraphExec_t graph = nullptr; const void* gsig[8] = {nullptr}; const void* last_sig[8] = {nullptr}; bool ipc_opened[SCSH_MAX] = {false};
-                     DevBuf<float> u3, thr; DevBuf<unsigned> packC, packD; } shard;
+                     DevBuf<float> u3, thr; DevBuf<unsigned> packC; DevBuf<int> list; int* d_nlist = nullptr; } shard;
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
     bool sct_attr_set = false; int sct_last_Q = 0; bool scdb_attr_set = false; int scdb_blocks_per_sm = 1;
     Profiler prof;
@@ -402,7 +402,7 @@ void liorf_destroy(liorf_ctx* c) {
         if (S.W.base[S.W.rank]) cudaFree(S.W.base[S.W.rank]);
         if (S.d_counter) cudaFree(S.d_counter);
         if (S.graph) cudaGraphExecDestroy(S.graph);
-        S.u3.release(); S.thr.release(); S.packC.release(); S.packD.release();
+        S.u3.release(); S.thr.release(); S.packC.release(); S.list.release();
     }
     if (c->d_dbg_gt) cudaFree(c->d_dbg_gt);
     if (c->h_sel) cudaFreeHost(c->h_sel);
@@ -1102,7 +1102,8 @@ static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_
 }
 
 // stage 2 for a batch of (query, candidate) pairs: TMA-staged kernel (sc_distance.cuh), persistent warps over the pairs
-static int sc_distance_launch(liorf_ctx* c, const double* qd, const double* qsk, const double* qcn, const int* cand, int pairs, int global_offset, double* pd, int* ps) {
+static int sc_distance_launch(liorf_ctx* c, const double* qd, const double* qsk, const double* qcn, const int* cand, int pairs, int global_offset, double* pd, int* ps,
+                              const int* pair_list = nullptr, const int* n_list = nullptr, const ShardPush* push = nullptr) {
     if (!c->scdb_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_sc_distance_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SCDB_SMEM));
         int occ = 0;
@@ -1112,8 +1113,10 @@ static int sc_distance_launch(liorf_ctx* c, const double* qd, const double* qsk,
     int blocks = (pairs + SCDB_WARPS - 1) / SCDB_WARPS;
     const int cap = c->num_sms * c->scdb_blocks_per_sm;
     if (blocks > cap) blocks = cap;
+    ShardPush P; std::memset(&P, 0, sizeof(P));
+    if (push) P = *push;
     k_sc_distance_bulk<<<blocks, SCDB_WARPS * 32, SCDB_SMEM, c->stream>>>(qd, qsk, qcn, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n,
-                                                                          pd, ps, c->d_err);
+                                                                          pd, ps, c->d_err, pair_list, n_list, P);
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
 }
@@ -1288,19 +1291,34 @@ int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, void* ipc_
     unsigned char* win = nullptr;
     CUDA_TRY(cudaMalloc(&win, S.win_bytes));
     CUDA_TRY(cudaMemset(win, 0, S.win_bytes));
-    CUDA_TRY(cudaMalloc(&S.d_counter, 2 * sizeof(unsigned)));
-    CUDA_TRY(cudaMemset(S.d_counter, 0, 2 * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&S.d_counter, 4 * sizeof(unsigned) + 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(S.d_counter, 0, 4 * sizeof(unsigned) + 4 * sizeof(unsigned long long)));
+    S.d_nlist = reinterpret_cast<int*>(S.d_counter + 2);
     S.d_batch = S.d_counter + 1;
+    S.W.wait_ns = reinterpret_cast<unsigned long long*>(S.d_counter + 4);
     S.W.base[rank] = win;
     if (ipc_handle_out) { cudaIpcMemHandle_t h; CUDA_TRY(cudaIpcGetMemHandle(&h, win)); static_assert(sizeof(h) == 64, "ipc handle"); std::memcpy(ipc_handle_out, &h, 64); }
     if (window_out) *window_out = win;
     return LIORF_OK;
 }
-int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B, nullable*/, void* const* window_ptrs /*world entries, nullable*/) {
-    if (!c || (!ipc_handles && !window_ptrs)) return LIORF_ERR_ARG;
+/* nanoseconds this rank's kernels spent waiting for the peers' pushes, per phase (T, C, D, K), accumulated since the last call; batches = batch counter */
+int liorf_sc_shard_wait_stats(liorf_ctx* c, unsigned long long wait_ns[4], unsigned* batches) {
+    if (!c || !wait_ns) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    liorf_ctx::ScShard& S = c->shard;
+    if (!S.d_counter) return LIORF_ERR_STATE;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(wait_ns, S.W.wait_ns, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (batches) CUDA_TRY(cudaMemcpy(batches, S.d_batch, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(S.W.wait_ns, 0, 4 * sizeof(unsigned long long)));
+    return LIORF_OK;
+}
+int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B, nullable*/, void* const* window_ptrs /*world entries, nullable*/, const int* row_begin /*world + 1*/) {
+    if (!c || (!ipc_handles && !window_ptrs) || !row_begin) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
     if (!S.W.base[S.W.rank] || S.ready) return LIORF_ERR_STATE;
+    for (int g = 0; g <= S.W.world; ++g) { S.W.row_begin[g] = row_begin[g]; if (g > 0 && row_begin[g] < row_begin[g - 1]) return LIORF_ERR_ARG; }
     for (int g = 0; g < S.W.world; ++g) {
         if (g == S.W.rank) continue;
         if (window_ptrs) S.W.base[g] = (unsigned char*)window_ptrs[g];               // same process: the peer context's pointer is directly usable
@@ -1325,10 +1343,9 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     if (c->sc_n < 1) return LIORF_ERR_STATE;
     int rc;
     if ((rc = c->sc_qsk.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qcn.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qkeys.reserve((size_t)Q * SC_RING)) ||
-        (rc = sc_reserve_query(c, Q)) || (rc = S.packC.reserve((size_t)6 * Q)) || (rc = S.packD.reserve((size_t)9 * Q + 1))) return rc;
+        (rc = sc_reserve_query(c, Q)) || (rc = S.packC.reserve((size_t)6 * Q)) || (rc = S.list.reserve((size_t)3 * Q))) return rc;
     const double* qd = (const double*)d_qdescs;
     float* ld = reinterpret_cast<float*>(S.packC.p); int* li = reinterpret_cast<int*>(S.packC.p) + (size_t)3 * Q;
-    double* pd = reinterpret_cast<double*>(S.packD.p); int* psh = reinterpret_cast<int*>(S.packD.p) + (size_t)6 * Q;
     int* cand = d_cand ? (int*)d_cand : c->sc_q_i.p;
     const int pairs = 3 * Q;
     const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && c->sc_n >= 4096);
@@ -1356,10 +1373,12 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     }
     if (phases & 4) {        // merge to the global top-3, owner-computes distanceBtnScanContext, push
         k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, Q, c->sc_q_d.p, cand, c->d_err);
-        k_scsh_fill_pairs<<<(pairs + 255) / 256, 256, 0, c->stream>>>(pd, psh, pairs);
+        // the pairs this rank owns → compact list → stage 2 on exactly those, results pushed by the stage-2 kernel itself
+        CUDA_TRY(cudaMemsetAsync(S.d_nlist, 0, sizeof(int), c->stream));
+        k_scsh_owned_list<<<(pairs + 255) / 256, 256, 0, c->stream>>>(cand, pairs, global_offset, c->sc_n, S.list.p, S.d_nlist);
         k_scsh_skcn_owned<<<Q, 64, 0, c->stream>>>(qd, cand, Q, global_offset, c->sc_n, c->sc_qsk.p, c->sc_qcn.p);      // sector keys / column norms of the queries whose candidates this rank owns
-        if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, pd, psh))) return rc;
-        k_scsh_push<<<std::min(64, (9 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_D, S.packD.p, (size_t)9 * Q, S.d_batch, S.d_counter);
+        ShardPush P; P.enabled = 1; P.Q = Q; P.W = S.W; P.counter = S.d_counter; P.batch_p = S.d_batch;
+        if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, nullptr, nullptr, S.list.p, S.d_nlist, &P))) return rc;
     }
     if (phases & 8)          // owner pick + decision
         k_scsh_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, cand, Q, (int*)d_loop_id, (int*)d_shift, (double*)d_dist, c->d_err);

@@ -9,7 +9,7 @@
 // single-query call; results are bit-identical (tests/test_gpu_sc_tensor.py, test_gpu_deskew_sc.py).
 // Algorithmic traffic per pair: 9 600 B candidate + 9 600 B query descriptor (three pairs share a query: L2) + 2 x 960 B keys/norms.
 #pragma once
-#include "sc_tensor.cuh"
+#include "sc_shard.cuh"
 
 namespace liorf {
 
@@ -20,7 +20,8 @@ constexpr int SCDB_SMEM = SCDB_WARPS * SCDB_WARP_BYTES + SCDB_WARPS * 8;
 __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const double* __restrict__ qdesc, const double* __restrict__ qsk, const double* __restrict__ qcn,
                                                                       const int* __restrict__ cand, int n_pairs, int cand_per_query,
                                                                       const double* __restrict__ db_desc, const double* __restrict__ db_sk, const double* __restrict__ db_cn,
-                                                                      int own_begin, int own_count, double* __restrict__ out_dist, int* __restrict__ out_shift, int* err_flag) {
+                                                                      int own_begin, int own_count, double* __restrict__ out_dist, int* __restrict__ out_shift, int* err_flag,
+                                                                      const int* __restrict__ pair_list, const int* __restrict__ n_list, ShardPush P) {
     extern __shared__ __align__(16) unsigned char scdb_smem[];
     const int w = warp_id(), l = lane_id();
     double* s_sc2 = reinterpret_cast<double*>(scdb_smem + (size_t)w * SCDB_WARP_BYTES);
@@ -34,7 +35,9 @@ __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const doub
     __syncthreads();
     uint32_t parity = 0;
     const int n_warps = gridDim.x * SCDB_WARPS;
-    for (int pair = blockIdx.x * SCDB_WARPS + w; pair < n_pairs; pair += n_warps) {
+    const int n_items = pair_list ? *n_list : n_pairs;               // sharded search: the compact list of the pairs this rank owns
+    for (int it = blockIdx.x * SCDB_WARPS + w; it < n_items; it += n_warps) {
+        const int pair = pair_list ? pair_list[it] : it;
         const int q = pair / cand_per_query;
         const int c = cand[pair];
         if (c == 0x7fffffff || c < 0) { if (l == 0) { out_dist[pair] = INFINITY; out_shift[pair] = 0; } continue; }
@@ -111,7 +114,32 @@ __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const doub
             double dj = __shfl_sync(FULL, dist, j); int sj = __shfl_sync(FULL, sh, j);
             if (dj < mn) { mn = dj; arg = sj; }
         }
-        if (l == 0) { out_dist[pair] = mn; out_shift[pair] = arg; }
+        if (l == 0) {
+            if (P.enabled) {             // push: slot [my rank] of every rank's window, straight from the warp that computed the pair
+                for (int g = 0; g < P.W.world; ++g) {
+                    unsigned char* slot = P.W.base[g] + P.W.off[SCSH_D] + (size_t)P.W.rank * P.W.stride[SCSH_D];
+                    reinterpret_cast<double*>(slot)[pair] = mn;
+                    reinterpret_cast<int*>(slot + (size_t)3 * P.Q * 8)[pair] = arg;
+                }
+            } else { out_dist[pair] = mn; out_shift[pair] = arg; }
+        }
+    }
+    if (P.enabled) {                     // the last block to finish raises this rank's phase-D flag in every peer window
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(P.counter, 1u);
+            if (t == gridDim.x - 1) {
+                *P.counter = 0u;
+                __threadfence_system();
+                const unsigned b = *P.batch_p;
+                for (int g = 0; g < P.W.world; ++g) {
+                    if (g == P.W.rank) continue;
+                    unsigned* f = reinterpret_cast<unsigned*>(P.W.base[g] + scsh_flag_off(P.W.rank, SCSH_D));
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(b) : "memory");
+                }
+            }
+        }
     }
 }
 

@@ -13,7 +13,8 @@
 //            that every rank can derive the GLOBAL candidate threshold (a rank that only knew its local third-smallest value
 //            would re-rank ~100 candidates per query whatever the shard size; with the global bound the re-rank work shards too)
 //   phase C: exact local top-3 {f32 dist, i32 global idx} → every rank merges the G lists by (dist, idx): identical global top-3
-//   phase D: distanceBtnScanContext of the candidates THIS rank owns {f64 dist, i32 shift}, +inf elsewhere → owner pick + decision
+//   phase D: distanceBtnScanContext of the candidates THIS rank owns {f64 dist, i32 shift}, written by the stage-2 kernel itself into every
+//            window (compute and transfer in ONE kernel); the consumer reads the owner's slot of each pair → decision
 // Exactly the global top-3 are evaluated, so results equal the unsharded search bit for bit (tests/test_gpu_sc_shard.py).
 //
 // Reuse without double buffering is safe: a rank enters phase p of batch b+1 only after it has consumed phase D of batch b,
@@ -29,6 +30,8 @@ enum { SCSH_T = 0, SCSH_C = 1, SCSH_D = 2, SCSH_K = 3 };
 struct ShardWin {                            // passed by value to the kernels
     unsigned char* base[SCSH_MAX];           // window of every rank as mapped into THIS process (base[rank] = own)
     int rank, world;
+    int row_begin[SCSH_MAX + 1];             // database rows [row_begin[g], row_begin[g + 1]) live on rank g
+    unsigned long long* wait_ns;             // optional [4]: nanoseconds block 0 spent waiting for the peers, per phase (accumulated; %globaltimer)
     unsigned long long off[4], stride[4];    // byte offset of a phase's region inside a window, byte stride between source slots (phase K: one shared array, stride 0)
 };
 __host__ __device__ __forceinline__ size_t scsh_flag_off(int src, int phase) { return ((size_t)src * 4 + phase) * sizeof(unsigned); }
@@ -37,6 +40,8 @@ __host__ __device__ __forceinline__ size_t scsh_flag_off(int src, int phase) { r
 __device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, const unsigned* batch_p, int* err_flag) {
     const unsigned batch = *batch_p;
     if (threadIdx.x == 0) {
+        unsigned long long t0 = 0;
+        if (W.wait_ns && blockIdx.x == 0 && blockIdx.y == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
         for (int g = 0; g < W.world; ++g) {
             if (g == W.rank) continue;
             const unsigned* f = reinterpret_cast<const unsigned*>(W.base[W.rank] + scsh_flag_off(g, phase));
@@ -47,6 +52,7 @@ __device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, const un
                 if (++spins > (1u << 22)) { atomicExch(err_flag, 3); break; }      // ~seconds: a peer that never arrives is an error, not a hang
             }
         }
+        if (t0) { unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1)); W.wait_ns[phase] += t1 - t0; }
     }
     __syncthreads();
 }
@@ -156,7 +162,25 @@ __global__ void __launch_bounds__(256) k_scsh_fill_pairs(double* __restrict__ pd
     if (i < n_pairs) { pd[i] = INFINITY; ps[i] = 0; }
 }
 
-// phase D consumer: owner pick per (query, candidate) pair, then the decision of detectLoopClosureID (:302-340)
+// the (query, candidate) pairs whose candidate THIS rank owns, as a compact list (order irrelevant: results are keyed by the pair id)
+__global__ void __launch_bounds__(256) k_scsh_owned_list(const int* __restrict__ cand, int n_pairs, int own_begin, int own_count, int* __restrict__ list, int* __restrict__ n_list) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool own = false;
+    if (i < n_pairs) { const int c = cand[i]; own = c != 0x7fffffff && c - own_begin >= 0 && c - own_begin < own_count; }
+    const unsigned m = __ballot_sync(FULL, own);
+    if (!m) return;
+    int base = 0;
+    if (lane_id() == __ffs(m) - 1) base = atomicAdd(n_list, __popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (own) list[base + __popc(m & ((1u << lane_id()) - 1u))] = i;
+}
+
+// what the stage-2 kernel needs to push its results itself (sc_distance.cuh): every owned pair's {f64 dist, i32 shift} goes straight
+// from the warp that computed it into slot [my rank] of EVERY window; the last block raises the phase-D flags
+struct ShardPush { int enabled; int Q; ShardWin W; unsigned* counter; const unsigned* batch_p; };
+
+// phase D consumer: each (query, candidate) pair was evaluated by the rank that owns the candidate's row → read THAT rank's slot;
+// then the decision of detectLoopClosureID (:302-340): candidates in kNN order, strict <, threshold
 __global__ void __launch_bounds__(128) k_scsh_decide(ShardWin W, const unsigned* __restrict__ batch, const int* __restrict__ cand, int Q, int* __restrict__ loop_id, int* __restrict__ shift,
                                                     double* __restrict__ dist, int* err_flag) {
     scsh_wait(W, SCSH_D, batch, err_flag);
@@ -166,13 +190,16 @@ __global__ void __launch_bounds__(128) k_scsh_decide(ShardWin W, const unsigned*
 #pragma unroll
     for (int c = 0; c < SC_NUM_CAND; ++c) {
         const size_t i = 3 * (size_t)q + c;
+        const int idx = cand[i];
         double d = INFINITY; int sh = 0;
-        for (int g = 0; g < W.world; ++g) {
+        if (idx != 0x7fffffff && idx >= 0) {
+            int g = 0;
+            while (g + 1 < W.world && idx >= W.row_begin[g + 1]) ++g;
             const unsigned char* slot = W.base[W.rank] + W.off[SCSH_D] + (size_t)g * W.stride[SCSH_D];
-            const double dp = __ldcg(reinterpret_cast<const double*>(slot) + i);
-            if (dp != INFINITY) { d = dp; sh = __ldcg(reinterpret_cast<const int*>(slot + (size_t)3 * Q * 8) + i); break; }   // NaN != inf: an owner's NaN is kept
+            d = __ldcg(reinterpret_cast<const double*>(slot) + i);
+            sh = __ldcg(reinterpret_cast<const int*>(slot + (size_t)3 * Q * 8) + i);
         }
-        if (d < mn) { mn = d; al = sh; nn = cand[i]; }
+        if (d < mn) { mn = d; al = sh; nn = idx; }
     }
     loop_id[q] = mn < SC_DIST_THRES ? nn : -1; shift[q] = al; dist[q] = mn;
 }

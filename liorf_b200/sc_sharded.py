@@ -207,8 +207,12 @@ class PeerShardedSearch:
     consumers spin on their own window.  One library call per batch, no collective launch, no host round trip.
     torch.distributed is used once, to hand the 64-byte cudaIpc handles around."""
 
-    def __init__(self, ctx, rank, world, global_offset, q_max, torch):
-        self.ctx, self.rank, self.world, self.off, self.q_max, self.torch = ctx, rank, world, int(global_offset), int(q_max), torch
+    def __init__(self, ctx, rank, world, row_begin, q_max, torch):
+        """row_begin: world + 1 global row indices — rank g holds database rows [row_begin[g], row_begin[g + 1])"""
+        self.ctx, self.rank, self.world, self.q_max, self.torch = ctx, rank, world, int(q_max), torch
+        self.row_begin = [int(v) for v in row_begin]
+        assert len(self.row_begin) == world + 1
+        self.off = self.row_begin[rank]
         self.dev = torch.device(f"cuda:{ctx.params.device}")
         self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.dev)
         self.handle = (C.c_ubyte * 64)()
@@ -224,9 +228,9 @@ class PeerShardedSearch:
             hs = [None] * self.world
             dist.all_gather_object(hs, bytes(self.handle))
             buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(hs))
-            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, buf, None)
+            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, buf, None, (C.c_int * (self.world + 1))(*self.row_begin))
         else:
-            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, self.handle, None)
+            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, self.handle, None, (C.c_int * (self.world + 1))(*self.row_begin))
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
         if self.world > 1:
@@ -235,9 +239,15 @@ class PeerShardedSearch:
     def connect_local(self, searches):
         """peers are other contexts of THIS process (tests: several shards on one GPU)"""
         ptrs = (C.c_void_p * self.world)(*[s.window.value for s in searches])
-        rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, None, ptrs)
+        rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, None, ptrs, (C.c_int * (self.world + 1))(*self.row_begin))
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
+
+    def wait_stats(self):
+        """(ns waited for the peers per phase {T, C, D, K} since the last call, batch counter)"""
+        w = (C.c_ulonglong * 4)(); b = C.c_uint(0)
+        self.ctx.lib.liorf_sc_shard_wait_stats(self.ctx.h, w, C.byref(b))
+        return dict(T=w[0], C=w[1], D=w[2], K=w[3]), b.value
 
     def query(self, d_q, phases=31):
         """d_q: (Q, 1200) float64 query descriptors on this rank's device (the same on every rank).  Asynchronous on the context's

@@ -21,7 +21,7 @@ def _run(synth, K, Q_list, world, path, bounds=None):
     ctxs = [liorf_b200.Context() for _ in range(world)]
     for g, c in enumerate(ctxs):
         c.scAddDescriptors(db[bounds[g]:bounds[g + 1]]); c.scSetSearchPath(path)
-    S = [PeerShardedSearch(c, g, world, bounds[g], max(Q_list), torch) for g, c in enumerate(ctxs)]
+    S = [PeerShardedSearch(c, g, world, bounds, max(Q_list), torch) for g, c in enumerate(ctxs)]
     for s in S:
         s.connect_local(S)
     dev = S[0].dev
@@ -101,7 +101,7 @@ def test_whole_batch_call_replays_from_a_graph(synth):
     db = synth.sc_descriptors(K, seed=81)
     ref = liorf_b200.Context(); ref.scAddDescriptors(db)
     ctx = liorf_b200.Context(); ctx.scAddDescriptors(db); ctx.scSetSearchPath(2)
-    S = PeerShardedSearch(ctx, 0, 1, 0, Q, torch)
+    S = PeerShardedSearch(ctx, 0, 1, [0, K], Q, torch)
     S.connect_local([S])
     d_q = torch.empty((Q, 1200), dtype=torch.float64, device=S.dev)
     for b in range(6):

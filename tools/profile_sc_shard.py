@@ -25,11 +25,14 @@ def main():
         c.reserve(1024, 1024, 0, kloc)
         for s in range(0, kloc, 10000):
             c.scAddDescriptors(synth.sc_descriptors(min(10000, kloc - s), first=g * kloc + s))
-    S = [PeerShardedSearch(c, g, world, g * kloc, Q, torch) for g, c in enumerate(ctxs)]
+    S = [PeerShardedSearch(c, g, world, [r * kloc for r in range(world + 1)], Q, torch) for g, c in enumerate(ctxs)]
     for s in S:
         s.connect_local(S)
-    sample = synth.sc_descriptors(min(K, 2000), first=0)
+    n_src = min(K, 2000)
+    src_rows = (np.arange(n_src, dtype=np.int64) * K) // n_src          # loop sources spread over all rows (and so over all ranks)
+    sample = np.concatenate([synth.sc_descriptors(1, first=int(i)) for i in src_rows])
     qd, src, shift = synth.sc_queries(sample, Q)
+    src = np.where(src >= 0, src_rows[np.maximum(src, 0)], -1)
     dq = []
     for s in S:
         with torch.cuda.stream(s.stream):
@@ -46,14 +49,14 @@ def main():
                 res = s.query(dq[g], phases=step)
                 with torch.cuda.stream(s.stream):
                     e1.record()
+                ctxs[g].sync()                          # one rank at a time: its kernels have the GPU to themselves, as on its own device
                 ev.append((e0, e1))
-            for c in ctxs:
-                c.sync()
             t[step] = [a.elapsed_time(b) for a, b in ev]
         if rep == 2:
             for step in (16, 1, 2, 4, 8):
-                print("%-42s %s ms per rank" % (names[step], ["%.3f" % v for v in t[step]]))
-            print("sum over steps, rank 0: %.3f ms for %d queries, %d keys per rank" % (sum(t[k][0] for k in t), Q, kloc))
+                print("%-46s rank 0 %.3f ms   mean %.3f   max %.3f" % (names[step], t[step][0], float(np.mean(t[step])), float(np.max(t[step]))))
+            print("sum over steps: rank 0 %.3f ms, sum of the per-step maxima %.3f ms, for %d queries, %d keys per rank, %d ranks" %
+                  (sum(t[k][0] for k in t), sum(max(t[k]) for k in t), Q, kloc, world))
     loop = res[0].cpu().numpy()
     print("planted found:", int(((loop == src) & (src >= 0)).sum()), "of", int((src >= 0).sum()))
     for c in ctxs:
