@@ -10,8 +10,9 @@ sequence; one STEP = one LiDAR frame through the whole path
 `e2e`    : the same metric through the C ABI with HOST (pinned) raw scans: H2D of every scan and D2H of the pose inside
            the timed region.
 Extra keys: `single_frame` (config 1: downsample + grid + 30 forced LM iterations against the local map — the "<1 ms"
-target), `knn_queries_per_s`, `sc` (config 5: ScanContext queries/s over a K-entry database sharded over the ranks,
-NCCL all-gather of the top-3 candidates), `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`.
+target), `knn_queries_per_s`, `sc` (config 5: ScanContext queries/s over a K-entry database sharded over the ranks, exchanged
+through NVLink peer-memory windows by the library's kernels), `batched`, `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`.
+Every frame announces its successor (liorf_frame_in.next): the next scan's H2D copy, deskew and downsample overlap this frame's solve.
 
 `--impl reference` times the CPU path (oracle restatement + the reference's vendored nanoflann from oracle/_ref) on
 the same frames, bounded sample, all host threads.
@@ -318,8 +319,9 @@ def dist_env():
 # ----------------------------------------------------------------------------------------------------------------
 def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     """config 5: K-entry database sharded by contiguous ranges over the ranks; Q replicated queries per step.
-    Orchestration = liorf_b200/sc_sharded.py (two small all_gathers per batch when world > 1).  The ring-key stage runs on
-    the tensor cores (csrc/sc_tensor.cuh); its GEMM kernel is timed live by the library's CUDA events."""
+    One library call per batch and rank (liorf_b200/sc_sharded.py: PeerShardedSearch → liorf_sc_shard_query_dev): the exchange is done by
+    the kernels through NVLink peer windows (csrc/sc_shard.cuh), the batch is replayed from a CUDA graph.  The ring-key stage runs on
+    the tensor cores (csrc/sc_tensor.cuh); its GEMM kernel is timed live by the library's CUDA events in a few extra batches."""
     import torch
     import liorf_b200
     from liorf_b200.sc_sharded import GpuOps, ShardedScanContextSearch
