@@ -376,7 +376,8 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
         ctx.enableTiming(True)
         if world > 1:
             dist.barrier()
-        for _ in range(max(3, reps_n // 2)):
+        n_timed = max(3, reps_n // 2)
+        for _ in range(n_timed):
             one()
         ctx.sync()
         tm = ctx.getTiming(); ctx.enableTiming(False)
@@ -391,7 +392,7 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
                    planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((shn[ok] == shift[ok]).sum()),
                    ringkey_path="tcgen05 filter + exact re-rank" if tm["sc_gemm"][1] > 0 else "cuda-core brute force",
                    exchange=("NVLink peer windows (push + system-scope flags from the kernels, 4 phases per batch), no NCCL; batch replayed from a CUDA graph" if world > 1 else "none (one shard)"),
-                   ringkey_stage_ms=2 * tm["sc_search"][0] / max(tm["sc_search"][1], 1), candidates_per_query=st["candidates"] / max(Qn, 1) * 32,
+                   ringkey_stage_ms=tm["sc_search"][0] / n_timed, candidates_per_query=st["candidates"] / max(Qn, 1) * 32,
                    overflow_queries=st["overflow"],
                    peer_wait_us_per_batch={k: v / 1e3 / reps_n for k, v in waits.items()},      # rank 0: time its consumer kernels spent waiting for the peers' pushes
                    roofline=dict(kernel="k_sc_tensor", bound="tensor", achieved=tflops, peak=peaks.get("bf16_tflops"), unit="TFLOP/s",

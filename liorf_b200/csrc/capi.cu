@@ -1349,6 +1349,12 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     int* cand = d_cand ? (int*)d_cand : c->sc_q_i.p;
     const int pairs = 3 * Q;
     const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && c->sc_n >= 4096);
+    if (S.W.world == 1 && phases == 31) {       // one rank, whole batch: nothing to exchange → the plain search (same kernels, one pass over the descriptors)
+        if ((rc = liorf_sc_prepare_queries_dev(c, qd, Q, c->sc_qkeys.p, c->sc_qsk.p, c->sc_qcn.p))) return rc;
+        if ((rc = sc_knn(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, global_offset, c->sc_q_d.p, cand))) return rc;
+        if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, c->sc_pair_d.p, c->sc_pair_s.p))) return rc;
+        return liorf_sc_decide_dev(c, c->sc_pair_d.p, c->sc_pair_s.p, cand, Q, d_loop_id, d_shift, d_dist);
+    }
     if (phases & 16) {       // phase K: ring keys of this rank's slice of the queries → every window; the sector keys / column norms stage 2 needs
         k_scsh_next_batch<<<1, 1, 0, c->stream>>>(S.d_batch);
         const int q0 = (int)((long long)Q * S.W.rank / S.W.world), q1 = (int)((long long)Q * (S.W.rank + 1) / S.W.world);
