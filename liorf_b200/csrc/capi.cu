@@ -1069,10 +1069,9 @@ static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, 
         c->launches += 3;
         if (shard_phase == 1) {      // phase T: this rank's inflated top-3 tile minima go to every window
             if ((rc = S.u3.reserve((size_t)3 * Q)) || (rc = S.thr.reserve(Q))) return rc;
-            k_scsh_u3<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->sct_part.p, rows, c->sct_qnorm.p, Q, c->sct_nmax, S.u3.p);
-            k_scsh_push<<<std::min(64, (3 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_T, reinterpret_cast<const unsigned*>(S.u3.p), (size_t)3 * Q, S.d_batch, S.d_counter);
+            k_scsh_u3_push<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, c->sct_part.p, rows, c->sct_qnorm.p, Q, c->sct_nmax, S.d_batch, S.d_counter);
             CUDA_TRY(cudaGetLastError());
-            c->launches += 2;
+            c->launches += 1;
             return LIORF_OK;
         }
     }
@@ -1378,11 +1377,10 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
         }
     }
     if (phases & 4) {        // merge to the global top-3, owner-computes distanceBtnScanContext, push
-        k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, Q, c->sc_q_d.p, cand, c->d_err);
-        // the pairs this rank owns → compact list → stage 2 on exactly those, results pushed by the stage-2 kernel itself
+        // global top-3 + the compact list of the pairs this rank owns → stage 2 on exactly those, results pushed by the stage-2 kernel itself
         CUDA_TRY(cudaMemsetAsync(S.d_nlist, 0, sizeof(int), c->stream));
-        k_scsh_owned_list<<<(pairs + 255) / 256, 256, 0, c->stream>>>(cand, pairs, global_offset, c->sc_n, S.list.p, S.d_nlist);
-        k_scsh_skcn_owned<<<Q, 64, 0, c->stream>>>(qd, cand, Q, global_offset, c->sc_n, c->sc_qsk.p, c->sc_qcn.p);      // sector keys / column norms of the queries whose candidates this rank owns
+        k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, Q, c->sc_q_d.p, cand, c->d_err, global_offset, c->sc_n, S.list.p, S.d_nlist);
+        k_scsh_skcn_owned<<<std::min(3 * Q, 32 * c->num_sms), 64, 0, c->stream>>>(qd, S.list.p, S.d_nlist, c->sc_qsk.p, c->sc_qcn.p);      // sector keys / column norms of the queries whose candidates this rank owns
         ShardPush P; P.enabled = 1; P.Q = Q; P.W = S.W; P.counter = S.d_counter; P.batch_p = S.d_batch;
         if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, nullptr, nullptr, S.list.p, S.d_nlist, &P))) return rc;
     }

@@ -90,22 +90,38 @@ __global__ void __launch_bounds__(256) k_scsh_gather_keys(ShardWin W, const unsi
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) dst[i] = __ldcg(src + i);
 }
 
-// phase T producer: merge the per-split partial top-3 tile minima of a query and inflate them by this rank's error bound:
-// u_j = m_j + eps_r(q) is an upper bound of the TRUE distance of a distinct database key
-__global__ void __launch_bounds__(128) k_scsh_u3(const float* __restrict__ part, int n_rows, const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
-                                                float* __restrict__ u3) {
+// phase T producer: merge the per-split partial top-3 tile minima of a query, inflate them by this rank's error bound —
+// u_j = m_j + eps_r(q) is an upper bound of the TRUE distance of a distinct database key — and store them straight into slot
+// [my rank] of every window; the last block raises the flags (compute + transfer in one kernel)
+__global__ void __launch_bounds__(128) k_scsh_u3_push(ShardWin W, const float* __restrict__ part, int n_rows, const float* __restrict__ qnorm, int Q,
+                                                     const unsigned* __restrict__ nmax_bits, const unsigned* __restrict__ batch_p, unsigned* counter) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
+    if (q < Q) {
+        float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
 #pragma unroll
-    for (int sp = 0; sp < SCS_SPLITS; ++sp) {
-        const float* p = part + ((size_t)sp * n_rows + q) * 3;
-        top3_min_update(p[0], t1, t2, t3); top3_min_update(p[1], t1, t2, t3); top3_min_update(p[2], t1, t2, t3);
+        for (int sp = 0; sp < SCS_SPLITS; ++sp) {
+            const float* p = part + ((size_t)sp * n_rows + q) * 3;
+            top3_min_update(p[0], t1, t2, t3); top3_min_update(p[1], t1, t2, t3); top3_min_update(p[2], t1, t2, t3);
+        }
+        const float eps = SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits));
+        const float u1 = t1 < 1.0e38f ? t1 + eps : 3.0e38f, u2 = t2 < 1.0e38f ? t2 + eps : 3.0e38f, u3 = t3 < 1.0e38f ? t3 + eps : 3.0e38f;
+        for (int g = 0; g < W.world; ++g) {
+            float* o = reinterpret_cast<float*>(W.base[g] + W.off[SCSH_T] + (size_t)W.rank * W.stride[SCSH_T]) + 3 * (size_t)q;
+            o[0] = u1; o[1] = u2; o[2] = u3;
+        }
     }
-    const float eps = SCT_EPS_REL * (qnorm[q] + __uint_as_float(*nmax_bits));
-    u3[3 * (size_t)q + 0] = t1 < 1.0e38f ? t1 + eps : 3.0e38f;
-    u3[3 * (size_t)q + 1] = t2 < 1.0e38f ? t2 + eps : 3.0e38f;
-    u3[3 * (size_t)q + 2] = t3 < 1.0e38f ? t3 + eps : 3.0e38f;
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) { const unsigned t = atomicAdd(counter, 1u); s_last = (t == gridDim.x - 1); }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *counter = 0u;
+    __threadfence_system();
+    if ((int)threadIdx.x < W.world && (int)threadIdx.x != W.rank) {
+        unsigned* f = reinterpret_cast<unsigned*>(W.base[threadIdx.x] + scsh_flag_off(W.rank, SCSH_T));
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(*batch_p) : "memory");
+    }
 }
 // phase T consumer: U3(q) = third smallest over all ranks' bounds >= the true global third-smallest distance d3; a key of THIS
 // rank in the global top-3 has d~ <= d + eps_r <= d3 + eps_r <= U3 + eps_r =: thr(q)
@@ -123,37 +139,52 @@ __global__ void __launch_bounds__(128) k_scsh_thr(ShardWin W, const unsigned* __
     thr[q] = t3 < 1.0e38f ? t3 + eps : 3.0e38f;
 }
 
-// phase C consumer: the G local top-3 lists → global top-3 by (dist, idx)   [same arithmetic as k_sc_merge_top3]
-__global__ void __launch_bounds__(128) k_scsh_merge(ShardWin W, const unsigned* __restrict__ batch, int Q, float* __restrict__ out_d, int* __restrict__ out_i, int* err_flag) {
+// phase C consumer: the G local top-3 lists → global top-3 by (dist, idx)   [same arithmetic as k_sc_merge_top3]; the pairs whose
+// candidate THIS rank owns go to a compact list on the way (order irrelevant: stage-2 results are keyed by the pair id)
+__global__ void __launch_bounds__(128) k_scsh_merge(ShardWin W, const unsigned* __restrict__ batch, int Q, float* __restrict__ out_d, int* __restrict__ out_i, int* err_flag,
+                                                   int own_begin, int own_count, int* __restrict__ list, int* __restrict__ n_list) {
     scsh_wait(W, SCSH_C, batch, err_flag);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
     Top3 t; top3_init(t);
-    for (int g = 0; g < W.world; ++g) {
-        const float* pd = reinterpret_cast<const float*>(W.base[W.rank] + W.off[SCSH_C] + (size_t)g * W.stride[SCSH_C]);
-        const int* pi = reinterpret_cast<const int*>(pd + 3 * (size_t)Q);
+    if (q < Q) {
+        for (int g = 0; g < W.world; ++g) {
+            const float* pd = reinterpret_cast<const float*>(W.base[W.rank] + W.off[SCSH_C] + (size_t)g * W.stride[SCSH_C]);
+            const int* pi = reinterpret_cast<const int*>(pd + 3 * (size_t)Q);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { const int i = __ldcg(pi + 3 * (size_t)q + j); if (i != 0x7fffffff) top3_insert(t, __ldcg(pd + 3 * (size_t)q + j), i); }
+            for (int j = 0; j < 3; ++j) { const int i = __ldcg(pi + 3 * (size_t)q + j); if (i != 0x7fffffff) top3_insert(t, __ldcg(pd + 3 * (size_t)q + j), i); }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { out_d[3 * (size_t)q + j] = t.d[j]; out_i[3 * (size_t)q + j] = t.i[j]; }
     }
+    if (!list) return;
+    int n_own = 0; bool own[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { out_d[3 * (size_t)q + j] = t.d[j]; out_i[3 * (size_t)q + j] = t.i[j]; }
+    for (int j = 0; j < 3; ++j) { own[j] = q < Q && t.i[j] != 0x7fffffff && t.i[j] - own_begin >= 0 && t.i[j] - own_begin < own_count; n_own += own[j] ? 1 : 0; }
+    int incl = n_own;                                        // warp-aggregated append: one atomic per warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane_id() >= o) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int base = 0;
+    if (lane_id() == 31 && total > 0) base = atomicAdd(n_list, total);
+    base = __shfl_sync(FULL, base, 31) + incl - n_own;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) if (own[j]) list[base++] = 3 * q + j;
 }
 
-// sector key and column norms (k_sc_keys_batch arithmetic) of the queries that have at least one candidate in THIS rank's rows: the
-// other queries' descriptors (9.6 kB each) are never read here
-__global__ void __launch_bounds__(64) k_scsh_skcn_owned(const double* __restrict__ desc, const int* __restrict__ cand, int Q, int own_begin, int own_count,
+// sector key and column norms (k_sc_keys_batch arithmetic) of the queries of the pairs THIS rank owns, one CTA per list entry (a query
+// with two owned candidates is simply written twice with the same values); the other queries' descriptors are never read here
+__global__ void __launch_bounds__(64) k_scsh_skcn_owned(const double* __restrict__ desc, const int* __restrict__ list, const int* __restrict__ n_list,
                                                         double* __restrict__ sectorkey, double* __restrict__ colnorm) {
-    const int e = blockIdx.x; if (e >= Q) return;
-    bool own = false;
-#pragma unroll
-    for (int j = 0; j < SC_NUM_CAND; ++j) { const int c = cand[3 * (size_t)e + j]; own |= (c != 0x7fffffff && c - own_begin >= 0 && c - own_begin < own_count); }
-    if (!own) return;
+    const int n = *n_list;
     const int t = threadIdx.x;
-    if (t < SC_SECTOR) {
-        double s = 0, q = 0;
-        for (int r = 0; r < SC_RING; ++r) { const double v = desc[(size_t)e * SC_DESC + r * SC_SECTOR + t]; s += v; q += v * v; }
-        sectorkey[(size_t)e * SC_SECTOR + t] = s / SC_RING;
-        colnorm[(size_t)e * SC_SECTOR + t] = sqrt(q);
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const int e = list[it] / 3;
+        if (t < SC_SECTOR) {
+            double s = 0, q = 0;
+            for (int r = 0; r < SC_RING; ++r) { const double v = desc[(size_t)e * SC_DESC + r * SC_SECTOR + t]; s += v; q += v * v; }
+            sectorkey[(size_t)e * SC_SECTOR + t] = s / SC_RING;
+            colnorm[(size_t)e * SC_SECTOR + t] = sqrt(q);
+        }
     }
 }
 

@@ -420,7 +420,7 @@ __device__ __forceinline__ void sct_emit_tile(const float* __restrict__ cmin32, 
 }
 __global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __restrict__ cmin, const float* __restrict__ cmin32, int n_chunks, int n_rows, const float* __restrict__ part,
                                                                const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
-                                                               int* __restrict__ cand, int* __restrict__ cand_cnt, const float* __restrict__ thr_in = nullptr) {
+                                                               int* __restrict__ cand, int* __restrict__ cand_cnt, const float* __restrict__ thr_in = nullptr) {   // thr_in: sharded search (sc_shard.cuh)
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane;
     if (q >= Q) return;
