@@ -76,6 +76,9 @@ int liorf_project_point_cloud_dev(liorf_ctx* ctx, const void* d_pts, int n, doub
 /* sets laserCloudSurfLast from a host cloud (what pcl::fromROSMsg does at src/mapOptmization.cpp:244) */
 int liorf_set_current_scan(liorf_ctx* ctx, const liorf_point* scan, int n);
 int liorf_set_current_scan_dev(liorf_ctx* ctx, const void* d_scan, int n);
+/* laserCloudSurfLast straight from cloud_info.cloud_deskewed (msg/cloud_info.msg:27, src/mapOptmization.cpp:245): the PointCloud2 data block with
+ * `point_step` bytes per point (32 for PCL's padded PointXYZI, include/utility.h:61), xyz at offset_xyz, intensity at offset_intensity (16) */
+int liorf_set_current_scan_strided(liorf_ctx* ctx, const void* data, int n, int point_step, int offset_xyz, int offset_intensity, int data_on_device);
 /* replaces mapOptimization::downsampleCurrentScan() (src/mapOptmization.cpp:1061): VoxelGrid(mappingSurfLeafSize) of
  * laserCloudSurfLast → laserCloudSurfLastDS.  out (nullable, capacity = input size), n_ds (nullable: skip the read-back).
  * membership (nullable, capacity = input size): output slot of every input point (bit-exact voxel membership). */

@@ -166,6 +166,12 @@ class Context:
         scan = _p4(scan)
         _chk(self.lib.liorf_set_current_scan(self.h, _vp(scan), C.c_int(len(scan))), "liorf_set_current_scan")
 
+    def setCurrentScanStrided(self, data, n, point_step, offset_xyz=0, offset_intensity=16):
+        """laserCloudSurfLast from a PointCloud2 data block (bytes / uint8 array): PCL's PointXYZI is 32 bytes per point, intensity at 16"""
+        buf = np.ascontiguousarray(np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1))
+        _chk(self.lib.liorf_set_current_scan_strided(self.h, _vp(buf), C.c_int(n), C.c_int(point_step), C.c_int(offset_xyz), C.c_int(offset_intensity), C.c_int(0)),
+             "liorf_set_current_scan_strided")
+
     def setCurrentScanDev(self, d_ptr, n):
         _chk(self.lib.liorf_set_current_scan_dev(self.h, C.c_void_p(d_ptr), C.c_int(n)), "liorf_set_current_scan_dev")
 

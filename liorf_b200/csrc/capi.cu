@@ -106,7 +106,7 @@ struct liorf_ctx {
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
     bool sct_attr_set = false; int sct_last_Q = 0; bool scdb_attr_set = false; int scdb_blocks_per_sm = 1;
     Profiler prof;
-    double host_us[6] = {0, 0, 0, 0, 0, 0}; long long host_frames = 0; bool host_timing = false;   // LIORF_HOST_TIMING=1
+    double host_us[12] = {0}; long long host_frames = 0; bool host_timing = false;   // LIORF_HOST_TIMING=1 ([6..10]: pieces of the keyframe tail)
     cudaEvent_t tl_ev[8] = {nullptr}; double tl_ms[8] = {0}; // debug GPU timeline stamps of process_frame
     long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
     // ---- pipelined front end (cloudHandler of frame i+1 overlaps laserCloudInfoHandler of frame i) ----
@@ -354,6 +354,8 @@ void liorf_destroy(liorf_ctx* c) {
         const char* nm[6] = {"enqueue deskew", "select+enqueue map", "enqueue downsample", "enqueue solver", "wait pose (sync)", "keyframe+sc+loop"};
         fprintf(stderr, "[liorf_b200] host timeline per frame over %lld frames:", c->host_frames);
         for (int k = 0; k < 6; ++k) fprintf(stderr, "  %s %.1f us;", nm[k], c->host_us[k] / c->host_frames);
+        fprintf(stderr, "\n[liorf_b200] keyframe tail per frame: save+add keyframe %.1f; extract_nearby(next) %.1f; enqueue next map %.1f; ScanContext make %.1f; loop detection %.1f us",
+                c->host_us[6] / c->host_frames, c->host_us[7] / c->host_frames, c->host_us[8] / c->host_frames, c->host_us[9] / c->host_frames, c->host_us[10] / c->host_frames);
         fprintf(stderr, "\n[liorf_b200] GPU timeline (us after frame start): deskew done %.1f; map+grid done %.1f; downsample done %.1f; joined %.1f; solver done %.1f\n",
                 1e3 * c->tl_ms[1] / c->host_frames, 1e3 * c->tl_ms[2] / c->host_frames, 1e3 * c->tl_ms[3] / c->host_frames, 1e3 * c->tl_ms[4] / c->host_frames,
                 1e3 * c->tl_ms[5] / c->host_frames);
@@ -485,6 +487,47 @@ static int set_scan_common(liorf_ctx* c, const void* src, int n, cudaMemcpyKind 
     CUDA_TRY(cudaMemcpyAsync(c->d_counts + C_N_SCAN, &c->h_mail[100], sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->n_scan_bound = n; c->h_n_scan = n; c->h_n_ds = -1;
+    return LIORF_OK;
+}
+// cloud_info.cloud_deskewed as mapOptimization receives it (msg/cloud_info.msg:27; pcl::fromROSMsg into PointXYZI, include/utility.h:61):
+// a sensor_msgs/PointCloud2 data block with `point_step` bytes per point (32 for PCL's padded PointXYZI), x, y, z as three consecutive floats
+// at offset_xyz and the intensity float at offset_intensity (16).  The block is copied as it is and unpacked to the library's 16-byte points
+// on the device, so a ROS shim can hand msg.data straight to the library.
+__global__ void __launch_bounds__(256) k_unpack_strided(const unsigned char* __restrict__ raw, int n, int step, int off_xyz, int off_i, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* p = raw + (size_t)i * step;
+    float4 o;
+    if (((step | off_xyz | off_i) & 3) == 0 && (reinterpret_cast<size_t>(raw) & 3) == 0) {
+        const float* f = reinterpret_cast<const float*>(p + off_xyz);
+        o.x = f[0]; o.y = f[1]; o.z = f[2]; o.w = *reinterpret_cast<const float*>(p + off_i);
+    } else {                                                       // unaligned layouts: byte-wise
+        float v[4];
+        for (int k = 0; k < 3; ++k) { unsigned u = 0; for (int b = 0; b < 4; ++b) u |= (unsigned)p[off_xyz + 4 * k + b] << (8 * b); v[k] = __uint_as_float(u); }
+        { unsigned u = 0; for (int b = 0; b < 4; ++b) u |= (unsigned)p[off_i + b] << (8 * b); v[3] = __uint_as_float(u); }
+        o = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    out[i] = o;
+}
+int liorf_set_current_scan_strided(liorf_ctx* c, const void* data, int n, int point_step, int offset_xyz, int offset_intensity, int data_on_device) {
+    if (!c || n < 0 || (n > 0 && !data) || point_step < 16 || offset_xyz < 0 || offset_intensity < 0 || offset_xyz + 12 > point_step || offset_intensity + 4 > point_step)
+        return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if ((rc = c->scan.reserve(n > 0 ? n : 1))) return rc;
+    const unsigned char* d_raw = (const unsigned char*)data;
+    if (!data_on_device && n > 0) {
+        const size_t bytes = (size_t)n * point_step;
+        if ((rc = c->dk.raw.reserve((bytes + sizeof(RawPoint) - 1) / sizeof(RawPoint)))) return rc;       // the raw-scan staging buffer doubles as the byte staging area
+        CUDA_TRY(cudaMemcpyAsync(c->dk.raw.p, data, bytes, cudaMemcpyHostToDevice, c->stream));
+        d_raw = reinterpret_cast<const unsigned char*>(c->dk.raw.p);
+    }
+    if (n > 0) k_unpack_strided<<<(n + 255) / 256, 256, 0, c->stream>>>(d_raw, n, point_step, offset_xyz, offset_intensity, c->scan.p);
+    CUDA_TRY(cudaGetLastError());
+    c->h_mail[100] = n;
+    CUDA_TRY(cudaMemcpyAsync(c->d_counts + C_N_SCAN, &c->h_mail[100], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->n_scan_bound = n; c->h_n_scan = n; c->h_n_ds = -1; c->launches += 1;
     return LIORF_OK;
 }
 int liorf_set_current_scan(liorf_ctx* c, const liorf_point* scan, int n) {
@@ -1701,10 +1744,13 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
     }
     std::memcpy(c->tf_mapped, out->pose, sizeof(c->tf_mapped));
     // saveKeyFramesAndFactor (the parts on the path): saveFrame gate, keyframe cloud, ScanContext descriptor
+    auto T1 = clk::now();
+    auto sub = [&](int k) { if (c->host_timing) { auto t = clk::now(); c->host_us[k] += std::chrono::duration<double, std::micro>(t - T1).count(); T1 = t; } };
     if (liorf_save_frame(c, out->pose, in->adding_dist_threshold, in->adding_angle_threshold) == 1) {
         int id = liorf_add_keyframe(c, out->pose, in->time_scan_cur);
         if (id < 0) return id;
         out->is_keyframe = 1; out->keyframe_id = id;
+        sub(6);
         // A new keyframe changes the NEXT frame's local map.  With look-ahead its timestamp is known, so extractSurroundingKeyFrames
         // for that frame is launched right here (stream_map, behind the keyframe copy only) instead of after the host has returned,
         // built the next call and come back; the next call's identical request then finds the map resident.
@@ -1713,13 +1759,17 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
             std::vector<liorf_host::KeyPose> kp(c->kfs.size());
             for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }
             std::vector<int> sel = liorf_host::extract_nearby(kp, nx->time_scan_cur, c->P.surroundingKeyframeSearchRadius, nx->surrounding_keyframe_density);
+            sub(7);
             if ((rc = liorf_extract_surrounding_keyframes(c, sel.data(), (int)sel.size(), nullptr))) return rc;
+            sub(8);
         }
         if ((rc = liorf_sc_make_and_save(c, nullptr, 0))) return rc;
+        sub(9);
     }
     if (in->loop_every > 0 && in->frame_index % in->loop_every == in->loop_every - 1) {
         out->loop_checked = 1;
         if ((rc = liorf_sc_detect_loop_closure_id(c, &out->loop_id, &out->loop_yaw, nullptr, nullptr))) return rc;
+        sub(10);
     }
     lap(5); ++c->host_frames;
     return LIORF_OK;

@@ -47,26 +47,34 @@ __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const doub
         const double* cn1 = qcn + (size_t)q * SC_SECTOR; const double* cn2 = db_cn + (size_t)lc * SC_SECTOR;
         __syncwarp();                                                   // every lane is done with the previous pair's buffers
         if (l == 0) { mbar_expect_tx(bar, SC_DESC * 8); bulk_g2s(smem_u32(s_sc2), db_desc + (size_t)lc * SC_DESC, SC_DESC * 8, bar); }
-        for (int k = l; k < SC_SECTOR; k += 32) { s_vk1[k] = qsk[(size_t)q * SC_SECTOR + k]; s_vk2[k] = db_sk[(size_t)lc * SC_SECTOR + k]; }
+        // the candidate's sector key twice in a row (in the not yet used similarity buffer): circshift(vkey2, s)[k] = vk2d[k - s + 60]
+        // is then a plain offset from a per-lane base — no modular index arithmetic inside the 60-step sums
+        double* s_vk2d = &s_sim[0][0];
+        for (int k = l; k < SC_SECTOR; k += 32) {
+            s_vk1[k] = qsk[(size_t)q * SC_SECTOR + k];
+            const double v = db_sk[(size_t)lc * SC_SECTOR + k];
+            s_vk2[k] = v; s_vk2d[k] = v; s_vk2d[k + SC_SECTOR] = v;
+        }
         __syncwarp();
         // fastAlignUsingVkey (:93-113): lane ↔ shift, sequential sum over columns; first strict minimum of the norm
         double best = 10000000.0; int best_s = 0x7fffffff;
         {
             const int sA = l, sB = l + 32;
             const bool hasB = sB < SC_SECTOR;
+            const double* pA = s_vk2d + SC_SECTOR - sA;
+            const double* pB = s_vk2d + SC_SECTOR - (hasB ? sB : 0);
             double ssA = 0, ssB = 0;
 #pragma unroll 12
             for (int k = 0; k < SC_SECTOR; ++k) {
-                int kA = k - sA; if (kA < 0) kA += SC_SECTOR;
-                int kB = k - (hasB ? sB : 0); if (kB < 0) kB += SC_SECTOR;
                 const double v1 = s_vk1[k];
-                const double dA = v1 - s_vk2[kA], dB = v1 - s_vk2[kB];
+                const double dA = v1 - pA[k], dB = v1 - pB[k];
                 ssA += dA * dA; ssB += dB * dB;
             }
             const double nA = sqrt(ssA), nB = sqrt(ssB);
             if (nA < best) { best = nA; best_s = sA; }
             if (hasB && nB < best) { best = nB; best_s = sB; }
         }
+        __syncwarp();                                                   // the similarity buffer is free again
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ob = __shfl_xor_sync(FULL, best, o); int os = __shfl_xor_sync(FULL, best_s, o);

@@ -131,3 +131,28 @@ def test_global_map_filters(oracle, synth):
     g2 = c.buildGlobalMap(search_radius=40.0, pose_density=10.0, leaf=1.0)
     assert np.array_equal(g2, oracle.voxel_grid(o_sel, 1.0)[0])
     c.close()
+
+
+def test_cloud_deskewed_wire_format(ctx, oracle, synth):
+    """mapOptimization receives laserCloudSurfLast as cloud_info.cloud_deskewed (msg/cloud_info.msg:27): a PointCloud2 block of PCL
+    PointXYZI points — 32 bytes each, x y z at 0, intensity at 16, padding elsewhere (include/utility.h:61).  Feeding that block as it
+    is gives the same downsampled cloud, bit for bit, as feeding packed 16-byte points; an odd 21-byte layout exercises the unaligned path."""
+    scan = synth.raw_to_xyzi(synth.scan(synth.HDL64, (0, 0, 0, 2.0, 0, 0), seed=synth.SEED0 + 5))[::7].copy()
+    n = len(scan)
+    ctx.setCurrentScan(scan)
+    ref_ds, n_ref = ctx.downsampleCurrentScan(n)
+    o_ds, _, _ = oracle.voxel_grid(scan, 0.4)
+    assert n_ref == len(o_ds) and np.array_equal(ref_ds[:n_ref], o_ds)
+    rng = np.random.default_rng(3)
+    pcl = rng.integers(0, 255, size=(n, 32), dtype=np.uint8)                  # padding bytes are garbage on purpose
+    pcl[:, 0:12] = scan[:, :3].copy().view(np.uint8).reshape(n, 12)
+    pcl[:, 16:20] = scan[:, 3:4].copy().view(np.uint8).reshape(n, 4)
+    ctx.setCurrentScanStrided(pcl, n, 32, 0, 16)
+    ds, n_ds = ctx.downsampleCurrentScan(n)
+    assert n_ds == n_ref and np.array_equal(ds[:n_ds], ref_ds[:n_ref])
+    odd = rng.integers(0, 255, size=(n, 21), dtype=np.uint8)
+    odd[:, 5:17] = scan[:, :3].copy().view(np.uint8).reshape(n, 12)
+    odd[:, 1:5] = scan[:, 3:4].copy().view(np.uint8).reshape(n, 4)
+    ctx.setCurrentScanStrided(odd, n, 21, 5, 1)
+    ds2, n_ds2 = ctx.downsampleCurrentScan(n)
+    assert n_ds2 == n_ref and np.array_equal(ds2[:n_ds2], ref_ds[:n_ref])
