@@ -399,6 +399,38 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
                                  frac=(tflops / peaks["bf16_tflops"]) if tflops and peaks.get("bf16_tflops") else None, traffic=None,
                                  avg_launch_ms=gemm_ms,
                                  note="executed tensor-core flops: 2 x 64 (split-bf16 contraction) x Kpad x Qpad per launch; the distance itself is 3 x 20 flops per pair"))
+        if world == 1:
+            # stage 2 alone (distanceBtnScanContext for the 3 Q pairs of this batch), timed live: the HBM-bound kernel of the search.
+            # Algorithmic bytes per pair: the candidate's 9 600-byte descriptor + a third of the query's (three pairs share it) + sector
+            # keys and column norms of both (4 x 480 B).
+            import ctypes as C
+            with torch.cuda.stream(ops.stream):
+                qq = ops.prepare_dev(d_q)
+                pd_ = torch.empty((Qn, 3), dtype=torch.float64, device=dev); ps_ = torch.empty((Qn, 3), dtype=torch.int32, device=dev)
+            vp = lambda t_: C.c_void_p(t_.data_ptr())
+            call = lambda: ctx.lib.liorf_sc_distance_batch_dev(ctx.h, vp(d_q), vp(qq["sk"]), vp(qq["cn"]), vp(cand), Qn, 0, vp(pd_), vp(ps_))
+            for _ in range(2):
+                call()
+            ctx.sync()
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ops.stream):
+                s0.record()
+            for _ in range(5):
+                call()
+            with torch.cuda.stream(ops.stream):
+                s1.record()
+            ctx.sync()
+            s2_ms = s0.elapsed_time(s1) / 5
+            alg = 3 * Qn * (9600 + 9600 / 3 + 4 * 480)
+            traffic2 = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic2 = tj.get("sc_distance_bulk", {}).get("dram_bytes_per_launch") if Qn == 32768 else None
+            except Exception:
+                pass
+            res["stage2_roofline"] = dict(kernel="k_sc_distance_bulk", bound="hbm", achieved=alg / (s2_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                                          frac=alg / (s2_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=traffic2, algorithmic_bytes_per_launch=alg, avg_launch_ms=s2_ms,
+                                          pairs=3 * Qn, note="fp64 sums in the reference's sequential order: ~3 300 warp-instructions per pair, issue slots 54 % busy (ncu)")
         return res, qd
     res, qd = run(Q, reps)
     if q_large > Q:
