@@ -317,7 +317,7 @@ def dist_env():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
+def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0, sc_lanes=2):
     """config 5: K-entry database sharded by contiguous ranges over the ranks; Q replicated queries per step.
     One library call per batch and rank (liorf_b200/sc_sharded.py: PeerShardedSearch → liorf_sc_shard_query_dev): the exchange is done by
     the kernels through NVLink peer windows (csrc/sc_shard.cuh), the batch is replayed from a CUDA graph.  The ring-key stage runs on
@@ -345,26 +345,52 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     from liorf_b200.sc_sharded import PeerShardedSearch
     peer = PeerShardedSearch(ctx, rank, world, [g * kloc for g in range(world + 1)], max(Q, q_large), torch)
     peer.connect_processes(dist)
+    # LANES query batches in flight per GPU: a batch is a chain of ~25 small dependent kernels and 4 exchanges that leaves most SMs idle most
+    # of the time; a second context on its own stream (and its own peer windows) searches the SAME database (liorf_sc_borrow_database, nothing
+    # copied) and takes every other batch
+    lanes = [(ctx, peer)]
+    for _ in range(max(1, sc_lanes) - 1):
+        c2 = liorf_b200.Context(device=ctx_device)
+        c2.scBorrowDatabase(ctx)
+        p2 = PeerShardedSearch(c2, rank, world, [g * kloc for g in range(world + 1)], max(Q, q_large), torch)
+        p2.connect_processes(dist)
+        lanes.append((c2, p2))
 
     def run(Qn, reps_n):
         qd, src, shift = synth.sc_queries(sample, Qn)
         with torch.cuda.stream(ops.stream):
             d_q = torch.from_numpy(qd).to(dev)
+        torch.cuda.synchronize()                                   # every lane's stream reads d_q
+
+        turn = [0]
 
         def one():
-            return peer.query(d_q)
-        for _ in range(4):                                         # warm-up (the third identical request captures the batch as a CUDA graph)
+            k = turn[0] % len(lanes); turn[0] += 1
+            return lanes[k][1].query(d_q)
+
+        def sync_all():
+            for c_, _ in lanes:
+                c_.sync()
+            torch.cuda.synchronize()
+        lane_streams = [p_.stream for _, p_ in lanes]
+        for _ in range(4 * len(lanes)):                            # warm-up (the third identical request of a lane captures its batch as a CUDA graph)
             loop, sh, dd, cand = one()
-        ctx.sync()
+        sync_all()
         peer.wait_stats()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        turn[0] = 0
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(ops.stream):
             e0.record()
-        for _ in range(reps_n):
-            loop, sh, dd, cand = one()
+        for st_ in lane_streams[1:]:
+            st_.wait_event(e0)                                     # every lane starts inside the timed region
+        n_batches = reps_n * len(lanes)
+        for _ in range(n_batches):
+            one()
+        for st_ in lane_streams[1:]:
+            ops.stream.wait_stream(st_)                            # ... and ends inside it
         with torch.cuda.stream(ops.stream):
             e1.record()
         torch.cuda.synchronize()
@@ -378,8 +404,8 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
             dist.barrier()
         n_timed = max(3, reps_n // 2)
         for _ in range(n_timed):
-            one()
-        ctx.sync()
+            loop, sh, dd, cand = lanes[0][1].query(d_q)            # lane 0 only: its context is the one with the sections on
+        sync_all()
         tm = ctx.getTiming(); ctx.enableTiming(False)
         st = ctx.scTensorStats()
         lp = loop.cpu().numpy(); shn = sh.cpu().numpy()
@@ -388,13 +414,13 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
         gemm_ms = tm["sc_gemm"][0] / max(tm["sc_gemm"][1], 1)
         kpad, qpad = (kloc + 127) // 128 * 128, (Qn + 255) // 256 * 256
         tflops = 2.0 * 64 * kpad * qpad / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        res = dict(K=K, Q=Qn, shards=world, ms_per_batch=ms / reps_n, queries_per_s=Qn * reps_n / (ms * 1e-3),
+        res = dict(K=K, Q=Qn, shards=world, batches_in_flight=len(lanes), ms_per_batch=ms / n_batches, queries_per_s=Qn * n_batches / (ms * 1e-3),
                    planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((shn[ok] == shift[ok]).sum()),
                    ringkey_path="tcgen05 filter + exact re-rank" if tm["sc_gemm"][1] > 0 else "cuda-core brute force",
                    exchange=("NVLink peer windows (push + system-scope flags from the kernels, 4 phases per batch), no NCCL; batch replayed from a CUDA graph" if world > 1 else "none (one shard)"),
                    ringkey_stage_ms=tm["sc_search"][0] / n_timed, candidates_per_query=st["candidates"] / max(Qn, 1) * 32,
                    overflow_queries=st["overflow"],
-                   peer_wait_us_per_batch={k: v / 1e3 / reps_n for k, v in waits.items()},      # rank 0: time its consumer kernels spent waiting for the peers' pushes
+                   peer_wait_us_per_batch={k: v / 1e3 / reps_n for k, v in waits.items()},      # lane 0      # rank 0: time its consumer kernels spent waiting for the peers' pushes
                    roofline=dict(kernel="k_sc_tensor", bound="tensor", achieved=tflops, peak=peaks.get("bf16_tflops"), unit="TFLOP/s",
                                  frac=(tflops / peaks["bf16_tflops"]) if tflops and peaks.get("bf16_tflops") else None, traffic=None,
                                  avg_launch_ms=gemm_ms,
@@ -436,6 +462,8 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0):
     if q_large > Q:
         res["large_batch"], _ = run(q_large, max(2, reps // 2))
         res["large_batch"].pop("roofline", None)
+    for c_, _ in lanes[1:]:
+        c_.close()
     ctx.close()
     return res, (qd, sample)
 
@@ -492,6 +520,7 @@ def main():
     ap.add_argument("--sc-q-large", type=int, default=32768, help="second, larger query batch for the sharded search (0 = skip)")
     ap.add_argument("--batched", type=int, default=2, help="independent sequences in flight on one GPU for the batched figure (0 = skip)")
     ap.add_argument("--no-sc", action="store_true")
+    ap.add_argument("--sc-lanes", type=int, default=2, help="ScanContext query batches in flight per GPU (contexts sharing one database)")
     ap.add_argument("--cpu-frames", type=int, default=12, help="bounded CPU-baseline sample (frames)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -654,7 +683,7 @@ def main():
     # ---- ScanContext search (config 5) ----
     sc = None
     if not args.no_sc:
-        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 10, dist, peaks, q_large=args.sc_q_large)
+        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 10, dist, peaks, q_large=args.sc_q_large, sc_lanes=args.sc_lanes)
 
     # ---- CPU baseline (rank 0, N=1 only): the same frames on the host cores ----
     cpu = None

@@ -209,6 +209,9 @@ int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_
  *   liorf_sc_shard_connect : map the peers' windows (array of `world` handles or pointers, own entry ignored)
  *   liorf_sc_shard_query_dev: one batch, asynchronous on the context's stream; every rank passes the same queries in the same order;
  *                            global_offset = index of this rank's first database row */
+/* a second context on the same device searching the SAME database without copying it (several query batches in flight per GPU, one
+ * context / stream each); the borrower is read-only, the owner must outlive it and not grow the database meanwhile */
+int liorf_sc_borrow_database(liorf_ctx* dst, liorf_ctx* src);
 int liorf_sc_shard_init(liorf_ctx* ctx, int rank, int world, int q_max, void* ipc_handle_out, void** window_out);
 int liorf_sc_shard_connect(liorf_ctx* ctx, const void* ipc_handles, void* const* window_ptrs, const int* row_begin /* world + 1: rows [row_begin[g], row_begin[g+1]) on rank g */);
 int liorf_sc_shard_wait_stats(liorf_ctx* ctx, unsigned long long wait_ns[4], unsigned* batches);   /* time spent waiting for peers per phase (T, C, D, K), measurement */

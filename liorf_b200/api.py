@@ -406,6 +406,10 @@ class Context:
     def scSize(self):
         return self.lib.liorf_sc_size(self.h)
 
+    def scBorrowDatabase(self, owner):
+        """search the ScanContext database of another context on the same device without copying it (read-only)"""
+        _chk(self.lib.liorf_sc_borrow_database(self.h, owner.h), "liorf_sc_borrow_database")
+
     def scGet(self, i):
         d = np.zeros(1200, np.float64); k = np.zeros(20, np.float32); sk = np.zeros(60, np.float64)
         _chk(self.lib.liorf_sc_get(self.h, C.c_int(i), _vp(d), _vp(k), _vp(sk)), "liorf_sc_get")

@@ -85,7 +85,7 @@ struct liorf_ctx {
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
     float* d_lm_out = nullptr;      // AtA[36] AtB[6] X[6]
     // ScanContext
-    DevBuf<double> sc_desc, sc_sk, sc_cn; DevBuf<float> sc_keys; int sc_n = 0;
+    DevBuf<double> sc_desc, sc_sk, sc_cn; DevBuf<float> sc_keys; int sc_n = 0; bool sc_borrowed = false;   // borrowed: the database buffers belong to another context
     unsigned* d_bins = nullptr;
     int sc_tree_n = 0, sc_counter = 0;
     DevBuf<float> sc_part_d; DevBuf<int> sc_part_i;
@@ -220,6 +220,7 @@ static int read_counts(liorf_ctx* c) {
 
 static int sc_reserve(liorf_ctx* c, int n) {
     int rc;
+    if (c->sc_borrowed) return (size_t)n * SC_RING <= c->sc_keys.cap ? LIORF_OK : LIORF_ERR_STATE;      // a borrowed database is read-only here
     if ((rc = c->sc_desc.reserve((size_t)n * SC_DESC, c->stream, true)) || (rc = c->sc_sk.reserve((size_t)n * SC_SECTOR, c->stream, true)) ||
         (rc = c->sc_cn.reserve((size_t)n * SC_SECTOR, c->stream, true)) || (rc = c->sc_keys.reserve((size_t)n * SC_RING, c->stream, true))) return rc;
     return LIORF_OK;
@@ -387,7 +388,8 @@ void liorf_destroy(liorf_ctx* c) {
     c->vg.scan.status.release(); c->grid.scan.status.release(); c->dk.scan.status.release(); c->combine_scan.status.release();
     c->grid.counts.release(); c->grid.cell_start.release();
     c->dk.raw.release(); c->dk.imu.release(); c->dk.kept.release();
-    c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); c->sc_part_d.release(); c->sc_part_i.release();
+    if (!c->sc_borrowed) { c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); }
+    c->sc_part_d.release(); c->sc_part_i.release();
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
     c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
     c->sct_bimg.release(); c->sct_aimg.release(); c->sct_cmin.release(); c->sct_cmin32.release(); c->sct_qnorm.release(); c->sct_part.release(); c->sct_cand.release(); c->sct_cnt.release();
@@ -1002,6 +1004,7 @@ int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
     } else {
         d_pts = c->scan.p; cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, c->n_scan_bound);
     }
+    if (c->sc_borrowed) return LIORF_ERR_STATE;
     if ((rc = sc_reserve(c, c->sc_n + 1))) return rc;
     ProfScope ps(c, SEC_SC_MAKE); c->launches += 2;
     if (cnt.bound > 0) {
@@ -1022,6 +1025,7 @@ int liorf_sc_add_descriptors(liorf_ctx* c, const double* descs, int count) {
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
     if (count == 0) return LIORF_OK;
+    if (c->sc_borrowed) return LIORF_ERR_STATE;
     if ((rc = sc_reserve(c, c->sc_n + count))) return rc;
     const size_t e = (size_t)c->sc_n;
     CUDA_TRY(cudaMemcpyAsync(c->sc_desc.p + e * SC_DESC, descs, (size_t)count * SC_DESC * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1030,6 +1034,18 @@ int liorf_sc_add_descriptors(liorf_ctx* c, const double* descs, int count) {
     CUDA_TRY(cudaGetLastError());
     c->sc_n += count;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LIORF_OK;
+}
+/* A second context on the same device that searches the SAME database (descriptors, ring keys, sector keys, column norms are not copied):
+ * several query batches in flight on one GPU, each on its own context / stream.  The borrower never adds entries; the owner must outlive it
+ * and must not grow the database while it is borrowed. */
+int liorf_sc_borrow_database(liorf_ctx* dst, liorf_ctx* src) {
+    if (!dst || !src || dst == src || dst->P.device != src->P.device) return LIORF_ERR_ARG;
+    if (dst->sc_n != 0 || dst->sc_desc.p) return LIORF_ERR_STATE;
+    CUDA_TRY(cudaSetDevice(src->P.device));
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    dst->sc_desc = src->sc_desc; dst->sc_sk = src->sc_sk; dst->sc_cn = src->sc_cn; dst->sc_keys = src->sc_keys; dst->sc_n = src->sc_n;
+    dst->sc_borrowed = true;
     return LIORF_OK;
 }
 int liorf_sc_size(liorf_ctx* c) { return c ? c->sc_n : LIORF_ERR_ARG; }

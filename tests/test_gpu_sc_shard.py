@@ -115,3 +115,34 @@ def test_whole_batch_call_replays_from_a_graph(synth):
         assert np.array_equal(loop.cpu().numpy(), r_loop) and np.array_equal(sh.cpu().numpy(), r_sh), b
         assert np.array_equal(np.nan_to_num(dd.cpu().numpy(), nan=-7.0), np.nan_to_num(r_dist, nan=-7.0)), b
     ctx.close(); ref.close()
+
+
+def test_borrowed_database_two_batches_in_flight(synth):
+    """liorf_sc_borrow_database: a second context on the same device searches the owner's database without copying it, so two query batches
+    can be in flight on one GPU (own stream, own scratch, own peer windows each).  Both lanes must give the reference answers while running
+    concurrently, and the borrower must refuse to modify the database."""
+    import torch
+    import liorf_b200
+    from liorf_b200.sc_sharded import PeerShardedSearch
+    K, Q = 9000, 600
+    db = synth.sc_descriptors(K, seed=95)
+    owner = liorf_b200.Context(); owner.scAddDescriptors(db); owner.scSetSearchPath(2)
+    guest = liorf_b200.Context(); guest.scBorrowDatabase(owner); guest.scSetSearchPath(2)
+    with pytest.raises(liorf_b200.api.LiorfError):
+        guest.scAddDescriptors(db[:3])
+    lanes = []
+    for c in (owner, guest):
+        s = PeerShardedSearch(c, 0, 1, [0, K], Q, torch); s.connect_local([s]); lanes.append(s)
+    ref = liorf_b200.Context(); ref.scAddDescriptors(db)
+    qs = [synth.sc_queries(db, Q, seed=96 + b)[0] for b in range(2)]
+    d_q = [torch.from_numpy(q).to(lanes[0].dev) for q in qs]
+    torch.cuda.synchronize()
+    for rep in range(5):                                          # the third round replays both lanes from their CUDA graphs
+        outs = [lanes[k].query(d_q[k]) for k in range(2)]          # both enqueued before either is waited for
+        owner.sync(); guest.sync(); torch.cuda.synchronize()
+        for k in range(2):
+            r_loop, r_sh, r_dist, r_cand = ref.scQueryBatch(qs[k])
+            loop, sh, dd, cand = [t.cpu().numpy() for t in outs[k]]
+            assert np.array_equal(cand, r_cand) and np.array_equal(loop, r_loop) and np.array_equal(sh, r_sh), (rep, k)
+            assert np.array_equal(np.nan_to_num(dd, nan=-7.0), np.nan_to_num(r_dist, nan=-7.0)), (rep, k)
+    guest.close(); owner.close(); ref.close()
