@@ -520,7 +520,7 @@ def main():
     ap.add_argument("--sc-q-large", type=int, default=32768, help="second, larger query batch for the sharded search (0 = skip)")
     ap.add_argument("--batched", type=int, default=2, help="independent sequences in flight on one GPU for the batched figure (0 = skip)")
     ap.add_argument("--no-sc", action="store_true")
-    ap.add_argument("--sc-lanes", type=int, default=2, help="ScanContext query batches in flight per GPU (contexts sharing one database)")
+    ap.add_argument("--sc-lanes", type=int, default=0, help="ScanContext query batches in flight per GPU (contexts sharing one database); 0 = 2 on one GPU, 4 when sharded")
     ap.add_argument("--cpu-frames", type=int, default=12, help="bounded CPU-baseline sample (frames)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -683,7 +683,7 @@ def main():
     # ---- ScanContext search (config 5) ----
     sc = None
     if not args.no_sc:
-        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 10, dist, peaks, q_large=args.sc_q_large, sc_lanes=args.sc_lanes)
+        sc, (qd, sample) = bench_sc(local_rank, rank, world, args.sc_k, args.sc_q, 10, dist, peaks, q_large=args.sc_q_large, sc_lanes=args.sc_lanes if args.sc_lanes > 0 else (2 if world == 1 else 4))
 
     # ---- CPU baseline (rank 0, N=1 only): the same frames on the host cores ----
     cpu = None
