@@ -361,6 +361,8 @@ def bench_sc(ctx_device, rank, world, K, Q, reps, dist, peaks, q_large=0, sc_lan
         with torch.cuda.stream(ops.stream):
             d_q = torch.from_numpy(qd).to(dev)
         torch.cuda.synchronize()                                   # every lane's stream reads d_q
+        if world > 1:
+            dist.barrier()                                         # ranks generate their (identical) queries at different speeds; a batch waits only seconds for a peer
 
         turn = [0]
 
