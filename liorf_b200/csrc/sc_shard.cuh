@@ -49,7 +49,9 @@ __device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, const un
             while (true) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
                 if ((int)(v - batch) >= 0) break;
-                if (++spins > (1u << 22)) { atomicExch(err_flag, 3); break; }      // ~seconds: a peer that never arrives is an error, not a hang
+                // a peer that never arrives is an error, not a hang: give up after ~10 s, and at once if the error flag is already up (a dead
+                // peer must not cost this bound again in every later wait)
+                if ((++spins & 1023u) == 0u && (spins > (1u << 24) || *reinterpret_cast<volatile int*>(err_flag) != 0)) { atomicExch(err_flag, 3); break; }
             }
         }
         if (t0) { unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1)); W.wait_ns[phase] += t1 - t0; }
