@@ -190,24 +190,6 @@ __global__ void __launch_bounds__(64) k_scsh_skcn_owned(const double* __restrict
     }
 }
 
-__global__ void __launch_bounds__(256) k_scsh_fill_pairs(double* __restrict__ pd, int* __restrict__ ps, int n_pairs) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pairs) { pd[i] = INFINITY; ps[i] = 0; }
-}
-
-// the (query, candidate) pairs whose candidate THIS rank owns, as a compact list (order irrelevant: results are keyed by the pair id)
-__global__ void __launch_bounds__(256) k_scsh_owned_list(const int* __restrict__ cand, int n_pairs, int own_begin, int own_count, int* __restrict__ list, int* __restrict__ n_list) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool own = false;
-    if (i < n_pairs) { const int c = cand[i]; own = c != 0x7fffffff && c - own_begin >= 0 && c - own_begin < own_count; }
-    const unsigned m = __ballot_sync(FULL, own);
-    if (!m) return;
-    int base = 0;
-    if (lane_id() == __ffs(m) - 1) base = atomicAdd(n_list, __popc(m));
-    base = __shfl_sync(FULL, base, __ffs(m) - 1);
-    if (own) list[base + __popc(m & ((1u << lane_id()) - 1u))] = i;
-}
-
 // what the stage-2 kernel needs to push its results itself (sc_distance.cuh): every owned pair's {f64 dist, i32 shift} goes straight
 // from the warp that computed it into slot [my rank] of EVERY window; the last block raises the phase-D flags
 struct ShardPush { int enabled; int Q; ShardWin W; unsigned* counter; const unsigned* batch_p; };
