@@ -282,7 +282,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv is None:
