@@ -166,31 +166,24 @@ int liorf_sc_get(liorf_ctx* ctx, int i, double desc[1200], float ringkey[20], do
  * tree (rebuilt every 10th call over keys[0 : n-30]).  cand3 / min_dist nullable diagnostics. */
 int liorf_sc_detect_loop_closure_id(liorf_ctx* ctx, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3);
 /* batched search (BASELINE config 5): Q queries against the context's database rows [0, n_db) which represent GLOBAL
- * rows [global_offset, global_offset + n_db) of a sharded database (single GPU: offset 0).
- *   stage 1: local exact top-3 per query → (dist[Q*3], idx[Q*3]) in DEVICE memory (d_* pointers are device pointers)
- *   merge  : combines n_parts gathered lists [part][Q][3] into the global top-3
- *   stage 2: distanceBtnScanContext for owned candidates (others left untouched)
- *   decide : strict-< argmin in kNN order + threshold */
+ * rows [global_offset, global_offset + n_db) (single GPU: offset 0).  The steps of one batch on DEVICE buffers (d_* are device pointers):
+ *   prepare: ring keys (a11) of Q query descriptors → d_qkeys [Q][20] f32 (d_qsk / d_qcn, nullable: sector keys / column norms [Q][60] f64)
+ *   stage 1: exact top-3 per query → (dist[Q*3], idx[Q*3]); unfilled slots carry idx INT_MAX
+ *   stage 2: distanceBtnScanContext for the candidates in [global_offset, global_offset + n_db) (others left untouched); the query's
+ *            sector key and column norms are derived inside the kernel from its descriptor
+ *   decide : strict-< argmin in kNN order + threshold (include/Scancontext.cpp:302-340) */
+int liorf_sc_prepare_queries_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, void* d_qkeys /*Q*20 f32*/, void* d_qsk /*Q*60 f64, nullable*/, void* d_qcn /*Q*60 f64, nullable*/);
 int liorf_sc_knn_batch_dev(liorf_ctx* ctx, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx);
-int liorf_sc_merge_top3_dev(liorf_ctx* ctx, const void* d_part_dist, const void* d_part_idx, int n_parts, int Q, void* d_dist, void* d_idx);
-/* the same merge on ONE all-gathered buffer: packed[part] = { float dist[Q*3]; int idx[Q*3]; } (a rank's stage-1 output
- * written into one allocation travels in a single collective) */
-int liorf_sc_merge_top3_packed_dev(liorf_ctx* ctx, const void* d_packed, int n_parts, int Q, void* d_dist, void* d_idx);
-/* sharded stage 2 → per pair the entry of the rank that owns the candidate; gathered[part] = { double dist[Q*3];
- * int shift[Q*3]; } at part * stride_bytes (stride_bytes >= 36 Q, multiple of 8) */
-int liorf_sc_combine_pairs_dev(liorf_ctx* ctx, const void* d_gathered, int n_parts, long long stride_bytes, int Q, void* d_pair_dist, void* d_pair_shift);
-int liorf_sc_prepare_queries_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, void* d_qkeys /*Q*20 f32*/, void* d_qsk /*Q*60 f64*/, void* d_qcn /*Q*60 f64*/);
-int liorf_sc_distance_batch_dev(liorf_ctx* ctx, const void* d_qdescs, const void* d_qsk, const void* d_qcn, const void* d_cand_idx, int Q,
-                                int global_offset, void* d_pair_dist /*Q*3 f64*/, void* d_pair_shift /*Q*3 i32*/);
+int liorf_sc_distance_batch_dev(liorf_ctx* ctx, const void* d_qdescs, const void* d_cand_idx, int Q, int global_offset, void* d_pair_dist /*Q*3 f64*/, void* d_pair_shift /*Q*3 i32*/);
 int liorf_sc_decide_dev(liorf_ctx* ctx, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q,
                         void* d_loop_id, void* d_shift, void* d_dist);
-/* Ring-key search implementation used by liorf_sc_knn_batch_dev / liorf_sc_query_batch:
+/* Ring-key search implementation used by liorf_sc_knn_batch_dev / liorf_sc_query_batch / the sharded search:
  *   0 auto (tensor cores for batches of >= 64 queries against >= 4096 keys), 1 CUDA-core brute force,
  *   2 tcgen05 coarse filter + exact re-rank (csrc/sc_tensor.cuh).  All three return the same exact top-3
  *   (nanoflann arithmetic, include/nanoflann.hpp:383-408, ties by (dist, idx)). */
 int liorf_sc_set_search_path(liorf_ctx* ctx, int mode);
 /* last tensor-core search: candidates the coarse filter passed to the exact re-rank (summed over the queries) and the
- * number of queries whose candidate list overflowed (answered by the brute-force kernel instead) */
+ * number of queries whose candidate list overflowed (answered by an exact scan of all keys instead) */
 int liorf_sc_tensor_stats(liorf_ctx* ctx, long long* n_candidates, int* n_overflow);
 /* test hook: raw tensor-core distances of Q host ring keys against the database, out[q * ld + k] */
 int liorf_sc_tensor_dump(liorf_ctx* ctx, const float* qkeys, int Q, float* out, long long out_capacity, int* ld, float center[20]);
@@ -198,28 +191,43 @@ int liorf_sc_tensor_dump(liorf_ctx* ctx, const float* qkeys, int Q, float* out, 
 int liorf_sc_query_batch(liorf_ctx* ctx, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3 /*nullable*/);
 
 /* ---- database sharded across GPUs, exchanged through NVLink peer memory (BASELINE config 5) -----------------
- * Rank g holds rows [g K/G, (g+1) K/G) of the SCManager database (polarcontexts_ / polarcontext_invkeys_mat_,
- * include/Scancontext.h:104-108); queries are replicated.  Each rank owns an exchange window that every peer maps; the
- * kernels of a batch push their per-query results (candidate-threshold bounds, local top-3, owner-computed
- * distanceBtnScanContext values) into all windows over NVLink and wait on flags in their own window — no NCCL call and no
- * host round trip inside a batch (csrc/sc_shard.cuh).  Exactly the global top-3 ring-key candidates are evaluated
- * (include/Scancontext.cpp:289-317), so loop ids / shifts / distances equal the unsharded search bit for bit.
- *   liorf_sc_shard_init    : allocate this rank's window for batches of up to q_max queries; returns its cudaIpc handle
+ * "Replicated index, sharded payload" — the split the reference's SCManager already has between its search index
+ * (polarcontext_invkeys_mat_ / polarcontext_tree_) and the descriptors it indexes (polarcontexts_), include/Scancontext.h:104-113:
+ *   rank g holds the descriptor, sector key and column norms of rows [row_begin[g], row_begin[g+1]) (10 560 B per row); the 80-byte fp32
+ *   ring key of EVERY row is replicated on every rank (pushed over NVLink by liorf_sc_shard_sync_keys when the database was loaded or grew).
+ * One batch = the same Q queries on every rank:
+ *   stage 1 (ring-key top-3, include/Scancontext.cpp:289-295) is split by QUERY — rank g answers queries [g Q/G, (g+1) Q/G) against all
+ *     keys, which yields the global top-3 directly — and its re-rank kernel writes the result into every rank's window (phase C);
+ *   stage 2 (distanceBtnScanContext, :302-317) is split by OWNER of the candidate row; the warp that evaluates a pair writes
+ *     {f64 dist, i32 shift} into every rank's window (phase D); every rank then takes the decision (:319-340) for all queries.
+ * The kernels push with plain stores over NVLink, fence at system scope, raise flags, and wait on flags in their own window — no
+ * NCCL call and no host round trip inside a batch (csrc/sc_shard.cuh).  Exactly the global top-3 are evaluated, so loop ids / shifts /
+ * distances / candidate triples equal the unsharded search bit for bit.
+ *   liorf_sc_shard_init    : allocate this rank's window for batches of up to q_max queries and a replicated index of up to k_total_max
+ *                            rows (0 = this context borrows the index, see liorf_sc_borrow_database); returns the window's cudaIpc handle
  *                            (64 bytes, for peers in other processes) and / or its device pointer (peers in this process)
- *   liorf_sc_shard_connect : map the peers' windows (array of `world` handles or pointers, own entry ignored)
+ *   liorf_sc_shard_connect : map the peers' windows (array of `world` handles or pointers, own entry ignored).  row_begin[world + 1],
+ *                            row_begin[0] = 0; the context must hold exactly rows [row_begin[rank], row_begin[rank+1]) (else LIORF_ERR_STATE)
+ *   liorf_sc_shard_sync_keys: collective; replicate the ring keys (call again, after a new connect, when the database has grown)
  *   liorf_sc_shard_query_dev: one batch, asynchronous on the context's stream; every rank passes the same queries in the same order;
- *                            global_offset = index of this rank's first database row */
+ *                            global_offset must equal row_begin[rank]; d_cand (nullable) receives the global candidate triples [Q][3] */
 /* a second context on the same device searching the SAME database without copying it (several query batches in flight per GPU, one
- * context / stream each); the borrower is read-only, the owner must outlive it and not grow the database meanwhile */
+ * context / stream each); the borrower is read-only, the owner must outlive it and not grow the database meanwhile.  Borrowing from a
+ * sharded owner AFTER its liorf_sc_shard_sync_keys also shares the replicated index. */
 int liorf_sc_borrow_database(liorf_ctx* dst, liorf_ctx* src);
-int liorf_sc_shard_init(liorf_ctx* ctx, int rank, int world, int q_max, void* ipc_handle_out, void** window_out);
+int liorf_sc_shard_init(liorf_ctx* ctx, int rank, int world, int q_max, int k_total_max, void* ipc_handle_out, void** window_out);
 int liorf_sc_shard_connect(liorf_ctx* ctx, const void* ipc_handles, void* const* window_ptrs, const int* row_begin /* world + 1: rows [row_begin[g], row_begin[g+1]) on rank g */);
-int liorf_sc_shard_wait_stats(liorf_ctx* ctx, unsigned long long wait_ns[4], unsigned* batches);   /* time spent waiting for peers per phase (T, C, D, K), measurement */
+int liorf_sc_shard_sync_keys(liorf_ctx* ctx);
+/* the same in steps (bit 0: push this rank's keys + raise the flags, bit 1: wait for every peer's keys) so that several ranks sharing ONE
+ * device (tests) can enqueue every push before any wait */
+int liorf_sc_shard_sync_keys_phases(liorf_ctx* ctx, int phases);
+int liorf_sc_shard_wait_stats(liorf_ctx* ctx, unsigned long long wait_ns[4], unsigned* batches);   /* time spent waiting for peers per phase (C, D, KEYS, -), measurement */
 int liorf_sc_shard_query_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand);
-/* the same batch enqueued in steps (bit 4: ring keys of this rank's query slice + push, then bit 0: all keys .. threshold-bound push, 1: global threshold ..
- * local top-3 push, 2: merge .. distance push, 3: decision; 31 = everything) so that
- * several ranks sharing ONE device (tests) can interleave their steps and never wait on work that has not been enqueued yet */
+/* the same batch enqueued in steps (bit 0: stage 1 of this rank's query slice + push C, bit 1: collect + stage 2 of the owned pairs + push D,
+ * bit 2: decision; 7 = everything) so that several ranks sharing ONE device (tests) can interleave their steps and never wait on work that
+ * has not been enqueued yet */
 int liorf_sc_shard_query_phases_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases);
+int liorf_sc_shard_debug_nowait(liorf_ctx* ctx, int on);   /* measurement: consumers skip the flag waits (one rank of G timed alone, tools/profile_sc_shard.py) */
 
 /* ---- loop-closure registration ------------------------------------------------------------------- */
 /* The ICP of mapOptimization::performSCLoopClosure (src/mapOptmization.cpp:624-730) without the factor graph:

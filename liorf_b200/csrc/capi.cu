@@ -90,19 +90,22 @@ struct liorf_ctx {
     int sc_tree_n = 0, sc_counter = 0;
     DevBuf<float> sc_part_d; DevBuf<int> sc_part_i;
     DevBuf<float> sc_q_d; DevBuf<int> sc_q_i; DevBuf<double> sc_pair_d; DevBuf<int> sc_pair_s;
-    DevBuf<double> sc_qdesc, sc_qsk, sc_qcn; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
-    // tensor-core ring-key search (sc_tensor.cuh): operand images + work buffers
-    DevBuf<uint8_t> sct_bimg, sct_aimg; DevBuf<float> sct_cmin, sct_cmin32, sct_qnorm, sct_part; DevBuf<int> sct_cand, sct_cnt, sct_over;
-    float* sct_center = nullptr; unsigned* sct_nmax = nullptr; int* sct_over_cnt = nullptr;
-    int sct_img_n = -1;              // number of database keys the B image was built from (-1: none)
+    DevBuf<double> sc_qdesc; DevBuf<float> sc_qkeys; DevBuf<int> sc_res_i; DevBuf<double> sc_res_d;
+    // tensor-core ring-key search (sc_tensor.cuh): operand images + work buffers.  A KeySet = a ring-key array the filter searches + the B
+    // operand image built from it: ks_local = this context's own rows (sc_keys), ks_all = the replicated index of a sharded database
+    struct KeySet { const float* keys = nullptr; int n = 0; unsigned gen = 0; DevBuf<uint8_t> bimg; float* center = nullptr; unsigned* nmax = nullptr;
+                    int img_n = -1; unsigned img_gen = 0; const float* img_keys = nullptr; } ks_local, ks_all;
+    DevBuf<uint8_t> sct_aimg; DevBuf<float> sct_cmin, sct_cmin32, sct_qnorm, sct_part; DevBuf<int> sct_cand, sct_cnt;
+    int* sct_over_cnt = nullptr;
     // loop-closure ICP (icp.cuh)
     DevBuf<float4> icp_raw, icp_src, icp_src0, icp_tgt; MapGrid icp_grid; DevBuf<double> icp_partial; double* icp_out = nullptr; int* icp_counter = nullptr;
     DevBuf<KfSel> icp_sel; DevBuf<int> icp_nn_idx; DevBuf<float> icp_nn_d2;
     liorf_guess_state guess_state = {}; float tf_mapped[6] = {0, 0, 0, 0, 0, 0};   // updateInitialGuess statics + transformTobeMapped
     // sharded search over peer windows (sc_shard.cuh)
-    struct ScShard { bool ready = false; ShardWin W; int qmax = 0; size_t win_bytes = 0; unsigned* d_batch = nullptr; unsigned* d_counter = nullptr;
-                     cudaGraphExec_t graph = nullptr; const void* gsig[8] = {nullptr}; const void* last_sig[8] = {nullptr}; bool ipc_opened[SCSH_MAX] = {false};
-                     DevBuf<float> u3, thr; DevBuf<unsigned> packC; DevBuf<int> list; int* d_nlist = nullptr; } shard;
+    struct ScShard { bool ready = false; ShardWin W; int qmax = 0, kcap = 0; size_t win_bytes = 0, off_keys = 0; unsigned* d_batch = nullptr; unsigned* d_counter = nullptr;
+                     unsigned keys_gen = 0; bool keys_pushed = false;
+                     cudaGraphExec_t graph = nullptr; const void* gsig[40] = {nullptr}; const void* last_sig[40] = {nullptr}; bool ipc_opened[SCSH_MAX] = {false};
+                     DevBuf<int> list; int* d_nlist = nullptr; } shard;
     int sc_path = 0;                 // 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank
     bool sct_attr_set = false; int sct_last_Q = 0; bool scdb_attr_set = false; int scdb_blocks_per_sm = 1;
     Profiler prof;
@@ -391,12 +394,13 @@ void liorf_destroy(liorf_ctx* c) {
     if (!c->sc_borrowed) { c->sc_desc.release(); c->sc_sk.release(); c->sc_cn.release(); c->sc_keys.release(); }
     c->sc_part_d.release(); c->sc_part_i.release();
     c->sc_q_d.release(); c->sc_q_i.release(); c->sc_pair_d.release(); c->sc_pair_s.release();
-    c->sc_qdesc.release(); c->sc_qsk.release(); c->sc_qcn.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
-    c->sct_bimg.release(); c->sct_aimg.release(); c->sct_cmin.release(); c->sct_cmin32.release(); c->sct_qnorm.release(); c->sct_part.release(); c->sct_cand.release(); c->sct_cnt.release();
+    c->sc_qdesc.release(); c->sc_qkeys.release(); c->sc_res_i.release(); c->sc_res_d.release();
+    c->sct_aimg.release(); c->sct_cmin.release(); c->sct_cmin32.release(); c->sct_qnorm.release(); c->sct_part.release(); c->sct_cand.release(); c->sct_cnt.release();
+    for (liorf_ctx::KeySet* k : {&c->ks_local, &c->ks_all}) { k->bimg.release(); if (k->center) cudaFree(k->center); if (k->nmax) cudaFree(k->nmax); }
     c->icp_raw.release(); c->icp_src.release(); c->icp_src0.release(); c->icp_tgt.release(); c->icp_partial.release(); c->icp_sel.release(); c->icp_nn_idx.release();
     c->icp_nn_d2.release(); c->icp_grid.counts.release(); c->icp_grid.cell_start.release(); c->icp_grid.sorted.release(); c->icp_grid.scan.status.release();
     if (c->icp_out) cudaFree(c->icp_out);
-    c->sct_over.release(); if (c->sct_center) cudaFree(c->sct_center); if (c->sct_nmax) cudaFree(c->sct_nmax); if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
+    if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); cudaFree(c->d_s2m_arrive); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
@@ -406,7 +410,7 @@ void liorf_destroy(liorf_ctx* c) {
         if (S.W.base[S.W.rank]) cudaFree(S.W.base[S.W.rank]);
         if (S.d_counter) cudaFree(S.d_counter);
         if (S.graph) cudaGraphExecDestroy(S.graph);
-        S.u3.release(); S.thr.release(); S.packC.release(); S.list.release();
+        S.list.release();
     }
     if (c->d_dbg_gt) cudaFree(c->d_dbg_gt);
     if (c->h_sel) cudaFreeHost(c->h_sel);
@@ -1041,10 +1045,12 @@ int liorf_sc_add_descriptors(liorf_ctx* c, const double* descs, int count) {
  * and must not grow the database while it is borrowed. */
 int liorf_sc_borrow_database(liorf_ctx* dst, liorf_ctx* src) {
     if (!dst || !src || dst == src || dst->P.device != src->P.device) return LIORF_ERR_ARG;
-    if (dst->sc_n != 0 || dst->sc_desc.p) return LIORF_ERR_STATE;
+    if (!dst->sc_borrowed && (dst->sc_n != 0 || dst->sc_desc.p)) return LIORF_ERR_STATE;
     CUDA_TRY(cudaSetDevice(src->P.device));
     CUDA_TRY(cudaStreamSynchronize(src->stream));
     dst->sc_desc = src->sc_desc; dst->sc_sk = src->sc_sk; dst->sc_cn = src->sc_cn; dst->sc_keys = src->sc_keys; dst->sc_n = src->sc_n;
+    // a sharded owner's replicated index (liorf_sc_shard_sync_keys) is shared too; the borrower builds its own operand image from it
+    dst->ks_all.keys = src->ks_all.keys; dst->ks_all.n = src->ks_all.n; dst->ks_all.gen = src->ks_all.gen;
     dst->sc_borrowed = true;
     return LIORF_OK;
 }
@@ -1076,91 +1082,75 @@ static int sc_knn_brute(liorf_ctx* c, const float* d_keys, int n_keys, const flo
     return LIORF_OK;
 }
 
-// tensor-core path (sc_tensor.cuh): operand images → pass A (thresholds) → pass B (candidates) → exact re-rank.
-// The B image of the database is rebuilt only when the database grew since it was made.
-static int sct_prepare(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, SctArgs& a, int& grid) {
+// tensor-core path (sc_tensor.cuh): operand images → GEMM filter → thresholds → candidates → exact re-rank.
+// The B image of a key set is rebuilt only when the set changed since it was made.
+static int sct_prepare(liorf_ctx* c, liorf_ctx::KeySet& ks, int n_keys, const float* d_qkeys, int Q, SctArgs& a, int& grid) {
     int rc;
     const int nkt = (n_keys + SCT_KT - 1) / SCT_KT, n_sqt = (Q + SCT_QT - 1) / SCT_QT;
-    if (!c->sct_center) {
-        CUDA_TRY(cudaMalloc(&c->sct_center, SC_RING * sizeof(float)));
-        CUDA_TRY(cudaMalloc(&c->sct_nmax, sizeof(unsigned)));
-        CUDA_TRY(cudaMalloc(&c->sct_over_cnt, sizeof(int)));
+    if (!ks.center) {
+        CUDA_TRY(cudaMalloc(&ks.center, SC_RING * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&ks.nmax, sizeof(unsigned)));
     }
+    if (!c->sct_over_cnt) { CUDA_TRY(cudaMalloc(&c->sct_over_cnt, sizeof(int))); CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream)); }
     if (!c->sct_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(k_sc_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCT_SMEM));
         c->sct_attr_set = true;
     }
-    if (c->sct_img_n != n_keys) {
-        if ((rc = c->sct_bimg.reserve((size_t)nkt * SCT_TILE_BYTES))) return rc;
-        k_sct_center<<<1, 1024, 0, c->stream>>>(c->sc_keys.p, n_keys, c->sct_center);
-        CUDA_TRY(cudaMemsetAsync(c->sct_nmax, 0, sizeof(unsigned), c->stream));
-        k_sct_image<true><<<(nkt * SCT_KT + 127) / 128, 128, 0, c->stream>>>(c->sc_keys.p, n_keys, nkt * SCT_KT, nkt, c->sct_center, c->sct_bimg.p, nullptr, c->sct_nmax);
+    if (ks.img_n != n_keys || ks.img_gen != ks.gen || ks.img_keys != ks.keys) {
+        if ((rc = ks.bimg.reserve((size_t)nkt * SCT_TILE_BYTES))) return rc;
+        k_sct_center<<<1, 1024, 0, c->stream>>>(ks.keys, n_keys, ks.center);
+        CUDA_TRY(cudaMemsetAsync(ks.nmax, 0, sizeof(unsigned), c->stream));
+        k_sct_image<true><<<(nkt * SCT_KT + 127) / 128, 128, 0, c->stream>>>(ks.keys, n_keys, nkt * SCT_KT, nkt, ks.center, ks.bimg.p, nullptr, ks.nmax);
         CUDA_TRY(cudaGetLastError());
-        c->sct_img_n = n_keys; c->launches += 2;
+        ks.img_n = n_keys; ks.img_gen = ks.gen; ks.img_keys = ks.keys; c->launches += 2;
     }
     const long long total = (long long)n_sqt * nkt;
     grid = (int)(total < c->num_sms ? total : c->num_sms);
     const size_t rows = (size_t)n_sqt * SCT_QT;
     if ((rc = c->sct_aimg.reserve((size_t)n_sqt * 2 * SCT_TILE_BYTES)) || (rc = c->sct_qnorm.reserve(rows)) || (rc = c->sct_cmin.reserve(rows * nkt)) || (rc = c->sct_cmin32.reserve(rows * nkt * 4)) || (rc = c->sct_part.reserve(rows * SCS_SPLITS * 3)) ||
-        (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q)) || (rc = c->sct_over.reserve(Q))) return rc;
-    k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, nkt, c->sct_center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
-    a.a_img = c->sct_aimg.p; a.b_img = c->sct_bimg.p; a.Q = Q; a.n_keys = n_keys; a.nkt = nkt; a.n_sqt = n_sqt;
+        (rc = c->sct_cand.reserve((size_t)Q * SCT_CAP)) || (rc = c->sct_cnt.reserve(Q))) return rc;
+    k_sct_image<false><<<(int)((rows + 127) / 128), 128, 0, c->stream>>>(d_qkeys, Q, (int)rows, nkt, ks.center, c->sct_aimg.p, c->sct_qnorm.p, nullptr);
+    a.a_img = c->sct_aimg.p; a.b_img = ks.bimg.p; a.Q = Q; a.n_keys = n_keys; a.nkt = nkt; a.n_sqt = n_sqt;
     a.cmin = c->sct_cmin.p; a.cmin32 = c->sct_cmin32.p; a.dump = nullptr; a.err_flag = c->d_err;
     c->launches += 1;
     return LIORF_OK;
 }
 
-// shard_phase: 0 = unsharded search; sharded search (sc_shard.cuh): 1 = images + GEMM + local bounds + push (phase T),
-// 2 = global threshold + select + exact re-rank
-static int sc_knn_tensor(liorf_ctx* c, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx, int shard_phase = 0) {
+// exact top-3 of Q queries over the first n_keys keys of a key set on the tensor cores.  push != nullptr: sharded search, the result goes
+// into every rank's window (phase C) from the re-rank kernel itself
+static int sc_knn_tensor(liorf_ctx* c, liorf_ctx::KeySet& ks, int n_keys, const float* d_qkeys, int Q, int idx_offset, float* d_dist, int* d_idx, const ShardPush* push = nullptr) {
     int rc, grid;
     SctArgs a;
     ProfScope ps(c, SEC_SC_SEARCH);
     const int nkt = (n_keys + SCT_KT - 1) / SCT_KT, rows = ((Q + SCT_QT - 1) / SCT_QT) * SCT_QT;
-    liorf_ctx::ScShard& S = c->shard;
-    if (shard_phase != 2) {
-        if ((rc = sct_prepare(c, n_keys, d_qkeys, Q, a, grid))) return rc;
-        CUDA_TRY(cudaMemsetAsync(c->sct_over_cnt, 0, sizeof(int), c->stream));
-        { ProfScope pg(c, SEC_SC_GEMM); k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a); }
-        CUDA_TRY(cudaMemsetAsync(c->sct_cnt.p, 0, (size_t)Q * sizeof(int), c->stream));
-        k_sct_top3<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, nkt, rows, c->sct_part.p);
-        c->launches += 3;
-        if (shard_phase == 1) {      // phase T: this rank's inflated top-3 tile minima go to every window
-            if ((rc = S.u3.reserve((size_t)3 * Q)) || (rc = S.thr.reserve(Q))) return rc;
-            k_scsh_u3_push<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, c->sct_part.p, rows, c->sct_qnorm.p, Q, c->sct_nmax, S.d_batch, S.d_counter);
-            CUDA_TRY(cudaGetLastError());
-            c->launches += 1;
-            return LIORF_OK;
-        }
-    }
-    const float* thr_in = nullptr;
-    if (shard_phase == 2) {          // every rank's bounds → the global candidate threshold
-        k_scsh_thr<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, c->sct_qnorm.p, Q, c->sct_nmax, S.thr.p, c->d_err);
-        thr_in = S.thr.p; c->launches += 1;
-    }
-    k_sct_select<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, c->sct_cmin32.p, nkt, rows, c->sct_part.p, c->sct_qnorm.p, Q, c->sct_nmax,
-                                                                                 c->sct_cand.p, c->sct_cnt.p, thr_in);
-    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, nkt, global_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over.p,
-                                                     c->sct_over_cnt);
-    k_sc_knn_overflow<<<64, 256, 0, c->stream>>>(c->sc_keys.p, n_keys, global_offset, d_qkeys, c->sct_over.p, c->sct_over_cnt, d_dist, d_idx);
+    if ((rc = sct_prepare(c, ks, n_keys, d_qkeys, Q, a, grid))) return rc;
+    { ProfScope pg(c, SEC_SC_GEMM); k_sc_tensor<false><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a); }
+    k_sct_top3<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, nkt, rows, c->sct_part.p, Q, c->sct_cnt.p, c->sct_over_cnt);
+    k_sct_select<<<dim3(rows / 32, SCS_SPLITS), 32 * SCS_SLICES, 0, c->stream>>>(c->sct_cmin.p, c->sct_cmin32.p, nkt, rows, c->sct_part.p, c->sct_qnorm.p, Q, ks.nmax,
+                                                                                 c->sct_cand.p, c->sct_cnt.p);
+    ShardPush P; std::memset(&P, 0, sizeof(P));
+    if (push) P = *push;
+    k_sct_rerank<<<(Q + 7) / 8, 256, 0, c->stream>>>(ks.keys, n_keys, nkt, idx_offset, d_qkeys, Q, c->sct_cand.p, c->sct_cnt.p, d_dist, d_idx, c->sct_over_cnt, P);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 3; c->sct_last_Q = Q;
+    c->launches += 4; c->sct_last_Q = Q;
     return LIORF_OK;
 }
 
-static int sc_knn(liorf_ctx* c, const float* d_keys, int n_keys, const float* d_qkeys, int Q, int global_offset, float* d_dist, int* d_idx) {
-    if (Q <= 0) return LIORF_OK;
-    // the tensor-core filter pays off for query batches against a sizeable database; the live detectLoopClosureID
-    // (one query) stays on the exact CUDA-core kernel
-    const bool can_tensor = d_keys == c->sc_keys.p && n_keys >= 1;
-    const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && n_keys >= 4096);
-    if (can_tensor && want_tensor) return sc_knn_tensor(c, n_keys, d_qkeys, Q, global_offset, d_dist, d_idx);
-    return sc_knn_brute(c, d_keys, n_keys, d_qkeys, Q, global_offset, d_dist, d_idx);
+static bool sc_want_tensor(const liorf_ctx* c, int Q, int n_keys) {
+    // the tensor-core filter pays off for query batches against a sizeable database; the live detectLoopClosureID (one query) stays on the
+    // exact CUDA-core kernel
+    return n_keys >= 1 && (c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && n_keys >= 4096));
 }
+static int sc_knn(liorf_ctx* c, liorf_ctx::KeySet& ks, int n_keys, const float* d_qkeys, int Q, int idx_offset, float* d_dist, int* d_idx) {
+    if (Q <= 0) return LIORF_OK;
+    if (sc_want_tensor(c, Q, n_keys)) return sc_knn_tensor(c, ks, n_keys, d_qkeys, Q, idx_offset, d_dist, d_idx);
+    return sc_knn_brute(c, ks.keys, n_keys, d_qkeys, Q, idx_offset, d_dist, d_idx);
+}
+static liorf_ctx::KeySet& local_keys(liorf_ctx* c) { c->ks_local.keys = c->sc_keys.p; c->ks_local.n = c->sc_n; return c->ks_local; }
 
 // stage 2 for a batch of (query, candidate) pairs: TMA-staged kernel (sc_distance.cuh), persistent warps over the pairs
-static int sc_distance_launch(liorf_ctx* c, const double* qd, const double* qsk, const double* qcn, const int* cand, int pairs, int global_offset, double* pd, int* ps,
+static int sc_distance_launch(liorf_ctx* c, const double* qd, const int* cand, int pairs, int global_offset, double* pd, int* ps,
                               const int* pair_list = nullptr, const int* n_list = nullptr, const ShardPush* push = nullptr) {
     if (!c->scdb_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_sc_distance_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SCDB_SMEM));
@@ -1171,60 +1161,35 @@ static int sc_distance_launch(liorf_ctx* c, const double* qd, const double* qsk,
     int blocks = (pairs + SCDB_WARPS - 1) / SCDB_WARPS;
     const int cap = c->num_sms * c->scdb_blocks_per_sm;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;                                   // a rank that owns no pair still raises its phase-D flag
     ShardPush P; std::memset(&P, 0, sizeof(P));
     if (push) P = *push;
-    k_sc_distance_bulk<<<blocks, SCDB_WARPS * 32, SCDB_SMEM, c->stream>>>(qd, qsk, qcn, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n,
+    k_sc_distance_bulk<<<blocks, SCDB_WARPS * 32, SCDB_SMEM, c->stream>>>(qd, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n,
                                                                           pd, ps, c->d_err, pair_list, n_list, P);
     CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
     return LIORF_OK;
 }
 
 int liorf_sc_knn_batch_dev(liorf_ctx* c, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx) {
     if (!c || Q < 0 || !d_qkeys || !d_dist || !d_idx) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
-    return sc_knn(c, c->sc_keys.p, c->sc_n, (const float*)d_qkeys, Q, global_offset, (float*)d_dist, (int*)d_idx);
-}
-int liorf_sc_merge_top3_dev(liorf_ctx* c, const void* d_part_dist, const void* d_part_idx, int n_parts, int Q, void* d_dist, void* d_idx) {
-    if (!c || Q < 0 || n_parts < 1) return LIORF_ERR_ARG;
-    CUDA_TRY(cudaSetDevice(c->P.device));
-    if (Q == 0) return LIORF_OK;
-    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>((const float*)d_part_dist, (const int*)d_part_idx, n_parts, (size_t)Q * 3, Q, (float*)d_dist, (int*)d_idx);
-    CUDA_TRY(cudaGetLastError());
-    return LIORF_OK;
-}
-int liorf_sc_merge_top3_packed_dev(liorf_ctx* c, const void* d_packed, int n_parts, int Q, void* d_dist, void* d_idx) {
-    if (!c || Q < 0 || n_parts < 1 || !d_packed) return LIORF_ERR_ARG;
-    CUDA_TRY(cudaSetDevice(c->P.device));
-    if (Q == 0) return LIORF_OK;
-    const float* pd = (const float*)d_packed;
-    k_sc_merge_top3<<<(Q + 127) / 128, 128, 0, c->stream>>>(pd, (const int*)(pd + (size_t)Q * 3), n_parts, (size_t)Q * 6, Q, (float*)d_dist, (int*)d_idx);
-    CUDA_TRY(cudaGetLastError());
-    return LIORF_OK;
-}
-int liorf_sc_combine_pairs_dev(liorf_ctx* c, const void* d_gathered, int n_parts, long long stride_bytes, int Q, void* d_pair_dist, void* d_pair_shift) {
-    if (!c || Q < 0 || n_parts < 1 || !d_gathered || stride_bytes < (long long)Q * 36 || (stride_bytes & 7)) return LIORF_ERR_ARG;
-    CUDA_TRY(cudaSetDevice(c->P.device));
-    if (Q == 0) return LIORF_OK;
-    k_sc_combine_pairs<<<(3 * Q + 127) / 128, 128, 0, c->stream>>>((const unsigned char*)d_gathered, n_parts, (size_t)stride_bytes, 3 * Q, (double*)d_pair_dist, (int*)d_pair_shift);
-    CUDA_TRY(cudaGetLastError());
-    return LIORF_OK;
+    return sc_knn(c, local_keys(c), c->sc_n, (const float*)d_qkeys, Q, global_offset, (float*)d_dist, (int*)d_idx);
 }
 int liorf_sc_prepare_queries_dev(liorf_ctx* c, const void* d_qdescs, int Q, void* d_qkeys, void* d_qsk, void* d_qcn) {
-    if (!c || Q < 0 || !d_qdescs || !d_qsk || !d_qcn) return LIORF_ERR_ARG;
+    if (!c || Q < 0 || !d_qdescs || (!d_qkeys && !d_qsk)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
     k_sc_keys_batch<<<Q, 64, 0, c->stream>>>((const double*)d_qdescs, Q, (float*)d_qkeys, (double*)d_qsk, (double*)d_qcn);
     CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
     return LIORF_OK;
 }
-int liorf_sc_distance_batch_dev(liorf_ctx* c, const void* d_qdescs, const void* d_qsk, const void* d_qcn, const void* d_cand_idx, int Q, int global_offset,
-                                void* d_pair_dist, void* d_pair_shift) {
-    if (!c || Q < 0) return LIORF_ERR_ARG;
+int liorf_sc_distance_batch_dev(liorf_ctx* c, const void* d_qdescs, const void* d_cand_idx, int Q, int global_offset, void* d_pair_dist, void* d_pair_shift) {
+    if (!c || Q < 0 || !d_qdescs || !d_cand_idx || !d_pair_dist || !d_pair_shift) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
-    const int pairs = Q * SC_NUM_CAND;
-    return sc_distance_launch(c, (const double*)d_qdescs, (const double*)d_qsk, (const double*)d_qcn, (const int*)d_cand_idx, pairs, global_offset, (double*)d_pair_dist,
-                              (int*)d_pair_shift);
+    return sc_distance_launch(c, (const double*)d_qdescs, (const int*)d_cand_idx, Q * SC_NUM_CAND, global_offset, (double*)d_pair_dist, (int*)d_pair_shift);
 }
 int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q, void* d_loop_id, void* d_shift,
                         void* d_dist) {
@@ -1234,6 +1199,7 @@ int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pai
     k_sc_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>((const double*)d_pair_dist, (const int*)d_pair_shift, (const int*)d_cand_idx, Q, (int*)d_loop_id,
                                                          (int*)d_shift, (double*)d_dist);
     CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
     return LIORF_OK;
 }
 
@@ -1266,7 +1232,7 @@ int liorf_sc_set_search_path(liorf_ctx* c, int mode) {
     return LIORF_OK;
 }
 /* statistics of the last tensor-core search: candidates emitted by the coarse filter (sum over queries), queries that
- * overflowed their list and were answered by the brute-force kernel */
+ * overflowed their list and were answered by the exact scan instead */
 int liorf_sc_tensor_stats(liorf_ctx* c, long long* n_candidates, int* n_overflow) {
     if (!c || !n_candidates || !n_overflow) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
@@ -1290,7 +1256,8 @@ int liorf_sc_tensor_dump(liorf_ctx* c, const float* qkeys, int Q, float* out, lo
     if ((rc = c->sc_qkeys.reserve((size_t)Q * SC_RING))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->sc_qkeys.p, qkeys, (size_t)Q * SC_RING * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SctArgs a;
-    if ((rc = sct_prepare(c, c->sc_n, c->sc_qkeys.p, Q, a, grid))) return rc;
+    liorf_ctx::KeySet& ks = local_keys(c);
+    if ((rc = sct_prepare(c, ks, c->sc_n, c->sc_qkeys.p, Q, a, grid))) return rc;
     const size_t rows = (size_t)a.n_sqt * SCT_QT, cols = (size_t)a.nkt * SCT_KT;
     *ld = (int)cols;
     if ((long long)((size_t)Q * cols) > out_capacity) return LIORF_ERR_ARG;
@@ -1299,7 +1266,7 @@ int liorf_sc_tensor_dump(liorf_ctx* c, const float* qkeys, int Q, float* out, lo
     k_sc_tensor<true><<<grid, SCT_THREADS, SCT_SMEM, c->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, dump.p, (size_t)Q * cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (center) CUDA_TRY(cudaMemcpyAsync(center, c->sct_center, SC_RING * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (center) CUDA_TRY(cudaMemcpyAsync(center, ks.center, SC_RING * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     rc = check_err(c);
     dump.release();
     return rc;
@@ -1312,19 +1279,25 @@ static int sc_reserve_query(liorf_ctx* c, int Q) {
     return LIORF_OK;
 }
 
+// the unsharded batch on device buffers: ring keys of the queries → exact top-3 → distanceBtnScanContext of the 3 Q pairs → decision
+static int sc_query_local_dev(liorf_ctx* c, const double* qd, int Q, int global_offset, int* cand, int* d_loop_id, int* d_shift, double* d_dist) {
+    int rc;
+    if ((rc = c->sc_qkeys.reserve((size_t)Q * SC_RING)) || (rc = sc_reserve_query(c, Q))) return rc;
+    if ((rc = liorf_sc_prepare_queries_dev(c, qd, Q, c->sc_qkeys.p, nullptr, nullptr))) return rc;
+    if ((rc = sc_knn(c, local_keys(c), c->sc_n, c->sc_qkeys.p, Q, global_offset, c->sc_q_d.p, cand))) return rc;
+    if ((rc = sc_distance_launch(c, qd, cand, 3 * Q, global_offset, c->sc_pair_d.p, c->sc_pair_s.p))) return rc;
+    return liorf_sc_decide_dev(c, c->sc_pair_d.p, c->sc_pair_s.p, cand, Q, d_loop_id, d_shift, d_dist);
+}
+
 int liorf_sc_query_batch(liorf_ctx* c, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3) {
     if (!c || Q < 0 || (Q > 0 && (!qdescs || !loop_id || !shift || !dist))) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
     if (c->sc_n < 1) return LIORF_ERR_STATE;
     int rc;
-    if ((rc = c->sc_qdesc.reserve((size_t)Q * SC_DESC)) || (rc = c->sc_qsk.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qcn.reserve((size_t)Q * SC_SECTOR)) ||
-        (rc = c->sc_qkeys.reserve((size_t)Q * SC_RING)) || (rc = sc_reserve_query(c, Q))) return rc;
+    if ((rc = c->sc_qdesc.reserve((size_t)Q * SC_DESC)) || (rc = sc_reserve_query(c, Q))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->sc_qdesc.p, qdescs, (size_t)Q * SC_DESC * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = liorf_sc_prepare_queries_dev(c, c->sc_qdesc.p, Q, c->sc_qkeys.p, c->sc_qsk.p, c->sc_qcn.p))) return rc;
-    if ((rc = sc_knn(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, 0, c->sc_q_d.p, c->sc_q_i.p))) return rc;
-    if ((rc = liorf_sc_distance_batch_dev(c, c->sc_qdesc.p, c->sc_qsk.p, c->sc_qcn.p, c->sc_q_i.p, Q, 0, c->sc_pair_d.p, c->sc_pair_s.p))) return rc;
-    if ((rc = liorf_sc_decide_dev(c, c->sc_pair_d.p, c->sc_pair_s.p, c->sc_q_i.p, Q, c->sc_res_i.p, c->sc_res_i.p + Q, c->sc_res_d.p))) return rc;
+    if ((rc = sc_query_local_dev(c, c->sc_qdesc.p, Q, 0, c->sc_q_i.p, c->sc_res_i.p, c->sc_res_i.p + Q, c->sc_res_d.p))) return rc;
     CUDA_TRY(cudaMemcpyAsync(loop_id, c->sc_res_i.p, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(shift, c->sc_res_i.p + Q, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(dist, c->sc_res_d.p, (size_t)Q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1334,23 +1307,22 @@ int liorf_sc_query_batch(liorf_ctx* c, const double* qdescs, int Q, int* loop_id
 
 // ---- sharded search over NVLink peer windows (sc_shard.cuh) ----
 static size_t scsh_round(size_t b) { return (b + 255) / 256 * 256; }
-int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, void* ipc_handle_out /*64 B, nullable*/, void** window_out /*nullable*/) {
-    if (!c || world < 1 || world > SCSH_MAX || rank < 0 || rank >= world || q_max < 1) return LIORF_ERR_ARG;
+int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, int k_total_max, void* ipc_handle_out /*64 B, nullable*/, void** window_out /*nullable*/) {
+    if (!c || world < 1 || world > SCSH_MAX || rank < 0 || rank >= world || q_max < 1 || k_total_max < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
-    if (S.ready) return LIORF_ERR_STATE;
+    if (S.ready || S.W.base[S.W.rank]) return LIORF_ERR_STATE;
     std::memset(&S.W, 0, sizeof(S.W));
-    S.W.rank = rank; S.W.world = world; S.qmax = q_max;
-    const size_t flags = scsh_round((size_t)world * 4 * sizeof(unsigned));
-    S.W.stride[SCSH_T] = scsh_round((size_t)q_max * 12); S.W.stride[SCSH_C] = scsh_round((size_t)q_max * 24); S.W.stride[SCSH_D] = scsh_round((size_t)q_max * 36);
-    S.W.off[SCSH_T] = flags; S.W.off[SCSH_C] = S.W.off[SCSH_T] + world * S.W.stride[SCSH_T]; S.W.off[SCSH_D] = S.W.off[SCSH_C] + world * S.W.stride[SCSH_C];
-    S.W.off[SCSH_K] = S.W.off[SCSH_D] + world * S.W.stride[SCSH_D]; S.W.stride[SCSH_K] = 0;      // one [q_max][20] f32 array, rank g fills the rows of its query slice
-    S.win_bytes = S.W.off[SCSH_K] + scsh_round((size_t)q_max * SC_RING * sizeof(float));
+    S.W.rank = rank; S.W.world = world; S.W.qmax = q_max; S.qmax = q_max; S.kcap = k_total_max;
+    S.W.off_c = scsh_round((size_t)SCSH_MAX * SCSH_NPHASE * sizeof(unsigned));
+    S.W.off_d = S.W.off_c + scsh_round((size_t)q_max * 24);
+    S.off_keys = S.W.off_d + scsh_round((size_t)q_max * 36);
+    S.win_bytes = S.off_keys + scsh_round((size_t)k_total_max * SC_RING * sizeof(float));
     unsigned char* win = nullptr;
     CUDA_TRY(cudaMalloc(&win, S.win_bytes));
     CUDA_TRY(cudaMemset(win, 0, S.win_bytes));
-    CUDA_TRY(cudaMalloc(&S.d_counter, 4 * sizeof(unsigned) + 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(S.d_counter, 0, 4 * sizeof(unsigned) + 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&S.d_counter, 4 * sizeof(unsigned) + SCSH_NPHASE * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(S.d_counter, 0, 4 * sizeof(unsigned) + SCSH_NPHASE * sizeof(unsigned long long)));
     S.d_nlist = reinterpret_cast<int*>(S.d_counter + 2);
     S.d_batch = S.d_counter + 1;
     S.W.wait_ns = reinterpret_cast<unsigned long long*>(S.d_counter + 4);
@@ -1359,16 +1331,16 @@ int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, void* ipc_
     if (window_out) *window_out = win;
     return LIORF_OK;
 }
-/* nanoseconds this rank's kernels spent waiting for the peers' pushes, per phase (T, C, D, K), accumulated since the last call; batches = batch counter */
+/* nanoseconds this rank's kernels spent waiting for the peers' pushes, per phase (C, D, KEYS, unused), accumulated since the last call; batches = batch counter */
 int liorf_sc_shard_wait_stats(liorf_ctx* c, unsigned long long wait_ns[4], unsigned* batches) {
     if (!c || !wait_ns) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
     if (!S.d_counter) return LIORF_ERR_STATE;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(wait_ns, S.W.wait_ns, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(wait_ns, S.W.wait_ns, SCSH_NPHASE * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (batches) CUDA_TRY(cudaMemcpy(batches, S.d_batch, sizeof(unsigned), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemset(S.W.wait_ns, 0, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(S.W.wait_ns, 0, SCSH_NPHASE * sizeof(unsigned long long)));
     return LIORF_OK;
 }
 int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B, nullable*/, void* const* window_ptrs /*world entries, nullable*/, const int* row_begin /*world + 1*/) {
@@ -1376,77 +1348,112 @@ int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B,
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
     if (!S.W.base[S.W.rank] || S.ready) return LIORF_ERR_STATE;
+    if (row_begin[0] != 0) return LIORF_ERR_ARG;
     for (int g = 0; g <= S.W.world; ++g) { S.W.row_begin[g] = row_begin[g]; if (g > 0 && row_begin[g] < row_begin[g - 1]) return LIORF_ERR_ARG; }
+    if (row_begin[S.W.world] < 1) return LIORF_ERR_ARG;                               // an empty DATABASE cannot be searched; an empty SHARD is fine
+    if (S.kcap > 0 && row_begin[S.W.world] > S.kcap) return LIORF_ERR_ARG;            // the replicated index must hold every row
+    // this rank's own rows must be the ones the context holds (a mismatch would make ranks disagree about who owns a candidate)
+    if (c->sc_n != row_begin[S.W.rank + 1] - row_begin[S.W.rank]) return LIORF_ERR_STATE;
     for (int g = 0; g < S.W.world; ++g) {
-        if (g == S.W.rank) continue;
-        if (window_ptrs) S.W.base[g] = (unsigned char*)window_ptrs[g];               // same process: the peer context's pointer is directly usable
-        else {
-            cudaIpcMemHandle_t h; std::memcpy(&h, (const unsigned char*)ipc_handles + (size_t)64 * g, 64);
-            void* p = nullptr;
-            CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-            S.W.base[g] = (unsigned char*)p; S.ipc_opened[g] = true;
+        if (g != S.W.rank) {
+            if (window_ptrs) S.W.base[g] = (unsigned char*)window_ptrs[g];               // same process: the peer context's pointer is directly usable
+            else {
+                cudaIpcMemHandle_t h; std::memcpy(&h, (const unsigned char*)ipc_handles + (size_t)64 * g, 64);
+                void* p = nullptr;
+                CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                S.W.base[g] = (unsigned char*)p; S.ipc_opened[g] = true;
+            }
+            if (!S.W.base[g]) return LIORF_ERR_ARG;
         }
-        if (!S.W.base[g]) return LIORF_ERR_ARG;
+        S.W.keys_all[g] = S.kcap > 0 ? reinterpret_cast<float*>(S.W.base[g] + S.off_keys) : nullptr;     // every rank uses the same window layout
     }
     S.ready = true;
     return LIORF_OK;
 }
+/* Replicates the index: bit 0 = push the ring keys of this rank's rows into every rank's key array and raise the flags, bit 1 = wait for
+ * every peer's keys (the next search rebuilds the operand image).  Collective: every rank calls it after the database was loaded or has
+ * grown (liorf_sc_shard_sync_keys = both bits; the split form lets several ranks that share ONE device — tests — enqueue push before wait). */
+int liorf_sc_shard_sync_keys_phases(liorf_ctx* c, int phases) {
+    if (!c || !(phases & 3)) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    liorf_ctx::ScShard& S = c->shard;
+    if (!S.ready || S.kcap < 1) return LIORF_ERR_STATE;
+    if (c->sc_n != S.W.row_begin[S.W.rank + 1] - S.W.row_begin[S.W.rank]) return LIORF_ERR_STATE;
+    if (phases & 1) {
+        ++S.keys_gen; S.keys_pushed = true;
+        const size_t words = (size_t)c->sc_n * SC_RING;
+        const int blocks = (int)std::max<size_t>(1, std::min<size_t>(4 * c->num_sms, (words + 1023) / 1024));
+        k_scsh_push_keys<<<blocks, 256, 0, c->stream>>>(S.W, c->sc_keys.p, c->sc_n, S.keys_gen, S.d_counter);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+    }
+    if (phases & 2) {
+        if (!S.keys_pushed) return LIORF_ERR_STATE;
+        k_scsh_wait_keys<<<1, 32, 0, c->stream>>>(S.W, S.keys_gen, c->d_err);
+        CUDA_TRY(cudaGetLastError());
+        c->ks_all.keys = S.W.keys_all[S.W.rank]; c->ks_all.n = S.W.row_begin[S.W.world]; c->ks_all.gen = S.keys_gen;
+        c->launches += 1;
+        return check_err(c);
+    }
+    return LIORF_OK;
+}
+int liorf_sc_shard_sync_keys(liorf_ctx* c) { return liorf_sc_shard_sync_keys_phases(c, 3); }
+/* measurement only: 1 = this rank's consumer kernels do not wait for the peers' flags (a single rank of a G-rank search timed alone on one GPU
+ * against windows that a complete earlier batch has filled; tools/profile_sc_shard.py) */
+int liorf_sc_shard_debug_nowait(liorf_ctx* c, int on) {
+    if (!c) return LIORF_ERR_ARG;
+    c->shard.W.nowait = on != 0;
+    if (c->shard.graph) { cudaGraphExecDestroy(c->shard.graph); c->shard.graph = nullptr; }
+    return LIORF_OK;
+}
+
 /* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
- * with the SAME queries in the same order. */
+ * with the SAME queries in the same order.  phases: bit 0 = stage 1 of this rank's query slice (+ push C), bit 1 = collect + stage 2 of
+ * the owned pairs (+ push D), bit 2 = decision. */
 int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases) {
-    if (!c || !d_qdescs || Q < 1 || !d_loop_id || !d_shift || !d_dist || !(phases & 31)) return LIORF_ERR_ARG;
+    if (!c || !d_qdescs || Q < 1 || !d_loop_id || !d_shift || !d_dist || !(phases & 7)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
     if (!S.ready || Q > S.qmax) return LIORF_ERR_STATE;
-    if (c->sc_n < 1) return LIORF_ERR_STATE;
+    // ownership must be the one every rank agreed on at connect time (a database that has grown needs a new connect + key sync)
+    if (global_offset != S.W.row_begin[S.W.rank] || c->sc_n != S.W.row_begin[S.W.rank + 1] - S.W.row_begin[S.W.rank]) return LIORF_ERR_STATE;
     int rc;
-    if ((rc = c->sc_qsk.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qcn.reserve((size_t)Q * SC_SECTOR)) || (rc = c->sc_qkeys.reserve((size_t)Q * SC_RING)) ||
-        (rc = sc_reserve_query(c, Q)) || (rc = S.packC.reserve((size_t)6 * Q)) || (rc = S.list.reserve((size_t)3 * Q))) return rc;
     const double* qd = (const double*)d_qdescs;
-    float* ld = reinterpret_cast<float*>(S.packC.p); int* li = reinterpret_cast<int*>(S.packC.p) + (size_t)3 * Q;
     int* cand = d_cand ? (int*)d_cand : c->sc_q_i.p;
-    const int pairs = 3 * Q;
-    const bool want_tensor = c->sc_path == 2 || (c->sc_path == 0 && Q >= 64 && c->sc_n >= 4096);
-    if (S.W.world == 1 && phases == 31) {       // one rank, whole batch: nothing to exchange → the plain search (same kernels, one pass over the descriptors)
-        if ((rc = liorf_sc_prepare_queries_dev(c, qd, Q, c->sc_qkeys.p, c->sc_qsk.p, c->sc_qcn.p))) return rc;
-        if ((rc = sc_knn(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, global_offset, c->sc_q_d.p, cand))) return rc;
-        if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, c->sc_pair_d.p, c->sc_pair_s.p))) return rc;
-        return liorf_sc_decide_dev(c, c->sc_pair_d.p, c->sc_pair_s.p, cand, Q, d_loop_id, d_shift, d_dist);
+    if (S.W.world == 1) {                        // one rank: nothing to exchange → the plain search (the same kernels)
+        if (phases != 7) return LIORF_ERR_ARG;
+        if (c->sc_n < 1) return LIORF_ERR_STATE;
+        if ((rc = sc_reserve_query(c, Q))) return rc;
+        if (!d_cand) cand = c->sc_q_i.p;
+        return sc_query_local_dev(c, qd, Q, global_offset, cand, (int*)d_loop_id, (int*)d_shift, (double*)d_dist);
     }
-    if (phases & 16) {       // phase K: ring keys of this rank's slice of the queries → every window; the sector keys / column norms stage 2 needs
-        k_scsh_next_batch<<<1, 1, 0, c->stream>>>(S.d_batch);
-        const int q0 = (int)((long long)Q * S.W.rank / S.W.world), q1 = (int)((long long)Q * (S.W.rank + 1) / S.W.world);
-        if (q1 > q0) k_sc_keys_batch<<<q1 - q0, 64, 0, c->stream>>>(qd + (size_t)q0 * SC_DESC, q1 - q0, c->sc_qkeys.p + (size_t)q0 * SC_RING, nullptr, nullptr);
-        const size_t words = (size_t)(q1 - q0) * SC_RING;
-        k_scsh_push<<<std::max(1, std::min(64, (int)((words + 255) / 256))), 256, 0, c->stream>>>(S.W, SCSH_K, reinterpret_cast<const unsigned*>(c->sc_qkeys.p + (size_t)q0 * SC_RING),
-                                                                                             words, S.d_batch, S.d_counter, (size_t)q0 * SC_RING * sizeof(float));
-    }
-    if (phases & 1) {        // all ring keys, stage-1 filter, push of the threshold bounds (tensor path) or of the exact local top-3 (CUDA-core path)
-        k_scsh_gather_keys<<<std::min(64, (Q * SC_RING + 255) / 256), 256, 0, c->stream>>>(S.W, S.d_batch, Q * SC_RING, reinterpret_cast<unsigned*>(c->sc_qkeys.p), c->d_err);
-        if (want_tensor) { if ((rc = sc_knn_tensor(c, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li, 1))) return rc; }
+    liorf_ctx::KeySet& ks = c->ks_all;
+    if (!ks.keys || ks.n != S.W.row_begin[S.W.world]) return LIORF_ERR_STATE;       // liorf_sc_shard_sync_keys (or a borrow from a synced context) first
+    const int q0 = (int)((long long)Q * S.W.rank / S.W.world), q1 = (int)((long long)Q * (S.W.rank + 1) / S.W.world), Qs = q1 - q0;
+    if ((rc = c->sc_qkeys.reserve((size_t)std::max(Qs, 1) * SC_RING)) || (rc = sc_reserve_query(c, Q)) || (rc = S.list.reserve((size_t)3 * Q))) return rc;
+    if (!d_cand) cand = c->sc_q_i.p;
+    ShardPush P; std::memset(&P, 0, sizeof(P));
+    P.enabled = 1; P.q0 = q0; P.W = S.W; P.counter = S.d_counter; P.batch_p = S.d_batch;
+    if (phases & 1) {        // ring keys of this rank's query slice (first block bumps the batch number) → exact GLOBAL top-3 → every window
+        k_sc_keys_batch<<<std::max(Qs, 1), 64, 0, c->stream>>>(qd + (size_t)q0 * SC_DESC, Qs, c->sc_qkeys.p, nullptr, nullptr, S.d_batch);
+        c->launches += 1;
+        if (Qs > 0 && sc_want_tensor(c, Qs, ks.n)) { if ((rc = sc_knn_tensor(c, ks, ks.n, c->sc_qkeys.p, Qs, 0, nullptr, nullptr, &P))) return rc; }
         else {
-            if ((rc = sc_knn_brute(c, c->sc_keys.p, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li))) return rc;
-            k_scsh_push<<<std::min(64, (6 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_C, S.packC.p, (size_t)6 * Q, S.d_batch, S.d_counter);
+            if (Qs > 0 && (rc = sc_knn_brute(c, ks.keys, ks.n, c->sc_qkeys.p, Qs, 0, c->sc_q_d.p, c->sc_q_i.p))) return rc;
+            k_scsh_push_c<<<std::max(1, std::min(64, (3 * Qs + 255) / 256)), 256, 0, c->stream>>>(S.W, c->sc_q_d.p, c->sc_q_i.p, q0, Qs, S.d_batch, S.d_counter);
+            c->launches += 1;
         }
     }
-    if (phases & 2) {        // global threshold → select → exact re-rank → push of the exact local top-3
-        if (want_tensor) {
-            if ((rc = sc_knn_tensor(c, c->sc_n, c->sc_qkeys.p, Q, global_offset, ld, li, 2))) return rc;
-            k_scsh_push<<<std::min(64, (6 * Q + 255) / 256), 256, 0, c->stream>>>(S.W, SCSH_C, S.packC.p, (size_t)6 * Q, S.d_batch, S.d_counter);
-        }
+    if (phases & 2) {        // every slice has arrived → local copy + the pairs this rank owns → distanceBtnScanContext on exactly those, pushed by the warps that compute them
+        k_scsh_collect<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, Q, c->sc_q_d.p, cand, c->d_err, global_offset, c->sc_n, S.list.p, S.d_nlist);
+        c->launches += 1;
+        if ((rc = sc_distance_launch(c, qd, cand, 3 * Q, global_offset, nullptr, nullptr, S.list.p, S.d_nlist, &P))) return rc;
     }
-    if (phases & 4) {        // merge to the global top-3, owner-computes distanceBtnScanContext, push
-        // global top-3 + the compact list of the pairs this rank owns → stage 2 on exactly those, results pushed by the stage-2 kernel itself
-        CUDA_TRY(cudaMemsetAsync(S.d_nlist, 0, sizeof(int), c->stream));
-        k_scsh_merge<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, Q, c->sc_q_d.p, cand, c->d_err, global_offset, c->sc_n, S.list.p, S.d_nlist);
-        k_scsh_skcn_owned<<<std::min(3 * Q, 32 * c->num_sms), 64, 0, c->stream>>>(qd, S.list.p, S.d_nlist, c->sc_qsk.p, c->sc_qcn.p);      // sector keys / column norms of the queries whose candidates this rank owns
-        ShardPush P; P.enabled = 1; P.Q = Q; P.W = S.W; P.counter = S.d_counter; P.batch_p = S.d_batch;
-        if ((rc = sc_distance_launch(c, qd, c->sc_qsk.p, c->sc_qcn.p, cand, pairs, global_offset, nullptr, nullptr, S.list.p, S.d_nlist, &P))) return rc;
+    if (phases & 4) {        // decision (+ re-arms the owned-pair counter)
+        k_scsh_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, cand, Q, (int*)d_loop_id, (int*)d_shift, (double*)d_dist, c->d_err, S.d_nlist);
+        c->launches += 1;
     }
-    if (phases & 8)          // owner pick + decision
-        k_scsh_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, cand, Q, (int*)d_loop_id, (int*)d_shift, (double*)d_dist, c->d_err);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 7;
     return LIORF_OK;
 }
 /* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
@@ -1454,32 +1461,53 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
 int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand) {
     if (!c) return LIORF_ERR_ARG;
     liorf_ctx::ScShard& S = c->shard;
-    // A batch is ~25 kernels of a few microseconds each: replayed from a CUDA graph once the same request (buffers, size) has been seen
-    // twice, so that the host's launch rate does not bound the queries/s.  Section timing (CUDA events) keeps the plain launches.
-    const void* sig[8] = {d_qdescs, (const void*)(size_t)Q, (const void*)(size_t)global_offset, d_loop_id, d_shift, d_dist, d_cand, (const void*)(size_t)c->sc_n};
+    // A batch is ~9 small kernels: replayed from a CUDA graph once the same request has been seen twice, so that the host's launch rate does
+    // not bound the queries/s.  The signature holds everything a captured kernel argument can depend on: the caller's buffers and sizes, the
+    // database extent and key generation, the search path, and every internal buffer (DevBuf::reserve may reallocate any of them).
     const bool can_graph = c->use_graphs && !c->prof.enabled && S.ready;
-    if (can_graph && S.graph && std::memcmp(sig, S.gsig, sizeof(sig)) == 0) {
+    if (!can_graph) return liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 7);
+    auto make_sig = [&](const void** sig) {
+        const liorf_ctx::KeySet& ks = S.W.world == 1 ? c->ks_local : c->ks_all;
+        const void* v[40] = {d_qdescs, (const void*)(size_t)Q, (const void*)(size_t)global_offset, d_loop_id, d_shift, d_dist, d_cand, (const void*)(size_t)c->sc_n,
+                             (const void*)(size_t)ks.n, (const void*)(size_t)ks.gen, (const void*)(size_t)ks.img_n, (const void*)(size_t)ks.img_gen, ks.keys, ks.bimg.p, ks.center,
+                             (const void*)(size_t)c->sc_path, (const void*)(size_t)S.W.nowait,
+                             c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, c->sc_keys.p, c->sc_qkeys.p, c->sc_q_d.p, c->sc_q_i.p, c->sc_pair_d.p, c->sc_pair_s.p, c->sc_part_d.p, c->sc_part_i.p,
+                             S.list.p, c->sct_aimg.p, c->sct_qnorm.p, c->sct_cmin.p, c->sct_cmin32.p, c->sct_part.p, c->sct_cand.p, c->sct_cnt.p, c->sct_over_cnt, nullptr, nullptr, nullptr};
+        std::memcpy(sig, v, sizeof(v));
+    };
+    const void* sig[40];
+    make_sig(sig);
+    if (S.graph && std::memcmp(sig, S.gsig, sizeof(sig)) == 0) {
         CUDA_TRY(cudaSetDevice(c->P.device));
         CUDA_TRY(cudaGraphLaunch(S.graph, c->stream));
-        c->launches += 25;
+        c->launches += 9;
         return LIORF_OK;
     }
-    if (can_graph && std::memcmp(sig, S.last_sig, sizeof(sig)) == 0) {        // second identical request: every buffer is sized, capture it
+    if (std::memcmp(sig, S.last_sig, sizeof(sig)) == 0) {        // second identical request: every buffer is sized and the operand image is current → capture
         CUDA_TRY(cudaSetDevice(c->P.device));
         if (S.graph) { cudaGraphExecDestroy(S.graph); S.graph = nullptr; }
         cudaGraph_t g = nullptr;
+        const long long launches0 = c->launches;
         CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 31);
+        const int rc = liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 7);
         const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        c->launches = launches0;
         if (rc || e != cudaSuccess) { if (g) cudaGraphDestroy(g); (void)cudaGetLastError(); return rc ? rc : LIORF_ERR_CUDA; }
+        make_sig(sig);
+        if (std::memcmp(sig, S.last_sig, sizeof(sig)) != 0) {     // something was (re)allocated or rebuilt during the capture after all: do not keep it
+            cudaGraphDestroy(g); std::memset(S.last_sig, 0, sizeof(S.last_sig));
+            return liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 7);
+        }
         CUDA_TRY(cudaGraphInstantiate(&S.graph, g, 0));
         cudaGraphDestroy(g);
         std::memcpy(S.gsig, sig, sizeof(sig));
         CUDA_TRY(cudaGraphLaunch(S.graph, c->stream));
+        c->launches += 9;
         return LIORF_OK;
     }
-    std::memcpy(S.last_sig, sig, sizeof(sig));
-    return liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 31);
+    const int rc = liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 7);
+    make_sig(S.last_sig);                                         // as of AFTER the call: buffers sized, image built
+    return rc;
 }
 
 int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3) {
@@ -1492,7 +1520,7 @@ int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_
     int rc;
     if ((rc = sc_reserve_query(c, 1))) return rc;
     const size_t qe = (size_t)c->sc_n - 1;                                       // query = last entry (:257-258)
-    if ((rc = sc_knn(c, c->sc_keys.p, c->sc_tree_n, c->sc_keys.p + qe * SC_RING, 1, 0, c->sc_q_d.p, c->sc_q_i.p))) return rc;
+    if ((rc = sc_knn(c, local_keys(c), c->sc_tree_n, c->sc_keys.p + qe * SC_RING, 1, 0, c->sc_q_d.p, c->sc_q_i.p))) return rc;
     // result slots are zero-initialised in the reference (:289-290): an unfilled slot means candidate 0
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 700, c->sc_q_i.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));

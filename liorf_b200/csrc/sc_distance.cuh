@@ -7,7 +7,7 @@
 // column sets from shared memory instead of issuing 140 dependent global loads per lane.  The arithmetic — every fp64 sum
 // in the reference's sequential order — is the one of k_sc_distance (scancontext.cuh), which stays in use for the live
 // single-query call; results are bit-identical (tests/test_gpu_sc_tensor.py, test_gpu_deskew_sc.py).
-// Algorithmic traffic per pair: 9 600 B candidate + 9 600 B query descriptor (three pairs share a query: L2) + 2 x 960 B keys/norms.
+// Algorithmic traffic per pair: 9 600 B candidate + 9 600 B query descriptor (three pairs share a query: L2) + 960 B candidate keys/norms.
 #pragma once
 #include "sc_shard.cuh"
 
@@ -17,8 +17,7 @@ constexpr int SCDB_WARPS = 4;
 constexpr int SCDB_WARP_BYTES = SC_DESC * 8 + 2 * SC_SECTOR * 8 + 7 * SC_SECTOR * 8;      // candidate descriptor + two sector keys + 7 x 60 similarities = 13 920 B
 constexpr int SCDB_SMEM = SCDB_WARPS * SCDB_WARP_BYTES + SCDB_WARPS * 8;
 
-__global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const double* __restrict__ qdesc, const double* __restrict__ qsk, const double* __restrict__ qcn,
-                                                                      const int* __restrict__ cand, int n_pairs, int cand_per_query,
+__global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const double* __restrict__ qdesc, const int* __restrict__ cand, int n_pairs, int cand_per_query,
                                                                       const double* __restrict__ db_desc, const double* __restrict__ db_sk, const double* __restrict__ db_cn,
                                                                       int own_begin, int own_count, double* __restrict__ out_dist, int* __restrict__ out_shift, int* err_flag,
                                                                       const int* __restrict__ pair_list, const int* __restrict__ n_list, ShardPush P) {
@@ -40,20 +39,32 @@ __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const doub
         const int pair = pair_list ? pair_list[it] : it;
         const int q = pair / cand_per_query;
         const int c = cand[pair];
-        if (c == 0x7fffffff || c < 0) { if (l == 0) { out_dist[pair] = INFINITY; out_shift[pair] = 0; } continue; }
+        if (c == 0x7fffffff || c < 0) { if (l == 0 && out_dist) { out_dist[pair] = INFINITY; out_shift[pair] = 0; } continue; }
         const int lc = c - own_begin;
         if (lc < 0 || lc >= own_count) continue;
         const double* sc1 = qdesc + (size_t)q * SC_DESC;
-        const double* cn1 = qcn + (size_t)q * SC_SECTOR; const double* cn2 = db_cn + (size_t)lc * SC_SECTOR;
+        const double* cn2 = db_cn + (size_t)lc * SC_SECTOR;
         __syncwarp();                                                   // every lane is done with the previous pair's buffers
         if (l == 0) { mbar_expect_tx(bar, SC_DESC * 8); bulk_g2s(smem_u32(s_sc2), db_desc + (size_t)lc * SC_DESC, SC_DESC * 8, bar); }
         // the candidate's sector key twice in a row (in the not yet used similarity buffer): circshift(vkey2, s)[k] = vk2d[k - s + 60]
         // is then a plain offset from a per-lane base — no modular index arithmetic inside the 60-step sums
         double* s_vk2d = &s_sim[0][0];
-        for (int k = l; k < SC_SECTOR; k += 32) {
-            s_vk1[k] = qsk[(size_t)q * SC_SECTOR + k];
-            const double v = db_sk[(size_t)lc * SC_SECTOR + k];
-            s_vk2[k] = v; s_vk2d[k] = v; s_vk2d[k + SC_SECTOR] = v;
+        // the QUERY's sector key and column norms are derived here, from the descriptor the fine search reads anyway (lane ↔ column,
+        // the 40 loads of a lane are independent; k_sc_keys_batch's arithmetic: sequential sums over the rings, :214-227, :75-81) —
+        // no per-query key arrays, no kernel in front of this one
+        double n1A = 0, n1B = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = l + 32 * h;
+            if (k < SC_SECTOR) {
+                double sum = 0, sq = 0;
+#pragma unroll
+                for (int r = 0; r < SC_RING; ++r) { const double v = sc1[r * SC_SECTOR + k]; sum += v; sq += v * v; }
+                s_vk1[k] = sum / SC_RING;
+                if (h == 0) n1A = sqrt(sq); else n1B = sqrt(sq);
+                const double v2 = db_sk[(size_t)lc * SC_SECTOR + k];
+                s_vk2[k] = v2; s_vk2d[k] = v2; s_vk2d[k + SC_SECTOR] = v2;
+            }
         }
         __syncwarp();
         // fastAlignUsingVkey (:93-113): lane ↔ shift, sequential sum over columns; first strict minimum of the norm
@@ -87,14 +98,14 @@ __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const doub
 #pragma unroll
         for (int a = 1; a < 7; ++a) { int v = shifts[a]; int b = a - 1; while (b >= 0 && shifts[b] > v) { shifts[b + 1] = shifts[b]; --b; } shifts[b + 1] = v; }
         // the candidate descriptor has landed (or the wait gives up with the error flag set)
-        if (!mbar_wait(bar, parity, &s_abort, err_flag)) return;
+        if (!mbar_wait(bar, parity, &s_abort, err_flag)) break;        // error flag is set; the epilogue below still runs (flags, counter)
         parity ^= 1u;
         // fine search (:123-144): lane ↔ column, dot over the 20 rings for each of the 7 shifts, candidate columns from shared memory
         for (int k = l; k < SC_SECTOR; k += 32) {
             double a1[SC_RING];
 #pragma unroll
             for (int r = 0; r < SC_RING; ++r) a1[r] = sc1[r * SC_SECTOR + k];
-            const double n1 = cn1[k];
+            const double n1 = k < 32 ? n1A : n1B;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 int k2 = k - shifts[j]; if (k2 < 0) k2 += SC_SECTOR;
@@ -123,32 +134,12 @@ __global__ void __launch_bounds__(SCDB_WARPS * 32) k_sc_distance_bulk(const doub
             if (dj < mn) { mn = dj; arg = sj; }
         }
         if (l == 0) {
-            if (P.enabled) {             // push: slot [my rank] of every rank's window, straight from the warp that computed the pair
-                for (int g = 0; g < P.W.world; ++g) {
-                    unsigned char* slot = P.W.base[g] + P.W.off[SCSH_D] + (size_t)P.W.rank * P.W.stride[SCSH_D];
-                    reinterpret_cast<double*>(slot)[pair] = mn;
-                    reinterpret_cast<int*>(slot + (size_t)3 * P.Q * 8)[pair] = arg;
-                }
+            if (P.enabled) {             // push: entry [pair] of the pair array of every rank's window, straight from the warp that computed the pair
+                for (int g = 0; g < P.W.world; ++g) { scsh_d_dist(P.W, g)[pair] = mn; scsh_d_shift(P.W, g)[pair] = arg; }
             } else { out_dist[pair] = mn; out_shift[pair] = arg; }
         }
     }
-    if (P.enabled) {                     // the last block to finish raises this rank's phase-D flag in every peer window
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned t = atomicAdd(P.counter, 1u);
-            if (t == gridDim.x - 1) {
-                *P.counter = 0u;
-                __threadfence_system();
-                const unsigned b = *P.batch_p;
-                for (int g = 0; g < P.W.world; ++g) {
-                    if (g == P.W.rank) continue;
-                    unsigned* f = reinterpret_cast<unsigned*>(P.W.base[g] + scsh_flag_off(P.W.rank, SCSH_D));
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(b) : "memory");
-                }
-            }
-        }
-    }
+    if (P.enabled) scsh_raise(P.W, SCSH_D, *P.batch_p, P.counter);      // the last block to finish raises this rank's phase-D flag in every peer window
 }
 
 }  // namespace liorf

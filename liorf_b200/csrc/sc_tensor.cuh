@@ -21,8 +21,8 @@
 //   k_sct_rerank: exact nanoflann-order distances of the <= 32 keys of each candidate chunk, top-3 by (dist, idx)
 //   Completeness: the exact 3rd-best distance d3 <= t3 + eps (three different keys have d~ <= t3, hence exact distance
 //   <= t3 + eps), and a key of the exact top-3 has d~ <= d + eps <= d3 + eps <= t3 + 2 eps  =>  its chunk is a candidate.
-//   A query with more than SCT_CAP candidate chunks is answered by the exact brute-force kernel instead
-//   (k_sc_knn_overflow) — never a wrong answer.
+//   A query with more than SCT_CAP candidate chunks is answered by an exact scan of all keys instead (same warp of
+//   k_sct_rerank) — never a wrong answer.
 //
 // Kernel shape (k_sc_tensor): persistent, one CTA per SM, 320 threads:
 //   warp 0     TMA producer: 16 KB operand images with cp.async.bulk + mbarrier complete_tx (6-stage key ring, 2 query buffers)
@@ -35,6 +35,7 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include "scancontext.cuh"
+#include "sc_window.cuh"
 
 namespace liorf {
 
@@ -386,10 +387,15 @@ __device__ __forceinline__ void scs_range(int n_chunks, int& c0, int& c1) {
     const int per = (n_chunks + SCS_SPLITS - 1) / SCS_SPLITS;
     c0 = blockIdx.y * per; c1 = min(n_chunks, c0 + per);
 }
-__global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_top3(const float* __restrict__ cmin, int n_chunks, int n_rows, float* __restrict__ part) {
+__global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_top3(const float* __restrict__ cmin, int n_chunks, int n_rows, float* __restrict__ part, int Q, int* __restrict__ cand_cnt,
+                                                             int* __restrict__ over_cnt) {
     __shared__ float s_t[SCS_SLICES][3][32];
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane;
+    if (blockIdx.y == 0 && sl == 0) {                       // arms the selection that follows: candidate counters of these queries, overflow statistic
+        if (q < Q) cand_cnt[q] = 0;
+        if (blockIdx.x == 0 && lane == 0) *over_cnt = 0;
+    }
     const float* col = cmin + q;
     int c0, c1; scs_range(n_chunks, c0, c1);
     float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
@@ -420,13 +426,12 @@ __device__ __forceinline__ void sct_emit_tile(const float* __restrict__ cmin32, 
 }
 __global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __restrict__ cmin, const float* __restrict__ cmin32, int n_chunks, int n_rows, const float* __restrict__ part,
                                                                const float* __restrict__ qnorm, int Q, const unsigned* __restrict__ nmax_bits,
-                                                               int* __restrict__ cand, int* __restrict__ cand_cnt, const float* __restrict__ thr_in = nullptr) {   // thr_in: sharded search (sc_shard.cuh)
+                                                               int* __restrict__ cand, int* __restrict__ cand_cnt) {
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane;
     if (q >= Q) return;
     float thr;
-    if (thr_in) thr = thr_in[q];                     // sharded search: the threshold derived from every rank's bounds (sc_shard.cuh)
-    else {
+    {
         float t1 = 3.0e38f, t2 = 3.0e38f, t3 = 3.0e38f;
 #pragma unroll
         for (int sp = 0; sp < SCS_SPLITS; ++sp) {
@@ -455,58 +460,53 @@ __global__ void __launch_bounds__(32 * SCS_SLICES) k_sct_select(const float* __r
 
 // exact re-rank: one warp per query, one lane per key of a candidate chunk; nanoflann's evalMetric op order
 // (ringkey_dist_dev), total order (dist, idx).  chunk id = kt * 4 + c holds keys ((32 c + lane) * nkt + kt).
+// A query whose candidate list overflowed (> SCT_CAP chunks passed the filter: only adversarial databases do that) is answered by
+// the same warp with an exact scan of ALL keys — never a wrong answer.
+// Sharded search (sc_shard.cuh, P.enabled): the queries are this rank's slice [P.q0, P.q0 + Q) of the batch and the result — the
+// GLOBAL top-3, the keys being the replicated index — goes straight into the candidate array of every rank's window (phase C);
+// the last block raises the flags: compute and transfer in ONE kernel.
 __global__ void __launch_bounds__(256) k_sct_rerank(const float* __restrict__ keys, int n_keys, int nkt, int idx_offset, const float* __restrict__ qkeys, int Q,
                                                    const int* __restrict__ cand, const int* __restrict__ cand_cnt, float* __restrict__ out_d, int* __restrict__ out_i,
-                                                   int* __restrict__ over_list, int* __restrict__ over_cnt) {
+                                                   int* __restrict__ over_cnt, ShardPush P) {
     const int q = blockIdx.x * (blockDim.x / 32) + warp_id();
-    if (q >= Q) return;
     const int l = lane_id();
-    const int n = cand_cnt[q];
-    if (n > SCT_CAP) { if (l == 0) { const int s = atomicAdd(over_cnt, 1); over_list[s] = q; } return; }
-    float aq[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) aq[k] = __ldg(qkeys + 20 * (size_t)q + k);
-    Top3 t; top3_init(t);
-    for (int i = 0; i < n; ++i) {
-        const int ch = cand[(size_t)q * SCT_CAP + i];
-        const int kidx = (SCT_CHUNK * (ch & 3) + l) * nkt + (ch >> 2);
-        if (kidx < n_keys) top3_insert(t, ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)kidx)), idx_offset + kidx);
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        float md = t.d[0]; int mi = t.i[0];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(FULL, md, o); const int oi = __shfl_xor_sync(FULL, mi, o);
-            if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
-        }
-        if (t.d[0] == md && t.i[0] == mi) { t.d[0] = t.d[1]; t.i[0] = t.i[1]; t.d[1] = t.d[2]; t.i[1] = t.i[2]; t.d[2] = INFINITY; t.i[2] = 0x7fffffff; }
-        if (l == 0) { out_d[3 * (size_t)q + r] = md; out_i[3 * (size_t)q + r] = mi; }
-    }
-}
-
-// queries whose candidate list overflowed: exact brute force, one block per query (grid-stride over the device-side list)
-__global__ void __launch_bounds__(256) k_sc_knn_overflow(const float* __restrict__ keys, int n_keys, int idx_offset, const float* __restrict__ qkeys,
-                                                        const int* __restrict__ over_list, const int* __restrict__ over_cnt, float* __restrict__ out_d, int* __restrict__ out_i) {
-    __shared__ float s_d[256 * 3]; __shared__ int s_i[256 * 3];
-    const int n_over = *over_cnt;
-    for (int o = blockIdx.x; o < n_over; o += gridDim.x) {
-        const int q = over_list[o];
+    if (q < Q) {
+        const int n = cand_cnt[q];
         float aq[20];
 #pragma unroll
         for (int k = 0; k < 20; ++k) aq[k] = __ldg(qkeys + 20 * (size_t)q + k);
         Top3 t; top3_init(t);
-        for (int k = threadIdx.x; k < n_keys; k += blockDim.x) top3_insert(t, ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)k)), idx_offset + k);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { s_d[3 * threadIdx.x + j] = t.d[j]; s_i[3 * threadIdx.x + j] = t.i[j]; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Top3 g; top3_init(g);
-            for (int e = 0; e < 256 * 3; ++e) if (s_i[e] != 0x7fffffff) top3_insert(g, s_d[e], s_i[e]);
-            for (int j = 0; j < 3; ++j) { out_d[3 * (size_t)q + j] = g.d[j]; out_i[3 * (size_t)q + j] = g.i[j]; }
+        if (n > SCT_CAP) {
+            if (l == 0) atomicAdd(over_cnt, 1);
+            for (int kidx = l; kidx < n_keys; kidx += 32) top3_insert(t, ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)kidx)), idx_offset + kidx);
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int ch = cand[(size_t)q * SCT_CAP + i];
+                const int kidx = (SCT_CHUNK * (ch & 3) + l) * nkt + (ch >> 2);
+                if (kidx < n_keys) top3_insert(t, ringkey_dist_dev(aq, reinterpret_cast<const float4*>(keys + 20 * (size_t)kidx)), idx_offset + kidx);
+            }
         }
-        __syncthreads();
+        float rd = INFINITY; int ri = 0x7fffffff;                  // lane r < 3 ends up holding the r-th best
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float md = t.d[0]; int mi = t.i[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(FULL, md, o); const int oi = __shfl_xor_sync(FULL, mi, o);
+                if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+            }
+            if (t.d[0] == md && t.i[0] == mi) { t.d[0] = t.d[1]; t.i[0] = t.i[1]; t.d[1] = t.d[2]; t.i[1] = t.i[2]; t.d[2] = INFINITY; t.i[2] = 0x7fffffff; }
+            if (l == r) { rd = md; ri = mi; }
+        }
+        if (l < 3) {
+            if (out_d) { out_d[3 * (size_t)q + l] = rd; out_i[3 * (size_t)q + l] = ri; }
+            if (P.enabled) {
+                const size_t e = 3 * (size_t)(P.q0 + q) + l;
+                for (int g = 0; g < P.W.world; ++g) { scsh_c_dist(P.W, g)[e] = rd; scsh_c_idx(P.W, g)[e] = ri; }
+            }
+        }
     }
+    if (P.enabled) scsh_raise(P.W, SCSH_C, *P.batch_p, P.counter);
 }
 
 }  // namespace liorf

@@ -258,9 +258,11 @@ __global__ void __launch_bounds__(128) k_sc_decide(const double* __restrict__ pa
 }
 
 // keys (fp32 ring key, sector key, column norms) for externally supplied descriptors — batch version of k_sc_finalize
+// batch (nullable): the sharded search's batch number, bumped once per launch (sc_shard.cuh: this is the first kernel of a batch)
 __global__ void __launch_bounds__(64) k_sc_keys_batch(const double* __restrict__ desc, int n, float* __restrict__ ringkey, double* __restrict__ sectorkey,
-                                                     double* __restrict__ colnorm) {
+                                                     double* __restrict__ colnorm, unsigned* batch = nullptr) {
     __shared__ double s_d[SC_DESC];
+    if (batch && blockIdx.x == 0 && threadIdx.x == 0) *batch += 1u;
     const int e = blockIdx.x; if (e >= n) return;
     for (int i = threadIdx.x; i < SC_DESC; i += blockDim.x) s_d[i] = desc[(size_t)e * SC_DESC + i];
     __syncthreads();

@@ -1,258 +1,86 @@
-"""ScanContext loop-closure search over a keyframe database sharded across ranks (BASELINE config 5).
+"""ScanContext loop-closure search over a keyframe database sharded across ranks (BASELINE config 5) — the Python side of
+liorf_sc_shard_* (csrc/sc_shard.cuh).
 
-Partitioning: database rows [g*K/G, (g+1)*K/G) live on rank g (ring keys + descriptors); queries are replicated.
-Protocol per query batch (the only data-path collectives of the whole library):
-  1. every rank: exact local top-3 ring-key candidates (global indices)                      [local kernel]
-  2. all_gather of Q x 3 x (f32 dist, i32 idx) = 24 B per query per rank                       [NCCL / gloo]
-  3. every rank: merge the G lists by (dist, idx) -> the GLOBAL top-3 (identical everywhere)   [local kernel]
-  4. owner-computes: distanceBtnScanContext for the candidates this rank owns, +inf otherwise  [local kernel]
-  5. all_gather of Q x 3 x (f64 dist, i32 shift); every pair is finite on exactly one rank      [NCCL / gloo]
-  6. every rank: strict-< argmin in kNN order + SC_DIST_THRES                                  [local kernel]
-Evaluating exactly the global top-3 (never extra local candidates) keeps results identical to the reference.
-
-`ops` supplies the four local steps, so the same orchestration runs on the GPU library (GpuOps) and, in the CPU tests,
-on a stand-in that calls the oracle (tests/test_multiproc_gloo.py)."""
+"Replicated index, sharded payload": rank g holds the descriptors / sector keys / column norms of rows [row_begin[g], row_begin[g+1]);
+the 80-byte ring key of every row is replicated (pushed over NVLink once, `sync_keys`).  Per batch every rank runs stage 1 (ring-key
+top-3, include/Scancontext.cpp:289-295) for ITS SLICE of the queries against all keys and stage 2 (distanceBtnScanContext, :302-317) for
+the candidates IT OWNS; the two exchanges are done by the library's own kernels through peer-memory windows (plain stores over NVLink +
+system-scope flags), one library call per batch, no collective launch, no host round trip.  torch.distributed is used once, to hand the
+64-byte cudaIpc handles around."""
 import ctypes as C
-
-import numpy as np
-
-
-def merge_top3_numpy(gd, gi):
-    """(G,Q,3) dist / idx -> global top-3 by (dist, idx); unfilled slots carry idx INT_MAX."""
-    G, Q, _ = gd.shape
-    d = np.transpose(gd, (1, 0, 2)).reshape(Q, G * 3)
-    i = np.transpose(gi, (1, 0, 2)).reshape(Q, G * 3).astype(np.int64)
-    d = np.where(i == 0x7fffffff, np.inf, d)
-    order = np.lexsort((i, d), axis=1)[:, :3]
-    rows = np.arange(Q)[:, None]
-    return d[rows, order].astype(np.float32), i[rows, order].astype(np.int32)
-
-
-class ShardedScanContextSearch:
-    def __init__(self, ops, rank, world, dist=None):
-        self.ops, self.rank, self.world, self.dist = ops, rank, world, dist
-        self._gbuf = {}
-
-    def _all_gather(self, t):
-        if self.world == 1:
-            return t.unsqueeze(0)
-        key = (tuple(t.shape), t.dtype, t.device)
-        out = self._gbuf.get(key)
-        if out is None:
-            out = self._gbuf[key] = t.new_empty((self.world * t.shape[0],) + tuple(t.shape[1:]))     # concatenated layout works for NCCL and gloo
-        self.dist.all_gather_into_tensor(out, t.contiguous())
-        return out.view((self.world,) + tuple(t.shape))
-
-    def query(self, q):
-        """q: prepared queries (ops-specific handle).  Returns (loop_id, shift, dist, cand) as tensors of the ops' device."""
-        if self.world > 1 and hasattr(self.ops, "knn_packed"):
-            return self._query_packed(q)
-        ld, li = self.ops.knn(q)                                   # 1
-        if self.world > 1:
-            # 2: ONE collective for (f32 dist, i32 idx): the distance travels as its bit pattern next to the index
-            packed = self._all_gather(self.ops.xp_stack_i32(ld, li))
-            gd, gi = self.ops.xp_unstack_i32(packed)
-            cd, ci = self.ops.merge(gd, gi)                        # 3
-        else:
-            cd, ci = ld, li
-        pd, ps = self.ops.distance(q, ci)                          # 4
-        if self.world > 1:
-            # 5: ONE collective for (f64 dist, shift): the shift (0..59) travels as an exact double
-            g = self._all_gather(self.ops.xp_stack_f64(pd, ps))
-            gpd, gps = g[..., 0], g[..., 1]
-            best = gpd.argmin(dim=0, keepdim=True)
-            pd, ps = gpd.gather(0, best)[0].contiguous(), gps.gather(0, best)[0].to(ps.dtype).contiguous()
-        return self.ops.decide(pd, ps, ci) + (ci,)                 # 6
-
-    def _query_packed(self, q):
-        """same protocol with the library writing each phase's output into ONE buffer per collective and doing the merge /
-        owner pick in its own kernels: per batch 7 library calls + 2 all_gathers, no tensor-library ops on the host path."""
-        ops = self.ops
-        buf = ops.knn_packed(q)                                    # 1   {f32 dist[Q][3], i32 idx[Q][3]}
-        cd, ci = ops.merge_packed(self._all_gather(buf), self.world)          # 2, 3
-        pbuf = ops.distance_packed(q, ci)                          # 4   {f64 dist[Q][3], i32 shift[Q][3]}
-        pd, ps = ops.combine_packed(self._all_gather(pbuf), self.world)       # 5
-        return ops.decide(pd, ps, ci) + (ci,)                      # 6
-
-
-class TorchPacking:
-    """(dist, idx) / (dist, shift) packing shared by the GPU ops and the CPU stand-in of the tests (torch tensors)."""
-
-    @staticmethod
-    def xp_stack_i32(d, i):
-        import torch
-        return torch.stack([d.contiguous().view(torch.int32), i], dim=-1).contiguous()
-
-    @staticmethod
-    def xp_unstack_i32(p):
-        import torch
-        return p[..., 0].contiguous().view(torch.float32), p[..., 1].contiguous()
-
-    @staticmethod
-    def xp_stack_f64(d, s):
-        import torch
-        return torch.stack([d, s.to(torch.float64)], dim=-1).contiguous()
-
-
-class GpuOps(TorchPacking):
-    """The four local steps on the CUDA library; all tensors live on the context's device and stream."""
-
-    def __init__(self, ctx, global_offset, torch):
-        self.ctx, self.off, self.torch = ctx, int(global_offset), torch
-        self.dev = torch.device(f"cuda:{ctx.params.device}")
-        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.dev)
-        self._bufs = {}
-
-    @staticmethod
-    def _vp(t):
-        return C.c_void_p(t.data_ptr())
-
-    def prepare(self, qdesc_host):
-        t = self.torch
-        with t.cuda.stream(self.stream):
-            d_q = t.from_numpy(np.ascontiguousarray(qdesc_host, np.float64).reshape(-1, 1200)).to(self.dev)
-        return self.prepare_dev(d_q)
-
-    def _buf(self, name, shape, dtype):
-        """output tensors are allocated once per (name, shape): a batch is a handful of ~100 us kernels, so allocator calls
-        in the loop would show up in the queries/s."""
-        key = (name, tuple(shape))
-        b = self._bufs.get(key)
-        if b is None:
-            b = self._bufs[key] = self.torch.empty(shape, dtype=dtype, device=self.dev)
-        return b
-
-    def prepare_dev(self, d_q):
-        """ring keys (a11), sector keys and column norms of query descriptors already on the device."""
-        t = self.torch
-        with t.cuda.stream(self.stream):
-            Q = d_q.shape[0]
-            keys = self._buf("keys", (Q, 20), t.float32); sk = self._buf("sk", (Q, 60), t.float64); cn = self._buf("cn", (Q, 60), t.float64)
-            self.ctx.lib.liorf_sc_prepare_queries_dev(self.ctx.h, self._vp(d_q), Q, self._vp(keys), self._vp(sk), self._vp(cn))
-        return dict(desc=d_q, keys=keys, sk=sk, cn=cn, Q=Q)
-
-    def knn(self, q):
-        t = self.torch
-        with t.cuda.stream(self.stream):
-            d = self._buf("knn_d", (q["Q"], 3), t.float32); i = self._buf("knn_i", (q["Q"], 3), t.int32)
-            self.ctx.lib.liorf_sc_knn_batch_dev(self.ctx.h, self._vp(q["keys"]), q["Q"], self.off, self._vp(d), self._vp(i))
-        return d, i
-
-    def merge(self, gd, gi):
-        t = self.torch
-        G, Q, _ = gd.shape
-        with t.cuda.stream(self.stream):
-            d = self._buf("mrg_d", (Q, 3), t.float32); i = self._buf("mrg_i", (Q, 3), t.int32)
-            self.ctx.lib.liorf_sc_merge_top3_dev(self.ctx.h, self._vp(gd), self._vp(gi), G, Q, self._vp(d), self._vp(i))
-        return d, i
-
-    def distance(self, q, cand):
-        t = self.torch
-        with t.cuda.stream(self.stream):
-            pd = self._buf("pd", (q["Q"], 3), t.float64); ps = self._buf("ps", (q["Q"], 3), t.int32)
-            pd.fill_(float("inf")); ps.zero_()
-            self.ctx.lib.liorf_sc_distance_batch_dev(self.ctx.h, self._vp(q["desc"]), self._vp(q["sk"]), self._vp(q["cn"]), self._vp(cand), q["Q"], self.off,
-                                                     self._vp(pd), self._vp(ps))
-        return pd, ps
-
-    def decide(self, pd, ps, cand):
-        t = self.torch
-        Q = pd.shape[0]
-        with t.cuda.stream(self.stream):
-            loop = self._buf("loop", (Q,), t.int32); sh = self._buf("sh", (Q,), t.int32); dd = self._buf("dd", (Q,), t.float64)
-            self.ctx.lib.liorf_sc_decide_dev(self.ctx.h, self._vp(pd), self._vp(ps), self._vp(cand), Q, self._vp(loop), self._vp(sh), self._vp(dd))
-        return loop, sh, dd
-
-    # ---- packed variants: one allocation per collective ----
-    def knn_packed(self, q):
-        t = self.torch
-        Q = q["Q"]
-        with t.cuda.stream(self.stream):
-            buf = self._buf("knn_packed", (6 * Q,), t.int32)
-            self.ctx.lib.liorf_sc_knn_batch_dev(self.ctx.h, self._vp(q["keys"]), Q, self.off, C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr() + 12 * Q))
-        return buf
-
-    def merge_packed(self, g, world):
-        t = self.torch
-        Q = g.shape[-1] // 6
-        with t.cuda.stream(self.stream):
-            d = self._buf("mrg_d", (Q, 3), t.float32); i = self._buf("mrg_i", (Q, 3), t.int32)
-            self.ctx.lib.liorf_sc_merge_top3_packed_dev(self.ctx.h, self._vp(g), world, Q, self._vp(d), self._vp(i))
-        return d, i
-
-    def distance_packed(self, q, cand):
-        t = self.torch
-        Q = q["Q"]
-        with t.cuda.stream(self.stream):
-            buf = self._buf("pair_packed", (9 * Q + (Q & 1),), t.int32)             # 24 Q bytes of f64 + 12 Q bytes of i32, 8-byte multiple
-            pd = buf[:6 * Q].view(t.float64); ps = buf[6 * Q:9 * Q]
-            pd.fill_(float("inf")); ps.zero_()
-            self.ctx.lib.liorf_sc_distance_batch_dev(self.ctx.h, self._vp(q["desc"]), self._vp(q["sk"]), self._vp(q["cn"]), self._vp(cand), Q, self.off,
-                                                     C.c_void_p(pd.data_ptr()), C.c_void_p(ps.data_ptr()))
-        return buf
-
-    def combine_packed(self, g, world):
-        t = self.torch
-        stride = g.shape[-1] * 4
-        Q = (g.shape[-1]) // 9
-        with t.cuda.stream(self.stream):
-            pd = self._buf("cmb_d", (Q, 3), t.float64); ps = self._buf("cmb_s", (Q, 3), t.int32)
-            self.ctx.lib.liorf_sc_combine_pairs_dev(self.ctx.h, self._vp(g), world, C.c_longlong(stride), Q, self._vp(pd), self._vp(ps))
-        return pd, ps
 
 
 class PeerShardedSearch:
-    """The same sharded search with the exchange done by the library's own kernels over NVLink PEER MEMORY
-    (csrc/sc_shard.cuh, liorf_sc_shard_*): every rank owns a window that all peers map, producers push and raise flags,
-    consumers spin on their own window.  One library call per batch, no collective launch, no host round trip.
-    torch.distributed is used once, to hand the 64-byte cudaIpc handles around."""
-
-    def __init__(self, ctx, rank, world, row_begin, q_max, torch):
-        """row_begin: world + 1 global row indices — rank g holds database rows [row_begin[g], row_begin[g + 1])"""
+    def __init__(self, ctx, rank, world, row_begin, q_max, torch, k_total_max=None):
+        """row_begin: world + 1 global row indices — rank g holds database rows [row_begin[g], row_begin[g + 1]).
+        k_total_max: capacity of the replicated ring-key index (None = row_begin[-1]; 0 = this context borrowed the database AND the
+        index of a synced context on the same device, see Context.scBorrowDatabase)."""
         self.ctx, self.rank, self.world, self.q_max, self.torch = ctx, rank, world, int(q_max), torch
         self.row_begin = [int(v) for v in row_begin]
         assert len(self.row_begin) == world + 1
         self.off = self.row_begin[rank]
+        self.k_cap = self.row_begin[-1] if k_total_max is None else int(k_total_max)
         self.dev = torch.device(f"cuda:{ctx.params.device}")
         self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.dev)
         self.handle = (C.c_ubyte * 64)()
         self.window = C.c_void_p()
-        rc = ctx.lib.liorf_sc_shard_init(ctx.h, C.c_int(rank), C.c_int(world), C.c_int(self.q_max), self.handle, C.byref(self.window))
+        rc = ctx.lib.liorf_sc_shard_init(ctx.h, C.c_int(rank), C.c_int(world), C.c_int(self.q_max), C.c_int(self.k_cap), self.handle, C.byref(self.window))
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_init failed with code {rc}")
         self._out = {}
 
+    def _rows(self):
+        return (C.c_int * (self.world + 1))(*self.row_begin)
+
     def connect_processes(self, dist):
-        """peers live in other processes (one per GPU): exchange the cudaIpc handles, map the windows"""
+        """peers live in other processes (one per GPU): exchange the cudaIpc handles, map the windows, replicate the ring keys"""
         if self.world > 1:
             hs = [None] * self.world
             dist.all_gather_object(hs, bytes(self.handle))
             buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(hs))
-            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, buf, None, (C.c_int * (self.world + 1))(*self.row_begin))
+            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, buf, None, self._rows())
         else:
-            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, self.handle, None, (C.c_int * (self.world + 1))(*self.row_begin))
+            rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, self.handle, None, self._rows())
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
         if self.world > 1:
+            dist.barrier()                                         # every window is mapped everywhere before anybody pushes into one
+            if self.k_cap > 0:
+                self.sync_keys()
             dist.barrier()
 
     def connect_local(self, searches):
-        """peers are other contexts of THIS process (tests: several shards on one GPU)"""
+        """peers are other contexts of THIS process (tests: several shards on one GPU); call sync_keys_local(searches) afterwards"""
         ptrs = (C.c_void_p * self.world)(*[s.window.value for s in searches])
-        rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, None, ptrs, (C.c_int * (self.world + 1))(*self.row_begin))
+        rc = self.ctx.lib.liorf_sc_shard_connect(self.ctx.h, None, ptrs, self._rows())
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_connect failed with code {rc}")
 
+    def sync_keys(self, phases=3):
+        rc = self.ctx.lib.liorf_sc_shard_sync_keys_phases(self.ctx.h, C.c_int(phases))
+        if rc < 0:
+            raise RuntimeError(f"liorf_sc_shard_sync_keys failed with code {rc}")
+
+    @staticmethod
+    def sync_keys_local(searches):
+        """ranks sharing one device: every push is enqueued before any wait"""
+        if searches[0].world == 1:
+            return
+        for s in searches:
+            s.sync_keys(1)
+        for s in searches:
+            s.sync_keys(2)
+
     def wait_stats(self):
-        """(ns waited for the peers per phase {T, C, D, K} since the last call, batch counter)"""
+        """(ns waited for the peers per phase {C, D, KEYS} since the last call, batch counter)"""
         w = (C.c_ulonglong * 4)(); b = C.c_uint(0)
         self.ctx.lib.liorf_sc_shard_wait_stats(self.ctx.h, w, C.byref(b))
-        return dict(T=w[0], C=w[1], D=w[2], K=w[3]), b.value
+        return dict(C=w[0], D=w[1], KEYS=w[2]), b.value
 
-    def query(self, d_q, phases=31):
+    def query(self, d_q, phases=7):
         """d_q: (Q, 1200) float64 query descriptors on this rank's device (the same on every rank).  Asynchronous on the context's
-        stream.  Returns (loop_id, shift, dist, cand) device tensors.  phases: bit mask of the batch's four steps (tests that put
-        several ranks on one device enqueue step by step over the ranks; a real rank passes 31)."""
+        stream.  Returns (loop_id, shift, dist, cand) device tensors.  phases: bit mask of the batch's three steps (tests that put
+        several ranks on one device enqueue step by step over the ranks; a real rank passes 7)."""
         t = self.torch
         Q = int(d_q.shape[0])
         o = self._out.get(Q)
@@ -261,7 +89,7 @@ class PeerShardedSearch:
                                 t.empty(Q, dtype=t.float64, device=self.dev), t.empty((Q, 3), dtype=t.int32, device=self.dev))
         args = (self.ctx.h, C.c_void_p(d_q.data_ptr()), C.c_int(Q), C.c_int(self.off), C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()),
                 C.c_void_p(o[2].data_ptr()), C.c_void_p(o[3].data_ptr()))
-        if phases == 31:
+        if phases == 7:
             rc = self.ctx.lib.liorf_sc_shard_query_dev(*args)           # the whole batch (a CUDA graph replay from the third identical request on)
         else:
             rc = self.ctx.lib.liorf_sc_shard_query_phases_dev(*args, C.c_int(phases))

@@ -105,56 +105,6 @@ def test_query_batch_uses_tensor_path_and_matches_oracle(oracle, synth):
     ctx.close()
 
 
-def test_sharded_packed_protocol_equals_unsharded(oracle, synth):
-    """the 2-rank packed protocol of liorf_b200/sc_sharded.py (one buffer per collective, library-side merge and owner pick),
-    emulated on one GPU with two contexts that each hold half of the database: the decisions must equal the unsharded
-    search and the oracle bit for bit."""
-    import torch
-    import liorf_b200
-    from liorf_b200.sc_sharded import GpuOps
-    K, Q = 9000, 333                                               # odd Q: exercises the 8-byte padding of the pair buffer
-    db = synth.sc_descriptors(K, seed=61)
-    qd, src, shift = synth.sc_queries(db, Q, seed=62)
-    ref = liorf_b200.Context()
-    ref.scAddDescriptors(db)
-    r_loop, r_sh, r_dist, r_cand = ref.scQueryBatch(qd)
-    ref.close()
-    half = K // 2
-    ctxs = [liorf_b200.Context(), liorf_b200.Context()]
-    ctxs[0].scAddDescriptors(db[:half]); ctxs[1].scAddDescriptors(db[half:])
-    for c in ctxs:
-        c.scSetSearchPath(2)
-    ops = [GpuOps(ctxs[0], 0, torch), GpuOps(ctxs[1], half, torch)]
-    dev = ops[0].dev
-
-    def sync():
-        for c in ctxs:
-            c.sync()
-        torch.cuda.synchronize()
-    qs = []
-    for o in ops:
-        with torch.cuda.stream(o.stream):
-            qs.append(o.prepare_dev(torch.from_numpy(qd).to(dev)))
-    sync()
-    bufs = [o.knn_packed(q) for o, q in zip(ops, qs)]; sync()
-    g = torch.stack(bufs).contiguous()                             # what all_gather_into_tensor produces on every rank
-    merged = [o.merge_packed(g, 2) for o in ops]; sync()
-    assert torch.equal(merged[0][1], merged[1][1])                 # identical global top-3 on both ranks
-    pbufs = [o.distance_packed(q, m[1]) for o, q, m in zip(ops, qs, merged)]; sync()
-    g2 = torch.stack(pbufs).contiguous()
-    outs = []
-    for o, m in zip(ops, merged):
-        pd, ps = o.combine_packed(g2, 2)
-        outs.append(o.decide(pd, ps, m[1]) + (m[1],))
-    sync()
-    for loop, sh, dd, cand in outs:
-        assert np.array_equal(cand.cpu().numpy(), r_cand)
-        assert np.array_equal(loop.cpu().numpy(), r_loop) and np.array_equal(sh.cpu().numpy(), r_sh)
-        assert np.array_equal(dd.cpu().numpy(), r_dist, equal_nan=True)
-    for c in ctxs:
-        c.close()
-
-
 @pytest.mark.parametrize("case", ["random_walk", "all_identical", "huge_heights", "two_clusters"])
 def test_tensor_filter_adversarial_databases(oracle, synth, case):
     """key distributions chosen to stress the filter's completeness argument: a drive-like random walk (neighbouring keys nearly

@@ -29,7 +29,7 @@ def main():
     with torch.cuda.stream(st):
         d_q = torch.from_numpy(qd).to(dev)
         keys = torch.empty((Q, 20), dtype=torch.float32, device=dev); sk = torch.empty((Q, 60), dtype=torch.float64, device=dev); cn = torch.empty_like(sk)
-        ctx.lib.liorf_sc_prepare_queries_dev(ctx.h, C.c_void_p(d_q.data_ptr()), Q, C.c_void_p(keys.data_ptr()), C.c_void_p(sk.data_ptr()), C.c_void_p(cn.data_ptr()))
+        ctx.lib.liorf_sc_prepare_queries_dev(ctx.h, C.c_void_p(d_q.data_ptr()), Q, C.c_void_p(keys.data_ptr()), None, None)
         d = torch.empty((Q, 3), dtype=torch.float32, device=dev); i = torch.empty((Q, 3), dtype=torch.int32, device=dev)
         pd = torch.empty((Q, 3), dtype=torch.float64, device=dev); ps = torch.empty((Q, 3), dtype=torch.int32, device=dev)
     out = {}
@@ -56,8 +56,7 @@ def main():
         with torch.cuda.stream(st):
             e0.record()
         for _ in range(reps):
-            ctx.lib.liorf_sc_distance_batch_dev(ctx.h, C.c_void_p(d_q.data_ptr()), C.c_void_p(sk.data_ptr()), C.c_void_p(cn.data_ptr()), C.c_void_p(i.data_ptr()), Q, 0,
-                                                C.c_void_p(pd.data_ptr()), C.c_void_p(ps.data_ptr()))
+            ctx.lib.liorf_sc_distance_batch_dev(ctx.h, C.c_void_p(d_q.data_ptr()), C.c_void_p(i.data_ptr()), Q, 0, C.c_void_p(pd.data_ptr()), C.c_void_p(ps.data_ptr()))
         with torch.cuda.stream(st):
             e1.record()
         ctx.sync()
@@ -65,7 +64,7 @@ def main():
     with torch.cuda.stream(st):
         e0.record()
     for _ in range(reps):
-        ctx.lib.liorf_sc_prepare_queries_dev(ctx.h, C.c_void_p(d_q.data_ptr()), Q, C.c_void_p(keys.data_ptr()), C.c_void_p(sk.data_ptr()), C.c_void_p(cn.data_ptr()))
+        ctx.lib.liorf_sc_prepare_queries_dev(ctx.h, C.c_void_p(d_q.data_ptr()), Q, C.c_void_p(keys.data_ptr()), None, None)
     with torch.cuda.stream(st):
         e1.record()
     ctx.sync()
