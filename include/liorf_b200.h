@@ -101,6 +101,10 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* ctx, const int* keyframe_ids,
 /* sets laserCloudSurfFromMapDS directly from a host cloud and builds the grid (parity tests / static maps) */
 int liorf_set_local_map(liorf_ctx* ctx, const liorf_point* map_ds, int m);
 int liorf_get_local_map(liorf_ctx* ctx, liorf_point* out, int capacity, int* m_ds);
+/* replaces kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (src/mapOptmization.cpp:1302): rebuilds the voxel-hash grid over the
+ * resident laserCloudSurfFromMapDS.  liorf_extract_surrounding_keyframes / liorf_set_local_map already do this once per map; the entry
+ * lets a caller (bench.py) repeat the step the reference repeats in every scan2MapOptimization call.  Asynchronous. */
+int liorf_kdtree_set_input_cloud(liorf_ctx* ctx);
 int liorf_get_scan_ds(liorf_ctx* ctx, liorf_point* out, int capacity, int* n_ds);
 
 /* keyframe SELECTION of extractNearby (src/mapOptmization.cpp:975-1010) over the context's key poses: radius search

@@ -237,6 +237,10 @@ class Context:
         _chk(self.lib.liorf_get_local_map(self.h, _vp(out), C.c_int(len(out)), C.byref(m)), "liorf_get_local_map")
         return out[:m.value].copy()
 
+    def kdtreeSetInputCloud(self):
+        """kdtreeSurfFromMap->setInputCloud (src/mapOptmization.cpp:1302): rebuild the voxel-hash grid over the resident local map (async)"""
+        _chk(self.lib.liorf_kdtree_set_input_cloud(self.h), "liorf_kdtree_set_input_cloud")
+
     def getScanDS(self):
         n = C.c_int(0)
         _chk(self.lib.liorf_get_scan_ds(self.h, None, C.c_int(0), C.byref(n)), "liorf_get_scan_ds")

@@ -484,6 +484,7 @@ int liorf_project_point_cloud_dev(liorf_ctx* c, const void* d_pts, int n, double
 }
 
 // ------------------------------------------------------------------------------------------------ mapOptimization
+static Count map_count(liorf_ctx* c);
 static int set_scan_common(liorf_ctx* c, const void* src, int n, cudaMemcpyKind kind) {
     int rc;
     if ((rc = c->scan.reserve(n > 0 ? n : 1))) return rc;
@@ -811,6 +812,18 @@ int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
     c->m_bound = m; c->h_m_ds = m; c->map_valid = false;
     if ((rc = build_map_grid(c->map_ds.p, Count::of_host(m), c->grid, c->stream))) return rc;
     return check_err(c);
+}
+/* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (src/mapOptmization.cpp:1302): the reference rebuilds its kd-tree at the top of
+ * every scan2MapOptimization call; here the voxel-hash grid is built together with the map (liorf_extract_surrounding_keyframes), so this
+ * entry only exists to time / repeat that step on the resident map: asynchronous on the context's stream. */
+int liorf_kdtree_set_input_cloud(liorf_ctx* c) {
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if ((rc = join_map(c))) return rc;
+    if (!c->map_ds.p || c->m_bound <= 0) return LIORF_ERR_STATE;
+    ProfScope ps(c, SEC_GRID_BUILD); c->launches += 3;
+    return build_map_grid(c->map_ds.p, map_count(c), c->grid, c->stream);
 }
 int liorf_get_local_map(liorf_ctx* c, liorf_point* out, int capacity, int* m_ds) {
     if (!c) return LIORF_ERR_ARG;
@@ -1155,16 +1168,16 @@ static int sc_distance_launch(liorf_ctx* c, const double* qd, const int* cand, i
     if (!c->scdb_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_sc_distance_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SCDB_SMEM));
         int occ = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sc_distance_bulk, SCDB_WARPS * 32, SCDB_SMEM));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sc_distance_bulk, SCDB_THREADS, SCDB_SMEM));
         c->scdb_blocks_per_sm = occ > 0 ? occ : 1; c->scdb_attr_set = true;
     }
-    int blocks = (pairs + SCDB_WARPS - 1) / SCDB_WARPS;
+    int blocks = (pairs + SCDB_TEAMS - 1) / SCDB_TEAMS;
     const int cap = c->num_sms * c->scdb_blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;                                   // a rank that owns no pair still raises its phase-D flag
     ShardPush P; std::memset(&P, 0, sizeof(P));
     if (push) P = *push;
-    k_sc_distance_bulk<<<blocks, SCDB_WARPS * 32, SCDB_SMEM, c->stream>>>(qd, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n,
+    k_sc_distance_bulk<<<blocks, SCDB_THREADS, SCDB_SMEM, c->stream>>>(qd, cand, pairs, SC_NUM_CAND, c->sc_desc.p, c->sc_sk.p, c->sc_cn.p, global_offset, c->sc_n,
                                                                           pd, ps, c->d_err, pair_list, n_list, P);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;

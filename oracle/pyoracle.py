@@ -16,7 +16,7 @@ PRAW = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("i", "<f4"), ("ring"
 
 def build(force=False):
     so = os.path.join(HERE, "libliorf_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cpp", "liorf_oracle.hpp", "ref_nanoflann.cpp", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cpp", "liorf_oracle.hpp", "ref_nanoflann.cpp", "ref_scancontext.cpp", "Makefile")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
     if stale:
         subprocess.run(["make", "-C", HERE, "-s"], check=True)
@@ -220,6 +220,22 @@ def sc_query_batch(keys, descs, qkeys, qdescs):
     return loop, shift, dist, cand
 
 
+def ref_sc_query_batch(keys, descs, qkeys, qdescs):
+    """the same batch with the reference's vendored nanoflann kd-tree as stage 1 (oracle/_ref); returns (loop, shift, dist, cand, (tree_s, query_s))"""
+    keys = np.ascontiguousarray(keys, np.float32).reshape(-1, 20); descs = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+    qkeys = np.ascontiguousarray(qkeys, np.float32).reshape(-1, 20); qdescs = np.ascontiguousarray(qdescs, np.float64).reshape(-1, 1200)
+    Q = len(qkeys)
+    loop = np.zeros(Q, np.int32); shift = np.zeros(Q, np.int32); dist = np.zeros(Q, np.float64); cand = np.zeros((Q, 3), np.int32); tm = np.zeros(2, np.float64)
+    ref().ref_sc_query_batch(_fp(keys), _fp(descs), C.c_int(len(keys)), _fp(qkeys), _fp(qdescs), C.c_int(Q), _fp(loop), _fp(shift), _fp(dist), _fp(cand), _fp(tm))
+    return loop, shift, dist, cand, (float(tm[0]), float(tm[1]))
+
+
+def sc_keys_batch(descs):
+    """ring keys (fp32) of many descriptors"""
+    descs = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+    return np.stack([sc_keys_from_desc(d)[0] for d in descs]) if len(descs) else np.zeros((0, 20), np.float32)
+
+
 class SCManager:
     def __init__(self):
         self.h = C.c_void_p(lib().orc_sc_create())
@@ -250,6 +266,70 @@ class SCManager:
         lid = C.c_int(); yaw = C.c_float(); md = C.c_double(); cand = np.zeros(3, np.int32)
         lib().orc_sc_detect(self.h, C.byref(lid), C.byref(yaw), C.byref(md), _fp(cand))
         return lid.value, yaw.value, md.value, cand
+
+
+_refsc = None
+
+
+def refsc():
+    """The reference's OWN include/Scancontext.cpp compiled unchanged against oracle/shim (oracle/_ref/libliorf_ref_sc.so); None if never built."""
+    global _refsc
+    if _refsc is None:
+        build()
+        p = os.path.join(HERE, "_ref", "libliorf_ref_sc.so")
+        if not os.path.exists(p):
+            return None
+        _refsc = C.CDLL(p)
+        _refsc.refsc_create.restype = C.c_void_p
+        _refsc.refsc_xy2theta.restype = C.c_float
+        _refsc.refsc_xy2theta.argtypes = [C.c_float, C.c_float]
+    return _refsc
+
+
+class RefSCManager:
+    """SCManager of the reference itself (include/Scancontext.h:61-118) — the pin of the oracle's restatement"""
+
+    def __init__(self):
+        self.h = C.c_void_p(refsc().refsc_create())
+
+    def __del__(self):
+        try:
+            refsc().refsc_destroy(self.h)
+        except Exception:
+            pass
+
+    def make(self, pts):
+        pts = _as_p4(pts)
+        desc = np.zeros(1200, np.float64); rk = np.zeros(20, np.float32); sk = np.zeros(60, np.float64)
+        refsc().refsc_make(self.h, _fp(pts), C.c_int(len(pts)), _fp(desc), _fp(rk), _fp(sk))
+        return desc.reshape(20, 60), rk, sk
+
+    def make_and_save(self, pts):
+        pts = _as_p4(pts)
+        refsc().refsc_make_and_save(self.h, _fp(pts), C.c_int(len(pts)))
+
+    def save_descriptor(self, desc):
+        desc = np.ascontiguousarray(desc, np.float64).reshape(-1)
+        refsc().refsc_save_descriptor(self.h, _fp(desc))
+
+    def size(self):
+        return refsc().refsc_size(self.h)
+
+    def get(self, i):
+        d = np.zeros(1200, np.float64); k = np.zeros(20, np.float32)
+        refsc().refsc_get(self.h, C.c_int(i), _fp(d), _fp(k))
+        return d.reshape(20, 60), k
+
+    def detect(self):
+        lid = C.c_int(); yaw = C.c_float()
+        refsc().refsc_detect(self.h, C.byref(lid), C.byref(yaw))
+        return lid.value, yaw.value
+
+    def distance(self, sc1, sc2):
+        sc1 = np.ascontiguousarray(sc1, np.float64).reshape(-1); sc2 = np.ascontiguousarray(sc2, np.float64).reshape(-1)
+        d = C.c_double(); s = C.c_int()
+        refsc().refsc_distance(self.h, _fp(sc1), _fp(sc2), C.byref(d), C.byref(s))
+        return d.value, s.value
 
 
 def cv_qr_solve6(A, b):

@@ -56,6 +56,36 @@ double ref_ringkey_tree_build_seconds(const float* keys, int ntree) {
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// CPU baseline of the batched ScanContext search (BASELINE config 5): the reference's own kd-tree (built once per call, as
+// detectLoopClosureID rebuilds it every TREE_MAKING_PERIOD_ calls, include/Scancontext.cpp:270-281) over all K ring keys, then per
+// query the :289-340 sequence — 3-NN, distanceBtnScanContext of the candidates in kNN order, strict <, threshold — with OpenMP over
+// the queries.  timings_s[2] = {tree build, queries}.
+void ref_sc_query_batch(const float* keys, const double* descs, int K, const float* qkeys, const double* qdescs, int Q,
+                        int* loop_id, int* shift, double* dist, int* cand3, double* timings_s) {
+    using clk = std::chrono::steady_clock;
+    auto T0 = clk::now();
+    KeyMat mat(K, std::vector<float>(20));
+    for (int k = 0; k < K; ++k) std::memcpy(mat[k].data(), keys + 20 * (size_t)k, 20 * sizeof(float));
+    InvKeyTree tree(20, mat, 10);
+    auto T1 = clk::now();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int q = 0; q < Q; ++q) {
+        std::vector<size_t> ci(3);
+        std::vector<float> cd(3);
+        nanoflann::KNNResultSet<float> rs(3);
+        rs.init(&ci[0], &cd[0]);
+        tree.index->findNeighbors(rs, qkeys + 20 * (size_t)q, nanoflann::SearchParams(10));
+        double mn = 10000000; int al = 0, nn = 0;
+        for (int c = 0; c < 3; ++c) {
+            auto r = distance_btn_scancontext(qdescs + 1200 * (size_t)q, descs + 1200 * ci[c]);
+            if (r.first < mn) { mn = r.first; al = r.second; nn = (int)ci[c]; }
+        }
+        loop_id[q] = mn < SC_DIST_THRES ? nn : -1; shift[q] = al; dist[q] = mn;
+        if (cand3) for (int c = 0; c < 3; ++c) cand3[3 * q + c] = (int)ci[c];
+    }
+    if (timings_s) { timings_s[0] = std::chrono::duration<double>(T1 - T0).count(); timings_s[1] = std::chrono::duration<double>(clk::now() - T1).count(); }
+}
+
 // 3-D kd-tree 5-NN (stand-in for pcl::KdTreeFLANN::nearestKSearch, src/mapOptmization.cpp:1087,1302)
 void ref_kdtree_knn5(const P4* map, int m, const P4* q, int n, int* idx, float* d2) {
     Cloud3 c{map, (size_t)m};

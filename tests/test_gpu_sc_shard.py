@@ -247,3 +247,8 @@ def test_two_ranks_two_lanes_borrowed_index(synth):
     for c in guests + owners:
         c.close()
     ref.close()
+
+
+def test_full_scale_100k_four_shards_vs_oracle(synth, oracle):
+    """BASELINE config 5 at its full database size, 4 ranks, tensor path, two batches: == oracle == unsharded, every query"""
+    _run(synth, 100000, [4096, 1500], 4, 0, oracle=oracle)
