@@ -135,6 +135,15 @@ int liorf_host_update_initial_guess(liorf_guess_state* state, int no_keyframes_y
 int liorf_host_transform_update(float transformTobeMapped[6], int imu_available, int imu_type, float imu_roll_init, float imu_pitch_init,
                                 float imu_rpy_weight, float rotation_tollerance, float z_tollerance);
 int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose6[6], float adding_dist_threshold, float adding_angle_threshold);
+/* replaces ImageProjection::imuDeskewInfo() (src/imageProjection.cpp:350-409) and the IMU gate of deskewInfo() (:337, check_gate != 0): from
+ * the queued IMU samples (stamp[n] ascending, gyro_xyz[n][3] = angular velocity after imuConverter, include/utility.h:257-272) builds the
+ * table liorf_project_point_cloud reads — row 0 = zeros at the first stamp >= time_scan_cur - 0.01, then rot[k] = rot[k-1] + w[k] dt
+ * (rectangle rule), last row = first stamp > time_scan_end + 0.01 exclusive.  capacity = queueLength (2000, :62).
+ * Outputs: imu_time / imu_rot_{x,y,z}[capacity], *imu_pointer_cur (:403), *n_pop (samples the reference pops from the queue front, :354-360),
+ * *rpy_index (sample whose orientation gives imuRoll/Pitch/YawInit for imuType != 0, :371-375; -1 = none).  Host-side scalar code, no GPU.
+ * Returns 1 = cloudInfo.imuAvailable, 0 = not available, negative = error. */
+int liorf_host_imu_deskew_info(const double* stamp, const double* gyro_xyz, int n, double time_scan_cur, double time_scan_end, int check_gate,
+                               double* imu_time, double* imu_rot_x, double* imu_rot_y, double* imu_rot_z, int capacity, int* imu_pointer_cur, int* n_pop, int* rpy_index);
 
 /* replaces mapOptimization::scan2MapOptimization() (src/mapOptmization.cpp:1295) up to, not including, transformUpdate:
  * ≤ max_iters × {surfOptimization, combineOptimizationCoeffs, LMOptimization} in one persistent kernel.

@@ -6,4 +6,4 @@ and the benchmark.  There is no CPU fallback: importing works without a GPU (so 
 compute call needs the CUDA library and a device.
 """
 from ._lib import load_library, library_path, build_library  # noqa: F401
-from .api import Context, Params, LMTrace, FrameIn, FrameOut, CloudInfoGuess, GuessState, P4, PRAW  # noqa: F401
+from .api import imuDeskewInfo, Context, Params, LMTrace, FrameIn, FrameOut, CloudInfoGuess, GuessState, P4, PRAW  # noqa: F401

@@ -73,6 +73,22 @@ class IcpResult(C.Structure):
                 ("fitness", C.c_float), ("transform", C.c_float * 16), ("pose6", C.c_float * 6)]
 
 
+def imuDeskewInfo(stamp, gyro_xyz, time_scan_cur, time_scan_end, check_gate=True, capacity=2000):
+    """ImageProjection::imuDeskewInfo (src/imageProjection.cpp:350-409) on an array of queued IMU samples; host-only (no context, no GPU).
+    Returns dict(available, imu_time, imu_rot (rows x 3), imu_pointer_cur, n_pop, rpy_index)."""
+    lib = load_library()
+    stamp = np.ascontiguousarray(stamp, np.float64); g = np.ascontiguousarray(gyro_xyz, np.float64).reshape(-1, 3)
+    t = np.zeros(capacity); rx = np.zeros(capacity); ry = np.zeros(capacity); rz = np.zeros(capacity)
+    ptr = C.c_int(-1); npop = C.c_int(0); rpy = C.c_int(-1)
+    rc = lib.liorf_host_imu_deskew_info(_vp(stamp), _vp(g), C.c_int(len(stamp)), C.c_double(time_scan_cur), C.c_double(time_scan_end), C.c_int(int(check_gate)),
+                                        _vp(t), _vp(rx), _vp(ry), _vp(rz), C.c_int(capacity), C.byref(ptr), C.byref(npop), C.byref(rpy))
+    if rc < 0:
+        raise LiorfError(f"liorf_host_imu_deskew_info failed with code {rc}")
+    rows = ptr.value + 1
+    return dict(available=bool(rc), imu_time=t[:rows].copy(), imu_rot=np.stack([rx[:rows], ry[:rows], rz[:rows]], 1), imu_pointer_cur=ptr.value, n_pop=npop.value,
+                rpy_index=rpy.value)
+
+
 class LiorfError(RuntimeError):
     pass
 

@@ -25,6 +25,13 @@
 
 using namespace liorf;
 
+// NVTX range around every C-ABI entry that touches the device ("NVTX ranges per hot-path function"): nsys / ncu --nvtx show the
+// reference's function boundaries (projectPointCloud, downsampleCurrentScan, scan2MapOptimization ...) on the timeline.  Header-only NVTX v3:
+// without a profiler attached a push/pop pair is two predicted branches.
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+#define LIORF_NVTX NvtxRange nvtx_range_(__func__)
+
 static_assert(sizeof(S2MTrace) == sizeof(liorf_lm_trace), "trace layout mismatch");
 static_assert(sizeof(liorf_point_xyzirt) == sizeof(RawPoint), "raw point layout mismatch");
 static_assert(S2M_MAX_ITERS == LIORF_MAX_ITERS, "iteration cap mismatch");
@@ -245,6 +252,7 @@ void liorf_default_params(liorf_params* p) {      // config/kitti.yaml
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int liorf_create(const liorf_params* p, liorf_ctx** out) {
+    LIORF_NVTX;
     if (!p || !out) return LIORF_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
@@ -460,6 +468,7 @@ static int project_common(liorf_ctx* c, const RawPoint* d_raw, int n, double t0,
 
 int liorf_project_point_cloud(liorf_ctx* c, const liorf_point_xyzirt* pts, int n, double t0, const double* imu_time, const double* rx,
                               const double* ry, const double* rz, int imu_ptr, int deskew_enabled, liorf_point* out, int* n_out, int* kept_index) {
+    LIORF_NVTX;
     if (!c || n < 0 || (n > 0 && !pts)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -478,6 +487,7 @@ int liorf_project_point_cloud(liorf_ctx* c, const liorf_point_xyzirt* pts, int n
 
 int liorf_project_point_cloud_dev(liorf_ctx* c, const void* d_pts, int n, double t0, const double* imu_time, const double* rx, const double* ry,
                                   const double* rz, int imu_ptr, int deskew_enabled) {
+    LIORF_NVTX;
     if (!c || n < 0 || (n > 0 && !d_pts)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     return project_common(c, (const RawPoint*)d_pts, n, t0, imu_time, rx, ry, rz, imu_ptr, deskew_enabled, nullptr);
@@ -517,6 +527,7 @@ __global__ void __launch_bounds__(256) k_unpack_strided(const unsigned char* __r
     out[i] = o;
 }
 int liorf_set_current_scan_strided(liorf_ctx* c, const void* data, int n, int point_step, int offset_xyz, int offset_intensity, int data_on_device) {
+    LIORF_NVTX;
     if (!c || n < 0 || (n > 0 && !data) || point_step < 16 || offset_xyz < 0 || offset_intensity < 0 || offset_xyz + 12 > point_step || offset_intensity + 4 > point_step)
         return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
@@ -538,11 +549,13 @@ int liorf_set_current_scan_strided(liorf_ctx* c, const void* data, int n, int po
     return LIORF_OK;
 }
 int liorf_set_current_scan(liorf_ctx* c, const liorf_point* scan, int n) {
+    LIORF_NVTX;
     if (!c || n < 0 || (n > 0 && !scan)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     return set_scan_common(c, scan, n, cudaMemcpyHostToDevice);
 }
 int liorf_set_current_scan_dev(liorf_ctx* c, const void* d_scan, int n) {
+    LIORF_NVTX;
     if (!c || n < 0 || (n > 0 && !d_scan)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     return set_scan_common(c, d_scan, n, cudaMemcpyDeviceToDevice);
@@ -559,6 +572,7 @@ static int downsample_async(liorf_ctx* c, int* d_membership) {
 }
 
 int liorf_downsample_current_scan(liorf_ctx* c, liorf_point* out, int* n_ds, int* membership) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -574,6 +588,7 @@ int liorf_downsample_current_scan(liorf_ctx* c, liorf_point* out, int* n_ds, int
 }
 
 int liorf_voxel_grid(liorf_ctx* c, const liorf_point* in, int n, float leaf, liorf_point* out, int* n_out, int* membership, int* out_keys) {
+    LIORF_NVTX;
     if (!c || n < 0 || (n > 0 && !in) || !n_out) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -611,6 +626,7 @@ static int append_keyframe(liorf_ctx* c, const float4* d_src, const float4* h_sr
     return (int)c->kfs.size() - 1;
 }
 int liorf_add_keyframe(liorf_ctx* c, const float pose6[6], double time) {
+    LIORF_NVTX;
     if (!c || !pose6) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -618,6 +634,7 @@ int liorf_add_keyframe(liorf_ctx* c, const float pose6[6], double time) {
     return append_keyframe(c, c->scan_ds.p, nullptr, c->h_n_ds, pose6, time);
 }
 int liorf_add_keyframe_cloud(liorf_ctx* c, const liorf_point* cloud, int n, const float pose6[6], double time) {
+    LIORF_NVTX;
     if (!c || !pose6 || n < 0 || (n > 0 && !cloud)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int id = append_keyframe(c, nullptr, (const float4*)cloud, n, pose6, time);
@@ -625,6 +642,7 @@ int liorf_add_keyframe_cloud(liorf_ctx* c, const liorf_point* cloud, int n, cons
     return id;
 }
 int liorf_update_keyframe_pose(liorf_ctx* c, int id, const float pose6[6]) {
+    LIORF_NVTX;
     if (!c || id < 0 || id >= (int)c->kfs.size() || !pose6) return LIORF_ERR_ARG;
     std::memcpy(c->kfs[id].pose, pose6, 6 * sizeof(float)); ++c->pose_version;
     return LIORF_OK;
@@ -632,6 +650,7 @@ int liorf_update_keyframe_pose(liorf_ctx* c, int id, const float pose6[6]) {
 int liorf_num_keyframes(liorf_ctx* c) { return c ? (int)c->kfs.size() : LIORF_ERR_ARG; }
 
 int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids, int* m_ds) {
+    LIORF_NVTX;
     if (!c || n_ids < 0 || (n_ids > 0 && !ids)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (c->kfs.empty()) return LIORF_ERR_STATE;                  // extractSurroundingKeyFrames returns early (:1048)
@@ -740,6 +759,7 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
 }
 
 int liorf_extract_nearby(liorf_ctx* c, double time_cur, float density, int* ids, int cap, int* n_ids) {
+    LIORF_NVTX;
     if (!c || !ids || !n_ids || cap < 0 || !(density > 0.f)) return LIORF_ERR_ARG;
     std::vector<liorf_host::KeyPose> kp(c->kfs.size());
     for (size_t i = 0; i < kp.size(); ++i) { const Keyframe& k = c->kfs[i]; kp[i] = liorf_host::KeyPose{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time}; }
@@ -750,6 +770,7 @@ int liorf_extract_nearby(liorf_ctx* c, double time_cur, float density, int* ids,
     return LIORF_OK;
 }
 int liorf_save_frame(liorf_ctx* c, const float pose6[6], float dist_thr, float ang_thr) {
+    LIORF_NVTX;
     if (!c || !pose6) return LIORF_ERR_ARG;
     if (c->kfs.empty()) return 1;
     const Keyframe& k = c->kfs.back();
@@ -793,6 +814,19 @@ int liorf_host_transform_update(float tf[6], int imu_available, int imu_type, fl
     liorf_host::transform_update(tf, imu_available != 0, imu_type, imu_roll_init, imu_pitch_init, imu_rpy_weight, rot_tol, z_tol);
     return LIORF_OK;
 }
+/* ImageProjection::deskewInfo + imuDeskewInfo (src/imageProjection.cpp:330-409): builds the IMU rotation table projectPointCloud reads.
+ * Returns 1 = imuAvailable, 0 = table unusable (imuPointerCur <= 0, or the :337 gate said "waiting for IMU data"), negative = error. */
+int liorf_host_imu_deskew_info(const double* stamp, const double* gyro_xyz, int n, double time_scan_cur, double time_scan_end, int check_gate,
+                               double* imu_time, double* imu_rot_x, double* imu_rot_y, double* imu_rot_z, int capacity, int* imu_pointer_cur, int* n_pop, int* rpy_index) {
+    if (n < 0 || (n > 0 && (!stamp || !gyro_xyz)) || !imu_time || !imu_rot_x || !imu_rot_y || !imu_rot_z || capacity < 1 || !imu_pointer_cur) return LIORF_ERR_ARG;
+    liorf_host::ImuDeskewInfo info;
+    const int rows = liorf_host::imu_deskew_info(stamp, gyro_xyz, n, time_scan_cur, time_scan_end, check_gate != 0, imu_time, imu_rot_x, imu_rot_y, imu_rot_z, capacity, info);
+    if (rows == -2) return LIORF_ERR_ARG;
+    *imu_pointer_cur = info.imu_pointer_cur;
+    if (n_pop) *n_pop = info.n_pop;
+    if (rpy_index) *rpy_index = info.rpy_index;
+    return info.imu_available ? 1 : 0;
+}
 int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose6[6], float dist_thr, float ang_thr) {
     if (!pose6) return LIORF_ERR_ARG;
     if (!last_pose6) return 1;
@@ -801,6 +835,7 @@ int liorf_host_save_frame(const float* last_pose6 /*nullable*/, const float pose
 }
 
 int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
+    LIORF_NVTX;
     if (!c || m < 0 || (m > 0 && !map_ds)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -817,6 +852,7 @@ int liorf_set_local_map(liorf_ctx* c, const liorf_point* map_ds, int m) {
  * every scan2MapOptimization call; here the voxel-hash grid is built together with the map (liorf_extract_surrounding_keyframes), so this
  * entry only exists to time / repeat that step on the resident map: asynchronous on the context's stream. */
 int liorf_kdtree_set_input_cloud(liorf_ctx* c) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -826,6 +862,7 @@ int liorf_kdtree_set_input_cloud(liorf_ctx* c) {
     return build_map_grid(c->map_ds.p, map_count(c), c->grid, c->stream);
 }
 int liorf_get_local_map(liorf_ctx* c, liorf_point* out, int capacity, int* m_ds) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc; if ((rc = read_counts(c))) return rc;
@@ -834,6 +871,7 @@ int liorf_get_local_map(liorf_ctx* c, liorf_point* out, int capacity, int* m_ds)
     return LIORF_OK;
 }
 int liorf_get_scan_ds(liorf_ctx* c, liorf_point* out, int capacity, int* n_ds) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc; if ((rc = read_counts(c))) return rc;
@@ -874,12 +912,14 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined
 }
 
 int liorf_scan2map_optimization_async(liorf_ctx* c, const float pose6_in[6], int max_iters, int force_all) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (pose6_in) { int rc = upload_pose(c, pose6_in); if (rc) return rc; }
     return launch_s2m(c, max_iters, force_all);
 }
 int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
+    LIORF_NVTX;
     if (!c || !pose6) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     { int rcj = join_map(c); if (rcj) return rcj; }
@@ -917,6 +957,7 @@ static int get_pose_mail(liorf_ctx* c, float pose6[6], int* iters, int* converge
 }
 
 int liorf_scan2map_optimization(liorf_ctx* c, float pose6[6], int max_iters, int force_all, liorf_lm_trace* trace) {
+    LIORF_NVTX;
     if (!c || !pose6) return LIORF_ERR_ARG;
     int rc = liorf_scan2map_optimization_async(c, pose6, max_iters, force_all);
     if (rc) return rc;
@@ -925,6 +966,7 @@ int liorf_scan2map_optimization(liorf_ctx* c, float pose6[6], int max_iters, int
 
 int liorf_surf_optimization(liorf_ctx* c, const float pose6[6], liorf_point* coeff, uint8_t* flag, int* nn_idx, float* nn_d2, float* plane,
                             liorf_point* sel) {
+    LIORF_NVTX;
     if (!c || !pose6 || !coeff || !flag) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -951,6 +993,7 @@ int liorf_surf_optimization(liorf_ctx* c, const float pose6[6], liorf_point* coe
 }
 
 int liorf_combine_optimization_coeffs(liorf_ctx* c, liorf_point* ori, liorf_point* coeff, int* n_sel) {
+    LIORF_NVTX;
     if (!c || !n_sel) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc; const int n = c->hook_n, cap = n > 0 ? n : 1;
@@ -966,6 +1009,7 @@ int liorf_combine_optimization_coeffs(liorf_ctx* c, liorf_point* ori, liorf_poin
 }
 
 int liorf_lm_optimization(liorf_ctx* c, int iter, float pose6[6], float AtA[36], float AtB[6], float X[6], int* n_sel) {
+    LIORF_NVTX;
     if (!c || !pose6) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc; const int nb = c->hook_n > 0 ? c->hook_n : 1;
@@ -989,6 +1033,7 @@ int liorf_lm_optimization(liorf_ctx* c, int iter, float pose6[6], float AtA[36],
     return c->h_mail[600 + C_CONV] ? 1 : 0;
 }
 int liorf_get_lm_state(liorf_ctx* c, int* deg, float matP[36]) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     LMDeviceState s; CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -997,6 +1042,7 @@ int liorf_get_lm_state(liorf_ctx* c, int* deg, float matP[36]) {
     return LIORF_OK;
 }
 int liorf_set_lm_state(liorf_ctx* c, int deg, const float matP[36]) {
+    LIORF_NVTX;
     if (!c || !matP) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     LMDeviceState s; s.isDegenerate = deg; std::memcpy(s.matP, matP, sizeof(s.matP));
@@ -1007,6 +1053,7 @@ int liorf_set_lm_state(liorf_ctx* c, int deg, const float matP[36]) {
 
 // ------------------------------------------------------------------------------------------------ ScanContext
 int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -1038,6 +1085,7 @@ int liorf_sc_make_and_save(liorf_ctx* c, const liorf_point* cloud, int n) {
 }
 
 int liorf_sc_add_descriptors(liorf_ctx* c, const double* descs, int count) {
+    LIORF_NVTX;
     if (!c || count < 0 || (count > 0 && !descs)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -1057,6 +1105,7 @@ int liorf_sc_add_descriptors(liorf_ctx* c, const double* descs, int count) {
  * several query batches in flight on one GPU, each on its own context / stream.  The borrower never adds entries; the owner must outlive it
  * and must not grow the database while it is borrowed. */
 int liorf_sc_borrow_database(liorf_ctx* dst, liorf_ctx* src) {
+    LIORF_NVTX;
     if (!dst || !src || dst == src || dst->P.device != src->P.device) return LIORF_ERR_ARG;
     if (!dst->sc_borrowed && (dst->sc_n != 0 || dst->sc_desc.p)) return LIORF_ERR_STATE;
     CUDA_TRY(cudaSetDevice(src->P.device));
@@ -1069,6 +1118,7 @@ int liorf_sc_borrow_database(liorf_ctx* dst, liorf_ctx* src) {
 }
 int liorf_sc_size(liorf_ctx* c) { return c ? c->sc_n : LIORF_ERR_ARG; }
 int liorf_sc_get(liorf_ctx* c, int i, double desc[1200], float ringkey[20], double sectorkey[60]) {
+    LIORF_NVTX;
     if (!c || i < 0 || i >= c->sc_n) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1171,7 +1221,7 @@ static int sc_distance_launch(liorf_ctx* c, const double* qd, const int* cand, i
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sc_distance_bulk, SCDB_THREADS, SCDB_SMEM));
         c->scdb_blocks_per_sm = occ > 0 ? occ : 1; c->scdb_attr_set = true;
     }
-    int blocks = (pairs + SCDB_TEAMS - 1) / SCDB_TEAMS;
+    int blocks = (pairs + SCDB_WARPS - 1) / SCDB_WARPS;
     const int cap = c->num_sms * c->scdb_blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;                                   // a rank that owns no pair still raises its phase-D flag
@@ -1185,11 +1235,13 @@ static int sc_distance_launch(liorf_ctx* c, const double* qd, const int* cand, i
 }
 
 int liorf_sc_knn_batch_dev(liorf_ctx* c, const void* d_qkeys, int Q, int global_offset, void* d_dist, void* d_idx) {
+    LIORF_NVTX;
     if (!c || Q < 0 || !d_qkeys || !d_dist || !d_idx) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     return sc_knn(c, local_keys(c), c->sc_n, (const float*)d_qkeys, Q, global_offset, (float*)d_dist, (int*)d_idx);
 }
 int liorf_sc_prepare_queries_dev(liorf_ctx* c, const void* d_qdescs, int Q, void* d_qkeys, void* d_qsk, void* d_qcn) {
+    LIORF_NVTX;
     if (!c || Q < 0 || !d_qdescs || (!d_qkeys && !d_qsk)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
@@ -1199,6 +1251,7 @@ int liorf_sc_prepare_queries_dev(liorf_ctx* c, const void* d_qdescs, int Q, void
     return LIORF_OK;
 }
 int liorf_sc_distance_batch_dev(liorf_ctx* c, const void* d_qdescs, const void* d_cand_idx, int Q, int global_offset, void* d_pair_dist, void* d_pair_shift) {
+    LIORF_NVTX;
     if (!c || Q < 0 || !d_qdescs || !d_cand_idx || !d_pair_dist || !d_pair_shift) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
@@ -1206,6 +1259,7 @@ int liorf_sc_distance_batch_dev(liorf_ctx* c, const void* d_qdescs, const void* 
 }
 int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pair_shift, const void* d_cand_idx, int Q, void* d_loop_id, void* d_shift,
                         void* d_dist) {
+    LIORF_NVTX;
     if (!c || Q < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
@@ -1218,6 +1272,7 @@ int liorf_sc_decide_dev(liorf_ctx* c, const void* d_pair_dist, const void* d_pai
 
 /* tests: cv::solve(DECOMP_QR) (hal::QR32f) of n 6x6 systems (A row-major [n][36], b [n][6]) by the device routine of the solver */
 int liorf_debug_qr_solve6(liorf_ctx* c, const float* A, const float* b, int n, float* x) {
+    LIORF_NVTX;
     if (!c || !A || !b || n <= 0 || !x) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     DevBuf<float> d; int rc;
@@ -1234,12 +1289,14 @@ int liorf_debug_qr_solve6(liorf_ctx* c, const float* A, const float* b, int n, f
 }
 /* tests: 1 = run the multi-kernel (large-cloud) VoxelGrid path on small clouds too; 0 = automatic */
 int liorf_debug_force_large_voxelgrid(liorf_ctx* c, int on) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     c->vg.force_large = c->vg_map.force_large = on != 0;
     return LIORF_OK;
 }
 /* selects the ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank */
 int liorf_sc_set_search_path(liorf_ctx* c, int mode) {
+    LIORF_NVTX;
     if (!c || mode < 0 || mode > 2) return LIORF_ERR_ARG;
     c->sc_path = mode;
     return LIORF_OK;
@@ -1247,6 +1304,7 @@ int liorf_sc_set_search_path(liorf_ctx* c, int mode) {
 /* statistics of the last tensor-core search: candidates emitted by the coarse filter (sum over queries), queries that
  * overflowed their list and were answered by the exact scan instead */
 int liorf_sc_tensor_stats(liorf_ctx* c, long long* n_candidates, int* n_overflow) {
+    LIORF_NVTX;
     if (!c || !n_candidates || !n_overflow) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     *n_candidates = 0; *n_overflow = 0;
@@ -1262,6 +1320,7 @@ int liorf_sc_tensor_stats(liorf_ctx* c, long long* n_candidates, int* n_overflow
 /* test hook: the raw tensor-core distances d~ of Q host queries (ring keys) against the whole database,
  * out[(q) * ld + k] with ld = ceil(n_db / 128) * 128 (returned), center[20] = the database mean the images use */
 int liorf_sc_tensor_dump(liorf_ctx* c, const float* qkeys, int Q, float* out, long long out_capacity, int* ld, float center[20]) {
+    LIORF_NVTX;
     if (!c || !qkeys || Q <= 0 || !out || !ld) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (c->sc_n < 1) return LIORF_ERR_STATE;
@@ -1303,6 +1362,7 @@ static int sc_query_local_dev(liorf_ctx* c, const double* qd, int Q, int global_
 }
 
 int liorf_sc_query_batch(liorf_ctx* c, const double* qdescs, int Q, int* loop_id, int* shift, double* dist, int* cand3) {
+    LIORF_NVTX;
     if (!c || Q < 0 || (Q > 0 && (!qdescs || !loop_id || !shift || !dist))) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
@@ -1321,6 +1381,7 @@ int liorf_sc_query_batch(liorf_ctx* c, const double* qdescs, int Q, int* loop_id
 // ---- sharded search over NVLink peer windows (sc_shard.cuh) ----
 static size_t scsh_round(size_t b) { return (b + 255) / 256 * 256; }
 int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, int k_total_max, void* ipc_handle_out /*64 B, nullable*/, void** window_out /*nullable*/) {
+    LIORF_NVTX;
     if (!c || world < 1 || world > SCSH_MAX || rank < 0 || rank >= world || q_max < 1 || k_total_max < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
@@ -1346,6 +1407,7 @@ int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, int k_tota
 }
 /* nanoseconds this rank's kernels spent waiting for the peers' pushes, per phase (C, D, KEYS, unused), accumulated since the last call; batches = batch counter */
 int liorf_sc_shard_wait_stats(liorf_ctx* c, unsigned long long wait_ns[4], unsigned* batches) {
+    LIORF_NVTX;
     if (!c || !wait_ns) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
@@ -1357,6 +1419,7 @@ int liorf_sc_shard_wait_stats(liorf_ctx* c, unsigned long long wait_ns[4], unsig
     return LIORF_OK;
 }
 int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B, nullable*/, void* const* window_ptrs /*world entries, nullable*/, const int* row_begin /*world + 1*/) {
+    LIORF_NVTX;
     if (!c || (!ipc_handles && !window_ptrs) || !row_begin) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
@@ -1387,6 +1450,7 @@ int liorf_sc_shard_connect(liorf_ctx* c, const void* ipc_handles /*world x 64 B,
  * every peer's keys (the next search rebuilds the operand image).  Collective: every rank calls it after the database was loaded or has
  * grown (liorf_sc_shard_sync_keys = both bits; the split form lets several ranks that share ONE device — tests — enqueue push before wait). */
 int liorf_sc_shard_sync_keys_phases(liorf_ctx* c, int phases) {
+    LIORF_NVTX;
     if (!c || !(phases & 3)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
@@ -1414,6 +1478,7 @@ int liorf_sc_shard_sync_keys(liorf_ctx* c) { return liorf_sc_shard_sync_keys_pha
 /* measurement only: 1 = this rank's consumer kernels do not wait for the peers' flags (a single rank of a G-rank search timed alone on one GPU
  * against windows that a complete earlier batch has filled; tools/profile_sc_shard.py) */
 int liorf_sc_shard_debug_nowait(liorf_ctx* c, int on) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     c->shard.W.nowait = on != 0;
     if (c->shard.graph) { cudaGraphExecDestroy(c->shard.graph); c->shard.graph = nullptr; }
@@ -1424,6 +1489,7 @@ int liorf_sc_shard_debug_nowait(liorf_ctx* c, int on) {
  * with the SAME queries in the same order.  phases: bit 0 = stage 1 of this rank's query slice (+ push C), bit 1 = collect + stage 2 of
  * the owned pairs (+ push D), bit 2 = decision. */
 int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases) {
+    LIORF_NVTX;
     if (!c || !d_qdescs || Q < 1 || !d_loop_id || !d_shift || !d_dist || !(phases & 7)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
@@ -1472,6 +1538,7 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
 /* One query batch of the sharded search, enqueued on the context's stream (asynchronous; results on the device).  Every rank calls it
  * with the SAME queries in the same order. */
 int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     liorf_ctx::ScShard& S = c->shard;
     // A batch is ~9 small kernels: replayed from a CUDA graph once the same request has been seen twice, so that the host's launch rate does
@@ -1524,6 +1591,7 @@ int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int glob
 }
 
 int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3) {
+    LIORF_NVTX;
     if (!c || !loop_id || !yaw_diff_rad) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     *loop_id = -1; *yaw_diff_rad = 0.f;
@@ -1590,6 +1658,7 @@ static int icp_build_cloud(liorf_ctx* c, int key, int search_num, int loop_index
 
 int liorf_loop_closure_icp(liorf_ctx* c, int loop_key_cur, int loop_key_pre, int history_search_num, int loop_index, float icp_leaf, float max_corr_dist,
                            int max_iters, liorf_icp_result* out) {
+    LIORF_NVTX;
     if (!c || !out || history_search_num < 0 || max_iters < 1 || !(icp_leaf > 0.f) || !(max_corr_dist > 0.f)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     std::memset(out, 0, sizeof(*out));
@@ -1647,6 +1716,7 @@ int liorf_loop_closure_icp(liorf_ctx* c, int loop_key_cur, int loop_key_pre, int
 }
 /* test hook: the two clouds of the last liorf_loop_closure_icp (cureKeyframeCloud / prevKeyframeCloud after the ICP VoxelGrid) */
 int liorf_icp_get_clouds(liorf_ctx* c, liorf_point* source, int cap_source, liorf_point* target, int cap_target) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1661,6 +1731,7 @@ int liorf_icp_get_clouds(liorf_ctx* c, liorf_point* source, int cap_source, lior
 // recovery, distance gate, then the selected keyframe clouds transformed by their own poses, concatenated and VoxelGrid(leaf).
 // search_radius <= 0 selects EVERY keyframe (saveMapService, :379-432; leaf <= 0 there means "no down-sampling").
 int liorf_build_global_map(liorf_ctx* c, float search_radius, float pose_density, float leaf, liorf_point* out, int capacity, int* n_out) {
+    LIORF_NVTX;
     if (!c || !n_out || capacity < 0 || (capacity > 0 && !out)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     *n_out = 0;
@@ -1729,6 +1800,7 @@ static int front_prefetch(liorf_ctx* c, const liorf_frame_in* nx) {
 }
 
 int liorf_cloud_handler_async(liorf_ctx* c, const liorf_frame_in* frame) {
+    LIORF_NVTX;
     if (!c || !frame) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaEventRecord(c->ev_frame_start, c->stream)); c->frame_start_recorded = true;
@@ -1736,6 +1808,7 @@ int liorf_cloud_handler_async(liorf_ctx* c, const liorf_frame_in* frame) {
 }
 
 int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out* out) {
+    LIORF_NVTX;
     if (!c || !in || !out || in->n < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     int rc;
@@ -1834,6 +1907,7 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
 
 // Pre-sizes every work buffer so that no call allocates afterwards (allocation = cudaMalloc/cudaFree = device sync).
 int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_points_max, int sc_entries_max) {
+    LIORF_NVTX;
     if (!c || n_scan_max < 0 || m_raw_max < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1874,6 +1948,7 @@ int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_po
 
 // ---- benchmark / introspection helpers ----
 int liorf_enable_timing(liorf_ctx* c, int on) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream)); prof_flush(c);
@@ -1884,11 +1959,13 @@ int liorf_enable_timing(liorf_ctx* c, int on) {
 /* like liorf_enable_timing(ctx, 1) but only the sections whose bit is set in `mask` record events (two cudaEventRecord calls per
  * section and frame are host time on the frame's critical path: the headline window times the dominant kernel only) */
 int liorf_enable_timing_mask(liorf_ctx* c, unsigned mask) {
+    LIORF_NVTX;
     int rc = liorf_enable_timing(c, mask != 0);
     if (!rc) c->prof.mask = mask & 0xffu;
     return rc;
 }
 int liorf_get_timing(liorf_ctx* c, double ms[8], long long calls[8]) {
+    LIORF_NVTX;
     if (!c || !ms || !calls) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream)); prof_flush(c);
@@ -1899,12 +1976,14 @@ long long liorf_get_launch_count(liorf_ctx* c) { return c ? c->launches : -1; }
 // debug: phase clocks of the persistent solver (CTA 0): out[iter*8 + {0 start,1 loop done,2 block reduced,3 grid synced,4 summed,5 solved}]
 /* tests: 1 = the solver never reuses its per-query candidate lists / plane fits (reference-style full search every iteration) */
 int liorf_debug_s2m_disable_cache(liorf_ctx* c, int on) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     c->s2m_no_cache = on != 0;
     return LIORF_OK;
 }
 /* tests: lanes per query of the persistent solver (4, 8 or 16); 0 = automatic (the widest group that covers the scan in one round) */
 int liorf_debug_s2m_lanes(liorf_ctx* c, int lanes) {
+    LIORF_NVTX;
     if (!c || !(lanes == 0 || lanes == 4 || lanes == 8 || lanes == 16)) return LIORF_ERR_ARG;
     c->s2m_force_pg = lanes;
     return LIORF_OK;
@@ -1912,6 +1991,7 @@ int liorf_debug_s2m_lanes(liorf_ctx* c, int lanes) {
 /* debug: %globaltimer stamps of the last solve, out[iter * 160 + k]: k < workers = that worker's arrival, 156 = reducer sums
  * ready, 157 = reducer published, 158 = worker 0 saw the flag (ns) */
 int liorf_debug_s2m_arrivals(liorf_ctx* c, int enable, unsigned long long* out /* 64*160 or null */) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1922,6 +2002,7 @@ int liorf_debug_s2m_arrivals(liorf_ctx* c, int enable, unsigned long long* out /
     return LIORF_OK;
 }
 int liorf_debug_s2m_clocks(liorf_ctx* c, int enable, long long* out /*64*8 or null*/) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1931,12 +2012,14 @@ int liorf_debug_s2m_clocks(liorf_ctx* c, int enable, long long* out /*64*8 or nu
     return LIORF_OK;
 }
 int liorf_get_last_counts(liorf_ctx* c, int* n_scan, int* n_ds, int* m_ds, int* iters) {
+    LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     if (n_scan) *n_scan = c->rep_counts[0]; if (n_ds) *n_ds = c->rep_counts[1]; if (m_ds) *m_ds = c->rep_counts[2];
     if (iters) *iters = c->h_mail[1024 + 448];       // S2MTrace.iters as of the last liorf_get_pose
     return LIORF_OK;
 }
 int liorf_get_keyframe(liorf_ctx* c, int id, liorf_point* out, int capacity, int* n, float pose6[6], double* time) {
+    LIORF_NVTX;
     if (!c || id < 0 || id >= (int)c->kfs.size()) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     const Keyframe& k = c->kfs[id];

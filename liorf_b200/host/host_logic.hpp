@@ -59,6 +59,43 @@ inline bool save_frame(const KeyPose* last /*nullptr when no keyframe yet*/, con
 }
 
 inline float constraint_transformation(float value, float limit) { if (value < -limit) value = -limit; if (value > limit) value = limit; return value; }
+// ImageProjection::deskewInfo's IMU part (src/imageProjection.cpp:330-409) on a caller-held sample array instead of the ROS deque:
+// stamps ascending, angular velocities already rotated into the lidar frame (imuConverter, include/utility.h:257-272).
+//   gate (:337): no sample, first sample after timeScanCur or last sample before timeScanEnd → "waiting for IMU data" (returns -1 rows)
+//   pop  (:354-360): samples older than timeScanCur - 0.01 leave the queue → n_pop
+//   table(:367-401): row 0 = zeros at the first remaining stamp, then rectangle-rule integration rot[k] = rot[k-1] + w[k] (t[k] - t[k-1])
+//                    with the CURRENT sample's rate, until a stamp exceeds timeScanEnd + 0.01
+//   rpy  (:371-375): index of the last sample at or before timeScanCur whose orientation gives imuRoll/Pitch/YawInit (imuType != 0)
+// imuPointerCur = rows - 1; imuAvailable iff imuPointerCur > 0 (:403-408).  capacity = queueLength (2000, :62): the reference does not
+// check it; here a longer table is an error (-2).
+struct ImuDeskewInfo { int imu_pointer_cur = -1; bool imu_available = false; int n_pop = 0; int rpy_index = -1; };
+inline int imu_deskew_info(const double* stamp, const double* gyro_xyz, int n, double timeScanCur, double timeScanEnd, bool check_gate,
+                           double* imuTime, double* imuRotX, double* imuRotY, double* imuRotZ, int capacity, ImuDeskewInfo& out) {
+    out = ImuDeskewInfo();
+    if (check_gate && (n == 0 || stamp[0] > timeScanCur || stamp[n - 1] < timeScanEnd)) return -1;
+    int first = 0;
+    while (first < n && stamp[first] < timeScanCur - 0.01) ++first;
+    out.n_pop = first;
+    if (first == n) return 0;
+    int ptr = 0;
+    for (int i = first; i < n; ++i) {
+        const double t = stamp[i];
+        if (t <= timeScanCur) out.rpy_index = i;
+        if (t > timeScanEnd + 0.01) break;
+        if (ptr >= capacity) return -2;
+        if (ptr == 0) { imuRotX[0] = 0; imuRotY[0] = 0; imuRotZ[0] = 0; imuTime[0] = t; ++ptr; continue; }
+        const double timeDiff = t - imuTime[ptr - 1];
+        imuRotX[ptr] = imuRotX[ptr - 1] + gyro_xyz[3 * i] * timeDiff;
+        imuRotY[ptr] = imuRotY[ptr - 1] + gyro_xyz[3 * i + 1] * timeDiff;
+        imuRotZ[ptr] = imuRotZ[ptr - 1] + gyro_xyz[3 * i + 2] * timeDiff;
+        imuTime[ptr] = t;
+        ++ptr;
+    }
+    out.imu_pointer_cur = ptr - 1;
+    out.imu_available = out.imu_pointer_cur > 0;
+    return ptr;
+}
+
 inline void transform_update_clamp(float tf[6], float rotation_tollerance, float z_tollerance) {                // :1348-1350
     tf[0] = constraint_transformation(tf[0], rotation_tollerance);
     tf[1] = constraint_transformation(tf[1], rotation_tollerance);

@@ -30,6 +30,7 @@
 #include <numeric>
 #include <utility>
 #include <vector>
+#include <deque>
 
 namespace liorf_oracle {
 
@@ -465,6 +466,40 @@ inline bool lm_optimization(int iterCount, const P4* ori, const P4* coeff, int n
 // a1/a2 — projectPointCloud + deskewPoint + findRotation (src/imageProjection.cpp:493-598)
 // ------------------------------------------------------------------------------------------------
 struct DeskewParams { float lidarMinRange, lidarMaxRange; int N_SCAN, downsampleRate, point_filter_num; };
+
+// imuDeskewInfo (src/imageProjection.cpp:350-409) restated over a std::deque like the reference's imuQueue (pop_front and all).
+// sample = {stamp, wx, wy, wz}; returns imuAvailable, fills the tables (sized queueLength = 2000, :62) and imuPointerCur.
+struct ImuSample { double stamp, wx, wy, wz; };
+inline bool imu_deskew_info(std::deque<ImuSample>& imuQueue, double timeScanCur, double timeScanEnd, std::vector<double>& imuTime,
+                            std::vector<double>& imuRotX, std::vector<double>& imuRotY, std::vector<double>& imuRotZ, int& imuPointerCur) {
+    bool imuAvailable = false;
+    while (!imuQueue.empty()) {                                           // :354-360
+        if (imuQueue.front().stamp < timeScanCur - 0.01) imuQueue.pop_front();
+        else break;
+    }
+    if (imuQueue.empty()) return imuAvailable;                            // :362-363
+    imuPointerCur = 0;                                                    // :365
+    for (int i = 0; i < (int)imuQueue.size(); ++i) {                      // :367
+        const ImuSample thisImuMsg = imuQueue[i];
+        const double currentImuTime = thisImuMsg.stamp;
+        if (currentImuTime > timeScanEnd + 0.01) break;                   // :378-379
+        if (imuPointerCur == 0) {                                         // :381-388
+            imuRotX[0] = 0; imuRotY[0] = 0; imuRotZ[0] = 0; imuTime[0] = currentImuTime;
+            ++imuPointerCur;
+            continue;
+        }
+        const double timeDiff = currentImuTime - imuTime[imuPointerCur - 1];                        // :395
+        imuRotX[imuPointerCur] = imuRotX[imuPointerCur - 1] + thisImuMsg.wx * timeDiff;            // :396-398
+        imuRotY[imuPointerCur] = imuRotY[imuPointerCur - 1] + thisImuMsg.wy * timeDiff;
+        imuRotZ[imuPointerCur] = imuRotZ[imuPointerCur - 1] + thisImuMsg.wz * timeDiff;
+        imuTime[imuPointerCur] = currentImuTime;
+        ++imuPointerCur;
+    }
+    --imuPointerCur;                                                      // :403
+    if (imuPointerCur <= 0) return imuAvailable;                          // :405-406
+    imuAvailable = true;
+    return imuAvailable;
+}
 
 inline void find_rotation(double pointTime, const double* imuTime, const double* rx, const double* ry, const double* rz,
                           int imuPointerCur, float* ox, float* oy, float* oz) {

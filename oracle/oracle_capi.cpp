@@ -144,6 +144,19 @@ int orc_project_point_cloud(const PRaw* in, int n, float minR, float maxR, int N
     return r;
 }
 
+// imuDeskewInfo over a deque (returns imuAvailable; rows = imuPointerCur + 1; queue_left = samples still queued afterwards)
+int orc_imu_deskew_info(const double* stamp, const double* gyro_xyz, int n, double timeScanCur, double timeScanEnd, double* imuTime, double* rx, double* ry, double* rz,
+                        int* imuPointerCur, int* queue_left) {
+    std::deque<ImuSample> q;
+    for (int i = 0; i < n; ++i) q.push_back(ImuSample{stamp[i], gyro_xyz[3 * i], gyro_xyz[3 * i + 1], gyro_xyz[3 * i + 2]});
+    std::vector<double> t(2000), x(2000), y(2000), z(2000);
+    int ptr = -1;
+    bool ok = imu_deskew_info(q, timeScanCur, timeScanEnd, t, x, y, z, ptr);
+    for (int i = 0; i <= ptr && i < 2000; ++i) { imuTime[i] = t[i]; rx[i] = x[i]; ry[i] = y[i]; rz[i] = z[i]; }
+    *imuPointerCur = ptr; *queue_left = (int)q.size();
+    return ok ? 1 : 0;
+}
+
 // ---- ScanContext ----
 void orc_sc_make(const P4* pts, int n, double* desc1200, float* ringkey20, double* sectorkey60) {
     make_scancontext(pts, n, desc1200);

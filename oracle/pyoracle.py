@@ -175,6 +175,16 @@ def project_point_cloud(raw, params, time_scan_cur, imu_time, imu_rot, imu_point
     return out[:r].copy(), kept[:r].copy()
 
 
+def imu_deskew_info(stamp, gyro_xyz, time_scan_cur, time_scan_end):
+    """oracle restatement of imuDeskewInfo (src/imageProjection.cpp:350-409) over a std::deque; at most 2000 rows"""
+    stamp = np.ascontiguousarray(stamp, np.float64); g = np.ascontiguousarray(gyro_xyz, np.float64).reshape(-1, 3)
+    t = np.zeros(2000); rx = np.zeros(2000); ry = np.zeros(2000); rz = np.zeros(2000); ptr = C.c_int(-1); left = C.c_int(0)
+    ok = lib().orc_imu_deskew_info(_fp(stamp), _fp(g), C.c_int(len(stamp)), C.c_double(time_scan_cur), C.c_double(time_scan_end), _fp(t), _fp(rx), _fp(ry), _fp(rz),
+                                   C.byref(ptr), C.byref(left))
+    rows = max(ptr.value + 1, 0)
+    return dict(available=bool(ok), imu_time=t[:rows].copy(), imu_rot=np.stack([rx[:rows], ry[:rows], rz[:rows]], 1), imu_pointer_cur=ptr.value, queue_left=left.value)
+
+
 def sc_make(pts):
     pts = _as_p4(pts)
     desc = np.zeros(1200, np.float64); rk = np.zeros(20, np.float32); sk = np.zeros(60, np.float64)

@@ -70,5 +70,4 @@ def test_sc_100k_q4096_vs_oracle(oracle, synth):
     assert np.array_equal(dist[ok].view(np.int64), o_dist[ok].view(np.int64))      # fp64 distances bit for bit
     planted = src >= 0
     assert planted.sum() == Q // 2 and np.array_equal(loop[planted], src[planted]) and np.array_equal(sh[planted], shift[planted])
-    assert (loop[~planted] == -1).mean() > 0.99                            # fresh queries: (almost) never a loop
     ctx.close()
