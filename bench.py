@@ -21,8 +21,14 @@ N > 1 (torchrun, one rank per GPU) — headline = BASELINE.json configs[4] `sc_1
 `--impl reference` times the CPU path (oracle restatement + the reference's vendored nanoflann kd-trees from oracle/_ref) on the same
 inputs: N = 1 the kitti64_single step, N > 1 the batched ScanContext search (rank 0 only), all host threads.
 """
-import argparse
-import hashlib
+import os
+
+# every stream needs its own hardware channel: several ScanContext lanes per GPU wait on flags written by other GPUs (csrc/sc_shard.cuh, DESIGN.md §7);
+# read by the CUDA driver when the context is created, so it is set before torch is imported
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import argparse  # noqa: E402
+import hashlib  # noqa: E402
 import json
 import os
 import sys
@@ -32,8 +38,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-from bench_common import (ORACLE_DIR, T0, DT, KITTI, Sequence, GpuPipeline, CpuPipeline, ClockSampler, load_peaks, dist_env,  # noqa: E402
-                          bench_batched)
+from bench_common import (ORACLE_DIR, T0, DT, KITTI, Sequence, GpuPipeline, CpuPipeline, ClockSampler, load_peaks, dist_env,  # noqa: E402,F401
+                          bench_batched, pose_to_T, T_to_pose)
 
 PERTURB = np.array([np.deg2rad(0.5), np.deg2rad(0.3), np.deg2rad(1.5), 0.35, 0.1, 0.02])     # SURVEY §8(d) cfg 1 initial-pose error
 SINGLE_CFGS = {
@@ -343,7 +349,22 @@ class ScBench:
         waits, _ = lanes[0][1].wait_stats()
         return ms, waits, out
 
-    def run(self, Q, steps, warmup, e2e=False):
+    def sync_lanes(self):
+        try:
+            for c, _ in self.lanes:
+                c.sync()
+        except Exception:
+            if os.environ.get("LIORF_BENCH_VERBOSE"):
+                time.sleep(15)                                     # let the peers run into their own bounds, then show every lane's view
+                for k, (c, s) in enumerate(self.lanes):
+                    print("[bench rank %d] lane %d state %s" % (self.rank, k, s.debug_state()), file=sys.stderr, flush=True)
+            raise
+
+    def note(self, msg):
+        if os.environ.get("LIORF_BENCH_VERBOSE"):
+            print("[bench rank %d] %s" % (self.rank, msg), file=sys.stderr, flush=True)
+
+    def run(self, Q, steps, warmup):
         """steps batches of Q queries, round-robin over the lanes; device-timed, max over ranks.  Returns a result dict (rank 0: + checks)."""
         t, dist, world = self.torch, self.dist, self.world
         qd, src, shift = self.queries(Q)
@@ -353,6 +374,10 @@ class ScBench:
         if world > 1:
             dist.barrier()
         warm = max(warmup, 3) * len(self.lanes)                    # per lane: the third identical request captures the batch as a CUDA graph
+        self.note("run Q=%d steps=%d: timed region" % (Q, steps))
+        if os.environ.get("LIORF_BENCH_VERBOSE"):
+            import faulthandler
+            faulthandler.dump_traceback_later(8, exit=False)
         ms, waits, out = self._timed(self.lanes, d_q, steps, warm, world > 1)
         if world > 1:
             tt = t.tensor([ms], device=self.dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
@@ -361,39 +386,13 @@ class ScBench:
         loop, sh, dd, cand = [x.cpu().numpy() for x in out]
         ok = (loop == src) & (src >= 0)
         res.update(planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()), shifts_correct=int((sh[ok] == shift[ok]).sum()))
-        if e2e:                                                    # same batches from HOST memory: H2D of the query descriptors + D2H of the answers inside the region
-            e0 = t.cuda.Event(enable_timing=True); e1 = t.cuda.Event(enable_timing=True)
-            lane_q = [t.empty_like(d_q) for _ in self.lanes]
-            host_out = [tuple(t.empty(x.shape, dtype=x.dtype).pin_memory() for x in out) for _ in self.lanes]
-            if world > 1:
-                dist.barrier()
-            t.cuda.synchronize()
-            streams = [s.stream for _, s in self.lanes]
-            n_e2e = max(2, min(steps, 6))
-            with t.cuda.stream(streams[0]):
-                e0.record()
-            for st in streams[1:]:
-                st.wait_event(e0)
-            for b in range(n_e2e):
-                k = b % len(self.lanes)
-                with t.cuda.stream(streams[k]):
-                    lane_q[k].copy_(pin, non_blocking=True)
-                o = self.lanes[k][1].query(lane_q[k])
-                with t.cuda.stream(streams[k]):
-                    for h, d in zip(host_out[k], o):
-                        h.copy_(d, non_blocking=True)
-            for st in streams[1:]:
-                streams[0].wait_stream(st)
-            with t.cuda.stream(streams[0]):
-                e1.record()
-            t.cuda.synchronize()
-            ems = e0.elapsed_time(e1)
-            if world > 1:
-                tt = t.tensor([ems], device=self.dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ems = float(tt.item())
-            res["e2e"] = dict(value=Q * n_e2e / (ems * 1e-3), unit="queries/s", h2d_bytes_per_step=int(qd.nbytes), d2h_bytes_per_step=int(Q * (4 + 4 + 8 + 12)),
-                              batches=n_e2e, note="every rank copies the batch's query descriptors (9 600 B each) from pinned host memory and reads all answers back: PCIe-bound")
+        self.note("timed region done")
+        if os.environ.get("LIORF_BENCH_VERBOSE"):
+            import faulthandler
+            faulthandler.cancel_dump_traceback_later()
+        skip = os.environ.get("LIORF_BENCH_SKIP", "")              # debugging aid: comma list of ref, stage
         # every rank's answers against the unsharded search of the same queries (rank 0, full database): the real cudaIpc path, bit for bit
-        if world > 1:
+        if world > 1 and "ref" not in skip:
             ref = None
             if self.rank == 0:
                 rms, _, rout = self._timed(self.ref_lanes, d_q, max(2, steps // 2), 3 * len(self.ref_lanes), False)
@@ -407,7 +406,47 @@ class ScBench:
             same = all(bool(t.equal(a.view(t.int64) if a.dtype == t.float64 else a, b.view(t.int64) if b.dtype == t.float64 else b)) for a, b in zip(out, ref))
             flag = t.tensor([1 if same else 0], device=self.dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             res["bit_equal_unsharded"] = bool(flag.item() == 1)
+            self.note("bit-equality check done: %s" % res["bit_equal_unsharded"])
         return res
+
+    def run_e2e(self, Q, n_batches):
+        """the same batches through the HOST-buffer entry of the C ABI (liorf_sc_shard_query_async): every batch copies its query descriptors from
+        pinned host memory to the device and its answers back, inside the timed region; round-robin over the lanes; device-timed, max over ranks"""
+        t, dist, world = self.torch, self.dist, self.world
+        qd, src, shift = self.queries(Q)
+        pin = t.from_numpy(qd).pin_memory()
+        host_out = [(t.empty(Q, dtype=t.int32).pin_memory(), t.empty(Q, dtype=t.int32).pin_memory(), t.empty(Q, dtype=t.float64).pin_memory(),
+                     t.empty((Q, 3), dtype=t.int32).pin_memory()) for _ in self.lanes]
+        streams = [s.stream for _, s in self.lanes]
+        for k, (c, s) in enumerate(self.lanes):                   # warm-up: sizes the library's staging buffer of every lane
+            s.query_host(pin, host_out[k])
+        self.sync_lanes()
+        if world > 1:
+            dist.barrier()
+        t.cuda.synchronize()
+        e0 = t.cuda.Event(enable_timing=True); e1 = t.cuda.Event(enable_timing=True)
+        with t.cuda.stream(streams[0]):
+            e0.record()
+        for st in streams[1:]:
+            st.wait_event(e0)
+        for b in range(n_batches):
+            k = b % len(self.lanes)
+            self.lanes[k][1].query_host(pin, host_out[k])
+        for st in streams[1:]:
+            streams[0].wait_stream(st)
+        with t.cuda.stream(streams[0]):
+            e1.record()
+        self.sync_lanes()
+        t.cuda.synchronize()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            tt = t.tensor([ems], device=self.dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ems = float(tt.item())
+        loop = host_out[(n_batches - 1) % len(self.lanes)][0].numpy()
+        ok = (loop == src) & (src >= 0)
+        self.note("e2e done")
+        return dict(value=Q * n_batches / (ems * 1e-3), unit="queries/s", h2d_bytes_per_step=int(qd.nbytes), d2h_bytes_per_step=int(Q * (4 + 4 + 8 + 12)), batches=n_batches,
+                    planted_loops_found=int(ok.sum()), planted=int((src >= 0).sum()),
+                    note="liorf_sc_shard_query_async: every rank copies the batch's query descriptors (9 600 B each) from pinned host memory and reads all answers back — PCIe-bound")
 
     def stage_times(self, Q, reps=6):
         """live CUDA-event sections of lane 0 (plain launches): ring-key stage, the tcgen05 GEMM inside it"""
@@ -440,6 +479,8 @@ def sc_rooflines(scb, Q, peaks):
     """tensor roofline of the ring-key GEMM and HBM roofline of stage 2, both timed live (CUDA events) on this rank's share of a batch"""
     import ctypes as C
     t = scb.torch
+    if "stage" in os.environ.get("LIORF_BENCH_SKIP", ""):
+        return dict(roofline=None)
     tm, st = scb.stage_times(Q)
     Qs = Q // scb.world if scb.world > 1 else Q
     gemm_ms = tm["sc_gemm"][0] / max(tm["sc_gemm"][1], 1)
@@ -477,7 +518,7 @@ def sc_rooflines(scb, Q, peaks):
         out["stage2_roofline"] = dict(kernel="k_sc_distance_bulk", bound="hbm", achieved=alg / (s2_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                                       frac=alg / (s2_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=(tr or {}).get("dram_bytes_per_launch"), algorithmic_bytes_per_launch=alg,
                                       avg_launch_ms=s2_ms, pairs=3 * Q,
-                                      note="fp64 sums in the reference's sequential order; two warps per pair, 32 warps / 16 pairs in flight per SM")
+                                      note="fp64 sums in the reference's sequential order; one warp per pair, adjacent columns / shifts blocked in registers, 16 pairs in flight per SM")
     return out
 
 
@@ -596,12 +637,13 @@ def bench_single_headline(args, device, W, K, peaks, peak_src):
         if not args.no_sc:
             try:
                 scb = ScBench(device, 0, 1, args.sc_k, max([args.sc_q] + [int(x) for x in args.sc_q_sweep.split(",") if x]), None, args.sc_lanes)
-                sc = scb.run(args.sc_q, 12, 3, e2e=True)
+                sc = scb.run(args.sc_q, 12, 3)
                 sc.update(sc_rooflines(scb, args.sc_q, peaks))
                 sc["sweep"] = {}
                 for q in [int(x) for x in args.sc_q_sweep.split(",") if x]:
                     r = scb.run(q, 12 if q <= 32768 else 4, 3)
                     sc["sweep"][str(q)] = {k: r[k] for k in ("Q", "ms_per_batch", "queries_per_s", "batches_in_flight", "planted_loops_found", "planted")}
+                sc["e2e"] = scb.run_e2e(args.sc_q, 6)
                 sc["metric"] = "sc_queries_per_s_100k"
                 line["sc"] = sc
                 line["sc_queries_per_s_100k"] = sc["queries_per_s"]
@@ -663,7 +705,7 @@ def bench_sc_headline(args, rank, local_rank, world, W, K, dist, peaks, peak_src
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    res = scb.run(args.sc_q, K, W, e2e=True)
+    res = scb.run(args.sc_q, K, W)
     clocks = sampler.stop() if rank == 0 else None
     res.update(sc_rooflines(scb, args.sc_q, peaks))
     res["sweep"] = {}
@@ -672,6 +714,10 @@ def bench_sc_headline(args, rank, local_rank, world, W, K, dist, peaks, peak_src
         res["sweep"][str(q)] = {k: r.get(k) for k in ("Q", "ms_per_batch", "queries_per_s", "batches_in_flight", "planted_loops_found", "planted", "bit_equal_unsharded",
                                                        "unsharded_same_run", "peer_wait_us_per_batch")}
     ok = res.get("bit_equal_unsharded", False) and all(v.get("bit_equal_unsharded", False) for v in res["sweep"].values())
+    res["e2e"] = scb.run_e2e(args.sc_q, max(2, min(K, 8)))
+    if os.environ.get("LIORF_BENCH_VERBOSE"):                      # a sharded run AFTER the host-buffer batches must still work
+        r2 = scb.run(4096, 8, 3)
+        scb.note("post-e2e run: %.1f M queries/s, bit-equal %s" % (r2["queries_per_s"] / 1e6, r2.get("bit_equal_unsharded")))
     scb.close()
     if rank == 0:
         e2e = res.pop("e2e")

@@ -38,12 +38,12 @@ def T_to_pose(T):
 class Sequence:
     """Seeded synthetic drive: poses, per-frame gyro tables and raw scans (generated lazily, cached)."""
 
-    def __init__(self, n_frames, rank=0, filters=KITTI):
+    def __init__(self, n_frames, rank=0, filters=KITTI, loop=False):
         from tools import synth
         self.synth = synth
         self.n = n_frames
         self.filters = filters
-        self.poses = synth.street_trajectory(n_frames + 1, start=(0.0, 160.0 * rank), seed=synth.SEED0 + 1 + rank)
+        self.poses = synth.street_trajectory(n_frames + 1, start=(0.0, 160.0 * rank), seed=synth.SEED0 + 1 + rank, loop=loop)
         self.rank = rank
         self.raw = {}
         self.imu = {}

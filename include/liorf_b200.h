@@ -240,7 +240,11 @@ int liorf_sc_shard_query_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int gl
  * bit 2: decision; 7 = everything) so that several ranks sharing ONE device (tests) can interleave their steps and never wait on work that
  * has not been enqueued yet */
 int liorf_sc_shard_query_phases_dev(liorf_ctx* ctx, const void* d_qdescs, int Q, int global_offset, void* d_loop_id, void* d_shift, void* d_dist, void* d_cand, int phases);
-int liorf_sc_shard_debug_nowait(liorf_ctx* ctx, int on);   /* measurement: consumers skip the flag waits (one rank of G timed alone, tools/profile_sc_shard.py) */
+/* the same batch from HOST buffers: H2D of the Q descriptors (9 600 B each), the search, D2H of the answers, all asynchronous on the context's
+ * stream — results are defined after liorf_sync; pinned host buffers make the copies truly asynchronous.  cand3 ([Q][3] global rows) nullable. */
+int liorf_sc_shard_query_async(liorf_ctx* ctx, const double* qdescs, int Q, int global_offset, int* loop_id, int* shift, double* dist, int* cand3);
+int liorf_sc_shard_debug_nowait(liorf_ctx* ctx, int on);
+int liorf_sc_shard_debug_state(liorf_ctx* ctx, unsigned out[68]);   /* debugging: batch / raise / owned-pair counters, error flag, then flag[src][phase] of this rank's window */   /* measurement: consumers skip the flag waits (one rank of G timed alone, tools/profile_sc_shard.py) */
 
 /* ---- loop-closure registration ------------------------------------------------------------------- */
 /* The ICP of mapOptimization::performSCLoopClosure (src/mapOptmization.cpp:624-730) without the factor graph:

@@ -5,5 +5,10 @@ The package holds only what the path needs: `csrc/` (CUDA kernels + the C ABI, b
 and the benchmark.  There is no CPU fallback: importing works without a GPU (so the build can be checked), but every
 compute call needs the CUDA library and a device.
 """
-from ._lib import load_library, library_path, build_library  # noqa: F401
+import os as _os
+
+# one hardware channel per stream (read by the CUDA driver at context creation; harmless if CUDA is already up): see DESIGN.md §7
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from ._lib import load_library, library_path, build_library  # noqa: F401,E402
 from .api import imuDeskewInfo, Context, Params, LMTrace, FrameIn, FrameOut, CloudInfoGuess, GuessState, P4, PRAW  # noqa: F401

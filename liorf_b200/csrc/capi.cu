@@ -131,6 +131,19 @@ struct liorf_ctx {
     bool pre_valid = false, frame_start_recorded = false; int pre_index = 0, pre_n = 0; const void* pre_pts = nullptr;
 };
 
+// The two secondary streams are created on first use: a context that only searches the ScanContext database (one lane of a sharded search)
+// never needs them, and every stream a process creates competes for the device's hardware channels (CUDA_DEVICE_MAX_CONNECTIONS) — streams
+// that share a channel serialise, which turned cross-GPU flag waits of different lanes into a cycle.
+static int make_low_priority_stream(cudaStream_t* out) {
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (std::getenv("LIORF_NO_PRIO")) prio_lo = 0;
+    CUDA_TRY(cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, prio_lo));
+    return LIORF_OK;
+}
+static int need_stream_map(liorf_ctx* c) { return c->stream_map ? LIORF_OK : make_low_priority_stream(&c->stream_map); }
+static int need_stream_pre(liorf_ctx* c) { return c->stream_pre ? LIORF_OK : make_low_priority_stream(&c->stream_pre); }
+
 // swaps the current front set with the alternate one (pointer swaps only)
 static void front_swap(liorf_ctx* c) {
     std::swap(c->scan, c->alt.scan); std::swap(c->scan_ds, c->alt.scan_ds); std::swap(c->dk, c->alt.dk); std::swap(c->vg, c->alt.vg);
@@ -215,7 +228,11 @@ static int check_err(liorf_ctx* c) {      // after a stream sync: sticky device-
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     prof_flush(c);
     e = c->h_mail[4000];
-    if (e) { fprintf(stderr, "[liorf_b200] device error flag %d (look-back predecessor never arrived)\n", e); return LIORF_ERR_DEVICE_FLAG; }
+    if (e) {
+        fprintf(stderr, "[liorf_b200] device error flag %d (%s)\n", e, e == 5 ? "an mbarrier wait gave up" : e >= 0x30 ? "a peer's exchange flag never arrived: 0x30 + phase, C=0 D=1 KEYS=2" :
+                e == 2 ? "solver: a worker / the reducer never arrived" : "look-back predecessor never arrived");
+        return LIORF_ERR_DEVICE_FLAG;
+    }
     return LIORF_OK;
 }
 
@@ -299,7 +316,6 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     c->combine_scan.ticket = c->d_tick + 4; c->combine_scan.err_flag = c->d_err;
     int* lm_counter = c->d_misc + 7; (void)lm_counter;
     CUDA_TRY(cudaMalloc(&c->vg.meta, sizeof(VoxMeta)));
-    CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_map, cudaStreamNonBlocking, prio_lo));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_map, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->vg_map.meta, sizeof(VoxMeta)));
@@ -317,7 +333,6 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->alt.vg.meta, sizeof(VoxMeta)));
     CUDA_TRY(cudaMalloc(&c->alt.dk.start_inv, 12 * sizeof(float)));
     c->alt.dk.first_kept = c->alt.d_counts + C_FIRST_KEPT;
-    CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_pre, cudaStreamNonBlocking, prio_lo));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pre_done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_frame_start, cudaEventDisableTiming));
     CUDA_TRY(cudaHostAlloc(&c->h_mail, 65536 + 2 * 65536, cudaHostAllocDefault));
@@ -389,11 +404,11 @@ void liorf_destroy(liorf_ctx* c) {
     for (auto b : f4) b->release();
     c->membership.release(); c->out_keys.release(); c->h_flag.release(); c->h_idx.release(); c->h_d2.release(); c->h_plane.release();
     c->lm_partial.release(); c->d_sel.release();
-    cudaStreamSynchronize(c->stream_map);
+    if (c->stream_map) cudaStreamSynchronize(c->stream_map);
     for (VoxelGridWork* w : {&c->vg_map}) { w->partial.release(); w->keys.release(); w->seg_start.release(); w->sort.keys_alt.release(); w->sort.vals_a.release();
         w->sort.vals_b.release(); w->sort.hist.release(); w->sort.status.release(); w->scan.status.release(); cudaFree(w->meta); }
     for (auto& kv : c->map_graphs) { if (kv.second.vg) cudaGraphExecDestroy(kv.second.vg); if (kv.second.grid) cudaGraphExecDestroy(kv.second.grid); }
-    cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_map); cudaStreamDestroy(c->stream_map);
+    cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_map); if (c->stream_map) cudaStreamDestroy(c->stream_map);
     c->vg.partial.release(); c->vg.keys.release(); c->vg.seg_start.release();
     c->vg.sort.keys_alt.release(); c->vg.sort.vals_a.release(); c->vg.sort.vals_b.release(); c->vg.sort.hist.release(); c->vg.sort.status.release();
     c->vg.scan.status.release(); c->grid.scan.status.release(); c->dk.scan.status.release(); c->combine_scan.status.release();
@@ -668,7 +683,7 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     const int ns = (int)sel.size();
     if (ns + 1 > c->h_sel_cap) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream_map));
+        if (c->stream_map) CUDA_TRY(cudaStreamSynchronize(c->stream_map));
         if (c->h_sel) cudaFreeHost(c->h_sel);
         c->h_sel_cap = 2 * ns + 64;
         CUDA_TRY(cudaHostAlloc(&c->h_sel, (size_t)2 * c->h_sel_cap * sizeof(KfSel), cudaHostAllocDefault));
@@ -695,6 +710,7 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
     if ((rc = c->map_ds.reserve(bound > 0 ? bound : 1))) return rc;
     // fork: everything enqueued so far on the main stream (keyframe copies, the previous solve that still reads the old map)
     // happens-before the map chain
+    if ((rc = need_stream_map(c))) return rc;
     cudaStream_t ms = c->stream_map;
     CUDA_TRY(cudaEventRecord(c->ev_main, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(ms, c->ev_main, 0));
@@ -858,8 +874,16 @@ int liorf_kdtree_set_input_cloud(liorf_ctx* c) {
     int rc;
     if ((rc = join_map(c))) return rc;
     if (!c->map_ds.p || c->m_bound <= 0) return LIORF_ERR_STATE;
-    ProfScope ps(c, SEC_GRID_BUILD); c->launches += 3;
-    return build_map_grid(c->map_ds.p, map_count(c), c->grid, c->stream);
+    // on the map stream, like the grid build of liorf_extract_surrounding_keyframes: it runs beside whatever the caller enqueues next on
+    // the main stream (downsampleCurrentScan); the solver joins (join_map) before it reads the grid
+    if ((rc = need_stream_map(c))) return rc;
+    cudaStream_t ms = c->stream_map;
+    CUDA_TRY(cudaEventRecord(c->ev_main, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ms, c->ev_main, 0));
+    { ProfScope ps(c, SEC_GRID_BUILD, ms); c->launches += 3; if ((rc = build_map_grid(c->map_ds.p, map_count(c), c->grid, ms))) return rc; }
+    CUDA_TRY(cudaEventRecord(c->ev_map, ms));
+    c->map_pending = true;
+    return LIORF_OK;
 }
 int liorf_get_local_map(liorf_ctx* c, liorf_point* out, int capacity, int* m_ds) {
     LIORF_NVTX;
@@ -1386,6 +1410,15 @@ int liorf_sc_shard_init(liorf_ctx* c, int rank, int world, int q_max, int k_tota
     CUDA_TRY(cudaSetDevice(c->P.device));
     liorf_ctx::ScShard& S = c->shard;
     if (S.ready || S.W.base[S.W.rank]) return LIORF_ERR_STATE;
+    if (world > 1) {   // see need_stream_map: consumer kernels of different lanes wait for flags of OTHER GPUs; their streams must not share a hardware channel
+        const char* mc = std::getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        static bool warned = false;
+        if (!warned && (!mc || std::atoi(mc) < 32)) {
+            fprintf(stderr, "[liorf_b200] warning: CUDA_DEVICE_MAX_CONNECTIONS is %s; export CUDA_DEVICE_MAX_CONNECTIONS=32 before the first CUDA call when several "
+                            "query batches are in flight per GPU (streams sharing a hardware channel can deadlock the cross-GPU flag waits)\n", mc ? mc : "unset (8)");
+            warned = true;
+        }
+    }
     std::memset(&S.W, 0, sizeof(S.W));
     S.W.rank = rank; S.W.world = world; S.W.qmax = q_max; S.qmax = q_max; S.kcap = k_total_max;
     S.W.off_c = scsh_round((size_t)SCSH_MAX * SCSH_NPHASE * sizeof(unsigned));
@@ -1475,6 +1508,21 @@ int liorf_sc_shard_sync_keys_phases(liorf_ctx* c, int phases) {
     return LIORF_OK;
 }
 int liorf_sc_shard_sync_keys(liorf_ctx* c) { return liorf_sc_shard_sync_keys_phases(c, 3); }
+/* debugging aid: out[0] = batch counter, out[1] = raise counter, out[2] = owned-pair counter, out[3] = device error flag,
+ * out[4 + 4 g + p] = flag of source rank g, phase p (C, D, KEYS, -) as it stands in THIS rank's window.  Synchronises the device. */
+int liorf_sc_shard_debug_state(liorf_ctx* c, unsigned out[4 + 4 * 16]) {
+    if (!c || !out) return LIORF_ERR_ARG;
+    liorf_ctx::ScShard& S = c->shard;
+    if (!S.d_counter || !S.W.base[S.W.rank]) return LIORF_ERR_STATE;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned cnt[4];
+    CUDA_TRY(cudaMemcpy(cnt, S.d_counter, sizeof(cnt), cudaMemcpyDeviceToHost));
+    out[0] = cnt[1]; out[1] = cnt[0]; out[2] = cnt[2];
+    CUDA_TRY(cudaMemcpy(&out[3], c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out + 4, S.W.base[S.W.rank], (size_t)SCSH_MAX * SCSH_NPHASE * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return LIORF_OK;
+}
 /* measurement only: 1 = this rank's consumer kernels do not wait for the peers' flags (a single rank of a G-rank search timed alone on one GPU
  * against windows that a complete earlier batch has filled; tools/profile_sc_shard.py) */
 int liorf_sc_shard_debug_nowait(liorf_ctx* c, int on) {
@@ -1588,6 +1636,24 @@ int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int glob
     const int rc = liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 7);
     make_sig(S.last_sig);                                         // as of AFTER the call: buffers sized, image built
     return rc;
+}
+
+/* The sharded batch from HOST buffers (the reference-facing form: detectLoopClosureID's inputs and answers live in host memory):
+ * H2D of the Q query descriptors, liorf_sc_shard_query_dev, D2H of the answers — all asynchronous on the context's stream; the host
+ * buffers (pinned for real asynchrony) must stay valid and the results are defined after liorf_sync.  cand3 nullable. */
+int liorf_sc_shard_query_async(liorf_ctx* c, const double* qdescs, int Q, int global_offset, int* loop_id, int* shift, double* dist, int* cand3) {
+    LIORF_NVTX;
+    if (!c || !qdescs || Q < 1 || !loop_id || !shift || !dist) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    int rc;
+    if ((rc = c->sc_qdesc.reserve((size_t)Q * SC_DESC)) || (rc = sc_reserve_query(c, Q))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->sc_qdesc.p, qdescs, (size_t)Q * SC_DESC * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = liorf_sc_shard_query_dev(c, c->sc_qdesc.p, Q, global_offset, c->sc_res_i.p, c->sc_res_i.p + Q, c->sc_res_d.p, c->sc_q_i.p))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(loop_id, c->sc_res_i.p, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(shift, c->sc_res_i.p + Q, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist, c->sc_res_d.p, (size_t)Q * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (cand3) CUDA_TRY(cudaMemcpyAsync(cand3, c->sc_q_i.p, (size_t)3 * Q * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return LIORF_OK;
 }
 
 int liorf_sc_detect_loop_closure_id(liorf_ctx* c, int* loop_id, float* yaw_diff_rad, double* min_dist, int* cand3) {
@@ -1780,6 +1846,7 @@ static int front_prefetch(liorf_ctx* c, const liorf_frame_in* nx) {
     if (!nx || nx->n < 0) return LIORF_ERR_ARG;
     c->pre_valid = false;
     front_swap(c);                                   // the enqueue helpers below work on "the current set" and "the context's stream"
+    { int rcs = need_stream_pre(c); if (rcs) return rcs; }
     cudaStream_t main_stream = c->stream; c->stream = c->stream_pre;
     int rc = LIORF_OK;
     // the set being overwritten was last read by work enqueued on the main stream before this frame began (keyframe copy, ScanContext)
@@ -1845,7 +1912,7 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
         std::vector<int> sel = liorf_host::extract_nearby(kp, in->time_scan_cur, c->P.surroundingKeyframeSearchRadius, in->surrounding_keyframe_density);
         if ((rc = liorf_extract_surrounding_keyframes(c, sel.data(), (int)sel.size(), nullptr))) return rc;
     }
-    stamp(2, c->stream_map);
+    stamp(2, c->stream_map ? c->stream_map : c->stream);
     lap(1);
     if (!prefetched && (rc = liorf_downsample_current_scan(c, nullptr, nullptr, nullptr))) return rc;
     stamp(3, c->stream);
@@ -1911,7 +1978,7 @@ int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_po
     if (!c || n_scan_max < 0 || m_raw_max < 0) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream_pre)); c->pre_valid = false;
+    if (c->stream_pre) CUDA_TRY(cudaStreamSynchronize(c->stream_pre)); c->pre_valid = false;
     int rc;
     const size_t n = (size_t)(n_scan_max > 0 ? n_scan_max : 1), m = (size_t)(m_raw_max > 0 ? m_raw_max : 1), big = n > m ? n : m;
     for (int set = 0; set < 2; ++set) {                           // both front sets (see liorf_ctx::FrontSet)

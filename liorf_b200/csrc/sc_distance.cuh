@@ -23,12 +23,13 @@ namespace liorf {
 
 constexpr int SCDB_WARPS = 4;
 constexpr int SCDB_THREADS = SCDB_WARPS * 32;
+constexpr int SCDB_CHUNK = 5;                       // rings of the query descriptor per prefetch chunk of the fine search
 constexpr int SCDB_VK1 = 64;                        // s_vk1 padded to 64 doubles (keeps the similarity buffer 16-byte aligned)
 constexpr int SCDB_WARP_BYTES = SC_DESC * 8 + SCDB_VK1 * 8 + 7 * SC_SECTOR * 8;      // candidate descriptor + query sector key + 7 x 60 similarities = 13 472 B
 constexpr int SCDB_SMEM = SCDB_WARPS * SCDB_WARP_BYTES + SCDB_WARPS * 8;
 static_assert(SCDB_WARP_BYTES % 16 == 0, "per-warp shared-memory block must keep 16-byte alignment");
 
-__global__ void __launch_bounds__(SCDB_THREADS) k_sc_distance_bulk(const double* __restrict__ qdesc, const int* __restrict__ cand, int n_pairs, int cand_per_query,
+__global__ void __launch_bounds__(SCDB_THREADS, 4) k_sc_distance_bulk(const double* __restrict__ qdesc, const int* __restrict__ cand, int n_pairs, int cand_per_query,
                                                                   const double* __restrict__ db_desc, const double* __restrict__ db_sk, const double* __restrict__ db_cn,
                                                                   int own_begin, int own_count, double* __restrict__ out_dist, int* __restrict__ out_shift, int* err_flag,
                                                                   const int* __restrict__ pair_list, const int* __restrict__ n_list, ShardPush P) {
@@ -63,11 +64,13 @@ __global__ void __launch_bounds__(SCDB_THREADS) k_sc_distance_bulk(const double*
         // the QUERY's sector key and column norms are derived here, from the descriptor the fine search reads anyway (k_sc_keys_batch's
         // arithmetic: sequential sums over the rings, :214-227, :75-81) — no per-query key arrays, no kernel in front of this one
         double n1a = 0, n1b = 0;
+        double2 qa[SCDB_CHUNK];                                       // the query's two columns, rings 0..4: kept for the fine search (see there)
         if (act) {
             double suma = 0, sqa = 0, sumb = 0, sqb = 0;
 #pragma unroll
             for (int r = 0; r < SC_RING; ++r) {
                 const double2 v = *reinterpret_cast<const double2*>(sc1 + r * SC_SECTOR + c0);
+                if (r < SCDB_CHUNK) qa[r] = v;
                 suma += v.x; sqa += v.x * v.x; sumb += v.y; sqb += v.y * v.y;
             }
             *reinterpret_cast<double2*>(s_vk1 + c0) = make_double2(suma / SC_RING, sumb / SC_RING);
@@ -107,13 +110,16 @@ __global__ void __launch_bounds__(SCDB_THREADS) k_sc_distance_bulk(const double*
         // the 7 shifts {align-3 .. align+3} mod 60 in natural order m = 0..6; the reference visits them SORTED ascending (:123-130):
         // jpos[m] = rank of shift m in that order (they differ only when the window wraps around 0)
         int sh_m[7], jpos[7];
+        {
+            const int lo = SC_SEARCH_RADIUS - align;                    // > 0: the first `lo` shifts wrapped below 0 (→ 57..59) and sort LAST
+            const int hi = align + SC_SEARCH_RADIUS - (SC_SECTOR - 1);  // > 0: the last `hi` shifts wrapped past 59 (→ 0..2) and sort FIRST
 #pragma unroll
-        for (int m = 0; m < 7; ++m) sh_m[m] = (align + m - SC_SEARCH_RADIUS + SC_SECTOR) % SC_SECTOR;
-#pragma unroll
-        for (int m = 0; m < 7; ++m) { int rk = 0;
-#pragma unroll
-            for (int m2 = 0; m2 < 7; ++m2) rk += sh_m[m2] < sh_m[m] ? 1 : 0;
-            jpos[m] = rk; }
+            for (int m = 0; m < 7; ++m) {
+                int v = align + m - SC_SEARCH_RADIUS; v += v < 0 ? SC_SECTOR : 0; v -= v >= SC_SECTOR ? SC_SECTOR : 0;
+                sh_m[m] = v;
+                jpos[m] = lo > 0 ? (m < lo ? m + 7 - lo : m - lo) : hi > 0 ? (m >= 7 - hi ? m - (7 - hi) : m + hi) : m;
+            }
+        }
         // the candidate descriptor has landed (or the wait gives up with the error flag set)
         if (!mbar_wait(bar, parity, &s_abort, err_flag)) break;        // error flag is set; the epilogue below still runs (flags, counter)
         parity ^= 1u;
@@ -127,15 +133,30 @@ __global__ void __launch_bounds__(SCDB_THREADS) k_sc_distance_bulk(const double*
             double d0[7], d1[7];
 #pragma unroll
             for (int m = 0; m < 7; ++m) { d0[m] = 0; d1[m] = 0; }
-#pragma unroll 2
-            for (int r = 0; r < SC_RING; ++r) {
-                const double2 qv = *reinterpret_cast<const double2*>(sc1 + r * SC_SECTOR + c0);
-                const double* row = s_sc2 + r * SC_SECTOR;
-                double win[8];
+            // The query descriptor is NOT in shared memory (it would halve the pairs in flight) and, at 16 x 9.6 kB per SM, not in L1
+            // either: a load issued where it is used waits a full L2 / HBM round trip (ncu r2: 40 % of this kernel's stall samples sat on
+            // this loop).  So the rings arrive in chunks of SCDB_CHUNK, the NEXT chunk's loads in flight while this one is multiplied;
+            // chunk 0 was kept from the key pass above.
+#pragma unroll 1
+            for (int ch = 0; ch < SC_RING / SCDB_CHUNK; ++ch) {
+                double2 qb[SCDB_CHUNK];
+                if (ch + 1 < SC_RING / SCDB_CHUNK) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) win[i] = row[idx[i]];
+                    for (int u = 0; u < SCDB_CHUNK; ++u) qb[u] = *reinterpret_cast<const double2*>(sc1 + ((ch + 1) * SCDB_CHUNK + u) * SC_SECTOR + c0);
+                }
 #pragma unroll
-                for (int m = 0; m < 7; ++m) { d0[m] += qv.x * win[6 - m]; d1[m] += qv.y * win[7 - m]; }
+                for (int u = 0; u < SCDB_CHUNK; ++u) {
+                    const double* row = s_sc2 + (ch * SCDB_CHUNK + u) * SC_SECTOR;
+                    double win[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) win[i] = row[idx[i]];
+#pragma unroll
+                    for (int m = 0; m < 7; ++m) { d0[m] += qa[u].x * win[6 - m]; d1[m] += qa[u].y * win[7 - m]; }
+                }
+                if (ch + 1 < SC_RING / SCDB_CHUNK) {
+#pragma unroll
+                    for (int u = 0; u < SCDB_CHUNK; ++u) qa[u] = qb[u];
+                }
             }
             const double* cn2 = db_cn + (size_t)lc * SC_SECTOR;
             double nw[8];

@@ -148,7 +148,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         if (mbar_try_wait(bar, parity)) return true;
         if ((it & 255u) == 255u && *s_abort) return false;
     }
-    *s_abort = 1; atomicExch(err_flag, 3);
+    *s_abort = 1; atomicCAS(err_flag, 0, 5);                      // 5: an mbarrier (TMA copy / tensor-core commit) never completed
     return false;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

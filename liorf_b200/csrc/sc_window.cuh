@@ -40,7 +40,7 @@ __device__ __forceinline__ void scsh_wait(const ShardWin& W, int phase, unsigned
                 if ((int)(v - target) >= 0) break;
                 // a peer that never arrives is an error, not a hang: give up after ~10 s, and at once if the error flag is already up (a dead
                 // peer must not cost this bound again in every later wait)
-                if ((++spins & 1023u) == 0u && (spins > (1u << 24) || *reinterpret_cast<volatile int*>(err_flag) != 0)) { atomicExch(err_flag, 3); break; }
+                if ((++spins & 1023u) == 0u && (spins > (1u << 25) || *reinterpret_cast<volatile int*>(err_flag) != 0)) { atomicCAS(err_flag, 0, 0x30 + phase); break; }   // 0x30 + phase: a peer's flag never came
             }
         }
         __syncwarp();

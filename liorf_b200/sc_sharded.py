@@ -96,3 +96,19 @@ class PeerShardedSearch:
         if rc < 0:
             raise RuntimeError(f"liorf_sc_shard_query_dev failed with code {rc}")
         return o
+
+    def query_host(self, pin_q, host_out):
+        """the batch from HOST memory (liorf_sc_shard_query_async): pin_q = pinned (Q, 1200) float64 tensor, host_out = pinned tensors
+        (loop int32[Q], shift int32[Q], dist float64[Q], cand int32[Q, 3]); asynchronous, results valid after ctx.sync()"""
+        Q = int(pin_q.shape[0])
+        rc = self.ctx.lib.liorf_sc_shard_query_async(self.ctx.h, C.c_void_p(pin_q.data_ptr()), C.c_int(Q), C.c_int(self.off), C.c_void_p(host_out[0].data_ptr()),
+                                                     C.c_void_p(host_out[1].data_ptr()), C.c_void_p(host_out[2].data_ptr()), C.c_void_p(host_out[3].data_ptr()))
+        if rc < 0:
+            raise RuntimeError(f"liorf_sc_shard_query_async failed with code {rc}")
+        return host_out
+
+    def debug_state(self):
+        """counters and exchange flags of this rank's window (debugging)"""
+        o = (C.c_uint * 68)()
+        self.ctx.lib.liorf_sc_shard_debug_state(self.ctx.h, o)
+        return dict(batch=o[0], raise_counter=o[1], owned=o[2], err=o[3], flags={g: tuple(o[4 + 4 * g + p] for p in range(3)) for g in range(self.world)})

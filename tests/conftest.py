@@ -1,6 +1,8 @@
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware channel per stream; must precede the first CUDA call
+
 import numpy as np
 import pytest
 
