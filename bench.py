@@ -724,7 +724,7 @@ def bench_sc_headline(args, rank, local_rank, world, W, K, dist, peaks, peak_src
         line = dict(metric="sc_queries_per_s_100k", value=res["queries_per_s"], unit="queries/s", n_gpus=world, steps=K, warmup=W, ms_per_step=res["ms_per_batch"],
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32 ring keys (bf16 split filter + exact re-rank), f64 descriptors", data="synthetic",
                     config=sc_config(args),
-                    e2e=e2e, gpu_launches=9 * K, sc=res, roofline=res["roofline"], clocks=clocks,
+                    e2e=e2e, gpu_launches=11 * K, sc=res, roofline=res["roofline"], clocks=clocks,
                     note="N > 1 measures the one workload of the path that shards (SURVEY §8e); the N = 1 line's headline is kitti64_single and carries the same search on "
                          "one GPU, same batches in flight, as `sc` / `sc_queries_per_s_100k`; `sc.unsharded_same_run` is that figure measured in THIS run on rank 0")
         print(json.dumps(line))

@@ -1572,13 +1572,15 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
         }
     }
     if (phases & 2) {        // every slice has arrived → local copy + the pairs this rank owns → distanceBtnScanContext on exactly those, pushed by the warps that compute them
+        k_scsh_wait_phase<<<1, 32, 0, c->stream>>>(S.W, SCSH_C, S.d_batch, c->d_err);
         k_scsh_collect<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, Q, c->sc_q_d.p, cand, c->d_err, global_offset, c->sc_n, S.list.p, S.d_nlist);
-        c->launches += 1;
+        c->launches += 2;
         if ((rc = sc_distance_launch(c, qd, cand, 3 * Q, global_offset, nullptr, nullptr, S.list.p, S.d_nlist, &P))) return rc;
     }
     if (phases & 4) {        // decision (+ re-arms the owned-pair counter)
+        k_scsh_wait_phase<<<1, 32, 0, c->stream>>>(S.W, SCSH_D, S.d_batch, c->d_err);
         k_scsh_decide<<<(Q + 127) / 128, 128, 0, c->stream>>>(S.W, S.d_batch, cand, Q, (int*)d_loop_id, (int*)d_shift, (double*)d_dist, c->d_err, S.d_nlist);
-        c->launches += 1;
+        c->launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
     return LIORF_OK;
@@ -1608,7 +1610,7 @@ int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int glob
     if (S.graph && std::memcmp(sig, S.gsig, sizeof(sig)) == 0) {
         CUDA_TRY(cudaSetDevice(c->P.device));
         CUDA_TRY(cudaGraphLaunch(S.graph, c->stream));
-        c->launches += 9;
+        c->launches += 11;
         return LIORF_OK;
     }
     if (std::memcmp(sig, S.last_sig, sizeof(sig)) == 0) {        // second identical request: every buffer is sized and the operand image is current → capture
@@ -1630,7 +1632,7 @@ int liorf_sc_shard_query_dev(liorf_ctx* c, const void* d_qdescs, int Q, int glob
         cudaGraphDestroy(g);
         std::memcpy(S.gsig, sig, sizeof(sig));
         CUDA_TRY(cudaGraphLaunch(S.graph, c->stream));
-        c->launches += 9;
+        c->launches += 11;
         return LIORF_OK;
     }
     const int rc = liorf_sc_shard_query_phases_dev(c, d_qdescs, Q, global_offset, d_loop_id, d_shift, d_dist, d_cand, 7);

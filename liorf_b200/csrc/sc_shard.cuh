@@ -39,6 +39,13 @@ __global__ void __launch_bounds__(256) k_scsh_push_keys(ShardWin W, const float*
     scsh_raise(W, SCSH_KEYS, gen, counter);
 }
 __global__ void k_scsh_wait_keys(ShardWin W, unsigned gen, int* err_flag) { scsh_wait(W, SCSH_KEYS, gen, err_flag); }
+// The consumer side of a phase is ONE WARP: a <<<1, 32>>> kernel in front of the kernel that reads the exchanged data.  Waiting inside the
+// consumer kernels themselves (every CTA of k_scsh_collect / k_scsh_decide spinning) was how round 1 and the first version of this file did
+// it — and with several query batches in flight per GPU the spinning CTAs of the lanes that wait (256 CTAs x 128 threads and their registers
+// per lane at Q = 32 768) can leave no SM with room for the 320-thread / 213 kB tensor-core CTAs or the stage-2 CTAs of the lane whose push
+// the OTHER GPUs are waiting for: a cross-GPU resource cycle, observed as soon as host copies skewed the lanes (bench --gpus 2 / 8, r2).
+// One warp per waiting lane cannot starve anything.
+__global__ void k_scsh_wait_phase(ShardWin W, int phase, const unsigned* __restrict__ batch, int* err_flag) { scsh_wait(W, phase, *batch, err_flag); }
 
 // phase C producer of the CUDA-core search path (the tensor-core path pushes from its re-rank kernel): the exact global top-3 of this
 // rank's query slice, n_q rows starting at query q0, into the candidate array of every window
@@ -53,11 +60,10 @@ __global__ void __launch_bounds__(256) k_scsh_push_c(ShardWin W, const float* __
     scsh_raise(W, SCSH_C, *batch_p, counter);
 }
 
-// phase C consumer: every slice of the candidate array in this window is complete → local copy (the window is overwritten by the
+// phase C consumer (runs behind k_scsh_wait_phase(C)): every slice of the candidate array in this window is complete → local copy (the window is overwritten by the
 // next batch) + the compact list of the pairs whose candidate THIS rank owns (order irrelevant: stage-2 results are keyed by the pair id)
 __global__ void __launch_bounds__(128) k_scsh_collect(ShardWin W, const unsigned* __restrict__ batch, int Q, float* __restrict__ out_d, int* __restrict__ out_i, int* err_flag,
                                                      int own_begin, int own_count, int* __restrict__ list, int* __restrict__ n_list) {
-    scsh_wait(W, SCSH_C, *batch, err_flag);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     int ci[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
     if (q < Q) {
@@ -80,11 +86,10 @@ __global__ void __launch_bounds__(128) k_scsh_collect(ShardWin W, const unsigned
     for (int j = 0; j < 3; ++j) if (own[j]) list[base++] = 3 * q + j;
 }
 
-// phase D consumer: entry [pair] of the pair array was written by the rank that owns the candidate's row; then the decision of
+// phase D consumer (runs behind k_scsh_wait_phase(D)): entry [pair] of the pair array was written by the rank that owns the candidate's row; then the decision of
 // detectLoopClosureID (:302-340): candidates in kNN order, strict <, threshold.  Re-arms the owned-pair counter for the next batch.
 __global__ void __launch_bounds__(128) k_scsh_decide(ShardWin W, const unsigned* __restrict__ batch, const int* __restrict__ cand, int Q, int* __restrict__ loop_id, int* __restrict__ shift,
                                                     double* __restrict__ dist, int* err_flag, int* __restrict__ n_list) {
-    scsh_wait(W, SCSH_D, *batch, err_flag);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q == 0) *n_list = 0;
     if (q >= Q) return;
