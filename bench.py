@@ -488,7 +488,8 @@ def sc_rooflines(scb, Q, peaks):
     tflops = 2.0 * 64 * kpad * qpad / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     out = dict(ringkey_stage_ms=tm["sc_search"][0] / max(tm["sc_search"][1], 1), candidates_per_query=st["candidates"] / max(Qs, 1) * 32, overflow_queries=st["overflow"],
                roofline=dict(kernel="k_sc_tensor", bound="tensor", achieved=tflops, peak=peaks.get("bf16_tflops"), unit="TFLOP/s",
-                             frac=(tflops / peaks["bf16_tflops"]) if tflops and peaks.get("bf16_tflops") else None, traffic=None, avg_launch_ms=gemm_ms,
+                             frac=(tflops / peaks["bf16_tflops"]) if tflops and peaks.get("bf16_tflops") else None,
+                             traffic=(traffic_entry("sc_tensor.k%dk_q%d" % (scb.K // 1000, Qs)) or {}).get("dram_bytes_per_launch"), avg_launch_ms=gemm_ms,
                              queries_per_launch=Qs, keys=scb.K,
                              note="executed tensor-core flops: 2 x 64 (split-bf16 contraction) x Kpad x Qpad per launch; the distance itself is 3 x 20 flops per pair"))
     if scb.world == 1:
@@ -514,7 +515,7 @@ def sc_rooflines(scb, Q, peaks):
         ctx.sync()
         s2_ms = s0.elapsed_time(s1) / 5
         alg = 3 * Q * (9600 + 9600 / 3 + 2 * 480)                # candidate descriptor + a third of the query's + the candidate's sector key and column norms
-        tr = traffic_entry("sc_distance_bulk.Q%d" % Q)
+        tr = traffic_entry("sc_distance_bulk.k%dk_q%d" % (scb.K // 1000, Q))
         out["stage2_roofline"] = dict(kernel="k_sc_distance_bulk", bound="hbm", achieved=alg / (s2_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                                       frac=alg / (s2_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=(tr or {}).get("dram_bytes_per_launch"), algorithmic_bytes_per_launch=alg,
                                       avg_launch_ms=s2_ms, pairs=3 * Q,
@@ -532,7 +533,7 @@ def main():
     ap.add_argument("--sc-k", type=int, default=100000)
     ap.add_argument("--sc-q", type=int, default=32768, help="queries per batch of the ScanContext workload (the N > 1 headline)")
     ap.add_argument("--sc-q-sweep", default="4096,131072", help="further batch sizes reported as extras (empty = none)")
-    ap.add_argument("--sc-lanes", type=int, default=4, help="ScanContext query batches in flight per GPU — the SAME at every N")
+    ap.add_argument("--sc-lanes", type=int, default=6, help="ScanContext query batches in flight per GPU — the SAME at every N")
     ap.add_argument("--no-sc", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: headline only (no rows / sequence / sc extras)")
     ap.add_argument("--seq-frames", type=int, default=60, help="timed frames of the kitti05_seq extra (0 = skip)")

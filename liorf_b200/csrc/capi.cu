@@ -1245,8 +1245,13 @@ static int sc_distance_launch(liorf_ctx* c, const double* qd, const int* cand, i
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sc_distance_bulk, SCDB_THREADS, SCDB_SMEM));
         c->scdb_blocks_per_sm = occ > 0 ? occ : 1; c->scdb_attr_set = true;
     }
-    int blocks = (pairs + SCDB_WARPS - 1) / SCDB_WARPS;
+    // persistent warps, one pair at a time each: the fewest CTAs that still finish in the same number of rounds (a sharded rank owns
+    // about pairs / world of the pairs: 5.2 rounds of the full grid are 6 rounds either way, and the CTAs not launched leave their
+    // shared memory to the other lanes' kernels)
     const int cap = c->num_sms * c->scdb_blocks_per_sm;
+    const long long est = push ? ((long long)pairs + push->W.world - 1) / push->W.world : pairs;
+    const long long rounds = std::max<long long>(1, (est + (long long)cap * SCDB_WARPS - 1) / ((long long)cap * SCDB_WARPS));
+    int blocks = (int)((est + rounds * SCDB_WARPS - 1) / (rounds * SCDB_WARPS));
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;                                   // a rank that owns no pair still raises its phase-D flag
     ShardPush P; std::memset(&P, 0, sizeof(P));
