@@ -373,6 +373,9 @@ class Context:
     def solverLanes(self, lanes=0):
         _chk(self.lib.liorf_debug_s2m_lanes(self.h, C.c_int(int(lanes))), "liorf_debug_s2m_lanes")
 
+    def solverGlobalState(self, on=True):
+        _chk(self.lib.liorf_debug_s2m_global_state(self.h, C.c_int(int(on))), "liorf_debug_s2m_global_state")
+
     def disableSolverCache(self, on=True):
         _chk(self.lib.liorf_debug_s2m_disable_cache(self.h, C.c_int(int(on))), "liorf_debug_s2m_disable_cache")
 

@@ -85,8 +85,8 @@ struct liorf_ctx {
     std::map<int, MapGraphs> map_graphs; bool use_graphs = true;
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
-    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
-    DevBuf<QueryCache> qcache; DevBuf<float4> cand; S2MResult* d_result = nullptr; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; unsigned* d_s2m_arrive = nullptr;
+    float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; ulonglong2* d_wpart = nullptr; unsigned long long* d_res = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
+    DevBuf<QueryCache> qcache; DevBuf<float4> cand; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; bool s2m_global_state = false;
     int s2m_grid = 0; bool s2m_no_cache = false; int s2m_force_pg = 0;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
@@ -344,7 +344,8 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     CUDA_TRY(cudaMemset(c->d_trace, 0, sizeof(S2MTrace)));
     CUDA_TRY(cudaMalloc(&c->d_lm_out, 48 * sizeof(float)));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan2map_persistent, S2MP_BLOCK, 0));
+    CUDA_TRY(cudaFuncSetAttribute(k_scan2map_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, S2MP_SMEM));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan2map_persistent, S2MP_BLOCK, S2MP_SMEM));
     if (occ < 1) { fprintf(stderr, "[liorf_b200] persistent kernel does not fit\n"); return LIORF_ERR_CUDA; }
     // One persistent CTA per SM, on all but S2M_SPARE_SMS of them.  The solver's CTA owns its SM outright (512 threads x 128
     // registers = the whole register file), so the SMs it leaves free are where the NEXT frame's cloudHandler + downsample
@@ -359,10 +360,11 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     }
     CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->num_sms * NPROD * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->d_mail, sizeof(S2MMail)));
-    CUDA_TRY(cudaMalloc(&c->d_s2m_arrive, (size_t)c->num_sms * sizeof(unsigned)));
-    CUDA_TRY(cudaMemset(c->d_s2m_arrive, 0, (size_t)c->num_sms * sizeof(unsigned)));
-    CUDA_TRY(cudaMalloc(&c->d_result, 2 * sizeof(S2MResult)));
-    CUDA_TRY(cudaMemset(c->d_result, 0, 2 * sizeof(S2MResult)));
+    // hand-off words of the solver (epoch-tagged: zero never matches an epoch, launch sequence numbers start at 1)
+    CUDA_TRY(cudaMalloc(&c->d_wpart, (size_t)c->num_sms * NPROD * sizeof(ulonglong2)));
+    CUDA_TRY(cudaMemset(c->d_wpart, 0, (size_t)c->num_sms * NPROD * sizeof(ulonglong2)));
+    CUDA_TRY(cudaMalloc(&c->d_res, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_res, 0, 8 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->d_bins, SC_DESC * sizeof(unsigned)));
     {   // arm the ScanContext bins with the NO_POINT code
         std::vector<unsigned> init(SC_DESC);
@@ -425,7 +427,7 @@ void liorf_destroy(liorf_ctx* c) {
     if (c->icp_out) cudaFree(c->icp_out);
     if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
-    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_result); cudaFree(c->d_mail); cudaFree(c->d_s2m_arrive); c->qcache.release(); c->cand.release();
+    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_wpart); cudaFree(c->d_res); cudaFree(c->d_mail); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
     {   // peer windows
         liorf_ctx::ScShard& S = c->shard;
@@ -921,16 +923,15 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined
     if ((rc = c->qcache.reserve(qb)) || (rc = c->cand.reserve(qb * CAND_CAP))) return rc;
     if ((rc = join_map(c))) return rc;
     S2MArgs a;
-    a.qcache = c->qcache.p; a.cand = c->cand.p; a.result = c->d_result;
-    a.arrive = c->d_s2m_arrive; a.flag = reinterpret_cast<unsigned*>(c->d_misc + 9); a.err_flag = c->d_err;
+    a.qcache = c->qcache.p; a.cand = c->cand.p; a.res = c->d_res; a.wpart = c->d_wpart; a.err_flag = c->d_err; a.global_state = c->s2m_global_state ? 1 : 0;
     a.epoch_base = (++c->s2m_launch_seq) * 64u;
     a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
-    a.tf6 = c->d_tf6; a.st = c->d_lm; a.partial = c->d_partial; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.force_pg = c->s2m_force_pg; a.dbg = c->d_dbg; a.dbg_gt = c->d_dbg_gt;
+    a.tf6 = c->d_tf6; a.st = c->d_lm; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.force_pg = c->s2m_force_pg; a.dbg = c->d_dbg; a.dbg_gt = c->d_dbg_gt;
     a.mail = c->d_mail; a.cnt_n_scan = c->d_counts + C_N_SCAN;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(pipelined ? c->s2m_grid : c->num_sms), dim3(S2MP_BLOCK), args, 0, c->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(pipelined ? c->s2m_grid : c->num_sms), dim3(S2MP_BLOCK), args, S2MP_SMEM, c->stream));
     c->mail_fresh = true;
     return LIORF_OK;
 }
@@ -1309,7 +1310,7 @@ int liorf_debug_qr_solve6(liorf_ctx* c, const float* A, const float* b, int n, f
     float* dA = d.p; float* db = dA + (size_t)36 * n; float* dx = db + (size_t)6 * n;
     CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)36 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(db, b, (size_t)6 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    k_debug_qr6<<<(n + 63) / 64, 64, 0, c->stream>>>(dA, db, n, dx);
+    k_debug_qr6<<<(n + 1) / 2, 64, 0, c->stream>>>(dA, db, n, dx, c->d_err);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(x, dx, (size_t)6 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     rc = check_err(c);
@@ -2053,6 +2054,14 @@ int liorf_debug_s2m_disable_cache(liorf_ctx* c, int on) {
     LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     c->s2m_no_cache = on != 0;
+    return LIORF_OK;
+}
+/* tests: 1 = the solver keeps its per-query state (cache header, candidate list) in global memory even when the scan fits one round
+ * of the grid (the layout multi-round solves use); 0 = automatic (shared memory whenever one round covers the scan) */
+int liorf_debug_s2m_global_state(liorf_ctx* c, int on) {
+    LIORF_NVTX;
+    if (!c) return LIORF_ERR_ARG;
+    c->s2m_global_state = on != 0;
     return LIORF_OK;
 }
 /* tests: lanes per query of the persistent solver (4, 8 or 16); 0 = automatic (the widest group that covers the scan in one round) */

@@ -190,6 +190,73 @@ __device__ __forceinline__ bool qr_solve6(const float* __restrict__ Ain, const f
     return ok;
 }
 
+// qr_solve6 by one warp — same arithmetic, same order, bit-identical results (tests: liorf_debug_qr6 with mode 1).
+// Lane j < 6 holds column j of A, lane 6 the right-hand side.  Step l: lane l forms the Householder vector from its column and
+// broadcasts it; every column applies the reflector to itself at once, the right-hand side applies the STORED form of the same
+// reflector ((1, v1/v0, ..), hF = v0^2 — hal::QR32f transforms b from the stored factors after the sweep; reflector l's stored
+// factors never change after step l, so doing it inside the sweep is the same sequence of operations on b).  The six dependent
+// column sweeps of the one-thread version become one; the back substitution runs redundantly in every lane, which all return x.
+__device__ __forceinline__ bool qr_solve6_warp_cols(float (&col)[6], float* __restrict__ x) {
+    const int j = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+        float vl[6], vp[6];
+        float vlNorm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6 - l; ++i) { vl[i] = col[l + i]; vlNorm += vl[i] * vl[i]; }
+        float tmpV = vl[0];
+        vl[0] = vl[0] + (vl[0] < 0.f ? -1.f : 1.f) * sqrtf(vlNorm);
+        vlNorm = sqrtf(vlNorm + vl[0] * vl[0] - tmpV * tmpV);
+#pragma unroll
+        for (int i = 0; i < 6 - l; ++i) vl[i] /= vlNorm;
+#pragma unroll
+        for (int i = 0; i < 6 - l; ++i) vl[i] = __shfl_sync(0xffffffffu, vl[i], l);
+        const float hF = vl[0] * vl[0];
+        vp[0] = 1.f;
+#pragma unroll
+        for (int i = 1; i < 6 - l; ++i) vp[i] = vl[i] / vl[0];
+        float v_lA = 0.f, v_lB = 0.f;
+#pragma unroll
+        for (int i = l; i < 6; ++i) { v_lA += vl[i - l] * col[i]; v_lB += vp[i - l] * col[i]; }
+#pragma unroll
+        for (int i = l; i < 6; ++i) {
+            const float nA = col[i] - 2 * vl[i - l] * v_lA;
+            const float nB = col[i] - 2 * vp[i - l] * v_lB * hF;
+            col[i] = j == 6 ? nB : ((j >= l && j < 6) ? nA : col[i]);
+        }
+#pragma unroll
+        for (int i = 1; i < 6 - l; ++i) if (j == l) col[l + i] = vp[i];
+    }
+    float b[6], R[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        b[i] = __shfl_sync(0xffffffffu, col[i], 6);
+#pragma unroll
+        for (int jj = i; jj < 6; ++jj) R[i][jj] = __shfl_sync(0xffffffffu, col[i], jj);
+    }
+    const float eps = FLT_EPSILON * 10;
+    bool ok = true;
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        if (ok) {
+#pragma unroll
+            for (int jj = 5; jj > i; --jj) b[i] -= b[jj] * R[i][jj];
+            if (fabsf(R[i][i]) < eps) ok = false;
+            else b[i] /= R[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = ok ? b[i] : 0.f;
+    return ok;
+}
+__device__ __forceinline__ bool qr_solve6_warp(const float* __restrict__ Ain, const float* __restrict__ bin, float* __restrict__ x) {
+    const int j = threadIdx.x & 31;
+    float col[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) col[i] = j < 6 ? Ain[i * 6 + j] : (j == 6 ? bin[i] : 0.f);
+    return qr_solve6_warp_cols(col, x);
+}
+
 __device__ __forceinline__ float cv_hypot(float a, float b) {
     a = fabsf(a); b = fabsf(b);
     if (a > b) { b /= a; return a * sqrtf(1 + b * b); }

@@ -293,12 +293,17 @@ __device__ __forceinline__ bool lm_solve_dev(int iter, const double* sums, float
 // Per-function parity hooks
 // ---------------------------------------------------------------------------------------------------------------
 // test hook: cv::solve(DECOMP_QR) of n 6x6 systems by the device routine the solver uses (one thread each)
-__global__ void __launch_bounds__(64) k_debug_qr6(const float* __restrict__ A, const float* __restrict__ b, int n, float* __restrict__ x) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// (one warp per system: the warp routine of the persistent solver; lane 0 repeats the solve with the one-thread routine of the LM
+// hook and raises err_flag = 7 if a single bit differs)
+__global__ void __launch_bounds__(64) k_debug_qr6(const float* __restrict__ A, const float* __restrict__ b, int n, float* __restrict__ x, int* err_flag) {
+    const int s = blockIdx.x * 2 + (threadIdx.x >> 5);
     if (s >= n) return;
-    float xs[6];
-    qr_solve6(A + 36 * s, b + 6 * s, xs);
-    for (int i = 0; i < 6; ++i) x[6 * s + i] = xs[i];
+    float xw[6], xs[6];
+    qr_solve6_warp(A + 36 * s, b + 6 * s, xw);
+    if ((threadIdx.x & 31) == 0) {
+        qr_solve6(A + 36 * s, b + 6 * s, xs);
+        for (int i = 0; i < 6; ++i) { x[6 * s + i] = xw[i]; if (__float_as_uint(xw[i]) != __float_as_uint(xs[i])) atomicExch(err_flag, 7); }
+    }
 }
 
 __global__ void __launch_bounds__(S2M_BLOCK) k_surf_optimization(const float4* __restrict__ scan, Count n_scan, const float* __restrict__ tf6,
@@ -404,6 +409,11 @@ constexpr int S2MP_WARPS = S2MP_BLOCK / 32;
 constexpr int CAND_CAP = 64;                // cached candidates per query (float4 each); overflow → always full search
 constexpr float S2M_MARGIN = 0.15f;
 constexpr int PPL = NPROD / 4;              // products per accumulating lane (lanes 0..3 of a group: 28 / 4 = 7)
+// Shared-memory query state of one-round solves (n <= workers x 128: ONE thread serves the same query in every iteration): candidate
+// rows of CAND_CAP float4 at an odd stride (65: the eight lanes of a quarter warp, one row each, hit eight different 16-byte bank
+// groups), then the four header words of QueryCache as four arrays (lane t reads element t: conflict-free).
+constexpr int S2M_ROW = CAND_CAP + 1;
+constexpr int S2MP_SMEM = S2MP_QPB * (S2M_ROW + 4) * (int)sizeof(float4);          // 141 312 B
 
 struct QueryCache {                         // 64 B per query
     float qx, qy, qz; int cnt;              // cached query position q0 and candidate count (-1: none, -2: overflow)
@@ -412,35 +422,53 @@ struct QueryCache {                         // 64 B per query
 };
 static_assert(sizeof(QueryCache) == 64, "QueryCache must be 64 bytes");
 
-struct alignas(16) S2MResult { float tf[6]; int conv; int nsel; };
 struct alignas(16) S2MMail { float tf[6]; int iters, converged, degenerate, ran, n_scan, n_ds, m_ds, err; int pad[2]; };
 static_assert(sizeof(S2MMail) == 64, "S2MMail must be 64 bytes");
 
 constexpr int S2M_MAX_WORKERS = 152;    // >= SMs - 1 (B200: 147)
 constexpr int S2M_GT_STRIDE = 160;      // per iteration: [0..W) worker arrival, [156] reducer sums ready, [157] reducer published, [158] worker 0 saw the flag
+constexpr int S2M_POLL = (S2M_MAX_WORKERS * NPROD + S2MP_BLOCK - 1) / S2MP_BLOCK;      // partial-sum words one reducer thread collects
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// Hand-off words between the workers and the reducer.  Every 64-bit word carries 32 bits of payload and, in its upper half, the epoch
+// of the iteration it belongs to (64-bit accesses are single-copy atomic): the data IS the flag.  Neither side needs a release fence
+// in front of a separate flag store nor a second round trip behind an acquire load — one L2 round trip per direction and iteration.
+__device__ __forceinline__ void st_word2(ulonglong2* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_word2(const ulonglong2* p) {
+    ulonglong2 v; asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_word(unsigned long long* p, unsigned long long a) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+
 struct S2MArgs {
     const float4* scan; Count n_scan;
     const unsigned* cell_start; const float4* gmap; GridDims g; Count m_map;
     float* tf6;                      // in/out transformTobeMapped (device)
     LMDeviceState* st;
-    double* partial;                 // [2][gridDim.x][NPROD]
+    ulonglong2* wpart;               // [workers][NPROD]: a worker's partial sums, each fp64 as two epoch-tagged words
     S2MTrace* trace;
     int max_iters; int force_all;
     int force_pg;                    // tests: lanes per query (4, 8 or 16); 0 = automatic
     int no_cache;                    // tests: 1 = never reuse candidate lists / planes (every iteration searches the 27 cells and refits)
+    int global_state;                // tests: 1 = per-query state in global memory even when the scan fits one round
     long long* dbg;                  // optional [S2M_MAX_ITERS][8] clock64 phase stamps of CTA 0 (nullptr = off)
     unsigned long long* dbg_gt;      // optional [S2M_MAX_ITERS][S2M_GT_STRIDE] %globaltimer stamps: worker arrivals, flag seen by worker 0, reducer sum-ready / published
-    QueryCache* qcache;              // [n_scan bound]
+    QueryCache* qcache;              // [n_scan bound]   (multi-round solves)
     float4* cand;                    // [n_scan bound][CAND_CAP]
-    S2MResult* result;               // [2]
-    unsigned* arrive;                // [gridDim.x] per-worker arrival words (hold the epoch of the iteration whose partial is complete)
-    unsigned* flag;                  // epoch flag
-    unsigned epoch_base;             // launch-unique: flag value for iteration k is epoch_base + k + 1
+    unsigned long long* res;         // [8]: tf[0..5], converged, nsel — epoch-tagged words written by the reducer
+    unsigned epoch_base;             // launch-unique: the epoch of iteration k is epoch_base + k + 1
     int* err_flag;
     S2MMail* mail;                   // optional: everything the host reads after a frame, in ONE 64-byte record (one D2H copy)
     const int* cnt_n_scan;           // device counts copied into the mail (nullable)
 };
+
+// multi-round solves: per-query state in global memory behind L2 (.cg: written and re-read by the same group only)
+__device__ __forceinline__ float4 qs_ld(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ void qs_st(float4* p, const float4 v) { __stcg(p, v); }
 
 template <int G>
 __device__ __forceinline__ void top5_merge(Top5& mine, Top5& res) {
@@ -510,7 +538,7 @@ __device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigne
                 const bool keep = d < r2c;
                 const unsigned km = __ballot_sync(gmask, keep);          // only this query's lanes vote (other groups may be elsewhere)
                 const int slot = ncache + __popc(km & ((1u << lane_id()) - 1u));
-                if (keep && slot < CAND_CAP) __stcg(clist + slot, p[u]);
+                if (keep && slot < CAND_CAP) qs_st(clist + slot, p[u]);
                 if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), (int)pos[u]);
                 ncache += __popc(km);
             }
@@ -532,7 +560,7 @@ __device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigne
                 const bool keep = d < r2c;
                 const unsigned km = __ballot_sync(gmask, keep);
                 const int slot = ncache + __popc(km & ((1u << lane_id()) - 1u));
-                if (keep && slot < CAND_CAP) __stcg(clist + slot, pt);
+                if (keep && slot < CAND_CAP) qs_st(clist + slot, pt);
                 if (d < 1.0f) top5_insert(mine, d, __float_as_int(pt.w), (int)(b + f0));
                 ncache += __popc(km);
             }
@@ -546,6 +574,8 @@ __device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigne
 // More lanes per query shorten the serial candidate walk of the 27-cell search and put fewer queries in a warp (less
 // divergence between cached / searching / refitting queries); the kernel picks the widest group that still covers the
 // scan in ONE round of the grid.
+// (multi-round solves — more than 128 queries per worker, e.g. OS1-128 at 0.2 m — and the layout forced by liorf_debug_s2m_global_state;
+// scans that fit one round take s2m_iter_one_round below)
 template <int PG>
 __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, const int W, const int iter, const float (&s_t)[12], const LMTrig& s_trig,
                                                float (*s_rows)[8], const int (&pij)[PPL], double (&acc)[PPL]) {
@@ -555,18 +585,18 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
         const int q = (j0 + qslot) * W + (int)blockIdx.x;
         const bool active = q < n;
         const int qq = active ? q : 0;
-        QueryCache* qc = a.qcache + qq;
+        float4* hdr = reinterpret_cast<float4*>(a.qcache + qq);
         float4* clist = a.cand + (size_t)qq * CAND_CAP;
-        // every independent load of the cached path is issued up front (one L2 round trip): the point, the cache
+        // every independent load of the cached path is issued up front (one round trip): the point, the cache
         // header (written by this same group earlier in this launch), the cached plane and the first candidates
         float4 ori = active ? __ldg(a.scan + q) : make_float4(0, 0, 0, 0);
-        const float4 h0 = __ldcg(reinterpret_cast<const float4*>(qc));
-        const float4 h1 = __ldcg(reinterpret_cast<const float4*>(qc) + 1);              // nn[0..3]
-        const float4 h2 = __ldcg(reinterpret_cast<const float4*>(qc) + 2);              // nn[4], plane_ok, pa, pb
-        const float4 h3 = __ldcg(reinterpret_cast<const float4*>(qc) + 3);              // pc, pd
+        const float4 h0 = qs_ld(hdr);
+        const float4 h1 = qs_ld(hdr + 1);              // nn[0..3]
+        const float4 h2 = qs_ld(hdr + 2);              // nn[4], plane_ok, pa, pb
+        const float4 h3 = qs_ld(hdr + 3);              // pc, pd
         float4 pre[KNN_U];
 #pragma unroll
-        for (int u = 0; u < KNN_U; ++u) pre[u] = __ldcg(clist + gl + PG * u);           // speculative: slots exist even if unused
+        for (int u = 0; u < KNN_U; ++u) pre[u] = qs_ld(clist + gl + PG * u);           // speculative: slots exist even if unused
         float4 sel = apply_affine_dev(s_t, ori);
         const int cnt = __float_as_int(h0.w);
         float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
@@ -577,14 +607,13 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
         const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
         const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
         Top5 mine; top5_init(mine);
-        int list_cnt;                                       // >= 0: results index the candidate list; -2: they index gmap... see below
         if (use_cache) {
             for (int f0 = gl; f0 < cnt; f0 += PG * KNN_U) {
                 float4 p[KNN_U];
 #pragma unroll
                 for (int u = 0; u < KNN_U; ++u) {
                     const int f = f0 + PG * u;
-                    p[u] = f0 == gl ? pre[u] : (f < cnt ? __ldcg(clist + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f));
+                    p[u] = f0 == gl ? pre[u] : (f < cnt ? qs_ld(clist + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f));
                     if (f >= cnt) p[u] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
                 }
 #pragma unroll
@@ -594,11 +623,10 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
                     if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), f0 + PG * u);
                 }
             }
-            list_cnt = cnt;
         } else if (active) {
-            list_cnt = knn5_full_and_cache<PG>(sel, a.cell_start, a.gmap, a.g, clist, mine);
-            if (gl == 0) { float4 h = make_float4(sel.x, sel.y, sel.z, __int_as_float(list_cnt)); __stcg(reinterpret_cast<float4*>(qc), h); }
-        } else list_cnt = -1;
+            const int list_cnt = knn5_full_and_cache<PG>(sel, a.cell_start, a.gmap, a.g, clist, mine);
+            if (gl == 0) qs_st(hdr, make_float4(sel.x, sel.y, sel.z, __int_as_float(list_cnt)));
+        }
         Top5 nn; top5_merge<PG>(mine, nn);
         // ---- plane: reuse when the ordered neighbour ids are unchanged ----
         const bool have5 = active && nn.pos[4] != -1 && (double)nn.d[4] < 1.0;          // :1097
@@ -610,10 +638,12 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
             if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
             else {
                 float A[5][3];
+                // results index the candidate list in cached mode, gmap otherwise
 #pragma unroll
-                const float4* nsrc = use_cache ? clist : a.gmap;      // results index the candidate list in cached mode, gmap otherwise
-#pragma unroll
-                for (int j = 0; j < 5; ++j) { float4 mpt = __ldcg(nsrc + nn.pos[j]); A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z; }
+                for (int j = 0; j < 5; ++j) {
+                    const float4 mpt = use_cache ? qs_ld(clist + nn.pos[j]) : __ldcg(a.gmap + nn.pos[j]);
+                    A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z;
+                }
                 float x[3];
                 colpiv_qr_solve_5x3(A, x);                                               // :1104
                 pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
@@ -624,9 +654,9 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
                 for (int j = 0; j < 5; ++j)                                              // :1115-1122
                     if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
                 if (gl == 0) {
-                    __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3])));
-                    __stcg(reinterpret_cast<float4*>(qc) + 2, make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb));
-                    __stcg(reinterpret_cast<float4*>(qc) + 3, make_float4(pc, pd, 0.f, 0.f));
+                    qs_st(hdr + 1, make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3])));
+                    qs_st(hdr + 2, make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb));
+                    qs_st(hdr + 3, make_float4(pc, pd, 0.f, 0.f));
                 }
             }
             if (planeValid) {
@@ -637,7 +667,7 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
                 f = (double)sw > 0.1;                                                    // :1135
             }
         } else if (iter == 0 && active && gl == 0) {
-            __stcg(reinterpret_cast<float4*>(qc) + 1, make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)));   // no cached plane
+            qs_st(hdr + 1, make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)));   // no cached plane
         }
         float v[8];
         lm_row_dev(s_trig, ori, coeff, v); v[7] = 1.f;
@@ -653,10 +683,354 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-round solves (n <= workers x 128 — the KITTI / Livox sizes): ONE THREAD PER QUERY, state in shared memory.
+// The 4-lanes-per-query pass above is bound by instruction issue, not memory (ncu r2: 7.6k warp instructions per scheduler and
+// iteration; a quarter of them the insertion sort of the per-lane top-5 lists, another tenth their merge, and everything after the
+// search executed four times over).  Here an iteration is three phases over the worker's <= 128 queries:
+//   1. (thread = query) pointSel; is the cached candidate list still valid (see above)?  If not, queue the query.
+//   2. (warp = queued query) rebuild the list: the 27 cells are walked 32 points at a time and every point within 1 + m of the new
+//      q0 is appended (ballot compaction) — no top-5 bookkeeping at all.  Steady state: nothing queued.
+//   3. (thread = query) exact 5-NN by one ordered insertion pass over the ~15 listed points (no merge, nothing redundant), plane
+//      reuse / refit, weight, Jacobian row → s_rows.
+// followed by the products: 16 chains x 28 products sum their queries' row products in fp64 (fixed order), combined by the same
+// 4-chain tree as before.  Same arithmetic per point and the same (distance, index) order — the neighbour sets and rows are
+// bit-identical to the multi-round path; only the order of the fp64 partial sums differs (as it does between lane widths).
+// A list that overflows CAND_CAP (-2) is answered by an exact one-thread walk of the 27 cells (rare: > 64 map points within 1.15 m).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int build_list_warp(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g,
+                                               float4* __restrict__ clist) {
+    const int l = lane_id();
+    const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
+    const int x0 = (cx - 1) & (g.DX - 1), x1 = cx & (g.DX - 1), x2 = (cx + 1) & (g.DX - 1);
+    const float r2c = (1.0f + S2M_MARGIN) * (1.0f + S2M_MARGIN);
+    const unsigned lt = (1u << l) - 1u;
+    int ncache = 0;
+    if (x0 + 2 == x2) {
+        // lane r < 9 fetches the bounds of x-run r; an inclusive scan over those lanes turns the lengths into the flattened index space
+        unsigned b = 0, len = 0;
+        if (l < 9) {
+            const int dz = l / 3 - 1, dy = l % 3 - 1;
+            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
+            b = __ldg(cell_start + row + x0); len = __ldg(cell_start + row + x2 + 1) - b;
+        }
+        unsigned incl = len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (l >= o) incl += v; }
+        unsigned bs[9], P[10];
+        P[0] = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) { bs[r] = __shfl_sync(FULL, b, r); P[r + 1] = __shfl_sync(FULL, incl, r); }
+        const unsigned T = P[9];
+        for (unsigned f0 = 0; f0 < T; f0 += 64) {
+            float4 p[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const unsigned f = f0 + 32 * u + l;
+                unsigned base = bs[0], pb = 0;
+#pragma unroll
+                for (int rr = 1; rr < 9; ++rr) if (f >= P[rr]) { base = bs[rr]; pb = P[rr]; }
+                p[u] = f < T ? __ldg(gmap + base + (f - pb)) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float dx = q.x - p[u].x, dy = q.y - p[u].y, dz = q.z - p[u].z;
+                float d = dx * dx; d += dy * dy; d += dz * dz;      // FLANN L2_Simple op order, no FMA
+                const bool keep = d < r2c;
+                const unsigned km = __ballot_sync(FULL, keep);
+                const int slot = ncache + __popc(km & lt);
+                if (keep && slot < CAND_CAP) clist[slot] = p[u];
+                ncache += __popc(km);
+            }
+        }
+    } else {                                     // x-run wraps around the torus: 27 single cells
+#pragma unroll 1
+        for (int c27 = 0; c27 < 27; ++c27) {
+            const int r = c27 / 3, xi = c27 % 3;
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
+            const int xc = xi == 0 ? x0 : (xi == 1 ? x1 : x2);
+            const unsigned b = __ldg(cell_start + row + xc), e = __ldg(cell_start + row + xc + 1);
+            for (unsigned f0 = b; f0 < e; f0 += 32) {
+                const unsigned f = f0 + l;
+                const float4 pt = f < e ? __ldg(gmap + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+                float dx = q.x - pt.x, dy2 = q.y - pt.y, dz2 = q.z - pt.z;
+                float d = dx * dx; d += dy2 * dy2; d += dz2 * dz2;
+                const bool keep = d < r2c;
+                const unsigned km = __ballot_sync(FULL, keep);
+                const int slot = ncache + __popc(km & lt);
+                if (keep && slot < CAND_CAP) clist[slot] = pt;
+                ncache += __popc(km);
+            }
+        }
+    }
+    return ncache <= CAND_CAP ? ncache : -2;
+}
+
+// exact 5-NN by ONE thread over the 27 cells (list overflow only); pos = index into gmap
+__device__ __noinline__ void knn5_lane(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g, Top5& t) {
+    const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
+    for (int c27 = 0; c27 < 27; ++c27) {
+        const int dz = c27 / 9 - 1, dy = (c27 / 3) % 3 - 1, dx = c27 % 3 - 1;
+        const int cell = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX + ((cx + dx) & (g.DX - 1));
+        const unsigned b = __ldg(cell_start + cell), e = __ldg(cell_start + cell + 1);
+        for (unsigned k = b; k < e; ++k) {
+            const float4 p = __ldg(gmap + k);
+            float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
+            float d = ex * ex; d += ey * ey; d += ez * ez;
+            if (d < 1.0f) top5_insert(t, d, __float_as_int(p.w), (int)k);
+        }
+    }
+}
+
+struct S2MShared {                      // views into the dynamic shared memory of a one-round worker
+    float4* list;                       // [S2MP_QPB][S2M_ROW]
+    float4* h0; float4* h1; float4* h2; float4* h3;      // [S2MP_QPB] each: QueryCache's four 16-byte words; h3.z = list positions of the current top-5 (6 bits each)
+};
+
+// (distance, original index) as ONE unsigned 64-bit key: squared distances are non-negative floats, whose bit patterns order like the
+// values, and the original indices are non-negative ints — key order == less_di order
+__device__ __forceinline__ unsigned long long nn_key(float d, int oi) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)oi; }
+__device__ __forceinline__ float sqdist_dev(const float4 q, const float4 p) {
+    float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+    float d = dx * dx; d += dy * dy; d += dz * dz;                  // FLANN L2_Simple op order, no FMA
+    return d;
+}
+
+// phase 2 epilogue, one warp: list positions of the five smallest keys of a freshly built list (cnt >= 5), packed 6 bits each, smallest
+// first — the prior that phase 3 verifies from now on
+__device__ __forceinline__ unsigned top5_positions_warp(const float4 q, const float4* __restrict__ row, int cnt) {
+    const int l = lane_id();
+    unsigned long long kA = ~0ull, kB = ~0ull;
+    if (l < cnt) { const float4 p = row[l]; kA = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
+    if (l + 32 < cnt) { const float4 p = row[l + 32]; kB = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
+    unsigned packed = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const unsigned long long mine = kA < kB ? kA : kB;
+        unsigned long long m = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(FULL, m, o); m = v < m ? v : m; }
+        const int owner = __ffs(__ballot_sync(FULL, mine == m)) - 1;          // keys are unique (distinct original indices)
+        const int pos = kA < kB ? l : l + 32;
+        packed |= (unsigned)__shfl_sync(FULL, pos, owner) << (6 * r);
+        if (l == owner) { if (kA < kB) kA = ~0ull; else kB = ~0ull; }
+    }
+    return packed;
+}
+
+__device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n, const int W, const int iter, const float (&s_t)[12], const LMTrig& s_trig,
+                                                   float (*s_rows)[8], const S2MShared& S, const float4 ori, const float rr, int* s_todo, int* s_ntodo) {
+    const int tid = threadIdx.x;
+    const bool mine = tid < S2MP_QPB && tid * W + (int)blockIdx.x < n;
+    float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- 1. pointSel; queue the queries whose candidate list must be rebuilt ----
+    if (mine) {
+        sel = apply_affine_dev(s_t, ori);
+        const float4 h0 = S.h0[tid];
+        const int cnt = __float_as_int(h0.w);
+        float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
+        float moved = mx * mx; moved += my * my; moved += mz * mz;
+        const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
+        const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
+        const bool valid = iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
+        if (!valid) { s_todo[atomicAdd(s_ntodo, 1)] = tid; S.h0[tid] = make_float4(sel.x, sel.y, sel.z, __int_as_float(-1)); }
+        // iteration 0 never trusts a cached plane (it belongs to an earlier launch / another map)
+        if (iter == 0) S.h1[tid] = make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1));
+    }
+    __syncthreads();
+    // ---- 2. one warp per queued query rebuilds its list around the new q0 and leaves the positions of its five nearest entries ----
+    const int ntodo = *s_ntodo;
+    for (int k = warp_id(); k < ntodo; k += S2MP_WARPS) {
+        const int slot = s_todo[k];
+        const float4 q0 = S.h0[slot];
+        float4* row = S.list + slot * S2M_ROW;
+        const int c = build_list_warp(q0, a.cell_start, a.gmap, a.g, row);
+        __syncwarp();
+        unsigned packed = 0;
+        if (c >= 5) packed = top5_positions_warp(q0, row, c);
+        if (lane_id() == 0) {
+            S.h0[slot] = make_float4(q0.x, q0.y, q0.z, __int_as_float(c));
+            float4 h3 = S.h3[slot]; h3.z = __uint_as_float(packed); S.h3[slot] = h3;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) *s_ntodo = 0;                  // the next iteration's phase 1 is at least two barriers away
+    // ---- 3. exact 5-NN from the list, plane, weight, Jacobian row ----
+    if (tid < S2MP_QPB) {
+        bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[8];
+        if (mine) {
+            const int cnt = __float_as_int(S.h0[tid].w);
+            const float4* row = S.list + tid * S2M_ROW;
+            const float4 h3 = S.h3[tid];
+            Top5 nn; top5_init(nn);
+            if (cnt >= 5) {
+                // The five entries that were nearest last time (or when the list was built) bound the new 5th-smallest key from above:
+                // only entries with key <= thr can be among the new five.  Usually those are the same five in the same order — then the
+                // neighbours are unchanged and nothing is sorted at all; otherwise the few entries under the bound are inserted in order.
+                unsigned pk = __float_as_uint(h3.z);
+                unsigned long long ck[5]; float cd[5]; int coi[5], cpos[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    cpos[j] = (int)((pk >> (6 * j)) & 63u);
+                    const float4 p = row[cpos[j]];
+                    cd[j] = sqdist_dev(sel, p); coi[j] = __float_as_int(p.w); ck[j] = nn_key(cd[j], coi[j]);
+                }
+                unsigned long long thr = ck[0];
+#pragma unroll
+                for (int j = 1; j < 5; ++j) thr = ck[j] > thr ? ck[j] : thr;
+                unsigned long long mask = 0;
+                for (int f0 = 0; f0 < cnt; f0 += 4) {
+                    float4 p[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) p[u] = row[f0 + u];          // the row is padded: entries past cnt are read but masked out
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned long long k = nn_key(sqdist_dev(sel, p[u]), __float_as_int(p[u].w));
+                        mask |= (unsigned long long)((k <= thr) && (f0 + u < cnt)) << (f0 + u);
+                    }
+                }
+                const bool sorted = ck[0] < ck[1] && ck[1] < ck[2] && ck[2] < ck[3] && ck[3] < ck[4];
+                if (__popcll(mask) == 5 && sorted && cd[4] < 1.0f) {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { nn.d[j] = cd[j]; nn.oi[j] = coi[j]; nn.pos[j] = cpos[j]; }
+                } else {
+                    while (mask) {
+                        const int i = __ffsll((long long)mask) - 1; mask &= mask - 1;
+                        const float4 p = row[i];
+                        const float d = sqdist_dev(sel, p);
+                        if (d < 1.0f) top5_insert(nn, d, __float_as_int(p.w), i);
+                    }
+                    if (nn.pos[4] != -1) {
+                        pk = 0;
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) pk |= (unsigned)nn.pos[j] << (6 * j);
+                        float4 h3n = h3; h3n.z = __uint_as_float(pk); S.h3[tid] = h3n;
+                    }
+                }
+            } else if (cnt == -2) knn5_lane(sel, a.cell_start, a.gmap, a.g, nn);
+            const bool have5 = nn.pos[4] != -1 && (double)nn.d[4] < 1.0;                // :1097
+            if (have5) {
+                const float4 h1 = S.h1[tid], h2 = S.h2[tid];
+                const bool same = iter > 0 && !a.no_cache && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
+                                  __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
+                float pa, pb, pc, pd; bool planeValid;
+                if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
+                else {
+                    float A[5][3];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 mpt = cnt >= 0 ? row[nn.pos[j]] : __ldg(a.gmap + nn.pos[j]);
+                        A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z;
+                    }
+                    float x[3];
+                    colpiv_qr_solve_5x3(A, x);                                           // :1104
+                    pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
+                    float ps = sqrtf(pa * pa + pb * pb + pc * pc);                       // :1111
+                    pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+                    planeValid = true;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)                                          // :1115-1122
+                        if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
+                    S.h1[tid] = make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3]));
+                    S.h2[tid] = make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb);
+                    float4 h3n = S.h3[tid]; h3n.x = pc; h3n.y = pd; S.h3[tid] = h3n;
+                }
+                if (planeValid) {
+                    float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;               // :1125
+                    float sw = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)rr);     // :1127-1128 (rr = sqrt(sqrt(|pointOri|^2)) does not change between iterations)
+                    coeff = make_float4(sw * pa, sw * pb, sw * pc, sw * pd2);            // :1130-1133
+                    f = (double)sw > 0.1;                                                // :1135
+                }
+            }
+            lm_row_dev(s_trig, ori, coeff, v); v[7] = 1.f;
+        }
+        float4* r4 = reinterpret_cast<float4*>(&s_rows[tid][0]);             // zero row when the point is not selected / the slot is idle
+        r4[0] = f ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r4[1] = f ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// The reducer's solve (lm_solve_dev's arithmetic) by ONE WARP: the Householder sweep over the six columns and the right-hand side is
+// the long pole of an iteration, and its columns are independent (qr_solve6_warp).  sums: 28 fp64 totals in shared memory.
+// Every lane returns the same (tf, converged, nsel).
+template <bool FAST_DEGENERACY>
+__device__ __forceinline__ bool lm_solve_warp(int iter, const double* sums, float (&tf)[6], LMDeviceState* st, float* scratchA /*36*/, float* scratchV /*36*/, int& nsel) {
+    float X[6];
+    nsel = (int)(sums[27] + 0.5);
+    if (nsel < 50) return false;                                                    // :1178
+    {   // lane j < 6 takes column j of AtA (symmetric: entry (i, j) is product rs(min) + |i - j|), lane 6 takes AtB
+        const int j = lane_id();
+        float col[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int lo = i < j ? i : j, hi = i < j ? j : i;
+            const int p = j < 6 ? lo * 6 - lo * (lo - 1) / 2 + (hi - lo) : (j == 6 ? 21 + i : 27);
+            col[i] = (float)sums[p];
+        }
+        qr_solve6_warp_cols(col, X);                                                // :1240
+    }
+    if (iter == 0) {                                                                // :1242-1264
+        float AtA[36];
+#pragma unroll
+        for (int p = 0; p < 21; ++p) { const float v = (float)sums[p]; AtA[prod_i(p) * 6 + prod_j(p)] = v; AtA[prod_j(p) * 6 + prod_i(p)] = v; }
+        const bool cert = FAST_DEGENERACY && certify_non_degenerate(AtA);           // same verdict in every lane
+        if (lane_id() == 0) {
+            if (cert) {
+                st->isDegenerate = 0;
+#pragma unroll
+                for (int i = 0; i < 36; ++i) st->matP[i] = (i % 7 == 0) ? 1.f : 0.f;
+            } else {
+                float tmpA[36];
+#pragma unroll
+                for (int i = 0; i < 36; ++i) tmpA[i] = AtA[i];
+                lm_degeneracy_dev(tmpA, st, scratchA, scratchV);
+            }
+        }
+        __syncwarp();
+    }
+    if (st->isDegenerate) {                                                         // :1266-1271
+        float X2[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) X2[i] = X[i];
+        gemv6(st->matP, X2, X);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) tf[i] += X[i];                                      // :1273-1278
+    const float r2d = 57.29578f;
+    double a0 = (double)(X[0] * r2d), a1 = (double)(X[1] * r2d), a2 = (double)(X[2] * r2d);
+    double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
+    float deltaR = (float)sqrt(a0 * a0 + a1 * a1 + a2 * a2);                        // :1280-1287
+    float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    return (double)deltaR < 0.05 && (double)deltaT < 0.05;                          // :1289
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scan2MapOptimization: ONE persistent kernel (cooperative launch = co-residency guarantee, one CTA per SM) runs the
+// whole ≤30-iteration loop with no host round trips.
+//
+// Per iteration and query (PG = 4, 8 or 16 lanes per query):
+//   pointSel = T * pointOri
+//   candidates: iteration-0 style FULL search walks the 27 cells and, on the way, stores every map point within
+//               (1 + m) of the query position q0 (m = S2M_MARGIN) as the query's cached candidate list.
+//               While |pointSel - q0| <= m - eps AND pointSel stays in q0's grid cell, every point that can be within
+//               1 m of pointSel is in that list (triangle inequality for the radius; same cell so that the unit ball
+//               around pointSel stays inside the 27 cells that were searched), so later iterations scan ONLY the
+//               ~15-point list — same exact 5-NN, same order.
+//   plane     : depends only on the ordered neighbour ids → cached with them; the 5x3 QR is redone only when they change.
+//   products  : the 28 normal-equation products are split over four lanes of the group, accumulated in fp64.
+// Per iteration and CTA: fixed-tree block reduction → 28 epoch-tagged partial sums written straight to the reducer's inbox.
+// The REDUCER CTA collects the inboxes as they fill, sums them in worker order (deterministic), one of its warps solves the 6x6
+// system and publishes (pose, converged, nsel) as eight epoch-tagged words the workers poll.
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a) {
+    extern __shared__ __align__(16) float4 s_state[];     // S2MP_SMEM bytes: per-query candidate rows + headers (one-round solves)
+    __shared__ int s_todo[S2MP_QPB];
+    __shared__ int s_ntodo;
     __shared__ float s_tf[6];
     __shared__ float s_sc[6];                              // cos/sin of yaw, pitch, roll for this iteration
-    __shared__ float s_rows[S2MP_QPB][8];
+    __shared__ __align__(16) float s_rows[S2MP_QPB][8];
     __shared__ double s_red[S2MP_WARPS][NPROD];
     __shared__ double s_sum[NPROD];
     __shared__ float s_A[36], s_V[36];
@@ -675,10 +1049,19 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     const int m = a.m_map.get();
     // lanes per query: the widest group that covers the scan in one round of the workers (same choice in every CTA)
     const int pg = a.force_pg ? a.force_pg : (n <= W * (S2MP_BLOCK / 16) ? 16 : (n <= W * (S2MP_BLOCK / 8) ? 8 : 4));
+    const bool one_round = !a.global_state && n <= W * S2MP_QPB;              // one thread per query, state in registers / shared memory
+    S2MShared S; S.list = s_state; S.h0 = s_state + S2MP_QPB * S2M_ROW; S.h1 = S.h0 + S2MP_QPB; S.h2 = S.h1 + S2MP_QPB; S.h3 = S.h2 + S2MP_QPB;
     const int gl = threadIdx.x & (pg - 1);              // lane within the query group; lanes 0..3 own 7 products each
     if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
+    if (threadIdx.x == 32) { s_conv = 0; s_ntodo = 0; }
     if (reducer && threadIdx.x >= 64 && threadIdx.x < 64 + 37)          // persistent LM state (members :139-140)
         reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
+    float4 ori_keep = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rr_keep = 0.f;
+    if (!reducer && one_round && threadIdx.x < S2MP_QPB) { const int q = (int)threadIdx.x * W + (int)blockIdx.x; if (q < n) { ori_keep = __ldg(a.scan + q); rr_keep = sqrtf(sqrtf(ori_keep.x * ori_keep.x + ori_keep.y * ori_keep.y + ori_keep.z * ori_keep.z)); } }
+    // product owned by this thread in the one-round reduction: chain k16 = tid / 28 of 16, product p16 = tid % 28
+    const int k16 = (int)threadIdx.x / NPROD, p16 = (int)threadIdx.x % NPROD;
+    const int pi16 = prod_i(p16), pj16 = prod_j(p16);
     __syncthreads();
     // guards of scan2MapOptimization (:1297-1300): a map must exist (and hold >= 5 points for the 5-NN), n > 30
     const bool run = (m >= 5) && (n > 30);
@@ -691,8 +1074,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
         // iteration 0 never trusts the per-query caches (they belong to an earlier launch / another map)
         for (int iter = 0; iter < a.max_iters; ++iter) {
             const unsigned epoch = a.epoch_base + (unsigned)iter + 1u;
-            double* part = a.partial + (size_t)(iter & 1) * gridDim.x * NPROD;
-            S2MResult* res = a.result + (iter & 1);
+            const unsigned long long etag = (unsigned long long)epoch << 32;
             if (!reducer) {
                 const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && iter < S2M_MAX_ITERS;
                 if (dbg) a.dbg[iter * 8 + 0] = clock64();
@@ -707,70 +1089,88 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                     s_t[8] = -D;     s_t[9] = Cc * F;         s_t[10] = Cc * E;        s_t[11] = s_tf[5];
                     s_trig.srx = B; s_trig.crx = A; s_trig.sry = D; s_trig.cry = Cc; s_trig.srz = F; s_trig.crz = E;   // :1170-1175
                 }
-                double acc[PPL];
+                if (one_round) {
+                    s2m_iter_one_round(a, n, W, iter, s_t, s_trig, s_rows, S, ori_keep, rr_keep, s_todo, &s_ntodo);
+                    if (dbg) a.dbg[iter * 8 + 1] = clock64();
+                    __syncthreads();
+                    if (k16 < S2MP_WARPS) {               // 16 chains x 28 products, chain k takes queries k, k + 16, ... in ascending order
+                        const int nq = min(S2MP_QPB, (n - (int)blockIdx.x + W - 1) / W);
+                        double sacc = 0.0;
+                        for (int q = k16; q < nq; q += S2MP_WARPS) sacc += (double)s_rows[q][pi16] * (double)s_rows[q][pj16];
+                        s_red[k16][p16] = sacc;
+                    }
+                } else {
+                    double acc[PPL];
 #pragma unroll
-                for (int t = 0; t < PPL; ++t) acc[t] = 0.0;
-                if (pg == 16) s2m_query_pass<16>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
-                else if (pg == 8) s2m_query_pass<8>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
-                else s2m_query_pass<4>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
-                if (dbg) a.dbg[iter * 8 + 1] = clock64();
-                // block reduction (fixed tree): lanes 0..3 of the groups of a warp, then across warps
+                    for (int t = 0; t < PPL; ++t) acc[t] = 0.0;
+                    if (pg == 16) s2m_query_pass<16>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
+                    else if (pg == 8) s2m_query_pass<8>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
+                    else s2m_query_pass<4>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
+                    if (dbg) a.dbg[iter * 8 + 1] = clock64();
+                    // block reduction (fixed tree): lanes 0..3 of the groups of a warp, then across warps
 #pragma unroll
-                for (int t = 0; t < PPL; ++t) {                      // lanes 0..3 of every group hold sums; groups are pg lanes apart
-                    if (pg <= 4) acc[t] += __shfl_xor_sync(FULL, acc[t], 4);
-                    if (pg <= 8) acc[t] += __shfl_xor_sync(FULL, acc[t], 8);
-                    acc[t] += __shfl_xor_sync(FULL, acc[t], 16);
-                }
-                if (lane_id() < 4) {
+                    for (int t = 0; t < PPL; ++t) {                      // lanes 0..3 of every group hold sums; groups are pg lanes apart
+                        if (pg <= 4) acc[t] += __shfl_xor_sync(FULL, acc[t], 4);
+                        if (pg <= 8) acc[t] += __shfl_xor_sync(FULL, acc[t], 8);
+                        acc[t] += __shfl_xor_sync(FULL, acc[t], 16);
+                    }
+                    if (lane_id() < 4) {
 #pragma unroll
-                    for (int t = 0; t < PPL; ++t) s_red[warp_id()][gl * PPL + t] = acc[t];
+                        for (int t = 0; t < PPL; ++t) s_red[warp_id()][gl * PPL + t] = acc[t];
+                    }
                 }
                 __syncthreads();
                 if (threadIdx.x < NPROD) {
                     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                     for (int w = 0; w < S2MP_WARPS; w += 4) { s0 += s_red[w][threadIdx.x]; s1 += s_red[w + 1][threadIdx.x]; s2 += s_red[w + 2][threadIdx.x]; s3 += s_red[w + 3][threadIdx.x]; }
-                    __stcg(part + (size_t)blockIdx.x * NPROD + threadIdx.x, (s0 + s1) + (s2 + s3));
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong((s0 + s1) + (s2 + s3));
+                    st_word2(a.wpart + (size_t)blockIdx.x * NPROD + threadIdx.x, (bits & 0xffffffffull) | etag, (bits >> 32) | etag);
                 }
-                __syncthreads();
-                if (dbg) a.dbg[iter * 8 + 2] = clock64();
-                if (threadIdx.x == 0) {
-                    // release: this CTA's partial (ordered before by the barrier) becomes visible with its arrival word
-                    if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + blockIdx.x] = gtimer();
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.arrive + blockIdx.x), "r"(epoch) : "memory");
-                    if (dbg) a.dbg[iter * 8 + 3] = clock64();
-                    unsigned v, spins = 0;
+                if (dbg) { a.dbg[iter * 8 + 2] = clock64(); a.dbg[iter * 8 + 3] = a.dbg[iter * 8 + 2]; }
+                if (threadIdx.x == 0 && a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + blockIdx.x] = gtimer();
+                // the reducer's answer: eight lanes poll one word each (one L2 round trip once it is there)
+                if (threadIdx.x < 8) {
+                    unsigned long long v; unsigned spins = 0;
                     while (true) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag) : "memory");
-                        if (v == epoch) break;
+                        v = ld_word(a.res + threadIdx.x);
+                        if ((unsigned)(v >> 32) == epoch) break;
                         if (++spins > (1u << 26)) { atomicExch(a.err_flag, 2); break; }
                     }
+                    if (threadIdx.x < 6) s_tf[threadIdx.x] = __uint_as_float((unsigned)v);
+                    else if (threadIdx.x == 6) s_conv = (int)(unsigned)v;
                     if (dbg) a.dbg[iter * 8 + 4] = clock64();
-                    if (a.dbg_gt && blockIdx.x == 0 && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 158] = gtimer();
+                    if (a.dbg_gt && blockIdx.x == 0 && threadIdx.x == 0 && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 158] = gtimer();
                 }
-                __syncthreads();
-                if (threadIdx.x < 6) s_tf[threadIdx.x] = __ldcg(&res->tf[threadIdx.x]);
-                if (threadIdx.x == 32) s_conv = __ldcg(&res->conv);
                 __syncthreads();
                 if (dbg) a.dbg[iter * 8 + 5] = clock64();
             } else {
-                // ---- reducer: thread t waits for worker t and pulls its 28 partial sums into shared memory (all workers in
-                // parallel: two L2 round trips after the last arrival, not two per worker); the sums are then taken in a FIXED
-                // order (chunk k = workers k, k + 16, ... sequentially; chunks combined by the 4-chain tree below), so the
-                // result does not depend on the arrival order ----
-                for (int b = threadIdx.x; b < W; b += S2MP_BLOCK) {
-                    unsigned v, spins = 0;
+                // ---- reducer: its threads poll the W x 28 inbox entries in parallel (thread t takes entries t, t + 512, ...; an entry is
+                // complete when both halves carry this iteration's epoch); the sums are then taken in a FIXED order (chunk k = workers
+                // k, k + 16, ... sequentially; chunks combined by the 4-chain tree below), so the result does not depend on the arrival order ----
+                {
+                    const int total = W * NPROD;
+                    bool got[S2M_POLL];
+#pragma unroll
+                    for (int k = 0; k < S2M_POLL; ++k) got[k] = (int)threadIdx.x + k * S2MP_BLOCK >= total;
+                    unsigned spins = 0;
                     while (true) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.arrive + b) : "memory");
-                        if (v == epoch) break;
-                        if (++spins > (1u << 26)) { atomicExch(a.err_flag, 2); break; }
+                        ulonglong2 w2[S2M_POLL];
+#pragma unroll
+                        for (int k = 0; k < S2M_POLL; ++k) if (!got[k]) w2[k] = ld_word2(a.wpart + threadIdx.x + k * S2MP_BLOCK);
+                        bool all = true;
+#pragma unroll
+                        for (int k = 0; k < S2M_POLL; ++k) {
+                            if (got[k]) continue;
+                            if ((unsigned)(w2[k].x >> 32) == epoch && (unsigned)(w2[k].y >> 32) == epoch) {
+                                const int e = (int)threadIdx.x + k * S2MP_BLOCK;
+                                s_part[e % NPROD][e / NPROD] = __longlong_as_double((long long)((w2[k].x & 0xffffffffull) | (w2[k].y << 32)));
+                                got[k] = true;
+                            } else all = false;
+                        }
+                        if (all) break;
+                        if (++spins > (1u << 24)) { atomicExch(a.err_flag, 2); break; }
                     }
-                    const double2* src = reinterpret_cast<const double2*>(part + (size_t)b * NPROD);
-                    double2 vv[NPROD / 2];
-#pragma unroll
-                    for (int k2 = 0; k2 < NPROD / 2; ++k2) vv[k2] = __ldcg(src + k2);
-#pragma unroll
-                    for (int k2 = 0; k2 < NPROD / 2; ++k2) { s_part[2 * k2][b] = vv[k2].x; s_part[2 * k2 + 1][b] = vv[k2].y; }
                 }
                 __syncthreads();
                 if (threadIdx.x < S2MP_WARPS * 32) {
@@ -791,30 +1191,34 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                 }
                 __syncthreads();
                 const long long lc1 = clock64();
-                if (threadIdx.x == 0) {
-                    if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 156] = gtimer();
-                    int nsel;
+                if (threadIdx.x < 32) {
+                    if (threadIdx.x == 0 && a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 156] = gtimer();
+                    int nsel = 0;
                     float tfn[6];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) tfn[k] = s_tf[k];
-                    bool c = lm_solve_dev<true>(iter, s_sum, tfn, &s_st, s_A, s_V, nullptr, nullptr, nullptr, &nsel);
-                    {   // result = 2 x 16-byte stores
-                        float4* r4 = reinterpret_cast<float4*>(res);
-                        __stcg(r4, make_float4(tfn[0], tfn[1], tfn[2], tfn[3]));
-                        __stcg(r4 + 1, make_float4(tfn[4], tfn[5], __int_as_float(c ? 1 : 0), __int_as_float(nsel)));
-                    }
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flag), "r"(epoch) : "memory");
-                    if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 157] = gtimer();
-                    // off the critical path: the workers are already running the next iteration
+                    const bool c = lm_solve_warp<true>(iter, s_sum, tfn, &s_st, s_A, s_V, nsel);
+                    if (threadIdx.x < 8) {          // the answer: eight self-validating words
+                        unsigned pay = 0;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) s_tf[k] = tfn[k];
-                    s_conv = c ? 1 : 0;
-                    if (iter == 0) *a.st = s_st;
-                    if (a.dbg && iter < S2M_MAX_ITERS) { a.dbg[iter * 8 + 6] = lc1 - lc0; a.dbg[iter * 8 + 7] = clock64() - lc1; }
-                    if (a.trace && iter < S2M_MAX_ITERS) {
-                        for (int k = 0; k < 6; ++k) a.trace->pose[iter][k] = tfn[k];
-                        a.trace->nsel[iter] = nsel;
-                        a.trace->degenerate = s_st.isDegenerate;
+                        for (int k = 0; k < 6; ++k) if ((int)threadIdx.x == k) pay = __float_as_uint(tfn[k]);
+                        if (threadIdx.x == 6) pay = c ? 1u : 0u;
+                        if (threadIdx.x == 7) pay = (unsigned)nsel;
+                        st_word(a.res + threadIdx.x, (unsigned long long)pay | etag);
+                    }
+                    if (threadIdx.x == 0) {
+                        if (a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + 157] = gtimer();
+                        // off the critical path: the workers are already running the next iteration
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) s_tf[k] = tfn[k];
+                        s_conv = c ? 1 : 0;
+                        if (iter == 0) *a.st = s_st;
+                        if (a.dbg && iter < S2M_MAX_ITERS) { a.dbg[iter * 8 + 6] = lc1 - lc0; a.dbg[iter * 8 + 7] = clock64() - lc1; }
+                        if (a.trace && iter < S2M_MAX_ITERS) {
+                            for (int k = 0; k < 6; ++k) a.trace->pose[iter][k] = tfn[k];
+                            a.trace->nsel[iter] = nsel;
+                            a.trace->degenerate = s_st.isDegenerate;
+                        }
                     }
                 }
                 __syncthreads();

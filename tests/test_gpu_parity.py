@@ -227,16 +227,38 @@ def test_solver_lane_widths_agree(ctx, oracle, kitti_case):
     tf0 = kitti_case["init"]
     o = oracle.scan2map(ds, o_map, tf0, 30, force_all=True)
     runs = {}
+    ctx.solverGlobalState(True)                      # lane widths belong to the multi-round path
     for lanes in (4, 8, 16):
         ctx.solverLanes(lanes)
         pose, tr = ctx.scan2MapOptimization(tf0, 30, force_all_iters=True)
         runs[lanes] = (tr.poses().copy(), np.array(tr.nsel[:30]))
         assert tr.iters == 30
         assert np.max(np.abs(runs[lanes][0][:, 3:] - o["trace"][:, 3:])) < 1e-4 and np.max(np.abs(runs[lanes][0][:, :3] - o["trace"][:, :3])) < 1e-5
-    ctx.solverLanes(0)
+    ctx.solverLanes(0); ctx.solverGlobalState(False)
     for lanes in (8, 16):
         assert np.array_equal(runs[lanes][1], runs[4][1])
         assert np.max(np.abs(runs[lanes][0] - runs[4][0])) < 2e-6
+
+
+def test_solver_paths_agree(ctx, oracle, kitti_case):
+    """Scans that fit one round of the grid are solved with one thread per query and the query state in shared memory, larger ones
+    with 4 / 8 / 16 lanes per query and the state in global memory.  Forcing the second path on the same instance changes only the
+    order of the fp64 partial sums: identical selected-row counts in all 30 iterations, poses equal to fp32 rounding, both within the
+    north-star tolerance of the oracle."""
+    o_map, ds = _setup_registration(ctx, oracle, kitti_case)
+    tf0 = kitti_case["init"]
+    o = oracle.scan2map(ds, o_map, tf0, 30, force_all=True)
+    runs = []
+    for glob in (False, True):
+        ctx.solverGlobalState(glob)
+        ctx.setLMState(0, np.eye(6, dtype=np.float32))
+        pose, tr = ctx.scan2MapOptimization(tf0, 30, force_all_iters=True)
+        runs.append((tr.poses().copy(), tr.nsels().copy(), pose.copy()))
+        assert tr.iters == 30
+        assert np.max(np.abs(runs[-1][0][:, 3:] - o["trace"][:, 3:])) < 1e-4 and np.max(np.abs(runs[-1][0][:, :3] - o["trace"][:, :3])) < 1e-5
+    ctx.solverGlobalState(False)
+    assert np.array_equal(runs[0][1], runs[1][1])
+    assert np.max(np.abs(runs[0][0] - runs[1][0])) < 2e-6
 
 
 def test_lm_too_few_correspondences(ctx, oracle):
@@ -291,11 +313,13 @@ def test_scan2map_deterministic(ctx, oracle, kitti_case):
 
 
 # ---------------------------------------------------------------------------------------------- solver caches are exact
+@pytest.mark.parametrize("global_state", [False, True])
 @pytest.mark.parametrize("seed", range(6))
-def test_solver_caches_do_not_change_results(kitti_case, seed):
+def test_solver_caches_do_not_change_results(kitti_case, seed, global_state):
     """property test (no oracle needed): the persistent solver with its candidate-list / plane caches must produce the SAME
     trace, bit for bit, as with the caches disabled (full 27-cell search and refit every iteration) — for start poses that
-    push the scan across voxel-cell boundaries between iterations (large perturbations, 30 forced iterations)."""
+    push the scan across voxel-cell boundaries between iterations (large perturbations, 30 forced iterations).  Both solver paths:
+    one thread per query with the state in shared memory (one-round scans) and lanes per query with the state in global memory."""
     import liorf_b200
     rng = np.random.default_rng(100 + seed)
     c = liorf_b200.Context()
@@ -309,6 +333,7 @@ def test_solver_caches_do_not_change_results(kitti_case, seed):
     c.downsampleCurrentScan(want_output=False)
     init = (kitti_case["truth"] + rng.normal(scale=[0.01, 0.01, 0.03, 0.6, 0.6, 0.1])).astype(np.float32)
     traces = []
+    c.solverGlobalState(global_state)
     for no_cache in (False, True):
         c.disableSolverCache(no_cache)
         c.setLMState(0, np.eye(6, dtype=np.float32))

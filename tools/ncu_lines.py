@@ -11,9 +11,12 @@ from collections import defaultdict
 rep, kern = sys.argv[1], sys.argv[2]
 lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "liorf_b200", "lib", "libliorf_b200.so")
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+if lib.endswith(".cubin"):
+    cubin_path = lib
+else:
+    subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    cubin_path = os.path.join(tmp, [f for f in os.listdir(tmp) if f.endswith(".cubin")][0])
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin_path], capture_output=True, text=True).stdout.splitlines()
 # instruction index -> (file, line) for the kernel section
 inside = False; cur = ("?", 0); lines = []
 for ln in dis:
@@ -49,9 +52,10 @@ for k, r in enumerate(rows[hi + 1:]):
     tot += s; toti += ie
 print(f"total samples {tot}, warp instructions {toti}, sass instrs {len(rows) - hi - 1}, disasm instrs {len(lines)}")
 src_cache = {}
-for key, (s, ie, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+by_inst = os.environ.get("NCU_SORT", "samples") == "inst"            # NCU_SORT=inst: order by executed instructions instead of stall samples
+for key, (s, ie, st) in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_inst else 0])[:int(os.environ.get("NCU_TOP", "40"))]:
     f, l = key
-    path = os.path.join(os.path.dirname(lib), "..", "csrc", f)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "liorf_b200", "csrc", f)
     if f not in src_cache:
         try:
             src_cache[f] = open(path).read().splitlines()
