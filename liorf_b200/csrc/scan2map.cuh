@@ -413,7 +413,7 @@ constexpr int PPL = NPROD / 4;              // products per accumulating lane (l
 // rows of CAND_CAP float4 at an odd stride (65: the eight lanes of a quarter warp, one row each, hit eight different 16-byte bank
 // groups), then the four header words of QueryCache as four arrays (lane t reads element t: conflict-free).
 constexpr int S2M_ROW = CAND_CAP + 1;
-constexpr int S2MP_SMEM = S2MP_QPB * (S2M_ROW + 4) * (int)sizeof(float4);          // 141 312 B
+constexpr int S2MP_SMEM = S2MP_QPB * (S2M_ROW + 7) * (int)sizeof(float4);          // 147 456 B (headers: 4 words + a second cached plane of 3)
 
 struct QueryCache {                         // 64 B per query
     float qx, qy, qz; int cnt;              // cached query position q0 and candidate count (-1: none, -2: overflow)
@@ -427,7 +427,6 @@ static_assert(sizeof(S2MMail) == 64, "S2MMail must be 64 bytes");
 
 constexpr int S2M_MAX_WORKERS = 152;    // >= SMs - 1 (B200: 147)
 constexpr int S2M_GT_STRIDE = 160;      // per iteration: [0..W) worker arrival, [156] reducer sums ready, [157] reducer published, [158] worker 0 saw the flag
-constexpr int S2M_POLL = (S2M_MAX_WORKERS * NPROD + S2MP_BLOCK - 1) / S2MP_BLOCK;      // partial-sum words one reducer thread collects
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // Hand-off words between the workers and the reducer.  Every 64-bit word carries 32 bits of payload and, in its upper half, the epoch
@@ -698,9 +697,12 @@ __device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, co
 // bit-identical to the multi-round path; only the order of the fp64 partial sums differs (as it does between lane widths).
 // A list that overflows CAND_CAP (-2) is answered by an exact one-thread walk of the 27 cells (rare: > 64 map points within 1.15 m).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int build_list_warp(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g,
+// Sixteen lanes (one half of a warp) per queued query — the two halves of a warp work on two queries at once, so twice as many
+// dependent L2 round trips (cell bounds → candidate points) are in flight per SM.  Four candidates per lane and step.
+__device__ __forceinline__ int build_list_half(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g,
                                                float4* __restrict__ clist) {
-    const int l = lane_id();
+    const int l = lane_id() & 15, hb = lane_id() & 16;
+    const unsigned gmask = 0xffffu << hb;
     const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
     const int x0 = (cx - 1) & (g.DX - 1), x1 = cx & (g.DX - 1), x2 = (cx + 1) & (g.DX - 1);
     const float r2c = (1.0f + S2M_MARGIN) * (1.0f + S2M_MARGIN);
@@ -716,28 +718,28 @@ __device__ __forceinline__ int build_list_warp(const float4 q, const unsigned* _
         }
         unsigned incl = len;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (l >= o) incl += v; }
+        for (int o = 1; o < 16; o <<= 1) { const unsigned v = __shfl_up_sync(gmask, incl, o, 16); if (l >= o) incl += v; }
         unsigned bs[9], P[10];
         P[0] = 0;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) { bs[r] = __shfl_sync(FULL, b, r); P[r + 1] = __shfl_sync(FULL, incl, r); }
+        for (int r = 0; r < 9; ++r) { bs[r] = __shfl_sync(gmask, b, r, 16); P[r + 1] = __shfl_sync(gmask, incl, r, 16); }
         const unsigned T = P[9];
         for (unsigned f0 = 0; f0 < T; f0 += 64) {
-            float4 p[2];
+            float4 p[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const unsigned f = f0 + 32 * u + l;
+            for (int u = 0; u < 4; ++u) {
+                const unsigned f = f0 + 16 * u + l;
                 unsigned base = bs[0], pb = 0;
 #pragma unroll
                 for (int rr = 1; rr < 9; ++rr) if (f >= P[rr]) { base = bs[rr]; pb = P[rr]; }
                 p[u] = f < T ? __ldg(gmap + base + (f - pb)) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 float dx = q.x - p[u].x, dy = q.y - p[u].y, dz = q.z - p[u].z;
                 float d = dx * dx; d += dy * dy; d += dz * dz;      // FLANN L2_Simple op order, no FMA
                 const bool keep = d < r2c;
-                const unsigned km = __ballot_sync(FULL, keep);
+                const unsigned km = (__ballot_sync(gmask, keep) >> hb) & 0xffffu;
                 const int slot = ncache + __popc(km & lt);
                 if (keep && slot < CAND_CAP) clist[slot] = p[u];
                 ncache += __popc(km);
@@ -751,13 +753,13 @@ __device__ __forceinline__ int build_list_warp(const float4 q, const unsigned* _
             const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
             const int xc = xi == 0 ? x0 : (xi == 1 ? x1 : x2);
             const unsigned b = __ldg(cell_start + row + xc), e = __ldg(cell_start + row + xc + 1);
-            for (unsigned f0 = b; f0 < e; f0 += 32) {
+            for (unsigned f0 = b; f0 < e; f0 += 16) {
                 const unsigned f = f0 + l;
                 const float4 pt = f < e ? __ldg(gmap + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
                 float dx = q.x - pt.x, dy2 = q.y - pt.y, dz2 = q.z - pt.z;
                 float d = dx * dx; d += dy2 * dy2; d += dz2 * dz2;
                 const bool keep = d < r2c;
-                const unsigned km = __ballot_sync(FULL, keep);
+                const unsigned km = (__ballot_sync(gmask, keep) >> hb) & 0xffffu;
                 const int slot = ncache + __popc(km & lt);
                 if (keep && slot < CAND_CAP) clist[slot] = pt;
                 ncache += __popc(km);
@@ -785,7 +787,10 @@ __device__ __noinline__ void knn5_lane(const float4 q, const unsigned* __restric
 
 struct S2MShared {                      // views into the dynamic shared memory of a one-round worker
     float4* list;                       // [S2MP_QPB][S2M_ROW]
-    float4* h0; float4* h1; float4* h2; float4* h3;      // [S2MP_QPB] each: QueryCache's four 16-byte words; h3.z = list positions of the current top-5 (6 bits each)
+    float4* h0; float4* h1; float4* h2; float4* h3;      // [S2MP_QPB] each: QueryCache's four 16-byte words; h3.z = list positions of the current top-5 (6 bits each),
+                                                         // h3.w = which of the two cached planes was used last
+    float4* g1; float4* g2; float4* g3;                  // a SECOND cached plane (ids, validity, coefficients): a query whose 5th / 6th neighbours are
+                                                         // nearly equidistant flips between two neighbour lists as the pose settles — one refit each, not one per iteration
 };
 
 // (distance, original index) as ONE unsigned 64-bit key: squared distances are non-negative floats, whose bit patterns order like the
@@ -797,30 +802,38 @@ __device__ __forceinline__ float sqdist_dev(const float4 q, const float4 p) {
     return d;
 }
 
-// phase 2 epilogue, one warp: list positions of the five smallest keys of a freshly built list (cnt >= 5), packed 6 bits each, smallest
-// first — the prior that phase 3 verifies from now on
-__device__ __forceinline__ unsigned top5_positions_warp(const float4 q, const float4* __restrict__ row, int cnt) {
-    const int l = lane_id();
-    unsigned long long kA = ~0ull, kB = ~0ull;
-    if (l < cnt) { const float4 p = row[l]; kA = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
-    if (l + 32 < cnt) { const float4 p = row[l + 32]; kB = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
+// phase 2 epilogue, one half warp: list positions of the five smallest keys of a freshly built list (cnt >= 5), packed 6 bits each,
+// smallest first — the prior that phase 3 verifies from now on.  Lane l holds entries l, l + 16, l + 32, l + 48.
+__device__ __forceinline__ unsigned top5_positions_half(const float4 q, const float4* __restrict__ row, int cnt) {
+    const int l = lane_id() & 15, hb = lane_id() & 16;
+    const unsigned gmask = 0xffffu << hb;
+    unsigned long long k4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        k4[u] = ~0ull;
+        if (l + 16 * u < cnt) { const float4 p = row[l + 16 * u]; k4[u] = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
+    }
     unsigned packed = 0;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
-        const unsigned long long mine = kA < kB ? kA : kB;
+        unsigned long long mine = k4[0]; int mu = 0;
+#pragma unroll
+        for (int u = 1; u < 4; ++u) if (k4[u] < mine) { mine = k4[u]; mu = u; }
         unsigned long long m = mine;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(FULL, m, o); m = v < m ? v : m; }
-        const int owner = __ffs(__ballot_sync(FULL, mine == m)) - 1;          // keys are unique (distinct original indices)
-        const int pos = kA < kB ? l : l + 32;
-        packed |= (unsigned)__shfl_sync(FULL, pos, owner) << (6 * r);
-        if (l == owner) { if (kA < kB) kA = ~0ull; else kB = ~0ull; }
+        for (int o = 8; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(gmask, m, o, 16); m = v < m ? v : m; }
+        const int owner = __ffs((__ballot_sync(gmask, mine == m) >> hb) & 0xffffu) - 1;          // keys are unique (distinct original indices)
+        packed |= (unsigned)__shfl_sync(gmask, l + 16 * mu, owner, 16) << (6 * r);
+        if (l == owner) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (u == mu) k4[u] = ~0ull;
+        }
     }
     return packed;
 }
 
 __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n, const int W, const int iter, const float (&s_t)[12], const LMTrig& s_trig,
-                                                   float (*s_rows)[8], const S2MShared& S, const float4 ori, const float rr, int* s_todo, int* s_ntodo) {
+                                                   float (*s_rows)[8], const S2MShared& S, const float4 ori, const float rr, int* s_todo, int* s_ntodo, long long* dbg_p2) {
     const int tid = threadIdx.x;
     const bool mine = tid < S2MP_QPB && tid * W + (int)blockIdx.x < n;
     float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -835,26 +848,28 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
         const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
         const bool valid = iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
         if (!valid) { s_todo[atomicAdd(s_ntodo, 1)] = tid; S.h0[tid] = make_float4(sel.x, sel.y, sel.z, __int_as_float(-1)); }
+        if (a.dbg_gt && !valid && iter >= 10) atomicAdd(a.dbg_gt + 40 * S2M_GT_STRIDE + blockIdx.x, 1ull);
         // iteration 0 never trusts a cached plane (it belongs to an earlier launch / another map)
-        if (iter == 0) S.h1[tid] = make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1));
+        if (iter == 0) { S.h1[tid] = make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)); S.g1[tid] = S.h1[tid]; }
     }
     __syncthreads();
-    // ---- 2. one warp per queued query rebuilds its list around the new q0 and leaves the positions of its five nearest entries ----
+    // ---- 2. one half warp per queued query rebuilds its list around the new q0 and leaves the positions of its five nearest entries ----
     const int ntodo = *s_ntodo;
-    for (int k = warp_id(); k < ntodo; k += S2MP_WARPS) {
+    for (int k = 2 * warp_id() + (lane_id() >> 4); k < ntodo; k += 2 * S2MP_WARPS) {       // the two halves of a warp take one query each
         const int slot = s_todo[k];
         const float4 q0 = S.h0[slot];
         float4* row = S.list + slot * S2M_ROW;
-        const int c = build_list_warp(q0, a.cell_start, a.gmap, a.g, row);
-        __syncwarp();
+        const int c = build_list_half(q0, a.cell_start, a.gmap, a.g, row);
+        __syncwarp(0xffffu << (lane_id() & 16));
         unsigned packed = 0;
-        if (c >= 5) packed = top5_positions_warp(q0, row, c);
-        if (lane_id() == 0) {
+        if (c >= 5) packed = top5_positions_half(q0, row, c);
+        if ((lane_id() & 15) == 0) {
             S.h0[slot] = make_float4(q0.x, q0.y, q0.z, __int_as_float(c));
             float4 h3 = S.h3[slot]; h3.z = __uint_as_float(packed); S.h3[slot] = h3;
         }
     }
     __syncthreads();
+    if (dbg_p2) *dbg_p2 = clock64();
     if (tid == 0) *s_ntodo = 0;                  // the next iteration's phase 1 is at least two barriers away
     // ---- 3. exact 5-NN from the list, plane, weight, Jacobian row ----
     if (tid < S2MP_QPB) {
@@ -880,22 +895,37 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                 unsigned long long thr = ck[0];
 #pragma unroll
                 for (int j = 1; j < 5; ++j) thr = ck[j] > thr ? ck[j] : thr;
-                unsigned long long mask = 0;
+                unsigned long long mask = 0; int n1 = 0;                 // n1: entries within 1 m — fewer than five ⇒ no plane (:1097), nothing to order
                 for (int f0 = 0; f0 < cnt; f0 += 4) {
                     float4 p[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) p[u] = row[f0 + u];          // the row is padded: entries past cnt are read but masked out
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const unsigned long long k = nn_key(sqdist_dev(sel, p[u]), __float_as_int(p[u].w));
+                        const float d = sqdist_dev(sel, p[u]);
+                        const unsigned long long k = nn_key(d, __float_as_int(p[u].w));
                         mask |= (unsigned long long)((k <= thr) && (f0 + u < cnt)) << (f0 + u);
+                        n1 += (d < 1.0f) && (f0 + u < cnt);
                     }
                 }
                 const bool sorted = ck[0] < ck[1] && ck[1] < ck[2] && ck[2] < ck[3] && ck[3] < ck[4];
-                if (__popcll(mask) == 5 && sorted && cd[4] < 1.0f) {
+                if (n1 < 5) {
+                    // nn stays empty
+                } else if (__popcll(mask) == 5 && sorted && cd[4] < 1.0f) {
 #pragma unroll
                     for (int j = 0; j < 5; ++j) { nn.d[j] = cd[j]; nn.oi[j] = coi[j]; nn.pos[j] = cpos[j]; }
+                } else if (__popcll(mask) == 5 && cd[0] < 1.0f && cd[1] < 1.0f && cd[2] < 1.0f && cd[3] < 1.0f && cd[4] < 1.0f) {
+                    // the same five in a different order: a 9-exchange sorting network on the keys instead of an insertion pass
+#define S2M_CE(i, j) if (ck[j] < ck[i]) { const unsigned long long tk = ck[i]; ck[i] = ck[j]; ck[j] = tk; const float td = cd[i]; cd[i] = cd[j]; cd[j] = td; \
+                                           const int to = coi[i]; coi[i] = coi[j]; coi[j] = to; const int tp = cpos[i]; cpos[i] = cpos[j]; cpos[j] = tp; }
+                    S2M_CE(0, 1) S2M_CE(3, 4) S2M_CE(2, 4) S2M_CE(2, 3) S2M_CE(1, 4) S2M_CE(0, 3) S2M_CE(0, 2) S2M_CE(1, 3) S2M_CE(1, 2)
+#undef S2M_CE
+                    pk = 0;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { nn.d[j] = cd[j]; nn.oi[j] = coi[j]; nn.pos[j] = cpos[j]; pk |= (unsigned)cpos[j] << (6 * j); }
+                    float4 h3n = h3; h3n.z = __uint_as_float(pk); S.h3[tid] = h3n;
                 } else {
+                    if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 41 * S2M_GT_STRIDE + blockIdx.x, 1ull);
                     while (mask) {
                         const int i = __ffsll((long long)mask) - 1; mask &= mask - 1;
                         const float4 p = row[i];
@@ -909,14 +939,18 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                         float4 h3n = h3; h3n.z = __uint_as_float(pk); S.h3[tid] = h3n;
                     }
                 }
-            } else if (cnt == -2) knn5_lane(sel, a.cell_start, a.gmap, a.g, nn);
+            } else if (cnt == -2) { knn5_lane(sel, a.cell_start, a.gmap, a.g, nn); if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 43 * S2M_GT_STRIDE + blockIdx.x, 1ull); }
             const bool have5 = nn.pos[4] != -1 && (double)nn.d[4] < 1.0;                // :1097
             if (have5) {
-                const float4 h1 = S.h1[tid], h2 = S.h2[tid];
-                const bool same = iter > 0 && !a.no_cache && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
-                                  __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
+                const float4 h1 = S.h1[tid], h2 = S.h2[tid], g1 = S.g1[tid], g2 = S.g2[tid];
+                const bool use = iter > 0 && !a.no_cache;
+                const bool same0 = use && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
+                                   __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
+                const bool same1 = use && __float_as_int(g1.x) == nn.oi[0] && __float_as_int(g1.y) == nn.oi[1] && __float_as_int(g1.z) == nn.oi[2] &&
+                                   __float_as_int(g1.w) == nn.oi[3] && __float_as_int(g2.x) == nn.oi[4];
                 float pa, pb, pc, pd; bool planeValid;
-                if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
+                if (same0) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = S.h3[tid].x; pd = S.h3[tid].y; }
+                else if (same1) { const float4 g3 = S.g3[tid]; planeValid = __float_as_int(g2.y) != 0; pa = g2.z; pb = g2.w; pc = g3.x; pd = g3.y; }
                 else {
                     float A[5][3];
 #pragma unroll
@@ -925,6 +959,7 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                         A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z;
                     }
                     float x[3];
+                    if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 42 * S2M_GT_STRIDE + blockIdx.x, 1ull);
                     colpiv_qr_solve_5x3(A, x);                                           // :1104
                     pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
                     float ps = sqrtf(pa * pa + pb * pb + pc * pc);                       // :1111
@@ -933,9 +968,19 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
 #pragma unroll
                     for (int j = 0; j < 5; ++j)                                          // :1115-1122
                         if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
-                    S.h1[tid] = make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3]));
-                    S.h2[tid] = make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb);
-                    float4 h3n = S.h3[tid]; h3n.x = pc; h3n.y = pd; S.h3[tid] = h3n;
+                    // replace the plane that was NOT used last
+                    float4 h3n = S.h3[tid];
+                    const bool into1 = __float_as_int(h3n.w) == 0;
+                    const float4 n1v = make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3]));
+                    const float4 n2v = make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb);
+                    if (into1) { S.g1[tid] = n1v; S.g2[tid] = n2v; S.g3[tid] = make_float4(pc, pd, 0.f, 0.f); h3n.w = __int_as_float(1); }
+                    else { S.h1[tid] = n1v; S.h2[tid] = n2v; h3n.x = pc; h3n.y = pd; h3n.w = __int_as_float(0); }
+                    S.h3[tid] = h3n;
+                }
+                if (same0 || same1) {
+                    const int used = same0 ? 0 : 1;
+                    float4 h3n = S.h3[tid];
+                    if (__float_as_int(h3n.w) != used) { h3n.w = __int_as_float(used); S.h3[tid] = h3n; }
                 }
                 if (planeValid) {
                     float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;               // :1125
@@ -1036,7 +1081,6 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     __shared__ float s_A[36], s_V[36];
     __shared__ LMDeviceState s_st;
     __shared__ int s_conv;
-    __shared__ double s_part[NPROD][S2M_MAX_WORKERS];      // reducer only: the workers' partial sums, component-major
 
     // Roles: CTAs 0 .. W-1 are WORKERS (queries), the last CTA is the REDUCER: it owns the LM state, sums the workers'
     // partials in CTA order as they arrive, solves the 6x6 system and publishes (pose, converged).  A fixed reducer keeps the
@@ -1050,7 +1094,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     // lanes per query: the widest group that covers the scan in one round of the workers (same choice in every CTA)
     const int pg = a.force_pg ? a.force_pg : (n <= W * (S2MP_BLOCK / 16) ? 16 : (n <= W * (S2MP_BLOCK / 8) ? 8 : 4));
     const bool one_round = !a.global_state && n <= W * S2MP_QPB;              // one thread per query, state in registers / shared memory
-    S2MShared S; S.list = s_state; S.h0 = s_state + S2MP_QPB * S2M_ROW; S.h1 = S.h0 + S2MP_QPB; S.h2 = S.h1 + S2MP_QPB; S.h3 = S.h2 + S2MP_QPB;
+    S2MShared S; S.list = s_state; S.h0 = s_state + S2MP_QPB * S2M_ROW; S.h1 = S.h0 + S2MP_QPB; S.h2 = S.h1 + S2MP_QPB; S.h3 = S.h2 + S2MP_QPB; S.g1 = S.h3 + S2MP_QPB; S.g2 = S.g1 + S2MP_QPB; S.g3 = S.g2 + S2MP_QPB;
     const int gl = threadIdx.x & (pg - 1);              // lane within the query group; lanes 0..3 own 7 products each
     if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
     if (threadIdx.x == 32) { s_conv = 0; s_ntodo = 0; }
@@ -1090,7 +1134,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                     s_trig.srx = B; s_trig.crx = A; s_trig.sry = D; s_trig.cry = Cc; s_trig.srz = F; s_trig.crz = E;   // :1170-1175
                 }
                 if (one_round) {
-                    s2m_iter_one_round(a, n, W, iter, s_t, s_trig, s_rows, S, ori_keep, rr_keep, s_todo, &s_ntodo);
+                    s2m_iter_one_round(a, n, W, iter, s_t, s_trig, s_rows, S, ori_keep, rr_keep, s_todo, &s_ntodo, dbg ? a.dbg + iter * 8 + 3 : nullptr);
                     if (dbg) a.dbg[iter * 8 + 1] = clock64();
                     __syncthreads();
                     if (k16 < S2MP_WARPS) {               // 16 chains x 28 products, chain k takes queries k, k + 16, ... in ascending order
@@ -1127,7 +1171,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                     const unsigned long long bits = (unsigned long long)__double_as_longlong((s0 + s1) + (s2 + s3));
                     st_word2(a.wpart + (size_t)blockIdx.x * NPROD + threadIdx.x, (bits & 0xffffffffull) | etag, (bits >> 32) | etag);
                 }
-                if (dbg) { a.dbg[iter * 8 + 2] = clock64(); a.dbg[iter * 8 + 3] = a.dbg[iter * 8 + 2]; }
+                if (dbg) a.dbg[iter * 8 + 2] = clock64();
                 if (threadIdx.x == 0 && a.dbg_gt && iter < S2M_MAX_ITERS) a.dbg_gt[iter * S2M_GT_STRIDE + blockIdx.x] = gtimer();
                 // the reducer's answer: eight lanes poll one word each (one L2 round trip once it is there)
                 if (threadIdx.x < 8) {
@@ -1145,40 +1189,34 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                 __syncthreads();
                 if (dbg) a.dbg[iter * 8 + 5] = clock64();
             } else {
-                // ---- reducer: its threads poll the W x 28 inbox entries in parallel (thread t takes entries t, t + 512, ...; an entry is
-                // complete when both halves carry this iteration's epoch); the sums are then taken in a FIXED order (chunk k = workers
-                // k, k + 16, ... sequentially; chunks combined by the 4-chain tree below), so the result does not depend on the arrival order ----
+                // ---- reducer: warp k polls the inboxes of workers k, k + 16, ... (lane = product; an entry is complete when both halves
+                // carry this iteration's epoch; only the missing ones are re-read) and sums them in that FIXED order; the 16 chunk sums are
+                // combined by the 4-chain tree below, so the result does not depend on the arrival order ----
                 {
-                    const int total = W * NPROD;
-                    bool got[S2M_POLL];
+                    constexpr int MAXB = (S2M_MAX_WORKERS + S2MP_WARPS - 1) / S2MP_WARPS;
+                    const int wk = warp_id(), pl = lane_id();
+                    ulonglong2 w2[MAXB]; bool got[MAXB];
 #pragma unroll
-                    for (int k = 0; k < S2M_POLL; ++k) got[k] = (int)threadIdx.x + k * S2MP_BLOCK >= total;
+                    for (int j = 0; j < MAXB; ++j) got[j] = !(wk + S2MP_WARPS * j < W && pl < NPROD);
                     unsigned spins = 0;
                     while (true) {
-                        ulonglong2 w2[S2M_POLL];
 #pragma unroll
-                        for (int k = 0; k < S2M_POLL; ++k) if (!got[k]) w2[k] = ld_word2(a.wpart + threadIdx.x + k * S2MP_BLOCK);
+                        for (int j = 0; j < MAXB; ++j) if (!got[j]) w2[j] = ld_word2(a.wpart + (size_t)(wk + S2MP_WARPS * j) * NPROD + pl);
                         bool all = true;
 #pragma unroll
-                        for (int k = 0; k < S2M_POLL; ++k) {
-                            if (got[k]) continue;
-                            if ((unsigned)(w2[k].x >> 32) == epoch && (unsigned)(w2[k].y >> 32) == epoch) {
-                                const int e = (int)threadIdx.x + k * S2MP_BLOCK;
-                                s_part[e % NPROD][e / NPROD] = __longlong_as_double((long long)((w2[k].x & 0xffffffffull) | (w2[k].y << 32)));
-                                got[k] = true;
-                            } else all = false;
+                        for (int j = 0; j < MAXB; ++j) {
+                            if (got[j]) continue;
+                            if ((unsigned)(w2[j].x >> 32) == epoch && (unsigned)(w2[j].y >> 32) == epoch) got[j] = true; else all = false;
                         }
                         if (all) break;
                         if (++spins > (1u << 24)) { atomicExch(a.err_flag, 2); break; }
                     }
-                }
-                __syncthreads();
-                if (threadIdx.x < S2MP_WARPS * 32) {
-                    const int k = threadIdx.x >> 5, c = threadIdx.x & 31;        // chunk k, component c
-                    if (c < NPROD) {
+                    if (pl < NPROD) {
                         double s0 = 0;
-                        for (int b = k; b < W; b += S2MP_WARPS) s0 += s_part[c][b];
-                        s_red[k][c] = s0;
+#pragma unroll
+                        for (int j = 0; j < MAXB; ++j)
+                            if (wk + S2MP_WARPS * j < W) s0 += __longlong_as_double((long long)((w2[j].x & 0xffffffffull) | (w2[j].y << 32)));
+                        s_red[wk][pl] = s0;
                     }
                 }
                 __syncthreads();

@@ -58,14 +58,42 @@ def main():
     buf = (C.c_longlong * 512)()
     ctx.lib.liorf_debug_s2m_clocks(ctx.h, 1, buf)
     full = np.array(list(buf), np.int64).reshape(64, 8)[:30]
-    d = full[:, :6]
+    d = full[:, [0, 3, 1, 2, 4, 5]]              # start, lists rebuilt (phases 1 + 2), rows done (phase 3), partial published, answer seen, broadcast
     ph = np.diff(d, axis=1)
     print(f"last CTA: sum partials {np.median(full[1:, 6]):.0f} cyc, solve+publish {np.median(full[1:, 7]):.0f} cyc (iter0: {full[0, 6]}, {full[0, 7]})")
-    names = ["loop(knn+fit)", "block reduce", "arrive", "wait for flag", "read result"]
+    names = ["check + rebuild", "5-NN + rows", "products", "wait for answer", "broadcast"]
     print("phase cycles (median over iterations 1..29), CTA 0:")
     for k, nme in enumerate(names):
         print(f"   {nme:14s} {np.median(ph[1:, k]):9.0f} cyc   iter0 {ph[0, k]:9.0f}")
     print(f"   per-iteration total {np.median(d[2:, 0] - d[1:-1, 0]):9.0f} cyc")
+    for k in range(6):
+        print(f"   iteration {k}: " + "  ".join(f"{nme} {ph[k, j]}" for j, nme in enumerate(names)))
+    # %globaltimer timeline: arrival spread of the workers, reducer latency, flag propagation
+    ctx.lib.liorf_debug_s2m_clocks(ctx.h, 0, None)
+    ctx.lib.liorf_debug_s2m_arrivals(ctx.h, 1, None)
+    ctx.scan2MapOptimizationAsync(init, 30, True); ctx.getPose()
+    gb = (C.c_ulonglong * (64 * 160))()
+    ctx.lib.liorf_debug_s2m_arrivals(ctx.h, 1, gb)
+    g = np.array(list(gb), np.int64).reshape(64, 160)
+    W = int(np.count_nonzero(g[1, :156]))
+    ev = g[40:44, :W]
+    print("   events over iterations 10..29 (all workers): list rebuilds %d, ordered insert passes %d, plane refits %d, one-thread searches %d" % tuple(ev.sum(1)))
+    for nm, row in zip(["rebuilds", "insert passes", "refits", "one-thread searches"], ev):
+        top = np.argsort(row)[-3:][::-1]
+        print(f"      most {nm}: " + ", ".join(f"worker {int(w)}: {int(row[w])}" for w in top))
+    prev_pub = None
+    for k in range(30):
+        arr = g[k, :W]; ready, pub, seen = g[k, 156], g[k, 157], g[k, 158]
+        base = prev_pub if prev_pub is not None else arr.min()
+        a = np.sort(arr - base) / 1e3
+        if k < 8 or k % 5 == 0:
+            print(f"   iter {k:2d}: arrivals after previous publish: first {a[0]:6.1f}  p50 {a[len(a) // 2]:6.1f}  p90 {a[int(len(a) * 0.9)]:6.1f}  last {a[-1]:6.1f} us;"
+                  f"  last arrival -> sums ready {(ready - arr.max()) / 1e3:5.1f};  solve+publish {(pub - ready) / 1e3:5.1f};  publish -> worker 0 sees it {(seen - pub) / 1e3:5.1f};"
+                  f"  iteration {((pub - base) / 1e3):6.1f} us")
+        if k == 10:
+            late = np.argsort(arr)[-5:]
+            print("      latest workers of iteration 10:", [(int(w), round(float(arr[w] - base) / 1e3, 1)) for w in late])
+        prev_pub = pub
     ctx.close()
 
 
