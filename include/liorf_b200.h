@@ -323,7 +323,6 @@ long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels
 int liorf_get_last_counts(liorf_ctx* ctx, int* n_scan, int* n_ds, int* m_ds, int* iters);   /* as of the last liorf_get_pose */
 int liorf_debug_qr_solve6(liorf_ctx* ctx, const float* A, const float* b, int n, float* x);   /* tests: the device routine behind cv::solve(DECOMP_QR) 6x6 (src/mapOptmization.cpp:1240) */
 int liorf_debug_force_large_voxelgrid(liorf_ctx* ctx, int on);   /* tests: multi-kernel VoxelGrid path on small clouds too */
-int liorf_debug_s2m_lanes(liorf_ctx* ctx, int lanes);              /* tests: lanes per query in the solver (4 / 8 / 16, 0 = automatic) */
 int liorf_debug_s2m_global_state(liorf_ctx* ctx, int on);          /* tests: solver keeps per-query state in global memory (the multi-round layout) */
 int liorf_debug_s2m_disable_cache(liorf_ctx* ctx, int on);        /* tests: full 27-cell search + plane refit every iteration */
 int liorf_debug_s2m_clocks(liorf_ctx* ctx, int enable, long long* out /* 64*8, nullable */);

@@ -370,9 +370,6 @@ class Context:
         _chk(self.lib.liorf_debug_qr_solve6(self.h, _vp(A), _vp(b), C.c_int(len(A)), _vp(x)), "liorf_debug_qr_solve6")
         return x
 
-    def solverLanes(self, lanes=0):
-        _chk(self.lib.liorf_debug_s2m_lanes(self.h, C.c_int(int(lanes))), "liorf_debug_s2m_lanes")
-
     def solverGlobalState(self, on=True):
         _chk(self.lib.liorf_debug_s2m_global_state(self.h, C.c_int(int(on))), "liorf_debug_s2m_global_state")
 

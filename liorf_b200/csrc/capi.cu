@@ -87,7 +87,7 @@ struct liorf_ctx {
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; ulonglong2* d_wpart = nullptr; unsigned long long* d_res = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
     DevBuf<QueryCache> qcache; DevBuf<float4> cand; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; bool s2m_global_state = false;
-    int s2m_grid = 0; bool s2m_no_cache = false; int s2m_force_pg = 0;
+    int s2m_grid = 0; bool s2m_no_cache = false;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
     float* d_lm_out = nullptr;      // AtA[36] AtB[6] X[6]
@@ -920,14 +920,14 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined
     }
     int rc;
     const size_t qb = (size_t)(c->n_scan_bound > 0 ? c->n_scan_bound : 1);
-    if ((rc = c->qcache.reserve(qb)) || (rc = c->cand.reserve(qb * CAND_CAP))) return rc;
+    if ((rc = c->qcache.reserve(qb)) || (rc = c->cand.reserve(qb * S2M_GROW))) return rc;
     if ((rc = join_map(c))) return rc;
     S2MArgs a;
     a.qcache = c->qcache.p; a.cand = c->cand.p; a.res = c->d_res; a.wpart = c->d_wpart; a.err_flag = c->d_err; a.global_state = c->s2m_global_state ? 1 : 0;
     a.epoch_base = (++c->s2m_launch_seq) * 64u;
     a.scan = c->scan_ds.p; a.n_scan = scan_ds_count(c);
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
-    a.tf6 = c->d_tf6; a.st = c->d_lm; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.force_pg = c->s2m_force_pg; a.dbg = c->d_dbg; a.dbg_gt = c->d_dbg_gt;
+    a.tf6 = c->d_tf6; a.st = c->d_lm; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.dbg = c->d_dbg; a.dbg_gt = c->d_dbg_gt;
     a.mail = c->d_mail; a.cnt_n_scan = c->d_counts + C_N_SCAN;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
@@ -2004,7 +2004,7 @@ int liorf_reserve(liorf_ctx* c, int n_scan_max, int m_raw_max, int n_keyframe_po
     }
     if ((rc = c->membership.reserve(big)) || (rc = c->out_keys.reserve(big)) ||
         (rc = c->map_raw.reserve(m)) || (rc = c->map_ds.reserve(m)) || (rc = c->grid.sorted.reserve(m)) ||
-        (rc = c->qcache.reserve(n)) || (rc = c->cand.reserve(n * CAND_CAP)) || (rc = c->d_sel.reserve(4096)) ||
+        (rc = c->qcache.reserve(n)) || (rc = c->cand.reserve((size_t)n * S2M_GROW)) || (rc = c->d_sel.reserve(4096)) ||
         (rc = c->vg_map.keys.reserve(m)) || (rc = c->vg_map.seg_start.reserve(m + 1)) || (rc = c->vg_map.partial.reserve((size_t)kNumSMs * 6)) ||
         (rc = c->vg_map.sort.keys_alt.reserve(m)) || (rc = c->vg_map.sort.vals_a.reserve(m)) || (rc = c->vg_map.sort.vals_b.reserve(m)) ||
         (rc = c->vg_map.sort.hist.reserve(4 * RADIX)) ||
@@ -2062,13 +2062,6 @@ int liorf_debug_s2m_global_state(liorf_ctx* c, int on) {
     LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     c->s2m_global_state = on != 0;
-    return LIORF_OK;
-}
-/* tests: lanes per query of the persistent solver (4, 8 or 16); 0 = automatic (the widest group that covers the scan in one round) */
-int liorf_debug_s2m_lanes(liorf_ctx* c, int lanes) {
-    LIORF_NVTX;
-    if (!c || !(lanes == 0 || lanes == 4 || lanes == 8 || lanes == 16)) return LIORF_ERR_ARG;
-    c->s2m_force_pg = lanes;
     return LIORF_OK;
 }
 /* debug: %globaltimer stamps of the last solve, out[iter * 160 + k]: k < workers = that worker's arrival, 156 = reducer sums

@@ -402,25 +402,22 @@ __global__ void __launch_bounds__(256) k_lm_hook(int iter, const float4* __restr
 // sums the partials in CTA order (deterministic whoever is last), solves the 6x6 system, publishes (pose, converged)
 // and releases an epoch flag the other CTAs spin on (bounded).  This replaces grid.sync + 148 redundant sums/solves.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PG_MIN = 4;                   // FEWEST lanes per query in the persistent solver (large scans); small scans get 8 or 16
-constexpr int S2MP_BLOCK = 512;             // one CTA per SM: grid x 128 queries per round at 4 lanes per query
-constexpr int S2MP_QPB = S2MP_BLOCK / PG_MIN;
+constexpr int S2MP_BLOCK = 512;             // one CTA per SM
+constexpr int S2MP_QPB = 128;               // queries per worker and round: one thread each (the first four warps); all 16 warps rebuild lists / sum products
 constexpr int S2MP_WARPS = S2MP_BLOCK / 32;
 constexpr int CAND_CAP = 64;                // cached candidates per query (float4 each); overflow → always full search
 constexpr float S2M_MARGIN = 0.15f;
-constexpr int PPL = NPROD / 4;              // products per accumulating lane (lanes 0..3 of a group: 28 / 4 = 7)
 // Shared-memory query state of one-round solves (n <= workers x 128: ONE thread serves the same query in every iteration): candidate
 // rows of CAND_CAP float4 at an odd stride (65: the eight lanes of a quarter warp, one row each, hit eight different 16-byte bank
 // groups), then the four header words of QueryCache as four arrays (lane t reads element t: conflict-free).
 constexpr int S2M_ROW = CAND_CAP + 1;
 constexpr int S2MP_SMEM = S2MP_QPB * (S2M_ROW + 7) * (int)sizeof(float4);          // 147 456 B (headers: 4 words + a second cached plane of 3)
 
-struct QueryCache {                         // 64 B per query
-    float qx, qy, qz; int cnt;              // cached query position q0 and candidate count (-1: none, -2: overflow)
-    int nn[5]; int plane_ok;                // ordered neighbour ids of the cached plane (-1: none), planeValid
-    float pa, pb, pc, pd; int pad0, pad1;
-};
-static_assert(sizeof(QueryCache) == 64, "QueryCache must be 64 bytes");
+struct QueryCache {                         // 128 B per query (global-memory layout; shared memory holds the same seven words as seven arrays)
+    float4 w[8];                            // 0: q0.xyz, candidate count (-1 none, -2 overflow) | 1: plane A ids 0..3 | 2: id 4, valid, pa, pb |
+};                                          // 3: pc, pd, top-5 list positions, plane used last | 4..6: plane B (ids | id 4, valid, pa, pb | pc, pd) | 7: unused
+static_assert(sizeof(QueryCache) == 128, "QueryCache must be 128 bytes");
+constexpr int S2M_GROW = CAND_CAP + 4;      // global candidate rows: 64 entries + padding for the 4-wide scan
 
 struct alignas(16) S2MMail { float tf[6]; int iters, converged, degenerate, ran, n_scan, n_ds, m_ds, err; int pad[2]; };
 static_assert(sizeof(S2MMail) == 64, "S2MMail must be 64 bytes");
@@ -451,13 +448,12 @@ struct S2MArgs {
     ulonglong2* wpart;               // [workers][NPROD]: a worker's partial sums, each fp64 as two epoch-tagged words
     S2MTrace* trace;
     int max_iters; int force_all;
-    int force_pg;                    // tests: lanes per query (4, 8 or 16); 0 = automatic
     int no_cache;                    // tests: 1 = never reuse candidate lists / planes (every iteration searches the 27 cells and refits)
-    int global_state;                // tests: 1 = per-query state in global memory even when the scan fits one round
+    int global_state;                // tests: 1 = per-query state in global memory even when the scan fits one round (the layout of multi-round solves)
     long long* dbg;                  // optional [S2M_MAX_ITERS][8] clock64 phase stamps of CTA 0 (nullptr = off)
     unsigned long long* dbg_gt;      // optional [S2M_MAX_ITERS][S2M_GT_STRIDE] %globaltimer stamps: worker arrivals, flag seen by worker 0, reducer sum-ready / published
     QueryCache* qcache;              // [n_scan bound]   (multi-round solves)
-    float4* cand;                    // [n_scan bound][CAND_CAP]
+    float4* cand;                    // [n_scan bound][S2M_GROW]
     unsigned long long* res;         // [8]: tf[0..5], converged, nsel — epoch-tagged words written by the reducer
     unsigned epoch_base;             // launch-unique: the epoch of iteration k is epoch_base + k + 1
     int* err_flag;
@@ -465,240 +461,30 @@ struct S2MArgs {
     const int* cnt_n_scan;           // device counts copied into the mail (nullable)
 };
 
-// multi-round solves: per-query state in global memory behind L2 (.cg: written and re-read by the same group only)
-__device__ __forceinline__ float4 qs_ld(const float4* p) { return __ldcg(p); }
-__device__ __forceinline__ void qs_st(float4* p, const float4 v) { __stcg(p, v); }
-
-template <int G>
-__device__ __forceinline__ void top5_merge(Top5& mine, Top5& res) {
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        float md = mine.d[0]; int mi = mine.oi[0], mp = mine.pos[0];
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            float od = __shfl_xor_sync(FULL, md, o); int oi = __shfl_xor_sync(FULL, mi, o); int op = __shfl_xor_sync(FULL, mp, o);
-            if (less_di(od, oi, md, mi)) { md = od; mi = oi; mp = op; }
-        }
-        if (mine.d[0] == md && mine.oi[0] == mi) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { mine.d[j] = mine.d[j + 1]; mine.oi[j] = mine.oi[j + 1]; mine.pos[j] = mine.pos[j + 1]; }
-            mine.d[4] = INFINITY; mine.oi[4] = 0x7fffffff; mine.pos[4] = -1;
-        }
-        res.d[r] = md; res.oi[r] = mi; res.pos[r] = mp;
-    }
-}
-
-// FULL search over the 27 cells with PG lanes; also builds the cached candidate list around q (= new q0).
-// Returns the number of cached candidates (or -2 on overflow).  `pos` of the results = index into gmap.
-template <int PG>
-__device__ __forceinline__ int knn5_full_and_cache(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap,
-                                                   GridDims g, float4* __restrict__ clist, Top5& mine) {
-    const int gl = threadIdx.x & (PG - 1);
-    const unsigned gmask = ((1u << PG) - 1u) << (lane_id() & ~(PG - 1));
-    const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
-    const int x0 = (cx - 1) & (g.DX - 1), x1 = cx & (g.DX - 1), x2 = (cx + 1) & (g.DX - 1);
-    const bool contiguous = (x0 + 2 == x2);
-    const float r2c = (1.0f + S2M_MARGIN) * (1.0f + S2M_MARGIN);
-    int ncache = 0;                              // group-uniform running count of cached candidates
-    unsigned bs[9], P[10];
-    if (contiguous) {
-        P[0] = 0;
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            const int dz = r / 3 - 1, dy = r % 3 - 1;
-            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
-            bs[r] = __ldg(cell_start + row + x0);
-            P[r + 1] = __ldg(cell_start + row + x2 + 1);
-        }
-#pragma unroll
-        for (int r = 0; r < 9; ++r) P[r + 1] = P[r] + (P[r + 1] - bs[r]);
-    } else {                                     // wrapped x-run: 27 single-cell ranges, walked through the same flattened loop
-        P[0] = 0;
-#pragma unroll
-        for (int r = 0; r < 9; ++r) { bs[r] = 0; P[r + 1] = 0; }
-    }
-    if (contiguous) {
-        const unsigned T = P[9];
-        for (unsigned f0 = gl; f0 < T + (PG - 1) - ((T + PG - 1) % PG); f0 += PG * KNN_U) {    // group-uniform trip count
-            float4 p[KNN_U]; unsigned pos[KNN_U];
-#pragma unroll
-            for (int u = 0; u < KNN_U; ++u) {
-                const unsigned f = f0 + PG * u;
-                unsigned base = bs[0], pb = 0;
-#pragma unroll
-                for (int rr = 1; rr < 9; ++rr) if (f >= P[rr]) { base = bs[rr]; pb = P[rr]; }
-                pos[u] = base + (f - pb);
-                p[u] = f < T ? __ldg(gmap + pos[u]) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < KNN_U; ++u) {
-                float dx = q.x - p[u].x, dy = q.y - p[u].y, dz = q.z - p[u].z;
-                float d = dx * dx; d += dy * dy; d += dz * dz;      // FLANN L2_Simple op order, no FMA
-                const bool keep = d < r2c;
-                const unsigned km = __ballot_sync(gmask, keep);          // only this query's lanes vote (other groups may be elsewhere)
-                const int slot = ncache + __popc(km & ((1u << lane_id()) - 1u));
-                if (keep && slot < CAND_CAP) qs_st(clist + slot, p[u]);
-                if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), (int)pos[u]);
-                ncache += __popc(km);
-            }
-        }
-    } else {
-#pragma unroll 1
-        for (int c27 = 0; c27 < 27; ++c27) {
-            const int r = c27 / 3, xi = c27 % 3;
-            const int dz = r / 3 - 1, dy = r % 3 - 1;
-            const int row = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX;
-            const int xc = xi == 0 ? x0 : (xi == 1 ? x1 : x2);
-            const unsigned b = __ldg(cell_start + row + xc), e = __ldg(cell_start + row + xc + 1);
-            const unsigned Tn = e - b;
-            for (unsigned f0 = gl; f0 < Tn + (PG - 1) - ((Tn + PG - 1) % PG); f0 += PG) {
-                const bool in = f0 < Tn;
-                float4 pt = in ? __ldg(gmap + b + f0) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
-                float dx = q.x - pt.x, dy2 = q.y - pt.y, dz2 = q.z - pt.z;
-                float d = dx * dx; d += dy2 * dy2; d += dz2 * dz2;
-                const bool keep = d < r2c;
-                const unsigned km = __ballot_sync(gmask, keep);
-                const int slot = ncache + __popc(km & ((1u << lane_id()) - 1u));
-                if (keep && slot < CAND_CAP) qs_st(clist + slot, pt);
-                if (d < 1.0f) top5_insert(mine, d, __float_as_int(pt.w), (int)(b + f0));
-                ncache += __popc(km);
-            }
-        }
-    }
-    return ncache <= CAND_CAP ? ncache : -2;
-}
-
-// One pass over the scan for one LM iteration with PG lanes per query (4, 8 or 16): surfOptimization for every query and
-// the 28 normal-equation products, accumulated in fp64 by the first four lanes of each group (7 products each).
-// More lanes per query shorten the serial candidate walk of the 27-cell search and put fewer queries in a warp (less
-// divergence between cached / searching / refitting queries); the kernel picks the widest group that still covers the
-// scan in ONE round of the grid.
-// (multi-round solves — more than 128 queries per worker, e.g. OS1-128 at 0.2 m — and the layout forced by liorf_debug_s2m_global_state;
-// scans that fit one round take s2m_iter_one_round below)
-template <int PG>
-__device__ __forceinline__ void s2m_query_pass(const S2MArgs& a, const int n, const int W, const int iter, const float (&s_t)[12], const LMTrig& s_trig,
-                                               float (*s_rows)[8], const int (&pij)[PPL], double (&acc)[PPL]) {
-    const int gl = threadIdx.x & (PG - 1);
-    const int qslot = threadIdx.x / PG;
-    for (int j0 = 0; j0 * W < n; j0 += (S2MP_BLOCK / PG)) {          // query q is served by worker (q mod W): dense and sparse regions spread over all SMs
-        const int q = (j0 + qslot) * W + (int)blockIdx.x;
-        const bool active = q < n;
-        const int qq = active ? q : 0;
-        float4* hdr = reinterpret_cast<float4*>(a.qcache + qq);
-        float4* clist = a.cand + (size_t)qq * CAND_CAP;
-        // every independent load of the cached path is issued up front (one round trip): the point, the cache
-        // header (written by this same group earlier in this launch), the cached plane and the first candidates
-        float4 ori = active ? __ldg(a.scan + q) : make_float4(0, 0, 0, 0);
-        const float4 h0 = qs_ld(hdr);
-        const float4 h1 = qs_ld(hdr + 1);              // nn[0..3]
-        const float4 h2 = qs_ld(hdr + 2);              // nn[4], plane_ok, pa, pb
-        const float4 h3 = qs_ld(hdr + 3);              // pc, pd
-        float4 pre[KNN_U];
-#pragma unroll
-        for (int u = 0; u < KNN_U; ++u) pre[u] = qs_ld(clist + gl + PG * u);           // speculative: slots exist even if unused
-        float4 sel = apply_affine_dev(s_t, ori);
-        const int cnt = __float_as_int(h0.w);
-        float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
-        float moved = mx * mx; moved += my * my; moved += mz * mz;
-        const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
-        // the list holds the points within 1 + m of q0 THAT LIE IN q0's 27 cells; the unit ball around pointSel stays
-        // inside that block of cells only while pointSel is in q0's own cell
-        const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
-        const bool use_cache = active && iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
-        Top5 mine; top5_init(mine);
-        if (use_cache) {
-            for (int f0 = gl; f0 < cnt; f0 += PG * KNN_U) {
-                float4 p[KNN_U];
-#pragma unroll
-                for (int u = 0; u < KNN_U; ++u) {
-                    const int f = f0 + PG * u;
-                    p[u] = f0 == gl ? pre[u] : (f < cnt ? qs_ld(clist + f) : make_float4(1e30f, 1e30f, 1e30f, 0.f));
-                    if (f >= cnt) p[u] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < KNN_U; ++u) {
-                    float dx = sel.x - p[u].x, dy = sel.y - p[u].y, dz = sel.z - p[u].z;
-                    float d = dx * dx; d += dy * dy; d += dz * dz;
-                    if (d < 1.0f) top5_insert(mine, d, __float_as_int(p[u].w), f0 + PG * u);
-                }
-            }
-        } else if (active) {
-            const int list_cnt = knn5_full_and_cache<PG>(sel, a.cell_start, a.gmap, a.g, clist, mine);
-            if (gl == 0) qs_st(hdr, make_float4(sel.x, sel.y, sel.z, __int_as_float(list_cnt)));
-        }
-        Top5 nn; top5_merge<PG>(mine, nn);
-        // ---- plane: reuse when the ordered neighbour ids are unchanged ----
-        const bool have5 = active && nn.pos[4] != -1 && (double)nn.d[4] < 1.0;          // :1097
-        bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (have5) {
-            const bool same = iter > 0 && !a.no_cache && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
-                              __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
-            float pa, pb, pc, pd; bool planeValid;
-            if (same) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3.x; pd = h3.y; }
-            else {
-                float A[5][3];
-                // results index the candidate list in cached mode, gmap otherwise
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const float4 mpt = use_cache ? qs_ld(clist + nn.pos[j]) : __ldcg(a.gmap + nn.pos[j]);
-                    A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z;
-                }
-                float x[3];
-                colpiv_qr_solve_5x3(A, x);                                               // :1104
-                pa = x[0]; pb = x[1]; pc = x[2]; pd = 1.f;
-                float ps = sqrtf(pa * pa + pb * pb + pc * pc);                           // :1111
-                pa /= ps; pb /= ps; pc /= ps; pd /= ps;
-                planeValid = true;
-#pragma unroll
-                for (int j = 0; j < 5; ++j)                                              // :1115-1122
-                    if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
-                if (gl == 0) {
-                    qs_st(hdr + 1, make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3])));
-                    qs_st(hdr + 2, make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb));
-                    qs_st(hdr + 3, make_float4(pc, pd, 0.f, 0.f));
-                }
-            }
-            if (planeValid) {
-                float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;                   // :1125
-                float rr = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z));
-                float sw = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)rr);         // :1127-1128
-                coeff = make_float4(sw * pa, sw * pb, sw * pc, sw * pd2);                // :1130-1133
-                f = (double)sw > 0.1;                                                    // :1135
-            }
-        } else if (iter == 0 && active && gl == 0) {
-            qs_st(hdr + 1, make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)));   // no cached plane
-        }
-        float v[8];
-        lm_row_dev(s_trig, ori, coeff, v); v[7] = 1.f;
-        __syncwarp();
-        {   // lanes 0..3 of the group publish two row entries each (zero row when the point is not selected)
-            const float e0 = gl == 0 ? v[0] : gl == 1 ? v[1] : gl == 2 ? v[2] : v[3];
-            const float e1 = gl == 0 ? v[4] : gl == 1 ? v[5] : gl == 2 ? v[6] : v[7];
-            if (gl < 4) { s_rows[qslot][gl] = f ? e0 : 0.f; s_rows[qslot][4 + gl] = f ? e1 : 0.f; }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < PPL; ++t) if (gl < 4) acc[t] += (double)s_rows[qslot][pij[t] & 15] * (double)s_rows[qslot][pij[t] >> 4];
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// One-round solves (n <= workers x 128 — the KITTI / Livox sizes): ONE THREAD PER QUERY, state in shared memory.
-// The 4-lanes-per-query pass above is bound by instruction issue, not memory (ncu r2: 7.6k warp instructions per scheduler and
-// iteration; a quarter of them the insertion sort of the per-lane top-5 lists, another tenth their merge, and everything after the
-// search executed four times over).  Here an iteration is three phases over the worker's <= 128 queries:
+// The worker side of an iteration: ONE THREAD PER QUERY, 128 queries per worker and round.
+// (Rounds 1 and early 2 gave every query 4 lanes.  ncu showed that pass bound by instruction issue, not memory: 7.6k warp instructions
+// per scheduler and iteration, a quarter of them the insertion sort of the per-lane top-5 lists, a tenth their merge, and everything
+// after the search executed four times over.)  A round is three phases:
 //   1. (thread = query) pointSel; is the cached candidate list still valid (see above)?  If not, queue the query.
-//   2. (warp = queued query) rebuild the list: the 27 cells are walked 32 points at a time and every point within 1 + m of the new
-//      q0 is appended (ballot compaction) — no top-5 bookkeeping at all.  Steady state: nothing queued.
-//   3. (thread = query) exact 5-NN by one ordered insertion pass over the ~15 listed points (no merge, nothing redundant), plane
-//      reuse / refit, weight, Jacobian row → s_rows.
-// followed by the products: 16 chains x 28 products sum their queries' row products in fp64 (fixed order), combined by the same
-// 4-chain tree as before.  Same arithmetic per point and the same (distance, index) order — the neighbour sets and rows are
-// bit-identical to the multi-round path; only the order of the fp64 partial sums differs (as it does between lane widths).
-// A list that overflows CAND_CAP (-2) is answered by an exact one-thread walk of the 27 cells (rare: > 64 map points within 1.15 m).
+//   2. (half warp = queued query) rebuild the list: the 27 cells are walked 64 points at a time and every point within 1 + m of the new
+//      q0 is appended (ballot compaction); the half warp leaves the list positions of the five nearest entries.  Steady state: nothing queued.
+//   3. (thread = query) exact 5-NN from the list, VERIFY FIRST: the five entries that were nearest last time bound the new 5th-smallest
+//      key from above; if exactly those five lie under the bound, still in order, the neighbours are unchanged and nothing is sorted.
+//      Otherwise the few entries under the bound are re-ordered (sorting network) or inserted in order.  Then plane reuse (two cached
+//      planes per query) / refit, weight, Jacobian row → s_rows.
+// followed by the products: 16 chains x 28 products sum their queries' row products in fp64 in a fixed order.
+// Same arithmetic per point and the same (distance, index) order as the per-function hooks: neighbour sets and rows are bit-identical.
+// Scans that fit ONE round (n <= workers x 128: KITTI, Livox) keep the point in a register and the per-query state in SHARED memory —
+// a steady-state iteration touches neither L2 nor HBM; larger scans (OS1-128 at 0.2 m) run several rounds with the same state in
+// global memory behind L2 (SM = false).  A list that overflows CAND_CAP (-2) is answered by an exact one-thread walk of the 27 cells.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool SM> __device__ __forceinline__ float4 ldq(const float4* p) { if (SM) return *p; return __ldcg(p); }
+template <bool SM> __device__ __forceinline__ void stq(float4* p, const float4 v) { if (SM) *p = v; else __stcg(p, v); }
+
 // Sixteen lanes (one half of a warp) per queued query — the two halves of a warp work on two queries at once, so twice as many
 // dependent L2 round trips (cell bounds → candidate points) are in flight per SM.  Four candidates per lane and step.
+template <bool SM>
 __device__ __forceinline__ int build_list_half(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g,
                                                float4* __restrict__ clist) {
     const int l = lane_id() & 15, hb = lane_id() & 16;
@@ -741,7 +527,7 @@ __device__ __forceinline__ int build_list_half(const float4 q, const unsigned* _
                 const bool keep = d < r2c;
                 const unsigned km = (__ballot_sync(gmask, keep) >> hb) & 0xffffu;
                 const int slot = ncache + __popc(km & lt);
-                if (keep && slot < CAND_CAP) clist[slot] = p[u];
+                if (keep && slot < CAND_CAP) stq<SM>(clist + slot, p[u]);
                 ncache += __popc(km);
             }
         }
@@ -761,7 +547,7 @@ __device__ __forceinline__ int build_list_half(const float4 q, const unsigned* _
                 const bool keep = d < r2c;
                 const unsigned km = (__ballot_sync(gmask, keep) >> hb) & 0xffffu;
                 const int slot = ncache + __popc(km & lt);
-                if (keep && slot < CAND_CAP) clist[slot] = pt;
+                if (keep && slot < CAND_CAP) stq<SM>(clist + slot, pt);
                 ncache += __popc(km);
             }
         }
@@ -787,10 +573,7 @@ __device__ __noinline__ void knn5_lane(const float4 q, const unsigned* __restric
 
 struct S2MShared {                      // views into the dynamic shared memory of a one-round worker
     float4* list;                       // [S2MP_QPB][S2M_ROW]
-    float4* h0; float4* h1; float4* h2; float4* h3;      // [S2MP_QPB] each: QueryCache's four 16-byte words; h3.z = list positions of the current top-5 (6 bits each),
-                                                         // h3.w = which of the two cached planes was used last
-    float4* g1; float4* g2; float4* g3;                  // a SECOND cached plane (ids, validity, coefficients): a query whose 5th / 6th neighbours are
-                                                         // nearly equidistant flips between two neighbour lists as the pose settles — one refit each, not one per iteration
+    float4* h;                          // [7][S2MP_QPB]: the seven words of QueryCache as seven arrays (lane t reads element t: conflict-free)
 };
 
 // (distance, original index) as ONE unsigned 64-bit key: squared distances are non-negative floats, whose bit patterns order like the
@@ -804,6 +587,7 @@ __device__ __forceinline__ float sqdist_dev(const float4 q, const float4 p) {
 
 // phase 2 epilogue, one half warp: list positions of the five smallest keys of a freshly built list (cnt >= 5), packed 6 bits each,
 // smallest first — the prior that phase 3 verifies from now on.  Lane l holds entries l, l + 16, l + 32, l + 48.
+template <bool SM>
 __device__ __forceinline__ unsigned top5_positions_half(const float4 q, const float4* __restrict__ row, int cnt) {
     const int l = lane_id() & 15, hb = lane_id() & 16;
     const unsigned gmask = 0xffffu << hb;
@@ -811,7 +595,7 @@ __device__ __forceinline__ unsigned top5_positions_half(const float4 q, const fl
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         k4[u] = ~0ull;
-        if (l + 16 * u < cnt) { const float4 p = row[l + 16 * u]; k4[u] = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
+        if (l + 16 * u < cnt) { const float4 p = ldq<SM>(row + l + 16 * u); k4[u] = nn_key(sqdist_dev(q, p), __float_as_int(p.w)); }
     }
     unsigned packed = 0;
 #pragma unroll
@@ -832,64 +616,76 @@ __device__ __forceinline__ unsigned top5_positions_half(const float4 q, const fl
     return packed;
 }
 
-__device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n, const int W, const int iter, const float (&s_t)[12], const LMTrig& s_trig,
-                                                   float (*s_rows)[8], const S2MShared& S, const float4 ori, const float rr, int* s_todo, int* s_ntodo, long long* dbg_p2) {
+template <bool SM>
+__device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const int W, const int iter, const int round, const float (&s_t)[12], const LMTrig& s_trig,
+                                          float (*s_rows)[8], const S2MShared& S, const float4 ori_keep, const float rr_keep, int* s_todo, int* s_ntodo, long long* dbg_p2) {
     const int tid = threadIdx.x;
-    const bool mine = tid < S2MP_QPB && tid * W + (int)blockIdx.x < n;
+    // slot s of this round is query (round * 128 + s) * W + worker: dense and sparse regions of the scan spread over all SMs
+    auto query_of = [&](int slot) { return (round * S2MP_QPB + slot) * W + (int)blockIdx.x; };
+    auto hdr = [&](int slot, int k) -> float4* { if (SM) return S.h + k * S2MP_QPB + slot; return a.qcache[query_of(slot)].w + k; };
+    auto rowp = [&](int slot) -> float4* { if (SM) return S.list + slot * S2M_ROW; return a.cand + (size_t)query_of(slot) * S2M_GROW; };
+    const bool mine = tid < S2MP_QPB && query_of(tid) < n;
+    float4 ori = ori_keep; float rr = rr_keep;
+    if (!SM && mine) { ori = __ldg(a.scan + query_of(tid)); rr = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z)); }
     float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
     // ---- 1. pointSel; queue the queries whose candidate list must be rebuilt ----
     if (mine) {
         sel = apply_affine_dev(s_t, ori);
-        const float4 h0 = S.h0[tid];
+        const float4 h0 = ldq<SM>(hdr(tid, 0));
         const int cnt = __float_as_int(h0.w);
         float mx = sel.x - h0.x, my = sel.y - h0.y, mz = sel.z - h0.z;
         float moved = mx * mx; moved += my * my; moved += mz * mz;
         const float lim = (S2M_MARGIN - 1e-3f) * (S2M_MARGIN - 1e-3f);
+        // the list holds the points within 1 + m of q0 THAT LIE IN q0's 27 cells; the unit ball around pointSel stays
+        // inside that block of cells only while pointSel is in q0's own cell
         const bool same_cell = floorf(sel.x) == floorf(h0.x) && floorf(sel.y) == floorf(h0.y) && floorf(sel.z) == floorf(h0.z);
         const bool valid = iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
-        if (!valid) { s_todo[atomicAdd(s_ntodo, 1)] = tid; S.h0[tid] = make_float4(sel.x, sel.y, sel.z, __int_as_float(-1)); }
+        if (!valid) { s_todo[atomicAdd(s_ntodo, 1)] = tid; stq<SM>(hdr(tid, 0), make_float4(sel.x, sel.y, sel.z, __int_as_float(-1))); }
         if (a.dbg_gt && !valid && iter >= 10) atomicAdd(a.dbg_gt + 40 * S2M_GT_STRIDE + blockIdx.x, 1ull);
         // iteration 0 never trusts a cached plane (it belongs to an earlier launch / another map)
-        if (iter == 0) { S.h1[tid] = make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1)); S.g1[tid] = S.h1[tid]; }
+        if (iter == 0) {
+            const float4 none = make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1));
+            stq<SM>(hdr(tid, 1), none); stq<SM>(hdr(tid, 4), none);
+        }
     }
     __syncthreads();
     // ---- 2. one half warp per queued query rebuilds its list around the new q0 and leaves the positions of its five nearest entries ----
     const int ntodo = *s_ntodo;
     for (int k = 2 * warp_id() + (lane_id() >> 4); k < ntodo; k += 2 * S2MP_WARPS) {       // the two halves of a warp take one query each
         const int slot = s_todo[k];
-        const float4 q0 = S.h0[slot];
-        float4* row = S.list + slot * S2M_ROW;
-        const int c = build_list_half(q0, a.cell_start, a.gmap, a.g, row);
+        const float4 q0 = ldq<SM>(hdr(slot, 0));
+        float4* row = rowp(slot);
+        const int c = build_list_half<SM>(q0, a.cell_start, a.gmap, a.g, row);
         __syncwarp(0xffffu << (lane_id() & 16));
         unsigned packed = 0;
-        if (c >= 5) packed = top5_positions_half(q0, row, c);
+        if (c >= 5) packed = top5_positions_half<SM>(q0, row, c);
         if ((lane_id() & 15) == 0) {
-            S.h0[slot] = make_float4(q0.x, q0.y, q0.z, __int_as_float(c));
-            float4 h3 = S.h3[slot]; h3.z = __uint_as_float(packed); S.h3[slot] = h3;
+            stq<SM>(hdr(slot, 0), make_float4(q0.x, q0.y, q0.z, __int_as_float(c)));
+            float4 h3 = ldq<SM>(hdr(slot, 3)); h3.z = __uint_as_float(packed); stq<SM>(hdr(slot, 3), h3);
         }
     }
     __syncthreads();
     if (dbg_p2) *dbg_p2 = clock64();
-    if (tid == 0) *s_ntodo = 0;                  // the next iteration's phase 1 is at least two barriers away
+    if (tid == 0) *s_ntodo = 0;                  // the next phase 1 is at least two barriers away
     // ---- 3. exact 5-NN from the list, plane, weight, Jacobian row ----
     if (tid < S2MP_QPB) {
         bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
         float v[8];
         if (mine) {
-            const int cnt = __float_as_int(S.h0[tid].w);
-            const float4* row = S.list + tid * S2M_ROW;
-            const float4 h3 = S.h3[tid];
+            const int cnt = __float_as_int(ldq<SM>(hdr(tid, 0)).w);
+            const float4* row = rowp(tid);
+            const float4 h3 = ldq<SM>(hdr(tid, 3));
             Top5 nn; top5_init(nn);
             if (cnt >= 5) {
                 // The five entries that were nearest last time (or when the list was built) bound the new 5th-smallest key from above:
                 // only entries with key <= thr can be among the new five.  Usually those are the same five in the same order — then the
-                // neighbours are unchanged and nothing is sorted at all; otherwise the few entries under the bound are inserted in order.
+                // neighbours are unchanged and nothing is sorted at all; otherwise the few entries under the bound are re-ordered / inserted.
                 unsigned pk = __float_as_uint(h3.z);
                 unsigned long long ck[5]; float cd[5]; int coi[5], cpos[5];
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
                     cpos[j] = (int)((pk >> (6 * j)) & 63u);
-                    const float4 p = row[cpos[j]];
+                    const float4 p = ldq<SM>(row + cpos[j]);
                     cd[j] = sqdist_dev(sel, p); coi[j] = __float_as_int(p.w); ck[j] = nn_key(cd[j], coi[j]);
                 }
                 unsigned long long thr = ck[0];
@@ -899,7 +695,7 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                 for (int f0 = 0; f0 < cnt; f0 += 4) {
                     float4 p[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) p[u] = row[f0 + u];          // the row is padded: entries past cnt are read but masked out
+                    for (int u = 0; u < 4; ++u) p[u] = ldq<SM>(row + f0 + u);          // the row is padded: entries past cnt are read but masked out
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float d = sqdist_dev(sel, p[u]);
@@ -923,12 +719,12 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                     pk = 0;
 #pragma unroll
                     for (int j = 0; j < 5; ++j) { nn.d[j] = cd[j]; nn.oi[j] = coi[j]; nn.pos[j] = cpos[j]; pk |= (unsigned)cpos[j] << (6 * j); }
-                    float4 h3n = h3; h3n.z = __uint_as_float(pk); S.h3[tid] = h3n;
+                    float4 h3n = h3; h3n.z = __uint_as_float(pk); stq<SM>(hdr(tid, 3), h3n);
                 } else {
                     if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 41 * S2M_GT_STRIDE + blockIdx.x, 1ull);
                     while (mask) {
                         const int i = __ffsll((long long)mask) - 1; mask &= mask - 1;
-                        const float4 p = row[i];
+                        const float4 p = ldq<SM>(row + i);
                         const float d = sqdist_dev(sel, p);
                         if (d < 1.0f) top5_insert(nn, d, __float_as_int(p.w), i);
                     }
@@ -936,26 +732,28 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                         pk = 0;
 #pragma unroll
                         for (int j = 0; j < 5; ++j) pk |= (unsigned)nn.pos[j] << (6 * j);
-                        float4 h3n = h3; h3n.z = __uint_as_float(pk); S.h3[tid] = h3n;
+                        float4 h3n = h3; h3n.z = __uint_as_float(pk); stq<SM>(hdr(tid, 3), h3n);
                     }
                 }
             } else if (cnt == -2) { knn5_lane(sel, a.cell_start, a.gmap, a.g, nn); if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 43 * S2M_GT_STRIDE + blockIdx.x, 1ull); }
             const bool have5 = nn.pos[4] != -1 && (double)nn.d[4] < 1.0;                // :1097
             if (have5) {
-                const float4 h1 = S.h1[tid], h2 = S.h2[tid], g1 = S.g1[tid], g2 = S.g2[tid];
+                // ---- plane: reuse when the ordered neighbour ids match one of the two cached planes ----
+                const float4 h1 = ldq<SM>(hdr(tid, 1)), h2 = ldq<SM>(hdr(tid, 2)), g1 = ldq<SM>(hdr(tid, 4)), g2 = ldq<SM>(hdr(tid, 5));
                 const bool use = iter > 0 && !a.no_cache;
                 const bool same0 = use && __float_as_int(h1.x) == nn.oi[0] && __float_as_int(h1.y) == nn.oi[1] && __float_as_int(h1.z) == nn.oi[2] &&
                                    __float_as_int(h1.w) == nn.oi[3] && __float_as_int(h2.x) == nn.oi[4];
                 const bool same1 = use && __float_as_int(g1.x) == nn.oi[0] && __float_as_int(g1.y) == nn.oi[1] && __float_as_int(g1.z) == nn.oi[2] &&
                                    __float_as_int(g1.w) == nn.oi[3] && __float_as_int(g2.x) == nn.oi[4];
                 float pa, pb, pc, pd; bool planeValid;
-                if (same0) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = S.h3[tid].x; pd = S.h3[tid].y; }
-                else if (same1) { const float4 g3 = S.g3[tid]; planeValid = __float_as_int(g2.y) != 0; pa = g2.z; pb = g2.w; pc = g3.x; pd = g3.y; }
+                float4 h3c = ldq<SM>(hdr(tid, 3));                                       // (the top-5 positions may just have been rewritten)
+                if (same0) { planeValid = __float_as_int(h2.y) != 0; pa = h2.z; pb = h2.w; pc = h3c.x; pd = h3c.y; }
+                else if (same1) { const float4 g3 = ldq<SM>(hdr(tid, 6)); planeValid = __float_as_int(g2.y) != 0; pa = g2.z; pb = g2.w; pc = g3.x; pd = g3.y; }
                 else {
                     float A[5][3];
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        const float4 mpt = cnt >= 0 ? row[nn.pos[j]] : __ldg(a.gmap + nn.pos[j]);
+                        const float4 mpt = cnt >= 0 ? ldq<SM>(row + nn.pos[j]) : __ldg(a.gmap + nn.pos[j]);
                         A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z;
                     }
                     float x[3];
@@ -969,18 +767,16 @@ __device__ __forceinline__ void s2m_iter_one_round(const S2MArgs& a, const int n
                     for (int j = 0; j < 5; ++j)                                          // :1115-1122
                         if ((double)fabsf(pa * A[j][0] + pb * A[j][1] + pc * A[j][2] + pd) > 0.2) planeValid = false;
                     // replace the plane that was NOT used last
-                    float4 h3n = S.h3[tid];
-                    const bool into1 = __float_as_int(h3n.w) == 0;
+                    const bool into1 = __float_as_int(h3c.w) == 0;
                     const float4 n1v = make_float4(__int_as_float(nn.oi[0]), __int_as_float(nn.oi[1]), __int_as_float(nn.oi[2]), __int_as_float(nn.oi[3]));
                     const float4 n2v = make_float4(__int_as_float(nn.oi[4]), __int_as_float(planeValid ? 1 : 0), pa, pb);
-                    if (into1) { S.g1[tid] = n1v; S.g2[tid] = n2v; S.g3[tid] = make_float4(pc, pd, 0.f, 0.f); h3n.w = __int_as_float(1); }
-                    else { S.h1[tid] = n1v; S.h2[tid] = n2v; h3n.x = pc; h3n.y = pd; h3n.w = __int_as_float(0); }
-                    S.h3[tid] = h3n;
+                    if (into1) { stq<SM>(hdr(tid, 4), n1v); stq<SM>(hdr(tid, 5), n2v); stq<SM>(hdr(tid, 6), make_float4(pc, pd, 0.f, 0.f)); h3c.w = __int_as_float(1); }
+                    else { stq<SM>(hdr(tid, 1), n1v); stq<SM>(hdr(tid, 2), n2v); h3c.x = pc; h3c.y = pd; h3c.w = __int_as_float(0); }
+                    stq<SM>(hdr(tid, 3), h3c);
                 }
                 if (same0 || same1) {
                     const int used = same0 ? 0 : 1;
-                    float4 h3n = S.h3[tid];
-                    if (__float_as_int(h3n.w) != used) { h3n.w = __int_as_float(used); S.h3[tid] = h3n; }
+                    if (__float_as_int(h3c.w) != used) { h3c.w = __int_as_float(used); stq<SM>(hdr(tid, 3), h3c); }
                 }
                 if (planeValid) {
                     float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;               // :1125
@@ -1091,11 +887,9 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     const bool reducer = (int)blockIdx.x == W;
     const int n = a.n_scan.get();
     const int m = a.m_map.get();
-    // lanes per query: the widest group that covers the scan in one round of the workers (same choice in every CTA)
-    const int pg = a.force_pg ? a.force_pg : (n <= W * (S2MP_BLOCK / 16) ? 16 : (n <= W * (S2MP_BLOCK / 8) ? 8 : 4));
-    const bool one_round = !a.global_state && n <= W * S2MP_QPB;              // one thread per query, state in registers / shared memory
-    S2MShared S; S.list = s_state; S.h0 = s_state + S2MP_QPB * S2M_ROW; S.h1 = S.h0 + S2MP_QPB; S.h2 = S.h1 + S2MP_QPB; S.h3 = S.h2 + S2MP_QPB; S.g1 = S.h3 + S2MP_QPB; S.g2 = S.g1 + S2MP_QPB; S.g3 = S.g2 + S2MP_QPB;
-    const int gl = threadIdx.x & (pg - 1);              // lane within the query group; lanes 0..3 own 7 products each
+    const bool one_round = !a.global_state && n <= W * S2MP_QPB;              // query state in registers / shared memory
+    const int rounds = one_round ? 1 : (n + W * S2MP_QPB - 1) / (W * S2MP_QPB);
+    S2MShared S; S.list = s_state; S.h = s_state + S2MP_QPB * S2M_ROW;
     if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
     if (threadIdx.x == 32) { s_conv = 0; s_ntodo = 0; }
     if (reducer && threadIdx.x >= 64 && threadIdx.x < 64 + 37)          // persistent LM state (members :139-140)
@@ -1111,10 +905,6 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     const bool run = (m >= 5) && (n > 30);
     int iters_done = 0, converged = 0;
     if (run) {
-        // product indices owned by this lane: p in [PPL*gl, PPL*gl + PPL)
-        int pij[PPL];
-#pragma unroll
-        for (int t = 0; t < PPL; ++t) { const int p = (gl & 3) * PPL + t; pij[t] = prod_i(p) | (prod_j(p) << 4); }
         // iteration 0 never trusts the per-query caches (they belong to an earlier launch / another map)
         for (int iter = 0; iter < a.max_iters; ++iter) {
             const unsigned epoch = a.epoch_base + (unsigned)iter + 1u;
@@ -1133,36 +923,20 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                     s_t[8] = -D;     s_t[9] = Cc * F;         s_t[10] = Cc * E;        s_t[11] = s_tf[5];
                     s_trig.srx = B; s_trig.crx = A; s_trig.sry = D; s_trig.cry = Cc; s_trig.srz = F; s_trig.crz = E;   // :1170-1175
                 }
-                if (one_round) {
-                    s2m_iter_one_round(a, n, W, iter, s_t, s_trig, s_rows, S, ori_keep, rr_keep, s_todo, &s_ntodo, dbg ? a.dbg + iter * 8 + 3 : nullptr);
-                    if (dbg) a.dbg[iter * 8 + 1] = clock64();
+                double sacc = 0.0;
+                for (int round = 0; round < rounds; ++round) {
+                    long long* dbg_p2 = dbg && round == 0 ? a.dbg + iter * 8 + 3 : nullptr;
+                    if (one_round) s2m_round<true>(a, n, W, iter, round, s_t, s_trig, s_rows, S, ori_keep, rr_keep, s_todo, &s_ntodo, dbg_p2);
+                    else s2m_round<false>(a, n, W, iter, round, s_t, s_trig, s_rows, S, ori_keep, rr_keep, s_todo, &s_ntodo, dbg_p2);
+                    if (dbg && round == rounds - 1) a.dbg[iter * 8 + 1] = clock64();
                     __syncthreads();
-                    if (k16 < S2MP_WARPS) {               // 16 chains x 28 products, chain k takes queries k, k + 16, ... in ascending order
-                        const int nq = min(S2MP_QPB, (n - (int)blockIdx.x + W - 1) / W);
-                        double sacc = 0.0;
+                    if (k16 < S2MP_WARPS) {               // 16 chains x 28 products, chain k takes this round's queries k, k + 16, ... in ascending order
+                        const int nq = max(0, min(S2MP_QPB, (n - (int)blockIdx.x + W - 1) / W - round * S2MP_QPB));
                         for (int q = k16; q < nq; q += S2MP_WARPS) sacc += (double)s_rows[q][pi16] * (double)s_rows[q][pj16];
-                        s_red[k16][p16] = sacc;
                     }
-                } else {
-                    double acc[PPL];
-#pragma unroll
-                    for (int t = 0; t < PPL; ++t) acc[t] = 0.0;
-                    if (pg == 16) s2m_query_pass<16>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
-                    else if (pg == 8) s2m_query_pass<8>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
-                    else s2m_query_pass<4>(a, n, W, iter, s_t, s_trig, s_rows, pij, acc);
-                    if (dbg) a.dbg[iter * 8 + 1] = clock64();
-                    // block reduction (fixed tree): lanes 0..3 of the groups of a warp, then across warps
-#pragma unroll
-                    for (int t = 0; t < PPL; ++t) {                      // lanes 0..3 of every group hold sums; groups are pg lanes apart
-                        if (pg <= 4) acc[t] += __shfl_xor_sync(FULL, acc[t], 4);
-                        if (pg <= 8) acc[t] += __shfl_xor_sync(FULL, acc[t], 8);
-                        acc[t] += __shfl_xor_sync(FULL, acc[t], 16);
-                    }
-                    if (lane_id() < 4) {
-#pragma unroll
-                        for (int t = 0; t < PPL; ++t) s_red[warp_id()][gl * PPL + t] = acc[t];
-                    }
+                    if (round + 1 < rounds) __syncthreads();      // the next round overwrites the rows
                 }
+                if (k16 < S2MP_WARPS) s_red[k16][p16] = sacc;
                 __syncthreads();
                 if (threadIdx.x < NPROD) {
                     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
