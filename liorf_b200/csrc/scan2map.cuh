@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(256) k_lm_hook(int iter, const float4* __restr
 // and releases an epoch flag the other CTAs spin on (bounded).  This replaces grid.sync + 148 redundant sums/solves.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int S2MP_BLOCK = 512;             // one CTA per SM
-constexpr int S2MP_QPB = 128;               // queries per worker and round: one thread each (the first four warps); all 16 warps rebuild lists / sum products
+constexpr int S2MP_QPB = 128;               // queries per worker and round with the state in shared memory: one thread each (the first four warps)
+constexpr int S2MP_QPB_GLOBAL = S2MP_BLOCK; // ... with the state in global memory: every thread takes a query (no shared-memory capacity to respect)
 constexpr int S2MP_WARPS = S2MP_BLOCK / 32;
 constexpr int CAND_CAP = 64;                // cached candidates per query (float4 each); overflow → always full search
 constexpr float S2M_MARGIN = 0.15f;
@@ -477,8 +478,18 @@ struct S2MArgs {
 // Same arithmetic per point and the same (distance, index) order as the per-function hooks: neighbour sets and rows are bit-identical.
 // Scans that fit ONE round (n <= workers x 128: KITTI, Livox) keep the point in a register and the per-query state in SHARED memory —
 // a steady-state iteration touches neither L2 nor HBM; larger scans (OS1-128 at 0.2 m) run several rounds with the same state in
-// global memory behind L2 (SM = false).  A list that overflows CAND_CAP (-2) is answered by an exact one-thread walk of the 27 cells.
+// global memory behind L2 (SM = false), every thread of the CTA taking a query.  A list that overflows CAND_CAP is replaced by the exact
+// five nearest points, found by the same half warp (exact_top5_half), and rebuilt in every iteration.
 // ---------------------------------------------------------------------------------------------------------------
+// (distance, original index) as ONE unsigned 64-bit key: squared distances are non-negative floats, whose bit patterns order like the
+// values, and the original indices are non-negative ints — key order == less_di order
+__device__ __forceinline__ unsigned long long nn_key(float d, int oi) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)oi; }
+__device__ __forceinline__ float sqdist_dev(const float4 q, const float4 p) {
+    float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+    float d = dx * dx; d += dy * dy; d += dz * dz;                  // FLANN L2_Simple op order, no FMA
+    return d;
+}
+
 template <bool SM> __device__ __forceinline__ float4 ldq(const float4* p) { if (SM) return *p; return __ldcg(p); }
 template <bool SM> __device__ __forceinline__ void stq(float4* p, const float4 v) { if (SM) *p = v; else __stcg(p, v); }
 
@@ -555,35 +566,51 @@ __device__ __forceinline__ int build_list_half(const float4 q, const unsigned* _
     return ncache <= CAND_CAP ? ncache : -2;
 }
 
-// exact 5-NN by ONE thread over the 27 cells (list overflow only); pos = index into gmap
-__device__ __noinline__ void knn5_lane(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g, Top5& t) {
+// A list that overflows CAND_CAP (dense maps: Livox at 0.3 m leaves has > 64 points within 1.15 m of most queries): the half warp
+// searches the 27 cells exactly — per-lane ordered top-5 over its share of the points, merged by (distance, index) — and leaves the
+// five winners as the whole list.  Returns how many were found (0..5); such a list is exact for THIS pointSel only.
+template <bool SM>
+__device__ __forceinline__ int exact_top5_half(const float4 q, const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g,
+                                               float4* __restrict__ clist) {
+    const int l = lane_id() & 15, hb = lane_id() & 16;
+    const unsigned gmask = 0xffffu << hb;
     const int cx = (int)floorf(q.x), cy = (int)floorf(q.y), cz = (int)floorf(q.z);
+    Top5 mine; top5_init(mine);
+#pragma unroll 1
     for (int c27 = 0; c27 < 27; ++c27) {
         const int dz = c27 / 9 - 1, dy = (c27 / 3) % 3 - 1, dx = c27 % 3 - 1;
         const int cell = (((cz + dz) & (g.DZ - 1)) * g.DY + ((cy + dy) & (g.DY - 1))) * g.DX + ((cx + dx) & (g.DX - 1));
         const unsigned b = __ldg(cell_start + cell), e = __ldg(cell_start + cell + 1);
-        for (unsigned k = b; k < e; ++k) {
+        for (unsigned k = b + l; k < e; k += 16) {
             const float4 p = __ldg(gmap + k);
-            float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
-            float d = ex * ex; d += ey * ey; d += ez * ez;
-            if (d < 1.0f) top5_insert(t, d, __float_as_int(p.w), (int)k);
+            const float d = sqdist_dev(q, p);
+            if (d < 1.0f) top5_insert(mine, d, __float_as_int(p.w), (int)k);
         }
     }
+    __syncwarp(gmask);
+    int found = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {                   // 5 rounds of half-warp arg-min by (d, oi); the winning lane pops its head
+        float md = mine.d[0]; int mi = mine.oi[0], mp = mine.pos[0];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(gmask, md, o, 16); const int oi = __shfl_xor_sync(gmask, mi, o, 16); const int op = __shfl_xor_sync(gmask, mp, o, 16);
+            if (less_di(od, oi, md, mi)) { md = od; mi = oi; mp = op; }
+        }
+        if (mine.d[0] == md && mine.oi[0] == mi) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mine.d[j] = mine.d[j + 1]; mine.oi[j] = mine.oi[j + 1]; mine.pos[j] = mine.pos[j + 1]; }
+            mine.d[4] = INFINITY; mine.oi[4] = 0x7fffffff; mine.pos[4] = -1;
+        }
+        if (mp >= 0) { if (l == r) stq<SM>(clist + r, __ldg(gmap + mp)); ++found; }
+    }
+    return found;
 }
 
 struct S2MShared {                      // views into the dynamic shared memory of a one-round worker
     float4* list;                       // [S2MP_QPB][S2M_ROW]
     float4* h;                          // [7][S2MP_QPB]: the seven words of QueryCache as seven arrays (lane t reads element t: conflict-free)
 };
-
-// (distance, original index) as ONE unsigned 64-bit key: squared distances are non-negative floats, whose bit patterns order like the
-// values, and the original indices are non-negative ints — key order == less_di order
-__device__ __forceinline__ unsigned long long nn_key(float d, int oi) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)oi; }
-__device__ __forceinline__ float sqdist_dev(const float4 q, const float4 p) {
-    float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
-    float d = dx * dx; d += dy * dy; d += dz * dz;                  // FLANN L2_Simple op order, no FMA
-    return d;
-}
 
 // phase 2 epilogue, one half warp: list positions of the five smallest keys of a freshly built list (cnt >= 5), packed 6 bits each,
 // smallest first — the prior that phase 3 verifies from now on.  Lane l holds entries l, l + 16, l + 32, l + 48.
@@ -621,10 +648,11 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
                                           float (*s_rows)[8], const S2MShared& S, const float4 ori_keep, const float rr_keep, int* s_todo, int* s_ntodo, long long* dbg_p2) {
     const int tid = threadIdx.x;
     // slot s of this round is query (round * 128 + s) * W + worker: dense and sparse regions of the scan spread over all SMs
-    auto query_of = [&](int slot) { return (round * S2MP_QPB + slot) * W + (int)blockIdx.x; };
+    constexpr int QPB = SM ? S2MP_QPB : S2MP_QPB_GLOBAL;
+    auto query_of = [&](int slot) { return (round * QPB + slot) * W + (int)blockIdx.x; };
     auto hdr = [&](int slot, int k) -> float4* { if (SM) return S.h + k * S2MP_QPB + slot; return a.qcache[query_of(slot)].w + k; };
     auto rowp = [&](int slot) -> float4* { if (SM) return S.list + slot * S2M_ROW; return a.cand + (size_t)query_of(slot) * S2M_GROW; };
-    const bool mine = tid < S2MP_QPB && query_of(tid) < n;
+    const bool mine = tid < QPB && query_of(tid) < n;
     float4 ori = ori_keep; float rr = rr_keep;
     if (!SM && mine) { ori = __ldg(a.scan + query_of(tid)); rr = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z)); }
     float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -642,6 +670,7 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
         const bool valid = iter > 0 && cnt >= 0 && moved <= lim && same_cell && !a.no_cache;
         if (!valid) { s_todo[atomicAdd(s_ntodo, 1)] = tid; stq<SM>(hdr(tid, 0), make_float4(sel.x, sel.y, sel.z, __int_as_float(-1))); }
         if (a.dbg_gt && !valid && iter >= 10) atomicAdd(a.dbg_gt + 40 * S2M_GT_STRIDE + blockIdx.x, 1ull);
+        if (a.dbg_gt && !valid && iter >= 10 && h0.x != h0.x) atomicAdd(a.dbg_gt + 43 * S2M_GT_STRIDE + blockIdx.x, 1ull);     // overflowed list
         // iteration 0 never trusts a cached plane (it belongs to an earlier launch / another map)
         if (iter == 0) {
             const float4 none = make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(-1));
@@ -655,12 +684,18 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
         const int slot = s_todo[k];
         const float4 q0 = ldq<SM>(hdr(slot, 0));
         float4* row = rowp(slot);
-        const int c = build_list_half<SM>(q0, a.cell_start, a.gmap, a.g, row);
+        int c = build_list_half<SM>(q0, a.cell_start, a.gmap, a.g, row);
         __syncwarp(0xffffu << (lane_id() & 16));
         unsigned packed = 0;
-        if (c >= 5) packed = top5_positions_half<SM>(q0, row, c);
+        float q0x = q0.x;
+        if (c == -2) {                               // overflow: the five nearest ARE the list, in order; NaN in q0.x keeps it from ever being reused
+            c = exact_top5_half<SM>(q0, a.cell_start, a.gmap, a.g, row);
+            __syncwarp(0xffffu << (lane_id() & 16));
+            packed = 0u | (1u << 6) | (2u << 12) | (3u << 18) | (4u << 24);
+            q0x = __int_as_float(0x7fc00000);
+        } else if (c >= 5) packed = top5_positions_half<SM>(q0, row, c);
         if ((lane_id() & 15) == 0) {
-            stq<SM>(hdr(slot, 0), make_float4(q0.x, q0.y, q0.z, __int_as_float(c)));
+            stq<SM>(hdr(slot, 0), make_float4(q0x, q0.y, q0.z, __int_as_float(c)));
             float4 h3 = ldq<SM>(hdr(slot, 3)); h3.z = __uint_as_float(packed); stq<SM>(hdr(slot, 3), h3);
         }
     }
@@ -668,7 +703,7 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
     if (dbg_p2) *dbg_p2 = clock64();
     if (tid == 0) *s_ntodo = 0;                  // the next phase 1 is at least two barriers away
     // ---- 3. exact 5-NN from the list, plane, weight, Jacobian row ----
-    if (tid < S2MP_QPB) {
+    if (tid < QPB) {
         bool f = false; float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
         float v[8];
         if (mine) {
@@ -735,7 +770,7 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
                         float4 h3n = h3; h3n.z = __uint_as_float(pk); stq<SM>(hdr(tid, 3), h3n);
                     }
                 }
-            } else if (cnt == -2) { knn5_lane(sel, a.cell_start, a.gmap, a.g, nn); if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 43 * S2M_GT_STRIDE + blockIdx.x, 1ull); }
+            }
             const bool have5 = nn.pos[4] != -1 && (double)nn.d[4] < 1.0;                // :1097
             if (have5) {
                 // ---- plane: reuse when the ordered neighbour ids match one of the two cached planes ----
@@ -753,7 +788,7 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
                     float A[5][3];
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        const float4 mpt = cnt >= 0 ? ldq<SM>(row + nn.pos[j]) : __ldg(a.gmap + nn.pos[j]);
+                        const float4 mpt = ldq<SM>(row + nn.pos[j]);
                         A[j][0] = mpt.x; A[j][1] = mpt.y; A[j][2] = mpt.z;
                     }
                     float x[3];
@@ -867,11 +902,11 @@ __device__ __forceinline__ bool lm_solve_warp(int iter, const double* sums, floa
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a) {
     extern __shared__ __align__(16) float4 s_state[];     // S2MP_SMEM bytes: per-query candidate rows + headers (one-round solves)
-    __shared__ int s_todo[S2MP_QPB];
+    __shared__ int s_todo[S2MP_QPB_GLOBAL];
     __shared__ int s_ntodo;
     __shared__ float s_tf[6];
     __shared__ float s_sc[6];                              // cos/sin of yaw, pitch, roll for this iteration
-    __shared__ __align__(16) float s_rows[S2MP_QPB][8];
+    __shared__ __align__(16) float s_rows[S2MP_QPB_GLOBAL][8];
     __shared__ double s_red[S2MP_WARPS][NPROD];
     __shared__ double s_sum[NPROD];
     __shared__ float s_A[36], s_V[36];
@@ -888,7 +923,8 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     const int n = a.n_scan.get();
     const int m = a.m_map.get();
     const bool one_round = !a.global_state && n <= W * S2MP_QPB;              // query state in registers / shared memory
-    const int rounds = one_round ? 1 : (n + W * S2MP_QPB - 1) / (W * S2MP_QPB);
+    const int qpb = one_round ? S2MP_QPB : S2MP_QPB_GLOBAL;
+    const int rounds = one_round ? 1 : (n + W * qpb - 1) / (W * qpb);
     S2MShared S; S.list = s_state; S.h = s_state + S2MP_QPB * S2M_ROW;
     if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
     if (threadIdx.x == 32) { s_conv = 0; s_ntodo = 0; }
@@ -931,7 +967,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
                     if (dbg && round == rounds - 1) a.dbg[iter * 8 + 1] = clock64();
                     __syncthreads();
                     if (k16 < S2MP_WARPS) {               // 16 chains x 28 products, chain k takes this round's queries k, k + 16, ... in ascending order
-                        const int nq = max(0, min(S2MP_QPB, (n - (int)blockIdx.x + W - 1) / W - round * S2MP_QPB));
+                        const int nq = max(0, min(qpb, (n - (int)blockIdx.x + W - 1) / W - round * qpb));
                         for (int q = k16; q < nq; q += S2MP_WARPS) sacc += (double)s_rows[q][pi16] * (double)s_rows[q][pj16];
                     }
                     if (round + 1 < rounds) __syncthreads();      // the next round overwrites the rows

@@ -77,8 +77,8 @@ def main():
     g = np.array(list(gb), np.int64).reshape(64, 160)
     W = int(np.count_nonzero(g[1, :156]))
     ev = g[40:44, :W]
-    print("   events over iterations 10..29 (all workers): list rebuilds %d, ordered insert passes %d, plane refits %d, one-thread searches %d" % tuple(ev.sum(1)))
-    for nm, row in zip(["rebuilds", "insert passes", "refits", "one-thread searches"], ev):
+    print("   events over iterations 10..29 (all workers): list rebuilds %d, ordered insert passes %d, plane refits %d, overflowed lists %d" % tuple(ev.sum(1)))
+    for nm, row in zip(["rebuilds", "insert passes", "refits", "overflowed lists"], ev):
         top = np.argsort(row)[-3:][::-1]
         print(f"      most {nm}: " + ", ".join(f"worker {int(w)}: {int(row[w])}" for w in top))
     prev_pub = None
