@@ -322,7 +322,9 @@ int liorf_get_timing(liorf_ctx* ctx, double ms[8], long long calls[8]);
 long long liorf_get_launch_count(liorf_ctx* ctx);                     /* kernels launched by this context so far */
 int liorf_get_last_counts(liorf_ctx* ctx, int* n_scan, int* n_ds, int* m_ds, int* iters);   /* as of the last liorf_get_pose */
 int liorf_debug_qr_solve6(liorf_ctx* ctx, const float* A, const float* b, int n, float* x);   /* tests: the device routine behind cv::solve(DECOMP_QR) 6x6 (src/mapOptmization.cpp:1240) */
-int liorf_debug_force_large_voxelgrid(liorf_ctx* ctx, int on);   /* tests: multi-kernel VoxelGrid path on small clouds too */
+int liorf_debug_force_large_voxelgrid(liorf_ctx* ctx, int on);   /* tests: multi-kernel VoxelGrid path on every cloud */
+int liorf_debug_voxelgrid_stamps(liorf_ctx* ctx, int enable, unsigned long long* out /* 32, nullable */);   /* debug: phase stamps of the one-kernel VoxelGrid */
+int liorf_debug_force_fused_voxelgrid(liorf_ctx* ctx, int on);   /* tests: one-kernel cooperative VoxelGrid path on small clouds too */
 int liorf_debug_s2m_global_state(liorf_ctx* ctx, int on);          /* tests: solver keeps per-query state in global memory (the multi-round layout) */
 int liorf_debug_s2m_disable_cache(liorf_ctx* ctx, int on);        /* tests: full 27-cell search + plane refit every iteration */
 int liorf_debug_s2m_clocks(liorf_ctx* ctx, int enable, long long* out /* 64*8, nullable */);

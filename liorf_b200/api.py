@@ -376,6 +376,9 @@ class Context:
     def disableSolverCache(self, on=True):
         _chk(self.lib.liorf_debug_s2m_disable_cache(self.h, C.c_int(int(on))), "liorf_debug_s2m_disable_cache")
 
+    def forceFusedVoxelGrid(self, on=True):
+        _chk(self.lib.liorf_debug_force_fused_voxelgrid(self.h, C.c_int(int(on))), "liorf_debug_force_fused_voxelgrid")
+
     def forceLargeVoxelGrid(self, on=True):
         _chk(self.lib.liorf_debug_force_large_voxelgrid(self.h, C.c_int(int(on))), "liorf_debug_force_large_voxelgrid")
 

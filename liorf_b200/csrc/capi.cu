@@ -316,6 +316,9 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
     c->combine_scan.ticket = c->d_tick + 4; c->combine_scan.err_flag = c->d_err;
     int* lm_counter = c->d_misc + 7; (void)lm_counter;
     CUDA_TRY(cudaMalloc(&c->vg.meta, sizeof(VoxMeta)));
+    for (VoxelGridWork* vw : {&c->vg, &c->vg_map, &c->alt.vg}) {          // grid-barrier words of the one-kernel VoxelGrid
+        CUDA_TRY(cudaMalloc(&vw->fused_bar, 2 * sizeof(unsigned))); CUDA_TRY(cudaMemset(vw->fused_bar, 0, 2 * sizeof(unsigned))); vw->err_flag = c->d_err;
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_map, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->vg_map.meta, sizeof(VoxMeta)));
@@ -426,6 +429,7 @@ void liorf_destroy(liorf_ctx* c) {
     c->icp_nn_d2.release(); c->icp_grid.counts.release(); c->icp_grid.cell_start.release(); c->icp_grid.sorted.release(); c->icp_grid.scan.status.release();
     if (c->icp_out) cudaFree(c->icp_out);
     if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
+    for (VoxelGridWork* vw : {&c->vg, &c->vg_map, &c->alt.vg}) { vw->pts_sorted.release(); vw->cta_hist.release(); vw->cta_heads.release(); if (vw->fused_bar) cudaFree(vw->fused_bar); vw->fused_bar = nullptr; }
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_wpart); cudaFree(c->d_res); cudaFree(c->d_mail); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
@@ -578,14 +582,15 @@ int liorf_set_current_scan_dev(liorf_ctx* c, const void* d_scan, int n) {
     return set_scan_common(c, d_scan, n, cudaMemcpyDeviceToDevice);
 }
 
-static int downsample_async(liorf_ctx* c, int* d_membership) {
+// coop_grid: CTAs of the one-kernel VoxelGrid (all SMs for a standalone call, the SMs the solver leaves free for the look-ahead front end)
+static int downsample_async(liorf_ctx* c, int* d_membership, int coop_grid) {
     int rc;
     const int nb = c->n_scan_bound;
     if ((rc = c->scan_ds.reserve(nb > 0 ? nb : 1))) return rc;
     c->h_n_ds = -1;
     Count cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, nb);
     ProfScope ps(c, SEC_DOWNSAMPLE); c->launches += 9;
-    return voxel_grid_device(c->scan.p, cnt, c->P.mappingSurfLeafSize, c->scan_ds.p, c->d_counts + C_N_DS, d_membership, nullptr, c->vg, c->stream);
+    return voxel_grid_device(c->scan.p, cnt, c->P.mappingSurfLeafSize, c->scan_ds.p, c->d_counts + C_N_DS, d_membership, nullptr, c->vg, c->stream, coop_grid);
 }
 
 int liorf_downsample_current_scan(liorf_ctx* c, liorf_point* out, int* n_ds, int* membership) {
@@ -595,7 +600,7 @@ int liorf_downsample_current_scan(liorf_ctx* c, liorf_point* out, int* n_ds, int
     int rc;
     int* d_mem = nullptr;
     if (membership) { if ((rc = c->membership.reserve(c->n_scan_bound > 0 ? c->n_scan_bound : 1))) return rc; d_mem = c->membership.p; }
-    if ((rc = downsample_async(c, d_mem))) return rc;
+    if ((rc = downsample_async(c, d_mem, c->num_sms))) return rc;
     if (!out && !n_ds && !membership) return LIORF_OK;           // stay asynchronous
     if ((rc = read_counts(c))) return rc;
     if (n_ds) *n_ds = c->h_n_ds;
@@ -616,7 +621,7 @@ int liorf_voxel_grid(liorf_ctx* c, const liorf_point* in, int n, float leaf, lio
     if ((rc = c->membership.reserve(cap))) return rc;
     if ((rc = c->out_keys.reserve(cap))) return rc;
     if (n > 0) CUDA_TRY(cudaMemcpyAsync(c->map_raw.p, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-    rc = voxel_grid_device(c->map_raw.p, Count::of_host(n), leaf, tmp_out.p, c->d_counts + C_NSEL, c->membership.p, c->out_keys.p, c->vg, c->stream);
+    rc = voxel_grid_device(c->map_raw.p, Count::of_host(n), leaf, tmp_out.p, c->d_counts + C_NSEL, c->membership.p, c->out_keys.p, c->vg, c->stream, c->num_sms);
     if (rc) { tmp_out.release(); return rc; }
     CUDA_TRY(cudaMemcpyAsync(c->h_mail + 200, c->d_counts + C_NSEL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1321,7 +1326,27 @@ int liorf_debug_qr_solve6(liorf_ctx* c, const float* A, const float* b, int n, f
 int liorf_debug_force_large_voxelgrid(liorf_ctx* c, int on) {
     LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
-    c->vg.force_large = c->vg_map.force_large = on != 0;
+    c->vg.force_large = c->vg_map.force_large = c->alt.vg.force_large = on != 0;
+    c->vg.force_multi = c->vg_map.force_multi = c->alt.vg.force_multi = on != 0;
+    return LIORF_OK;
+}
+/* debug: %globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last one-kernel VoxelGrid of the scan side */
+int liorf_debug_voxelgrid_stamps(liorf_ctx* c, int enable, unsigned long long* out /* 32, nullable */) {
+    LIORF_NVTX;
+    if (!c) return LIORF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->P.device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (enable && !c->vg.dbg) { CUDA_TRY(cudaMalloc(&c->vg.dbg, 32 * sizeof(unsigned long long))); CUDA_TRY(cudaMemset(c->vg.dbg, 0, 32 * sizeof(unsigned long long))); }
+    if (out && c->vg.dbg) CUDA_TRY(cudaMemcpy(out, c->vg.dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (!enable && c->vg.dbg) { cudaFree(c->vg.dbg); c->vg.dbg = nullptr; }
+    return LIORF_OK;
+}
+/* tests: 1 = run the one-kernel cooperative VoxelGrid path on small clouds too; 0 = automatic */
+int liorf_debug_force_fused_voxelgrid(liorf_ctx* c, int on) {
+    LIORF_NVTX;
+    if (!c) return LIORF_ERR_ARG;
+    c->vg.force_large = c->vg_map.force_large = c->alt.vg.force_large = on != 0;
+    c->vg.force_multi = c->vg_map.force_multi = c->alt.vg.force_multi = false;
     return LIORF_OK;
 }
 /* selects the ring-key search implementation: 0 auto, 1 CUDA-core brute force, 2 tensor-core filter + exact re-rank */
@@ -1865,7 +1890,7 @@ static int front_prefetch(liorf_ctx* c, const liorf_frame_in* nx) {
         else rc = liorf_project_point_cloud(c, (const liorf_point_xyzirt*)nx->pts, nx->n, nx->time_scan_cur, nx->imu_time, nx->imu_rot_x, nx->imu_rot_y,
                                             nx->imu_rot_z, nx->imu_pointer_cur, nx->deskew_enabled, nullptr, nullptr, nullptr);
     }
-    if (!rc) rc = downsample_async(c, nullptr);
+    if (!rc) rc = downsample_async(c, nullptr, c->num_sms - c->s2m_grid >= 4 ? c->num_sms - c->s2m_grid : 0);      // beside the solver: its spare SMs
     if (!rc && cudaEventRecord(c->ev_pre_done, c->stream_pre) != cudaSuccess) rc = LIORF_ERR_CUDA;
     c->stream = main_stream;
     front_swap(c);

@@ -10,6 +10,7 @@
 //   k_vg_centroid : one thread per voxel; sequential fp32 sums in ascending input index, divided by (float)count
 // HBM traffic (algorithmic): 16 N in + 16 N_out out; the sort moves 8 N per pass on top (L2 resident for one scan).
 #pragma once
+#include <cstdlib>
 #include "prims.cuh"
 
 namespace liorf {
@@ -33,6 +34,12 @@ struct VoxelGridWork {
     ScanWork scan;
     bool small_attr_set = false;
     bool force_large = false;       // tests: run the multi-kernel path on small clouds too
+    // one-kernel path (k_vg_fused)
+    DevBuf<float4> pts_sorted; DevBuf<unsigned> cta_hist; DevBuf<unsigned> cta_heads;
+    unsigned* fused_bar = nullptr;  // device [2], zero-initialised once
+    int* err_flag = nullptr;
+    bool force_multi = false;       // tests: never take the one-kernel path
+    unsigned long long* dbg = nullptr;   // debug: phase stamps of the one-kernel path
 };
 
 constexpr int VG_MM_BLOCK = 256;
@@ -337,12 +344,378 @@ __global__ void __launch_bounds__(VGS_THREADS, 1) k_vg_small(const float4* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Larger clouds (a 120 k-point scan, a 650 k-point local map): the whole filter as ONE cooperative kernel.
+// The multi-kernel path below spends 93 us on a KITTI scan — ten dependent launches whose kernels are each latency-bound (a
+// look-back chain over 58 tiles per radix pass, a centroid kernel that chases index → point through L2 four points at a time).
+// Here the CTAs stay resident, each owns a CONTIGUOUS chunk of the points (chunk order == input order, which is what keeps the
+// sort stable), and the phases are separated by a grid barrier of ~1 us:
+//   bounds      block min/max → per-CTA partials | barrier | every CTA folds the partials and derives PCL's min_b / div_b itself
+//   radix pass  (only as many 8-bit passes as the largest voxel index has bits: 3 for a KITTI scan at 0.4 m)
+//               per-CTA digit histogram of the chunk | barrier | every CTA sums the histograms of the CTAs before it (and all of
+//               them: the digit bases) — 148 x 1 KB, no look-back chain | stable scatter of the chunk, tile by tile | barrier.
+//               Pass 0 computes the voxel index from the point (no key kernel); a chunk of one tile keeps keys, values and ranks
+//               in registers between histogram and scatter; the LAST pass also moves the 16-byte point to its sorted place.
+//   heads       per-CTA count of segment heads | barrier | segment starts written at (heads of earlier CTAs) + local rank | barrier
+//   centroids   one thread per voxel over CONTIGUOUS points: sequential fp32 sums in ascending input index (the stable sort's
+//               order), eight loads in flight.
+// Results are bit-identical to the multi-kernel path (tests force either).  The grid is chosen by the caller: all SMs, or the few
+// SMs the persistent solver leaves free when the next frame's front end runs beside it.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int VGF_THREADS = 512;
+constexpr int VGF_WARPS = VGF_THREADS / 32;
+constexpr int VGF_IPT = 2;
+constexpr int VGF_TILE = VGF_THREADS * VGF_IPT;        // 1024 points per tile
+constexpr int VGF_PF = 10;                             // histogram rows a thread of the prefix step keeps in flight (2 x 10 x 8 covers 148 CTAs)
+
+struct VgFusedArgs {
+    const float4* pts; Count cnt; float leaf;
+    float4* out; int* n_out; int* membership; int* out_keys; VoxMeta* meta;
+    unsigned* keys_a; unsigned* keys_b; unsigned* vals_a; unsigned* vals_b;      // ping-pong (key, input index)
+    float4* pts_sorted; unsigned* seg_start;
+    float* partial_mm;            // [grid][6]
+    unsigned* cta_hist;           // [grid][RADIX]
+    unsigned* cta_heads;          // [grid]
+    unsigned* bar;                // [2]: arrivals, generation (zero-initialised once; reusable across launches)
+    int* err_flag;
+    unsigned long long* dbg;      // optional [32] %globaltimer stamps of CTA 0 at the phase boundaries (nullptr = off)
+};
+
+// grid barrier for co-resident CTAs: arrivals are counted in ONE monotonic word per launch (barrier k is complete at (k + 1) x grid);
+// a CTA arrives with a fire-and-forget red.release (its threads' earlier writes are ordered before it by the CTA barrier in front) and
+// polls with ld.acquire — one fence, no atomic round trip, no reset between barriers.  The last CTA to LEAVE the kernel zeroes the
+// words for the next launch (vgf_finish).
+__device__ __forceinline__ void vgf_grid_barrier(unsigned* bar, unsigned& gen, int* err_flag) {
+    __syncthreads();
+    ++gen;
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        const unsigned target = gen * gridDim.x;
+        unsigned v, spins = 0;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
+            if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void vgf_finish(unsigned* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1) { bar[0] = 0u; bar[1] = 0u; __threadfence(); }
+}
+
+__device__ __forceinline__ unsigned vgf_key(const float4 p, float inv, int b0, int b1, int b2, int m1, int m2) {
+    const int i0 = (int)(floorf(p.x * inv) - (float)b0), i1 = (int)(floorf(p.y * inv) - (float)b1), i2 = (int)(floorf(p.z * inv) - (float)b2);
+    return (unsigned)(i0 + i1 * m1 + i2 * m2);
+}
+
+__global__ void __launch_bounds__(VGF_THREADS, 1) k_vg_fused(VgFusedArgs a) {
+    __shared__ float s_red[VGF_WARPS][6];
+    __shared__ VoxMeta s_meta;
+    __shared__ unsigned s_whist[VGF_WARPS][RADIX];      // per-warp digit counts of a tile → exclusive warp offsets
+    __shared__ unsigned s_hist[RADIX];                  // digit counts of the CTA's chunk
+    __shared__ unsigned s_run[RADIX];                   // next output position per digit
+    __shared__ unsigned s_warp[VGF_WARPS + 1];
+    __shared__ uint4 s_part4[2][8][RADIX / 4];          // prefix step: (before me | all) x 8 row groups x 64 digit quads
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+    const int n = a.cnt.get();
+    unsigned gen = 0;                                    // barriers passed so far (every thread counts along)
+    int dbg_k = 0;
+    auto stamp = [&]() { if (a.dbg && c == 0 && tid == 0 && dbg_k < 32) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[dbg_k] = t; } ++dbg_k; };
+    stamp();
+    if (n <= 0) { if (c == 0 && tid == 0) *a.n_out = 0; return; }        // (no barrier was entered: the words stay zero)
+    // ---- bounds (min/max are order independent) ----
+    {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = c * VGF_THREADS + tid; i < n; i += G * VGF_THREADS) {
+            const float4 p = a.pts[i];
+            mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+            mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+            mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(FULL, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(FULL, mx[k], o)); }
+        if (l == 0) { for (int k = 0; k < 3; ++k) { s_red[w][k] = mn[k]; s_red[w][3 + k] = mx[k]; } }
+        __syncthreads();
+        if (tid < 6) {
+            float v = s_red[0][tid];
+            for (int ww = 1; ww < VGF_WARPS; ++ww) v = tid < 3 ? fminf(v, s_red[ww][tid]) : fmaxf(v, s_red[ww][tid]);
+            __stcg(a.partial_mm + c * 6 + tid, v);
+        }
+        stamp();
+        vgf_grid_barrier(a.bar, gen, a.err_flag);
+        stamp();
+        if (w == 0) {
+            for (int k = 0; k < 3; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+            for (int b = l; b < G; b += 32)
+                for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], __ldcg(a.partial_mm + b * 6 + k)); mx[k] = fmaxf(mx[k], __ldcg(a.partial_mm + b * 6 + 3 + k)); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(FULL, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(FULL, mx[k], o)); }
+            if (l == 0) {
+                VoxMeta m;
+                m.n = n;
+                m.inv = 1.0f / a.leaf;
+                long long d[3];
+                for (int k = 0; k < 3; ++k) {
+                    m.minp[k] = mn[k]; m.maxp[k] = mx[k];
+                    d[k] = (long long)((mx[k] - mn[k]) * m.inv) + 1;
+                    m.min_b[k] = (int)floorf(mn[k] * m.inv);
+                    const int max_b = (int)floorf(mx[k] * m.inv);
+                    m.div_b[k] = max_b - m.min_b[k] + 1;
+                }
+                m.overflow = (d[0] * d[1] * d[2] > 2147483647LL) ? 1 : 0;
+                m.mul1 = m.div_b[0]; m.mul2 = m.div_b[0] * m.div_b[1];
+                s_meta = m;
+                if (c == 0) *a.meta = m;
+            }
+        }
+        __syncthreads();
+    }
+    const float inv = s_meta.inv; const int b0 = s_meta.min_b[0], b1 = s_meta.min_b[1], b2 = s_meta.min_b[2], m1 = s_meta.mul1, m2 = s_meta.mul2;
+    if (s_meta.overflow) {
+        // PCL: "Leaf size is too small for the input dataset" → output = input (every point its own voxel, key = index)
+        for (int i = c * VGF_THREADS + tid; i < n; i += G * VGF_THREADS) {
+            const float4 p = a.pts[i];
+            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+            sx += p.x; sy += p.y; sz += p.z; si += p.w;
+            a.out[i] = make_float4(sx / 1.f, sy / 1.f, sz / 1.f, si / 1.f);
+            if (a.membership) a.membership[i] = i;
+            if (a.out_keys) a.out_keys[i] = i;
+            a.seg_start[i] = (unsigned)i;
+        }
+        if (c == 0 && tid == 0) { a.seg_start[n] = (unsigned)n; *a.n_out = n; }
+        vgf_finish(a.bar);
+        return;
+    }
+    const unsigned max_key = (unsigned)((long long)s_meta.div_b[0] * s_meta.div_b[1] * s_meta.div_b[2] - 1);
+    const int bits = 32 - __clz(max_key | 1u);
+    const int npass = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    // the CTA's chunk of the input order: whole tiles, contiguous
+    const int chunk = (((n + G - 1) / G + VGF_TILE - 1) / VGF_TILE) * VGF_TILE;
+    const int lo = min(n, c * chunk), hi = min(n, lo + chunk);
+    const bool one_tile = chunk == VGF_TILE;
+    const unsigned lt_mask = (1u << l) - 1u;
+    unsigned* kin = a.keys_a; unsigned* kout = a.keys_b; unsigned* vin = a.vals_a; unsigned* vout = a.vals_b;
+    for (int pass = 0; pass < npass; ++pass) {
+        const int shift = RADIX_BITS * pass;
+        const bool last = pass == npass - 1;
+        unsigned key[VGF_IPT], val[VGF_IPT], rank[VGF_IPT];
+        // element e of a tile is (warp, j, lane): index = tile base + w * 64 + j * 32 + l — ascending in (w, j, l)
+        auto load_tile = [&](int tb) {
+#pragma unroll
+            for (int j = 0; j < VGF_IPT; ++j) {
+                const int i = tb + w * (32 * VGF_IPT) + j * 32 + l;
+                const bool valid = i < hi;
+                if (pass == 0) { key[j] = valid ? vgf_key(a.pts[i], inv, b0, b1, b2, m1, m2) : 0xffffffffu; val[j] = (unsigned)i; }
+                else { key[j] = valid ? kin[i] : 0xffffffffu; val[j] = valid ? vin[i] : 0u; }
+            }
+        };
+        // per-warp stable ranks of a loaded tile (s_whist[w] must be zero on entry); leaves the warp's digit counts in s_whist[w]
+        auto rank_tile = [&](int tb) {
+#pragma unroll
+            for (int j = 0; j < VGF_IPT; ++j) {
+                const int i = tb + w * (32 * VGF_IPT) + j * 32 + l;
+                const bool valid = i < hi;
+                const unsigned d = (key[j] >> shift) & (RADIX - 1);
+                const unsigned vm = __ballot_sync(FULL, valid);
+                const unsigned mm = __match_any_sync(FULL, d) & vm;
+                unsigned old = 0;
+                const int leader = __ffs(mm) - 1;
+                if (valid && l == leader) { old = s_whist[w][d]; s_whist[w][d] = old + __popc(mm); }
+                __syncwarp();
+                old = __shfl_sync(FULL, old, leader < 0 ? 0 : leader);
+                rank[j] = old + __popc(mm & lt_mask);
+            }
+        };
+        // ---- histogram of the chunk ----
+        for (int i = tid; i < VGF_WARPS * RADIX; i += VGF_THREADS) (&s_whist[0][0])[i] = 0;
+        if (tid < RADIX) s_hist[tid] = 0;
+        __syncthreads();
+        if (one_tile) {
+            load_tile(lo); rank_tile(lo);
+            __syncthreads();
+            if (tid < RADIX) { unsigned run = 0; for (int ww = 0; ww < VGF_WARPS; ++ww) { const unsigned v = s_whist[ww][tid]; s_whist[ww][tid] = run; run += v; } s_hist[tid] = run; }
+        } else {
+            for (int tb = lo; tb < hi; tb += VGF_TILE) {
+                load_tile(tb);
+#pragma unroll
+                for (int j = 0; j < VGF_IPT; ++j) {
+                    const int i = tb + w * (32 * VGF_IPT) + j * 32 + l;
+                    const bool valid = i < hi;
+                    const unsigned d = (key[j] >> shift) & (RADIX - 1);
+                    const unsigned mm = __match_any_sync(FULL, d) & __ballot_sync(FULL, valid);
+                    if (valid && l == __ffs(mm) - 1) atomicAdd(&s_hist[d], (unsigned)__popc(mm));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < RADIX) __stcg(a.cta_hist + (size_t)c * RADIX + tid, s_hist[tid]);
+        stamp();
+        vgf_grid_barrier(a.bar, gen, a.err_flag);
+        stamp();
+        // ---- digit bases + what the CTAs before this one hold of each digit ----
+        {   // thread (g, q): rows g, g + 8, ... of the histogram matrix, digits 4q .. 4q + 3 as one 16-byte load — all of a thread's ~19 loads in flight at once
+            const int q = tid & 63, g = tid >> 6;
+            uint4 pre = make_uint4(0, 0, 0, 0), tot = make_uint4(0, 0, 0, 0);
+            const uint4* H = reinterpret_cast<const uint4*>(a.cta_hist);
+            for (int c0 = g; c0 < G; c0 += 8 * VGF_PF) {              // VGF_PF rows per thread in flight
+                uint4 v[VGF_PF];
+#pragma unroll
+                for (int u = 0; u < VGF_PF; ++u) { const int cc = c0 + 8 * u; v[u] = cc < G ? __ldcg(H + (size_t)cc * (RADIX / 4) + q) : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+                for (int u = 0; u < VGF_PF; ++u) {
+                    tot.x += v[u].x; tot.y += v[u].y; tot.z += v[u].z; tot.w += v[u].w;
+                    if (c0 + 8 * u < c) { pre.x += v[u].x; pre.y += v[u].y; pre.z += v[u].z; pre.w += v[u].w; }
+                }
+            }
+            s_part4[0][g][q] = pre; s_part4[1][g][q] = tot;
+            __syncthreads();
+            unsigned mypre = 0, mytot = 0;
+            if (tid < RADIX) {
+                const unsigned* P0 = reinterpret_cast<const unsigned*>(&s_part4[0][0][0]);
+                const unsigned* P1 = reinterpret_cast<const unsigned*>(&s_part4[1][0][0]);
+#pragma unroll
+                for (int gg = 0; gg < 8; ++gg) { mypre += P0[gg * RADIX + tid]; mytot += P1[gg * RADIX + tid]; }
+            }
+            unsigned total;
+            const unsigned goff = block_excl_scan<VGF_THREADS>(mytot, s_warp, total);      // threads 0..255 hold the digits in order, the rest add 0 behind them
+            if (tid < RADIX) s_run[tid] = goff + mypre;
+            __syncthreads();
+        }
+        stamp();
+        // ---- stable scatter ----
+        if (one_tile) {
+#pragma unroll
+            for (int j = 0; j < VGF_IPT; ++j) {
+                const int i = lo + w * (32 * VGF_IPT) + j * 32 + l;
+                if (i < hi) {
+                    const unsigned d = (key[j] >> shift) & (RADIX - 1);
+                    const unsigned pos = s_run[d] + s_whist[w][d] + rank[j];
+                    kout[pos] = key[j]; vout[pos] = val[j];
+                    if (last) a.pts_sorted[pos] = a.pts[val[j]];
+                }
+            }
+        } else {
+            for (int tb = lo; tb < hi; tb += VGF_TILE) {
+                for (int i = tid; i < VGF_WARPS * RADIX; i += VGF_THREADS) (&s_whist[0][0])[i] = 0;
+                __syncthreads();
+                load_tile(tb); rank_tile(tb);
+                __syncthreads();
+                unsigned tile_total = 0;
+                if (tid < RADIX) { unsigned run = 0; for (int ww = 0; ww < VGF_WARPS; ++ww) { const unsigned v = s_whist[ww][tid]; s_whist[ww][tid] = run; run += v; } tile_total = run; }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < VGF_IPT; ++j) {
+                    const int i = tb + w * (32 * VGF_IPT) + j * 32 + l;
+                    if (i < hi) {
+                        const unsigned d = (key[j] >> shift) & (RADIX - 1);
+                        const unsigned pos = s_run[d] + s_whist[w][d] + rank[j];
+                        kout[pos] = key[j]; vout[pos] = val[j];
+                        if (last) a.pts_sorted[pos] = a.pts[val[j]];
+                    }
+                }
+                __syncthreads();
+                if (tid < RADIX) s_run[tid] += tile_total;
+            }
+        }
+        stamp();
+        vgf_grid_barrier(a.bar, gen, a.err_flag);
+        stamp();
+        { unsigned* t = kin; kin = kout; kout = t; t = vin; vin = vout; vout = t; }
+    }
+    // sorted (key, input index) now in kin / vin, the points in pts_sorted
+    // ---- segment heads: count per chunk | barrier | every head's thread sums its segment ----
+    // (item pair of thread t in a tile: tb + 2t, tb + 2t + 1 — contiguous, so the block scan numbers the heads in ascending order)
+    {
+        auto is_head = [&](int i) { return i < hi && (i == 0 || kin[i] != kin[i - 1]); };
+        unsigned f0r = 0, f1r = 0;                         // a chunk of one tile keeps its flags across the barrier
+        unsigned cnt_local = 0;
+        for (int tb = lo; tb < hi; tb += VGF_TILE) {
+            const int i0 = tb + tid * VGF_IPT;
+            f0r = is_head(i0) ? 1u : 0u; f1r = is_head(i0 + 1) ? 1u : 0u;
+            cnt_local += f0r + f1r;
+        }
+        unsigned total;
+        (void)block_excl_scan<VGF_THREADS>(cnt_local, s_warp, total);
+        if (tid == 0) __stcg(a.cta_heads + c, total);
+        stamp();
+        vgf_grid_barrier(a.bar, gen, a.err_flag);
+        stamp();
+        unsigned pre = 0, tot = 0;
+        for (int cc = tid; cc < G; cc += VGF_THREADS) { const unsigned v = __ldcg(a.cta_heads + cc); tot += v; if (cc < c) pre += v; }
+        unsigned t1, t2;
+        (void)block_excl_scan<VGF_THREADS>(pre, s_warp, t1);
+        (void)block_excl_scan<VGF_THREADS>(tot, s_warp, t2);
+        unsigned slot_base = t1;
+        if (c == 0 && tid == 0) { *a.n_out = (int)t2; a.seg_start[t2] = (unsigned)n; }
+        for (int tb = lo; tb < hi; tb += VGF_TILE) {
+            const int i0 = tb + tid * VGF_IPT;
+            unsigned f[VGF_IPT];
+            if (one_tile) { f[0] = f0r; f[1] = f1r; } else { f[0] = is_head(i0) ? 1u : 0u; f[1] = is_head(i0 + 1) ? 1u : 0u; }
+            unsigned tile_total;
+            const unsigned off = block_excl_scan<VGF_THREADS>(f[0] + f[1], s_warp, tile_total);
+            unsigned slot = slot_base + off;
+#pragma unroll
+            for (int j = 0; j < VGF_IPT; ++j) {
+                if (!f[j]) continue;
+                // centroid of the voxel that starts at item i0 + j: sequential fp32 sums over the contiguous sorted points (ascending input
+                // index within a voxel: the sort is stable), divided by (float)count; the segment ends where the key changes
+                const unsigned b = (unsigned)(i0 + j);
+                const unsigned key = kin[b];
+                float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+                unsigned k = b; bool open = true;
+                while (open) {
+                    float4 p[8]; unsigned kk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const unsigned idx = k + u; const bool in = idx < (unsigned)n; kk[u] = in ? __ldcg(kin + idx) : ~key; p[u] = in ? __ldcg(a.pts_sorted + idx) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (open && kk[u] == key) { sx += p[u].x; sy += p[u].y; sz += p[u].z; si += p[u].w; ++k; }
+                        else open = false;
+                    }
+                }
+                const float cn = (float)(k - b);
+                a.seg_start[slot] = b;
+                a.out[slot] = make_float4(sx / cn, sy / cn, sz / cn, si / cn);
+                if (a.out_keys) a.out_keys[slot] = (int)key;
+                if (a.membership) for (unsigned m2 = b; m2 < k; ++m2) a.membership[__ldcg(vin + m2)] = (int)slot;
+                ++slot;
+            }
+            slot_base += tile_total;
+        }
+    }
+    stamp();
+    vgf_finish(a.bar);
+}
+
 // out must hold cnt.bound points.  n_out_dev receives the voxel count (device int).
+// coop_grid > 0: clouds beyond the single-CTA size take the one-kernel cooperative path on that many CTAs (one per SM).
 inline int voxel_grid_device(const float4* in, Count cnt, float leaf, float4* out, int* n_out_dev, int* membership, int* out_keys,
-                             VoxelGridWork& w, cudaStream_t s) {
+                             VoxelGridWork& w, cudaStream_t s, int coop_grid = 0) {
     const int nb = cnt.bound;
     if (nb <= 0) { CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(int), s)); return LIORF_OK; }
     int rc;
+    if (coop_grid > 0 && w.fused_bar && !w.force_multi && (nb > VGS_CAP || w.force_large)) {
+        if ((rc = w.keys.reserve(nb)) || (rc = w.sort.keys_alt.reserve(nb)) || (rc = w.sort.vals_a.reserve(nb)) || (rc = w.sort.vals_b.reserve(nb)) ||
+            (rc = w.seg_start.reserve((size_t)nb + 1)) || (rc = w.pts_sorted.reserve(nb)) || (rc = w.partial.reserve((size_t)coop_grid * 6)) ||
+            (rc = w.cta_hist.reserve((size_t)coop_grid * RADIX)) || (rc = w.cta_heads.reserve(coop_grid))) return rc;
+        VgFusedArgs a;
+        a.pts = in; a.cnt = cnt; a.leaf = leaf; a.out = out; a.n_out = n_out_dev; a.membership = membership; a.out_keys = out_keys; a.meta = w.meta;
+        a.keys_a = w.keys.p; a.keys_b = w.sort.keys_alt.p; a.vals_a = w.sort.vals_a.p; a.vals_b = w.sort.vals_b.p;
+        a.pts_sorted = w.pts_sorted.p; a.seg_start = w.seg_start.p; a.partial_mm = w.partial.p; a.cta_hist = w.cta_hist.p; a.cta_heads = w.cta_heads.p;
+        a.bar = w.fused_bar; a.err_flag = w.err_flag; a.dbg = w.dbg;
+        void* args[] = {&a};
+        static const bool plain_launch = std::getenv("LIORF_VG_PLAIN_LAUNCH") != nullptr;     // experiment: launch latency of a cooperative launch
+        if (plain_launch) k_vg_fused<<<coop_grid, VGF_THREADS, 0, s>>>(a);
+        else CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_vg_fused, dim3(coop_grid), dim3(VGF_THREADS), args, 0, s));
+        return LIORF_OK;
+    }
     if (nb <= VGS_CAP && !w.force_large) {
         if ((rc = w.seg_start.reserve((size_t)nb + 1))) return rc;
         if (!w.small_attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_vg_small, cudaFuncAttributeMaxDynamicSharedMemorySize, VGS_SMEM)); w.small_attr_set = true; }

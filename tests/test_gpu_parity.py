@@ -19,27 +19,33 @@ def test_voxel_grid_random(ctx, oracle, n, leaf, seed):
     rng = np.random.default_rng(seed)
     pts = rng.uniform(-40, 40, size=(n, 4)).astype(np.float32)
     pts[:, 2] *= 0.1
-    out, mem, keys = ctx.voxelGrid(pts, leaf)
     o_out, o_mem, o_keys = oracle.voxel_grid(pts, leaf)
-    assert len(out) == len(o_out)
-    assert np.array_equal(mem, o_mem)            # voxel membership bit-exact
-    assert np.array_equal(keys, o_keys)          # ascending linear voxel index
-    assert np.array_equal(out, o_out)            # canonical order ⇒ centroids bit-exact too
+    for path in ("auto", "multi"):                # auto: one CTA up to 3072 points, the one-kernel cooperative path beyond; multi: the multi-kernel radix path
+        ctx.forceLargeVoxelGrid(path == "multi")
+        out, mem, keys = ctx.voxelGrid(pts, leaf)
+        assert len(out) == len(o_out), path
+        assert np.array_equal(mem, o_mem), path      # voxel membership bit-exact
+        assert np.array_equal(keys, o_keys), path    # ascending linear voxel index
+        assert np.array_equal(out, o_out), path      # canonical order ⇒ centroids bit-exact too
+    ctx.forceLargeVoxelGrid(False)
 
 
 @pytest.mark.parametrize("n", [1, 2, 767, 768, 769, 3071, 3072, 3073, 20000])
 def test_voxel_grid_small_and_large_paths_agree(ctx, oracle, n):
-    """clouds of <= 3072 points take the single-CTA kernel (radix sort in shared memory), larger ones the multi-kernel
-    radix path; both must give the oracle's result bit for bit, including at the capacity boundary."""
+    """clouds of <= 3072 points take the single-CTA kernel (radix sort in shared memory), larger ones the one-kernel cooperative path
+    (k_vg_fused; the multi-kernel radix path remains for work areas that cannot launch cooperatively); all three must give the oracle's
+    result bit for bit, including at the capacity boundary and for clouds much smaller than the grid."""
     rng = np.random.default_rng(n)
     pts = rng.uniform(-30, 30, size=(n, 4)).astype(np.float32); pts[:, 2] *= 0.05
     pts[n // 2:] = pts[:n - n // 2] + np.float32(0.01)        # many multi-point voxels
     o_out, o_mem, o_keys = oracle.voxel_grid(pts, 0.4)
-    for force_large in (False, True):
-        ctx.forceLargeVoxelGrid(force_large)
+    for path in ("auto", "multi", "fused"):
+        ctx.forceLargeVoxelGrid(path == "multi")
+        if path == "fused":
+            ctx.forceFusedVoxelGrid(True)
         out, mem, keys = ctx.voxelGrid(pts, 0.4)
-        assert np.array_equal(out, o_out) and np.array_equal(mem, o_mem) and np.array_equal(keys, o_keys), (n, force_large)
-    ctx.forceLargeVoxelGrid(False)
+        assert np.array_equal(out, o_out) and np.array_equal(mem, o_mem) and np.array_equal(keys, o_keys), (n, path)
+    ctx.forceFusedVoxelGrid(False)
 
 
 def test_voxel_grid_empty_and_edges(ctx, oracle):
@@ -60,10 +66,15 @@ def test_voxel_grid_overflow_guard(ctx, oracle):
     rng = np.random.default_rng(5)
     pts = rng.uniform(-20, 20, size=(2000, 4)).astype(np.float32)
     pts[17, :3] = (900.0, -950.0, 800.0); pts[900, :3] = (-990.0, 940.0, -700.0)
-    out, mem, keys = ctx.voxelGrid(pts, 0.15)
     o_out, o_mem, _ = oracle.voxel_grid(pts, 0.15)
     assert len(o_out) == len(pts)
-    assert np.array_equal(out, o_out) and np.array_equal(mem, o_mem)
+    for path in ("auto", "multi", "fused"):
+        ctx.forceLargeVoxelGrid(path == "multi")
+        if path == "fused":
+            ctx.forceFusedVoxelGrid(True)
+        out, mem, keys = ctx.voxelGrid(pts, 0.15)
+        assert np.array_equal(out, o_out) and np.array_equal(mem, o_mem), path
+    ctx.forceFusedVoxelGrid(False)
 
 
 def test_voxel_grid_idempotent_on_lidar(ctx, oracle, kitti_case):

@@ -94,6 +94,14 @@ def main():
             late = np.argsort(arr)[-5:]
             print("      latest workers of iteration 10:", [(int(w), round(float(arr[w] - base) / 1e3, 1)) for w in late])
         prev_pub = pub
+    # phase stamps of the one-kernel VoxelGrid (scan side)
+    ctx.lib.liorf_debug_voxelgrid_stamps(ctx.h, 1, None)
+    ctx.setCurrentScan(scan); ctx.downsampleCurrentScan(want_output=False); ctx.sync()
+    ctx.setCurrentScan(scan); ctx.downsampleCurrentScan(want_output=False); ctx.sync()
+    vb = (C.c_ulonglong * 32)()
+    ctx.lib.liorf_debug_voxelgrid_stamps(ctx.h, 1, vb)
+    v = np.array(list(vb), np.int64); v = v[v > 0]
+    print("VoxelGrid (one kernel) phase stamps, us since kernel start:", [round(float(x - v[0]) / 1e3, 1) for x in v])
     ctx.close()
 
 
