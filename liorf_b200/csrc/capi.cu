@@ -87,7 +87,7 @@ struct liorf_ctx {
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; ulonglong2* d_wpart = nullptr; unsigned long long* d_res = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
     DevBuf<QueryCache> qcache; DevBuf<float4> cand; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; bool s2m_global_state = false;
-    int s2m_grid = 0; bool s2m_no_cache = false;
+    int s2m_grid = 0; bool s2m_no_cache = false; int map_vg_grid = 0;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
     float* d_lm_out = nullptr;      // AtA[36] AtB[6] X[6]
@@ -360,6 +360,12 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
         if (const char* e = std::getenv("LIORF_SOLVER_SPARE_SMS")) spare = std::atoi(e);
         if (spare < 0) spare = 0;
         c->s2m_grid = c->num_sms - spare; if (c->s2m_grid < 2) c->s2m_grid = c->num_sms;      // >= 2: workers + the reducer CTA
+        // the local-map VoxelGrid stays on the multi-kernel path: at 300-650 k points the one-kernel version is no faster (its multi-tile chunks
+        // sweep the keys twice per pass: 0.146-0.228 ms against 0.154 ms measured) and two cooperative grids would compete for the SMs;
+        // LIORF_MAP_VG_GRID = CTAs of the one-kernel path for experiments
+        c->map_vg_grid = 0;
+        if (const char* e = std::getenv("LIORF_MAP_VG_GRID")) c->map_vg_grid = std::atoi(e);
+        if (c->map_vg_grid > c->num_sms) c->map_vg_grid = c->num_sms;
     }
     CUDA_TRY(cudaMalloc(&c->d_partial, (size_t)2 * c->num_sms * NPROD * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->d_mail, sizeof(S2MMail)));
@@ -729,7 +735,7 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
             if (graphs) k_transform_concat_hdr<<<(bound + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p, c->map_raw.p);
             else k_transform_concat<<<(tot + 255) / 256, 256, 0, ms>>>(c->kf_points.p, c->d_sel.p + 1, ns, tot, c->map_raw.p);
         }
-        return voxel_grid_device(c->map_raw.p, cnt_raw, c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_shared + C_M_DS, nullptr, nullptr, c->vg_map, ms);
+        return voxel_grid_device(c->map_raw.p, cnt_raw, c->P.surroundingKeyframeMapLeafSize, c->map_ds.p, c->d_shared + C_M_DS, nullptr, nullptr, c->vg_map, ms, c->map_vg_grid);
     };
     auto enqueue_grid = [&]() -> int { return build_map_grid(c->map_ds.p, Count::of_dev(c->d_shared + C_M_DS, bound), c->grid, ms); };
     if (!graphs) {
@@ -741,6 +747,7 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
         VoxelGridWork& w = c->vg_map; MapGrid& gr = c->grid;
         const int nc = grid_cells(gr.dims);
         int mmb = (bound + VG_MM_BLOCK * 8 - 1) / (VG_MM_BLOCK * 8); if (mmb > kNumSMs) mmb = kNumSMs;
+        if ((rc = w.pts_sorted.reserve(bound)) || (rc = w.cta_hist.reserve((size_t)kNumSMs * RADIX)) || (rc = w.cta_heads.reserve(kNumSMs)) || (rc = w.partial.reserve((size_t)kNumSMs * 6))) return rc;
         if ((rc = w.partial.reserve((size_t)mmb * 6)) || (rc = w.keys.reserve(bound)) || (rc = w.seg_start.reserve((size_t)bound + 1)) ||
             (rc = w.sort.keys_alt.reserve(bound)) || (rc = w.sort.vals_a.reserve(bound)) || (rc = w.sort.vals_b.reserve(bound)) || (rc = w.sort.hist.reserve(4 * RADIX)) ||
             (rc = reserve_zeroed(w.sort.status, (size_t)((bound + SORT_TILE - 1) / SORT_TILE) * RADIX, ms)) ||
@@ -750,7 +757,7 @@ int liorf_extract_surrounding_keyframes(liorf_ctx* c, const int* ids, int n_ids,
         if (!gr.counts_clean) { CUDA_TRY(cudaMemsetAsync(gr.counts.p, 0, (size_t)nc * sizeof(unsigned), ms)); gr.counts_clean = true; }
         const void* sig[20] = {c->kf_points.p, c->d_sel.p, c->map_raw.p, c->map_ds.p, w.partial.p, w.keys.p, w.seg_start.p, w.sort.keys_alt.p, w.sort.vals_a.p,
                                w.sort.vals_b.p, w.sort.hist.p, w.sort.status.p, w.scan.status.p, gr.counts.p, gr.cell_start.p, gr.sorted.p, gr.scan.status.p,
-                               w.meta, (const void*)(size_t)w.force_large, nullptr};
+                               w.meta, (const void*)(size_t)(w.force_large | (w.force_multi << 1) | (c->map_vg_grid << 2)), w.pts_sorted.p};
         if (G.vg && std::memcmp(sig, G.sig, sizeof(sig)) != 0) { cudaGraphExecDestroy(G.vg); cudaGraphExecDestroy(G.grid); G.vg = G.grid = nullptr; }
         if (!G.vg) {
             const bool prof_on = c->prof.enabled; c->prof.enabled = false;          // no timing events inside a capture
