@@ -1287,7 +1287,8 @@ int liorf_sc_prepare_queries_dev(liorf_ctx* c, const void* d_qdescs, int Q, void
     if (!c || Q < 0 || !d_qdescs || (!d_qkeys && !d_qsk)) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
     if (Q == 0) return LIORF_OK;
-    k_sc_keys_batch<<<Q, 64, 0, c->stream>>>((const double*)d_qdescs, Q, (float*)d_qkeys, (double*)d_qsk, (double*)d_qcn);
+    if (d_qkeys && !d_qsk && ((uintptr_t)d_qdescs & 15) == 0) k_sc_ringkeys_batch<<<(Q + SCK_WARPS - 1) / SCK_WARPS, 32 * SCK_WARPS, 0, c->stream>>>((const double*)d_qdescs, Q, (float*)d_qkeys);
+    else k_sc_keys_batch<<<Q, 64, 0, c->stream>>>((const double*)d_qdescs, Q, (float*)d_qkeys, (double*)d_qsk, (double*)d_qcn);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;
     return LIORF_OK;
@@ -1600,7 +1601,8 @@ int liorf_sc_shard_query_phases_dev(liorf_ctx* c, const void* d_qdescs, int Q, i
     ShardPush P; std::memset(&P, 0, sizeof(P));
     P.enabled = 1; P.q0 = q0; P.W = S.W; P.counter = S.d_counter; P.batch_p = S.d_batch;
     if (phases & 1) {        // ring keys of this rank's query slice (first block bumps the batch number) → exact GLOBAL top-3 → every window
-        k_sc_keys_batch<<<std::max(Qs, 1), 64, 0, c->stream>>>(qd + (size_t)q0 * SC_DESC, Qs, c->sc_qkeys.p, nullptr, nullptr, S.d_batch);
+        if (((uintptr_t)qd & 15) == 0) k_sc_ringkeys_batch<<<(std::max(Qs, 1) + SCK_WARPS - 1) / SCK_WARPS, 32 * SCK_WARPS, 0, c->stream>>>(qd + (size_t)q0 * SC_DESC, Qs, c->sc_qkeys.p, S.d_batch);
+        else k_sc_keys_batch<<<std::max(Qs, 1), 64, 0, c->stream>>>(qd + (size_t)q0 * SC_DESC, Qs, c->sc_qkeys.p, nullptr, nullptr, S.d_batch);
         c->launches += 1;
         if (Qs > 0 && sc_want_tensor(c, Qs, ks.n)) { if ((rc = sc_knn_tensor(c, ks, ks.n, c->sc_qkeys.p, Qs, 0, nullptr, nullptr, &P))) return rc; }
         else {

@@ -276,4 +276,25 @@ __global__ void __launch_bounds__(64) k_sc_keys_batch(const double* __restrict__
     }
 }
 
+
+// Ring keys only (query batches: the sector keys / column norms of a query are derived inside stage 2): ONE WARP per descriptor, lane r
+// sums ring r — its 60 sectors are 480 contiguous bytes, fetched as thirty 16-byte loads that are all in flight before the first add —
+// sequentially in sector order (makeRingkeyFromScancontext :214-227, the same fp64 sums as k_sc_keys_batch).  No shared memory, no barrier:
+// the kernel streams the descriptors at HBM speed (9 600 B per query) instead of paying a load → barrier → 60-add chain per 64-thread CTA.
+// batch (nullable): the sharded search's batch number, bumped once per launch.
+constexpr int SCK_WARPS = 4;
+__global__ void __launch_bounds__(32 * SCK_WARPS) k_sc_ringkeys_batch(const double* __restrict__ desc, int n, float* __restrict__ ringkey, unsigned* batch = nullptr) {
+    if (batch && blockIdx.x == 0 && threadIdx.x == 0) *batch += 1u;
+    const int e = blockIdx.x * SCK_WARPS + (threadIdx.x >> 5), r = threadIdx.x & 31;
+    if (e >= n || r >= SC_RING) return;
+    const double2* row = reinterpret_cast<const double2*>(desc + (size_t)e * SC_DESC + (size_t)r * SC_SECTOR);
+    double2 v[SC_SECTOR / 2];
+#pragma unroll
+    for (int c = 0; c < SC_SECTOR / 2; ++c) v[c] = __ldg(row + c);
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < SC_SECTOR / 2; ++c) { s += v[c].x; s += v[c].y; }
+    ringkey[(size_t)e * SC_RING + r] = (float)(s / SC_SECTOR);
+}
+
 }  // namespace liorf
