@@ -745,12 +745,29 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
                 } else if (__popcll(mask) == 5 && sorted && cd[4] < 1.0f) {
 #pragma unroll
                     for (int j = 0; j < 5; ++j) { nn.d[j] = cd[j]; nn.oi[j] = coi[j]; nn.pos[j] = cpos[j]; }
-                } else if (__popcll(mask) == 5 && cd[0] < 1.0f && cd[1] < 1.0f && cd[2] < 1.0f && cd[3] < 1.0f && cd[4] < 1.0f) {
-                    // the same five in a different order: a 9-exchange sorting network on the keys instead of an insertion pass
+                } else if (__popcll(mask) <= 6) {
+                    // the same five in a different order, or ONE entry slipped under the bound (n1 >= 5, so the five smallest keys are all
+                    // within 1 m): a 9-exchange sorting network on the cached keys, then the newcomer takes its place and the last one drops out
 #define S2M_CE(i, j) if (ck[j] < ck[i]) { const unsigned long long tk = ck[i]; ck[i] = ck[j]; ck[j] = tk; const float td = cd[i]; cd[i] = cd[j]; cd[j] = td; \
                                            const int to = coi[i]; coi[i] = coi[j]; coi[j] = to; const int tp = cpos[i]; cpos[i] = cpos[j]; cpos[j] = tp; }
                     S2M_CE(0, 1) S2M_CE(3, 4) S2M_CE(2, 4) S2M_CE(2, 3) S2M_CE(1, 4) S2M_CE(0, 3) S2M_CE(0, 2) S2M_CE(1, 3) S2M_CE(1, 2)
 #undef S2M_CE
+                    unsigned long long others = mask;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) others &= ~(1ull << cpos[j]);
+                    if (others) {
+                        const int ip = __ffsll((long long)others) - 1;
+                        const float4 p = ldq<SM>(row + ip);
+                        float nd = sqdist_dev(sel, p); int noi = __float_as_int(p.w), np = ip;
+                        unsigned long long nk = nn_key(nd, noi);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {                 // ripple insert: the larger of (newcomer, entry j) moves on
+                            if (nk < ck[j]) {
+                                const unsigned long long tk = ck[j]; ck[j] = nk; nk = tk; const float td = cd[j]; cd[j] = nd; nd = td;
+                                const int to = coi[j]; coi[j] = noi; noi = to; const int tp = cpos[j]; cpos[j] = np; np = tp;
+                            }
+                        }
+                    }
                     pk = 0;
 #pragma unroll
                     for (int j = 0; j < 5; ++j) { nn.d[j] = cd[j]; nn.oi[j] = coi[j]; nn.pos[j] = cpos[j]; pk |= (unsigned)cpos[j] << (6 * j); }

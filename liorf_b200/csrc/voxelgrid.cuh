@@ -410,7 +410,7 @@ __device__ __forceinline__ unsigned vgf_key(const float4 p, float inv, int b0, i
     return (unsigned)(i0 + i1 * m1 + i2 * m2);
 }
 
-__global__ void __launch_bounds__(VGF_THREADS, 1) k_vg_fused(VgFusedArgs a) {
+__global__ void __launch_bounds__(VGF_THREADS, 2) k_vg_fused(VgFusedArgs a) {
     __shared__ float s_red[VGF_WARPS][6];
     __shared__ VoxMeta s_meta;
     __shared__ unsigned s_whist[VGF_WARPS][RADIX];      // per-warp digit counts of a tile → exclusive warp offsets
