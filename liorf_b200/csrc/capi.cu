@@ -86,7 +86,7 @@ struct liorf_ctx {
     std::vector<int> last_sel; unsigned long long pose_version = 0, last_sel_version = ~0ull; bool map_valid = false;
     // LM
     float* d_tf6 = nullptr; LMDeviceState* d_lm = nullptr; S2MTrace* d_trace = nullptr; double* d_partial = nullptr; ulonglong2* d_wpart = nullptr; unsigned long long* d_res = nullptr; long long* d_dbg = nullptr; unsigned long long* d_dbg_gt = nullptr;
-    DevBuf<QueryCache> qcache; DevBuf<float4> cand; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; bool s2m_global_state = false;
+    IcpState* icp_state = nullptr; DevBuf<QueryCache> qcache; DevBuf<float4> cand; unsigned s2m_launch_seq = 0; S2MMail* d_mail = nullptr; bool mail_fresh = false; bool s2m_global_state = false;
     int s2m_grid = 0; bool s2m_no_cache = false; int map_vg_grid = 0;
     DevBuf<float4> h_coeff, h_sel_pts, h_ori_c, h_coeff_c; DevBuf<unsigned char> h_flag; DevBuf<int> h_idx; DevBuf<float> h_d2, h_plane;
     DevBuf<double> lm_partial; ScanWork combine_scan; int hook_n = 0;
@@ -437,7 +437,7 @@ void liorf_destroy(liorf_ctx* c) {
     if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
     for (VoxelGridWork* vw : {&c->vg, &c->vg_map, &c->alt.vg}) { vw->pts_sorted.release(); vw->cta_hist.release(); vw->cta_heads.release(); if (vw->fused_bar) cudaFree(vw->fused_bar); vw->fused_bar = nullptr; }
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
-    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_wpart); cudaFree(c->d_res); cudaFree(c->d_mail); c->qcache.release(); c->cand.release();
+    cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_wpart); cudaFree(c->d_res); cudaFree(c->d_mail); if (c->icp_state) cudaFree(c->icp_state); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
     {   // peer windows
         liorf_ctx::ScShard& S = c->shard;
@@ -1788,23 +1788,29 @@ int liorf_loop_closure_icp(liorf_ctx* c, int loop_key_cur, int loop_key_pre, int
     CUDA_TRY(cudaMemcpyAsync(c->icp_src.p, c->icp_src0.p, (size_t)n_src * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
     const int r_max = (int)std::ceil(max_corr_dist) + 1;
     const float max_d2 = max_corr_dist * max_corr_dist;
-    liorf_host::IcpConvergence cc; cc.max_iterations = max_iters;
-    float final_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, inc[16];
-    std::memcpy(inc, final_T, sizeof(inc));
-    bool converged = false;
-    double* h_sums = reinterpret_cast<double*>(c->h_mail + 3000);   // 8-byte aligned slot of the pinned mailbox
-    while (true) {
-        IcpT Ti; std::memcpy(Ti.t, inc, 12 * sizeof(float));
-        k_icp_iteration<<<blocks, ICP_BLOCK, 0, c->stream>>>(c->icp_src.p, n_src, Ti, c->icp_grid.cell_start.p, c->icp_grid.sorted.p, c->icp_grid.dims, r_max, max_d2,
-                                                           c->icp_partial.p, c->icp_counter, c->icp_out, nullptr, nullptr);
-        CUDA_TRY(cudaMemcpyAsync(h_sums, c->icp_out, ICP_NSUM * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // the loop runs on the device (csrc/icp.cuh): iterations are enqueued in chunks and the state is read back once per chunk
+    if (!c->icp_state) CUDA_TRY(cudaMalloc(&c->icp_state, sizeof(IcpState)));
+    IcpState hs; std::memset(&hs, 0, sizeof(hs));
+    hs.cc = liorf_host::IcpConvergence(); hs.cc.max_iterations = max_iters;
+    for (int i = 0; i < 4; ++i) hs.inc[5 * i] = hs.final_T[5 * i] = 1.f;
+    CUDA_TRY(cudaMemcpyAsync(c->icp_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                       // hs is pageable: the copy must have left it before it is reused below
+    constexpr int ICP_CHUNK = 8;
+    int enq = 0;
+    while (!hs.done && enq < max_iters) {
+        const int todo = std::min(ICP_CHUNK, max_iters - enq);
+        for (int k = 0; k < todo; ++k)
+            k_icp_iteration<<<blocks, ICP_BLOCK, 0, c->stream>>>(c->icp_src.p, n_src, c->icp_state, c->icp_grid.cell_start.p, c->icp_grid.sorted.p, c->icp_grid.dims, r_max, max_d2,
+                                                               c->icp_partial.p, c->icp_counter, c->icp_out, nullptr, nullptr);
+        enq += todo; c->launches += todo;
+        CUDA_TRY(cudaMemcpyAsync(&hs, c->icp_state, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        ++c->launches;
-        if (!liorf_host::icp_estimate(h_sums, inc)) { cc.state = liorf_host::IcpConvergence::NO_CORRESPONDENCES; converged = false; break; }
-        liorf_host::mat4_mul(inc, final_T, final_T);               // final_transformation_ = transformation_ * final_transformation_
-        ++out->iterations;
-        if (cc.has_converged(inc, h_sums[16] / h_sums[0])) { converged = true; break; }
     }
+    const bool converged = hs.converged != 0;
+    liorf_host::IcpConvergence cc = hs.cc;
+    float final_T[16]; std::memcpy(final_T, hs.final_T, sizeof(final_T));
+    out->iterations = hs.iterations;
+    double* h_sums = reinterpret_cast<double*>(c->h_mail + 3000);   // 8-byte aligned slot of the pinned mailbox
     out->converged = converged ? 1 : 0; out->convergence_state = (int)cc.state;
     std::memcpy(out->transform, final_T, sizeof(final_T));
     // getFitnessScore(): the original source under the final transformation, no range limit

@@ -6,9 +6,12 @@
 //                               grows cube shells until no unvisited cell can hold a closer point
 //   transformation estimation : the 17 sums the SVD step needs (count, sum s, sum d, sum d s^T, sum d2) reduced in fp64 by
 //                               a fixed tree + last-block fold (no float atomics: bit-reproducible)
-// The 3x3 SVD / convergence logic is scalar host code (host/host_logic.hpp), as in PCL.
+// The 3x3 SVD / convergence logic is the scalar code of host/host_logic.hpp (as in PCL), run by the LAST block of every iteration on the
+// device: the loop state (incremental and accumulated transform, convergence criteria) lives in device memory, an iteration that
+// finds the loop finished returns at once, and the host reads the state back once per chunk of iterations instead of once per iteration.
 #pragma once
 #include "localmap.cuh"
+#include "../host/host_logic.hpp"
 
 namespace liorf {
 
@@ -16,6 +19,12 @@ constexpr int ICP_NSUM = 17;      // n, sx sy sz, dx dy dz, H[3][3] (H[r][c] = s
 constexpr int ICP_BLOCK = 256;
 
 struct IcpT { float t[12]; };     // row-major 3x4, passed by value
+struct IcpState {                 // device-resident loop state of pcl::IterativeClosestPoint::computeTransformation
+    float inc[16];                // transformation_ of the last iteration (applied to the source at the start of the next)
+    float final_T[16];            // final_transformation_
+    liorf_host::IcpConvergence cc;
+    int iterations, done, converged, pad;
+};
 
 __device__ __forceinline__ void icp_visit(const unsigned* __restrict__ cell_start, const float4* __restrict__ gmap, GridDims g, int x, int y, int z,
                                           const float4 q, float& bd, int& bi, float4& bp) {
@@ -51,16 +60,21 @@ __device__ __forceinline__ bool icp_nearest(const float4 q, const unsigned* __re
 // One ICP iteration's device half.  src_cur ← T_inc * src_cur (pcl::transformPointCloud with the previous iteration's
 // estimate; identity on the first), correspondences with squared distance <= max_d2, partial sums → out[ICP_NSUM].
 // want_nn: also store the neighbour index / squared distance per source point (tests, fitness).
-__global__ void __launch_bounds__(ICP_BLOCK) k_icp_iteration(float4* __restrict__ src_cur, int n_src, IcpT T_inc, const unsigned* __restrict__ cell_start,
+__global__ void __launch_bounds__(ICP_BLOCK) k_icp_iteration(float4* __restrict__ src_cur, int n_src, IcpState* __restrict__ st, const unsigned* __restrict__ cell_start,
                                                             const float4* __restrict__ gmap, GridDims g, int r_max, float max_d2, double* __restrict__ partial,
                                                             int* __restrict__ counter, double* __restrict__ out, int* __restrict__ nn_idx, float* __restrict__ nn_d2) {
     __shared__ double s_red[ICP_BLOCK / 32][ICP_NSUM];
     __shared__ bool s_last;
+    __shared__ float s_T[12];
+    __shared__ double s_out[ICP_NSUM];
+    if (__ldcg(&st->done)) return;                             // the loop ended in an earlier launch of this chunk
+    if (threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->inc[threadIdx.x]);        // (rewritten only by this launch's LAST block, after every block has read it)
+    __syncthreads();
     double acc[ICP_NSUM];
 #pragma unroll
     for (int k = 0; k < ICP_NSUM; ++k) acc[k] = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
-        const float4 p = apply_affine_dev(T_inc.t, src_cur[i]);
+        const float4 p = apply_affine_dev(s_T, src_cur[i]);
         src_cur[i] = p;
         float bd; int bi; float4 bp;
         const bool found = icp_nearest(p, cell_start, gmap, g, r_max, bd, bi, bp) && bd <= max_d2;
@@ -91,9 +105,25 @@ __global__ void __launch_bounds__(ICP_BLOCK) k_icp_iteration(float4* __restrict_
     if (threadIdx.x < ICP_NSUM) {                              // fold the per-block partials in block order (deterministic whoever is last)
         const volatile double* vp = partial;
         double s = 0; for (int b = 0; b < (int)gridDim.x; ++b) s += vp[b * ICP_NSUM + threadIdx.x];
-        out[threadIdx.x] = s;
+        out[threadIdx.x] = s; s_out[threadIdx.x] = s;
     }
-    if (threadIdx.x == 0) *counter = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *counter = 0;
+        // transformation estimation + convergence criteria (pcl::IterativeClosestPoint::computeTransformation's loop body, :652-674)
+        float inc[16], fin[16];
+        if (!liorf_host::icp_estimate(s_out, inc)) { st->cc.state = liorf_host::IcpConvergence::NO_CORRESPONDENCES; st->converged = 0; st->done = 1; }
+        else {
+            for (int k = 0; k < 16; ++k) fin[k] = st->final_T[k];
+            liorf_host::mat4_mul(inc, fin, fin);                  // final_transformation_ = transformation_ * final_transformation_
+            for (int k = 0; k < 16; ++k) { st->final_T[k] = fin[k]; st->inc[k] = inc[k]; }
+            st->iterations += 1;
+            liorf_host::IcpConvergence cc = st->cc;
+            if (cc.has_converged(inc, s_out[16] / s_out[0])) { st->converged = 1; st->done = 1; }
+            st->cc = cc;
+        }
+        __threadfence();
+    }
 }
 
 // getFitnessScore (pcl::Registration::getFitnessScore, max_range = DBL_MAX): mean squared nearest-neighbour distance of the

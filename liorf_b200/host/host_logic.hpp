@@ -14,6 +14,13 @@
 #include <utility>
 #include <vector>
 
+// the ICP scalar half (sym3_jacobi .. IcpConvergence) also runs on the device: the last block of an ICP iteration calls it (csrc/icp.cuh)
+#ifdef __CUDACC__
+#define LIORF_HD __host__ __device__
+#else
+#define LIORF_HD
+#endif
+
 namespace liorf_host {
 
 struct KeyPose { float roll, pitch, yaw, x, y, z; double time; };
@@ -204,7 +211,7 @@ inline void update_initial_guess(InitialGuessState& st, bool no_keyframes_yet, c
 // TransformationEstimationSVD → Eigen::umeyama without scaling, from the 17 sums the device reduces:
 // s[0] = n, s[1..3] = sum of source points, s[4..6] = sum of their target neighbours, s[7..15] = sum d_r * s_c (row r of the
 // target point, column c of the source point), s[16] = sum of squared distances.  Returns false for fewer than 3 pairs.
-inline void sym3_jacobi(double A[3][3], double V[3][3]) {      // eigen-decomposition of a symmetric 3x3 by cyclic Jacobi rotations
+LIORF_HD inline void sym3_jacobi(double A[3][3], double V[3][3]) {      // eigen-decomposition of a symmetric 3x3 by cyclic Jacobi rotations
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 60; ++sweep) {
         const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
@@ -221,10 +228,10 @@ inline void sym3_jacobi(double A[3][3], double V[3][3]) {      // eigen-decompos
         }
     }
 }
-inline double det3(const double M[3][3]) {
+LIORF_HD inline double det3(const double M[3][3]) {
     return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
 }
-inline bool icp_estimate(const double s[17], float T[16]) {
+LIORF_HD inline bool icp_estimate(const double s[17], float T[16]) {
     const double n = s[0];
     if (n < 3.0) return false;                                   // min_number_correspondences_
     const double ms[3] = {s[1] / n, s[2] / n, s[3] / n}, md[3] = {s[4] / n, s[5] / n, s[6] / n};
@@ -234,9 +241,9 @@ inline bool icp_estimate(const double s[17], float T[16]) {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = S[0][i] * S[0][j] + S[1][i] * S[1][j] + S[2][i] * S[2][j];   // S^T S
     sym3_jacobi(A, V);
     int ord[3] = {0, 1, 2};                                      // singular values descending
-    for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (A[ord[b]][ord[b]] > A[ord[a]][ord[a]]) std::swap(ord[a], ord[b]);
+    for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (A[ord[b]][ord[b]] > A[ord[a]][ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
     double Vs[3][3], U[3][3], sv[3];
-    for (int k = 0; k < 3; ++k) { sv[k] = std::sqrt(std::max(A[ord[k]][ord[k]], 0.0)); for (int i = 0; i < 3; ++i) Vs[i][k] = V[i][ord[k]]; }
+    for (int k = 0; k < 3; ++k) { sv[k] = std::sqrt(A[ord[k]][ord[k]] > 0.0 ? A[ord[k]][ord[k]] : 0.0); for (int i = 0; i < 3; ++i) Vs[i][k] = V[i][ord[k]]; }
     for (int k = 0; k < 2; ++k) {
         double u[3] = {0, 0, 0};
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) u[i] += S[i][j] * Vs[j][k];
@@ -261,7 +268,7 @@ inline bool icp_estimate(const double s[17], float T[16]) {
     T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
     return true;
 }
-inline void mat4_mul(const float a[16], const float b[16], float o[16]) {       // Eigen Matrix4f product (float, k ascending)
+LIORF_HD inline void mat4_mul(const float a[16], const float b[16], float o[16]) {       // Eigen Matrix4f product (float, k ascending)
     float r[16];
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float v = 0.f; for (int k = 0; k < 4; ++k) v += a[4 * i + k] * b[4 * k + j]; r[4 * i + j] = v; }
     for (int k = 0; k < 16; ++k) o[k] = r[k];
@@ -274,7 +281,7 @@ struct IcpConvergence {
     int max_iterations = 100; double translation_threshold = 1e-6, rotation_threshold = 1.0 - 1e-6, mse_relative = 1e-6, mse_absolute = 1e-12;
     int iterations = 0; double prev_mse = 1.7976931348623157e308;
     enum State { NOT_CONVERGED, ITERATIONS, TRANSFORM, ABS_MSE, REL_MSE, NO_CORRESPONDENCES } state = NOT_CONVERGED;
-    bool has_converged(const float T[16], double cur_mse) {
+    LIORF_HD bool has_converged(const float T[16], double cur_mse) {
         state = NOT_CONVERGED;
         ++iterations;
         if (iterations >= max_iterations) { state = ITERATIONS; return true; }

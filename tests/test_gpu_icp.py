@@ -50,10 +50,11 @@ def test_icp_matches_oracle(oracle, synth, revisit):
     assert np.array_equal(src, o_src) and np.array_equal(tgt, o_tgt)               # the two clouds: bit-exact
     o = pyicp.icp(o_src, o_tgt, 20.0, 100)
     T = np.array(r.transform[:], np.float32).reshape(4, 4)
-    print("gpu iterations", r.iterations, "state", r.convergence_state, "fitness", r.fitness, "| oracle", o["iterations"], o["state"], o["fitness"])
+    print("gpu iterations", r.iterations, "state", r.convergence_state, "fitness", r.fitness, "| oracle", o["iterations"], o["state"], o["fitness"],
+          "| dT", float(np.max(np.abs(T[:3, 3] - o["transform"][:3, 3]))), "dR", float(_rot_err(T, o["transform"])))
     assert r.converged == int(o["converged"]) == 1
     assert abs(r.iterations - o["iterations"]) <= 1                                  # a stop criterion sitting on its threshold may flip
-    assert np.max(np.abs(T[:3, 3] - o["transform"][:3, 3])) < 1e-3 and _rot_err(T, o["transform"]) < 1e-4
+    assert np.max(np.abs(T[:3, 3] - o["transform"][:3, 3])) < 1e-4 and _rot_err(T, o["transform"]) < 1e-5      # north-star tolerance (measured: 6e-8 m, 0 rad)
     assert abs(r.fitness - o["fitness"]) < 1e-3 * max(o["fitness"], 1e-3)
     # the correction undoes the drift: applied to the drifted pose it lands on the true one
     from bench import pose_to_T, T_to_pose
@@ -81,7 +82,7 @@ def test_icp_reference_call_form_and_guards(oracle, synth, revisit):
     o = pyicp.icp(o_src, o_tgt, 20.0, 100)
     T = np.array(r.transform[:], np.float32).reshape(4, 4)
     assert r.converged == 1 and abs(r.iterations - o["iterations"]) <= 1
-    assert np.max(np.abs(T[:3, 3] - o["transform"][:3, 3])) < 1e-3 and _rot_err(T, o["transform"]) < 1e-4
+    assert np.max(np.abs(T[:3, 3] - o["transform"][:3, 3])) < 1e-4 and _rot_err(T, o["transform"]) < 1e-5      # north-star tolerance (measured: 6e-8 m, 0 rad)
     # both clouds are in their own sensor frames here, recorded at the same place: the correction is ~identity
     assert np.linalg.norm(T[:3, 3]) < 0.1 and _rot_err(T, np.eye(4, dtype=np.float32)) < 5e-3
     # guards (:655-656): a tiny cloud on either side → the ICP does not run
