@@ -774,12 +774,20 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
                     float4 h3n = h3; h3n.z = __uint_as_float(pk); stq<SM>(hdr(tid, 3), h3n);
                 } else {
                     if (a.dbg_gt && iter >= 10) atomicAdd(a.dbg_gt + 41 * S2M_GT_STRIDE + blockIdx.x, 1ull);
+                    // ordered insertion of the entries under the bound, on the u64 keys (distance and index travel inside the key)
+                    unsigned long long tk[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull}; int tp[5] = {-1, -1, -1, -1, -1};
                     while (mask) {
                         const int i = __ffsll((long long)mask) - 1; mask &= mask - 1;
                         const float4 p = ldq<SM>(row + i);
                         const float d = sqdist_dev(sel, p);
-                        if (d < 1.0f) top5_insert(nn, d, __float_as_int(p.w), i);
+                        unsigned long long k = nn_key(d, __float_as_int(p.w)); int kp = i;
+                        if (d < 1.0f && k < tk[4]) {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) if (k < tk[j]) { const unsigned long long t = tk[j]; tk[j] = k; k = t; const int t2 = tp[j]; tp[j] = kp; kp = t2; }
+                        }
                     }
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) if (tp[j] >= 0) { nn.d[j] = __uint_as_float((unsigned)(tk[j] >> 32)); nn.oi[j] = (int)(unsigned)tk[j]; nn.pos[j] = tp[j]; }
                     if (nn.pos[4] != -1) {
                         pk = 0;
 #pragma unroll
