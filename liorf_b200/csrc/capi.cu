@@ -595,8 +595,10 @@ static int downsample_async(liorf_ctx* c, int* d_membership, int coop_grid) {
     if ((rc = c->scan_ds.reserve(nb > 0 ? nb : 1))) return rc;
     c->h_n_ds = -1;
     Count cnt = c->h_n_scan >= 0 ? Count::of_host(c->h_n_scan) : Count::of_dev(c->d_counts + C_N_SCAN, nb);
-    ProfScope ps(c, SEC_DOWNSAMPLE); c->launches += 9;
-    return voxel_grid_device(c->scan.p, cnt, c->P.mappingSurfLeafSize, c->scan_ds.p, c->d_counts + C_N_DS, d_membership, nullptr, c->vg, c->stream, coop_grid);
+    ProfScope ps(c, SEC_DOWNSAMPLE);
+    rc = voxel_grid_device(c->scan.p, cnt, c->P.mappingSurfLeafSize, c->scan_ds.p, c->d_counts + C_N_DS, d_membership, nullptr, c->vg, c->stream, coop_grid);
+    c->launches += c->vg.last_launches;
+    return rc;
 }
 
 int liorf_downsample_current_scan(liorf_ctx* c, liorf_point* out, int* n_ds, int* membership) {

@@ -40,6 +40,7 @@ struct VoxelGridWork {
     int* err_flag = nullptr;
     bool force_multi = false;       // tests: never take the one-kernel path
     unsigned long long* dbg = nullptr;   // debug: phase stamps of the one-kernel path
+    int last_launches = 0;          // kernels (and memsets) the last voxel_grid_device call enqueued
 };
 
 constexpr int VG_MM_BLOCK = 256;
@@ -699,8 +700,9 @@ __global__ void __launch_bounds__(VGF_THREADS, 2) k_vg_fused(VgFusedArgs a) {
 inline int voxel_grid_device(const float4* in, Count cnt, float leaf, float4* out, int* n_out_dev, int* membership, int* out_keys,
                              VoxelGridWork& w, cudaStream_t s, int coop_grid = 0) {
     const int nb = cnt.bound;
-    if (nb <= 0) { CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(int), s)); return LIORF_OK; }
+    if (nb <= 0) { CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(int), s)); w.last_launches = 1; return LIORF_OK; }
     int rc;
+    w.last_launches = 10;                                           // multi-kernel path: memset + minmax + keys + hist + 4 passes + head scan + centroids
     if (coop_grid > 0 && w.fused_bar && !w.force_multi && (nb > VGS_CAP || w.force_large)) {
         if ((rc = w.keys.reserve(nb)) || (rc = w.sort.keys_alt.reserve(nb)) || (rc = w.sort.vals_a.reserve(nb)) || (rc = w.sort.vals_b.reserve(nb)) ||
             (rc = w.seg_start.reserve((size_t)nb + 1)) || (rc = w.pts_sorted.reserve(nb)) || (rc = w.partial.reserve((size_t)coop_grid * 6)) ||
@@ -714,12 +716,14 @@ inline int voxel_grid_device(const float4* in, Count cnt, float leaf, float4* ou
         static const bool plain_launch = std::getenv("LIORF_VG_PLAIN_LAUNCH") != nullptr;     // experiment: launch latency of a cooperative launch
         if (plain_launch) k_vg_fused<<<coop_grid, VGF_THREADS, 0, s>>>(a);
         else CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_vg_fused, dim3(coop_grid), dim3(VGF_THREADS), args, 0, s));
+        w.last_launches = 1;
         return LIORF_OK;
     }
     if (nb <= VGS_CAP && !w.force_large) {
         if ((rc = w.seg_start.reserve((size_t)nb + 1))) return rc;
         if (!w.small_attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_vg_small, cudaFuncAttributeMaxDynamicSharedMemorySize, VGS_SMEM)); w.small_attr_set = true; }
         k_vg_small<<<1, VGS_THREADS, VGS_SMEM, s>>>(in, cnt, leaf, out, n_out_dev, membership, out_keys, w.meta, w.seg_start.p);
+        w.last_launches = 1;
         CUDA_TRY(cudaGetLastError());
         return LIORF_OK;
     }
