@@ -4,6 +4,7 @@
 # (compute-sanitizer is closed on this pool — see profiles/r02_sanitizer.txt; tools/sanitize_smoke.py is the small-shape program it would run.)
 set -x
 O=gpurun_out
+python -m pytest tests -x -q -m gpu > $O/r02_gpu_tests.txt 2>&1; tail -2 $O/r02_gpu_tests.txt; python -c "import __graft_entry__ as g; g.smoke()" > $O/r02_smoke.txt 2>&1; cat $O/r02_smoke.txt
 python bench.py > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err || exit 1
 python bench.py --impl reference --steps 20 --warmup 5 > $O/r02_bench_reference_n1.json 2> $O/r02_bench_reference_n1.err
 python tools/profile_single_frame.py 3 50 > $O/r02_profile_single_frame.txt 2>&1 || exit 1
