@@ -361,7 +361,8 @@ int liorf_create(const liorf_params* p, liorf_ctx** out) {
         if (spare < 0) spare = 0;
         c->s2m_grid = c->num_sms - spare; if (c->s2m_grid < 2) c->s2m_grid = c->num_sms;      // >= 2: workers + the reducer CTA
         // the local-map VoxelGrid stays on the multi-kernel path: at 300-650 k points the one-kernel version is no faster (its multi-tile chunks
-        // sweep the keys twice per pass: 0.146-0.228 ms against 0.154 ms measured) and two cooperative grids would compete for the SMs;
+        // sweep the keys twice per pass: 0.142-0.228 ms against 0.144-0.154 ms for the KITTI map, 0.466 against 0.288 ms for the 2.3 M-point OS1-128
+        // selection, sequence 0.198 against 0.204 ms/frame) and two cooperative grids would compete for the SMs;
         // LIORF_MAP_VG_GRID = CTAs of the one-kernel path for experiments
         c->map_vg_grid = 0;
         if (const char* e = std::getenv("LIORF_MAP_VG_GRID")) c->map_vg_grid = std::atoi(e);
