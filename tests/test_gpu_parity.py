@@ -20,14 +20,16 @@ def test_voxel_grid_random(ctx, oracle, n, leaf, seed):
     pts = rng.uniform(-40, 40, size=(n, 4)).astype(np.float32)
     pts[:, 2] *= 0.1
     o_out, o_mem, o_keys = oracle.voxel_grid(pts, leaf)
-    for path in ("auto", "multi"):                # auto: one CTA up to 3072 points, the one-kernel cooperative path beyond; multi: the multi-kernel radix path
-        ctx.forceLargeVoxelGrid(path == "multi")
+    for path in ("auto", "multi", "fused"):       # auto: one CTA up to 3072 points, one cooperative kernel up to one tile per CTA, the multi-kernel
+        ctx.forceLargeVoxelGrid(path == "multi")  # radix path beyond; "fused" forces the cooperative kernel (300 000 points: two tiles per CTA)
+        if path == "fused":
+            ctx.forceFusedVoxelGrid(True)
         out, mem, keys = ctx.voxelGrid(pts, leaf)
         assert len(out) == len(o_out), path
         assert np.array_equal(mem, o_mem), path      # voxel membership bit-exact
         assert np.array_equal(keys, o_keys), path    # ascending linear voxel index
         assert np.array_equal(out, o_out), path      # canonical order ⇒ centroids bit-exact too
-    ctx.forceLargeVoxelGrid(False)
+    ctx.forceFusedVoxelGrid(False)
 
 
 @pytest.mark.parametrize("n", [1, 2, 767, 768, 769, 3071, 3072, 3073, 20000])
