@@ -418,7 +418,7 @@ struct QueryCache {                         // 128 B per query (global-memory la
     float4 w[8];                            // 0: q0.xyz, candidate count (-1 none, -2 overflow) | 1: plane A ids 0..3 | 2: id 4, valid, pa, pb |
 };                                          // 3: pc, pd, top-5 list positions, plane used last | 4..6: plane B (ids | id 4, valid, pa, pb | pc, pd) | 7: unused
 static_assert(sizeof(QueryCache) == 128, "QueryCache must be 128 bytes");
-constexpr int S2M_GROW = CAND_CAP + 4;      // global candidate rows: 64 entries + padding for the 4-wide scan
+constexpr int S2M_GROW = CAND_CAP + 8;      // global candidate rows: 64 entries + padding for the 8-wide scan
 
 struct alignas(16) S2MMail { float tf[6]; int iters, converged, degenerate, ran, n_scan, n_ds, m_ds, err; int pad[2]; };
 static_assert(sizeof(S2MMail) == 64, "S2MMail must be 64 bytes");
@@ -727,12 +727,12 @@ __device__ __forceinline__ void s2m_round(const S2MArgs& a, const int n, const i
 #pragma unroll
                 for (int j = 1; j < 5; ++j) thr = ck[j] > thr ? ck[j] : thr;
                 unsigned long long mask = 0; int n1 = 0;                 // n1: entries within 1 m — fewer than five ⇒ no plane (:1097), nothing to order
-                for (int f0 = 0; f0 < cnt; f0 += 4) {
-                    float4 p[4];
+                for (int f0 = 0; f0 < cnt; f0 += 8) {
+                    float4 p[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) p[u] = ldq<SM>(row + f0 + u);          // the row is padded: entries past cnt are read but masked out
+                    for (int u = 0; u < 8; ++u) p[u] = ldq<SM>(row + f0 + u);          // the row is padded: entries past cnt are read but masked out
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const float d = sqdist_dev(sel, p[u]);
                         const unsigned long long k = nn_key(d, __float_as_int(p[u].w));
                         mask |= (unsigned long long)((k <= thr) && (f0 + u < cnt)) << (f0 + u);
