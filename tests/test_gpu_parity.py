@@ -232,6 +232,48 @@ def test_device_qr_solve_matches_opencv_golden(ctx, oracle):
             assert np.array_equal(x2[i], xo), i
 
 
+def test_solver_dense_map_overflowing_lists(ctx, oracle):
+    """A map much denser than the candidate lists can hold (points every 0.12 m on a floor and two walls: several hundred within
+    1.15 m of a query, against a capacity of 64): every list overflows and is replaced by the exact five nearest points, found by the
+    half warp that rebuilds it, in every iteration.  Poses of all iterations against the oracle (north-star tolerance), selected-row
+    counts equal, and — both layouts, cache on / off — one arithmetic."""
+    rng = np.random.default_rng(21)
+    g = np.arange(-6, 6, 0.12, dtype=np.float32)
+    X, Y = np.meshgrid(g, g)
+    floor = np.stack([X.ravel(), Y.ravel(), np.full(X.size, -1.5, np.float32) + 0.01 * np.sin(3 * X.ravel())], 1)
+    h = np.arange(-1.5, 1.5, 0.12, dtype=np.float32)
+    A, H = np.meshgrid(g, h)
+    wall1 = np.stack([A.ravel(), np.full(A.size, 6.0, np.float32) + 0.01 * np.cos(2 * A.ravel()), H.ravel()], 1)
+    wall2 = np.stack([np.full(A.size, -6.0, np.float32) + 0.02 * np.sin(A.ravel()), A.ravel(), H.ravel()], 1)
+    mp = np.concatenate([floor, wall1, wall2]).astype(np.float32)
+    mp += rng.normal(scale=0.004, size=mp.shape).astype(np.float32)
+    mp = np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1)
+    truth = np.array([0.01, -0.02, 0.03, 0.2, -0.1, 0.05], np.float32)
+    pick = rng.choice(len(mp), 6000, replace=False)
+    scan_map = mp[pick].copy(); scan_map[:, :3] += rng.normal(scale=0.01, size=(len(pick), 3)).astype(np.float32)
+    # the scan = those map points seen from the true pose (inverse transform), so that the solve has something to converge to
+    from bench import pose_to_T
+    T = pose_to_T(truth.astype(np.float64)); Ti = np.linalg.inv(T)
+    scan = scan_map.copy(); scan[:, :3] = (scan_map[:, :3].astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3]).astype(np.float32)
+    init = (truth + np.array([0.004, -0.003, 0.01, 0.12, 0.08, -0.03], np.float32)).astype(np.float32)
+    ctx.setLocalMap(mp); ctx.setCurrentScan(scan)
+    ds, n = ctx.downsampleCurrentScan(len(scan))
+    o = oracle.scan2map(ds, mp, init, 12, force_all=True)
+    runs = []
+    for glob in (False, True):
+        for no_cache in (False, True):
+            ctx.solverGlobalState(glob); ctx.disableSolverCache(no_cache)
+            ctx.setLMState(0, np.eye(6, dtype=np.float32))
+            pose, tr = ctx.scan2MapOptimization(init, 12, force_all_iters=True)
+            runs.append((tr.poses().copy(), tr.nsels().copy()))
+            assert np.max(np.abs(runs[-1][0][:, 3:] - o["trace"][:, 3:])) < 1e-4 and np.max(np.abs(runs[-1][0][:, :3] - o["trace"][:, :3])) < 1e-5
+            assert np.max(np.abs(runs[-1][1].astype(int) - o["nsel"].astype(int))) <= 3
+    ctx.solverGlobalState(False); ctx.disableSolverCache(False)
+    for r in runs[1:]:
+        assert np.array_equal(r[1], runs[0][1]) and np.array_equal(r[0].view(np.uint32), runs[0][0].view(np.uint32))
+    assert runs[0][1].min() > 1000
+
+
 def test_solver_paths_agree(ctx, oracle, kitti_case):
     """Scans that fit one round of the grid keep the per-query state (candidate list, cached planes) in shared memory, larger ones run
     several rounds with the same state in global memory.  Forcing the global layout on the same instance is the same arithmetic in
