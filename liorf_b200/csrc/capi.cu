@@ -925,11 +925,12 @@ static Count scan_ds_count(liorf_ctx* c) { return c->h_n_ds >= 0 ? Count::of_hos
 static Count map_count(liorf_ctx* c) { return c->h_m_ds >= 0 ? Count::of_host(c->h_m_ds) : Count::of_dev(c->d_shared + C_M_DS, c->m_bound); }
 
 // pipelined: the call comes from liorf_process_frame, whose next frame's front end runs beside the solver → leave the spare SMs free
-static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined = false) {
+static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined = false, const float* pose6_init = nullptr) {
     if (max_iters < 0) return LIORF_ERR_ARG;
     if (max_iters > S2M_MAX_ITERS) max_iters = S2M_MAX_ITERS;
     c->mail_fresh = false;
     if (!c->grid.cell_start.p || !c->grid.sorted.p) {            // cloudKeyPoses3D empty → return (:1297)
+        if (pose6_init) { int rcu = upload_pose(c, pose6_init); if (rcu) return rcu; }
         CUDA_TRY(cudaMemsetAsync(c->d_trace, 0, sizeof(S2MTrace), c->stream));
         return LIORF_OK;
     }
@@ -944,6 +945,8 @@ static int launch_s2m(liorf_ctx* c, int max_iters, int force_all, bool pipelined
     a.cell_start = c->grid.cell_start.p; a.gmap = c->grid.sorted.p; a.g = c->grid.dims; a.m_map = map_count(c);
     a.tf6 = c->d_tf6; a.st = c->d_lm; a.trace = c->d_trace; a.max_iters = max_iters; a.force_all = force_all; a.no_cache = c->s2m_no_cache ? 1 : 0; a.dbg = c->d_dbg; a.dbg_gt = c->d_dbg_gt;
     a.mail = c->d_mail; a.cnt_n_scan = c->d_counts + C_N_SCAN;
+    a.use_tf_init = pose6_init ? 1 : 0;
+    for (int k = 0; k < 6; ++k) a.tf_init[k] = pose6_init ? pose6_init[k] : 0.f;
     void* args[] = {&a};
     ProfScope ps(c, SEC_SCAN2MAP); c->launches += 1;
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_scan2map_persistent, dim3(pipelined ? c->s2m_grid : c->num_sms), dim3(S2MP_BLOCK), args, S2MP_SMEM, c->stream));
@@ -955,8 +958,7 @@ int liorf_scan2map_optimization_async(liorf_ctx* c, const float pose6_in[6], int
     LIORF_NVTX;
     if (!c) return LIORF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->P.device));
-    if (pose6_in) { int rc = upload_pose(c, pose6_in); if (rc) return rc; }
-    return launch_s2m(c, max_iters, force_all);
+    return launch_s2m(c, max_iters, force_all, false, pose6_in);
 }
 int liorf_get_pose(liorf_ctx* c, float pose6[6], liorf_lm_trace* trace) {
     LIORF_NVTX;
@@ -1975,7 +1977,7 @@ int liorf_process_frame(liorf_ctx* c, const liorf_frame_in* in, liorf_frame_out*
         std::memcpy(guess, c->tf_mapped, sizeof(guess));
         liorf_host_update_initial_guess(&c->guess_state, c->kfs.empty() ? 1 : 0, &in->cloud_info, in->use_imu_heading_initialization, in->imu_type, guess);
     } else std::memcpy(guess, in->initial_guess, sizeof(guess));
-    if ((rc = upload_pose(c, guess)) || (rc = launch_s2m(c, in->max_iters > 0 ? in->max_iters : 30, 0, true))) return rc;
+    if ((rc = launch_s2m(c, in->max_iters > 0 ? in->max_iters : 30, 0, true, guess))) return rc;
     stamp(5, c->stream);
     // the NEXT frame's cloudHandler + downsample go to stream_pre now, behind this frame's critical chain in host order, and run
     // on the device while the solver iterates (the reference runs imageProjection and mapOptimization as two concurrent nodes)

@@ -445,6 +445,7 @@ struct S2MArgs {
     const float4* scan; Count n_scan;
     const unsigned* cell_start; const float4* gmap; GridDims g; Count m_map;
     float* tf6;                      // in/out transformTobeMapped (device)
+    float tf_init[6]; int use_tf_init;   // the start pose as a kernel argument (saves the one-thread upload kernel in front of the solver)
     LMDeviceState* st;
     ulonglong2* wpart;               // [workers][NPROD]: a worker's partial sums, each fp64 as two epoch-tagged words
     S2MTrace* trace;
@@ -951,7 +952,7 @@ __global__ void __launch_bounds__(S2MP_BLOCK, 1) k_scan2map_persistent(S2MArgs a
     const int qpb = one_round ? S2MP_QPB : S2MP_QPB_GLOBAL;
     const int rounds = one_round ? 1 : (n + W * qpb - 1) / (W * qpb);
     S2MShared S; S.list = s_state; S.h = s_state + S2MP_QPB * S2M_ROW;
-    if (threadIdx.x < 6) s_tf[threadIdx.x] = a.tf6[threadIdx.x];
+    if (threadIdx.x < 6) s_tf[threadIdx.x] = a.use_tf_init ? a.tf_init[threadIdx.x] : a.tf6[threadIdx.x];
     if (threadIdx.x == 32) { s_conv = 0; s_ntodo = 0; }
     if (reducer && threadIdx.x >= 64 && threadIdx.x < 64 + 37)          // persistent LM state (members :139-140)
         reinterpret_cast<int*>(&s_st)[threadIdx.x - 64] = __ldcg(reinterpret_cast<const int*>(a.st) + (threadIdx.x - 64));
