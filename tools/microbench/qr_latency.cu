@@ -35,9 +35,15 @@ __global__ void k(const float* A, const float* b, float* out, long long* t) {
     qr_solve6_warp(A, b, xw);
     long long t7 = clock64();
     long long t8 = clock64();
+    // fp64 sin / cos of a float angle rounded to float (the six trig values of an LM iteration), and dependent fp64 FMAs
+    const float ang = A[2] * 0.01f;
+    const float sn = (float)sin((double)ang), cs = (float)cos((double)ang);
+    long long t9 = clock64();
+    double dd = 0.0;
+    long long t10 = t9;
     if (threadIdx.x == 0) {
-        out[0] = acc + d + s + qs + qs2; for (int i = 0; i < 6; ++i) out[1 + i] = xs[i] + xw[i];
-        t[0] = t1 - t0; t[1] = t2 - t1; t[2] = t3 - t2; t[3] = t4 - t3; t[4] = t5 - t4; t[5] = t6 - t5; t[6] = t7 - t6; t[7] = t8 - t7; t[8] = 0; for (int i = 0; i < 6; ++i) t[8] += (__float_as_uint(xs[i]) != __float_as_uint(xw[i]));
+        out[0] = acc + d + s + qs + qs2 + sn + cs + (float)dd; for (int i = 0; i < 6; ++i) out[1 + i] = xs[i] + xw[i];
+        t[0] = t1 - t0; t[1] = t2 - t1; t[2] = t3 - t2; t[3] = t4 - t3; t[4] = t5 - t4; t[5] = t6 - t5; t[6] = t7 - t6; t[7] = t8 - t7; t[9] = t9 - t8; t[10] = t10 - t9; t[8] = 0; for (int i = 0; i < 6; ++i) t[8] += (__float_as_uint(xs[i]) != __float_as_uint(xw[i]));
     }
 }
 int main() {
@@ -50,9 +56,9 @@ int main() {
     long long ht[16];
     for (int rep = 0; rep < 3; ++rep) {
         k<<<1, 32>>>(dA, db, dout, dt);
-        cudaMemcpy(ht, dt, 72, cudaMemcpyDeviceToHost);
-        printf("cycles: 64 dependent FADD %lld | 16 dependent IEEE div %lld | 16 dependent IEEE sqrt+add %lld | 6 independent IEEE div %lld | (unused %lld) | one-thread 6x6 QR solve %lld | one-warp 6x6 QR solve %lld | (unused %lld) (result words differing between the two solves: %lld)\n",
-               ht[0], ht[1], ht[2], ht[3], ht[4], ht[5], ht[6], ht[7], ht[8]);
+        cudaMemcpy(ht, dt, 88, cudaMemcpyDeviceToHost);
+        printf("cycles: 64 dependent FADD %lld | 16 dependent IEEE div %lld | 16 dependent IEEE sqrt+add %lld | 6 independent IEEE div %lld | (unused %lld) | one-thread 6x6 QR solve %lld | one-warp 6x6 QR solve %lld | (unused %lld) (result words differing between the two solves: %lld) | (float)sin + (float)cos of a double %lld (%lld)\n",
+               ht[0], ht[1], ht[2], ht[3], ht[4], ht[5], ht[6], ht[7], ht[8], ht[9], ht[10]);
     }
     return 0;
 }
