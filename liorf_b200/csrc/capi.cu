@@ -436,7 +436,11 @@ void liorf_destroy(liorf_ctx* c) {
     c->icp_nn_d2.release(); c->icp_grid.counts.release(); c->icp_grid.cell_start.release(); c->icp_grid.sorted.release(); c->icp_grid.scan.status.release();
     if (c->icp_out) cudaFree(c->icp_out);
     if (c->sct_over_cnt) cudaFree(c->sct_over_cnt);
-    for (VoxelGridWork* vw : {&c->vg, &c->vg_map, &c->alt.vg}) { vw->pts_sorted.release(); vw->cta_hist.release(); vw->cta_heads.release(); if (vw->fused_bar) cudaFree(vw->fused_bar); vw->fused_bar = nullptr; }
+    for (VoxelGridWork* vw : {&c->vg, &c->vg_map, &c->alt.vg}) {
+        vw->pts_sorted.release(); vw->cta_hist.release(); vw->cta_heads.release();
+        if (vw->fused_bar) cudaFree(vw->fused_bar); vw->fused_bar = nullptr;
+        if (vw->dbg) cudaFree(vw->dbg); vw->dbg = nullptr;
+    }
     cudaFree(c->d_counts_base); cudaFree(c->d_misc); cudaFree(c->d_tick); cudaFree(c->vg.meta); cudaFree(c->dk.start_inv); cudaFree(c->d_tf6); cudaFree(c->d_lm);
     cudaFree(c->d_trace); cudaFree(c->d_lm_out); cudaFree(c->d_partial); cudaFree(c->d_bins); cudaFree(c->d_wpart); cudaFree(c->d_res); cudaFree(c->d_mail); if (c->icp_state) cudaFree(c->icp_state); c->qcache.release(); c->cand.release();
     if (c->d_dbg) cudaFree(c->d_dbg);
