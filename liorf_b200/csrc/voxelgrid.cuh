@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(VGF_THREADS, 2) k_vg_fused(VgFusedArgs a) {
                 const int i = tb + w * (32 * VGF_IPT) + j * 32 + l;
                 const bool valid = i < hi;
                 if (pass == 0) { key[j] = valid ? vgf_key(a.pts[i], inv, b0, b1, b2, m1, m2) : 0xffffffffu; val[j] = (unsigned)i; }
-                else { key[j] = valid ? kin[i] : 0xffffffffu; val[j] = valid ? vin[i] : 0u; }
+                else { key[j] = valid ? __ldcg(kin + i) : 0xffffffffu; val[j] = valid ? __ldcg(vin + i) : 0u; }      // written by other CTAs in the previous pass: read behind L1
             }
         };
         // per-warp stable ranks of a loaded tile (s_whist[w] must be zero on entry); leaves the warp's digit counts in s_whist[w]
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(VGF_THREADS, 2) k_vg_fused(VgFusedArgs a) {
     // ---- segment heads: count per chunk | barrier | every head's thread sums its segment ----
     // (item pair of thread t in a tile: tb + 2t, tb + 2t + 1 — contiguous, so the block scan numbers the heads in ascending order)
     {
-        auto is_head = [&](int i) { return i < hi && (i == 0 || kin[i] != kin[i - 1]); };
+        auto is_head = [&](int i) { return i < hi && (i == 0 || __ldcg(kin + i) != __ldcg(kin + i - 1)); };
         unsigned f0r = 0, f1r = 0;                         // a chunk of one tile keeps its flags across the barrier
         unsigned cnt_local = 0;
         for (int tb = lo; tb < hi; tb += VGF_TILE) {
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(VGF_THREADS, 2) k_vg_fused(VgFusedArgs a) {
                 // centroid of the voxel that starts at item i0 + j: sequential fp32 sums over the contiguous sorted points (ascending input
                 // index within a voxel: the sort is stable), divided by (float)count; the segment ends where the key changes
                 const unsigned b = (unsigned)(i0 + j);
-                const unsigned key = kin[b];
+                const unsigned key = __ldcg(kin + b);
                 float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
                 unsigned k = b; bool open = true;
                 while (open) {
