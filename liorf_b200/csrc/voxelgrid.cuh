@@ -703,9 +703,10 @@ inline int voxel_grid_device(const float4* in, Count cnt, float leaf, float4* ou
     if (nb <= 0) { CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(int), s)); w.last_launches = 1; return LIORF_OK; }
     int rc;
     w.last_launches = 10;                                           // multi-kernel path: memset + minmax + keys + hist + 4 passes + head scan + centroids
-    // (clouds of more than one tile per CTA keep the multi-kernel path: the one-kernel version then sweeps its chunk twice per pass and was
-    // measured slower — 0.47 against 0.29 ms for 2.3 M points; tests force it to cover the multi-tile code)
-    if (coop_grid > 0 && w.fused_bar && !w.force_multi && ((nb > VGS_CAP && nb <= coop_grid * VGF_TILE) || w.force_large)) {
+    // (clouds of more than four tiles per CTA keep the multi-kernel path: a chunk of several tiles is swept twice per pass, and the
+    // one-kernel version was measured slower there — 0.47 against 0.29 ms for 2.3 M points on 132 CTAs, 0.23 against 0.15 ms for 650 k on
+    // 64 — while at two tiles per CTA it is still ahead: the look-ahead front end's 24 k-point bound on 16 CTAs, 0.040 against 0.069 ms)
+    if (coop_grid > 0 && w.fused_bar && !w.force_multi && ((nb > VGS_CAP && nb <= 4 * coop_grid * VGF_TILE) || w.force_large)) {
         if ((rc = w.keys.reserve(nb)) || (rc = w.sort.keys_alt.reserve(nb)) || (rc = w.sort.vals_a.reserve(nb)) || (rc = w.sort.vals_b.reserve(nb)) ||
             (rc = w.seg_start.reserve((size_t)nb + 1)) || (rc = w.pts_sorted.reserve(nb)) || (rc = w.partial.reserve((size_t)coop_grid * 6)) ||
             (rc = w.cta_hist.reserve((size_t)coop_grid * RADIX)) || (rc = w.cta_heads.reserve(coop_grid))) return rc;
