@@ -253,13 +253,13 @@ int liorf_sc_shard_debug_state(liorf_ctx* ctx, unsigned out[68]);   /* debugging
  * base_key = 0; -1 = each cloud by its own pose as performRSLoopClosure does), VoxelGrid(icp_leaf = loopClosureICPSurfLeafSize),
  * guards (< 300 / < 1000 points → ran = 0), pcl::IterativeClosestPoint with max correspondence distance max_corr_dist
  * (= 2 historyKeyframeSearchRadius), max_iters (100), transformation / fitness epsilons 1e-6, no RANSAC, then getFitnessScore().
- * The caller applies `converged && fitness <= historyKeyframeFitnessScore` (:665). */
+ * The caller applies `converged && fitness <= historyKeyframeFitnessScore` (:677). */
 typedef struct {
     int ran, converged, convergence_state /* 1 iterations, 2 transform, 3 abs mse, 4 rel mse, 5 no correspondences */, iterations;
     int n_source, n_target;
     float fitness;
     float transform[16];            /* icp.getFinalTransformation(), row-major 4x4 */
-    float pose6[6];                 /* its (roll, pitch, yaw, x, y, z) by pcl::getTranslationAndEulerAngles (:693) */
+    float pose6[6];                 /* its (roll, pitch, yaw, x, y, z) by pcl::getTranslationAndEulerAngles (:707) */
 } liorf_icp_result;
 int liorf_loop_closure_icp(liorf_ctx* ctx, int loop_key_cur, int loop_key_pre, int history_search_num, int loop_index, float icp_leaf, float max_corr_dist,
                            int max_iters, liorf_icp_result* out);
