@@ -170,26 +170,71 @@ def traffic_entry(key):
 # ----------------------------------------------------------------------------------------------------------------
 # config 4: Livox deskew + registration (one frame: projectPointCloud with the 200 Hz IMU table → downsample → grid → solve)
 # ----------------------------------------------------------------------------------------------------------------
-def livox_row(device, steps, warmup):
-    import ctypes as C
-    import torch
-    import liorf_b200
+LIVOX_FILT = dict(lidarMinRange=1.0, lidarMaxRange=1000.0, N_SCAN=6, downsampleRate=1, point_filter_num=3)   # config/lio_sam_livox.yaml:27-32
+
+
+def livox_inputs(nkf=50):
+    """config 4 inputs (seeded): keyframe scans along +x, the query scan swept at 1 rad/s with its 200 Hz IMU table, the start pose"""
     from tools import synth
-    nkf = 50
-    ctx = liorf_b200.Context(device=device, N_SCAN=6, downsampleRate=1, point_filter_num=3, mappingSurfLeafSize=0.15, surroundingKeyframeMapLeafSize=0.3)
-    ctx.reserve(1 << 16, 1 << 20, 1 << 20, 0)
-    for k in range(nkf):
-        p = np.array([0, 0, 0, 1.0 * k, 0, 0], np.float64)
-        ctx.setCurrentScan(synth.raw_to_xyzi(synth.scan(synth.LIVOX, p, seed=synth.SEED0 + 3000 + k)))
-        ctx.downsampleCurrentScan(want_output=False)
-        ctx.addKeyframe(p.astype(np.float32), 0.1 * k)
-    m = ctx.extractSurroundingKeyFrames(list(range(nkf)))
+    poses = [np.array([0, 0, 0, 1.0 * k, 0, 0], np.float64) for k in range(nkf)]
+    kf_scans = [synth.raw_to_xyzi(synth.scan(synth.LIVOX, p, seed=synth.SEED0 + 3000 + k)) for k, p in enumerate(poses)]
     omega = (0.02, -0.03, 1.0)                                             # 1 rad/s yaw sweep: the deskew is not a no-op
-    qp = np.array([0, 0, 0, 1.0 * (nkf - 1), 0, 0], np.float64)
+    qp = poses[-1]
     raw = synth.scan(synth.LIVOX, qp, omega=omega, seed=synth.SEED0 + 3500)
     t0 = 20.0
     it, rot, ptr = synth.imu_table(t0, t0 + float(raw["time"][-1]), omega, rate_hz=200.0, gyro_noise=1e-3, seed=4)
-    init = (qp + 0.5 * PERTURB).astype(np.float32)
+    return dict(poses=poses, kf_scans=kf_scans, raw=raw, t0=t0, imu_time=it, imu_rot=rot, imu_ptr=ptr, init=(qp + 0.5 * PERTURB).astype(np.float32))
+
+
+def livox_cpu(L, reps, gpu=None):
+    """the CPU path on the same config-4 step (projectPointCloud + downsampleCurrentScan + kd-tree build + scan2MapOptimization with the
+    reference's convergence break), all host threads; `gpu` = (pose, counts) of the GPU run of the same inputs → differences reported"""
+    if ORACLE_DIR not in sys.path:
+        sys.path.insert(0, ORACLE_DIR)
+    import pyoracle as o
+    all_cores = os.cpu_count() or 1
+    o.set_num_threads(all_cores)
+    kfs = [o.voxel_grid(s, 0.15)[0] for s in L["kf_scans"]]
+    mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(c, p.astype(np.float32)) for c, p in zip(kfs, L["poses"])]), 0.3)
+    use_ref = o.ref() is not None
+    ts, split = [], np.zeros(3)
+    for r in range(reps + 1):
+        a = time.perf_counter()
+        cloud, kept = o.project_point_cloud(L["raw"], LIVOX_FILT, L["t0"], L["imu_time"], L["imu_rot"], L["imu_ptr"], True)
+        b = time.perf_counter()
+        ds, _, _ = o.voxel_grid(cloud, 0.15)
+        c = time.perf_counter()
+        res = o.scan2map(ds, mp, L["init"], 30, False, None, use_ref_kdtree=use_ref)
+        d = time.perf_counter()
+        if r > 0:
+            ts.append((d - a) * 1e3); split += np.array([b - a, c - b, d - c]) * 1e3
+    out = dict(value=float(np.median(ts)), unit="ms/frame", cores=all_cores, kind="port",
+               sample="%d repetitions of the same livox_deskew step (after 1 warm-up): oracle restatement of projectPointCloud / deskewPoint, VoxelGrid, scan2MapOptimization (early exit), "
+                      "kd-tree = the reference's vendored nanoflann%s; OpenMP %d threads (the deskew loop is serial in the reference too)" % (reps, "" if use_ref else " (oracle/_ref missing: brute-force kNN)", all_cores),
+               ms=stats_ms(ts), split_ms=dict(deskew=split[0] / reps, downsample=split[1] / reps, scan2map=split[2] / reps),
+               n_kept=int(len(kept)), n_ds=int(len(ds)), m_map=int(len(mp)), lm_iters=int(res["iters"]))
+    if gpu is not None:
+        pose, cnt, m = gpu
+        out["gpu_vs_cpu"] = dict(final_pose_max_abs_diff=float(np.max(np.abs(np.asarray(pose, np.float64) - res["tf"].astype(np.float64)))),
+                                 same_n_kept=bool(cnt["n_scan"] == len(kept)), same_n_ds=bool(cnt["n_ds"] == len(ds)), same_m_map=bool(m == len(mp)),
+                                 same_lm_iters=bool(cnt["iters"] == int(res["iters"])))
+    return out
+
+
+def livox_row(device, steps, warmup, cpu_reps=5):
+    import ctypes as C
+    import torch
+    import liorf_b200
+    L = livox_inputs()
+    nkf = len(L["poses"])
+    ctx = liorf_b200.Context(device=device, N_SCAN=6, downsampleRate=1, point_filter_num=3, mappingSurfLeafSize=0.15, surroundingKeyframeMapLeafSize=0.3)
+    ctx.reserve(1 << 16, 1 << 20, 1 << 20, 0)
+    for k in range(nkf):
+        ctx.setCurrentScan(L["kf_scans"][k])
+        ctx.downsampleCurrentScan(want_output=False)
+        ctx.addKeyframe(L["poses"][k].astype(np.float32), 0.1 * k)
+    m = ctx.extractSurroundingKeyFrames(list(range(nkf)))
+    raw, t0, it, rot, ptr, init = L["raw"], L["t0"], L["imu_time"], L["imu_rot"], L["imu_ptr"], L["init"]
     dev = torch.device(f"cuda:{device}")
     ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -210,11 +255,15 @@ def livox_row(device, steps, warmup):
         ctx.scan2MapOptimizationAsync(init, 30, False)
         with torch.cuda.stream(ext):
             e1.record()
-        ctx.getPose()
+        pose = ctx.getPose()
         if i >= warmup:
             ms.append(e0.elapsed_time(e1))
     tm = ctx.getTiming(); cnt = ctx.lastCounts()
     ctx.close()
+    try:                                                                    # the CPU figure must never take the GPU row down
+        cpu = livox_cpu(L, cpu_reps, (pose, cnt, m)) if cpu_reps > 0 else None
+    except Exception as e:
+        cpu = dict(error=repr(e))
     n_kept = cnt["n_scan"]
     dk_ms = tm["deskew"][0] / max(tm["deskew"][1], 1)
     alg = 24 * len(raw) + 16 * n_kept
@@ -223,7 +272,8 @@ def livox_row(device, steps, warmup):
                 n_kept=n_kept, n_ds=cnt["n_ds"], m_map=m, lm_iters=cnt["iters"], frame_ms=stats_ms(ms),
                 kernel_ms={k: v[0] / max(v[1], 1) for k, v in tm.items() if v[1]},
                 deskew_roofline=dict(kernel="k_first_kept + scan + k_deskew_points", bound="hbm", achieved=alg / (dk_ms * 1e-3) / 1e9 if dk_ms > 0 else None, unit="GB/s",
-                                     algorithmic_bytes_per_launch=alg, avg_launch_ms=dk_ms))
+                                     algorithmic_bytes_per_launch=alg, avg_launch_ms=dk_ms),
+                cpu_baseline=cpu)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -615,13 +665,13 @@ def bench_single_headline(args, device, W, K, peaks, peak_src):
         try:
             i3 = make_single_inputs("os1_128_dense")
             s3 = SingleFrameGpu("os1_128_dense", i3, device)
-            d, w, _ = s3.run(min(K, 20), 3, "dev")
+            d, w, p3 = s3.run(min(K, 20), 3, "dev")
             s3m = s3.timing["scan2map"]; s3ms = s3m[0] / max(s3m[1], 1)
             rows["os1_128_dense"] = dict(config=single_config("os1_128_dense", i3, s3.counts["n_ds"], s3.counts["m_ds"]), solve_ms=stats_ms(d),
                                          kernel_ms_per_step={k: v[0] / max(v[1], 1) for k, v in s3.timing.items() if v[1]}, map_build_ms=s3.map_build_ms(3),
                                          roofline=dict(kernel="k_scan2map_persistent", bound="hbm", achieved=96.0 * s3.counts["n_ds"] * 30 / (s3ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
                                                        unit="GB/s", frac=96.0 * s3.counts["n_ds"] * 30 / (s3ms * 1e-3) / 1e9 / peaks["hbm_gbs"], avg_launch_ms=s3ms),
-                                         cpu_baseline=cpu_single(i3, "os1_128_dense", 2, s3))
+                                         cpu_baseline=cpu_single(i3, "os1_128_dense", 2, s3, check_pose=p3))
             s3.close()
         except Exception as e:                                      # an extra must never take the headline down
             rows["os1_128_dense"] = dict(error=repr(e))
