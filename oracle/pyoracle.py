@@ -16,7 +16,7 @@ PRAW = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("i", "<f4"), ("ring"
 
 def build(force=False):
     so = os.path.join(HERE, "libliorf_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cpp", "liorf_oracle.hpp", "ref_nanoflann.cpp", "ref_scancontext.cpp", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cpp", "liorf_oracle.hpp", "ref_nanoflann.cpp", "ref_scancontext.cpp", "ref_mapopt.cpp", "ref_imageproj.cpp", "Makefile")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
     if stale:
         subprocess.run(["make", "-C", HERE, "-s"], check=True)
@@ -340,6 +340,119 @@ class RefSCManager:
         d = C.c_double(); s = C.c_int()
         refsc().refsc_distance(self.h, _fp(sc1), _fp(sc2), C.byref(d), C.byref(s))
         return d.value, s.value
+
+
+class RefMapOpt:
+    """The reference's OWN mapOptimization node (src/mapOptmization.cpp compiled unchanged against oracle/shim_ros into
+    oracle/_ref/libliorf_ref_mapopt.so) — the pin of the oracle's a4-a9 / f1 / f2 restatements.  The node keeps function-static state
+    (timeLastProcessing :254, lastImuTransformation :904 ...), so every instance loads its own private copy of the library.
+    params: ParamServer names without the "liorf/" prefix (include/utility.h:153-237)."""
+
+    @staticmethod
+    def available():
+        build()
+        return os.path.exists(os.path.join(HERE, "_ref", "libliorf_ref_mapopt.so"))
+
+    def __init__(self, **params):
+        import shutil
+        import tempfile
+        build()
+        src = os.path.join(HERE, "_ref", "libliorf_ref_mapopt.so")
+        fd, self._path = tempfile.mkstemp(suffix=".so", prefix="liorf_ref_mapopt_")
+        os.close(fd)
+        shutil.copyfile(src, self._path)
+        self.l = C.CDLL(self._path)
+        self.l.refmo_create.restype = C.c_void_p
+        self.l.refmo_param_num.argtypes = [C.c_char_p, C.c_double]
+        self.l.refmo_param_str.argtypes = [C.c_char_p, C.c_char_p]
+        defaults = dict(sensor="velodyne", N_SCAN=64, Horizon_SCAN=1800, mappingProcessInterval=0.0, numberOfCores=1, mappingSurfLeafSize=0.4,
+                        surroundingKeyframeMapLeafSize=0.5, surroundingKeyframeDensity=2.0, surroundingKeyframeSearchRadius=50.0,
+                        surroundingkeyframeAddingDistThreshold=1.0, surroundingkeyframeAddingAngleThreshold=0.2, z_tollerance=1000.0,
+                        rotation_tollerance=1000.0, imuType=0, imuRPYWeight=0.01)      # config/kitti.yaml
+        defaults.update(params)
+        for k, v in defaults.items():
+            if isinstance(v, str):
+                self.l.refmo_param_str(("liorf/" + k).encode(), v.encode())
+            else:
+                self.l.refmo_param_num(("liorf/" + k).encode(), float(v))
+        self.h = C.c_void_p(self.l.refmo_create())
+
+    def close(self):
+        if self.h:
+            self.l.refmo_destroy(self.h); self.h = None
+            try:
+                os.unlink(self._path)
+            except OSError:
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cloud_info(self, stamp, cloud, imu_available=0, odom_available=0, rpy_init=None, guess=None):
+        """one cloud_info message through laserCloudInfoHandler (:236-275)"""
+        cloud = _as_p4(cloud)
+        r = None if rpy_init is None else np.ascontiguousarray(rpy_init, np.float32)
+        g = None if guess is None else np.ascontiguousarray(guess, np.float32)
+        self.l.refmo_cloud_info(self.h, C.c_double(stamp), _fp(cloud), C.c_int(len(cloud)), C.c_int(int(imu_available)), C.c_int(int(odom_available)),
+                                None if r is None else _fp(r), None if g is None else _fp(g))
+
+    def state(self):
+        tf = np.zeros(6, np.float32); cnt = np.zeros(5, np.int32)
+        self.l.refmo_state(self.h, _fp(tf), _fp(cnt))
+        return dict(tf=tf, keyframes=int(cnt[0]), n_ds=int(cnt[1]), m_ds=int(cnt[2]), degenerate=int(cnt[3]), sc_entries=int(cnt[4]))
+
+    def set_transform(self, tf6):
+        tf = np.ascontiguousarray(tf6, np.float32)
+        self.l.refmo_set_transform(self.h, _fp(tf))
+
+    def get_cloud(self, which):
+        n = self.l.refmo_get_cloud(self.h, C.c_int(which), None, C.c_int(0))
+        if n < 0:
+            return None
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self.l.refmo_get_cloud(self.h, C.c_int(which), _fp(out), C.c_int(n))
+        return out[:n].copy()
+
+    def keypose(self, k):
+        p = np.zeros(6, np.float32); t = C.c_double()
+        if self.l.refmo_get_keypose(self.h, C.c_int(k), _fp(p), C.byref(t)) < 0:
+            return None
+        return p, t.value
+
+    def set_scan_and_map(self, scan_ds, map_ds):
+        a = _as_p4(scan_ds); b = _as_p4(map_ds)
+        self.l.refmo_set_scan_and_map(self.h, _fp(a), C.c_int(len(a)), _fp(b), C.c_int(len(b)))
+        self._n = len(a)
+
+    def iteration(self, it):
+        """{laserCloudOri/coeffSel clear, surfOptimization, combineOptimizationCoeffs, LMOptimization(it)} (:1304-1314) → (converged, tf, n_sel)"""
+        tf = np.zeros(6, np.float32); ns = C.c_int()
+        c = self.l.refmo_iteration(self.h, C.c_int(it), _fp(tf), C.byref(ns))
+        return bool(c), tf, ns.value
+
+    def surf_optimization(self):
+        coeff = np.zeros((self._n, 4), np.float32); flag = np.zeros(self._n, np.uint8)
+        self.l.refmo_surf_optimization(self.h, _fp(coeff), _fp(flag))
+        return coeff, flag
+
+    def scan2map(self, tf6, imu_available=0, rpy_init=None):
+        tf = np.array(tf6, np.float32).copy()
+        r = None if rpy_init is None else np.ascontiguousarray(rpy_init, np.float32)
+        self.l.refmo_scan2map(self.h, _fp(tf), C.c_int(int(imu_available)), None if r is None else _fp(r))
+        return tf
+
+    def lm_state(self):
+        P = np.zeros(36, np.float32)
+        d = self.l.refmo_get_lm_state(self.h, _fp(P))
+        return d, P
+
+    def sc_detect(self):
+        lid = C.c_int(); yaw = C.c_float()
+        self.l.refmo_sc_detect(self.h, C.byref(lid), C.byref(yaw))
+        return lid.value, yaw.value
 
 
 def cv_qr_solve6(A, b):

@@ -1,0 +1,4 @@
+// oracle/shim_ros — TEST INFRASTRUCTURE (see ros/ros.h).
+#pragma once
+#include <tf/transform_datatypes.h>
+namespace tf { struct TransformListener {}; }
