@@ -455,6 +455,72 @@ class RefMapOpt:
         return lid.value, yaw.value
 
 
+class RefImageProjection:
+    """The reference's OWN ImageProjection node (src/imageProjection.cpp compiled unchanged against oracle/shim_ros into
+    oracle/_ref/libliorf_ref_imageproj.so), driven through its public handlers only: imu() = imuHandler, cloud() = cloudHandler; the published
+    liorf/cloud_info is read back with last_info().  Every instance loads a private copy of the library (function-static state :291, :414)."""
+
+    @staticmethod
+    def available():
+        build()
+        return os.path.exists(os.path.join(HERE, "_ref", "libliorf_ref_imageproj.so"))
+
+    def __init__(self, **params):
+        import shutil
+        import tempfile
+        build()
+        fd, self._path = tempfile.mkstemp(suffix=".so", prefix="liorf_ref_imageproj_")
+        os.close(fd)
+        shutil.copyfile(os.path.join(HERE, "_ref", "libliorf_ref_imageproj.so"), self._path)
+        self.l = C.CDLL(self._path)
+        self.l.refip_create.restype = C.c_void_p
+        self.l.refip_cloud.restype = C.c_long
+        self.l.refip_param_num.argtypes = [C.c_char_p, C.c_double]
+        self.l.refip_param_str.argtypes = [C.c_char_p, C.c_char_p]
+        defaults = dict(sensor="velodyne", N_SCAN=64, Horizon_SCAN=1800, downsampleRate=2, point_filter_num=5, lidarMinRange=1.0, lidarMaxRange=1000.0,
+                        imuType=0, imuRate=100.0)                     # config/kitti.yaml
+        defaults.update(params)
+        for k, v in defaults.items():
+            if isinstance(v, str):
+                self.l.refip_param_str(("liorf/" + k).encode(), v.encode())
+            else:
+                self.l.refip_param_num(("liorf/" + k).encode(), float(v))
+        self.h = C.c_void_p(self.l.refip_create())
+
+    def close(self):
+        if self.h:
+            self.l.refip_destroy(self.h); self.h = None
+            try:
+                os.unlink(self._path)
+            except OSError:
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def imu(self, stamp, gyro_xyz, quat_xyzw=None):
+        g = np.ascontiguousarray(gyro_xyz, np.float64)
+        q = None if quat_xyzw is None else np.ascontiguousarray(quat_xyzw, np.float64)
+        self.l.refip_imu(self.h, C.c_double(stamp), _fp(g), None if q is None else _fp(q))
+
+    def cloud(self, stamp, raw, has_time=True):
+        """pushes one scan; returns the number of cloud_info messages published so far (the node answers two scans late, :209-215)"""
+        raw = np.ascontiguousarray(raw, dtype=PRAW)
+        return int(self.l.refip_cloud(self.h, C.c_double(stamp), _fp(raw), C.c_int(len(raw)), C.c_int(int(has_time))))
+
+    def last_info(self):
+        st = C.c_double(); av = np.zeros(2, np.int32); rpy = np.zeros(3, np.float32)
+        n = self.l.refip_last_info(C.byref(st), _fp(av), _fp(rpy), None, C.c_int(0))
+        if n < 0:
+            return None
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self.l.refip_last_info(C.byref(st), _fp(av), _fp(rpy), _fp(out), C.c_int(n))
+        return dict(stamp=st.value, imuAvailable=int(av[0]), odomAvailable=int(av[1]), rpy_init=rpy, cloud=out[:n].copy())
+
+
 def cv_qr_solve6(A, b):
     A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)
     x = np.zeros(6, np.float32)

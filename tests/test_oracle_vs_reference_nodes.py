@@ -1,0 +1,286 @@
+"""The oracle's restatement of the two ROS nodes, pinned to the reference's OWN source: /root/reference/src/mapOptmization.cpp and
+src/imageProjection.cpp compiled UNCHANGED against the header stand-ins of oracle/shim_ros (recipe: oracle/Makefile → oracle/_ref/
+libliorf_ref_mapopt.so, libliorf_ref_imageproj.so; wrappers oracle/ref_mapopt.cpp, oracle/ref_imageproj.cpp).
+
+What is the reference's own code in these comparisons: control flow, indexing, thresholds, float / double mixes, member state that persists
+across iterations and frames, queueing and call order of laserCloudInfoHandler (:236-275), updateInitialGuess (:899-958), extractNearby /
+extractCloud (:975-1044), downsampleCurrentScan (:1061-1067), surfOptimization / combineOptimizationCoeffs / LMOptimization /
+scan2MapOptimization / transformUpdate (:1074-1353), saveFrame / saveKeyFramesAndFactor (:1365-1384, 1503-1609), and of cloudHandler →
+cachePointCloud / deskewInfo / imuDeskewInfo / projectPointCloud / deskewPoint / findRotation (src/imageProjection.cpp:191-598).
+What is NOT: the arithmetic inside the third-party calls — the stand-ins forward VoxelGrid, ColPivHouseholderQR, cv::solve / eigen / inv,
+getTransformation, Affine3f and tf quaternions to oracle/liorf_oracle.hpp, the kd-tree is the reference's vendored nanoflann instead of FLANN,
+iSAM2 returns a new pose's initial value.  So a green test says: GIVEN those kernels, the oracle (and the library's host logic, where it is
+used below) does exactly what the reference does — bit for bit.  CPU only; skipped when oracle/_ref was never built."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def refnodes(oracle):
+    if not (oracle.RefMapOpt.available() and oracle.RefImageProjection.available()):
+        pytest.skip("oracle/_ref/libliorf_ref_mapopt.so / libliorf_ref_imageproj.so were never built (needs /root/reference at build time)")
+    return oracle
+
+
+def _map_and_scan(oracle, case, map_leaf=0.5, scan_leaf=0.4):
+    mp, _, _ = oracle.voxel_grid(np.concatenate([oracle.transform_cloud(c, p) for c, p in case["keyframes"]]), map_leaf)
+    ds, _, _ = oracle.voxel_grid(case["scan"], scan_leaf)
+    return ds, mp
+
+
+def test_surf_and_lm_optimization_bit_exact_vs_reference(refnodes, kitti_case):
+    """surfOptimization's flags and coefficients at the start pose, then 30 × {surfOptimization, combineOptimizationCoeffs, LMOptimization(i)} run by
+    the reference's own member functions: every per-iteration pose, every correspondence count, isDegenerate and matP equal the oracle's, bit for bit."""
+    o = refnodes
+    ds, mp = _map_and_scan(o, kitti_case)
+    R = o.RefMapOpt()
+    R.set_scan_and_map(ds, mp)
+    R.set_transform(kitti_case["init"])
+    so = o.surf_optimization(ds, mp, kitti_case["init"])
+    coeff, flag = R.surf_optimization()
+    assert np.array_equal(flag, so["flag"]) and flag.sum() > 0.7 * len(ds)
+    assert np.array_equal(_bits(coeff[flag == 1]), _bits(so["coeff"][flag == 1]))
+    res = o.scan2map(ds, mp, kitti_case["init"], 30, True, use_ref_kdtree=True)           # same kd-tree (the reference's nanoflann) on both sides
+    for it in range(30):
+        conv, tf, nsel = R.iteration(it)
+        assert np.array_equal(_bits(tf), _bits(res["trace"][it])), it
+        assert nsel == res["nsel"][it]
+    deg, P = R.lm_state()
+    assert deg == int(res["state"][0]) and np.array_equal(_bits(P), _bits(res["state"][1:]))
+    R.close()
+
+
+def test_degenerate_projector_and_state_persistence_vs_reference(refnodes):
+    """ground plane only: x / y / yaw unobservable → cv::eigen's small eigenvalues → isDegenerate, matP (:1242-1271); then a SECOND solve whose iteration 0
+    has fewer than 50 correspondences keeps the first solve's projector (members persist across frames, SURVEY trap 9)."""
+    o = refnodes
+    rng = np.random.default_rng(7)
+    g = np.zeros((20000, 4), np.float32); g[:, :2] = rng.uniform(-25, 25, size=(20000, 2)); g[:, 2] = -1.7 + rng.normal(scale=0.01, size=20000)
+    mp, _, _ = o.voxel_grid(g, 0.5)
+    q = np.zeros((6000, 4), np.float32); q[:, :2] = rng.uniform(-20, 20, size=(6000, 2)); q[:, 2] = -1.7 + rng.normal(scale=0.01, size=6000)
+    ds, _, _ = o.voxel_grid(q, 0.4)
+    init = np.array([0.01, -0.008, 0.02, 0.2, -0.1, 0.05], np.float32)
+    R = o.RefMapOpt()
+    R.set_scan_and_map(ds, mp)
+    R.set_transform(init)
+    res = o.scan2map(ds, mp, init, 12, True, use_ref_kdtree=True)
+    for it in range(12):
+        conv, tf, nsel = R.iteration(it)
+        assert np.array_equal(_bits(tf), _bits(res["trace"][it])), it
+    deg, P = R.lm_state()
+    assert deg == 1 == int(res["state"][0]) and np.array_equal(_bits(P), _bits(res["state"][1:]))
+    # second frame: 40 scan points only → N_sel < 50 at every iteration: LMOptimization returns false, pose untouched, projector kept
+    ds2 = ds[:40]
+    R.set_scan_and_map(ds2, mp)
+    R.set_transform(init)
+    res2 = o.scan2map(ds2, mp, init, 3, True, res["state"], use_ref_kdtree=True)
+    for it in range(3):
+        conv, tf, nsel = R.iteration(it)
+        assert not conv and nsel < 50 and np.array_equal(_bits(tf), _bits(init))
+    deg2, P2 = R.lm_state()
+    assert deg2 == 1 and np.array_equal(_bits(P2), _bits(P)) and np.array_equal(_bits(res2["state"]), _bits(res["state"]))
+    R.close()
+
+
+@pytest.mark.parametrize("imu_type", [0, 1])
+def test_scan2map_optimization_whole_function_vs_reference(refnodes, kitti_case, imu_type):
+    """scan2MapOptimization() as one call (:1295-1321): guards, kd-tree build, the loop with the reference's convergence break, transformUpdate (9-axis
+    roll / pitch slerp for imuType 1, clamps) — the final transformTobeMapped equals oracle scan2map (early exit) + oracle transform_update."""
+    o = refnodes
+    ds, mp = _map_and_scan(o, kitti_case)
+    rpy = np.array([0.004, -0.003, 0.1], np.float32)
+    R = o.RefMapOpt(imuType=imu_type, imuRPYWeight=0.05, rotation_tollerance=0.5, z_tollerance=20.0)
+    R.set_scan_and_map(ds, mp)
+    got = R.scan2map(kitti_case["init"], imu_available=1, rpy_init=rpy)
+    res = o.scan2map(ds, mp, kitti_case["init"], 30, False, use_ref_kdtree=True)
+    assert 2 <= res["iters"] < 30
+    want = o.transform_update(res["tf"], 1, imu_type, float(rpy[0]), float(rpy[1]), 0.05, 0.5, 20.0)
+    assert np.array_equal(_bits(got), _bits(want))
+    # the guard of :1300: 30 points or fewer → nothing runs, the pose is untouched
+    R.set_scan_and_map(ds[:30], mp)
+    assert np.array_equal(_bits(R.scan2map(kitti_case["init"])), _bits(kitti_case["init"]))
+    R.close()
+
+
+def _host(lib):
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def extract_nearby(poses, times, t_cur, radius, density):
+        P = np.ascontiguousarray(np.array(poses, np.float32)); T = np.ascontiguousarray(np.array(times, np.float64))
+        ids = np.zeros(4096, np.int32); n = C.c_int(0)
+        assert lib.liorf_host_extract_nearby(vp(P), vp(T), len(P), C.c_double(t_cur), C.c_float(radius), C.c_float(density), vp(ids), 4096, C.byref(n)) == 0
+        return ids[:n.value].copy()
+
+    def save_frame(last, cur, d, a):
+        last = None if last is None else np.ascontiguousarray(last, np.float32)
+        return lib.liorf_host_save_frame(None if last is None else vp(last), vp(cur), C.c_float(d), C.c_float(a)) == 1
+    return vp, extract_nearby, save_frame
+
+
+@pytest.mark.parametrize("imu_type,heading", [(0, 0), (1, 1)])
+def test_sequence_through_the_reference_node(refnodes, imu_type, heading):
+    """A 40-frame drive, one liorf::cloud_info per scan through the reference's laserCloudInfoHandler, against the same frames through the oracle's kernels
+    glued by the LIBRARY's host logic (liorf_host_update_initial_guess / extract_nearby / transform_update / save_frame — host-only entries of the C ABI,
+    no GPU): after every frame the pose is bit-equal, so are the keyframe decisions and both cloud sizes; at the end every stored keyframe cloud and pose,
+    the last local map and the ScanContext loop answer are equal.  Odometry and IMU availability toggle along the way (all three branches of
+    updateInitialGuess); the (1, 1) variant is a 9-axis IMU with heading initialisation (the slerp of transformUpdate)."""
+    import liorf_b200
+    from liorf_b200 import GuessState, CloudInfoGuess
+    from bench_common import Sequence
+    o = refnodes
+    lib = liorf_b200.load_library()
+    vp, extract_nearby, save_frame = _host(lib)
+    N = 40
+    seq = Sequence(N)
+    R = o.RefMapOpt(imuType=imu_type, useImuHeadingInitialization=heading, imuRPYWeight=0.02)
+    st = GuessState(); tf = np.zeros(6, np.float32); lm = np.zeros(37, np.float32)
+    kf_clouds, kf_poses, kf_times = [], [], []
+    sc = o.SCManager()
+    rng = np.random.default_rng(5)
+    mp = None
+    for i in range(N):
+        raw, (t0, it, rot, ptr) = seq.frame(i)
+        cloud, _ = o.project_point_cloud(raw, seq.filters, t0, it, rot, ptr, True)
+        odo = (seq.poses[i] + np.concatenate([rng.normal(scale=np.deg2rad(0.1), size=3), rng.normal(scale=0.02, size=3)])).astype(np.float32)
+        rpy = (seq.poses[i][:3] + rng.normal(scale=1e-3, size=3)).astype(np.float32)
+        guess = np.array([odo[3], odo[4], odo[5], odo[0], odo[1], odo[2]], np.float32)
+        imu_av, odo_av = int(i % 7 != 6), int(i % 5 != 4 and i % 11 != 3)
+        R.cloud_info(t0, cloud, imu_av, odo_av, rpy, guess)
+        rs = R.state()
+        ci = CloudInfoGuess(imu_av, odo_av, *[float(v) for v in rpy], *[float(v) for v in guess])
+        assert lib.liorf_host_update_initial_guess(C.byref(st), int(not kf_clouds), C.byref(ci), heading, imu_type, vp(tf)) == 0
+        m_ds = 0
+        if kf_clouds:
+            ids = extract_nearby(kf_poses, kf_times, t0, 50.0, 2.0)
+            mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(kf_clouds[k], kf_poses[k]) for k in ids]), 0.5); m_ds = len(mp)
+        ds, _, _ = o.voxel_grid(cloud, 0.4)
+        if kf_clouds and len(ds) > 30:
+            r = o.scan2map(ds, mp, tf, 30, False, lm, use_ref_kdtree=True)
+            tf, lm = r["tf"], r["state"]
+            lib.liorf_host_transform_update(vp(tf), imu_av, imu_type, C.c_float(rpy[0]), C.c_float(rpy[1]), C.c_float(0.02), C.c_float(1000.0), C.c_float(1000.0))
+        if save_frame(kf_poses[-1] if kf_poses else None, tf, 1.0, 0.2):
+            kf_clouds.append(ds); kf_poses.append(tf.copy()); kf_times.append(t0)
+            sc.make_and_save(cloud)
+        assert np.array_equal(_bits(tf), _bits(rs["tf"])), (i, tf, rs["tf"])
+        assert rs["keyframes"] == len(kf_clouds) and rs["n_ds"] == len(ds) and rs["m_ds"] == m_ds and rs["sc_entries"] == len(kf_clouds), i
+    assert 15 <= len(kf_clouds) < N
+    for k in range(len(kf_clouds)):
+        assert np.array_equal(_bits(R.get_cloud(100 + k)), _bits(kf_clouds[k]))
+        p, t = R.keypose(k)
+        assert np.array_equal(_bits(p), _bits(kf_poses[k])) and t == kf_times[k]
+    assert np.array_equal(_bits(R.get_cloud(1)), _bits(mp))                        # laserCloudSurfFromMapDS of the last frame that built one
+    for _ in range(3):                                                              # detectLoopClosureID of the node's SCManager (incl. the call counter)
+        lid, yaw = R.sc_detect()
+        olid, oyaw, _, _ = sc.detect()
+        assert lid == olid and np.float32(yaw) == np.float32(oyaw)
+    R.close()
+
+
+def test_map_cache_is_result_neutral_in_the_reference(refnodes, kitti_case):
+    """laserCloudMapContainer (:1022-1032) only memoises transformPointCloud: a node that saw the keyframes one by one (cache warm) and the oracle's
+    from-scratch map build agree on the local map — the property the library's resident-map reuse relies on."""
+    o = refnodes
+    R = o.RefMapOpt()
+    kfs = kitti_case["keyframes"]
+    t = 100.0
+    for cl, p in kfs:                                   # each keyframe enters through the handler: first frame = keyframe at its guess, later ones are solved
+        R.cloud_info(t, cl, 0, 0, None, None)
+        t += 0.1
+    s = R.state()
+    assert s["keyframes"] >= 1 and s["m_ds"] > 0
+    poses = [R.keypose(k)[0] for k in range(s["keyframes"])]
+    times = [R.keypose(k)[1] for k in range(s["keyframes"])]
+    clouds = [R.get_cloud(100 + k) for k in range(s["keyframes"])]
+    # rebuild the last frame's map from scratch with the oracle from what was stored BEFORE that frame added its own keyframe (if it did)
+    import liorf_b200
+    vp, extract_nearby, _ = _host(liorf_b200.load_library())
+    t_last = t - 0.1
+    n_before = s["keyframes"] - (1 if times[-1] == t_last else 0)
+    ids = extract_nearby(poses[:n_before], times[:n_before], t_last, 50.0, 2.0)
+    mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(clouds[k], poses[k]) for k in ids]), 0.5)
+    assert np.array_equal(_bits(R.get_cloud(1)), _bits(mp))
+    R.close()
+
+
+# ------------------------------------------------------------------------------------------------------------ ImageProjection
+def _imu_stream(rng, t0, t1, rate, omega):
+    n = int((t1 - t0) * rate) + 1
+    t = np.sort(t0 + np.arange(n) / rate + rng.uniform(-0.2 / rate, 0.2 / rate, n))
+    return t, rng.normal(0, 0.3, (n, 3)) + np.asarray(omega)
+
+
+@pytest.mark.parametrize("cfg", ["kitti", "livox"])
+def test_image_projection_node_vs_oracle(refnodes, synth, cfg):
+    """IMU samples through imuHandler, scans through cloudHandler, the published liorf/cloud_info read back: the deskewed cloud equals the oracle's
+    imu_deskew_info + project_point_cloud bit for bit (range / ring / raw-index filters, first-kept-point reference, findRotation's fp64 interpolation), the
+    node answers two scans late (:209-215), the IMU table of the library's host entry equals the oracle's.  KITTI filters (1/2 rings, every 5th point,
+    100 Hz) and the Livox configuration (6 lines, every 3rd point, 200 Hz)."""
+    import liorf_b200
+    o = refnodes
+    rng = np.random.default_rng(11)
+    if cfg == "kitti":
+        filt = dict(lidarMinRange=1.0, lidarMaxRange=1000.0, N_SCAN=64, downsampleRate=2, point_filter_num=5); sensor, rate = synth.HDL64, 100.0
+    else:
+        filt = dict(lidarMinRange=1.0, lidarMaxRange=1000.0, N_SCAN=6, downsampleRate=1, point_filter_num=3); sensor, rate = synth.LIVOX, 200.0
+    omega = (0.02, -0.03, 0.8)
+    R = o.RefImageProjection(imuRate=rate, **{k: filt[k] for k in ("N_SCAN", "downsampleRate", "point_filter_num", "lidarMinRange", "lidarMaxRange")})
+    stamps, gyro = _imu_stream(rng, 999.5, 1001.5, rate, omega)
+    for s, g in zip(stamps, gyro):
+        R.imu(s, g)
+    scans = [(1000.0 + 0.1 * k + 0.0037, synth.scan(sensor, np.array([0, 0, 0, 2.0 * k, 0, 0], np.float64), omega=omega, seed=77 + k)) for k in range(6)]
+    published = 0
+    for k, (cur, raw) in enumerate(scans):
+        n = R.cloud(cur, raw)
+        assert n == max(0, k - 1)                                                   # two scans are held back
+        if n > published:
+            published = n
+            c0, r0 = scans[k - 2]
+            info = R.last_info()
+            end = c0 + float(r0["time"][-1])                                        # timeScanEnd: the LAST point's time (:283)
+            od = o.imu_deskew_info(stamps, gyro, c0, end)
+            g = liorf_b200.imuDeskewInfo(stamps, gyro, c0, end)
+            assert info["stamp"] == c0 and info["imuAvailable"] == 1 and od["available"] and g["available"]
+            assert g["imu_pointer_cur"] == od["imu_pointer_cur"] and np.array_equal(g["imu_rot"], od["imu_rot"]) and np.array_equal(g["imu_time"], od["imu_time"])
+            cloud, kept = o.project_point_cloud(r0, filt, c0, od["imu_time"], od["imu_rot"], od["imu_pointer_cur"], True)
+            assert len(cloud) > 1000 and info["cloud"].shape == cloud.shape
+            assert np.array_equal(_bits(info["cloud"]), _bits(cloud))
+            assert np.abs(cloud[:, :3] - synth.raw_to_xyzi(r0)[kept][:, :3]).max() > 1e-3          # the deskew did move points
+    assert published == 4
+    R.close()
+
+
+def test_image_projection_gates_vs_oracle(refnodes, synth):
+    """no "time" field → deskewFlag = -1 → points pass through unrotated (:313-326, :538); IMU stream that does not cover the scan → deskewInfo returns false and
+    nothing is published (:336-340) — the gate the library's liorf_host_imu_deskew_info(check_gate = 1) reports as "not available"."""
+    import liorf_b200
+    o = refnodes
+    rng = np.random.default_rng(12)
+    filt = dict(lidarMinRange=1.0, lidarMaxRange=1000.0, N_SCAN=64, downsampleRate=2, point_filter_num=5)
+    stamps, gyro = _imu_stream(rng, 999.5, 1001.0, 100.0, (0, 0, 0.5))
+    raws = [synth.scan(synth.HDL64, np.array([0, 0, 0, 1.0 * k, 0, 0], np.float64), omega=(0, 0, 0.5), seed=5 + k) for k in range(3)]
+    R = o.RefImageProjection()
+    for s, g in zip(stamps, gyro):
+        R.imu(s, g)
+    for k in range(3):
+        n = R.cloud(1000.0 + 0.1 * k, raws[k], has_time=False)
+    assert n == 1
+    info = R.last_info()
+    cloud, kept = o.project_point_cloud(raws[0], filt, 1000.0, np.zeros(1), np.zeros((1, 3)), 0, False)
+    assert np.array_equal(_bits(info["cloud"]), _bits(cloud)) and np.array_equal(_bits(cloud), _bits(synth.raw_to_xyzi(raws[0])[kept]))
+    R.close()
+    R = o.RefImageProjection()
+    late = stamps[stamps > 1000.05]                                                 # the first IMU sample is younger than the scan start
+    for s, g in zip(late, gyro[stamps > 1000.05]):
+        R.imu(s, g)
+    for k in range(3):
+        n = R.cloud(1000.0 + 0.1 * k, raws[k])
+    assert n == 0 and R.last_info() is None
+    end = 1000.0 + float(raws[0]["time"][-1])
+    assert not liorf_b200.imuDeskewInfo(late, gyro[stamps > 1000.05], 1000.0, end, check_gate=True)["available"]
+    R.close()
