@@ -454,6 +454,25 @@ class RefMapOpt:
         self.l.refmo_sc_detect(self.h, C.byref(lid), C.byref(yaw))
         return lid.value, yaw.value
 
+    def add_keyframe(self, cloud, pose6, t):
+        """harness set-up: stores a keyframe the way saveKeyFramesAndFactor does (:1548-1580)"""
+        cloud = _as_p4(cloud); p = np.ascontiguousarray(pose6, np.float32)
+        self.l.refmo_add_keyframe(self.h, _fp(cloud), C.c_int(len(cloud)), _fp(p), C.c_double(t))
+
+    def _cloud_call(self, fn, *args):
+        n = fn(self.h, *args, None, C.c_int(0))
+        if n < 0:
+            return None
+        out = np.zeros((max(n, 1), 4), np.float32)
+        fn(self.h, *args, _fp(out), C.c_int(n))
+        return out[:n].copy()
+
+    def loop_find_near_keyframes(self, key, search_num, loop_index):
+        return self._cloud_call(self.l.refmo_loop_find_near_keyframes, C.c_int(key), C.c_int(search_num), C.c_int(loop_index))
+
+    def publish_global_map(self):
+        return self._cloud_call(self.l.refmo_publish_global_map)
+
 
 class RefImageProjection:
     """The reference's OWN ImageProjection node (src/imageProjection.cpp compiled unchanged against oracle/shim_ros into

@@ -130,6 +130,40 @@ int refmo_get_lm_state(void* h, float* matP36) {
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) matP36[i * 6 + j] = mo->matP.at<float>(i, j);
     return mo->isDegenerate ? 1 : 0;
 }
+// ---- the rows next to the path ----
+// harness set-up: appends a keyframe exactly as saveKeyFramesAndFactor stores one (:1548-1580: cloudKeyPoses3D / 6D with intensity = index, surfCloudKeyFrames)
+void refmo_add_keyframe(void* h, const float* xyzi, int n, const float* pose6, double time) {
+    mapOptimization* mo = (mapOptimization*)h;
+    PointType p3; PointTypePose p6;
+    p3.x = pose6[3]; p3.y = pose6[4]; p3.z = pose6[5]; p3.intensity = mo->cloudKeyPoses3D->size();
+    p6.x = p3.x; p6.y = p3.y; p6.z = p3.z; p6.intensity = p3.intensity; p6.roll = pose6[0]; p6.pitch = pose6[1]; p6.yaw = pose6[2]; p6.time = time;
+    mo->cloudKeyPoses3D->push_back(p3); mo->cloudKeyPoses6D->push_back(p6);
+    pcl::PointCloud<PointType>::Ptr c(new pcl::PointCloud<PointType>()); fill_cloud(xyzi, n, *c);
+    mo->surfCloudKeyFrames.push_back(c);
+    mo->timeLaserInfoCur = time;
+}
+// loopFindNearKeyframes (:821-844) on a snapshot of the key poses taken the way performSCLoopClosure takes it (:629-632); returns the size
+int refmo_loop_find_near_keyframes(void* h, int key, int search_num, int loop_index, float* out, int cap) {
+    mapOptimization* mo = (mapOptimization*)h;
+    *mo->copy_cloudKeyPoses3D = *mo->cloudKeyPoses3D;
+    *mo->copy_cloudKeyPoses6D = *mo->cloudKeyPoses6D;
+    pcl::PointCloud<PointType>::Ptr c(new pcl::PointCloud<PointType>());
+    mo->loopFindNearKeyframes(c, key, search_num, loop_index);
+    return copy_cloud(*c, out, cap);
+}
+// publishGlobalMap (:453-502) with one subscriber on liorf/mapping/map_global: the published cloud; returns its size (-1: nothing was published)
+int refmo_publish_global_map(void* h, float* out, int cap) {
+    mapOptimization* mo = (mapOptimization*)h;
+    const std::string topic = "liorf/mapping/map_global";
+    ros::shim::subscribers()[topic] = 1;
+    const long before = ros::shim::outcount<sensor_msgs::PointCloud2>()[topic];
+    mo->publishGlobalMap();
+    ros::shim::subscribers()[topic] = 0;
+    if (ros::shim::outcount<sensor_msgs::PointCloud2>()[topic] == before) return -1;
+    pcl::PointCloud<PointType> c; pcl::fromROSMsg(ros::shim::outbox<sensor_msgs::PointCloud2>()[topic], c);
+    return copy_cloud(c, out, cap);
+}
+
 // detectLoopClosureID of the node's SCManager (performSCLoopClosure :636)
 void refmo_sc_detect(void* h, int* loop_id, float* yaw) { auto r = ((mapOptimization*)h)->scManager.detectLoopClosureID(); *loop_id = r.first; *yaw = r.second; }
 

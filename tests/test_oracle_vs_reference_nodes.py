@@ -284,3 +284,80 @@ def test_image_projection_gates_vs_oracle(refnodes, synth):
     end = 1000.0 + float(raws[0]["time"][-1])
     assert not liorf_b200.imuDeskewInfo(late, gyro[stamps > 1000.05], 1000.0, end, check_gate=True)["available"]
     R.close()
+
+
+# ------------------------------------------------------------------------------------------------------------ §8f-3 / §8f-4 next to the path
+def _keyframe_set(oracle, synth, n, spacing):
+    kfs = []
+    for k in range(n):
+        p = np.array([0.002 * k, -0.001 * k, 0.01 * k, spacing * k, 0.3 * np.sin(k), 0.02 * k], np.float32)
+        cl, _, _ = oracle.voxel_grid(synth.raw_to_xyzi(synth.scan(synth.HDL64, p.astype(np.float64), seed=900 + k)), 0.4)
+        kfs.append((cl, p))
+    return kfs
+
+
+def test_loop_find_near_keyframes_vs_reference(refnodes, synth):
+    """the sub-map assembly of the loop-closure ICP (loopFindNearKeyframes :821-844, as performSCLoopClosure calls it with base_key = 0 and as
+    performRSLoopClosure does with -1): oracle/pyicp.py's restatement — what tests/test_gpu_icp.py checks the library against — equals the reference's own."""
+    import pyicp
+    o = refnodes
+    kfs = _keyframe_set(o, synth, 9, 1.5)
+    R = o.RefMapOpt(loopClosureICPSurfLeafSize=0.3)
+    for k, (cl, p) in enumerate(kfs):
+        R.add_keyframe(cl, p, 10.0 + 0.5 * k)
+    clouds = [c for c, _ in kfs]; poses = [p for _, p in kfs]
+    for key, num, base in ((8, 0, 0), (3, 25, 0), (3, 2, -1), (0, 1, -1), (8, 3, 0)):
+        want = pyicp.loop_find_near_keyframes(clouds, poses, key, num, base, 0.3, o)
+        got = R.loop_find_near_keyframes(key, num, base)
+        assert len(want) > 1000 and got.shape == want.shape and np.array_equal(_bits(got), _bits(want)), (key, num, base)
+    R.close()
+
+
+def test_publish_global_map_vs_reference(refnodes, synth):
+    """publishGlobalMap (:453-502): radius search around the newest key pose, pose thinning by a VoxelGrid, nearest-1 id recovery, the distance gate on
+    the voxel centroid, transform + concatenate + VoxelGrid — the numpy restatement tests/test_gpu_configs.py::test_global_map_filters holds the library
+    to, here against the reference's own function (one subscriber on liorf/mapping/map_global)."""
+    o = refnodes
+    kfs = _keyframe_set(o, synth, 14, 6.0)
+    R = o.RefMapOpt(globalMapVisualizationSearchRadius=40.0, globalMapVisualizationPoseDensity=10.0, globalMapVisualizationLeafSize=1.0)
+    assert R.publish_global_map() is None                                          # no key poses yet: early return (:458)
+    for k, (cl, p) in enumerate(kfs):
+        R.add_keyframe(cl, p, 10.0 + 0.5 * k)
+    P = np.array([p for _, p in kfs], np.float32)[:, 3:6]
+    d = ((P[-1] - P) ** 2).astype(np.float32).sum(1)
+    near = [i for i in np.lexsort((np.arange(len(P)), d)) if d[i] < 40.0 ** 2]
+    cent, _, _ = o.voxel_grid(np.concatenate([P[near], np.zeros((len(near), 1), np.float32)], 1), 10.0)
+    ids = [int(np.argmin(((cc[:3] - P) ** 2).sum(1))) for cc in cent if not np.sqrt(((cc[:3] - P[-1]) ** 2).sum()) > 40.0]
+    assert 2 <= len(ids) < len(near)
+    want = o.voxel_grid(np.concatenate([o.transform_cloud(kfs[i][0], kfs[i][1]) for i in ids]), 1.0)[0]
+    got = R.publish_global_map()
+    assert got.shape == want.shape and np.array_equal(_bits(got), _bits(want))
+    R.close()
+
+
+def test_headline_config_full_scale_vs_reference_and_committed_gpu_pose(refnodes):
+    """BASELINE config 1 at full size (50 full-density keyframes, N_ds = 13 364, M = 56 460, 30 forced iterations): the reference's own member functions
+    and the oracle agree on every iteration bit for bit — and the final pose is, bit for bit, the `final_pose` the B200 run of bench.py committed under
+    profiles/ for the same input bytes (sha256 in both lines).  GPU == oracle == the reference's code, on the configuration the < 1 ms target is quoted on."""
+    import json
+    import os
+    import bench
+    o = refnodes
+    inst = bench.make_single_inputs("kitti64_single")
+    kfs = [o.voxel_grid(s, 0.4)[0] for s in inst["scans"]]
+    mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(c, p.astype(np.float32)) for c, p in zip(kfs, inst["poses"])]), 0.5)
+    ds, _, _ = o.voxel_grid(inst["scan"], 0.4)
+    assert (len(ds), len(mp)) == (13364, 56460)
+    res = o.scan2map(ds, mp, inst["init"], 30, True, use_ref_kdtree=True)
+    R = o.RefMapOpt()
+    R.set_scan_and_map(ds, mp)
+    R.set_transform(inst["init"])
+    for it in range(30):
+        conv, tf, nsel = R.iteration(it)
+        assert np.array_equal(_bits(tf), _bits(res["trace"][it])) and nsel == res["nsel"][it], it
+    R.close()
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_bench_n1.json")
+    if os.path.exists(path):
+        line = [json.loads(l) for l in open(path) if l.strip().startswith("{")][-1]
+        if line["config"].get("input_sha256") == inst["sha256"]:
+            assert np.array_equal(_bits(np.array(line["final_pose"], np.float32)), _bits(tf))
