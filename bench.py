@@ -705,6 +705,49 @@ def bench_single_headline(args, device, W, K, peaks, peak_src):
     return 0
 
 
+REF_NODE_SAMPLE = ("the reference's own src/mapOptmization.cpp compiled unchanged with its build flags (-O3, OpenMP; oracle/_ref/libliorf_ref_mapopt_omp.so): "
+                   "downsampleCurrentScan + kd-tree setInputCloud + 30 x {surfOptimization, combineOptimizationCoeffs, LMOptimization}; behind its PCL / Eigen / OpenCV "
+                   "calls stand the oracle's restatements, the kd-tree is the reference's vendored nanoflann")
+
+
+class CpuStep:
+    """one headline step on the host cores: the reference's own member functions when oracle/_ref holds the compiled node (kind "reference"), else the
+    oracle port (kind "port").  step() -> (final pose, {downsample, kdtree_build, surf_optimization, lm_optimization} in ms)"""
+
+    def __init__(self, o, name, mp, threads):
+        self.o, self.mp, self.threads = o, mp, threads
+        _, n_scan, self.ls, _ = SINGLE_CFGS[name]
+        self.node = None
+        if o.RefMapOpt.available() and os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libliorf_ref_mapopt_omp.so")):
+            self.node = o.RefMapOpt(openmp=True, numberOfCores=threads, mappingSurfLeafSize=self.ls, N_SCAN=n_scan)
+            self.node.set_map(mp)
+        else:
+            o.set_num_threads(threads)
+        self.use_ref = o.ref() is not None
+        self.kind = "reference" if self.node is not None else "port"
+
+    def step(self, scan, init):
+        if self.node is not None:
+            pose, _, tm = self.node.bench_step(scan, init, 30, True)
+            return pose, tm, self.node.state()["n_ds"]
+        a = time.perf_counter()
+        ds, _, _ = self.o.voxel_grid(scan, self.ls)
+        b = time.perf_counter()
+        res = self.o.scan2map(ds, self.mp, init, 30, True, None, use_ref_kdtree=self.use_ref)
+        t = res.get("timings", (0.0, 0.0, 0.0))
+        return res["tf"], dict(downsample=(b - a) * 1e3, kdtree_build=t[0] * 1e3, surf_optimization=t[1] * 1e3, lm_optimization=t[2] * 1e3), len(ds)
+
+    def close(self):
+        if self.node is not None:
+            self.node.close()
+
+    def sample(self, name, reps, warm):
+        if self.node is not None:
+            return "%d repetitions of the same %s step (after %d warm-up): %s; OpenMP %d threads (numberOfCores)" % (reps, name, warm, REF_NODE_SAMPLE, self.threads)
+        return "%d repetitions of the same %s step (after %d warm-up): oracle restatement, kd-tree = the reference's vendored nanoflann%s; OpenMP %d threads" % (
+            reps, name, warm, "" if self.use_ref else " (oracle/_ref missing: brute-force kNN)", self.threads)
+
+
 def cpu_single(inst, name, reps, sf=None, check_pose=None):
     """the CPU path on the same step: VoxelGrid of the scan + kd-tree build (the reference's vendored nanoflann, leaf 15) + 30 forced
     iterations with OpenMP over the points (src/mapOptmization.cpp:1078), all host threads and 4 threads (numberOfCores, config/kitti.yaml:63)"""
@@ -717,31 +760,29 @@ def cpu_single(inst, name, reps, sf=None, check_pose=None):
     else:
         kfs = [o.voxel_grid(s, ls)[0] for s in inst["scans"]]
     mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(c, p.astype(np.float32)) for c, p in zip(kfs, inst["poses"])]), lm)
-    use_ref = o.ref() is not None
     out = {}
     all_cores = os.cpu_count() or 1
     pose = None
+    kind, sample, n_ds = "port", "", 0
     for threads in sorted({all_cores, min(4, all_cores)}, reverse=True):
-        o.set_num_threads(threads)
-        ts, split = [], np.zeros(4)
+        cs = CpuStep(o, name, mp, threads)
+        ts, split = [], {}
         for r in range(reps + 1):
             a = time.perf_counter()
-            ds, _, _ = o.voxel_grid(inst["scan"], ls)
-            b = time.perf_counter()
-            res = o.scan2map(ds, mp, inst["init"], 30, True, None, use_ref_kdtree=use_ref)
+            pose, tm, n_ds = cs.step(inst["scan"], inst["init"])
             c = time.perf_counter()
             if r > 0:
                 ts.append((c - a) * 1e3)
-                if use_ref:
-                    split += np.array([b - a, res["timings"][0], res["timings"][1], res["timings"][2]]) * 1e3
-        pose = res["tf"]
-        out[threads] = dict(ms=stats_ms(ts), split_ms=dict(downsample=split[0] / reps, kdtree_build=split[1] / reps, surf_optimization=split[2] / reps, lm_optimization=split[3] / reps))
+                for k, v in tm.items():
+                    split[k] = split.get(k, 0.0) + v / reps
+        out[threads] = dict(ms=stats_ms(ts), split_ms=split)
+        if threads == all_cores:
+            kind, sample = cs.kind, cs.sample(name, reps, 1)
+        cs.close()
     o.set_num_threads(all_cores)
     best = out[all_cores]
-    d = dict(value=best["ms"]["median"], unit="ms/frame", cores=all_cores, kind="port",
-             sample="%d repetitions of the same %s step (after 1 warm-up): oracle restatement, kd-tree = the reference's vendored nanoflann%s; OpenMP %d threads"
-                    % (reps, name, "" if use_ref else " (oracle/_ref missing: brute-force kNN)", all_cores),
-             ms=best["ms"], split_ms=best["split_ms"], n_ds=len(ds), m_map=len(mp))
+    d = dict(value=best["ms"]["median"], unit="ms/frame", cores=all_cores, kind=kind, sample=sample,
+             ms=best["ms"], split_ms=best["split_ms"], n_ds=int(n_ds), m_map=len(mp))
     if 4 in out and all_cores != 4:
         d["threads_4"] = out[4]
     if check_pose is not None and pose is not None:
@@ -829,36 +870,34 @@ def run_reference(args, W, K, world):
     _, _, ls, lm = SINGLE_CFGS[name]
     kfs = [o.voxel_grid(s, ls)[0] for s in inst["scans"]]
     mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(c, p.astype(np.float32)) for c, p in zip(kfs, inst["poses"])]), lm)
-    use_ref = o.ref() is not None
     flush = np.zeros(256 * 1024 * 1024 // 8)
     results = {}
+    kind, sample, pose, n_ds = "port", "", None, 0
     for threads in sorted({all_cores, min(4, all_cores)}, reverse=True):
-        o.set_num_threads(threads)
+        cs = CpuStep(o, name, mp, threads)
         steps = K if threads == all_cores else min(K, 10)
-        ts, split = [], np.zeros(4)
+        ts, split = [], {}
         for i in range(W + steps):
             flush += 1.0                                            # stream 256 MB through the caches between steps
             a = time.perf_counter()
-            ds, _, _ = o.voxel_grid(inst["scan"], ls)
-            b = time.perf_counter()
-            res = o.scan2map(ds, mp, inst["init"], 30, True, None, use_ref_kdtree=use_ref)
+            pose, tm, n_ds = cs.step(inst["scan"], inst["init"])
             c = time.perf_counter()
             if i >= W:
                 ts.append((c - a) * 1e3)
-                if use_ref:
-                    split += np.array([b - a, res["timings"][0], res["timings"][1], res["timings"][2]]) * 1e3
-        results[threads] = dict(ms=stats_ms(ts), steps=steps, split_ms=dict(downsample=split[0] / steps, kdtree_build=split[1] / steps, surf_optimization=split[2] / steps,
-                                                                           lm_optimization=split[3] / steps))
+                for k, v in tm.items():
+                    split[k] = split.get(k, 0.0) + v / steps
+        results[threads] = dict(ms=stats_ms(ts), steps=steps, split_ms=split)
+        if threads == all_cores:
+            kind, sample = cs.kind, cs.sample(name, steps, W)
+        cs.close()
     o.set_num_threads(all_cores)
     best = results[all_cores]
     v = best["ms"]["mean"]
     line = dict(impl="reference", metric="scan2map_ms_per_frame_64beam", value=v, unit="ms/frame", n_gpus=args.gpus, steps=K, warmup=W, ms_per_step=v,
-                higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=single_config(name, inst, len(ds), len(mp)),
-                cpu_baseline=dict(value=v, unit="ms/frame", cores=all_cores, kind="port",
-                                  sample="%d steps after %d warm-ups, all %d host threads: oracle restatement of downsampleCurrentScan + scan2MapOptimization, kd-tree = the reference's vendored nanoflann%s"
-                                         % (K, W, all_cores, "" if use_ref else " (oracle/_ref missing: brute-force kNN)"),
+                higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=single_config(name, inst, n_ds, len(mp)),
+                cpu_baseline=dict(value=v, unit="ms/frame", cores=all_cores, kind=kind, sample=sample,
                                   ms=best["ms"], split_ms=best["split_ms"], threads_4=results.get(4) if all_cores != 4 else None),
-                e2e=dict(value=v, unit="ms/frame", h2d_bytes_per_step=0, d2h_bytes_per_step=0), final_pose=[float(x) for x in res["tf"]])
+                e2e=dict(value=v, unit="ms/frame", h2d_bytes_per_step=0, d2h_bytes_per_step=0), final_pose=[float(x) for x in pose])
     print(json.dumps(line))
     return 0
 

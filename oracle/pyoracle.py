@@ -353,11 +353,13 @@ class RefMapOpt:
         build()
         return os.path.exists(os.path.join(HERE, "_ref", "libliorf_ref_mapopt.so"))
 
-    def __init__(self, **params):
+    def __init__(self, openmp=False, **params):
+        """openmp=True loads the build with the reference's own flags (-O3, OpenMP: bench.py's CPU arm; surfOptimization then writes its std::vector<bool>
+        flags from several threads as the reference does, :1078,1137); the default build has no OpenMP (tests: deterministic)."""
         import shutil
         import tempfile
         build()
-        src = os.path.join(HERE, "_ref", "libliorf_ref_mapopt.so")
+        src = os.path.join(HERE, "_ref", "libliorf_ref_mapopt_omp.so" if openmp else "libliorf_ref_mapopt.so")
         fd, self._path = tempfile.mkstemp(suffix=".so", prefix="liorf_ref_mapopt_")
         os.close(fd)
         shutil.copyfile(src, self._path)
@@ -453,6 +455,17 @@ class RefMapOpt:
         lid = C.c_int(); yaw = C.c_float()
         self.l.refmo_sc_detect(self.h, C.byref(lid), C.byref(yaw))
         return lid.value, yaw.value
+
+    def set_map(self, map_ds):
+        b = _as_p4(map_ds)
+        self.l.refmo_set_map(self.h, _fp(b), C.c_int(len(b)))
+
+    def bench_step(self, scan, tf6, iters=30, force_all=True):
+        """one headline step on the reference's own member functions: downsampleCurrentScan + kd-tree build + `iters` passes of scan2MapOptimization's
+        loop body.  Returns (final pose, iterations run, {downsample, kdtree_build, surf_optimization, lm_optimization} in ms)."""
+        a = _as_p4(scan); tf = np.ascontiguousarray(tf6, np.float32); out = np.zeros(6, np.float32); tm = np.zeros(4, np.float64)
+        it = self.l.refmo_bench_step(self.h, _fp(a), C.c_int(len(a)), _fp(tf), C.c_int(iters), C.c_int(int(force_all)), _fp(out), _fp(tm))
+        return out, int(it), dict(downsample=float(tm[0]), kdtree_build=float(tm[1]), surf_optimization=float(tm[2]), lm_optimization=float(tm[3]))
 
     def add_keyframe(self, cloud, pose6, t):
         """harness set-up: stores a keyframe the way saveKeyFramesAndFactor does (:1548-1580)"""

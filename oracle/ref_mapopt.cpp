@@ -14,6 +14,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <chrono>
 #define main liorf_ref_mapopt_main_unused
 #include "mapOptmization.cpp"
 #undef main
@@ -130,6 +131,47 @@ int refmo_get_lm_state(void* h, float* matP36) {
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) matP36[i * 6 + j] = mo->matP.at<float>(i, j);
     return mo->isDegenerate ? 1 : 0;
 }
+// ---- bench.py --impl reference / cpu_baseline: one headline step timed on the reference's own member functions ----
+// laserCloudSurfLast = scan (filled before the clock starts, like the GPU arm's resident scan), then downsampleCurrentScan() (:1061-1067), the kd-tree
+// build of scan2MapOptimization (:1302) and `iters` passes of its loop body (:1306-1314) — the convergence break is left out when force_all != 0, as the
+// headline configuration asks on both sides.  timings_ms = {downsample, kd-tree build, surfOptimization + combine, LMOptimization}.  Returns the iterations run.
+int refmo_bench_step(void* h, const float* scan_xyzi, int n, const float* tf6_init, int iters, int force_all, float* tf6_out, double* timings_ms) {
+    mapOptimization* mo = (mapOptimization*)h;
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fill_cloud(scan_xyzi, n, *mo->laserCloudSurfLast);
+    std::memcpy(mo->transformTobeMapped, tf6_init, 6 * sizeof(float));
+    std::fill(mo->laserCloudOriSurfFlag.begin(), mo->laserCloudOriSurfFlag.end(), false);
+    auto t0 = clk::now();
+    mo->downsampleCurrentScan();
+    auto t1 = clk::now();
+    if ((int)mo->laserCloudOriSurfVec.size() < mo->laserCloudSurfLastDSNum) {
+        mo->laserCloudOriSurfVec.resize(mo->laserCloudSurfLastDSNum); mo->coeffSelSurfVec.resize(mo->laserCloudSurfLastDSNum); mo->laserCloudOriSurfFlag.assign(mo->laserCloudSurfLastDSNum, false);
+    }
+    mo->kdtreeSurfFromMap->setInputCloud(mo->laserCloudSurfFromMapDS);
+    auto t2 = clk::now();
+    double t_surf = 0, t_lm = 0; int it = 0;
+    for (; it < iters; ++it) {
+        auto a = clk::now();
+        mo->laserCloudOri->clear();
+        mo->coeffSel->clear();
+        mo->surfOptimization();
+        mo->combineOptimizationCoeffs();
+        auto b = clk::now();
+        const bool conv = mo->LMOptimization(it);
+        auto c = clk::now();
+        t_surf += ms(a, b); t_lm += ms(b, c);
+        if (conv && !force_all) { ++it; break; }
+    }
+    if (tf6_out) std::memcpy(tf6_out, mo->transformTobeMapped, 6 * sizeof(float));
+    if (timings_ms) { timings_ms[0] = ms(t0, t1); timings_ms[1] = ms(t1, t2); timings_ms[2] = t_surf; timings_ms[3] = t_lm; }
+    return it;
+}
+void refmo_set_map(void* h, const float* map_ds, int m) {
+    mapOptimization* mo = (mapOptimization*)h;
+    fill_cloud(map_ds, m, *mo->laserCloudSurfFromMapDS); mo->laserCloudSurfFromMapDSNum = m;
+}
+
 // ---- the rows next to the path ----
 // harness set-up: appends a keyframe exactly as saveKeyFramesAndFactor stores one (:1548-1580: cloudKeyPoses3D / 6D with intensity = index, surfCloudKeyFrames)
 void refmo_add_keyframe(void* h, const float* xyzi, int n, const float* pose6, double time) {
