@@ -361,3 +361,31 @@ def test_headline_config_full_scale_vs_reference_and_committed_gpu_pose(refnodes
         line = [json.loads(l) for l in open(path) if l.strip().startswith("{")][-1]
         if line["config"].get("input_sha256") == inst["sha256"]:
             assert np.array_equal(_bits(np.array(line["final_pose"], np.float32)), _bits(tf))
+
+
+@pytest.mark.parametrize("cfg", ["os1_128_dense", "livox_deskew"])
+def test_other_configurations_vs_reference(refnodes, synth, cfg):
+    """BASELINE configs 3 and 4 at the sizes of tests/test_gpu_configs.py (same generator, same seeds): the node configured as lio_sam_ouster.yaml with the
+    0.2 m scan leaf BASELINE asks for / as lio_sam_livox.yaml (0.15 / 0.3 m) — downsampleCurrentScan by the reference's own function, then its iterations — against
+    the oracle.  The Livox field of view is weakly constrained sideways, so this also walks the degenerate branch on real-looking data."""
+    o = refnodes
+    sensor, n_scan, scan_leaf, map_leaf, n_kf, seed0 = ((synth.OS1_128, 128, 0.2, 0.5, 8, 300) if cfg == "os1_128_dense" else (synth.LIVOX, 6, 0.15, 0.3, 10, 500))
+    kfs = []
+    for k in range(n_kf):
+        p = np.array([0, 0, 0, 1.0 * k, 0, 0], np.float64)
+        ds, _, _ = o.voxel_grid(synth.raw_to_xyzi(synth.scan(sensor, p, seed=seed0 + k)), scan_leaf)
+        kfs.append((ds, p.astype(np.float32)))
+    qp = np.array([0, 0, 0, 1.0 * (n_kf - 1), 0, 0], np.float64)
+    scan = synth.raw_to_xyzi(synth.scan(sensor, qp, seed=seed0 + 100))
+    init = (qp + np.array([np.deg2rad(0.4), np.deg2rad(-0.3), np.deg2rad(1.0), 0.25, -0.1, 0.02])).astype(np.float32)
+    mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(c, p) for c, p in kfs]), map_leaf)
+    R = o.RefMapOpt(N_SCAN=n_scan, Horizon_SCAN=1024 if cfg == "os1_128_dense" else 4000, mappingSurfLeafSize=scan_leaf, surroundingKeyframeMapLeafSize=map_leaf)
+    R.set_map(mp)
+    pose, iters, _ = R.bench_step(scan, init, 30, True)                     # downsampleCurrentScan + kd-tree + 30 forced iterations, all the reference's
+    ds, _, _ = o.voxel_grid(scan, scan_leaf)
+    assert R.state()["n_ds"] == len(ds) and np.array_equal(_bits(R.get_cloud(0)), _bits(ds))
+    res = o.scan2map(ds, mp, init, 30, True, use_ref_kdtree=True)
+    assert iters == 30 and np.array_equal(_bits(pose), _bits(res["tf"]))
+    deg, P = R.lm_state()
+    assert deg == int(res["state"][0]) and np.array_equal(_bits(P), _bits(res["state"][1:]))
+    R.close()
