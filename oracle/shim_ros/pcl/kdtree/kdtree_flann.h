@@ -1,8 +1,9 @@
 // oracle/shim_ros — TEST INFRASTRUCTURE (see ros/ros.h).  pcl::KdTreeFLANN<PointXYZI>: exact k-NN through the reference's own vendored nanoflann
-// (KDTreeSingleIndexAdaptor, L2_Simple, leaf 15 — SURVEY §8(d)'s stand-in for FLANN's KDTreeSingleIndex), results ascending by distance;
+// (KDTreeSingleIndexAdaptor, L2_Simple, leaf 15 — SURVEY §8(d)'s stand-in for FLANN's KDTreeSingleIndex), results ascending by distance (nearest-1: brute force, ties to the lower index);
 // radiusSearch = squared L2_Simple distance strictly below r^2, ascending by (distance, index).  Third-party behaviour: NOT pinned.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <pcl/point_cloud.h>
 #include "nanoflann.hpp"
 namespace pcl {
@@ -25,6 +26,17 @@ public:
         if (k > n) k = n;                                       // PCL clamps k to the cloud size
         idx.assign(k, 0); d2.assign(k, 0.f);
         if (k == 0) return 0;
+        if (k == 1) {   // nearest-1 is only asked on key poses (extractNearby :995, publishGlobalMap :485): the centroid of a two-pose voxel is often EXACTLY
+                        // equidistant from both in fp32, and which one FLANN returns is its traversal's business — the canonical rule (distance, index) decides here
+            float bd = INFINITY; int best = 0;
+            for (int i = 0; i < n; ++i) {
+                const T& p = cloud_->points[i];
+                float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z; float d = dx * dx; d += dy * dy; d += dz * dz;
+                if (d < bd) { bd = d; best = i; }
+            }
+            idx[0] = best; d2[0] = bd;
+            return 1;
+        }
         float qp[3] = {q.x, q.y, q.z};
         nanoflann::KNNResultSet<float, int> rs(k); rs.init(idx.data(), d2.data());
         tree_->findNeighbors(rs, qp, nanoflann::SearchParams());
