@@ -335,6 +335,19 @@ class RefSCManager:
         refsc().refsc_detect(self.h, C.byref(lid), C.byref(yaw))
         return lid.value, yaw.value
 
+    def query_batch(self, qdescs):
+        """every query through the reference's own detectLoopClosureID, unchanged (see refsc_query_batch_own) → (loop_id, shift)"""
+        qd = np.ascontiguousarray(qdescs, np.float64).reshape(-1, 1200)
+        loop = np.zeros(len(qd), np.int32); sh = np.zeros(len(qd), np.int32)
+        refsc().refsc_query_batch_own(self.h, _fp(qd), C.c_int(len(qd)), _fp(loop), _fp(sh))
+        return loop, sh
+
+    def save_descriptors(self, descs):
+        d = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+        f = refsc().refsc_save_descriptor
+        for k in range(len(d)):
+            f(self.h, C.c_void_p(d[k].ctypes.data))
+
     def distance(self, sc1, sc2):
         sc1 = np.ascontiguousarray(sc1, np.float64).reshape(-1); sc2 = np.ascontiguousarray(sc2, np.float64).reshape(-1)
         d = C.c_double(); s = C.c_int()

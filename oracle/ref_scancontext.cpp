@@ -6,6 +6,7 @@
 // the stale-tree schedule — up to the reduction order of mean / norm / dot, which is the shim's (sequential), not Eigen's.
 #include "Scancontext.h"
 #include <cstring>
+#include <cmath>
 
 extern "C" {
 
@@ -52,5 +53,31 @@ void refsc_distance(void* h, const double* sc1, const double* sc2, double* dist,
     auto r = ((SCManager*)h)->distanceBtnScanContext(a, b); *dist = r.first; *shift = r.second;
 }
 float refsc_xy2theta(float x, float y) { return xy2theta(x, y); }
+
+// A BATCH of queries against the stored database through the reference's own detectLoopClosureID (:253-344), unchanged, one call per query (bench.py --impl
+// reference at N > 1).  The function answers for the LAST stored entry against a tree over entries [0, size - 30) (:270-281), so the harness keeps 29 padding
+// entries behind the K database rows, appends the query the way makeAndSaveScancontextAndKeys does (:236-250), calls the function and removes the query again;
+// the tree is built by the function itself on the first call (tree_making_period_conter == 0) and kept afterwards (the counter is held off the rebuild period:
+// the database does not change between queries).  shift = yaw / 6 degrees.  Single-threaded, as the reference's loop-closure thread is.
+void refsc_query_batch_own(void* h, const double* qdescs, int Q, int* loop_id, int* shift) {
+    SCManager* s = (SCManager*)h;
+    const size_t K = s->polarcontexts_.size();
+    for (int i = 0; i < 29; ++i) {                                  // padding: never inside the tree (the last 30 entries are excluded), never a candidate
+        s->polarcontexts_.push_back(s->polarcontexts_[0]); s->polarcontext_invkeys_.push_back(s->polarcontext_invkeys_[0]);
+        s->polarcontext_vkeys_.push_back(s->polarcontext_vkeys_[0]); s->polarcontext_invkeys_mat_.push_back(s->polarcontext_invkeys_mat_[0]);
+    }
+    s->tree_making_period_conter = 0;
+    for (int q = 0; q < Q; ++q) {
+        Eigen::MatrixXd sc = from_rowmajor(qdescs + (size_t)q * 1200, 20, 60);
+        Eigen::MatrixXd ringkey = s->makeRingkeyFromScancontext(sc), sectorkey = s->makeSectorkeyFromScancontext(sc);
+        std::vector<float> vec = eig2stdvec(ringkey);
+        s->polarcontexts_.push_back(sc); s->polarcontext_invkeys_.push_back(ringkey); s->polarcontext_vkeys_.push_back(sectorkey); s->polarcontext_invkeys_mat_.push_back(vec);
+        std::pair<int, float> r = s->detectLoopClosureID();
+        if (s->tree_making_period_conter % 10 == 0) s->tree_making_period_conter = 1;
+        loop_id[q] = r.first; shift[q] = (int)std::lround((double)r.second * 180.0 / M_PI / 6.0);
+        s->polarcontexts_.pop_back(); s->polarcontext_invkeys_.pop_back(); s->polarcontext_vkeys_.pop_back(); s->polarcontext_invkeys_mat_.pop_back();
+    }
+    s->polarcontexts_.resize(K); s->polarcontext_invkeys_.resize(K); s->polarcontext_vkeys_.resize(K); s->polarcontext_invkeys_mat_.resize(K);
+}
 
 }  // extern "C"

@@ -109,3 +109,23 @@ def test_detect_loop_closure_sequence_with_stale_tree(refsc, synth):
     for i in (0, 17, 399):
         d0, k0 = ref.get(i); d1, k1 = orc.get(i)
         assert np.array_equal(d0, d1) and np.array_equal(k0.view(np.int32), k1.view(np.int32))
+
+
+def test_batch_through_the_reference_detect_loop_closure_id(refsc, synth):
+    """bench.py --impl reference at N > 1: every query of a batch through the reference's own detectLoopClosureID, unchanged (the harness appends the query the way
+    makeAndSaveScancontextAndKeys stores a keyframe and removes it again) — loop ids and shifts equal the oracle's batch search (what the GPU search is held to)."""
+    import pyoracle as o
+    K, Q = 4000, 96
+    db = synth.sc_descriptors(K, seed=21)
+    qd, src, shift = synth.sc_queries(db, Q, seed=22)
+    R = o.RefSCManager()
+    R.save_descriptors(db)
+    loop, sh = R.query_batch(qd)
+    assert R.size() == K                                                # the harness leaves the database as it found it
+    keys = o.sc_keys_batch(db); qk = o.sc_keys_batch(qd)
+    l2, s2, _, _ = o.sc_query_batch(keys, db, qk, qd)
+    assert np.array_equal(loop, l2) and np.array_equal(sh, s2)
+    planted = src >= 0
+    assert planted.sum() >= Q // 3 and np.array_equal(loop[planted], src[planted]) and np.array_equal(sh[planted] % 60, shift[planted] % 60)
+    loop_b, sh_b = R.query_batch(qd[:10])                               # a second batch: same answers (tree rebuilt in its first call)
+    assert np.array_equal(loop_b, loop[:10]) and np.array_equal(sh_b, sh[:10])
