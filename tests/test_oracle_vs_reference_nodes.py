@@ -389,3 +389,39 @@ def test_other_configurations_vs_reference(refnodes, synth, cfg):
     deg, P = R.lm_state()
     assert deg == int(res["state"][0]) and np.array_equal(_bits(P), _bits(res["state"][1:]))
     R.close()
+
+
+def test_imu_rpy_init_sample_vs_reference(refnodes, synth):
+    """9-axis IMU (imuType 1): cloudInfo.imu{Roll,Pitch,Yaw}Init come from the LAST queued sample at or before the scan start that survived the pop (:371-375).
+    The library's liorf_host_imu_deskew_info reports that sample as rpy_index; its orientation through tf's getRPY (the oracle's restatement behind the stand-in) must be
+    what the reference node publishes."""
+    import liorf_b200
+    o = refnodes
+    rng = np.random.default_rng(13)
+    stamps, gyro = _imu_stream(rng, 999.5, 1001.0, 100.0, (0.0, 0.0, 0.3))
+    rpy = np.stack([0.02 * np.sin(stamps), 0.03 * np.cos(stamps), 0.3 * (stamps - 999.5)], 1)          # a smooth attitude, different at every sample
+    quats = []
+    for r, p, y in rpy:
+        cy, sy, cp, sp, cr, sr = np.cos(y / 2), np.sin(y / 2), np.cos(p / 2), np.sin(p / 2), np.cos(r / 2), np.sin(r / 2)
+        quats.append([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy])
+    quats = np.array(quats, np.float64)
+    R = o.RefImageProjection(imuType=1)                                    # extrinsicRPY absent → identity (the stand-in's Map of an empty vector)
+    for s, g, q in zip(stamps, gyro, quats):
+        R.imu(s, g, q)
+    raws = [synth.scan(synth.HDL64, np.array([0, 0, 0, 1.0 * k, 0, 0], np.float64), omega=(0, 0, 0.3), seed=40 + k) for k in range(4)]
+    curs = [1000.0 + 0.1 * k + 0.0042 for k in range(4)]
+    seen = 0
+    for k in range(4):
+        n = R.cloud(curs[k], raws[k])
+        if n > seen:
+            seen = n
+            c0 = curs[k - 2]; end = c0 + float(raws[k - 2]["time"][-1])
+            info = R.last_info()
+            g = liorf_b200.imuDeskewInfo(stamps, gyro, c0, end)
+            i = g["rpy_index"]
+            assert i >= 0 and stamps[i] <= c0 and (i + 1 == len(stamps) or stamps[i + 1] > c0)
+            want = rpy[i]
+            assert np.allclose(info["rpy_init"], want, atol=1e-6), (info["rpy_init"], want)
+            assert not np.allclose(info["rpy_init"], rpy[i - 1], atol=1e-5)                          # the neighbouring sample would not have passed
+    assert seen == 2
+    R.close()
