@@ -588,7 +588,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="N = 1: headline only (no rows / sequence / sc extras)")
     ap.add_argument("--seq-frames", type=int, default=60, help="timed frames of the kitti05_seq extra (0 = skip)")
     ap.add_argument("--seq-preroll", type=int, default=100)
-    ap.add_argument("--cpu-reps", type=int, default=5, help="bounded CPU-baseline sample (steps per thread setting)")
+    ap.add_argument("--cpu-reps", type=int, default=20, help="bounded CPU-baseline sample: repetitions per thread setting (BASELINE.md §3: median + p95 over >= 20)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     W = max(args.warmup, 3)
