@@ -718,10 +718,14 @@ class CpuStep:
         self.o, self.mp, self.threads = o, mp, threads
         _, n_scan, self.ls, _ = SINGLE_CFGS[name]
         self.node = None
-        if o.RefMapOpt.available() and os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libliorf_ref_mapopt_omp.so")):
-            self.node = o.RefMapOpt(openmp=True, numberOfCores=threads, mappingSurfLeafSize=self.ls, N_SCAN=n_scan)
-            self.node.set_map(mp)
-        else:
+        try:
+            if o.RefMapOpt.available() and os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libliorf_ref_mapopt_omp.so")):
+                self.node = o.RefMapOpt(openmp=True, numberOfCores=threads, mappingSurfLeafSize=self.ls, N_SCAN=n_scan)
+                self.node.set_map(mp)
+        except Exception as e:                                      # a CPU baseline must never take the GPU line down: fall back to the port and say so
+            print("[bench] reference node unavailable (%r): CPU baseline falls back to the oracle port" % (e,), file=sys.stderr)
+            self.node = None
+        if self.node is None:
             o.set_num_threads(threads)
         self.use_ref = o.ref() is not None
         self.kind = "reference" if self.node is not None else "port"
