@@ -849,9 +849,14 @@ def run_reference(args, W, K, world):
         qd, src, shift = synth.sc_queries(db[src_rows], args.sc_q)
         qd = qd[:Qc]; qk = o.sc_keys_batch(qd)
         use_ref = o.ref() is not None
-        node = o.RefSCManager() if o.refsc() is not None else None     # the reference's own SCManager (include/Scancontext.cpp compiled unchanged)
-        if node is not None:
-            node.save_descriptors(db)                                   # makeAndSaveScancontextAndKeys' bookkeeping on ready descriptors (:236-250)
+        node = None
+        try:
+            if o.refsc() is not None:
+                node = o.RefSCManager()                                 # the reference's own SCManager (include/Scancontext.cpp compiled unchanged)
+                node.save_descriptors(db)                               # makeAndSaveScancontextAndKeys' bookkeeping on ready descriptors (:236-250)
+        except Exception as e:
+            print("[bench] reference SCManager unavailable (%r): falling back to the oracle port" % (e,), file=sys.stderr)
+            node = None
         steps = min(K, 10)
         ts, tree_s, found = [], [], 0
         for i in range(min(W, 2) + steps):
