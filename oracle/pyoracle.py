@@ -493,6 +493,10 @@ class RefMapOpt:
         fn(self.h, *args, _fp(out), C.c_int(n))
         return out[:n].copy()
 
+    def extract_surrounding_keyframes(self, t):
+        """extractSurroundingKeyFrames() at laser time t (:1046-1059); get_cloud(2) / get_cloud(1) then hold the raw / filtered local map"""
+        self.l.refmo_extract_surrounding_keyframes(self.h, C.c_double(t))
+
     def loop_find_near_keyframes(self, key, search_num, loop_index):
         return self._cloud_call(self.l.refmo_loop_find_near_keyframes, C.c_int(key), C.c_int(search_num), C.c_int(loop_index))
 

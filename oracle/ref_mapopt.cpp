@@ -184,6 +184,13 @@ void refmo_add_keyframe(void* h, const float* xyzi, int n, const float* pose6, d
     mo->surfCloudKeyFrames.push_back(c);
     mo->timeLaserInfoCur = time;
 }
+// extractSurroundingKeyFrames() (:1046-1059 → extractNearby :975-1010 → extractCloud :1012-1044) at time t; laserCloudSurfFromMap (get_cloud 2) then holds the
+// selected keyframes' transformed clouds in selection order
+void refmo_extract_surrounding_keyframes(void* h, double t) {
+    mapOptimization* mo = (mapOptimization*)h;
+    mo->timeLaserInfoCur = t;
+    mo->extractSurroundingKeyFrames();
+}
 // loopFindNearKeyframes (:821-844) on a snapshot of the key poses taken the way performSCLoopClosure takes it (:629-632); returns the size
 int refmo_loop_find_near_keyframes(void* h, int key, int search_num, int loop_index, float* out, int cap) {
     mapOptimization* mo = (mapOptimization*)h;

@@ -425,3 +425,37 @@ def test_imu_rpy_init_sample_vs_reference(refnodes, synth):
             assert not np.allclose(info["rpy_init"], rpy[i - 1], atol=1e-5)                          # the neighbouring sample would not have passed
     assert seen == 2
     R.close()
+
+
+def test_keyframe_selection_at_scale_vs_reference(refnodes, synth):
+    """extractNearby + extractCloud (:975-1044) on 700 key poses of a closed drive that revisits its first leg: every keyframe cloud is ONE point whose intensity is the
+    keyframe id, so the reference's laserCloudSurfFromMap spells out its selection — ids, order, duplicates (radius set + time tail, SURVEY trap 10), the distance gate on the
+    voxel centroid — and the library's liorf_host_extract_nearby must spell the same list, at several query times (all keyframes older than 10 s; a 10 s tail; in between)."""
+    import liorf_b200
+    o = refnodes
+    vp, extract_nearby, _ = _host(liorf_b200.load_library())
+    traj = synth.street_trajectory(1400, loop=True)[::2]                       # 700 poses, 1.6 m apart
+    n = len(traj)
+    poses = np.concatenate([traj[:, :3], traj[:, 3:6]], 1).astype(np.float32)
+    times = 100.0 + 0.2 * np.arange(n)
+    R = o.RefMapOpt()
+    for k in range(n):
+        R.add_keyframe(np.array([[0.5, 0.0, 0.0, float(k)]], np.float32), poses[k], times[k])
+    checked = 0
+    for t_cur in (times[-1] + 0.1, times[-1] + 4.0, times[-1] + 30.0):
+        R.extract_surrounding_keyframes(t_cur)
+        got = R.get_cloud(2)[:, 3].astype(np.int64)
+        want = extract_nearby(poses, times, t_cur, 50.0, 2.0)
+        assert len(want) >= 20 and np.array_equal(got, want), (t_cur, got[:12], want[:12])
+        checked += 1
+    # a shorter history whose newest pose sits on the revisited leg: old and new keyframes of the same street are selected together
+    m = int(np.argmin(np.linalg.norm(poses[300:, 3:5] - poses[5, 3:5], axis=1))) + 300
+    R2 = o.RefMapOpt()
+    for k in range(m + 1):
+        R2.add_keyframe(np.array([[0.5, 0.0, 0.0, float(k)]], np.float32), poses[k], times[k])
+    R2.extract_surrounding_keyframes(times[m] + 0.05)
+    got = R2.get_cloud(2)[:, 3].astype(np.int64)
+    want = extract_nearby(poses[:m + 1], times[:m + 1], times[m] + 0.05, 50.0, 2.0)
+    assert np.array_equal(got, want) and got.min() < 40 and got.max() == m
+    R.close(); R2.close()
+    assert checked == 3
