@@ -823,6 +823,10 @@ def bench_sc_headline(args, rank, local_rank, world, W, K, dist, peaks, peak_src
                     e2e=e2e, gpu_launches=11 * K, sc=res, roofline=res["roofline"], clocks=clocks,
                     note="N > 1 measures the one workload of the path that shards (SURVEY §8e); the N = 1 line's headline is kitti64_single and carries the same search on "
                          "one GPU, same batches in flight, as `sc` / `sc_queries_per_s_100k`; `sc.unsharded_same_run` is that figure measured in THIS run on rank 0")
+        u = res.get("unsharded_same_run") or {}
+        if u.get("queries_per_s"):                                  # the one-GPU figure of THIS metric, measured in this run (the driver's N = 1 line carries the other headline)
+            line["one_gpu_same_metric"] = dict(metric="sc_queries_per_s_100k", value=u["queries_per_s"], unit="queries/s", n_gpus=1,
+                                               batches_in_flight=u.get("batches_in_flight"), measured="rank 0 alone, in this run, full copy of the database")
         print(json.dumps(line))
     return 0 if ok else 3
 
