@@ -174,3 +174,37 @@ def test_transform_update_slerp_and_clamps(lib):
         else:
             assert g[0] == np.clip(tf[0], -0.3, 0.3) and g[1] == np.clip(tf[1], -0.3, 0.3)
         assert g[5] == np.clip(tf[5], -2.0, 2.0) and np.array_equal(g[2:5], tf[2:5])
+
+
+def test_null_context_is_an_error_code_never_a_crash():
+    """Error behaviour of the boundary: every entry that takes the context answers a NULL context with LIORF_ERR_ARG (-1 for the launch counter, NULL
+    for the stream) — no CUDA call, no dereference.  Run in a child process so that a crash would fail the test instead of the suite."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, re, sys
+sys.path.insert(0, %r)
+import liorf_b200
+lib = liorf_b200.load_library()
+hdr = re.sub(r"/\*.*?\*/", "", open(%r).read(), flags=re.S)
+n_checked = 0
+for ret, name, args in re.findall(r"\b(int|void|long long|const char\*|void\*)\s+(liorf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+    args = " ".join(args.split())
+    if not args.startswith("liorf_ctx*"):
+        continue
+    n = len(re.split(r",(?![^()]*\))", args))
+    f = getattr(lib, name)
+    f.restype = None if ret == "void" else (C.c_void_p if ret == "void*" else (C.c_longlong if ret == "long long" else C.c_int))
+    r = f(*([C.c_void_p(0)] * n))
+    if ret == "int":
+        assert r == -2, (name, r)                     # LIORF_ERR_ARG
+    elif ret == "long long":
+        assert r == -1, (name, r)
+    elif ret == "void*":
+        assert not r, (name, r)
+    n_checked += 1
+assert n_checked >= 70, n_checked
+print("checked", n_checked)
+''' % (ROOT, os.path.join(ROOT, "include", "liorf_b200.h"))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "checked" in p.stdout, (p.returncode, p.stdout[-500:], p.stderr[-1500:])
