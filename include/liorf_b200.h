@@ -19,6 +19,13 @@ extern "C" {
 
 #define LIORF_MAX_ITERS 64
 
+/* return codes (token-identical to csrc/common.cuh, which the implementation includes after this header) */
+#define LIORF_OK 0
+#define LIORF_ERR_CUDA -1           /* no device / a CUDA call failed (the message goes to stderr) */
+#define LIORF_ERR_ARG -2            /* NULL context, NULL mandatory pointer, size or parameter out of range */
+#define LIORF_ERR_STATE -3          /* call order / ownership: e.g. a query before the database exists, shard extents that differ from the ones agreed at connect time */
+#define LIORF_ERR_DEVICE_FLAG -4    /* a bounded device-side wait gave up (look-back predecessor, solver hand-off, a peer's exchange flag); the context stays failed */
+
 typedef struct liorf_ctx liorf_ctx;
 
 /* pcl::PointXYZI payload (include/utility.h:61); device layout is the same 16 bytes */
