@@ -259,6 +259,7 @@ extern "C" {
 const char* liorf_version(void) { return "liorf_b200 0.1 (sm_100a)"; }
 
 void liorf_default_params(liorf_params* p) {      // config/kitti.yaml
+    if (!p) return;
     std::memset(p, 0, sizeof(*p));
     p->N_SCAN = 64; p->downsampleRate = 2; p->point_filter_num = 5;
     p->lidarMinRange = 1.0f; p->lidarMaxRange = 1000.0f;
@@ -814,7 +815,7 @@ int liorf_save_frame(liorf_ctx* c, const float pose6[6], float dist_thr, float a
     liorf_host::KeyPose last{k.pose[0], k.pose[1], k.pose[2], k.pose[3], k.pose[4], k.pose[5], k.time};
     return liorf_host::save_frame(&last, pose6, dist_thr, ang_thr) ? 1 : 0;
 }
-void liorf_transform_update_clamp(float pose6[6], float rot_tol, float z_tol) { liorf_host::transform_update_clamp(pose6, rot_tol, z_tol); }
+void liorf_transform_update_clamp(float pose6[6], float rot_tol, float z_tol) { if (pose6) liorf_host::transform_update_clamp(pose6, rot_tol, z_tol); }
 // context-free forms of the same host logic (poses: n x 6 floats (roll,pitch,yaw,x,y,z), times: n doubles)
 int liorf_host_extract_nearby(const float* poses6, const double* times, int n, double time_cur, float radius, float density, int* ids, int cap, int* n_ids) {
     if (n < 0 || !n_ids || (n > 0 && (!poses6 || !times)) || !(density > 0.f)) return LIORF_ERR_ARG;

@@ -204,6 +204,14 @@ for ret, name, args in re.findall(r"\b(int|void|long long|const char\*|void\*)\s
         assert not r, (name, r)
     n_checked += 1
 assert n_checked >= 70, n_checked
+# the context-free host entries: NULL mandatory pointers
+for name, n in (("liorf_host_extract_nearby", 9), ("liorf_host_update_initial_guess", 6), ("liorf_host_transform_update", 8), ("liorf_host_save_frame", 4),
+                ("liorf_host_imu_deskew_info", 14), ("liorf_create", 2)):
+    f = getattr(lib, name); f.restype = C.c_int
+    assert f(*([C.c_void_p(0)] * n)) == -2, name
+for name, n in (("liorf_transform_update_clamp", 3), ("liorf_default_params", 1), ("liorf_destroy", 1)):
+    f = getattr(lib, name); f.restype = None
+    f(*([C.c_void_p(0)] * n))                        # void: must simply return
 print("checked", n_checked)
 ''' % (ROOT, os.path.join(ROOT, "include", "liorf_b200.h"))
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
