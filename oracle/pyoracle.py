@@ -493,6 +493,21 @@ class RefMapOpt:
         fn(self.h, *args, _fp(out), C.c_int(n))
         return out[:n].copy()
 
+    def update_initial_guess(self, ci11, have_keyframes, tf6):
+        """updateInitialGuess() (:899-958) on cloud_info = (imuAvailable, odomAvailable, imuRollInit, imuPitchInit, imuYawInit, initialGuessX, Y, Z, Roll, Pitch, Yaw)"""
+        ci = np.ascontiguousarray(ci11, np.float32); tf = np.array(tf6, np.float32).copy()
+        self.l.refmo_update_initial_guess(self.h, _fp(ci), C.c_int(int(have_keyframes)), _fp(tf))
+        return tf
+
+    def transform_update(self, ci11, tf6):
+        ci = np.ascontiguousarray(ci11, np.float32); tf = np.array(tf6, np.float32).copy()
+        self.l.refmo_transform_update(self.h, _fp(ci), _fp(tf))
+        return tf
+
+    def save_frame(self, last_pose6, tf6):
+        last = None if last_pose6 is None else np.ascontiguousarray(last_pose6, np.float32); tf = np.ascontiguousarray(tf6, np.float32)
+        return bool(self.l.refmo_save_frame(self.h, None if last is None else _fp(last), _fp(tf)))
+
     def extract_surrounding_keyframes(self, t):
         """extractSurroundingKeyFrames() at laser time t (:1046-1059); get_cloud(2) / get_cloud(1) then hold the raw / filtered local map"""
         self.l.refmo_extract_surrounding_keyframes(self.h, C.c_double(t))

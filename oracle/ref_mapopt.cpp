@@ -131,6 +131,45 @@ int refmo_get_lm_state(void* h, float* matP36) {
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) matP36[i * 6 + j] = mo->matP.at<float>(i, j);
     return mo->isDegenerate ? 1 : 0;
 }
+// ---- the scalar member functions one by one (fuzzed against the library's host entries) ----
+static void set_cloud_info(mapOptimization* mo, const float* ci11) {   // (imuAvailable, odomAvailable, imuRollInit, imuPitchInit, imuYawInit, initialGuessX, Y, Z, Roll, Pitch, Yaw)
+    mo->cloudInfo.imuAvailable = (int64_t)ci11[0]; mo->cloudInfo.odomAvailable = (int64_t)ci11[1];
+    mo->cloudInfo.imuRollInit = ci11[2]; mo->cloudInfo.imuPitchInit = ci11[3]; mo->cloudInfo.imuYawInit = ci11[4];
+    mo->cloudInfo.initialGuessX = ci11[5]; mo->cloudInfo.initialGuessY = ci11[6]; mo->cloudInfo.initialGuessZ = ci11[7];
+    mo->cloudInfo.initialGuessRoll = ci11[8]; mo->cloudInfo.initialGuessPitch = ci11[9]; mo->cloudInfo.initialGuessYaw = ci11[10];
+}
+// updateInitialGuess() (:899-958); have_keyframes = whether cloudKeyPoses3D is non-empty (the harness adds / removes one dummy key pose)
+void refmo_update_initial_guess(void* h, const float* ci11, int have_keyframes, float* tf6_inout) {
+    mapOptimization* mo = (mapOptimization*)h;
+    set_cloud_info(mo, ci11);
+    if (have_keyframes && mo->cloudKeyPoses3D->points.empty()) { PointType p; mo->cloudKeyPoses3D->push_back(p); }
+    if (!have_keyframes) mo->cloudKeyPoses3D->clear();
+    std::memcpy(mo->transformTobeMapped, tf6_inout, 6 * sizeof(float));
+    mo->updateInitialGuess();
+    std::memcpy(tf6_inout, mo->transformTobeMapped, 6 * sizeof(float));
+}
+// transformUpdate() (:1323-1353)
+void refmo_transform_update(void* h, const float* ci11, float* tf6_inout) {
+    mapOptimization* mo = (mapOptimization*)h;
+    set_cloud_info(mo, ci11);
+    std::memcpy(mo->transformTobeMapped, tf6_inout, 6 * sizeof(float));
+    mo->transformUpdate();
+    std::memcpy(tf6_inout, mo->transformTobeMapped, 6 * sizeof(float));
+}
+// saveFrame() (:1365-1384) against a last key pose (NULL = no keyframes yet)
+int refmo_save_frame(void* h, const float* last_pose6, const float* tf6) {
+    mapOptimization* mo = (mapOptimization*)h;
+    mo->cloudKeyPoses3D->clear(); mo->cloudKeyPoses6D->clear();
+    if (last_pose6) {
+        PointType p3; PointTypePose p6;
+        p3.x = last_pose6[3]; p3.y = last_pose6[4]; p3.z = last_pose6[5];
+        p6.x = p3.x; p6.y = p3.y; p6.z = p3.z; p6.roll = last_pose6[0]; p6.pitch = last_pose6[1]; p6.yaw = last_pose6[2]; p6.time = 0; p6.intensity = 0;
+        mo->cloudKeyPoses3D->push_back(p3); mo->cloudKeyPoses6D->push_back(p6);
+    }
+    std::memcpy(mo->transformTobeMapped, tf6, 6 * sizeof(float));
+    return mo->saveFrame() ? 1 : 0;
+}
+
 // ---- bench.py --impl reference / cpu_baseline: one headline step timed on the reference's own member functions ----
 // laserCloudSurfLast = scan (filled before the clock starts, like the GPU arm's resident scan), then downsampleCurrentScan() (:1061-1067), the kd-tree
 // build of scan2MapOptimization (:1302) and `iters` passes of its loop body (:1306-1314) — the convergence break is left out when force_all != 0, as the

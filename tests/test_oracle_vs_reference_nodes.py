@@ -459,3 +459,50 @@ def test_keyframe_selection_at_scale_vs_reference(refnodes, synth):
     assert np.array_equal(got, want) and got.min() < 40 and got.max() == m
     R.close(); R2.close()
     assert checked == 3
+
+
+def test_scalar_host_entries_fuzzed_against_the_reference_members(refnodes):
+    """liorf_host_update_initial_guess / liorf_host_transform_update / liorf_host_save_frame against the reference's own updateInitialGuess (:899-958), transformUpdate
+    (:1323-1353) and saveFrame (:1365-1384), called directly on the node: random sequences (availability flags toggling, large attitudes up to the gimbal region, 6- and
+    9-axis, heading initialisation on / off), thousands of random pose pairs around the keyframe thresholds — bit for bit / decision for decision."""
+    import liorf_b200
+    from liorf_b200 import GuessState, CloudInfoGuess
+    o = refnodes
+    lib = liorf_b200.load_library()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(21)
+    for trial, (imu_type, heading) in enumerate([(0, 0), (1, 1), (1, 0), (0, 1)] * 3):
+        R = o.RefMapOpt(imuType=imu_type, useImuHeadingInitialization=heading, imuRPYWeight=0.07, rotation_tollerance=0.9, z_tollerance=3.0)
+        st = GuessState(); tf = np.zeros(6, np.float32); rtf = np.zeros(6, np.float32)
+        scale = [0.05, 0.3, 1.2][trial % 3]                                  # attitude spread: small, large, towards +-pi/2 pitch
+        odo = rng.normal(scale=[scale, scale, 1.0, 5, 5, 1], size=6)
+        for k in range(60):
+            odo = odo + rng.normal(scale=[0.01 * scale * 10, 0.01 * scale * 10, 0.05, 0.8, 0.3, 0.05], size=6)
+            odo[1] = np.clip(odo[1], -1.5, 1.5)
+            rpy = odo[:3] + rng.normal(scale=3e-3, size=3)
+            ci11 = np.array([rng.random() < 0.8, rng.random() < 0.7, *rpy, odo[3], odo[4], odo[5], odo[0], odo[1], odo[2]], np.float32)
+            have_kf = k > 0
+            ci = CloudInfoGuess(int(ci11[0]), int(ci11[1]), *[float(v) for v in ci11[2:]])
+            assert lib.liorf_host_update_initial_guess(C.byref(st), int(not have_kf), C.byref(ci), heading, imu_type, vp(tf)) == 0
+            rtf = R.update_initial_guess(ci11, have_kf, rtf)
+            assert np.array_equal(_bits(tf), _bits(rtf)), (trial, k, tf, rtf)
+            # a solver step in between (the same perturbation on both sides), then transformUpdate
+            step = rng.normal(scale=[2e-3, 2e-3, 5e-3, 0.05, 0.05, 0.02], size=6).astype(np.float32)
+            tf = (tf + step).astype(np.float32); rtf = (rtf + step).astype(np.float32)
+            lib.liorf_host_transform_update(vp(tf), int(ci11[0]), imu_type, C.c_float(ci11[2]), C.c_float(ci11[3]), C.c_float(0.07), C.c_float(0.9), C.c_float(3.0))
+            rtf = R.transform_update(ci11, rtf)
+            assert np.array_equal(_bits(tf), _bits(rtf)), (trial, k, "transformUpdate", tf, rtf)
+        R.close()
+    R = o.RefMapOpt(surroundingkeyframeAddingDistThreshold=1.0, surroundingkeyframeAddingAngleThreshold=0.2)
+    n_true = 0
+    for k in range(3000):
+        last = rng.normal(scale=[0.3, 0.3, 2.0, 50, 50, 2], size=6).astype(np.float32)
+        d = rng.normal(scale=[0.12, 0.12, 0.12, 0.6, 0.6, 0.3], size=6).astype(np.float32)
+        cur = (last + d).astype(np.float32)
+        want = R.save_frame(last, cur)
+        got = lib.liorf_host_save_frame(vp(last), vp(cur), C.c_float(1.0), C.c_float(0.2)) == 1
+        assert want == got, (k, last, cur)
+        n_true += int(want)
+    assert 300 < n_true < 2700                                                # both outcomes well represented
+    assert R.save_frame(None, np.zeros(6, np.float32)) is True and lib.liorf_host_save_frame(None, vp(np.zeros(6, np.float32)), C.c_float(1.0), C.c_float(0.2)) == 1
+    R.close()
