@@ -506,3 +506,40 @@ def test_scalar_host_entries_fuzzed_against_the_reference_members(refnodes):
     assert 300 < n_true < 2700                                                # both outcomes well represented
     assert R.save_frame(None, np.zeros(6, np.float32)) is True and lib.liorf_host_save_frame(None, vp(np.zeros(6, np.float32)), C.c_float(1.0), C.c_float(0.2)) == 1
     R.close()
+
+
+def test_surf_optimization_branches_fuzzed_against_the_reference(refnodes):
+    """surfOptimization (:1074-1143) on maps that are NOT friendly: noisy planes at several noise levels, sparse volumes (5th neighbour beyond 1 m → no fit), points far
+    from the sensor origin and near it (the s weight's sqrt(sqrt(range)) denominator), so that every branch — distance gate, plane validity at 0.2, s > 0.1 — is taken often;
+    flags and coefficient bits of every point equal the oracle's; the reference's kd-tree (nanoflann) neighbour ORDER is what the oracle's kd-tree variant reproduces."""
+    o = refnodes
+    rng = np.random.default_rng(33)
+    seen = dict(far=0, invalid=0, low_s=0, ok=0)
+    for trial in range(6):
+        noise = [0.005, 0.03, 0.08, 0.15, 0.02, 0.05][trial]
+        n_map = [30000, 30000, 20000, 20000, 4000, 8000][trial]
+        xy = rng.uniform(-30, 30, size=(n_map, 2))
+        planes = np.where(rng.random(n_map) < 0.5, -1.7 + noise * rng.normal(size=n_map), 0.0)
+        wall = rng.random(n_map) < 0.25
+        mp = np.zeros((n_map, 4), np.float32)
+        mp[:, 0] = np.where(wall, 12.0 + noise * rng.normal(size=n_map), xy[:, 0]); mp[:, 1] = xy[:, 1]
+        mp[:, 2] = np.where(wall, rng.uniform(-1.7, 4.0, n_map), planes + np.where(planes == 0.0, rng.uniform(-1.7, 6.0, n_map), 0.0))
+        mp = o.voxel_grid(mp, 0.5)[0]
+        n_q = 3000
+        q = np.zeros((n_q, 4), np.float32)
+        q[:, :2] = rng.uniform(-28, 28, size=(n_q, 2)) * (0.05 if trial == 5 else 1.0); q[:, 2] = np.where(rng.random(n_q) < 0.6, -1.7, rng.uniform(-1.7, 5.0, n_q)) + 0.3 * rng.normal(size=n_q) * (trial % 2)
+        tf = np.array([0.01, -0.02, 0.03, 0.2, -0.1, 0.05], np.float32) * (trial - 2)
+        R = o.RefMapOpt()
+        R.set_scan_and_map(q, mp)
+        R.set_transform(tf)
+        coeff, flag = R.surf_optimization()
+        R.close()
+        so = o.surf_optimization(q, mp, tf)
+        kidx, kd2 = o.kdtree_knn5(mp, so["sel"])
+        assert np.array_equal(flag, so["flag"]), (trial, int(flag.sum()), int(so["flag"].sum()))
+        assert np.array_equal(_bits(coeff[flag == 1]), _bits(so["coeff"][flag == 1])), trial
+        far = kd2[:, 4] >= 1.0
+        seen["far"] += int(far.sum()); seen["ok"] += int(flag.sum())
+        seen["invalid"] += int(((~far) & (so["plane"][:, :3] == 0).all(1) & (flag == 0)).sum())
+        seen["low_s"] += int(((~far) & (flag == 0)).sum())
+    assert seen["far"] > 1000 and seen["ok"] > 3000 and seen["low_s"] > 500, seen
