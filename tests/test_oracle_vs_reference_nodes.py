@@ -543,3 +543,44 @@ def test_surf_optimization_branches_fuzzed_against_the_reference(refnodes):
         seen["invalid"] += int(((~far) & (so["plane"][:, :3] == 0).all(1) & (flag == 0)).sum())
         seen["low_s"] += int(((~far) & (flag == 0)).sum())
     assert seen["far"] > 1000 and seen["ok"] > 3000 and seen["low_s"] > 500, seen
+
+
+def test_image_projection_fuzzed_filters_and_rates(refnodes, synth):
+    """random ParamServer settings through the reference's ImageProjection node: downsampleRate 1-4, point_filter_num 1-7, range windows that cut returns on both sides,
+    N_SCAN below the sensor's ring count (the ring gate, :585), IMU rates of 100 / 200 / 500 Hz with jitter, scans whose last points lie beyond the last IMU row (findRotation
+    never extrapolates, trap 3) — the published cloud equals the oracle's bit for bit, and the kept-index list equals the raw-index filter (trap 1)."""
+    o = refnodes
+    rng = np.random.default_rng(44)
+    total = 0
+    for trial in range(10):
+        filt = dict(lidarMinRange=float(rng.choice([0.5, 1.0, 3.0, 6.0])), lidarMaxRange=float(rng.choice([25.0, 60.0, 1000.0])), N_SCAN=int(rng.choice([64, 48, 32])),
+                    downsampleRate=int(rng.integers(1, 5)), point_filter_num=int(rng.integers(1, 8)))
+        rate = float(rng.choice([100.0, 200.0, 500.0]))
+        omega = tuple(rng.normal(scale=[0.05, 0.05, 0.9]))
+        R = o.RefImageProjection(imuRate=rate, **filt)
+        cur = 500.0 + float(rng.uniform(0, 0.01))
+        raws = [synth.scan(synth.HDL64, np.array([0, 0, 0, 1.0 * k, 0, 0], np.float64), omega=omega, seed=1000 + 10 * trial + k) for k in range(3)]
+        end = cur + float(raws[0]["time"][-1])
+        t_hi = end + 0.3 if trial % 3 else end + 0.004                       # every third trial: the IMU stream stops right after the scan end (few rows past it)
+        stamps, gyro = _imu_stream(rng, cur - 0.3, t_hi, rate, omega)
+        for s_, g_ in zip(stamps, gyro):
+            R.imu(s_, g_)
+        for k in range(3):
+            n = R.cloud(cur + 0.1 * k, raws[k])
+        covered = stamps[0] <= cur and stamps[-1] >= end
+        assert n == (1 if covered else 0), (trial, n, covered)
+        if not covered:
+            R.close(); continue
+        info = R.last_info()
+        od = o.imu_deskew_info(stamps, gyro, cur, end)
+        assert info["imuAvailable"] == int(od["available"])
+        cloud, kept = o.project_point_cloud(raws[0], filt, cur, od["imu_time"], od["imu_rot"], od["imu_pointer_cur"], bool(od["available"]))
+        assert info["cloud"].shape == cloud.shape and np.array_equal(_bits(info["cloud"]), _bits(cloud)), (trial, filt)
+        r0 = raws[0]
+        rng_ok = np.sqrt((r0["x"].astype(np.float32) ** 2 + r0["y"].astype(np.float32) ** 2 + r0["z"].astype(np.float32) ** 2).astype(np.float32))
+        want = np.nonzero((rng_ok >= filt["lidarMinRange"]) & (rng_ok <= filt["lidarMaxRange"]) & (r0["ring"] < filt["N_SCAN"]) & (r0["ring"] % filt["downsampleRate"] == 0)
+                          & (np.arange(len(r0)) % filt["point_filter_num"] == 0))[0]
+        assert abs(len(want) - len(kept)) <= 2 and np.all(kept % filt["point_filter_num"] == 0)      # (float range at the window edges may differ by an ulp from numpy's)
+        total += len(kept)
+        R.close()
+    assert total > 20000
