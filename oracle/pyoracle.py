@@ -493,6 +493,12 @@ class RefMapOpt:
         fn(self.h, *args, _fp(out), C.c_int(n))
         return out[:n].copy()
 
+    def lm_optimization(self, it, ori, coeff, tf6):
+        """LMOptimization(it) (:1158-1293) on given (laserCloudOri, coeffSel) → (converged, tf)"""
+        a = _as_p4(ori); b = _as_p4(coeff); tf = np.array(tf6, np.float32).copy()
+        c = self.l.refmo_lm_optimization(self.h, C.c_int(it), _fp(a), _fp(b), C.c_int(len(a)), _fp(tf))
+        return bool(c), tf
+
     def update_initial_guess(self, ci11, have_keyframes, tf6):
         """updateInitialGuess() (:899-958) on cloud_info = (imuAvailable, odomAvailable, imuRollInit, imuPitchInit, imuYawInit, initialGuessX, Y, Z, Roll, Pitch, Yaw)"""
         ci = np.ascontiguousarray(ci11, np.float32); tf = np.array(tf6, np.float32).copy()

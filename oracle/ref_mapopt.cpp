@@ -170,6 +170,16 @@ int refmo_save_frame(void* h, const float* last_pose6, const float* tf6) {
     return mo->saveFrame() ? 1 : 0;
 }
 
+// LMOptimization(iterCount) (:1158-1293) on given correspondences: laserCloudOri / coeffSel are filled directly (they are what combineOptimizationCoeffs leaves)
+int refmo_lm_optimization(void* h, int iterCount, const float* ori4, const float* coeff4, int n, float* tf6_inout) {
+    mapOptimization* mo = (mapOptimization*)h;
+    fill_cloud(ori4, n, *mo->laserCloudOri); fill_cloud(coeff4, n, *mo->coeffSel);
+    std::memcpy(mo->transformTobeMapped, tf6_inout, 6 * sizeof(float));
+    const bool conv = mo->LMOptimization(iterCount);
+    std::memcpy(tf6_inout, mo->transformTobeMapped, 6 * sizeof(float));
+    return conv ? 1 : 0;
+}
+
 // ---- bench.py --impl reference / cpu_baseline: one headline step timed on the reference's own member functions ----
 // laserCloudSurfLast = scan (filled before the clock starts, like the GPU arm's resident scan), then downsampleCurrentScan() (:1061-1067), the kd-tree
 // build of scan2MapOptimization (:1302) and `iters` passes of its loop body (:1306-1314) — the convergence break is left out when force_all != 0, as the

@@ -584,3 +584,39 @@ def test_image_projection_fuzzed_filters_and_rates(refnodes, synth):
         total += len(kept)
         R.close()
     assert total > 20000
+
+
+def test_lm_optimization_fuzzed_against_the_reference(refnodes):
+    """LMOptimization (:1158-1293) on synthetic correspondences: well-conditioned, rank-deficient (all normals parallel → five small eigenvalues), nearly degenerate, fewer than 50
+    rows, converged-size steps; iteration 0 (eigen-analysis, matP) followed by later iterations that reuse isDegenerate / matP — pose, verdict, isDegenerate and matP bits."""
+    o = refnodes
+    rng = np.random.default_rng(55)
+    outcomes = dict(conv=0, deg=0, short=0)
+    for trial in range(40):
+        n = int(rng.choice([10, 49, 50, 51, 300, 2000, 6000]))
+        kind = trial % 4
+        ori = np.zeros((n, 4), np.float32); ori[:, :3] = rng.normal(scale=[20, 20, 3], size=(n, 3))
+        nrm = rng.normal(size=(n, 3))
+        if kind == 1:
+            nrm = np.tile([0.0, 0.0, 1.0], (n, 1)) + 1e-4 * rng.normal(size=(n, 3))          # ground only
+        elif kind == 2:
+            nrm[:, 2] *= 1e-3                                                                # walls only: z unobservable
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        res = rng.normal(scale=[0.05, 1e-4, 0.02, 0.2][kind], size=n)
+        s = rng.uniform(0.1, 1.0, size=n)
+        coeff = np.concatenate([s[:, None] * nrm, (s * res)[:, None]], 1).astype(np.float32)
+        tf = rng.normal(scale=[0.02, 0.02, 1.0, 20, 20, 1], size=6).astype(np.float32)
+        R = o.RefMapOpt()
+        st = np.zeros(37, np.float32)
+        rtf = tf.copy()
+        for it in range(3):
+            conv, rtf = R.lm_optimization(it, ori, coeff, rtf)
+            r = o.lm_optimization(it, ori, coeff, tf, st)
+            tf, st = r["tf"], r["state"]
+            assert conv == r["converged"] and np.array_equal(_bits(rtf), _bits(tf)), (trial, it, n, kind)
+            deg, P = R.lm_state()
+            assert deg == int(st[0]) and np.array_equal(_bits(P), _bits(st[1:])), (trial, it)
+            outcomes["conv"] += int(conv); outcomes["short"] += int(n < 50)
+        outcomes["deg"] += int(st[0])
+        R.close()
+    assert outcomes["deg"] >= 8 and outcomes["short"] >= 9 and outcomes["conv"] >= 3, outcomes
