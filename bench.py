@@ -837,6 +837,35 @@ def sc_config(args):
                 K=args.sc_k, Q=args.sc_q, l2="inputs larger than L2: a batch reads 315 MB of query descriptors and ~0.9 GB of candidate descriptors")
 
 
+def reference_rows(o, inst, kfs, threads, reps=5):
+    """CPU figures beside the GPU line's `rows`: extractSurroundingKeyFrames of the 50 keyframes (extractNearby + transformPointCloud with OpenMP + the map VoxelGrid,
+    src/mapOptmization.cpp:975-1044) on the reference's node, makeAndSaveScancontextAndKeys of the full scan and detectLoopClosureID on the reference's SCManager"""
+    rows = {}
+    if o.RefMapOpt.available() and os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libliorf_ref_mapopt_omp.so")):
+        ts = []
+        for r in range(reps + 1):
+            R = o.RefMapOpt(openmp=True, numberOfCores=threads)     # a fresh node: the transformed-cloud cache (:1022-1032) starts empty, as for a new selection
+            for k, (c, p) in enumerate(zip(kfs, inst["poses"])):
+                R.add_keyframe(c, p.astype(np.float32), 100.0 + 0.1 * k)
+            a = time.perf_counter()
+            R.extract_surrounding_keyframes(100.0 + 0.1 * len(kfs))
+            ts.append((time.perf_counter() - a) * 1e3)
+            m = R.state()["m_ds"]
+            R.close()
+        rows["map_build_ms"] = dict(ms=stats_ms(ts[1:]), m_map=int(m), kind="reference", threads=threads,
+                                    note="extractSurroundingKeyFrames on the reference's node: selection + 50 x transformPointCloud + VoxelGrid(0.5 m) of the concatenation")
+    if o.refsc() is not None:
+        S = o.RefSCManager()
+        t_make, t_det = [], []
+        for r in range(60):                                         # detectLoopClosureID needs more than 30 entries; the tree is rebuilt every 10th call
+            a = time.perf_counter(); S.make_and_save(inst["scan"]); t_make.append((time.perf_counter() - a) * 1e3)
+        for r in range(20):
+            a = time.perf_counter(); S.detect(); t_det.append((time.perf_counter() - a) * 1e3)
+        rows["sc_make_ms"] = dict(ms=stats_ms(t_make[5:]), n_points=int(len(inst["scan"])), kind="reference", threads=1)
+        rows["sc_detect_ms"] = dict(ms=stats_ms(t_det), database=60, kind="reference", threads=1, note="one detectLoopClosureID call against 60 entries (tree rebuilt every 10th call)")
+    return rows
+
+
 def run_reference(args, W, K, world):
     """--impl reference: the CPU implementation of the path on the host cores — same metric / config as the GPU arm at this N, bounded sample."""
     sys.path.insert(0, ORACLE_DIR)
@@ -925,6 +954,10 @@ def run_reference(args, W, K, world):
                 cpu_baseline=dict(value=v, unit="ms/frame", cores=all_cores, kind=kind, sample=sample,
                                   ms=best["ms"], split_ms=best["split_ms"], threads_4=results.get(4) if all_cores != 4 else None),
                 e2e=dict(value=v, unit="ms/frame", h2d_bytes_per_step=0, d2h_bytes_per_step=0), final_pose=[float(x) for x in pose])
+    try:                                                            # the other per-function figures BASELINE.md §3 lists, on the reference's own code where it is compiled
+        line["rows"] = reference_rows(o, inst, kfs, all_cores)
+    except Exception as e:
+        line["rows"] = dict(error=repr(e))
     print(json.dumps(line))
     return 0
 
