@@ -335,16 +335,62 @@ inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double ti
             iv[k] = {overflow ? k : i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1], k};
         }
         std::sort(iv.begin(), iv.end());
+        // candidates of the nearest-1 searches below (see there): the poses closer to `back` than shell_r, bucketed into cells of edge g = 2 density
+        const double shell_r = (double)radius + 4.0 * (double)density + 1.0;
+        const double g = 2.0 * (double)density;
+        auto cell_of = [&](double v, double o) { return (long long)std::floor((v - o) / g) + (1ll << 19); };
+        auto key_of = [](long long cx, long long cy, long long cz) { return (cz << 42) | (cy << 21) | cx; };
+        std::vector<std::pair<long long, int>> cells;                                  // (cell key, pose index), sorted
+        for (int i = 0; i < n; ++i) {
+            const double ax = (double)kp[i].x - back.x, ay = (double)kp[i].y - back.y, az = (double)kp[i].z - back.z;
+            const double q = ax * ax + ay * ay + az * az;
+            if (q < shell_r * shell_r) cells.emplace_back(key_of(cell_of(kp[i].x, back.x), cell_of(kp[i].y, back.y), cell_of(kp[i].z, back.z)), i);   // (a NaN pose is left out: it can never win a `<`)
+        }
+        const bool shell_is_all = (int)cells.size() == n;
+        const bool grid_ok = shell_r < g * (double)(1 << 18);                          // cell coordinates fit their 21 bits
+        std::sort(cells.begin(), cells.end());
         int k = 0;
         while (k < m) {
             int j = k; float sx = 0, sy = 0, sz = 0;
             while (j < m && iv[j].first == iv[k].first) { const KeyPose& p = kp[near[iv[j].second].second]; sx += p.x; sy += p.y; sz += p.z; ++j; }
             float c = (float)(j - k), cx = sx / c, cy = sy / c, cz = sz / c;
+            // nearest-1 over ALL key poses, ties to the lower index (the order-independent form of "ascending scan, strict <").
+            //  (1) the voxel's own members are key poses: the best of them bounds the answer, bd <= (voxel diagonal)^2;
+            //  (2) any pose that beats or ties bd differs from the centroid by at most b = sqrt(bd) per axis, so it sits in one of the <= 2 x 2 x 2 cells around the
+            //      centroid (cell edge g >= b; the same monotonic cell function is applied to both, b carries a 1e-4 margin against the fp32 rounding of d);
+            //  (3) a pose OUTSIDE the shell is at least shell_r - |c - back| from the centroid (triangle inequality, in double, with margin): once bd is below that,
+            //      nothing outside can win or tie.  Otherwise — never seen on a drive; publishGlobalMap's 1 km radius makes the shell everything anyway — every
+            //      pose is scanned, as the reference's kd-tree would.
             int best = 0; float bd = INFINITY;
-            for (int i = 0; i < n; ++i) {
+            auto consider = [&](int i) {
                 float ex = cx - kp[i].x, ey = cy - kp[i].y, ez = cz - kp[i].z;
                 float d = ex * ex; d += ey * ey; d += ez * ez;
-                if (d < bd) { bd = d; best = i; }
+                if (d < bd || (d == bd && i < best)) { bd = d; best = i; }
+            };
+            for (int t = k; t < j; ++t) consider(near[iv[t].second].second);
+            bool done = false;
+            if (grid_ok && bd < INFINITY && cx == cx && cy == cy && cz == cz) {
+                const double b = std::sqrt((double)bd) * (1.0 + 1e-4) + 1e-30;
+                if (b < g) {
+                    const long long x0 = cell_of(cx - b, back.x), x1 = cell_of(cx + b, back.x), y0 = cell_of(cy - b, back.y), y1 = cell_of(cy + b, back.y),
+                                    z0 = cell_of(cz - b, back.z), z1 = cell_of(cz + b, back.z);
+                    for (long long zc = z0; zc <= z1; ++zc)
+                        for (long long yc = y0; yc <= y1; ++yc) {
+                            auto it = std::lower_bound(cells.begin(), cells.end(), std::make_pair(key_of(x0, yc, zc), -1));
+                            const long long last = key_of(x1, yc, zc);
+                            for (; it != cells.end() && it->first <= last; ++it) consider(it->second);
+                        }
+                    const double c_back = std::sqrt((double)(cx - back.x) * (cx - back.x) + (double)(cy - back.y) * (cy - back.y) + (double)(cz - back.z) * (cz - back.z));
+                    const double outside = shell_r - c_back;                           // lower bound of |p - c| for every pose p outside the shell
+                    done = shell_is_all || (outside > 0.0 && outside * outside * (1.0 - 1e-4) > (double)bd);
+                }
+            }
+            if (!done) {
+#ifdef LIORF_PROF_FALLBACK
+                LIORF_PROF_FALLBACK;
+#endif
+                best = 0; bd = INFINITY;
+                for (int i = 0; i < n; ++i) consider(i);
             }
             if (!(point_distance(cx, cy, cz, back.x, back.y, back.z) > radius)) out.push_back(best);      // :1018 on the centroid
             k = j;

@@ -620,3 +620,56 @@ def test_lm_optimization_fuzzed_against_the_reference(refnodes):
         outcomes["deg"] += int(st[0])
         R.close()
     assert outcomes["deg"] >= 8 and outcomes["short"] >= 9 and outcomes["conv"] >= 3, outcomes
+
+
+def test_keyframe_selection_adversarial_vs_reference(refnodes):
+    """liorf_host_extract_nearby's grid-pruned nearest-1 (exact by construction: own-voxel bound, cell cover, shell bound, full-scan fallback) against the reference's
+    extractNearby on data built to break a shortcut: key poses on an exact 1 m lattice (voxel centroids equidistant from several poses: ties), exact duplicates, a block
+    driven round many times (hundreds of poses inside the search ball), far-away clusters, poses just inside / outside the radius, several radii and densities."""
+    import liorf_b200
+    o = refnodes
+    vp, extract_nearby, _ = _host(liorf_b200.load_library())
+    rng = np.random.default_rng(66)
+
+    def check(poses, times, t_cur, radius, density):
+        poses = np.ascontiguousarray(poses, np.float32)
+        R = o.RefMapOpt(surroundingKeyframeSearchRadius=radius, surroundingKeyframeDensity=density)
+        for k in range(len(poses)):
+            R.add_keyframe(np.array([[0.5, 0.0, 0.0, float(k)]], np.float32), poses[k], times[k])
+        R.extract_surrounding_keyframes(t_cur)
+        got = R.get_cloud(2)[:, 3].astype(np.int64)
+        R.close()
+        want = extract_nearby(poses, times, t_cur, radius, density)
+        assert np.array_equal(got, want), (len(poses), radius, density, got[:10], want[:10])
+        return len(want)
+
+    total = 0
+    for trial in range(14):
+        n = int(rng.choice([40, 150, 400, 900]))
+        kind = trial % 7
+        P = np.zeros((n, 6), np.float32)
+        if kind == 0:                                    # exact lattice, visited in a random order
+            g = np.stack(np.meshgrid(np.arange(30), np.arange(30), [0.0]), -1).reshape(-1, 3)[rng.permutation(900)[:n]]
+            P[:, 3:6] = g
+        elif kind == 1:                                  # duplicates of a few positions
+            base = rng.uniform(-30, 30, size=(12, 3)) * [1, 1, 0.05]
+            P[:, 3:6] = base[rng.integers(0, 12, n)]
+        elif kind == 2:                                  # one block, many laps (1.3 m steps with jitter)
+            s = np.arange(n) * 1.3
+            per = 160.0; u = s % per
+            P[:, 3] = np.where(u < 50, u, np.where(u < 80, 50, np.where(u < 130, 130 - u, 0))) + rng.normal(scale=0.05, size=n)
+            P[:, 4] = np.where(u < 50, 0, np.where(u < 80, u - 50, np.where(u < 130, 30, 160 - u))) + rng.normal(scale=0.05, size=n)
+        elif kind == 3:                                  # clusters, some far away
+            c = rng.uniform(-300, 300, size=(6, 3)) * [1, 1, 0.01]; c[0] = 0
+            P[:, 3:6] = c[rng.integers(0, 6, n)] + rng.normal(scale=8.0, size=(n, 3)) * [1, 1, 0.05]
+        elif kind == 4:                                  # a ring of poses right at the radius around the newest one
+            ang = rng.uniform(0, 2 * np.pi, n); rad = 50.0 + rng.choice([-1e-3, 0.0, 1e-3, -2.0, 2.0], n)
+            P[:, 3] = rad * np.cos(ang); P[:, 4] = rad * np.sin(ang); P[-1, 3:6] = 0
+        elif kind == 5:                                  # straight drive with exact 0.5 m spacing (pairs share 2 m voxels symmetrically)
+            P[:, 3] = 0.5 * np.arange(n)
+        else:                                            # random walk
+            P[:, 3:6] = np.cumsum(rng.normal(scale=[1.0, 0.6, 0.02], size=(n, 3)), 0)
+        times = 100.0 + 0.1 * np.arange(n) * rng.choice([1.0, 3.0])
+        for radius, density in ((50.0, 2.0), (15.0, 1.0), (80.0, 5.0)):
+            total += check(P, times, times[-1] + float(rng.choice([0.05, 5.0, 50.0])), radius, density)
+    assert total > 3000
