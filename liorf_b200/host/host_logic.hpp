@@ -341,13 +341,13 @@ inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double ti
         auto cell_of = [&](double v, double o) { return (long long)std::floor((v - o) / g) + (1ll << 19); };
         auto key_of = [](long long cx, long long cy, long long cz) { return (cz << 42) | (cy << 21) | cx; };
         std::vector<std::pair<long long, int>> cells;                                  // (cell key, pose index), sorted
-        for (int i = 0; i < n; ++i) {
+        const bool grid_ok = g > 0.0 && shell_r < g * (double)(1 << 18);               // cell coordinates fit their 21 bits (else: full scans below)
+        for (int i = 0; grid_ok && i < n; ++i) {
             const double ax = (double)kp[i].x - back.x, ay = (double)kp[i].y - back.y, az = (double)kp[i].z - back.z;
             const double q = ax * ax + ay * ay + az * az;
             if (q < shell_r * shell_r) cells.emplace_back(key_of(cell_of(kp[i].x, back.x), cell_of(kp[i].y, back.y), cell_of(kp[i].z, back.z)), i);   // (a NaN pose is left out: it can never win a `<`)
         }
         const bool shell_is_all = (int)cells.size() == n;
-        const bool grid_ok = shell_r < g * (double)(1 << 18);                          // cell coordinates fit their 21 bits
         std::sort(cells.begin(), cells.end());
         int k = 0;
         while (k < m) {
