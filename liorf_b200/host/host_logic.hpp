@@ -386,9 +386,6 @@ inline std::vector<int> extract_nearby(const std::vector<KeyPose>& kp, double ti
                 }
             }
             if (!done) {
-#ifdef LIORF_PROF_FALLBACK
-                LIORF_PROF_FALLBACK;
-#endif
                 best = 0; bd = INFINITY;
                 for (int i = 0; i < n; ++i) consider(i);
             }
