@@ -314,9 +314,50 @@ def sequence_extra(local_rank, rank, P, W, K):
                          avg_n_ds=st["n_ds"] / max(st["frames"], 1), avg_m_ds=st["m_ds"] / max(st["frames"], 1), avg_lm_iters=st["iters"] / max(st["frames"], 1),
                          kernel_ms_per_frame={k: v[0] / K for k, v in tm.items() if v[1]})
         pipe.ctx.close()
+    try:                                                            # the CPU figure must never take the GPU row down
+        cpu = sequence_cpu_reference(seq, P + W, min(K, 20))
+    except Exception as e:
+        cpu = dict(error=repr(e))
     return dict(workload="kitti05_seq: synthetic 64-beam drive, %d-frame window after a %d-frame pre-roll, yaml filters, early-exit LM, one liorf_process_frame call per frame "
                          "with look-ahead (next frame's H2D + deskew + downsample overlap this frame's solve); every section timed (costs ~10 us/frame of host time)" % (K, P),
-                resident=out["dev"], e2e=out["e2e"], h2d_bytes_per_frame=int(np.mean([seq.raw[i].nbytes for i in range(P + W, P + W + K)])), d2h_bytes_per_frame=64)
+                resident=out["dev"], e2e=out["e2e"], h2d_bytes_per_frame=int(np.mean([seq.raw[i].nbytes for i in range(P + W, P + W + K)])), d2h_bytes_per_frame=64,
+                cpu_baseline=cpu)
+
+
+def sequence_cpu_reference(seq, preroll, frames, threads=None):
+    """config 2 on the host cores: the same frames, one liorf::cloud_info per scan through the reference's OWN mapOptimization node (src/mapOptmization.cpp compiled unchanged
+    with -O3 + OpenMP, oracle/_ref/libliorf_ref_mapopt_omp.so): updateInitialGuess, extractSurroundingKeyFrames, downsampleCurrentScan, scan2MapOptimization (early exit),
+    saveKeyFramesAndFactor incl. the ScanContext descriptor.  The deskew in front of it is the oracle port of projectPointCloud (the reference's ImageProjection node gives the same
+    bits, tests/test_oracle_vs_reference_nodes.py).  `preroll` frames build the keyframe map untimed, `frames` frames are timed."""
+    if ORACLE_DIR not in sys.path:
+        sys.path.insert(0, ORACLE_DIR)
+    import pyoracle as o
+    threads = threads or (os.cpu_count() or 1)
+    if not (o.RefMapOpt.available() and os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libliorf_ref_mapopt_omp.so"))):
+        return dict(unavailable="oracle/_ref/libliorf_ref_mapopt_omp.so is not on this box")
+    R = o.RefMapOpt(openmp=True, numberOfCores=threads, useImuHeadingInitialization=1)
+    prev, t_dk, t_node, kf0 = None, [], [], 0
+    for i in range(preroll + frames):
+        raw, (t0, it, rot, ptr) = seq.frame(i)
+        a = time.perf_counter()
+        cloud, _ = o.project_point_cloud(raw, seq.filters, t0, it, rot, ptr, True)
+        b = time.perf_counter()
+        g = np.asarray(seq.initial_guess(i, prev), np.float32)
+        R.set_transform(g)                                          # transformTobeMapped = this frame's guess (no odometry / IMU increment on top)
+        R.cloud_info(t0, cloud, 0, 0, g[:3], None)
+        c = time.perf_counter()
+        st = R.state(); prev = st["tf"].copy()
+        if i == preroll - 1:
+            kf0 = st["keyframes"]
+        if i >= preroll:
+            t_dk.append((b - a) * 1e3); t_node.append((c - b) * 1e3)
+    R.close()
+    tot = np.array(t_dk) + np.array(t_node)
+    return dict(value=float(np.mean(tot)), unit="ms/frame", cores=threads, kind="reference",
+                sample="%d frames after a %d-frame pre-roll (the frames the GPU window starts with): deskew = oracle port of projectPointCloud (1 thread, as the reference), then the "
+                       "reference's own mapOptimization node (laserCloudInfoHandler, -O3 + OpenMP %d threads; stand-ins behind its PCL / Eigen / OpenCV calls)" % (frames, preroll, threads),
+                ms=stats_ms(list(tot)), split_ms=dict(deskew=float(np.mean(t_dk)), map_optimization_node=float(np.mean(t_node))), keyframes_added=int(st["keyframes"] - kf0),
+                final_pose=[float(v) for v in prev])
 
 
 # ----------------------------------------------------------------------------------------------------------------
