@@ -736,6 +736,13 @@ def bench_single_headline(args, device, W, K, peaks, peak_src):
                     r = scb.run(q, 12 if q <= 32768 else 4, 3)
                     sc["sweep"][str(q)] = {k: r[k] for k in ("Q", "ms_per_batch", "queries_per_s", "batches_in_flight", "planted_loops_found", "planted")}
                 sc["e2e"] = scb.run_e2e(args.sc_q, 6)
+                try:                                                # config 5's CPU figure (bounded: 3 steps of 256 queries)
+                    if ORACLE_DIR not in sys.path:
+                        sys.path.insert(0, ORACLE_DIR)
+                    import pyoracle as o
+                    sc["cpu_baseline"] = sc_cpu_reference(o, args.sc_k, args.sc_q, 256, 3, 1, os.cpu_count() or 1)[0]
+                except Exception as e:
+                    sc["cpu_baseline"] = dict(error=repr(e))
                 sc["metric"] = "sc_queries_per_s_100k"
                 line["sc"] = sc
                 line["sc_queries_per_s_100k"] = sc["queries_per_s"]
@@ -878,6 +885,53 @@ def sc_config(args):
                 K=args.sc_k, Q=args.sc_q, l2="inputs larger than L2: a batch reads 315 MB of query descriptors and ~0.9 GB of candidate descriptors")
 
 
+def sc_cpu_reference(o, Kdb, sc_q, Qc, steps, warm, all_cores):
+    """config 5 on the host cores: Qc of a batch's sc_q queries per step against the same Kdb-entry database — every query through the reference's own
+    SCManager::detectLoopClosureID when oracle/_ref holds it (kind "reference", one thread), else the OpenMP port.  Returns (cpu_baseline dict, ms per step, steps)."""
+    from tools import synth
+    db = np.concatenate([synth.sc_descriptors(min(10000, Kdb - s), first=s) for s in range(0, Kdb, 10000)])
+    n_src = min(Kdb, 2000)
+    src_rows = (np.arange(n_src, dtype=np.int64) * Kdb) // n_src
+    qd, src, shift = synth.sc_queries(db[src_rows], sc_q)
+    qd = qd[:Qc]
+    use_ref = o.ref() is not None
+    node = None
+    try:
+        if o.refsc() is not None:
+            node = o.RefSCManager()                                 # the reference's own SCManager (include/Scancontext.cpp compiled unchanged)
+            node.save_descriptors(db)                               # makeAndSaveScancontextAndKeys' bookkeeping on ready descriptors (:236-250)
+    except Exception as e:
+        print("[bench] reference SCManager unavailable (%r): falling back to the oracle port" % (e,), file=sys.stderr)
+        node = None
+    if node is None:
+        keys = o.sc_keys_batch(db); qk = o.sc_keys_batch(qd)
+    ts, tree_s = [], []
+    for i in range(warm + steps):
+        a = time.perf_counter()
+        if node is not None:
+            loop, sh = node.query_batch(qd); tb = 0.0               # every query through detectLoopClosureID (:253-344), unchanged; the tree is built in the batch's first call
+        elif use_ref:
+            loop, sh, dd, cand, (tb, tq) = o.ref_sc_query_batch(keys, db, qk, qd)
+        else:
+            loop, sh, dd, cand = o.sc_query_batch(keys, db, qk, qd); tb = 0.0
+        dt = time.perf_counter() - a
+        if i >= warm:
+            ts.append(dt); tree_s.append(tb)
+    v = Qc / float(np.median(ts))
+    planted = src[:Qc] >= 0
+    found = int(np.sum(loop[planted] == src_rows[src[:Qc][planted]]))
+    if node is not None:
+        kind, cores = "reference", 1
+        sample = ("%d of the batch's %d queries per step, %d steps: every query through the reference's own SCManager::detectLoopClosureID (include/Scancontext.cpp compiled unchanged, "
+                  "oracle/_ref/libliorf_ref_sc.so; Eigen = header stand-in with sequential reductions) against all %d keys — kd-tree (the reference's vendored nanoflann) built in the "
+                  "step's first call, then 3 x distanceBtnScanContext per query; single-threaded as the reference's loop-closure thread is" % (Qc, sc_q, steps, Kdb))
+    else:
+        kind, cores = "port", all_cores
+        sample = ("%d of the batch's %d queries per step, %d steps: %s over all %d keys built once per step (%.1f ms of a step) + distanceBtnScanContext of the 3 candidates, OpenMP over the queries"
+                  % (Qc, sc_q, steps, "the reference's vendored nanoflann kd-tree" if use_ref else "brute-force top-3", Kdb, float(np.median(tree_s)) * 1e3))
+    return dict(value=v, unit="queries/s", cores=cores, kind=kind, sample=sample, planted_loops_found=found, planted=int(planted.sum())), float(np.median(ts)) * 1e3, steps
+
+
 def reference_rows(o, inst, kfs, threads, reps=5):
     """CPU figures beside the GPU line's `rows`: extractSurroundingKeyFrames of the 50 keyframes (extractNearby + transformPointCloud with OpenMP + the map VoxelGrid,
     src/mapOptmization.cpp:975-1044) on the reference's node, makeAndSaveScancontextAndKeys of the full scan and detectLoopClosureID on the reference's SCManager"""
@@ -914,52 +968,11 @@ def run_reference(args, W, K, world):
     all_cores = os.cpu_count() or 1
     o.set_num_threads(all_cores)                                  # torchrun exports OMP_NUM_THREADS=1: the baseline uses every host core regardless
     if world > 1 or args.gpus > 1:
-        from tools import synth
-        Kdb, Qc = args.sc_k, 256                                   # bounded: 256 of the batch's queries per step
-        db = np.concatenate([synth.sc_descriptors(min(10000, Kdb - s), first=s) for s in range(0, Kdb, 10000)])
-        keys = o.sc_keys_batch(db)
-        n_src = min(Kdb, 2000)
-        src_rows = (np.arange(n_src, dtype=np.int64) * Kdb) // n_src
-        qd, src, shift = synth.sc_queries(db[src_rows], args.sc_q)
-        qd = qd[:Qc]; qk = o.sc_keys_batch(qd)
-        use_ref = o.ref() is not None
-        node = None
-        try:
-            if o.refsc() is not None:
-                node = o.RefSCManager()                                 # the reference's own SCManager (include/Scancontext.cpp compiled unchanged)
-                node.save_descriptors(db)                               # makeAndSaveScancontextAndKeys' bookkeeping on ready descriptors (:236-250)
-        except Exception as e:
-            print("[bench] reference SCManager unavailable (%r): falling back to the oracle port" % (e,), file=sys.stderr)
-            node = None
-        steps = min(K, 10)
-        ts, tree_s, found = [], [], 0
-        for i in range(min(W, 2) + steps):
-            a = time.perf_counter()
-            if node is not None:
-                loop, sh = node.query_batch(qd); tb = 0.0               # every query through detectLoopClosureID (:253-344), unchanged; the tree is built in the batch's first call
-            elif use_ref:
-                loop, sh, dd, cand, (tb, tq) = o.ref_sc_query_batch(keys, db, qk, qd)
-            else:
-                loop, sh, dd, cand = o.sc_query_batch(keys, db, qk, qd); tb = 0.0
-            dt = time.perf_counter() - a
-            if i >= min(W, 2):
-                ts.append(dt); tree_s.append(tb)
-        v = Qc / float(np.median(ts))
-        planted = src[:Qc] >= 0
-        found = int(np.sum(loop[planted] == src_rows[src[:Qc][planted]]))
-        if node is not None:
-            kind, cores = "reference", 1
-            sample = ("%d of the batch's %d queries per step, %d steps: every query through the reference's own SCManager::detectLoopClosureID (include/Scancontext.cpp compiled unchanged, "
-                      "oracle/_ref/libliorf_ref_sc.so; Eigen = header stand-in with sequential reductions) against all %d keys — kd-tree (the reference's vendored nanoflann) built in the "
-                      "step's first call, then 3 x distanceBtnScanContext per query; single-threaded as the reference's loop-closure thread is" % (Qc, args.sc_q, steps, Kdb))
-        else:
-            kind, cores = "port", all_cores
-            sample = ("%d of the batch's %d queries per step, %d steps: %s over all %d keys built once per step (%.1f ms of a step) + distanceBtnScanContext of the 3 candidates, OpenMP over the queries"
-                      % (Qc, args.sc_q, steps, "the reference's vendored nanoflann kd-tree" if use_ref else "brute-force top-3", Kdb, float(np.median(tree_s)) * 1e3))
-        line = dict(impl="reference", metric="sc_queries_per_s_100k", value=v, unit="queries/s", n_gpus=args.gpus, steps=steps, warmup=W, ms_per_step=float(np.median(ts)) * 1e3,
+        cb, ms_step, steps = sc_cpu_reference(o, args.sc_k, args.sc_q, 256, min(K, 10), min(W, 2), all_cores)
+        v = cb["value"]
+        line = dict(impl="reference", metric="sc_queries_per_s_100k", value=v, unit="queries/s", n_gpus=args.gpus, steps=steps, warmup=W, ms_per_step=ms_step,
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32 ring keys (bf16 split filter + exact re-rank), f64 descriptors", data="synthetic", config=sc_config(args),
-                    cpu_baseline=dict(value=v, unit="queries/s", cores=cores, kind=kind, sample=sample, planted_loops_found=found, planted=int(planted.sum())),
-                    e2e=dict(value=v, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                    cpu_baseline=cb, e2e=dict(value=v, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
     name = "kitti64_single"
