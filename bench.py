@@ -197,22 +197,41 @@ def livox_cpu(L, reps, gpu=None):
     kfs = [o.voxel_grid(s, 0.15)[0] for s in L["kf_scans"]]
     mp, _, _ = o.voxel_grid(np.concatenate([o.transform_cloud(c, p.astype(np.float32)) for c, p in zip(kfs, L["poses"])]), 0.3)
     use_ref = o.ref() is not None
+    node = None
+    try:                                                            # the reference's own mapOptimization member functions where oracle/_ref holds them
+        if o.RefMapOpt.available() and os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libliorf_ref_mapopt_omp.so")):
+            node = o.RefMapOpt(openmp=True, numberOfCores=all_cores, N_SCAN=6, Horizon_SCAN=4000, mappingSurfLeafSize=0.15, surroundingKeyframeMapLeafSize=0.3)
+            node.set_map(mp)
+    except Exception:
+        node = None
     ts, split = [], np.zeros(3)
+    n_ds = iters = 0; tf = None
     for r in range(reps + 1):
         a = time.perf_counter()
         cloud, kept = o.project_point_cloud(L["raw"], LIVOX_FILT, L["t0"], L["imu_time"], L["imu_rot"], L["imu_ptr"], True)
         b = time.perf_counter()
-        ds, _, _ = o.voxel_grid(cloud, 0.15)
-        c = time.perf_counter()
-        res = o.scan2map(ds, mp, L["init"], 30, False, None, use_ref_kdtree=use_ref)
-        d = time.perf_counter()
+        if node is not None:
+            tf, iters, tm = node.bench_step(cloud, L["init"], 30, False)        # downsampleCurrentScan + kd-tree + the loop with the reference's convergence break
+            d = time.perf_counter(); c = b + tm["downsample"] * 1e-3
+            n_ds = node.state()["n_ds"]
+        else:
+            ds, _, _ = o.voxel_grid(cloud, 0.15)
+            c = time.perf_counter()
+            res = o.scan2map(ds, mp, L["init"], 30, False, None, use_ref_kdtree=use_ref)
+            d = time.perf_counter()
+            tf, iters, n_ds = res["tf"], int(res["iters"]), len(ds)
         if r > 0:
             ts.append((d - a) * 1e3); split += np.array([b - a, c - b, d - c]) * 1e3
-    out = dict(value=float(np.median(ts)), unit="ms/frame", cores=all_cores, kind="port",
-               sample="%d repetitions of the same livox_deskew step (after 1 warm-up): oracle restatement of projectPointCloud / deskewPoint, VoxelGrid, scan2MapOptimization (early exit), "
-                      "kd-tree = the reference's vendored nanoflann%s; OpenMP %d threads (the deskew loop is serial in the reference too)" % (reps, "" if use_ref else " (oracle/_ref missing: brute-force kNN)", all_cores),
+    if node is not None:
+        node.close()
+    out = dict(value=float(np.median(ts)), unit="ms/frame", cores=all_cores, kind="reference" if node is not None else "port",
+               sample="%d repetitions of the same livox_deskew step (after 1 warm-up): deskew = oracle port of projectPointCloud / deskewPoint (serial, as the reference), then %s; OpenMP %d threads"
+                      % (reps, "the reference's own downsampleCurrentScan + scan2MapOptimization loop (src/mapOptmization.cpp compiled unchanged, -O3 + OpenMP; stand-ins behind its third-party calls)"
+                         if node is not None else "the oracle's VoxelGrid + scan2MapOptimization (early exit), kd-tree = the reference's vendored nanoflann%s" % ("" if use_ref else " (oracle/_ref missing: brute-force kNN)"), all_cores),
                ms=stats_ms(ts), split_ms=dict(deskew=split[0] / reps, downsample=split[1] / reps, scan2map=split[2] / reps),
-               n_kept=int(len(kept)), n_ds=int(len(ds)), m_map=int(len(mp)), lm_iters=int(res["iters"]))
+               n_kept=int(len(kept)), n_ds=int(n_ds), m_map=int(len(mp)), lm_iters=int(iters))
+    res = dict(tf=tf, iters=iters)
+    ds = np.zeros((n_ds, 4), np.float32)
     if gpu is not None:
         pose, cnt, m = gpu
         out["gpu_vs_cpu"] = dict(final_pose_max_abs_diff=float(np.max(np.abs(np.asarray(pose, np.float64) - res["tf"].astype(np.float64)))),
