@@ -230,13 +230,11 @@ def livox_cpu(L, reps, gpu=None):
                          if node is not None else "the oracle's VoxelGrid + scan2MapOptimization (early exit), kd-tree = the reference's vendored nanoflann%s" % ("" if use_ref else " (oracle/_ref missing: brute-force kNN)"), all_cores),
                ms=stats_ms(ts), split_ms=dict(deskew=split[0] / reps, downsample=split[1] / reps, scan2map=split[2] / reps),
                n_kept=int(len(kept)), n_ds=int(n_ds), m_map=int(len(mp)), lm_iters=int(iters))
-    res = dict(tf=tf, iters=iters)
-    ds = np.zeros((n_ds, 4), np.float32)
     if gpu is not None:
         pose, cnt, m = gpu
-        out["gpu_vs_cpu"] = dict(final_pose_max_abs_diff=float(np.max(np.abs(np.asarray(pose, np.float64) - res["tf"].astype(np.float64)))),
-                                 same_n_kept=bool(cnt["n_scan"] == len(kept)), same_n_ds=bool(cnt["n_ds"] == len(ds)), same_m_map=bool(m == len(mp)),
-                                 same_lm_iters=bool(cnt["iters"] == int(res["iters"])))
+        out["gpu_vs_cpu"] = dict(final_pose_max_abs_diff=float(np.max(np.abs(np.asarray(pose, np.float64) - np.asarray(tf, np.float64)))),
+                                 same_n_kept=bool(cnt["n_scan"] == len(kept)), same_n_ds=bool(cnt["n_ds"] == n_ds), same_m_map=bool(m == len(mp)),
+                                 same_lm_iters=bool(cnt["iters"] == int(iters)))
     return out
 
 
